@@ -1,0 +1,115 @@
+/*
+ * peppan_b200.h -- C ABI of libpeppan_b200.so (CUDA, sm_100a).
+ *
+ * Drop-in boundary for the similarity-search / clustering hot path of PEPPAN
+ * (zheminzhou/PEPPAN).  Every entry point replaces work that the reference hands to an external
+ * process; the reference-side call site is cited on each declaration (paths relative to the
+ * reference checkout).  Plain C types only: caller-owned host buffers (numpy arrays through
+ * ctypes), sizes, and opaque handles.  No function aborts or throws across the boundary: each
+ * returns 0 (PB_OK) or a negative pb_status, with a message available from pb_last_error().
+ *
+ * Sequences cross the boundary as "seqsets": one uint8 array of residue codes (or ASCII for
+ * nucleotides, see each call) with an int64 offsets array of n+1 entries.
+ */
+#ifndef PEPPAN_B200_H
+#define PEPPAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+typedef enum {
+    PB_OK = 0,
+    PB_ERR_CUDA = -1,        /* a CUDA runtime call failed (message has the CUDA error string) */
+    PB_ERR_ARG = -2,         /* invalid argument */
+    PB_ERR_NOMEM = -3,       /* host or device allocation failed */
+    PB_ERR_NCCL = -4,        /* NCCL unavailable or a collective failed */
+    PB_ERR_LIMIT = -5,       /* an internal capacity limit was exceeded */
+    PB_ERR_NODEVICE = -6     /* no CUDA device: there is NO CPU fallback */
+} pb_status;
+
+/* Substitution scores + affine gap costs.  A gap of length L costs gap_open + L*gap_extend
+ * (BLAST convention).  matrix[a*32+b] for residue codes a,b < nsym-1; code nsym-1 is reserved as
+ * the padding symbol and must not occur in sequences.
+ *   protein: BLOSUM62, 11/1  -- DIAMOND defaults used at modules/uberBlast.py:550
+ *   nucleotide: +2/-3, 6/2   -- blastn flags at modules/uberBlast.py:294 */
+typedef struct {
+    int8_t  matrix[1024];
+    int32_t nsym;            /* number of symbols INCLUDING the trailing pad symbol (<= 32) */
+    int32_t gap_open;
+    int32_t gap_extend;
+} pb_score_params;
+
+/* Per-call statistics (device times from CUDA events on the library's stream). */
+typedef struct {
+    double  cells;           /* DP cells of the forward pass (sum of m*n) */
+    double  cells_reverse;   /* DP cells actually swept by the reverse (start-finding) pass */
+    float   ms_h2d, ms_forward, ms_reverse, ms_traceback, ms_d2h, ms_total_device;
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t kernel_launches; /* number of this library's kernels launched by the call */
+    int32_t n_s32_pairs;     /* pairs routed to the 32-bit kernel (score could exceed int16) */
+} pb_sw_stats;
+
+/* ---- context -------------------------------------------------------------------------- */
+/* One context per (process, GPU).  world > 1 enables pb_allgather_hits over NCCL; nccl_uid is
+ * the 128-byte ncclUniqueId produced by pb_nccl_unique_id() on rank 0 and distributed by the
+ * caller.  Replaces: process/thread pools of RunBlast.run (modules/uberBlast.py:333-338) and the
+ * per-genome worker fan-out (PEPPAN.py:922). */
+int  pb_init(int device, int rank, int world, const void* nccl_uid, pb_ctx** out);
+void pb_destroy(pb_ctx* ctx);
+const char* pb_last_error(pb_ctx* ctx);      /* ctx may be NULL: returns the last global error */
+int  pb_nccl_unique_id(void* uid128);
+int  pb_device_info(pb_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int64_t* hbm_bytes);
+
+/* ---- batched Smith-Waterman (gapped extension) --------------------------------------- */
+/* Replaces the gapped-extension + traceback arithmetic inside blastn (modules/uberBlast.py:294-296)
+ * and diamond blastp (:550-552).  For every pair p: local affine alignment of
+ * q[qoff[p]:qoff[p+1]] against t[toff[p]:toff[p+1]] (residue codes).  Outputs (caller-allocated,
+ * length npairs, any of qs/qe/ts/te may be NULL to skip the start-finding pass):
+ *   score; qs,qe,ts,te = 0-based inclusive coordinates, -1 when score == 0.
+ * Tie-breaks are those of oracle/pb_oracle.c (row-major-first end, row-major-first start of the
+ * reverse DP) and the results are bit-exact against it. */
+int pb_sw_batch(pb_ctx* ctx,
+                const uint8_t* q, const int64_t* qoff,
+                const uint8_t* t, const int64_t* toff, int64_t npairs,
+                const pb_score_params* params,
+                int32_t* score, int32_t* qs, int32_t* qe, int32_t* ts, int32_t* te,
+                pb_sw_stats* stats /* nullable */);
+
+/* Same, plus traceback.  cigar ops are (len<<2)|{0:M,1:I,2:D} (I consumes query, D consumes
+ * target: the convention of getCIGAR, modules/uberBlast.py:311-320).  Ops of pair p are
+ * (*cigar_ops)[cigar_off[p] : cigar_off[p+1]]; cigar_off is caller-allocated (npairs+1);
+ * *cigar_ops is library-allocated and released with pb_free().  counts (nullable,
+ * caller-allocated npairs*4 int32): n_match, n_mismatch, n_gap_runs, n_gap_bases. */
+int pb_sw_align_batch(pb_ctx* ctx,
+                      const uint8_t* q, const int64_t* qoff,
+                      const uint8_t* t, const int64_t* toff, int64_t npairs,
+                      const pb_score_params* params,
+                      int32_t* score, int32_t* qs, int32_t* qe, int32_t* ts, int32_t* te,
+                      int32_t* counts, int64_t* cigar_off, uint32_t** cigar_ops,
+                      pb_sw_stats* stats);
+
+/* Device-resident variant used to time the kernels alone (inputs already in HBM). */
+typedef struct pb_sw_job pb_sw_job;
+int  pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff,
+                      const uint8_t* t, const int64_t* toff, int64_t npairs,
+                      const pb_score_params* params, int want_coords, pb_sw_job** job);
+int  pb_sw_job_run(pb_ctx* ctx, pb_sw_job* job, pb_sw_stats* stats);      /* kernels only */
+int  pb_sw_job_fetch(pb_ctx* ctx, pb_sw_job* job, int32_t* score, int32_t* qs, int32_t* qe,
+                     int32_t* ts, int32_t* te);
+void pb_sw_job_destroy(pb_ctx* ctx, pb_sw_job* job);
+
+/* Measures the issue rate of dependent-free DPX chains on all SMs (lane-ops/s): the roofline
+ * denominator of the extension kernels.  which: 0 = viaddmax_s16x2, 1 = s32. */
+int pb_measure_dpx_peak(pb_ctx* ctx, int which, double* lane_ops_per_s);
+
+void pb_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,53 @@
+// Internal shared declarations of libpeppan_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/peppan_b200.h"
+
+struct pb_ctx {
+    int device = 0, rank = 0, world = 1;
+    int sm_count = 0, clock_khz = 0;
+    size_t smem_optin = 0;
+    int64_t hbm_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    void* nccl_comm = nullptr;      // ncclComm_t when world > 1
+    void* nccl_dl = nullptr;        // dlopen handle of libnccl
+    int* d_counter = nullptr;       // small scratch of task counters (64 ints)
+};
+
+void pb_set_error(pb_ctx* ctx, const char* fmt, ...);
+
+#define PB_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            pb_set_error((ctx), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
+                         cudaGetErrorString(e_));                                                 \
+            return PB_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+// RAII device buffer: freed on scope exit so error paths do not leak.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t n) {
+        release();
+        bytes = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&p, n);
+    }
+    void release() { if (p) { cudaFree(p); p = nullptr; } bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};

@@ -1,0 +1,132 @@
+// Context management, error reporting and NCCL plumbing of libpeppan_b200.
+#include "pb_common.h"
+#include <cstdarg>
+#include <dlfcn.h>
+#include <mutex>
+
+static std::string g_last_error;
+static std::mutex g_err_mutex;
+
+void pb_set_error(pb_ctx* ctx, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_error = buf;
+}
+
+extern "C" const char* pb_last_error(pb_ctx* ctx)
+{
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_last_error;
+    return copy.c_str();
+}
+
+// ---- NCCL through dlopen: the library has no link-time dependency on NCCL, single-GPU users never
+// load it, and inside a process that already loaded libnccl.so.2 (e.g. via torch.distributed) the
+// same copy is reused.
+typedef struct { char internal[128]; } pb_nccl_uid;
+typedef int (*nccl_get_uid_fn)(pb_nccl_uid*);
+typedef int (*nccl_init_rank_fn)(void** comm, int nranks, pb_nccl_uid id, int rank);
+typedef int (*nccl_destroy_fn)(void* comm);
+typedef const char* (*nccl_errstr_fn)(int);
+
+static void* open_nccl()
+{
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i]; ++i) {
+        void* h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (h) return h;
+    }
+    return nullptr;
+}
+
+extern "C" int pb_nccl_unique_id(void* uid128)
+{
+    if (!uid128) return PB_ERR_ARG;
+    void* h = open_nccl();
+    if (!h) { pb_set_error(nullptr, "libnccl.so.2 not found: %s", dlerror()); return PB_ERR_NCCL; }
+    auto f = (nccl_get_uid_fn)dlsym(h, "ncclGetUniqueId");
+    if (!f) { pb_set_error(nullptr, "ncclGetUniqueId missing"); return PB_ERR_NCCL; }
+    int rc = f((pb_nccl_uid*)uid128);
+    if (rc != 0) { pb_set_error(nullptr, "ncclGetUniqueId failed (%d)", rc); return PB_ERR_NCCL; }
+    return PB_OK;
+}
+
+extern "C" int pb_init(int device, int rank, int world, const void* nccl_uid, pb_ctx** out)
+{
+    if (!out || world < 1 || rank < 0 || rank >= world) { pb_set_error(nullptr, "pb_init: invalid argument"); return PB_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        pb_set_error(nullptr, "pb_init: no CUDA device available (%s); libpeppan_b200 has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return PB_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) { pb_set_error(nullptr, "pb_init: device %d out of range (%d devices)", device, ndev); return PB_ERR_ARG; }
+    pb_ctx* ctx = new (std::nothrow) pb_ctx();
+    if (!ctx) return PB_ERR_NOMEM;
+    ctx->device = device; ctx->rank = rank; ctx->world = world;
+    cudaDeviceProp prop;
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { pb_set_error(nullptr, "pb_init: %s: %s", #call, cudaGetErrorString(e_)); delete ctx; return PB_ERR_CUDA; } } while (0)
+    CK(cudaSetDevice(device));
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        pb_set_error(nullptr, "pb_init: device '%s' is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+        delete ctx; return PB_ERR_NODEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->clock_khz = prop.clockRate;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->hbm_bytes = (int64_t)prop.totalGlobalMem;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
+    CK(cudaMalloc(&ctx->d_counter, 64 * sizeof(int)));
+#undef CK
+    if (world > 1) {
+        if (!nccl_uid) { pb_set_error(nullptr, "pb_init: world > 1 requires an NCCL unique id"); pb_destroy(ctx); return PB_ERR_ARG; }
+        ctx->nccl_dl = open_nccl();
+        if (!ctx->nccl_dl) { pb_set_error(nullptr, "pb_init: libnccl.so.2 not found"); pb_destroy(ctx); return PB_ERR_NCCL; }
+        auto init = (nccl_init_rank_fn)dlsym(ctx->nccl_dl, "ncclCommInitRank");
+        if (!init) { pb_set_error(nullptr, "pb_init: ncclCommInitRank missing"); pb_destroy(ctx); return PB_ERR_NCCL; }
+        pb_nccl_uid id; memcpy(&id, nccl_uid, sizeof(id));
+        int rc = init(&ctx->nccl_comm, world, id, rank);
+        if (rc != 0) {
+            auto es = (nccl_errstr_fn)dlsym(ctx->nccl_dl, "ncclGetErrorString");
+            pb_set_error(nullptr, "pb_init: ncclCommInitRank failed: %s", es ? es(rc) : "?");
+            ctx->nccl_comm = nullptr; pb_destroy(ctx); return PB_ERR_NCCL;
+        }
+    }
+    *out = ctx;
+    return PB_OK;
+}
+
+extern "C" void pb_destroy(pb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm && ctx->nccl_dl) {
+        auto d = (nccl_destroy_fn)dlsym(ctx->nccl_dl, "ncclCommDestroy");
+        if (d) d(ctx->nccl_comm);
+    }
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int pb_device_info(pb_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int64_t* hbm_bytes)
+{
+    if (!ctx) return PB_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (clock_khz) *clock_khz = ctx->clock_khz;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+    return PB_OK;
+}
+
+extern "C" void pb_free(void* p) { free(p); }

@@ -1,0 +1,376 @@
+// Host side of the batched Smith-Waterman path: descriptor preparation and work ordering on the
+// device (no host-side sorting), kernel launches, the job API and pb_sw_batch.
+#include "pb_common.h"
+#include "pb_sw_kernel.cuh"
+#include <cub/cub.cuh>
+#include <climits>
+#include <algorithm>
+#include <memory>
+#include <new>
+
+using namespace pbsw;
+
+namespace {
+
+constexpr int SW_G = 16, SW_K = 19, SW_WARPS = 8;
+constexpr int SW_W = SW_G * SW_K;
+constexpr int PAD_SCORE = -16;
+
+// ---- small device kernels around the DP kernel ------------------------------------------------
+
+// forward descriptors + sort keys.  key (descending sort): [31] needs-s32, [30:20] column blocks,
+// [19:0] query length; longest work first so the dynamic scheduler packs well, and neighbours in
+// the sorted order (which share a task / a warp) have similar shapes.
+__global__ void make_desc_fwd(const int64_t* qoff, const int64_t* toff, int n, int maxscore,
+                              PairDesc* desc, uint32_t* keys, int* ids, int* meta /*[0]=n32,[1]=maxm,[2]=maxnb*/)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    long long qo = qoff[p], to = toff[p];
+    long long m = qoff[p + 1] - qo, nn = toff[p + 1] - to;
+    PairDesc d;
+    d.qoff = qo; d.toff = to; d.m = (int)m; d.n = (int)nn; d.target = INT_MAX; d.flags = 0;
+    long long bound = (m < nn ? m : nn) * (long long)maxscore;
+    int s32 = bound > 32000 ? 1 : 0;
+    int nb = (int)((nn + SW_W - 1) / SW_W);
+    if (m <= 0 || nn <= 0) { nb = 0; s32 = 0; }
+    d.flags = s32;
+    desc[p] = d;
+    keys[p] = ((uint32_t)s32 << 31) | ((uint32_t)min(nb, 2047) << 20) | (uint32_t)min((long long)0xfffff, m);
+    ids[p] = p;
+    if (s32) atomicAdd(&meta[0], 1);
+    if (nb > 1) { atomicMax(&meta[1], (int)m); }
+    atomicMax(&meta[2], nb);
+}
+
+// reverse descriptors: prefixes ending at the forward end cell, looking for the forward score.
+// key: [31] s32, [30:16] column blocks, [15:0] score (alignment length grows with the score, so
+// neighbours terminate their early-exit reverse sweep at similar rows).
+__global__ void make_desc_rev(const PairDesc* fwd, const int* score, const int* qe, const int* te, int n,
+                              PairDesc* desc, uint32_t* keys, int* ids, int* meta)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    PairDesc d = fwd[p];
+    int S = score[p];
+    if (S > 0) { d.m = qe[p] + 1; d.n = te[p] + 1; d.target = S; }
+    else { d.m = 0; d.n = 0; d.target = 0; }
+    int nb = (d.n + SW_W - 1) / SW_W;
+    desc[p] = d;
+    keys[p] = ((uint32_t)(d.flags & 1) << 31) | ((uint32_t)min(nb, 32767) << 16) | (uint32_t)min(S, 65535);
+    ids[p] = p;
+    if (d.flags & 1) atomicAdd(&meta[0], 1);
+    if (nb > 1) atomicMax(&meta[1], d.m);
+    atomicMax(&meta[2], nb);
+}
+
+__global__ void fill_int(int* p, int v, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// dependent-free DPX chains: the issue-rate roofline of the extension kernel
+template <int MODE>
+__global__ void __launch_bounds__(256) dpx_peak_kernel(unsigned* out, unsigned seed, unsigned b, unsigned c, int iters)
+{
+    unsigned x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = seed + threadIdx.x * 7 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (MODE == 0) x[i] = __viaddmax_s16x2(x[i], b, c);
+            else x[i] = (unsigned)__viaddmax_s32((int)x[i], (int)b, (int)c);
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <bool PACKED>
+size_t sw_smem_bytes(int nsym)
+{
+    constexpr int KP = ((SW_K + 3) / 4) * 4;
+    constexpr int NG = 32 / SW_G;
+    return 1024 + (size_t)SW_WARPS * NG * (PACKED ? 2 : 1) * nsym * SW_G * KP;
+}
+
+}  // namespace
+
+// ---- job ------------------------------------------------------------------------------------
+
+struct pb_sw_job {
+    int64_t npairs = 0;
+    int want_coords = 0;
+    pb_score_params params;
+    int maxscore = 1;
+    DevBuf q, t, qoff, toff, matrix;
+    DevBuf desc, desc_rev, keys, keys_sorted, ids, perm, perm_rev, meta, cub_tmp;
+    DevBuf score, qe, te, qs, ts, dump, boundary, cells;
+    size_t cub_bytes = 0;
+    int64_t qbytes = 0, tbytes = 0;
+    double fwd_cells = 0;
+};
+
+static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, const int* perm,
+                     int n32, int* launches)
+{
+    const int n = (int)J->npairs;
+    // boundary buffer sized from the device-side maxima
+    int meta[3];
+    PB_CUDA(ctx, cudaMemcpyAsync(meta, J->meta.p, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    n32 = meta[0];
+    int bstride = meta[2] > 1 ? ((meta[1] + 63) / 64) * 64 : 0;
+    const int grid = ctx->sm_count;
+    if (bstride > 0) {
+        size_t need = (size_t)grid * SW_WARPS * (32 / SW_G) * bstride * sizeof(uint2);
+        if (J->boundary.bytes < need) PB_CUDA(ctx, J->boundary.alloc(need));
+    }
+    SwArgs a;
+    a.q = J->q.as<uint8_t>(); a.t = J->t.as<uint8_t>();
+    a.desc = desc; a.perm = perm;
+    a.matrix = J->matrix.as<int8_t>(); a.nsym = J->params.nsym;
+    a.go = J->params.gap_open; a.ge = J->params.gap_extend;
+    a.dump = J->dump.as<uint32_t>(); a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride;
+    a.out_score = J->score.as<int>();
+    a.out_a = rev ? J->qs.as<int>() : J->qe.as<int>();
+    a.out_b = rev ? J->ts.as<int>() : J->te.as<int>();
+    a.cells = rev ? J->cells.as<unsigned long long>() : nullptr;
+    PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
+
+    size_t smem16 = sw_smem_bytes<true>(J->params.nsym), smem32 = sw_smem_bytes<false>(J->params.nsym);
+    if (smem16 > ctx->smem_optin) { pb_set_error(ctx, "nsym=%d needs %zu B shared memory (> %zu)", J->params.nsym, smem16, ctx->smem_optin); return PB_ERR_LIMIT; }
+    // s32 pairs sort first (key bit 31)
+    if (n32 > 0) {
+        a.first = 0; a.count = n32; a.counter = ctx->d_counter + (rev ? 2 : 0);
+        if (!rev) {
+            auto k = sw_kernel<SW_G, SW_K, false, false, SW_WARPS>;
+            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            k<<<grid, SW_WARPS * 32, smem32, ctx->stream>>>(a);
+        } else {
+            auto k = sw_kernel<SW_G, SW_K, false, true, SW_WARPS>;
+            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            k<<<grid, SW_WARPS * 32, smem32, ctx->stream>>>(a);
+        }
+        PB_CUDA(ctx, cudaGetLastError());
+        ++*launches;
+    }
+    if (n - n32 > 0) {
+        a.first = n32; a.count = n - n32; a.counter = ctx->d_counter + (rev ? 3 : 1);
+        if (!rev) {
+            auto k = sw_kernel<SW_G, SW_K, true, false, SW_WARPS>;
+            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            k<<<grid, SW_WARPS * 32, smem16, ctx->stream>>>(a);
+        } else {
+            auto k = sw_kernel<SW_G, SW_K, true, true, SW_WARPS>;
+            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            k<<<grid, SW_WARPS * 32, smem16, ctx->stream>>>(a);
+        }
+        PB_CUDA(ctx, cudaGetLastError());
+        ++*launches;
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t,
+                                const int64_t* toff, int64_t npairs, const pb_score_params* params,
+                                int want_coords, pb_sw_job** job)
+{
+    if (!ctx || !job || !params || npairs < 0 || (npairs > 0 && (!q || !qoff || !t || !toff))) {
+        pb_set_error(ctx, "pb_sw_job_create: invalid argument"); return PB_ERR_ARG;
+    }
+    if (npairs > INT_MAX / 2) { pb_set_error(ctx, "pb_sw_job_create: too many pairs in one batch"); return PB_ERR_LIMIT; }
+    if (params->nsym < 2 || params->nsym > 32 || params->gap_open < 0 || params->gap_extend <= 0 ||
+        params->gap_open + params->gap_extend > 255) {
+        pb_set_error(ctx, "pb_sw_job_create: bad scoring parameters"); return PB_ERR_ARG;
+    }
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_sw_job* J = new (std::nothrow) pb_sw_job();
+    if (!J) { pb_set_error(ctx, "out of host memory"); return PB_ERR_NOMEM; }
+    std::unique_ptr<pb_sw_job> guard(J);
+    J->npairs = npairs; J->want_coords = want_coords; J->params = *params;
+    const int n = (int)npairs;
+    J->qbytes = npairs ? qoff[npairs] : 0; J->tbytes = npairs ? toff[npairs] : 0;
+    // matrix with the pad symbol's row/column forced negative
+    int8_t mat[1024]; memcpy(mat, params->matrix, 1024);
+    const int pad = params->nsym - 1;
+    int maxscore = 1;
+    for (int a = 0; a < 32; ++a) for (int b = 0; b < 32; ++b) {
+        if (a == pad || b == pad || a >= params->nsym || b >= params->nsym) mat[a * 32 + b] = PAD_SCORE;
+        else maxscore = std::max(maxscore, (int)mat[a * 32 + b]);
+    }
+    J->maxscore = maxscore;
+    PB_CUDA(ctx, J->matrix.alloc(1024));
+    PB_CUDA(ctx, cudaMemcpyAsync(J->matrix.p, mat, 1024, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, J->q.alloc(std::max<int64_t>(J->qbytes, 16)));
+    PB_CUDA(ctx, J->t.alloc(std::max<int64_t>(J->tbytes, 16)));
+    PB_CUDA(ctx, J->qoff.alloc((npairs + 1) * 8));
+    PB_CUDA(ctx, J->toff.alloc((npairs + 1) * 8));
+    if (npairs) {
+        PB_CUDA(ctx, cudaMemcpyAsync(J->q.p, q, J->qbytes, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->t.p, t, J->tbytes, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->qoff.p, qoff, (npairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->toff.p, toff, (npairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    size_t nn = std::max(n, 1);
+    PB_CUDA(ctx, J->desc.alloc(nn * sizeof(PairDesc)));
+    PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc)));
+    PB_CUDA(ctx, J->keys.alloc(nn * 4)); PB_CUDA(ctx, J->keys_sorted.alloc(nn * 4));
+    PB_CUDA(ctx, J->ids.alloc(nn * 4)); PB_CUDA(ctx, J->perm.alloc(nn * 4)); PB_CUDA(ctx, J->perm_rev.alloc(nn * 4));
+    PB_CUDA(ctx, J->meta.alloc(16));
+    PB_CUDA(ctx, J->score.alloc(nn * 4)); PB_CUDA(ctx, J->qe.alloc(nn * 4)); PB_CUDA(ctx, J->te.alloc(nn * 4));
+    PB_CUDA(ctx, J->qs.alloc(nn * 4)); PB_CUDA(ctx, J->ts.alloc(nn * 4));
+    PB_CUDA(ctx, J->cells.alloc(8));
+    constexpr int KP = ((SW_K + 3) / 4) * 4;
+    PB_CUDA(ctx, J->dump.alloc((size_t)ctx->sm_count * SW_WARPS * 32 * 2 * KP * 4));
+    size_t tmp = 0;
+    PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
+                                                            J->ids.as<int>(), J->perm.as<int>(), n, 0, 32, ctx->stream));
+    J->cub_bytes = tmp;
+    PB_CUDA(ctx, J->cub_tmp.alloc(std::max<size_t>(tmp, 16)));
+    double cells = 0;
+    for (int64_t p = 0; p < npairs; ++p) cells += (double)(qoff[p + 1] - qoff[p]) * (double)(toff[p + 1] - toff[p]);
+    J->fwd_cells = cells;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *job = guard.release();
+    return PB_OK;
+}
+
+extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
+{
+    if (!ctx || !J) { pb_set_error(ctx, "pb_sw_job_run: invalid argument"); return PB_ERR_ARG; }
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = (int)J->npairs;
+    int launches = 0;
+    float ms_f = 0, ms_r = 0;
+    if (n > 0) {
+        const int tb = 256, gb = (n + tb - 1) / tb;
+        PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 16, ctx->stream));
+        make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(J->qoff.as<int64_t>(), J->toff.as<int64_t>(), n, J->maxscore,
+                                                  J->desc.as<PairDesc>(), J->keys.as<uint32_t>(), J->ids.as<int>(), J->meta.as<int>());
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        size_t tmp = J->cub_bytes;
+        PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(J->cub_tmp.p, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
+                                                                J->ids.as<int>(), J->perm.as<int>(), n, 0, 32, ctx->stream));
+        int rc = sw_launch(ctx, J, false, J->desc.as<PairDesc>(), J->perm.as<int>(), 0, &launches);
+        if (rc) return rc;
+        PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (J->want_coords) {
+            PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 16, ctx->stream));
+            PB_CUDA(ctx, cudaMemsetAsync(J->cells.p, 0, 8, ctx->stream));
+            fill_int<<<gb, tb, 0, ctx->stream>>>(J->qs.as<int>(), -1, n);
+            fill_int<<<gb, tb, 0, ctx->stream>>>(J->ts.as<int>(), -1, n);
+            launches += 2;
+            make_desc_rev<<<gb, tb, 0, ctx->stream>>>(J->desc.as<PairDesc>(), J->score.as<int>(), J->qe.as<int>(), J->te.as<int>(), n,
+                                                      J->desc_rev.as<PairDesc>(), J->keys.as<uint32_t>(), J->ids.as<int>(), J->meta.as<int>());
+            PB_CUDA(ctx, cudaGetLastError()); ++launches;
+            tmp = J->cub_bytes;
+            PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(J->cub_tmp.p, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
+                                                                    J->ids.as<int>(), J->perm_rev.as<int>(), n, 0, 32, ctx->stream));
+            rc = sw_launch(ctx, J, true, J->desc_rev.as<PairDesc>(), J->perm_rev.as<int>(), 0, &launches);
+            if (rc) return rc;
+        }
+        PB_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->ev[2]));
+        PB_CUDA(ctx, cudaEventElapsedTime(&ms_f, ctx->ev[0], ctx->ev[1]));
+        PB_CUDA(ctx, cudaEventElapsedTime(&ms_r, ctx->ev[1], ctx->ev[2]));
+    }
+    if (stats) {
+        stats->cells = J->fwd_cells;
+        unsigned long long rc = 0;
+        if (n > 0 && J->want_coords) PB_CUDA(ctx, cudaMemcpy(&rc, J->cells.p, 8, cudaMemcpyDeviceToHost));
+        stats->cells_reverse = (double)rc;
+        stats->ms_forward = ms_f; stats->ms_reverse = ms_r; stats->ms_traceback = 0;
+        stats->ms_total_device = ms_f + ms_r;
+        stats->kernel_launches = launches;
+        int meta0 = 0;
+        stats->n_s32_pairs = meta0;
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_sw_job_fetch(pb_ctx* ctx, pb_sw_job* J, int32_t* score, int32_t* qs, int32_t* qe, int32_t* ts, int32_t* te)
+{
+    if (!ctx || !J) { pb_set_error(ctx, "pb_sw_job_fetch: invalid argument"); return PB_ERR_ARG; }
+    size_t b = (size_t)J->npairs * 4;
+    if (b == 0) return PB_OK;
+    if (score) PB_CUDA(ctx, cudaMemcpyAsync(score, J->score.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (qe) PB_CUDA(ctx, cudaMemcpyAsync(qe, J->qe.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (te) PB_CUDA(ctx, cudaMemcpyAsync(te, J->te.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (J->want_coords) {
+        if (qs) PB_CUDA(ctx, cudaMemcpyAsync(qs, J->qs.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ts) PB_CUDA(ctx, cudaMemcpyAsync(ts, J->ts.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (J->want_coords && qs) {
+        for (int64_t p = 0; p < J->npairs; ++p)
+            if (qs[p] == -2) { pb_set_error(ctx, "internal: reverse pass did not reproduce the forward score for pair %lld", (long long)p); return PB_ERR_LIMIT; }
+    }
+    return PB_OK;
+}
+
+extern "C" void pb_sw_job_destroy(pb_ctx* ctx, pb_sw_job* job)
+{
+    (void)ctx;
+    delete job;
+}
+
+extern "C" int pb_sw_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t, const int64_t* toff,
+                           int64_t npairs, const pb_score_params* params, int32_t* score, int32_t* qs, int32_t* qe,
+                           int32_t* ts, int32_t* te, pb_sw_stats* stats)
+{
+    if (!ctx) return PB_ERR_ARG;
+    if (!score) { pb_set_error(ctx, "pb_sw_batch: score output is required"); return PB_ERR_ARG; }
+    pb_sw_job* J = nullptr;
+    const int want = (qs || ts) ? 1 : 0;
+    cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
+    PB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    int rc = pb_sw_job_create(ctx, q, qoff, t, toff, npairs, params, want, &J);
+    if (rc) return rc;
+    PB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    pb_sw_stats st; memset(&st, 0, sizeof(st));
+    rc = pb_sw_job_run(ctx, J, &st);
+    if (rc) { pb_sw_job_destroy(ctx, J); return rc; }
+    PB_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
+    rc = pb_sw_job_fetch(ctx, J, score, qs, qe, ts, te);
+    if (rc) { pb_sw_job_destroy(ctx, J); return rc; }
+    PB_CUDA(ctx, cudaEventRecord(e3, ctx->stream));
+    PB_CUDA(ctx, cudaEventSynchronize(e3));
+    if (stats) {
+        *stats = st;
+        cudaEventElapsedTime(&stats->ms_h2d, e0, e1);
+        cudaEventElapsedTime(&stats->ms_d2h, e2, e3);
+        stats->h2d_bytes = J->qbytes + J->tbytes + 16 * (npairs + 1) + 1024;
+        int nout = 1 + (qe ? 1 : 0) + (te ? 1 : 0) + (want ? ((qs ? 1 : 0) + (ts ? 1 : 0)) : 0);
+        stats->d2h_bytes = (int64_t)nout * 4 * npairs;
+    }
+    pb_sw_job_destroy(ctx, J);
+    return PB_OK;
+}
+
+extern "C" int pb_measure_dpx_peak(pb_ctx* ctx, int which, double* lane_ops_per_s)
+{
+    if (!ctx || !lane_ops_per_s) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, iters = 4096;
+    DevBuf out;
+    PB_CUDA(ctx, out.alloc((size_t)blocks * 256 * 4));
+    float best = 1e30f;
+    for (int r = 0; r < 8; ++r) {
+        PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        if (which == 0) dpx_peak_kernel<0><<<blocks, 256, 0, ctx->stream>>>(out.as<unsigned>(), 1234u, 0x00010001u, 0x00050003u, iters);
+        else dpx_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(out.as<unsigned>(), 1234u, 0x00010001u, 0x00050003u, iters);
+        PB_CUDA(ctx, cudaGetLastError());
+        PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+        float ms; PB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        if (r >= 3 && ms < best) best = ms;
+    }
+    *lane_ops_per_s = (double)blocks * 256 * iters * 8 / (best * 1e-3);
+    return PB_OK;
+}

@@ -1,0 +1,82 @@
+"""Synthetic workloads named in BASELINE.json `configs`.  Shared by bench.py and
+the parity tests so both see identical inputs.  Pure numpy; nothing here is on the product path."""
+import numpy as np
+
+SEED = 20200103
+
+
+def sw_microbench_pairs(npairs, length=300, seed=SEED, chunk=65536):
+    """Config 2: `npairs` protein pairs of `length` residues (codes 0..19).
+    Queries i.i.d. uniform.  Even pairs: target = mutated copy of the query (per-pair identity
+    U[0.4,1.0], substitutions uniform over the other 19 residues, ~1 % indel events with
+    geometric length of mean 2, trimmed / padded with random residues to `length`).  Odd pairs:
+    independent random target.  Returns (q, qoff, t, toff) as flat uint8 + int64 offsets."""
+    rng = np.random.default_rng(seed)
+    q = np.empty((npairs, length), dtype=np.uint8)
+    t = np.empty((npairs, length), dtype=np.uint8)
+    for c0 in range(0, npairs, chunk):
+        n = min(chunk, npairs - c0)
+        qq = rng.integers(0, 20, size=(n, length), dtype=np.uint8)
+        rnd = rng.integers(0, 20, size=(n, length), dtype=np.uint8)
+        iden = rng.uniform(0.4, 1.0, size=(n, 1))
+        # substitutions: add 1..19 modulo 20 -> uniform over the other residues
+        sub = rng.random((n, length)) >= iden
+        mut = np.where(sub, (qq + rng.integers(1, 20, size=(n, length), dtype=np.uint8)) % 20, qq).astype(np.uint8)
+        # indel events
+        ev = rng.random((n, length)) < 0.01
+        ln = rng.geometric(0.5, size=(n, length)).astype(np.int32)
+        is_del = rng.random((n, length)) < 0.5
+        delta = np.zeros((n, length + 1), dtype=np.int32)      # shift of the source index
+        rmask = np.zeros((n, length + 1), dtype=np.int32)      # >0 inside inserted segments
+        pi, pk = np.nonzero(ev)
+        L = ln[pi, pk]
+        d = is_del[pi, pk]
+        np.add.at(delta, (pi[d], pk[d]), L[d])                                  # deletion: skip L source residues
+        ins_end = np.minimum(pk[~d] + L[~d], length)
+        np.add.at(delta, (pi[~d], ins_end), -(ins_end - pk[~d]))                # insertion: source falls behind
+        np.add.at(rmask, (pi[~d], pk[~d]), 1)
+        np.add.at(rmask, (pi[~d], ins_end), -1)
+        shift = np.cumsum(delta[:, :length], axis=1)
+        inside = np.cumsum(rmask[:, :length], axis=1) > 0
+        src = np.arange(length, dtype=np.int32)[None, :] + shift
+        ok = (src >= 0) & (src < length) & ~inside
+        tt = np.where(ok, np.take_along_axis(mut, np.clip(src, 0, length - 1), axis=1), rnd).astype(np.uint8)
+        odd = ((np.arange(c0, c0 + n) & 1) == 1)
+        tt[odd] = rnd[odd]
+        q[c0:c0 + n] = qq
+        t[c0:c0 + n] = tt
+    off = np.arange(npairs + 1, dtype=np.int64) * length
+    return q.reshape(-1), off, t.reshape(-1), off.copy()
+
+
+def random_pairs(npairs, seed, nsym_real=20, min_len=1, max_len=400, related=0.5):
+    """Ragged random pairs for parity tests: a fraction `related` of targets derive from the query
+    by substitution / insertion / deletion; lengths uniform in [min_len, max_len]."""
+    rng = np.random.default_rng(seed)
+    qs, ts = [], []
+    for p in range(npairs):
+        m = int(rng.integers(min_len, max_len + 1))
+        qq = rng.integers(0, nsym_real, size=m, dtype=np.uint8)
+        if rng.random() < related:
+            iden = rng.uniform(0.3, 1.0)
+            out = []
+            i = 0
+            while i < m:
+                r = rng.random()
+                if r < 0.02:
+                    i += int(rng.geometric(0.4))
+                    continue
+                if r < 0.04:
+                    out.extend(rng.integers(0, nsym_real, size=int(rng.geometric(0.4))).tolist())
+                out.append(int(qq[i]) if rng.random() < iden else int(rng.integers(0, nsym_real)))
+                i += 1
+            a, b = int(rng.integers(0, 30)), int(rng.integers(0, 30))
+            tt = np.concatenate([rng.integers(0, nsym_real, size=a), np.array(out, dtype=np.int64),
+                                 rng.integers(0, nsym_real, size=b)]).astype(np.uint8)
+            if len(tt) == 0:
+                tt = rng.integers(0, nsym_real, size=1, dtype=np.uint8)
+        else:
+            n = int(rng.integers(min_len, max_len + 1))
+            tt = rng.integers(0, nsym_real, size=n, dtype=np.uint8)
+        qs.append(qq); ts.append(tt)
+    return qs, ts

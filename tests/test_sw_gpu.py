@@ -1,0 +1,79 @@
+"""GPU parity of the batched Smith-Waterman kernels (pb_sw_batch) against the scalar oracle.
+Bit-exact: score, end cell, start cell (oracle/pb_oracle.c tie-breaks)."""
+import numpy as np
+import pytest
+
+from peppan_b200 import seqcodec, sw, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(ctx, oracle, qs, ts, params, mat, go, ge, nthreads=8):
+    q, qoff = sw.concat(qs); t, toff = sw.concat(ts)
+    out, st = sw.sw_batch(ctx, q, qoff, t, toff, params)
+    ref, _ = oracle.sw_batch(q, qoff, t, toff, mat, go, ge, with_cigar=False, nthreads=nthreads)
+    for k in ('score', 'qe', 'te', 'qs', 'ts'):
+        bad = np.nonzero(out[k] != ref[k])[0]
+        assert len(bad) == 0, '%s differs for %d pairs, first %d: gpu=%d oracle=%d (m=%d n=%d)' % (
+            k, len(bad), bad[0], out[k][bad[0]], ref[k][bad[0]], len(qs[bad[0]]), len(ts[bad[0]]))
+    return out, st
+
+
+def _prot_mat_with_pad():
+    return seqcodec.protein_matrix().reshape(-1)
+
+
+def test_protein_ragged_pairs(ctx, oracle):
+    qs, ts = workloads.random_pairs(3000, seed=1, max_len=400)
+    _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
+
+
+def test_protein_multiblock_targets(ctx, oracle):
+    # targets wider than one column block (304 columns) exercise the block border buffer
+    qs, ts = workloads.random_pairs(400, seed=2, min_len=200, max_len=1500)
+    _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
+
+
+def test_edge_cases(ctx, oracle):
+    rng = np.random.default_rng(3)
+    e = np.zeros(0, np.uint8)
+    one = np.array([5], np.uint8)
+    a = rng.integers(0, 20, 50).astype(np.uint8)
+    qs = [e, one, one, a, a, e, a[:1], np.full(40, 17, np.uint8)]
+    ts = [a, one, np.array([6], np.uint8), e, a, e, a, np.full(700, 17, np.uint8)]
+    out, _ = _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
+    assert out['score'][0] == 0 and out['qe'][0] == -1 and out['qs'][0] == -1
+    assert out['score'][4] == sum(int(seqcodec.BLOSUM62[x, x]) for x in a)
+
+
+def test_single_pair_and_odd_counts(ctx, oracle):
+    for n in (1, 2, 3, 5, 33):
+        qs, ts = workloads.random_pairs(n, seed=10 + n, max_len=120)
+        _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
+
+
+def test_nucleotide_scoring(ctx, oracle):
+    # blastn parameters of modules/uberBlast.py:294: +2/-3, gap 6/2
+    qs, ts = workloads.random_pairs(600, seed=4, nsym_real=4, min_len=30, max_len=1200, related=0.8)
+    _compare(ctx, oracle, qs, ts, seqcodec.nt_params(), seqcodec.nt_matrix().reshape(-1), 6, 2)
+
+
+def test_int16_overflow_routes_to_s32(ctx, oracle):
+    # 3,400 identical tryptophans score 37,400 > int16: must take the 32-bit kernel
+    rng = np.random.default_rng(5)
+    big = rng.integers(0, 20, 3400).astype(np.uint8)
+    big[::3] = 17
+    qs = [big, big[:3100], rng.integers(0, 20, 300).astype(np.uint8)]
+    ts = [big.copy(), big.copy(), rng.integers(0, 20, 300).astype(np.uint8)]
+    out, _ = _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
+    assert out['score'][0] > 32767
+
+
+def test_config2_sample(ctx, oracle):
+    # the bench workload (BASELINE.json configs[1]) at a size the oracle finishes in seconds
+    q, qoff, t, toff = workloads.sw_microbench_pairs(4096)
+    out, st = sw.sw_batch(ctx, q, qoff, t, toff, seqcodec.protein_params())
+    ref, _ = oracle.sw_batch(q, qoff, t, toff, _prot_mat_with_pad(), 11, 1, with_cigar=False, nthreads=8)
+    for k in ('score', 'qe', 'te', 'qs', 'ts'):
+        assert np.array_equal(out[k], ref[k]), k
+    assert st['cells'] == 4096 * 300 * 300
