@@ -109,6 +109,12 @@ int pb_measure_dpx_peak(pb_ctx* ctx, int which, double* lane_ops_per_s);
 
 void pb_free(void* p);
 
+/* Pinned (page-locked) host buffers so the caller's H2D/D2H copies run at full PCIe rate; wrap
+ * them as numpy arrays on the Python side.  Optional: every entry point also accepts pageable
+ * memory. */
+int  pb_host_alloc(pb_ctx* ctx, int64_t bytes, void** out);
+void pb_host_free(pb_ctx* ctx, void* p);
+
 #ifdef __cplusplus
 }
 #endif

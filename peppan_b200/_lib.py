@@ -56,6 +56,9 @@ def load():
     lib.pb_measure_dpx_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.pb_free.argtypes = [vp]
     lib.pb_free.restype = None
+    lib.pb_host_alloc.argtypes = [vp, i64, C.POINTER(vp)]
+    lib.pb_host_free.argtypes = [vp, vp]
+    lib.pb_host_free.restype = None
     _lib = lib
     return lib
 
@@ -69,6 +72,7 @@ class Context(object):
 
     def __init__(self, device=0, rank=0, world=1, nccl_uid=None):
         self.lib = load()
+        self._pinned = []
         self.h = C.c_void_p()
         uid = None
         if nccl_uid is not None:
@@ -92,8 +96,21 @@ class Context(object):
         self.check(self.lib.pb_measure_dpx_peak(self.h, which, C.byref(v)), 'pb_measure_dpx_peak')
         return v.value
 
+    def pinned_empty(self, shape, dtype):
+        """numpy array backed by page-locked host memory (released with the context)."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self.check(self.lib.pb_host_alloc(self.h, n * dt.itemsize, C.byref(p)), 'pb_host_alloc')
+        self._pinned.append(p)
+        buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
     def close(self):
         if self.h:
+            for p in self._pinned:
+                self.lib.pb_host_free(self.h, p)
+            self._pinned = []
             self.lib.pb_destroy(self.h)
             self.h = C.c_void_p()
 

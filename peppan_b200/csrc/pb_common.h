@@ -34,20 +34,25 @@ void pb_set_error(pb_ctx* ctx, const char* fmt, ...);
         }                                                                                         \
     } while (0)
 
-// RAII device buffer: freed on scope exit so error paths do not leak.
+// RAII device buffer on the stream-ordered allocator: allocation and release are enqueued on the
+// context stream and served from the device's default memory pool (release threshold raised in
+// pb_init), so repeated calls reuse the same HBM without cudaMalloc/cudaFree round trips.
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    cudaStream_t stream = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    cudaError_t alloc(size_t n) {
+    cudaError_t alloc(size_t n, cudaStream_t s) {
         release();
-        bytes = n;
+        stream = s;
         if (n == 0) return cudaSuccess;
-        return cudaMalloc(&p, n);
+        cudaError_t e = cudaMallocAsync(&p, n, s);
+        if (e == cudaSuccess) bytes = n; else p = nullptr;
+        return e;
     }
-    void release() { if (p) { cudaFree(p); p = nullptr; } bytes = 0; }
+    void release() { if (p) { cudaFreeAsync(p, stream); p = nullptr; } bytes = 0; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };

@@ -87,6 +87,12 @@ extern "C" int pb_init(int device, int rank, int world, const void* nccl_uid, pb
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
     CK(cudaMalloc(&ctx->d_counter, 64 * sizeof(int)));
+    {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
 #undef CK
     if (world > 1) {
         if (!nccl_uid) { pb_set_error(nullptr, "pb_init: world > 1 requires an NCCL unique id"); pb_destroy(ctx); return PB_ERR_ARG; }
@@ -130,3 +136,18 @@ extern "C" int pb_device_info(pb_ctx* ctx, int32_t* sm_count, int32_t* clock_khz
 }
 
 extern "C" void pb_free(void* p) { free(p); }
+
+// Pinned host staging buffers for callers that want full-rate H2D/D2H copies.
+extern "C" int pb_host_alloc(pb_ctx* ctx, int64_t bytes, void** out)
+{
+    if (!ctx || !out || bytes < 0) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB_CUDA(ctx, cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return PB_OK;
+}
+
+extern "C" void pb_host_free(pb_ctx* ctx, void* p)
+{
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}

@@ -128,7 +128,7 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     const int grid = ctx->sm_count;
     if (bstride > 0) {
         size_t need = (size_t)grid * SW_WARPS * (32 / SW_G) * bstride * sizeof(uint2);
-        if (J->boundary.bytes < need) PB_CUDA(ctx, J->boundary.alloc(need));
+        if (J->boundary.bytes < need) PB_CUDA(ctx, J->boundary.alloc(need, ctx->stream));
     }
     SwArgs a;
     a.q = J->q.as<uint8_t>(); a.t = J->t.as<uint8_t>();
@@ -204,12 +204,12 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
         else maxscore = std::max(maxscore, (int)mat[a * 32 + b]);
     }
     J->maxscore = maxscore;
-    PB_CUDA(ctx, J->matrix.alloc(1024));
+    PB_CUDA(ctx, J->matrix.alloc(1024, ctx->stream));
     PB_CUDA(ctx, cudaMemcpyAsync(J->matrix.p, mat, 1024, cudaMemcpyHostToDevice, ctx->stream));
-    PB_CUDA(ctx, J->q.alloc(std::max<int64_t>(J->qbytes, 16)));
-    PB_CUDA(ctx, J->t.alloc(std::max<int64_t>(J->tbytes, 16)));
-    PB_CUDA(ctx, J->qoff.alloc((npairs + 1) * 8));
-    PB_CUDA(ctx, J->toff.alloc((npairs + 1) * 8));
+    PB_CUDA(ctx, J->q.alloc(std::max<int64_t>(J->qbytes, 16), ctx->stream));
+    PB_CUDA(ctx, J->t.alloc(std::max<int64_t>(J->tbytes, 16), ctx->stream));
+    PB_CUDA(ctx, J->qoff.alloc((npairs + 1) * 8, ctx->stream));
+    PB_CUDA(ctx, J->toff.alloc((npairs + 1) * 8, ctx->stream));
     if (npairs) {
         PB_CUDA(ctx, cudaMemcpyAsync(J->q.p, q, J->qbytes, cudaMemcpyHostToDevice, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(J->t.p, t, J->tbytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -217,21 +217,21 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
         PB_CUDA(ctx, cudaMemcpyAsync(J->toff.p, toff, (npairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     size_t nn = std::max(n, 1);
-    PB_CUDA(ctx, J->desc.alloc(nn * sizeof(PairDesc)));
-    PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc)));
-    PB_CUDA(ctx, J->keys.alloc(nn * 4)); PB_CUDA(ctx, J->keys_sorted.alloc(nn * 4));
-    PB_CUDA(ctx, J->ids.alloc(nn * 4)); PB_CUDA(ctx, J->perm.alloc(nn * 4)); PB_CUDA(ctx, J->perm_rev.alloc(nn * 4));
-    PB_CUDA(ctx, J->meta.alloc(16));
-    PB_CUDA(ctx, J->score.alloc(nn * 4)); PB_CUDA(ctx, J->qe.alloc(nn * 4)); PB_CUDA(ctx, J->te.alloc(nn * 4));
-    PB_CUDA(ctx, J->qs.alloc(nn * 4)); PB_CUDA(ctx, J->ts.alloc(nn * 4));
-    PB_CUDA(ctx, J->cells.alloc(8));
+    PB_CUDA(ctx, J->desc.alloc(nn * sizeof(PairDesc), ctx->stream));
+    PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc), ctx->stream));
+    PB_CUDA(ctx, J->keys.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->keys_sorted.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->ids.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm_rev.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->meta.alloc(16, ctx->stream));
+    PB_CUDA(ctx, J->score.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->qe.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->te.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->qs.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->ts.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->cells.alloc(8, ctx->stream));
     constexpr int KP = ((SW_K + 3) / 4) * 4;
-    PB_CUDA(ctx, J->dump.alloc((size_t)ctx->sm_count * SW_WARPS * 32 * 2 * KP * 4));
+    PB_CUDA(ctx, J->dump.alloc((size_t)ctx->sm_count * SW_WARPS * 32 * 2 * KP * 4, ctx->stream));
     size_t tmp = 0;
     PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
                                                             J->ids.as<int>(), J->perm.as<int>(), n, 0, 32, ctx->stream));
     J->cub_bytes = tmp;
-    PB_CUDA(ctx, J->cub_tmp.alloc(std::max<size_t>(tmp, 16)));
+    PB_CUDA(ctx, J->cub_tmp.alloc(std::max<size_t>(tmp, 16), ctx->stream));
     double cells = 0;
     for (int64_t p = 0; p < npairs; ++p) cells += (double)(qoff[p + 1] - qoff[p]) * (double)(toff[p + 1] - toff[p]);
     J->fwd_cells = cells;
@@ -359,7 +359,7 @@ extern "C" int pb_measure_dpx_peak(pb_ctx* ctx, int which, double* lane_ops_per_
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, iters = 4096;
     DevBuf out;
-    PB_CUDA(ctx, out.alloc((size_t)blocks * 256 * 4));
+    PB_CUDA(ctx, out.alloc((size_t)blocks * 256 * 4, ctx->stream));
     float best = 1e30f;
     for (int r = 0; r < 8; ++r) {
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));

@@ -59,11 +59,11 @@ def test_nucleotide_scoring(ctx, oracle):
 
 
 def test_int16_overflow_routes_to_s32(ctx, oracle):
-    # 3,400 identical tryptophans score 37,400 > int16: must take the 32-bit kernel
+    # a 5,000-residue self alignment scores far above int16: must take the 32-bit kernel
     rng = np.random.default_rng(5)
-    big = rng.integers(0, 20, 3400).astype(np.uint8)
-    big[::3] = 17
-    qs = [big, big[:3100], rng.integers(0, 20, 300).astype(np.uint8)]
+    big = rng.integers(0, 20, 5000).astype(np.uint8)
+    big[::2] = 17
+    qs = [big, big[:4100], rng.integers(0, 20, 300).astype(np.uint8)]
     ts = [big.copy(), big.copy(), rng.integers(0, 20, 300).astype(np.uint8)]
     out, _ = _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
     assert out['score'][0] > 32767
