@@ -12,16 +12,30 @@ using namespace pbsw;
 
 namespace {
 
-constexpr int SW_G = 16, SW_K = 19, SW_WARPS = 8;
-constexpr int SW_W = SW_G * SW_K;
 constexpr int PAD_SCORE = -16;
+
+// Kernel shapes: G lanes per task, K columns per lane, WARPS per (persistent, 1/SM) block.
+struct SwConfig { int G, K, WARPS; };
+constexpr SwConfig SW_CONFIGS[] = { {16, 19, 8}, {8, 38, 4}, {16, 20, 8}, {8, 40, 4} };
+
+SwConfig sw_pick_config()
+{
+    // PB_SW_CFG=G,K selects among the compiled shapes (tuning aid); default = first entry
+    const char* e = getenv("PB_SW_CFG");
+    if (e) {
+        int g = 0, k = 0;
+        if (sscanf(e, "%d,%d", &g, &k) == 2)
+            for (const SwConfig& c : SW_CONFIGS) if (c.G == g && c.K == k) return c;
+    }
+    return SW_CONFIGS[0];
+}
 
 // ---- small device kernels around the DP kernel ------------------------------------------------
 
 // forward descriptors + sort keys.  key (descending sort): [31] needs-s32, [30:20] column blocks,
 // [19:0] query length; longest work first so the dynamic scheduler packs well, and neighbours in
 // the sorted order (which share a task / a warp) have similar shapes.
-__global__ void make_desc_fwd(const int64_t* qoff, const int64_t* toff, int n, int maxscore,
+__global__ void make_desc_fwd(const int64_t* qoff, const int64_t* toff, int n, int maxscore, int SW_W,
                               PairDesc* desc, uint32_t* keys, int* ids, int* meta /*[0]=n32,[1]=maxm,[2]=maxnb*/)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,7 +60,7 @@ __global__ void make_desc_fwd(const int64_t* qoff, const int64_t* toff, int n, i
 // reverse descriptors: prefixes ending at the forward end cell, looking for the forward score.
 // key: [31] s32, [30:16] column blocks, [15:0] score (alignment length grows with the score, so
 // neighbours terminate their early-exit reverse sweep at similar rows).
-__global__ void make_desc_rev(const PairDesc* fwd, const int* score, const int* qe, const int* te, int n,
+__global__ void make_desc_rev(const PairDesc* fwd, const int* score, const int* qe, const int* te, int n, int SW_W,
                               PairDesc* desc, uint32_t* keys, int* ids, int* meta)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,12 +104,31 @@ __global__ void __launch_bounds__(256) dpx_peak_kernel(unsigned* out, unsigned s
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <bool PACKED>
-size_t sw_smem_bytes(int nsym)
+size_t sw_smem_bytes(const SwConfig& c, bool packed, int nsym)
 {
-    constexpr int KP = ((SW_K + 3) / 4) * 4;
-    constexpr int NG = 32 / SW_G;
-    return 1024 + (size_t)SW_WARPS * NG * (PACKED ? 2 : 1) * nsym * SW_G * KP;
+    const int KP = ((c.K + 3) / 4) * 4;
+    const int NG = 32 / c.G;
+    return 1024 + (size_t)c.WARPS * NG * (packed ? 2 : 1) * nsym * c.G * KP;
+}
+
+template <int G, int K, int WARPS, bool PACKED, bool REV>
+cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t st)
+{
+    auto k = sw_kernel<G, K, PACKED, REV, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <bool PACKED, bool REV>
+cudaError_t sw_dispatch(const SwConfig& c, const SwArgs& a, int grid, size_t smem, cudaStream_t st)
+{
+    if (c.G == 16 && c.K == 19) return sw_launch_one<16, 19, 8, PACKED, REV>(a, grid, smem, st);
+    if (c.G == 8 && c.K == 38) return sw_launch_one<8, 38, 4, PACKED, REV>(a, grid, smem, st);
+    if (c.G == 16 && c.K == 20) return sw_launch_one<16, 20, 8, PACKED, REV>(a, grid, smem, st);
+    if (c.G == 8 && c.K == 40) return sw_launch_one<8, 40, 4, PACKED, REV>(a, grid, smem, st);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -107,27 +140,30 @@ struct pb_sw_job {
     int want_coords = 0;
     pb_score_params params;
     int maxscore = 1;
+    SwConfig cfg;
     DevBuf q, t, qoff, toff, matrix;
     DevBuf desc, desc_rev, keys, keys_sorted, ids, perm, perm_rev, meta, cub_tmp;
-    DevBuf score, qe, te, qs, ts, dump, boundary, cells;
+    DevBuf score, qe, te, qs, ts, boundary, cells;
     size_t cub_bytes = 0;
+    int n32 = 0;
     int64_t qbytes = 0, tbytes = 0;
     double fwd_cells = 0;
 };
 
-static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, const int* perm,
-                     int n32, int* launches)
+static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, const int* perm, int* launches)
 {
     const int n = (int)J->npairs;
-    // boundary buffer sized from the device-side maxima
+    const SwConfig& c = J->cfg;
+    // boundary buffer sized from the device-side maxima; count of s32 pairs (they sort first)
     int meta[3];
     PB_CUDA(ctx, cudaMemcpyAsync(meta, J->meta.p, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    n32 = meta[0];
+    const int n32 = meta[0];
+    J->n32 = n32;
     int bstride = meta[2] > 1 ? ((meta[1] + 63) / 64) * 64 : 0;
     const int grid = ctx->sm_count;
     if (bstride > 0) {
-        size_t need = (size_t)grid * SW_WARPS * (32 / SW_G) * bstride * sizeof(uint2);
+        size_t need = (size_t)grid * c.WARPS * (32 / c.G) * bstride * sizeof(uint2);
         if (J->boundary.bytes < need) PB_CUDA(ctx, J->boundary.alloc(need, ctx->stream));
     }
     SwArgs a;
@@ -135,42 +171,23 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     a.desc = desc; a.perm = perm;
     a.matrix = J->matrix.as<int8_t>(); a.nsym = J->params.nsym;
     a.go = J->params.gap_open; a.ge = J->params.gap_extend;
-    a.dump = J->dump.as<uint32_t>(); a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride;
+    a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride;
     a.out_score = J->score.as<int>();
     a.out_a = rev ? J->qs.as<int>() : J->qe.as<int>();
     a.out_b = rev ? J->ts.as<int>() : J->te.as<int>();
     a.cells = rev ? J->cells.as<unsigned long long>() : nullptr;
     PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
 
-    size_t smem16 = sw_smem_bytes<true>(J->params.nsym), smem32 = sw_smem_bytes<false>(J->params.nsym);
+    const size_t smem16 = sw_smem_bytes(c, true, J->params.nsym), smem32 = sw_smem_bytes(c, false, J->params.nsym);
     if (smem16 > ctx->smem_optin) { pb_set_error(ctx, "nsym=%d needs %zu B shared memory (> %zu)", J->params.nsym, smem16, ctx->smem_optin); return PB_ERR_LIMIT; }
-    // s32 pairs sort first (key bit 31)
     if (n32 > 0) {
         a.first = 0; a.count = n32; a.counter = ctx->d_counter + (rev ? 2 : 0);
-        if (!rev) {
-            auto k = sw_kernel<SW_G, SW_K, false, false, SW_WARPS>;
-            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-            k<<<grid, SW_WARPS * 32, smem32, ctx->stream>>>(a);
-        } else {
-            auto k = sw_kernel<SW_G, SW_K, false, true, SW_WARPS>;
-            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-            k<<<grid, SW_WARPS * 32, smem32, ctx->stream>>>(a);
-        }
-        PB_CUDA(ctx, cudaGetLastError());
+        PB_CUDA(ctx, rev ? (sw_dispatch<false, true>(c, a, grid, smem32, ctx->stream)) : (sw_dispatch<false, false>(c, a, grid, smem32, ctx->stream)));
         ++*launches;
     }
     if (n - n32 > 0) {
         a.first = n32; a.count = n - n32; a.counter = ctx->d_counter + (rev ? 3 : 1);
-        if (!rev) {
-            auto k = sw_kernel<SW_G, SW_K, true, false, SW_WARPS>;
-            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-            k<<<grid, SW_WARPS * 32, smem16, ctx->stream>>>(a);
-        } else {
-            auto k = sw_kernel<SW_G, SW_K, true, true, SW_WARPS>;
-            PB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-            k<<<grid, SW_WARPS * 32, smem16, ctx->stream>>>(a);
-        }
-        PB_CUDA(ctx, cudaGetLastError());
+        PB_CUDA(ctx, rev ? (sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream)) : (sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream)));
         ++*launches;
     }
     return PB_OK;
@@ -193,6 +210,7 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
     if (!J) { pb_set_error(ctx, "out of host memory"); return PB_ERR_NOMEM; }
     std::unique_ptr<pb_sw_job> guard(J);
     J->npairs = npairs; J->want_coords = want_coords; J->params = *params;
+    J->cfg = sw_pick_config();
     const int n = (int)npairs;
     J->qbytes = npairs ? qoff[npairs] : 0; J->tbytes = npairs ? toff[npairs] : 0;
     // matrix with the pad symbol's row/column forced negative
@@ -225,8 +243,6 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
     PB_CUDA(ctx, J->score.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->qe.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->te.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->qs.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->ts.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->cells.alloc(8, ctx->stream));
-    constexpr int KP = ((SW_K + 3) / 4) * 4;
-    PB_CUDA(ctx, J->dump.alloc((size_t)ctx->sm_count * SW_WARPS * 32 * 2 * KP * 4, ctx->stream));
     size_t tmp = 0;
     PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
                                                             J->ids.as<int>(), J->perm.as<int>(), n, 0, 32, ctx->stream));
@@ -251,13 +267,13 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
         const int tb = 256, gb = (n + tb - 1) / tb;
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
         PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 16, ctx->stream));
-        make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(J->qoff.as<int64_t>(), J->toff.as<int64_t>(), n, J->maxscore,
+        make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(J->qoff.as<int64_t>(), J->toff.as<int64_t>(), n, J->maxscore, J->cfg.G * J->cfg.K,
                                                   J->desc.as<PairDesc>(), J->keys.as<uint32_t>(), J->ids.as<int>(), J->meta.as<int>());
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         size_t tmp = J->cub_bytes;
         PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(J->cub_tmp.p, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
                                                                 J->ids.as<int>(), J->perm.as<int>(), n, 0, 32, ctx->stream));
-        int rc = sw_launch(ctx, J, false, J->desc.as<PairDesc>(), J->perm.as<int>(), 0, &launches);
+        int rc = sw_launch(ctx, J, false, J->desc.as<PairDesc>(), J->perm.as<int>(), &launches);
         if (rc) return rc;
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
         if (J->want_coords) {
@@ -266,13 +282,13 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
             fill_int<<<gb, tb, 0, ctx->stream>>>(J->qs.as<int>(), -1, n);
             fill_int<<<gb, tb, 0, ctx->stream>>>(J->ts.as<int>(), -1, n);
             launches += 2;
-            make_desc_rev<<<gb, tb, 0, ctx->stream>>>(J->desc.as<PairDesc>(), J->score.as<int>(), J->qe.as<int>(), J->te.as<int>(), n,
+            make_desc_rev<<<gb, tb, 0, ctx->stream>>>(J->desc.as<PairDesc>(), J->score.as<int>(), J->qe.as<int>(), J->te.as<int>(), n, J->cfg.G * J->cfg.K,
                                                       J->desc_rev.as<PairDesc>(), J->keys.as<uint32_t>(), J->ids.as<int>(), J->meta.as<int>());
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
             tmp = J->cub_bytes;
             PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(J->cub_tmp.p, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
                                                                     J->ids.as<int>(), J->perm_rev.as<int>(), n, 0, 32, ctx->stream));
-            rc = sw_launch(ctx, J, true, J->desc_rev.as<PairDesc>(), J->perm_rev.as<int>(), 0, &launches);
+            rc = sw_launch(ctx, J, true, J->desc_rev.as<PairDesc>(), J->perm_rev.as<int>(), &launches);
             if (rc) return rc;
         }
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -288,8 +304,7 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
         stats->ms_forward = ms_f; stats->ms_reverse = ms_r; stats->ms_traceback = 0;
         stats->ms_total_device = ms_f + ms_r;
         stats->kernel_launches = launches;
-        int meta0 = 0;
-        stats->n_s32_pairs = meta0;
+        stats->n_s32_pairs = J->n32;
     }
     return PB_OK;
 }

@@ -16,20 +16,21 @@
 // private columns), built once per column block; the two pairs' bytes are merged and sign-
 // extended into one s16x2 word by a single PRMT.
 //
-// Recurrences per packed column (Eh = E + goe, Fh = F + goe; goe = open + extend):
-//   Eh = viaddmax(Eh, -ge, Hup)                     1 DPX
-//   mg = vimax3(Eh, Fh, goe) - goe                  1 DPX + 1 IADD (FMA pipe)   = max(E, F, 0)
-//   H  = viaddmax(Hdiag, s, mg)                     1 DPX      (>= 0 because mg >= 0)
-//   Fh' = viaddmax(Fh, -ge, H)                      1 DPX
+// Recurrences per packed column (Eh = E + goe, Fh = F + goe; goe = open + extend).  The F chain is
+// kept one instruction long per column so a single warp has enough ILP to fill the ALU pipe:
+//   Eh  = viaddmax(Eh, -ge, Hup)                    1 DPX
+//   eg  = vmax2(Eh, goe) - goe                      1 DPX + 1 IADD (FMA pipe)   = max(E, 0)
+//   U   = viaddmax(Hdiag, s, eg)                    1 DPX      max(0, Hdiag+s, E)
+//   H   = viaddmax(Fh, -goe, U)                     1 DPX      max(U, F)
+//   Fh' = viaddmax(Fh, -ge, U)                      1 DPX      (= max(Fh-ge, H) because ge <= goe)
 //   stepmax = vimax3(stepmax, H, H')                0.5 DPX
-//   s  = prmt(profA, profB)                         1 PRMT
-// => 5.5 ALU-pipe instructions per packed column = 2.75 per DP cell (roofline).
+//   s   = prmt(profA, profB)                        1 PRMT
+// => 6.5 ALU-pipe instructions per packed column = 3.25 per DP cell (roofline).
 //
 // End-cell tracking (bit-exact row-major-first maximum): each lane keeps its best value and the
-// first row where it was reached; whenever a lane's best strictly increases it dumps its H strip
-// (K words) to a lane-private global scratch slot.  After the last block the winning lane reads
-// its dump back to find the first column holding the maximum.  The dump stores use the LSU and
-// issue slots the ALU-bound loop leaves idle.
+// first row where it was reached; whenever a lane's best strictly increases it snapshots its H
+// strip into K spare registers (moves issue on the FMA pipe, which the DP leaves idle).  After
+// the last block the winning lane scans its snapshot for the first column holding the maximum.
 //
 // REV = true runs the same DP on the reversed prefixes q[0..m) and t[0..n) (m = qe+1, n = te+1
 // from the forward pass) and stops once the known score has been seen and every lane has passed
@@ -58,7 +59,6 @@ struct SwArgs {
     const int8_t* matrix;   // 32x32
     int nsym;               // profile rows incl. pad (pad code = nsym-1)
     int go, ge;
-    uint32_t* dump;         // [grid*warps*32][NPAIR][KD]
     uint2* boundary;        // [grid*warps*NG][bstride]
     int bstride;
     int* out_score;         // forward: score, row (qe), col (te); reverse: qs, ts
@@ -131,11 +131,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     const int pairBytes = nsym * rowBytes;
     uint8_t* prof = smem + 1024 + (size_t)((warp * NG + g) * NPAIR) * pairBytes;
     const int gwarp = blockIdx.x * WARPS + warp;
-    uint32_t* mydump = a.dump + ((size_t)gwarp * 32 + lane) * (NPAIR * KP);
     uint2* mybound = a.boundary ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
 
     const uint32_t NEG_GE = O::bcast(-a.ge);
     const uint32_t GOE = O::bcast(a.go + a.ge);
+    const uint32_t NEG_GOE = O::bcast(-(a.go + a.ge));
     const int ntasks = (a.count + NPAIR - 1) / NPAIR;
 
     for (;;) {
@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
         const int nblocks = (nw + W - 1) / W;
 
         uint32_t best = 0;
+        uint32_t snapA[K], snapB[K];
+#pragma unroll
+        for (int p = 0; p < K; ++p) { snapA[p] = 0; snapB[p] = 0; }
         int browA = 0x3fffffff, browB = 0x3fffffff, blkA = 0, blkB = 0;
         int rowcap = mw;                       // REV: rows later blocks still have to visit
         int bvalid = mw;                       // rows of the block border written by the previous block
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             int cB = PAD;
             if (PACKED) cB = (i >= 0 && i < mB) ? (int)__ldg(qB + (REV ? mB - 1 - i : i)) : PAD;
 
+#pragma unroll 2
             for (int s = 0; s < slimit; ++s) {
                 i = s - l;
                 // profile rows of this step
@@ -253,7 +257,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 }
                 uint32_t hdiag = hl_prev;
                 hl_prev = hl;
-                uint32_t hleft = hl;
                 uint32_t stepmax = 0;
 #pragma unroll
                 for (int p = 0; p < K; ++p) {
@@ -265,18 +268,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                         default: sc = O::template mix<3>(wA[p >> 2], wB[p >> 2]); break;
                     }
                     const uint32_t hup = H[p];
-                    // Fh for this column from the cell to the left
-                    fh = O::addmax(fh, NEG_GE, hleft);
-                    E[p] = O::addmax(E[p], NEG_GE, hup);
-                    uint32_t mg = O::max3(E[p], fh, GOE) - GOE;
-                    uint32_t hn = O::addmax(hdiag, sc, mg);
+                    const uint32_t eh = O::addmax(E[p], NEG_GE, hup);
+                    E[p] = eh;
+                    const uint32_t eg = O::max2(eh, GOE) - GOE;
+                    const uint32_t u = O::addmax(hdiag, sc, eg);
+                    const uint32_t hn = O::addmax(fh, NEG_GOE, u);
+                    fh = O::addmax(fh, NEG_GE, u);
                     hdiag = hup;
                     H[p] = hn;
-                    hleft = hn;
                     if (p & 1) stepmax = O::max3(stepmax, hn, H[p - 1]);
                     else if (p == K - 1) stepmax = O::max2(stepmax, hn);
                 }
-                hlast = hleft;
+                hlast = H[K - 1];
                 fout = fh;
                 if (nblocks > 1 && l == G - 1 && b + 1 < nblocks && i >= 0 && i < mw)
                     mybound[i] = make_uint2(hlast, fout);
@@ -293,12 +296,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                     if (!PACKED || (ch & 0xffff0000u)) {
                         browA = i; blkA = b;
 #pragma unroll
-                        for (int p = 0; p < K; ++p) mydump[p] = H[p];
+                        for (int p = 0; p < K; ++p) snapA[p] = H[p];
                     }
                     if (PACKED && (ch & 0x0000ffffu)) {
                         browB = i; blkB = b;
 #pragma unroll
-                        for (int p = 0; p < K; ++p) mydump[KP + p] = H[p];
+                        for (int p = 0; p < K; ++p) snapB[p] = H[p];
                     }
                 }
                 if (REV) {
@@ -334,8 +337,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             unsigned long long key = ~0ull;
             if (myb == S && S > 0) {
                 int pcol = K;
+#pragma unroll
                 for (int p = K - 1; p >= 0; --p) {
-                    uint32_t v = mydump[h * KP + p];
+                    uint32_t v = (h == 0) ? snapA[p] : snapB[p];
                     int hv = (h == 0) ? O::hi(v) : O::lo(v);
                     if (hv == S) pcol = p;
                 }
