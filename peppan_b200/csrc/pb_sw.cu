@@ -15,17 +15,18 @@ namespace {
 constexpr int PAD_SCORE = -16;
 
 // Kernel shapes: G lanes per task, K columns per lane, WARPS per (persistent, 1/SM) block.
-struct SwConfig { int G, K, WARPS; };
-constexpr SwConfig SW_CONFIGS[] = { {16, 19, 8}, {8, 38, 4}, {16, 20, 8}, {8, 40, 4} };
+struct SwConfig { int G, K, R, LONG, WARPS; };
+constexpr SwConfig SW_CONFIGS[] = { {16, 19, 2, 1, 8}, {16, 19, 1, 0, 8}, {16, 19, 2, 0, 8}, {16, 19, 1, 1, 8},
+                                    {8, 19, 2, 0, 8}, {8, 19, 2, 1, 8}, {8, 38, 1, 0, 4} };
 
 SwConfig sw_pick_config()
 {
-    // PB_SW_CFG=G,K selects among the compiled shapes (tuning aid); default = first entry
+    // PB_SW_CFG=G,K,R,LONG selects among the compiled shapes (tuning aid); default = first entry
     const char* e = getenv("PB_SW_CFG");
     if (e) {
-        int g = 0, k = 0;
-        if (sscanf(e, "%d,%d", &g, &k) == 2)
-            for (const SwConfig& c : SW_CONFIGS) if (c.G == g && c.K == k) return c;
+        int g = 0, k = 0, r = 1, lg = 0;
+        if (sscanf(e, "%d,%d,%d,%d", &g, &k, &r, &lg) >= 2)
+            for (const SwConfig& c : SW_CONFIGS) if (c.G == g && c.K == k && c.R == r && c.LONG == lg) return c;
     }
     return SW_CONFIGS[0];
 }
@@ -111,10 +112,10 @@ size_t sw_smem_bytes(const SwConfig& c, bool packed, int nsym)
     return 1024 + (size_t)c.WARPS * NG * (packed ? 2 : 1) * nsym * c.G * KP;
 }
 
-template <int G, int K, int WARPS, bool PACKED, bool REV>
+template <int G, int K, int R, bool LONG, int WARPS, bool PACKED, bool REV>
 cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = sw_kernel<G, K, PACKED, REV, WARPS>;
+    auto k = sw_kernel<G, K, R, LONG, PACKED, REV, WARPS>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, WARPS * 32, smem, st>>>(a);
@@ -124,10 +125,10 @@ cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t s
 template <bool PACKED, bool REV>
 cudaError_t sw_dispatch(const SwConfig& c, const SwArgs& a, int grid, size_t smem, cudaStream_t st)
 {
-    if (c.G == 16 && c.K == 19) return sw_launch_one<16, 19, 8, PACKED, REV>(a, grid, smem, st);
-    if (c.G == 8 && c.K == 38) return sw_launch_one<8, 38, 4, PACKED, REV>(a, grid, smem, st);
-    if (c.G == 16 && c.K == 20) return sw_launch_one<16, 20, 8, PACKED, REV>(a, grid, smem, st);
-    if (c.G == 8 && c.K == 40) return sw_launch_one<8, 40, 4, PACKED, REV>(a, grid, smem, st);
+#define PB_CFG(g, k, r, lg, w) if (c.G == g && c.K == k && c.R == r && c.LONG == lg) return sw_launch_one<g, k, r, (lg != 0), w, PACKED, REV>(a, grid, smem, st);
+    PB_CFG(16, 19, 1, 0, 8) PB_CFG(16, 19, 2, 0, 8) PB_CFG(16, 19, 2, 1, 8) PB_CFG(16, 19, 1, 1, 8)
+    PB_CFG(8, 19, 2, 0, 8) PB_CFG(8, 19, 2, 1, 8) PB_CFG(8, 38, 1, 0, 4)
+#undef PB_CFG
     return cudaErrorInvalidValue;
 }
 
@@ -176,6 +177,7 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     a.out_a = rev ? J->qs.as<int>() : J->qe.as<int>();
     a.out_b = rev ? J->ts.as<int>() : J->te.as<int>();
     a.cells = rev ? J->cells.as<unsigned long long>() : nullptr;
+    a.dbg = getenv("PB_SW_DBG") ? atoi(getenv("PB_SW_DBG")) : 0;
     PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
 
     const size_t smem16 = sw_smem_bytes(c, true, J->params.nsym), smem32 = sw_smem_bytes(c, false, J->params.nsym);

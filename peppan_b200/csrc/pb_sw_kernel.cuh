@@ -16,8 +16,12 @@
 // private columns), built once per column block; the two pairs' bytes are merged and sign-
 // extended into one s16x2 word by a single PRMT.
 //
-// Recurrences per packed column (Eh = E + goe, Fh = F + goe; goe = open + extend).  The F chain is
-// kept one instruction long per column so a single warp has enough ILP to fill the ALU pipe:
+// R query rows are processed per step (R = 2 interleaves two row chains one column apart, which
+// doubles the instruction-level parallelism of a warp and halves the per-step shuffle / load /
+// tracking overhead).
+//
+// Recurrences per packed column (Eh = E + goe, Fh = F + goe; goe = open + extend).  LONG = false
+// keeps the F chain one instruction long per column:
 //   Eh  = viaddmax(Eh, -ge, Hup)                    1 DPX
 //   eg  = vmax2(Eh, goe) - goe                      1 DPX + 1 IADD (FMA pipe)   = max(E, 0)
 //   U   = viaddmax(Hdiag, s, eg)                    1 DPX      max(0, Hdiag+s, E)
@@ -26,6 +30,9 @@
 //   stepmax = vimax3(stepmax, H, H')                0.5 DPX
 //   s   = prmt(profA, profB)                        1 PRMT
 // => 6.5 ALU-pipe instructions per packed column = 3.25 per DP cell (roofline).
+// LONG = true merges the two clamps (4-deep chain, one ALU instruction fewer):
+//   Eh  = viaddmax(Eh, -ge, Hup);  mg = vimax3(Eh, Fh, goe) - goe;  H = viaddmax(Hdiag, s, mg);
+//   Fh' = viaddmax(Fh, -ge, H)                      => 5.5 ALU-pipe instructions per packed column.
 //
 // End-cell tracking (bit-exact row-major-first maximum): each lane keeps its best value and the
 // first row where it was reached; whenever a lane's best strictly increases it snapshots its H
@@ -65,6 +72,7 @@ struct SwArgs {
     int* out_a;
     int* out_b;
     unsigned long long* cells;   // REV: DP cells actually swept (statistic), nullable
+    int dbg;                // tuning aid (PB_SW_DBG): bit0 skip max tracking, bit1 skip shuffles -- results invalid
 };
 
 __device__ __forceinline__ uint32_t shfl_up_g(uint32_t v, int G) { return __shfl_up_sync(0xffffffffu, v, 1, G); }
@@ -107,7 +115,7 @@ template <> struct Ops<false> {
     static __device__ __forceinline__ int lo(uint32_t) { return 0; }
 };
 
-template <int G, int K, bool PACKED, bool REV, int WARPS>
+template <int G, int K, int R, bool LONG, bool PACKED, bool REV, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
 {
     using O = Ops<PACKED>;
@@ -117,6 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     constexpr int NPAIR = PACKED ? 2 : 1;
     constexpr int W = G * K;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int BIGROW = 0x3fffffff;
 
     extern __shared__ __align__(16) uint8_t smem[];
     int8_t* smat = reinterpret_cast<int8_t*>(smem);
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
         uint32_t snapA[K], snapB[K];
 #pragma unroll
         for (int p = 0; p < K; ++p) { snapA[p] = 0; snapB[p] = 0; }
-        int browA = 0x3fffffff, browB = 0x3fffffff, blkA = 0, blkB = 0;
+        int browA = BIGROW, browB = BIGROW, blkA = 0, blkB = 0;
         int rowcap = mw;                       // REV: rows later blocks still have to visit
         int bvalid = mw;                       // rows of the block border written by the previous block
         unsigned long long swept = 0;
@@ -214,94 +223,167 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             uint32_t H[K], E[K];
 #pragma unroll
             for (int p = 0; p < K; ++p) { H[p] = 0; E[p] = 0; }
-            uint32_t hlast = 0, fout = 0, hl_prev = 0;
-            int slimit = min(mw, rowcap) + G - 1;
+            uint32_t hlast[R], fout[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) { hlast[rr] = 0; fout[rr] = 0; }
+            uint32_t hl_prev = 0;
+            const int rows_here = min(mw, rowcap);
+            int slimit = (rows_here + R - 1) / R + G - 1;
             bool armed = false;
 
             // prefetch the row symbols of step 0
-            int i = -l;
-            int cA = (i >= 0 && i < mA) ? (int)__ldg(qA + (REV ? mA - 1 - i : i)) : PAD;
-            int cB = PAD;
-            if (PACKED) cB = (i >= 0 && i < mB) ? (int)__ldg(qB + (REV ? mB - 1 - i : i)) : PAD;
+            int cA[R], cB[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                const int i0 = -l * R + rr;
+                cA[rr] = ((unsigned)i0 < (unsigned)mA) ? (int)__ldg(qA + (REV ? mA - 1 - i0 : i0)) : PAD;
+                cB[rr] = PAD;
+                if (PACKED) cB[rr] = ((unsigned)i0 < (unsigned)mB) ? (int)__ldg(qB + (REV ? mB - 1 - i0 : i0)) : PAD;
+            }
 
 #pragma unroll 2
             for (int s = 0; s < slimit; ++s) {
-                i = s - l;
+                const int r0 = (s - l) * R;
                 // profile rows of this step
-                uint32_t wA[KW], wB[KW];
-                {
-                    const uint32_t* rA = reinterpret_cast<const uint32_t*>(prof + cA * rowBytes + l * KP);
+                uint32_t wA[R][KW], wB[R][KW];
 #pragma unroll
-                    for (int w = 0; w < KW; ++w) wA[w] = rA[w];
+                for (int rr = 0; rr < R; ++rr) {
+                    const uint32_t* rA = reinterpret_cast<const uint32_t*>(prof + cA[rr] * rowBytes + l * KP);
+#pragma unroll
+                    for (int w = 0; w < KW; ++w) wA[rr][w] = rA[w];
                     if (PACKED) {
-                        const uint32_t* rB = reinterpret_cast<const uint32_t*>(prof + pairBytes + cB * rowBytes + l * KP);
+                        const uint32_t* rB = reinterpret_cast<const uint32_t*>(prof + pairBytes + cB[rr] * rowBytes + l * KP);
 #pragma unroll
-                        for (int w = 0; w < KW; ++w) wB[w] = rB[w];
+                        for (int w = 0; w < KW; ++w) wB[rr][w] = rB[w];
                     } else {
 #pragma unroll
-                        for (int w = 0; w < KW; ++w) wB[w] = 0;
+                        for (int w = 0; w < KW; ++w) wB[rr][w] = 0;
                     }
                 }
                 // prefetch next step's symbols
-                {
-                    int in = i + 1;
-                    cA = (in >= 0 && in < mA) ? (int)__ldg(qA + (REV ? mA - 1 - in : in)) : PAD;
-                    if (PACKED) cB = (in >= 0 && in < mB) ? (int)__ldg(qB + (REV ? mB - 1 - in : in)) : PAD;
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const int in = r0 + R + rr;
+                    cA[rr] = ((unsigned)in < (unsigned)mA) ? (int)__ldg(qA + (REV ? mA - 1 - in : in)) : PAD;
+                    if (PACKED) cB[rr] = ((unsigned)in < (unsigned)mB) ? (int)__ldg(qB + (REV ? mB - 1 - in : in)) : PAD;
                 }
                 // left border: from lane l-1 (previous step) or, for lane 0, the block border
-                uint32_t hl = shfl_up_g(hlast, G);
-                uint32_t fh = shfl_up_g(fout, G);
-                if (l == 0) {
-                    hl = 0; fh = 0;
-                    if (b > 0 && i >= 0 && i < bvalid) { uint2 v = mybound[i]; hl = v.x; fh = v.y; }
+                uint32_t hl[R], fh[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    if (a.dbg & 2) { hl[rr] = hlast[rr]; fh[rr] = fout[rr]; }
+                    else { hl[rr] = shfl_up_g(hlast[rr], G); fh[rr] = shfl_up_g(fout[rr], G); }
+                    if (l == 0) { hl[rr] = 0; fh[rr] = 0; }
                 }
-                uint32_t hdiag = hl_prev;
-                hl_prev = hl;
-                uint32_t stepmax = 0;
+                if (b > 0) {
+                    if (l == 0) {
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr)
+                            if ((unsigned)(r0 + rr) < (unsigned)bvalid) { uint2 v = mybound[r0 + rr]; hl[rr] = v.x; fh[rr] = v.y; }
+                    }
+                }
+                uint32_t hdiag[R];
+                hdiag[0] = hl_prev;
+#pragma unroll
+                for (int rr = 1; rr < R; ++rr) hdiag[rr] = hl[rr - 1];
+                hl_prev = hl[R - 1];
+                uint32_t stepmax[R];
+                uint32_t Hrow[R > 1 ? R - 1 : 1][K];   // H of the non-final rows (kept for snapshots)
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) stepmax[rr] = 0;
 #pragma unroll
                 for (int p = 0; p < K; ++p) {
-                    uint32_t sc;
-                    switch (p & 3) {
-                        case 0: sc = O::template mix<0>(wA[p >> 2], wB[p >> 2]); break;
-                        case 1: sc = O::template mix<1>(wA[p >> 2], wB[p >> 2]); break;
-                        case 2: sc = O::template mix<2>(wA[p >> 2], wB[p >> 2]); break;
-                        default: sc = O::template mix<3>(wA[p >> 2], wB[p >> 2]); break;
+                    uint32_t up = H[p];
+                    uint32_t eprev = E[p];
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        uint32_t sc;
+                        switch (p & 3) {
+                            case 0: sc = O::template mix<0>(wA[rr][p >> 2], wB[rr][p >> 2]); break;
+                            case 1: sc = O::template mix<1>(wA[rr][p >> 2], wB[rr][p >> 2]); break;
+                            case 2: sc = O::template mix<2>(wA[rr][p >> 2], wB[rr][p >> 2]); break;
+                            default: sc = O::template mix<3>(wA[rr][p >> 2], wB[rr][p >> 2]); break;
+                        }
+                        const uint32_t eh = O::addmax(eprev, NEG_GE, up);
+                        uint32_t hn;
+                        if (LONG) {
+                            const uint32_t mg = O::max3(eh, fh[rr], GOE) - GOE;
+                            hn = O::addmax(hdiag[rr], sc, mg);
+                            fh[rr] = O::addmax(fh[rr], NEG_GE, hn);
+                        } else {
+                            const uint32_t eg = O::max2(eh, GOE) - GOE;
+                            const uint32_t u = O::addmax(hdiag[rr], sc, eg);
+                            hn = O::addmax(fh[rr], NEG_GOE, u);
+                            fh[rr] = O::addmax(fh[rr], NEG_GE, u);
+                        }
+                        hdiag[rr] = up;
+                        up = hn;
+                        eprev = eh;
+                        if (rr < R - 1) Hrow[rr][p] = hn;
+                        if (p & 1) {
+                            const uint32_t prevh = (rr < R - 1) ? Hrow[rr][p - 1] : H[p - 1];
+                            stepmax[rr] = O::max3(stepmax[rr], hn, prevh);
+                        } else if (p == K - 1) stepmax[rr] = O::max2(stepmax[rr], hn);
                     }
-                    const uint32_t hup = H[p];
-                    const uint32_t eh = O::addmax(E[p], NEG_GE, hup);
-                    E[p] = eh;
-                    const uint32_t eg = O::max2(eh, GOE) - GOE;
-                    const uint32_t u = O::addmax(hdiag, sc, eg);
-                    const uint32_t hn = O::addmax(fh, NEG_GOE, u);
-                    fh = O::addmax(fh, NEG_GE, u);
-                    hdiag = hup;
-                    H[p] = hn;
-                    if (p & 1) stepmax = O::max3(stepmax, hn, H[p - 1]);
-                    else if (p == K - 1) stepmax = O::max2(stepmax, hn);
+                    H[p] = up;
+                    E[p] = eprev;
                 }
-                hlast = H[K - 1];
-                fout = fh;
-                if (nblocks > 1 && l == G - 1 && b + 1 < nblocks && i >= 0 && i < mw)
-                    mybound[i] = make_uint2(hlast, fout);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    hlast[rr] = (rr < R - 1) ? Hrow[rr][K - 1] : H[K - 1];
+                    fout[rr] = fh[rr];
+                }
+                if (nblocks > 1) {
+                    if (l == G - 1 && b + 1 < nblocks) {
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr)
+                            if ((unsigned)(r0 + rr) < (unsigned)mw) mybound[r0 + rr] = make_uint2(hlast[rr], fout[rr]);
+                    }
+                }
 
-                // ---- maximum tracking ----
-                uint32_t nbst = O::max2(best, stepmax);
-                uint32_t ch = nbst ^ best;
-                if (b > 0) {   // a later block may hold an equal maximum on an earlier row
-                    if (O::hi(stepmax) == O::hi(best) && i < browA && O::hi(best) > 0) ch |= PACKED ? 0xffff0000u : 1u;
-                    if (PACKED && O::lo(stepmax) == O::lo(best) && i < browB && O::lo(best) > 0) ch |= 0x0000ffffu;
-                }
-                best = nbst;
-                if (ch) {
-                    if (!PACKED || (ch & 0xffff0000u)) {
-                        browA = i; blkA = b;
+                // ---- maximum tracking: one decision per step; among the R rows the first one that
+                // reaches the step's final value wins (row-major-first), and only that row's strip is
+                // snapshotted ----
+                if (a.dbg & 1) { best = O::max2(best, stepmax[0]); if (R > 1) best = O::max2(best, stepmax[R - 1]); }
+                else {
+                    uint32_t fin = best;
 #pragma unroll
-                        for (int p = 0; p < K; ++p) snapA[p] = H[p];
+                    for (int rr = 0; rr < R; ++rr) fin = O::max2(fin, stepmax[rr]);
+                    uint32_t ch = fin ^ best;
+                    if (b > 0) {   // a later block may hold an equal maximum on an earlier row
+#pragma unroll
+                        for (int rr = R - 1; rr >= 0; --rr) {
+                            if (O::hi(stepmax[rr]) == O::hi(best) && r0 + rr < browA && O::hi(best) > 0) ch |= PACKED ? 0xffff0000u : 1u;
+                            if (PACKED && O::lo(stepmax[rr]) == O::lo(best) && r0 + rr < browB && O::lo(best) > 0) ch |= 0x0000ffffu;
+                        }
                     }
-                    if (PACKED && (ch & 0x0000ffffu)) {
-                        browB = i; blkB = b;
+                    best = fin;
+                    if (ch) {
+                        constexpr uint32_t HI = PACKED ? 0xffff0000u : 0xffffffffu;
+                        if (ch & HI) {
+                            int src = R - 1;
 #pragma unroll
-                        for (int p = 0; p < K; ++p) snapB[p] = H[p];
+                            for (int rr = R - 2; rr >= 0; --rr) if (((stepmax[rr] ^ fin) & HI) == 0) src = rr;
+                            browA = r0 + src; blkA = b;
+#pragma unroll
+                            for (int rr = 0; rr < R; ++rr)
+                                if (src == rr) {
+#pragma unroll
+                                    for (int p = 0; p < K; ++p) snapA[p] = (rr < R - 1) ? Hrow[rr][p] : H[p];
+                                }
+                        }
+                        if (PACKED && (ch & 0x0000ffffu)) {
+                            int src = R - 1;
+#pragma unroll
+                            for (int rr = R - 2; rr >= 0; --rr) if (((stepmax[rr] ^ fin) & 0x0000ffffu) == 0) src = rr;
+                            browB = r0 + src; blkB = b;
+#pragma unroll
+                            for (int rr = 0; rr < R; ++rr)
+                                if (src == rr) {
+#pragma unroll
+                                    for (int p = 0; p < K; ++p) snapB[p] = (rr < R - 1) ? Hrow[rr][p] : H[p];
+                                }
+                        }
                     }
                 }
                 if (REV) {
@@ -318,10 +400,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 }
             }
             if (REV) {
-                swept += (unsigned long long)min(slimit, mw) * (unsigned long long)min(nw - b * W, W);
-                if (armed) rowcap = min(rowcap, slimit - (G - 1));
-                bvalid = min(mw, slimit - (G - 1));
+                swept += (unsigned long long)min((slimit - (G - 1)) * R, mw) * (unsigned long long)min(nw - b * W, W);
+                if (armed) rowcap = min(rowcap, (slimit - (G - 1)) * R);
             }
+            bvalid = min(mw, (slimit - (G - 1)) * R);
             __syncwarp();
         }
 

@@ -7,7 +7,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 runs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ctx = Context(0)
 q, qoff, t, toff = workloads.sw_microbench_pairs(n)
-job = sw.SwJob(ctx, q, qoff, t, toff, seqcodec.protein_params(), coords=True)
+coords = (len(sys.argv) <= 3 or sys.argv[3] != "0")
+job = sw.SwJob(ctx, q, qoff, t, toff, seqcodec.protein_params(), coords=coords)
 for _ in range(runs):
     st = job.run()
 print(st)
