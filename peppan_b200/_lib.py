@@ -48,6 +48,8 @@ def load():
     lib.pb_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     lib.pb_sw_batch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ScoreParams), vp, vp, vp, vp, vp,
                                 C.POINTER(SwStats)]
+    lib.pb_sw_align_batch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ScoreParams), vp, vp, vp, vp, vp, vp, vp,
+                                      C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(SwStats)]
     lib.pb_sw_job_create.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ScoreParams), C.c_int, C.POINTER(vp)]
     lib.pb_sw_job_run.argtypes = [vp, vp, C.POINTER(SwStats)]
     lib.pb_sw_job_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp]

@@ -1,7 +1,6 @@
 // Host side of the batched Smith-Waterman path: descriptor preparation and work ordering on the
 // device (no host-side sorting), kernel launches, the job API and pb_sw_batch.
-#include "pb_common.h"
-#include "pb_sw_kernel.cuh"
+#include "pb_sw_job.h"
 #include <cub/cub.cuh>
 #include <climits>
 #include <algorithm>
@@ -13,11 +12,6 @@ using namespace pbsw;
 namespace {
 
 constexpr int PAD_SCORE = -16;
-
-// Kernel shapes: G lanes per task, K columns per lane, WARPS per (persistent, 1/SM) block.
-struct SwConfig { int G, K, R, LONG, WARPS; };
-constexpr SwConfig SW_CONFIGS[] = { {16, 19, 2, 1, 8}, {16, 19, 1, 0, 8}, {16, 19, 2, 0, 8}, {16, 19, 1, 1, 8},
-                                    {8, 19, 2, 0, 8}, {8, 19, 2, 1, 8}, {8, 38, 1, 0, 4} };
 
 SwConfig sw_pick_config()
 {
@@ -133,23 +127,6 @@ cudaError_t sw_dispatch(const SwConfig& c, const SwArgs& a, int grid, size_t sme
 }
 
 }  // namespace
-
-// ---- job ------------------------------------------------------------------------------------
-
-struct pb_sw_job {
-    int64_t npairs = 0;
-    int want_coords = 0;
-    pb_score_params params;
-    int maxscore = 1;
-    SwConfig cfg;
-    DevBuf q, t, qoff, toff, matrix;
-    DevBuf desc, desc_rev, keys, keys_sorted, ids, perm, perm_rev, meta, cub_tmp;
-    DevBuf score, qe, te, qs, ts, boundary, cells;
-    size_t cub_bytes = 0;
-    int n32 = 0;
-    int64_t qbytes = 0, tbytes = 0;
-    double fwd_cells = 0;
-};
 
 static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, const int* perm, int* launches)
 {

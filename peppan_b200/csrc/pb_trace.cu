@@ -1,0 +1,360 @@
+// Traceback (CIGAR) for aligned pairs: pb_sw_align_batch.
+//
+// After the forward and reverse passes the alignment box [qs..qe] x [ts..te] of every pair is
+// known.  The oracle defines the path as the traceback of the REVERSE DP (oracle/pb_oracle.c), so
+// this file recomputes that DP restricted to the box (a prefix rectangle of the reverse DP, hence
+// identical values), records 4 direction bits per cell, and walks them:
+//   bits 0-1  H source: 0 stop (H == 0), 1 diagonal, 2 E, 3 F  (priority diagonal > E > F)
+//   bit  2    E came from H (gap opened here; preferred over extension on ties)
+//   bit  3    F came from H
+// The DP kernel uses the same systolic strip layout as the score kernel (group of G lanes, K
+// columns per lane in registers, rows streamed, profile in shared memory), in s32, one pair per
+// group.  Direction words are written step-major ([block][step][lane][word]) so that every step
+// of a group is one contiguous, coalesced store.  A second kernel (one thread per pair) walks the
+// directions from the start cell to the origin, which emits the ops in alignment order.
+#include "pb_sw_job.h"
+#include <algorithm>
+#include <vector>
+#include <memory>
+
+using namespace pbsw;
+
+namespace {
+
+constexpr int TR_G = 16, TR_K = 16, TR_WARPS = 8;
+constexpr int TR_W = TR_G * TR_K;
+constexpr int TR_KW8 = TR_K / 8;        // direction words per lane per step
+constexpr int PAD_SCORE = -16;
+
+struct TraceDesc {
+    long long qoff, toff;   // start of the box in the code arrays
+    long long doff;         // offset (words) of this pair's direction block
+    int M, N;               // box rows / columns
+    int id;                 // pair id
+    int pad;
+};
+
+struct TraceArgs {
+    const uint8_t* q;
+    const uint8_t* t;
+    const TraceDesc* desc;
+    int count;
+    int* counter;
+    const int8_t* matrix;
+    int nsym, go, ge;
+    uint32_t* dir;
+    uint2* boundary;
+    int bstride;
+};
+
+template <int G, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs a)
+{
+    constexpr int KW = (K + 3) / 4, KP = KW * 4, NG = 32 / G, W = G * K, KW8 = K / 8;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) uint8_t smem[];
+    int8_t* smat = reinterpret_cast<int8_t*>(smem);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smat)[i] = reinterpret_cast<const uint32_t*>(a.matrix)[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / G, l = lane % G;
+    const int nsym = a.nsym, PAD = nsym - 1, rowBytes = G * KP;
+    uint8_t* prof = smem + 1024 + (size_t)(warp * NG + g) * nsym * rowBytes;
+    const int gwarp = blockIdx.x * WARPS + warp;
+    uint2* mybound = a.boundary ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
+    const int ge = a.ge, goe = a.go + a.ge;
+
+    for (;;) {
+        int bundle = 0;
+        if (lane == 0) bundle = atomicAdd(a.counter, 1);
+        bundle = __shfl_sync(FULL, bundle, 0);
+        if (bundle * NG >= a.count) break;
+        const int task = bundle * NG + g;
+        int M = 0, N = 0;
+        const uint8_t *qb = a.q, *tb = a.t;
+        long long doff = 0;
+        if (task < a.count) {
+            TraceDesc d = a.desc[task];
+            M = d.M; N = d.N; qb = a.q + d.qoff; tb = a.t + d.toff; doff = d.doff;
+        }
+        int mw = M, nw = N;
+#pragma unroll
+        for (int o = 16; o >= G; o >>= 1) {
+            mw = max(mw, __shfl_xor_sync(FULL, mw, o));
+            nw = max(nw, __shfl_xor_sync(FULL, nw, o));
+        }
+        const int nblocks = (nw + W - 1) / W;
+        const int nsteps_own = M + G - 1;
+
+        for (int b = 0; b < nblocks; ++b) {
+            const int col0 = b * W + l * K;
+            {
+                int tc[K];
+#pragma unroll
+                for (int p = 0; p < K; ++p) { int j = col0 + p; tc[p] = (j < N) ? (int)__ldg(tb + (N - 1 - j)) : PAD; }
+                for (int c = 0; c < nsym; ++c) {
+                    const int8_t* mrow = smat + c * 32;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(prof + c * rowBytes + l * KP);
+#pragma unroll
+                    for (int w = 0; w < KW; ++w) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) { int p = w * 4 + x; if (p < K) v |= ((uint32_t)(uint8_t)mrow[tc[p]]) << (8 * x); }
+                        dst[w] = v;
+                    }
+                }
+            }
+            __syncwarp();
+            int H[K], E[K];     // E holds E + goe, as in the score kernel
+#pragma unroll
+            for (int p = 0; p < K; ++p) { H[p] = 0; E[p] = 0; }
+            int hlast = 0, fout = 0, hl_prev = 0;
+            const int slimit = mw + G - 1;
+            const bool in_block = (b * W < N);       // this pair has real columns in this block
+            uint32_t* dbase = a.dir + doff + (size_t)b * nsteps_own * G * KW8;
+            int i0 = -l;
+            int cq = ((unsigned)i0 < (unsigned)M) ? (int)__ldg(qb + (M - 1 - i0)) : PAD;
+            for (int s = 0; s < slimit; ++s) {
+                const int i = s - l;
+                uint32_t w[KW];
+                const uint32_t* r = reinterpret_cast<const uint32_t*>(prof + cq * rowBytes + l * KP);
+#pragma unroll
+                for (int x = 0; x < KW; ++x) w[x] = r[x];
+                { int in = i + 1; cq = ((unsigned)in < (unsigned)M) ? (int)__ldg(qb + (M - 1 - in)) : PAD; }
+                int hl = __shfl_up_sync(FULL, hlast, 1, G), fh = __shfl_up_sync(FULL, fout, 1, G);
+                if (l == 0) {
+                    hl = 0; fh = 0;
+                    if (b > 0 && (unsigned)i < (unsigned)mw) { uint2 v = mybound[i]; hl = (int)v.x; fh = (int)v.y; }
+                }
+                int hdiag = hl_prev; hl_prev = hl;
+                int hleft = hl;
+                uint32_t codes[KW8];
+#pragma unroll
+                for (int x = 0; x < KW8; ++x) codes[x] = 0;
+#pragma unroll
+                for (int p = 0; p < K; ++p) {
+                    const int sc = (int)(int8_t)((w[p >> 2] >> (8 * (p & 3))) & 0xff);
+                    const int hup = H[p];
+                    // F + goe of this cell from the cell to the left; E + goe from the cell above
+                    const int fext = fh - ge;
+                    const int fopen = (hleft >= fext);            // tie -> opened here
+                    fh = max(fext, hleft);
+                    const int eext = E[p] - ge;
+                    const int eopen = (hup >= eext);
+                    const int eh = max(eext, hup);
+                    E[p] = eh;
+                    const int d = hdiag + sc, et = eh - goe, ft = fh - goe;
+                    const int hn = max(max(0, d), max(et, ft));
+                    int code = (hn == 0) ? 0 : ((hn == d) ? 1 : ((hn == et) ? 2 : 3));
+                    code |= (eopen << 2) | (fopen << 3);
+                    codes[p >> 3] |= (uint32_t)code << (4 * (p & 7));
+                    hdiag = hup; H[p] = hn; hleft = hn;
+                }
+                hlast = hleft; fout = fh;
+                if (nblocks > 1 && l == G - 1 && b + 1 < nblocks && (unsigned)i < (unsigned)mw) mybound[i] = make_uint2((uint32_t)hlast, (uint32_t)fout);
+                if (in_block && s < nsteps_own) {
+                    uint32_t* dst = dbase + ((size_t)s * G + l) * KW8;
+#pragma unroll
+                    for (int x = 0; x < KW8; ++x) dst[x] = codes[x];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// One thread per pair: walk the direction words from the start cell (M-1, N-1 in reverse
+// coordinates) to the origin.  WRITE = false counts ops and match statistics, WRITE = true
+// stores the run-length ops at ops[ooff[pair]].
+template <bool WRITE>
+__global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDesc* desc, int count, const uint32_t* dir,
+                               int* nops, int* counts, const long long* ooff, uint32_t* ops)
+{
+    constexpr int G = TR_G, K = TR_K, W = TR_W, KW8 = TR_KW8;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= count) return;
+    const TraceDesc d = desc[x];
+    const uint8_t* qb = q + d.qoff; const uint8_t* tb = t + d.toff;
+    const int nsteps = d.M + G - 1;
+    const uint32_t* base = dir + d.doff;
+    int i = d.M - 1, j = d.N - 1, state = 0;
+    int cur = -1, len = 0, n = 0, nm = 0, nx = 0, ngo = 0, ngb = 0;
+    uint32_t* out = WRITE ? ops + ooff[x] : nullptr;
+    while (i >= 0 && j >= 0) {
+        const int b = j / W, jj = j - b * W, l = jj / K, p = jj - l * K;
+        const uint32_t wv = base[((size_t)b * nsteps + (i + l)) * G * KW8 + (size_t)l * KW8 + (p >> 3)];
+        const int code = (wv >> (4 * (p & 7))) & 15;
+        int op;
+        if (state == 0) {
+            const int h = code & 3;
+            if (h == 0) break;
+            if (h == 1) {
+                op = 0;
+                if (!WRITE) { if (qb[d.M - 1 - i] == tb[d.N - 1 - j]) ++nm; else ++nx; }
+                --i; --j;
+            } else { state = (h == 2) ? 1 : 2; continue; }
+        } else if (state == 1) {
+            op = 1; if (cur != 1) ++ngo; ++ngb;
+            if (code & 4) state = 0;
+            --i;
+        } else {
+            op = 2; if (cur != 2) ++ngo; ++ngb;
+            if (code & 8) state = 0;
+            --j;
+        }
+        if (op == cur) ++len;
+        else {
+            if (cur >= 0) { if (WRITE) out[n] = ((uint32_t)len << 2) | (uint32_t)cur; ++n; }
+            cur = op; len = 1;
+        }
+    }
+    if (cur >= 0) { if (WRITE) out[n] = ((uint32_t)len << 2) | (uint32_t)cur; ++n; }
+    if (!WRITE) {
+        nops[x] = n;
+        counts[4 * x + 0] = nm; counts[4 * x + 1] = nx; counts[4 * x + 2] = ngo; counts[4 * x + 3] = ngb;
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_sw_align_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t, const int64_t* toff,
+                                 int64_t npairs, const pb_score_params* params, int32_t* score, int32_t* qs, int32_t* qe,
+                                 int32_t* ts, int32_t* te, int32_t* counts, int64_t* cigar_off, uint32_t** cigar_ops,
+                                 pb_sw_stats* stats)
+{
+    if (!ctx) return PB_ERR_ARG;
+    if (!score || !qs || !qe || !ts || !te || !cigar_off || !cigar_ops) {
+        pb_set_error(ctx, "pb_sw_align_batch: score, coordinates, cigar_off and cigar_ops are required"); return PB_ERR_ARG;
+    }
+    *cigar_ops = nullptr;
+    pb_sw_job* J = nullptr;
+    int rc = pb_sw_job_create(ctx, q, qoff, t, toff, npairs, params, 1, &J);
+    if (rc) return rc;
+    std::unique_ptr<pb_sw_job> guard(J);
+    pb_sw_stats st; memset(&st, 0, sizeof(st));
+    rc = pb_sw_job_run(ctx, J, &st);
+    if (rc) return rc;
+    rc = pb_sw_job_fetch(ctx, J, score, qs, qe, ts, te);
+    if (rc) return rc;
+
+    // ---- traceback over the aligned pairs, in chunks bounded by the direction-buffer budget ----
+    std::vector<TraceDesc> all;
+    all.reserve((size_t)npairs);
+    for (int64_t p = 0; p < npairs; ++p) {
+        if (score[p] <= 0) continue;
+        TraceDesc d;
+        d.qoff = qoff[p] + qs[p]; d.toff = toff[p] + ts[p];
+        d.M = qe[p] - qs[p] + 1; d.N = te[p] - ts[p] + 1; d.id = (int)p; d.pad = 0; d.doff = 0;
+        all.push_back(d);
+    }
+    // longest boxes first: similar shapes share a warp, and the dynamic scheduler packs well
+    std::sort(all.begin(), all.end(), [](const TraceDesc& a, const TraceDesc& b) {
+        int ba = (a.N + TR_W - 1) / TR_W, bb = (b.N + TR_W - 1) / TR_W;
+        if (ba != bb) return ba > bb;
+        if (a.M != b.M) return a.M > b.M;
+        return a.id < b.id;
+    });
+    std::vector<int> h_nops((size_t)npairs, 0);
+    std::vector<int> h_counts((size_t)npairs * 4, 0);
+    const size_t budget_words = (size_t)std::min<int64_t>(ctx->hbm_bytes / 8, (int64_t)12 << 30) / 4;
+    const int grid = ctx->sm_count;
+    const size_t smem = 1024 + (size_t)TR_WARPS * (32 / TR_G) * params->nsym * TR_G * (((TR_K + 3) / 4) * 4);
+    auto kern = sw_trace_kernel<TR_G, TR_K, TR_WARPS>;
+    PB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float ms_trace = 0;
+    int launches = 0;
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+
+    struct Chunk { size_t first, count; size_t words; int maxM; int maxNB; };
+    std::vector<Chunk> chunks;
+    {
+        size_t i = 0;
+        while (i < all.size()) {
+            Chunk c{i, 0, 0, 0, 0};
+            while (i < all.size()) {
+                TraceDesc& d = all[i];
+                int nb = (d.N + TR_W - 1) / TR_W;
+                size_t w = (size_t)nb * (d.M + TR_G - 1) * TR_G * TR_KW8;
+                if (w > budget_words) { pb_set_error(ctx, "pb_sw_align_batch: a single alignment box needs %zu direction words", w); return PB_ERR_LIMIT; }
+                if (c.count > 0 && c.words + w > budget_words) break;
+                d.doff = (long long)c.words;
+                c.words += w; c.count++; c.maxM = std::max(c.maxM, d.M); c.maxNB = std::max(c.maxNB, nb);
+                ++i;
+            }
+            chunks.push_back(c);
+        }
+    }
+    // cigar ops: first pass counts, then ops are written per chunk into a device buffer and copied out
+    std::vector<std::vector<uint32_t>> chunk_ops(chunks.size());
+    std::vector<std::vector<long long>> chunk_ooff(chunks.size());
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk& c = chunks[ci];
+        DevBuf ddesc, ddir, dnops, dcounts, dooff, dops, dbound;
+        PB_CUDA(ctx, ddesc.alloc(c.count * sizeof(TraceDesc), ctx->stream));
+        PB_CUDA(ctx, ddir.alloc(std::max<size_t>(c.words, 4) * 4, ctx->stream));
+        PB_CUDA(ctx, dnops.alloc(c.count * 4, ctx->stream));
+        PB_CUDA(ctx, dcounts.alloc(c.count * 16, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(ddesc.p, all.data() + c.first, c.count * sizeof(TraceDesc), cudaMemcpyHostToDevice, ctx->stream));
+        int bstride = c.maxNB > 1 ? ((c.maxM + 63) / 64) * 64 : 0;
+        if (bstride) PB_CUDA(ctx, dbound.alloc((size_t)grid * TR_WARPS * (32 / TR_G) * bstride * sizeof(uint2), ctx->stream));
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
+        TraceArgs a;
+        a.q = J->q.as<uint8_t>(); a.t = J->t.as<uint8_t>(); a.desc = ddesc.as<TraceDesc>(); a.count = (int)c.count;
+        a.counter = ctx->d_counter; a.matrix = J->matrix.as<int8_t>(); a.nsym = params->nsym; a.go = params->gap_open; a.ge = params->gap_extend;
+        a.dir = ddir.as<uint32_t>(); a.boundary = bstride ? dbound.as<uint2>() : nullptr; a.bstride = bstride;
+        kern<<<grid, TR_WARPS * 32, smem, ctx->stream>>>(a);
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        const int tb = 128, gb = (int)((c.count + tb - 1) / tb);
+        sw_walk_kernel<false><<<gb, tb, 0, ctx->stream>>>(a.q, a.t, a.desc, a.count, a.dir, dnops.as<int>(), dcounts.as<int>(), nullptr, nullptr);
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        std::vector<int> nops(c.count), cnt(c.count * 4);
+        PB_CUDA(ctx, cudaMemcpyAsync(nops.data(), dnops.p, c.count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(cnt.data(), dcounts.p, c.count * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<long long>& ooff = chunk_ooff[ci];
+        ooff.resize(c.count + 1);
+        long long tot = 0;
+        for (size_t k = 0; k < c.count; ++k) {
+            ooff[k] = tot; tot += nops[k];
+            int id = all[c.first + k].id;
+            h_nops[id] = nops[k];
+            memcpy(&h_counts[(size_t)id * 4], &cnt[k * 4], 16);
+        }
+        ooff[c.count] = tot;
+        PB_CUDA(ctx, dooff.alloc((c.count + 1) * 8, ctx->stream));
+        PB_CUDA(ctx, dops.alloc(std::max<long long>(tot, 1) * 4, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(dooff.p, ooff.data(), (c.count + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        sw_walk_kernel<true><<<gb, tb, 0, ctx->stream>>>(a.q, a.t, a.desc, a.count, a.dir, nullptr, nullptr, dooff.as<long long>(), dops.as<uint32_t>());
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        chunk_ops[ci].resize((size_t)tot);
+        if (tot) PB_CUDA(ctx, cudaMemcpyAsync(chunk_ops[ci].data(), dops.p, (size_t)tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    PB_CUDA(ctx, cudaEventElapsedTime(&ms_trace, ctx->ev[0], ctx->ev[1]));
+
+    // ---- assemble per-pair output in input order ----
+    int64_t total = 0;
+    for (int64_t p = 0; p < npairs; ++p) { cigar_off[p] = total; total += h_nops[p]; }
+    cigar_off[npairs] = total;
+    uint32_t* ops = (uint32_t*)malloc((size_t)std::max<int64_t>(total, 1) * 4);
+    if (!ops) { pb_set_error(ctx, "pb_sw_align_batch: out of host memory"); return PB_ERR_NOMEM; }
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk& c = chunks[ci];
+        for (size_t k = 0; k < c.count; ++k) {
+            int id = all[c.first + k].id;
+            long long o = chunk_ooff[ci][k], n = chunk_ooff[ci][k + 1] - o;
+            if (n) memcpy(ops + cigar_off[id], chunk_ops[ci].data() + o, (size_t)n * 4);
+        }
+    }
+    *cigar_ops = ops;
+    if (counts) memcpy(counts, h_counts.data(), (size_t)npairs * 16);
+    if (stats) {
+        *stats = st;
+        stats->ms_traceback = ms_trace;
+        stats->ms_total_device = st.ms_total_device + ms_trace;
+        stats->kernel_launches = st.kernel_launches + launches;
+    }
+    return PB_OK;
+}

@@ -30,6 +30,33 @@ def sw_batch(ctx, q, qoff, t, toff, params, coords=True):
     return out, st.as_dict()
 
 
+def sw_align_batch(ctx, q, qoff, t, toff, params):
+    """sw_batch plus traceback.  Adds 'counts' (n,4: matches, mismatches, gap runs, gap bases),
+    'cigar_off' (n+1) and 'cigar_ops' (uint32, (len<<2)|{0:M,1:I,2:D}) to the result dict."""
+    n = len(qoff) - 1
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
+    qoff = np.ascontiguousarray(qoff, dtype=np.int64); toff = np.ascontiguousarray(toff, dtype=np.int64)
+    out = {k: np.full(n, -1, dtype=np.int32) for k in ('score', 'qs', 'qe', 'ts', 'te')}
+    out['counts'] = np.zeros((n, 4), dtype=np.int32)
+    out['cigar_off'] = np.zeros(n + 1, dtype=np.int64)
+    ops = C.POINTER(C.c_uint32)()
+    st = SwStats()
+    rc = ctx.lib.pb_sw_align_batch(ctx.h, ptr(q), ptr(qoff), ptr(t), ptr(toff), n, C.byref(params),
+                                   ptr(out['score']), ptr(out['qs']), ptr(out['qe']), ptr(out['ts']), ptr(out['te']),
+                                   ptr(out['counts']), ptr(out['cigar_off']), C.byref(ops), C.byref(st))
+    ctx.check(rc, 'pb_sw_align_batch')
+    total = int(out['cigar_off'][-1])
+    try:
+        out['cigar_ops'] = np.ctypeslib.as_array(ops, shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+    finally:
+        ctx.lib.pb_free(ops)
+    return out, st.as_dict()
+
+
+def cigar_str(ops):
+    return ''.join('%d%s' % (int(o) >> 2, 'MID'[int(o) & 3]) for o in ops)
+
+
 class SwJob(object):
     """Device-resident batch: upload once, run the kernels any number of times, fetch results."""
 

@@ -77,3 +77,38 @@ def test_config2_sample(ctx, oracle):
     for k in ('score', 'qe', 'te', 'qs', 'ts'):
         assert np.array_equal(out[k], ref[k]), k
     assert st['cells'] == 4096 * 300 * 300
+
+
+def _compare_align(ctx, oracle, qs, ts, params, mat, go, ge):
+    q, qoff = sw.concat(qs); t, toff = sw.concat(ts)
+    out, st = sw.sw_align_batch(ctx, q, qoff, t, toff, params)
+    ref, cigs = oracle.sw_batch(q, qoff, t, toff, mat, go, ge, with_cigar=True, nthreads=8)
+    for k in ('score', 'qe', 'te', 'qs', 'ts'):
+        assert np.array_equal(out[k], ref[k]), k
+    for p in range(len(qs)):
+        got = out['cigar_ops'][out['cigar_off'][p]:out['cigar_off'][p + 1]]
+        assert np.array_equal(got, cigs[p]), 'cigar of pair %d: gpu %s oracle %s' % (p, sw.cigar_str(got), sw.cigar_str(cigs[p]))
+        assert out['counts'][p].tolist() == [ref['n_match'][p], ref['n_mismatch'][p], ref['n_gapopen'][p], ref['n_gapbases'][p]]
+    return out, st
+
+
+def test_traceback_cigars_protein(ctx, oracle):
+    qs, ts = workloads.random_pairs(1500, seed=21, max_len=400, related=0.8)
+    _compare_align(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
+
+
+def test_traceback_cigars_nucleotide_wide_boxes(ctx, oracle):
+    # boxes wider than one trace block (256 columns) and gap-rich alignments
+    qs, ts = workloads.random_pairs(300, seed=22, nsym_real=4, min_len=100, max_len=1500, related=0.9)
+    _compare_align(ctx, oracle, qs, ts, seqcodec.nt_params(), seqcodec.nt_matrix().reshape(-1), 6, 2)
+
+
+def test_traceback_config2_sample_10k(ctx, oracle):
+    # CIGAR checked on a 10k sample of the micro-bench workload
+    q, qoff, t, toff = workloads.sw_microbench_pairs(10000)
+    out, st = sw.sw_align_batch(ctx, q, qoff, t, toff, seqcodec.protein_params())
+    ref, cigs = oracle.sw_batch(q, qoff, t, toff, _prot_mat_with_pad(), 11, 1, with_cigar=True, nthreads=8)
+    assert np.array_equal(out['score'], ref['score'])
+    flat = np.concatenate(cigs) if len(cigs) else np.zeros(0, np.uint32)
+    assert np.array_equal(out['cigar_ops'], flat)
+    assert np.array_equal(out['cigar_off'][1:], np.cumsum([len(c) for c in cigs]))
