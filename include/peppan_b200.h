@@ -103,6 +103,79 @@ int  pb_sw_job_fetch(pb_ctx* ctx, pb_sw_job* job, int32_t* score, int32_t* qs, i
                      int32_t* ts, int32_t* te);
 void pb_sw_job_destroy(pb_ctx* ctx, pb_sw_job* job);
 
+/* ---- similarity search (seed -> ungapped X-drop -> windowed Smith-Waterman with traceback) ---- */
+/* A set of sequences: concatenated bytes + n+1 offsets.  For pb_search / pb_cluster the bytes are
+ * ASCII nucleotides exactly as readFastq returns them (upper-cased, modules/configure.py:118-150);
+ * the library encodes, reverse-complements and translates on the device. */
+typedef struct {
+    const uint8_t* residues;
+    const int64_t* offsets;      /* n + 1 entries */
+    int64_t        n;
+} pb_seqset;
+
+/* Which reference tool the call stands in for (the `tools` dict of RunBlast.run,
+ * modules/uberBlast.py:327). */
+typedef enum {
+    PB_MODE_NT = 1,              /* runBlast: blastn, nt vs nt, both strands (:482-509, flags :294) */
+    PB_MODE_PROT6 = 2,           /* runDiamond: best forward frame of each query vs 6 frames (:513-560) */
+    PB_MODE_PROT3_SELF = 3       /* runDiamondSELF: vs the 3 forward frames, no self hits, k=200 (:511-512) */
+} pb_search_mode;
+
+typedef struct {
+    int32_t mode;                /* pb_search_mode */
+    int32_t gtable;              /* 11 (default) or 4: --gtable of uberBlast (:573) */
+    float   min_id;              /* --min_id: hits below are dropped (:283, :39) */
+    float   min_cov;             /* --min_cov: minimum aligned query span in nt (:283, :30) */
+    float   min_ratio;           /* --min_ratio: minimum aligned fraction of the query (:283, :31-32) */
+    int32_t max_hits_per_query;  /* 0 = mode default (blastn -num_alignments 1000; diamond -k 10 x 5 shards / 200) */
+    int32_t reserved[6];
+} pb_search_params;
+
+/* One HSP.  Coordinates are 1-based inclusive nucleotide positions as in the BLAST-tabular
+ * record the reference builds; s_start > s_end means minus strand. */
+typedef struct {
+    int32_t q_id, s_id;          /* indices into the query / target seqsets */
+    int32_t q_start, q_end, s_start, s_end;
+    int32_t aln_len, mismatch, gapopen;
+    int32_t raw_score;
+    int32_t q_len, s_len;
+    float   identity;            /* blastn: matches / alignment columns; protein: 1 - round(3*NM/cl, 3) (:38) */
+    float   evalue;
+    int32_t frame;               /* 0 for nucleotide hits, else target frame 1..6 */
+    uint32_t cigar_off, cigar_n; /* ops in pb_hits.cigar, nt units, (len<<2)|{0:M,1:I,2:D} */
+} pb_hit;
+
+typedef struct {
+    pb_hit*   hits;              /* library-allocated; release with pb_free_hits */
+    int64_t   n_hits;
+    uint32_t* cigar;
+    int64_t   n_cigar;
+    int64_t*  rank_offsets;      /* after pb_allgather_hits: world+1 offsets into hits (rank r owns [r, r+1)); else NULL */
+    int64_t   n_ranks;
+} pb_hits;
+
+typedef struct {
+    int64_t n_query_kmers, n_seed_hits, n_ungapped, n_windows, n_hits;
+    double  sw_cells;
+    float   ms_encode, ms_index, ms_seed, ms_sw, ms_trace, ms_total;
+    int64_t algo_bytes_seed;     /* R_nt + 9*R_q + 16*N_seed */
+    int32_t kernel_launches;
+    int32_t reserved;
+} pb_search_stats;
+
+/* Replaces tools[method](ref, qry) of RunBlast.run (modules/uberBlast.py:343-345): all local
+ * alignments of every query against every target that pass the thresholds.  Hits are sorted by
+ * (q_id, s_id, s_start, q_start); the result is deterministic. */
+int  pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target,
+               const pb_search_params* params, pb_hits* out, pb_search_stats* stats /* nullable */);
+void pb_free_hits(pb_hits* hits);
+
+/* Multi-GPU: every rank contributes its hit table and receives the concatenation of all ranks'
+ * tables in rank order (one NCCL allgather of counts, one of the padded records, one of the CIGAR
+ * side buffer; identical result on every rank).  With world == 1 this is a no-op.  Replaces the
+ * per-genome result files merged by the parent process (PEPPAN.py:922-990). */
+int  pb_allgather_hits(pb_ctx* ctx, pb_hits* inout);
+
 /* Measures the issue rate of dependent-free DPX chains on all SMs (lane-ops/s): the roofline
  * denominator of the extension kernels.  which: 0 = viaddmax_s16x2, 1 = s32. */
 int pb_measure_dpx_peak(pb_ctx* ctx, int which, double* lane_ops_per_s);

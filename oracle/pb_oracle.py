@@ -19,8 +19,8 @@ ORC_ALN_DTYPE = np.dtype([(k, np.int32) for k in (
 
 def build(force=False):
     so = os.path.join(_HERE, 'libpb_oracle.so')
-    src = os.path.join(_HERE, 'pb_oracle.c')
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ('pb_oracle.c', 'pb_search_oracle.c')]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(['make', '-C', _HERE, '-s', '-B'])
     return so
 
@@ -111,3 +111,26 @@ def greedy_cluster(n, ea, eb):
 
 def cigar_to_str(ops):
     return ''.join('%d%s' % (int(o) >> 2, 'MID'[int(o) & 3]) for o in ops)
+
+
+ORC_HIT_DTYPE = np.dtype([('q_id', 'i4'), ('s_id', 'i4'), ('q_start', 'i4'), ('q_end', 'i4'), ('s_start', 'i4'), ('s_end', 'i4'),
+                          ('aln_len', 'i4'), ('mismatch', 'i4'), ('gapopen', 'i4'), ('raw_score', 'i4'), ('q_len', 'i4'), ('s_len', 'i4'),
+                          ('identity', 'f4'), ('evalue', 'f4'), ('frame', 'i4'), ('cigar_off', 'u4'), ('cigar_n', 'u4')])
+
+
+def search(q_bytes, q_off, t_bytes, t_off, mode, matrix21, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0,
+           cap=200000, cigar_cap=4000000):
+    """Scalar restatement of pb_search (pb_search_oracle.c).  Returns (hits, cigar)."""
+    q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8); t_bytes = np.ascontiguousarray(t_bytes, dtype=np.uint8)
+    q_off = np.ascontiguousarray(q_off, dtype=np.int64); t_off = np.ascontiguousarray(t_off, dtype=np.int64)
+    m = np.ascontiguousarray(matrix21, dtype=np.int8)
+    hits = np.zeros(cap, dtype=ORC_HIT_DTYPE); cigar = np.zeros(cigar_cap, dtype=np.uint32)
+    nc = C.c_int64()
+    f = lib().orc_search
+    f.restype = C.c_int64
+    n = f(_p(q_bytes), _p(q_off), C.c_int64(len(q_off) - 1), _p(t_bytes), _p(t_off), C.c_int64(len(t_off) - 1), C.c_int(mode),
+          C.c_int(gtable), C.c_double(min_id), C.c_double(min_cov), C.c_double(min_ratio), C.c_int(max_hits), _p(m),
+          _p(hits), C.c_int64(cap), _p(cigar), C.c_int64(cigar_cap), C.byref(nc))
+    if n < 0:
+        raise RuntimeError('oracle search: output capacity too small')
+    return hits[:n].copy(), cigar[:nc.value].copy()

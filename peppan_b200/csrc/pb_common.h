@@ -15,7 +15,7 @@ struct pb_ctx {
     size_t smem_optin = 0;
     int64_t hbm_bytes = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[16] = {};   // 0-3 SW job, 4-7 pb_sw_batch, 8-13 search / cluster
     std::string err;
     void* nccl_comm = nullptr;      // ncclComm_t when world > 1
     void* nccl_dl = nullptr;        // dlopen handle of libnccl

@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <dlfcn.h>
 #include <mutex>
+#include <vector>
+#include <algorithm>
 
 static std::string g_last_error;
 static std::mutex g_err_mutex;
@@ -150,4 +152,68 @@ extern "C" void pb_host_free(pb_ctx* ctx, void* p)
 {
     (void)ctx;
     if (p) cudaFreeHost(p);
+}
+
+
+// ---- hit-table exchange -------------------------------------------------------------------------
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+
+extern "C" int pb_allgather_hits(pb_ctx* ctx, pb_hits* io)
+{
+    if (!ctx || !io) return PB_ERR_ARG;
+    if (ctx->world == 1) return PB_OK;
+    if (!ctx->nccl_comm) { pb_set_error(ctx, "pb_allgather_hits: context was created without NCCL"); return PB_ERR_NCCL; }
+    auto allgather = (nccl_allgather_fn)dlsym(ctx->nccl_dl, "ncclAllGather");
+    if (!allgather) { pb_set_error(ctx, "pb_allgather_hits: ncclAllGather missing"); return PB_ERR_NCCL; }
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = ctx->world;
+    cudaStream_t sm = ctx->stream;
+    // 1. counts
+    DevBuf d_cnt, d_cnts;
+    PB_CUDA(ctx, d_cnt.alloc(16, sm)); PB_CUDA(ctx, d_cnts.alloc(16 * W, sm));
+    int64_t mine[2] = {io->n_hits, io->n_cigar};
+    PB_CUDA(ctx, cudaMemcpyAsync(d_cnt.p, mine, 16, cudaMemcpyHostToDevice, sm));
+    int rc = allgather(d_cnt.p, d_cnts.p, 2, 4 /* ncclInt64 */, ctx->nccl_comm, sm);
+    if (rc) { pb_set_error(ctx, "ncclAllGather(counts) failed (%d)", rc); return PB_ERR_NCCL; }
+    std::vector<int64_t> all(2 * W);
+    PB_CUDA(ctx, cudaMemcpyAsync(all.data(), d_cnts.p, 16 * W, cudaMemcpyDeviceToHost, sm));
+    PB_CUDA(ctx, cudaStreamSynchronize(sm));
+    int64_t maxh = 0, maxc = 0, toth = 0, totc = 0;
+    for (int r = 0; r < W; ++r) { maxh = std::max(maxh, all[2 * r]); maxc = std::max(maxc, all[2 * r + 1]); toth += all[2 * r]; totc += all[2 * r + 1]; }
+    // 2. fixed-width records and 3. CIGAR side buffer, padded to the largest rank
+    const size_t hb = (size_t)std::max<int64_t>(maxh, 1) * sizeof(pb_hit), cb = (size_t)std::max<int64_t>(maxc, 1) * 4;
+    DevBuf d_h, d_hall, d_c, d_call;
+    PB_CUDA(ctx, d_h.alloc(hb, sm)); PB_CUDA(ctx, d_hall.alloc(hb * W, sm));
+    PB_CUDA(ctx, d_c.alloc(cb, sm)); PB_CUDA(ctx, d_call.alloc(cb * W, sm));
+    PB_CUDA(ctx, cudaMemsetAsync(d_h.p, 0, hb, sm)); PB_CUDA(ctx, cudaMemsetAsync(d_c.p, 0, cb, sm));
+    if (io->n_hits) PB_CUDA(ctx, cudaMemcpyAsync(d_h.p, io->hits, (size_t)io->n_hits * sizeof(pb_hit), cudaMemcpyHostToDevice, sm));
+    if (io->n_cigar) PB_CUDA(ctx, cudaMemcpyAsync(d_c.p, io->cigar, (size_t)io->n_cigar * 4, cudaMemcpyHostToDevice, sm));
+    rc = allgather(d_h.p, d_hall.p, hb, 0 /* ncclInt8 */, ctx->nccl_comm, sm);
+    if (rc) { pb_set_error(ctx, "ncclAllGather(hits) failed (%d)", rc); return PB_ERR_NCCL; }
+    rc = allgather(d_c.p, d_call.p, cb, 0, ctx->nccl_comm, sm);
+    if (rc) { pb_set_error(ctx, "ncclAllGather(cigar) failed (%d)", rc); return PB_ERR_NCCL; }
+    pb_hit* hits = (pb_hit*)malloc((size_t)std::max<int64_t>(toth, 1) * sizeof(pb_hit));
+    uint32_t* cig = (uint32_t*)malloc((size_t)std::max<int64_t>(totc, 1) * 4);
+    int64_t* roff = (int64_t*)malloc((size_t)(W + 1) * 8);
+    if (!hits || !cig || !roff) { free(hits); free(cig); free(roff); pb_set_error(ctx, "pb_allgather_hits: out of host memory"); return PB_ERR_NOMEM; }
+    int64_t ho = 0, co = 0;
+    for (int r = 0; r < W; ++r) {
+        const int64_t nh = all[2 * r], ncg = all[2 * r + 1];
+        roff[r] = ho;
+        if (nh) cudaMemcpyAsync(hits + ho, (char*)d_hall.p + (size_t)r * hb, (size_t)nh * sizeof(pb_hit), cudaMemcpyDeviceToHost, sm);
+        if (ncg) cudaMemcpyAsync(cig + co, (char*)d_call.p + (size_t)r * cb, (size_t)ncg * 4, cudaMemcpyDeviceToHost, sm);
+        ho += nh; co += ncg;
+    }
+    roff[W] = ho;
+    cudaError_t e = cudaStreamSynchronize(sm);
+    if (e != cudaSuccess) { free(hits); free(cig); free(roff); pb_set_error(ctx, "pb_allgather_hits: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    // rebase the CIGAR offsets of every rank's records
+    co = 0;
+    for (int r = 0; r < W; ++r) {
+        for (int64_t i = roff[r]; i < roff[r + 1]; ++i) hits[i].cigar_off += (uint32_t)co;
+        co += all[2 * r + 1];
+    }
+    free(io->hits); free(io->cigar); free(io->rank_offsets);
+    io->hits = hits; io->n_hits = toth; io->cigar = cig; io->n_cigar = totc; io->rank_offsets = roff; io->n_ranks = W;
+    return PB_OK;
 }

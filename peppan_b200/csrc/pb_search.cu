@@ -1,0 +1,702 @@
+// Similarity search: pb_search.  Stands in for what RunBlast.runBlast / runDiamond obtain from
+// blastn and diamond (modules/uberBlast.py:482-560).
+//
+// Pipeline (every stage on the device unless noted):
+//   K0  encode ASCII -> residue codes; reverse-complement copy (nucleotide mode) or translation
+//       of the targets into 6 / 3 frames and of every query into its best forward frame
+//       (frame choice of modules/uberBlast.py:527-529, codon table of modules/configure.py:167-170)
+//   K1a query index: every valid k-mer (k = 12 over ACGT; k = 7 over a 10-letter reduced amino-
+//       acid alphabet) -> (key, position), radix sort, direct-address table key -> first slot
+//   K1b seed scan over the target: table lookup per position, keep only the leftmost seed of an
+//       exact-match run, ungapped X-drop extension in place, emit ungapped HSPs above a cut-off
+//   host  cluster HSPs by (query, target, diagonal) and cut one target window per cluster
+//   K2  windowed Smith-Waterman (score, end, start, traceback) through the batched SW job on
+//       views of the device-resident code arrays (no gather)
+//   host  map to nucleotide coordinates, apply the reference's thresholds, build the hit table
+//
+// The search specification (constants below) is restated in scalar C in oracle/pb_search_oracle.c
+// and the two are compared hit for hit by tests/test_search_gpu.py.
+#include "pb_sw_job.h"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <vector>
+
+namespace {
+
+constexpr uint8_t SENT = 31;          // separator between sequences: never seeds, stops extensions
+constexpr uint32_t NOKEY = 0xffffffffu;
+
+// ---- search specification ---------------------------------------------------------------------
+struct SeedSpec {
+    int k;               // seed length
+    int base;            // seed alphabet size
+    int xdrop;           // ungapped X-drop
+    int min_ungapped;    // ungapped HSP score needed to open a window
+    int diag_span;       // HSPs of one (query, target) whose diagonals differ by <= this share a window
+    int pad;             // window slack on both sides
+    uint8_t seedmap[32]; // scoring code -> seed code, 255 = cannot seed
+};
+
+struct DevSpec {
+    int k, base, xdrop, min_ungapped;
+    uint8_t seedmap[32];
+    int8_t score[1024];
+};
+
+// nucleotide: exact 12-mers (a superset of blastn -word_size 17 seeds), +2/-3, X-drop 20, cut-off 32
+SeedSpec nt_spec()
+{
+    SeedSpec s{12, 4, 20, 32, 16, 32, {}};
+    for (int i = 0; i < 32; ++i) s.seedmap[i] = 255;
+    for (int i = 0; i < 4; ++i) s.seedmap[i] = (uint8_t)i;
+    return s;
+}
+
+// protein: 7-mers over the reduced alphabet {AST}{RK}{ND}{C}{QE}{G}{H}{ILVM}{FYW}{P}, BLOSUM62
+// ungapped X-drop 12, cut-off 38.  Codes follow seqcodec.AA = ARNDCQEGHILKMFPSTWYVX.
+SeedSpec aa_spec()
+{
+    SeedSpec s{7, 10, 12, 38, 12, 24, {}};
+    for (int i = 0; i < 32; ++i) s.seedmap[i] = 255;
+    const char* aa = "ARNDCQEGHILKMFPSTWYV";
+    const char* grp[10] = {"AST", "RK", "ND", "C", "QE", "G", "H", "ILVM", "FYW", "P"};
+    for (int g = 0; g < 10; ++g)
+        for (const char* c = grp[g]; *c; ++c)
+            for (int i = 0; i < 20; ++i) if (aa[i] == *c) s.seedmap[i] = (uint8_t)g;
+    return s;
+}
+
+struct Cand { uint32_t qpos, tpos, len; int32_t score; };
+
+// ---- K0 kernels -------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t nt_code(uint8_t c)
+{
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2;
+                 case 'T': case 't': return 3; default: return 4; }
+}
+
+// one block per sequence: dst[doff[s] .. ) = codes, optionally also the reverse complement at roff[s]
+__global__ void encode_nt_kernel(const uint8_t* src, const int64_t* soff, const int64_t* doff, const int64_t* roff, int64_t nseq,
+                                 uint8_t* dst)
+{
+    for (int64_t s = blockIdx.x; s < nseq; s += gridDim.x) {
+        const int64_t a = soff[s], L = soff[s + 1] - a, d = doff[s];
+        for (int64_t i = threadIdx.x; i < L; i += blockDim.x) {
+            uint8_t c = nt_code(src[a + i]);
+            dst[d + i] = c;
+            if (roff) dst[roff[s] + (L - 1 - i)] = c < 4 ? (uint8_t)(3 - c) : c;
+        }
+    }
+}
+
+__global__ void fill_u8(uint8_t* p, uint8_t v, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void put_sentinels(uint8_t* p, const int64_t* pos, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[pos[i]] = SENT;
+}
+
+// codon -> amino-acid code (0..20, seqcodec.AA order), index b0<<4|b1<<2|b2 with A0 C1 G2 T3
+// (modules/configure.py:170: KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVVXYXYSSSSXCWCLFLF; table 4: index 56 -> W)
+__constant__ uint8_t c_codon[64];
+
+__device__ __forceinline__ uint8_t translate_codon(const uint8_t* nt, int64_t L, int64_t p0, bool rev, int table4)
+{
+    // nt are codes of the plus strand; rev reads the reverse complement
+    int idx = 0; bool bad = false;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        int64_t p = p0 + x;
+        uint8_t c = 4;
+        if (p < L) { c = rev ? nt[L - 1 - p] : nt[p]; if (rev && c < 4) c = 3 - c; }
+        if (c >= 4) bad = true;
+        idx = (idx << 2) | (c & 3);
+    }
+    if (bad) return 20;                         // 'X' (ambiguous, gap, or padded tail: configure.py:186-191)
+    if (table4 && idx == 56) return 17;         // TGA -> W
+    return c_codon[idx];
+}
+
+// targets: frame f (1..6) of contig s -> dst[doff[s*F + f-1] ..)
+__global__ void translate_targets_kernel(const uint8_t* nt, const int64_t* ntoff, const int64_t* doff, int64_t nseq, int F,
+                                         int table4, uint8_t* dst)
+{
+    for (int64_t sf = blockIdx.x; sf < nseq * F; sf += gridDim.x) {
+        const int64_t s = sf / F; const int f = (int)(sf % F);
+        const int64_t a = ntoff[s], L = ntoff[s + 1] - a;
+        const int off = f % 3; const bool rev = f >= 3;
+        const int64_t rem = L - off, na = rem > 0 ? (rem + 2) / 3 : 0;
+        for (int64_t i = threadIdx.x; i < na; i += blockDim.x)
+            dst[doff[sf] + i] = translate_codon(nt + a, L, off + 3 * i, rev, table4);
+    }
+}
+
+// queries: choose the forward frame with the fewest 'X'-separated pieces, counted on the frame
+// without its last residue (modules/uberBlast.py:528); ties -> lowest frame.  One warp per gene.
+__global__ void choose_frame_kernel(const uint8_t* nt, const int64_t* ntoff, int64_t nseq, int table4, int* frame, int* aalen)
+{
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nseq) return;
+    const int64_t a = ntoff[w], L = ntoff[w + 1] - a;
+    int best = 0, bestx = 0x7fffffff, bestlen = 0;
+    for (int f = 0; f < 3; ++f) {
+        const int64_t rem = L - f, na = rem > 0 ? (rem + 2) / 3 : 0;
+        int nx = 0;
+        for (int64_t i = lane; i < na - 1; i += 32) nx += translate_codon(nt + a, L, f + 3 * i, false, table4) == 20;
+        for (int o = 16; o; o >>= 1) nx += __shfl_xor_sync(0xffffffffu, nx, o);
+        if (nx < bestx) { bestx = nx; best = f; bestlen = (int)na; }
+    }
+    if (lane == 0) { frame[w] = best; aalen[w] = bestlen; }
+}
+
+__global__ void translate_queries_kernel(const uint8_t* nt, const int64_t* ntoff, const int64_t* doff, const int* frame,
+                                         int64_t nseq, int table4, uint8_t* dst)
+{
+    for (int64_t s = blockIdx.x; s < nseq; s += gridDim.x) {
+        const int64_t a = ntoff[s], L = ntoff[s + 1] - a;
+        const int f = frame[s];
+        const int64_t rem = L - f, na = rem > 0 ? (rem + 2) / 3 : 0;
+        for (int64_t i = threadIdx.x; i < na; i += blockDim.x)
+            dst[doff[s] + i] = translate_codon(nt + a, L, f + 3 * i, false, table4);
+    }
+}
+
+// ---- K1a: query k-mers ---------------------------------------------------------------------------
+__global__ void extract_kmers_kernel(const uint8_t* codes, int64_t n, DevSpec sp, uint32_t* keys, uint32_t* vals, unsigned long long* nvalid)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t key = 0; bool ok = p + sp.k <= n;
+    if (ok) {
+        for (int i = 0; i < sp.k; ++i) {
+            uint8_t c = codes[p + i];
+            uint8_t sc = c < 32 ? sp.seedmap[c] : 255;
+            if (sc == 255) { ok = false; break; }
+            key = key * sp.base + sc;
+        }
+    }
+    keys[p] = ok ? key : NOKEY;
+    vals[p] = (uint32_t)p;
+    if (ok) atomicAdd(nvalid, 1ull);
+}
+
+__global__ void build_table_kernel(const uint32_t* keys, int64_t nvalid, uint32_t* table)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvalid) return;
+    if (i == 0 || keys[i] != keys[i - 1]) table[keys[i]] = (uint32_t)i;
+}
+
+// ---- K1b: seed scan + ungapped X-drop ---------------------------------------------------------------
+// Each block stages a tile of the target codes in shared memory with 128-bit loads; every thread
+// then owns SCAN_PER_THREAD consecutive positions and rolls the k-mer key across them.
+constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__global__ void __launch_bounds__(SCAN_THREADS) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
+                                                                 const uint8_t* __restrict__ qcodes, int64_t qn,
+                                                                 const uint32_t* __restrict__ table, const uint32_t* __restrict__ keys,
+                                                                 const uint32_t* __restrict__ vals, int64_t nvalid, DevSpec sp,
+                                                                 Cand* cand, unsigned long long* ncand, unsigned long long cap,
+                                                                 unsigned long long* nseed)
+{
+    __shared__ __align__(16) uint8_t tile[SCAN_TILE + 64];
+    __shared__ int8_t sscore[1024];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t*>(sscore)[i] = reinterpret_cast<const uint32_t*>(sp.score)[i];
+    uint32_t pw = 1;
+    for (int i = 1; i < sp.k; ++i) pw *= sp.base;          // base^(k-1)
+    unsigned long long myseeds = 0;
+    for (int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE; t0 < tn; t0 += (int64_t)gridDim.x * SCAN_TILE) {
+        __syncthreads();
+        // stage tile [t0, t0 + SCAN_TILE + k) (t0 is a multiple of 16: 128-bit loads)
+        const int nload = SCAN_TILE + 64;
+        for (int i = threadIdx.x * 16; i < nload; i += blockDim.x * 16) {
+            uint4 v = make_uint4(0x1f1f1f1fu, 0x1f1f1f1fu, 0x1f1f1f1fu, 0x1f1f1f1fu);
+            if (t0 + i + 16 <= tn) v = *reinterpret_cast<const uint4*>(tcodes + t0 + i);
+            else for (int x = 0; x < 16; ++x) if (t0 + i + x < tn) reinterpret_cast<uint8_t*>(&v)[x] = tcodes[t0 + i + x];
+            *reinterpret_cast<uint4*>(tile + i) = v;
+        }
+        __syncthreads();
+        const int base_i = threadIdx.x * SCAN_PER_THREAD;
+        uint32_t key = 0; int bad = 0;        // bad = number of positions until the window is free of invalid residues
+        for (int i = 0; i < sp.k - 1; ++i) {
+            uint8_t c = tile[base_i + i];
+            uint8_t sc = c < 32 ? sp.seedmap[c] : 255;
+            if (sc == 255) { bad = i + 1; sc = 0; }
+            key = key * sp.base + sc;
+        }
+        // after the loop `bad` holds (index of last invalid)+1 within the first k-1 residues
+        int last_bad = bad - 1;                  // position (relative to base_i) of the last invalid residue, -1 if none
+        for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+            const int pos = base_i + j;
+            uint8_t c = tile[pos + sp.k - 1];
+            uint8_t sc = c < 32 ? sp.seedmap[c] : 255;
+            if (sc == 255) { last_bad = j + sp.k - 1; sc = 0; }
+            key = key * sp.base + sc;            // key now covers [pos, pos+k)
+            const int64_t tpos = t0 + pos;
+            if (last_bad < j && tpos + sp.k <= tn) {
+                uint32_t slot = table[key];
+                if (slot != NOKEY) {
+                    for (int64_t o = slot; o < nvalid && keys[o] == key; ++o) {
+                        const int64_t qpos = vals[o];
+                        ++myseeds;
+                        // leftmost seed of a match run only: if the preceding residues agree in the seed alphabet the
+                        // preceding k-mer is a seed on the same diagonal and extends to the same HSP
+                        if (qpos > 0 && tpos > 0) {
+                            uint8_t a = qcodes[qpos - 1], b = tcodes[tpos - 1];
+                            uint8_t sa = a < 32 ? sp.seedmap[a] : 255, sb = b < 32 ? sp.seedmap[b] : 255;
+                            if (sa != 255 && sa == sb) continue;
+                        }
+                        // seed score
+                        int score = 0;
+                        for (int i = 0; i < sp.k; ++i) score += sscore[qcodes[qpos + i] * 32 + tile[pos + i]];
+                        int best = score, cur = score, rlen = sp.k;
+                        // extend right
+                        for (int64_t x = sp.k;; ++x) {
+                            if (qpos + x >= qn || tpos + x >= tn) break;
+                            uint8_t a = qcodes[qpos + x], b = tcodes[tpos + x];
+                            if (a == SENT || b == SENT) break;
+                            cur += sscore[a * 32 + b];
+                            if (cur > best) { best = cur; rlen = (int)x + 1; }
+                            else if (best - cur > sp.xdrop) break;
+                        }
+                        // extend left
+                        int lbest = best, llen = 0; cur = best;
+                        for (int64_t x = 1;; ++x) {
+                            if (qpos - x < 0 || tpos - x < 0) break;
+                            uint8_t a = qcodes[qpos - x], b = tcodes[tpos - x];
+                            if (a == SENT || b == SENT) break;
+                            cur += sscore[a * 32 + b];
+                            if (cur > lbest) { lbest = cur; llen = (int)x; }
+                            else if (lbest - cur > sp.xdrop) break;
+                        }
+                        if (lbest >= sp.min_ungapped) {
+                            unsigned long long slot2 = atomicAdd(ncand, 1ull);
+                            if (slot2 < cap) {
+                                Cand cd; cd.qpos = (uint32_t)(qpos - llen); cd.tpos = (uint32_t)(tpos - llen); cd.len = (uint32_t)(rlen + llen); cd.score = lbest;
+                                cand[slot2] = cd;
+                            }
+                        }
+                    }
+                }
+            }
+            // roll: drop the leading residue
+            uint8_t c0 = tile[pos];
+            uint8_t s0 = c0 < 32 ? sp.seedmap[c0] : 255;
+            if (s0 == 255) s0 = 0;
+            key -= s0 * pw;
+        }
+    }
+    if (myseeds) atomicAdd(nseed, myseeds);
+}
+
+// ---- host helpers -------------------------------------------------------------------------------
+struct SeqLayout {
+    std::vector<int64_t> off;     // begin of every sequence in the device code array
+    std::vector<int64_t> len;
+    int64_t total = 0;
+};
+
+// sequences separated (and surrounded) by one sentinel, begins aligned so that the array start is 16-byte aligned
+SeqLayout make_layout(const std::vector<int64_t>& lens)
+{
+    SeqLayout L; L.off.resize(lens.size()); L.len = lens;
+    int64_t p = 1;
+    for (size_t i = 0; i < lens.size(); ++i) { L.off[i] = p; p += lens[i] + 1; }
+    L.total = p;
+    return L;
+}
+
+inline int find_seq(const SeqLayout& L, int64_t pos)
+{
+    size_t i = std::upper_bound(L.off.begin(), L.off.end(), pos) - L.off.begin();
+    return (int)i - 1;
+}
+
+struct Window { int qid, tid; int64_t tbeg; int tlen; };
+
+const char* CODON11 = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVVXYXYSSSSXCWCLFLF";
+
+// BLOSUM62 over ARNDCQEGHILKMFPSTWYVX (standard NCBI table = what modules/configure.py:49-87 decodes to;
+// checked against tests/golden/blosum62.json through peppan_b200.seqcodec)
+const int8_t PB_BLOSUM62_21[21 * 21] = {
+     4,-1,-2,-2, 0,-1,-1, 0,-2,-1,-1,-1,-1,-2,-1, 1, 0,-3,-2, 0, 0,
+    -1, 5, 0,-2,-3, 1, 0,-2, 0,-3,-2, 2,-1,-3,-2,-1,-1,-3,-2,-3,-1,
+    -2, 0, 6, 1,-3, 0, 0, 0, 1,-3,-3, 0,-2,-3,-2, 1, 0,-4,-2,-3,-1,
+    -2,-2, 1, 6,-3, 0, 2,-1,-1,-3,-4,-1,-3,-3,-1, 0,-1,-4,-3,-3,-1,
+     0,-3,-3,-3, 9,-3,-4,-3,-3,-1,-1,-3,-1,-2,-3,-1,-1,-2,-2,-1,-2,
+    -1, 1, 0, 0,-3, 5, 2,-2, 0,-3,-2, 1, 0,-3,-1, 0,-1,-2,-1,-2,-1,
+    -1, 0, 0, 2,-4, 2, 5,-2, 0,-3,-3, 1,-2,-3,-1, 0,-1,-3,-2,-2,-1,
+     0,-2, 0,-1,-3,-2,-2, 6,-2,-4,-4,-2,-3,-3,-2, 0,-2,-2,-3,-3,-1,
+    -2, 0, 1,-1,-3, 0, 0,-2, 8,-3,-3,-1,-2,-1,-2,-1,-2,-2, 2,-3,-1,
+    -1,-3,-3,-3,-1,-3,-3,-4,-3, 4, 2,-3, 1, 0,-3,-2,-1,-3,-1, 3,-1,
+    -1,-2,-3,-4,-1,-2,-3,-4,-3, 2, 4,-2, 2, 0,-3,-2,-1,-2,-1, 1,-1,
+    -1, 2, 0,-1,-3, 1, 1,-2,-1,-3,-2, 5,-1,-3,-1, 0,-1,-3,-2,-2,-1,
+    -1,-1,-2,-3,-1, 0,-2,-3,-2, 1, 2,-1, 5, 0,-2,-1,-1,-1,-1, 1,-1,
+    -2,-3,-3,-3,-2,-3,-3,-3,-1, 0, 0,-3, 0, 6,-4,-2,-2, 1, 3,-1,-1,
+    -1,-2,-2,-1,-3,-1,-1,-2,-2,-3,-3,-1,-2,-4, 7,-1,-1,-4,-3,-2,-2,
+     1,-1, 1, 0,-1, 0, 0, 0,-1,-2,-2, 0,-1,-2,-1, 4, 1,-3,-2,-2, 0,
+     0,-1, 0,-1,-1,-1,-1,-2,-2,-1,-1,-1,-1,-2,-1, 1, 5,-2,-2, 0, 0,
+    -3,-3,-4,-4,-2,-2,-3,-2,-2,-3,-2,-3,-1, 1,-4,-3,-2,11, 2,-3,-2,
+    -2,-2,-2,-3,-2,-1,-2,-3, 2,-1,-1,-2,-1, 3,-3,-2,-2, 2, 7,-1,-1,
+     0,-3,-3,-3,-1,-2,-2,-3,-3, 3, 1,-2, 1,-1,-2,-2, 0,-3,-1, 4,-1,
+     0,-1,-1,-1,-2,-1,-1,-1,-1,-1,-1,-1,-1,-1,-2, 0, 0,-2,-1,-1,-1};
+
+}  // namespace
+
+// ==================================================================================================
+extern "C" void pb_free_hits(pb_hits* h)
+{
+    if (!h) return;
+    free(h->hits); free(h->cigar); free(h->rank_offsets);
+    h->hits = nullptr; h->cigar = nullptr; h->rank_offsets = nullptr; h->n_hits = 0; h->n_cigar = 0; h->n_ranks = 0;
+}
+
+extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const pb_search_params* prm,
+                         pb_hits* out, pb_search_stats* stats)
+{
+    if (!ctx || !query || !target || !prm || !out) { pb_set_error(ctx, "pb_search: invalid argument"); return PB_ERR_ARG; }
+    if (prm->mode < PB_MODE_NT || prm->mode > PB_MODE_PROT3_SELF) { pb_set_error(ctx, "pb_search: unknown mode %d", prm->mode); return PB_ERR_ARG; }
+    out->hits = nullptr; out->cigar = nullptr; out->n_hits = 0; out->n_cigar = 0; out->rank_offsets = nullptr; out->n_ranks = 0;
+    pb_search_stats st; memset(&st, 0, sizeof(st));
+    if (query->n == 0 || target->n == 0) { if (stats) *stats = st; return PB_OK; }
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t sm = ctx->stream;
+    const bool nt = prm->mode == PB_MODE_NT;
+    const int F = nt ? 2 : (prm->mode == PB_MODE_PROT6 ? 6 : 3);
+    const int table4 = prm->gtable == 4;
+    const SeedSpec spec = nt ? nt_spec() : aa_spec();
+    const int64_t nq = query->n, nc = target->n;
+    const int64_t qbytes = query->offsets[nq], tbytes = target->offsets[nc];
+    if (qbytes >= (int64_t)0xfffffff0 || tbytes * (nt ? 2 : 1) >= (int64_t)0xfffffff0) {
+        pb_set_error(ctx, "pb_search: a single call is limited to 4 G residues per side; block the input"); return PB_ERR_LIMIT;
+    }
+    cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10], e3 = ctx->ev[11];
+    int launches = 0;
+    PB_CUDA(ctx, cudaEventRecord(e0, sm));
+
+    // ---- scoring ----
+    pb_score_params sp; memset(&sp, 0, sizeof(sp));
+    DevSpec ds; memset(&ds, 0, sizeof(ds));
+    ds.k = spec.k; ds.base = spec.base; ds.xdrop = spec.xdrop; ds.min_ungapped = spec.min_ungapped;
+    memcpy(ds.seedmap, spec.seedmap, 32);
+    if (nt) {
+        sp.nsym = 6; sp.gap_open = 6; sp.gap_extend = 2;
+        for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) sp.matrix[a * 32 + b] = (a == b && a < 4) ? 2 : -3;
+    } else {
+        sp.nsym = 22; sp.gap_open = 11; sp.gap_extend = 1;
+        for (int a = 0; a < 21; ++a) for (int b = 0; b < 21; ++b) sp.matrix[a * 32 + b] = PB_BLOSUM62_21[a * 21 + b];
+    }
+    for (int a = 0; a < 32; ++a) for (int b = 0; b < 32; ++b) ds.score[a * 32 + b] = (a < sp.nsym - 1 && b < sp.nsym - 1) ? sp.matrix[a * 32 + b] : -100;
+
+    // ---- K0: upload ASCII, encode / translate ----
+    DevBuf d_qascii, d_tascii, d_qsoff, d_tsoff;
+    PB_CUDA(ctx, d_qascii.alloc(std::max<int64_t>(qbytes, 16), sm)); PB_CUDA(ctx, d_tascii.alloc(std::max<int64_t>(tbytes, 16), sm));
+    PB_CUDA(ctx, d_qsoff.alloc((nq + 1) * 8, sm)); PB_CUDA(ctx, d_tsoff.alloc((nc + 1) * 8, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_qascii.p, query->residues, qbytes, cudaMemcpyHostToDevice, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_tascii.p, target->residues, tbytes, cudaMemcpyHostToDevice, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_qsoff.p, query->offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_tsoff.p, target->offsets, (nc + 1) * 8, cudaMemcpyHostToDevice, sm));
+
+    std::vector<int64_t> qlen_nt(nq), tlen_nt(nc);
+    for (int64_t i = 0; i < nq; ++i) qlen_nt[i] = query->offsets[i + 1] - query->offsets[i];
+    for (int64_t i = 0; i < nc; ++i) tlen_nt[i] = target->offsets[i + 1] - target->offsets[i];
+
+    SeqLayout QL, TL;
+    std::vector<int> qframe(nq, 0);
+    DevBuf d_qc, d_tc, d_tmpq, d_tmpt, d_off1, d_off2, d_frame, d_aalen;
+    if (nt) {
+        QL = make_layout(qlen_nt);
+        std::vector<int64_t> tl2(2 * nc);
+        for (int64_t i = 0; i < nc; ++i) { tl2[i] = tlen_nt[i]; tl2[nc + i] = tlen_nt[i]; }
+        TL = make_layout(tl2);
+        PB_CUDA(ctx, d_qc.alloc(QL.total + 64, sm)); PB_CUDA(ctx, d_tc.alloc(TL.total + 64, sm));
+        fill_u8<<<(unsigned)((QL.total + 64 + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), SENT, QL.total + 64);
+        fill_u8<<<(unsigned)((TL.total + 64 + 255) / 256), 256, 0, sm>>>(d_tc.as<uint8_t>(), SENT, TL.total + 64);
+        PB_CUDA(ctx, d_off1.alloc(nq * 8, sm)); PB_CUDA(ctx, d_off2.alloc(2 * nc * 8, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(d_off1.p, QL.off.data(), nq * 8, cudaMemcpyHostToDevice, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), 2 * nc * 8, cudaMemcpyHostToDevice, sm));
+        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nq, 4096), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), nullptr, nq, d_qc.as<uint8_t>());
+        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nc, 4096), 1024, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), d_off2.as<int64_t>() + nc, nc, d_tc.as<uint8_t>());
+        PB_CUDA(ctx, cudaGetLastError()); launches += 4;
+    } else {
+        // codon table in amino-acid codes
+        uint8_t codon[64];
+        const char* aa = "ARNDCQEGHILKMFPSTWYVX";
+        for (int i = 0; i < 64; ++i) { const char* p = strchr(aa, CODON11[i]); codon[i] = (uint8_t)(p - aa); }
+        PB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_codon, codon, 64, 0, cudaMemcpyHostToDevice, sm));
+        // nucleotide codes of both sets (plain, no sentinels) as translation input
+        PB_CUDA(ctx, d_tmpq.alloc(std::max<int64_t>(qbytes, 16), sm)); PB_CUDA(ctx, d_tmpt.alloc(std::max<int64_t>(tbytes, 16), sm));
+        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nq, 4096), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_qsoff.as<int64_t>(), nullptr, nq, d_tmpq.as<uint8_t>());
+        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nc, 4096), 1024, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_tsoff.as<int64_t>(), nullptr, nc, d_tmpt.as<uint8_t>());
+        PB_CUDA(ctx, d_frame.alloc(nq * 4, sm)); PB_CUDA(ctx, d_aalen.alloc(nq * 4, sm));
+        choose_frame_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), nq, table4, d_frame.as<int>(), d_aalen.as<int>());
+        PB_CUDA(ctx, cudaGetLastError()); launches += 3;
+        std::vector<int> aalen(nq);
+        PB_CUDA(ctx, cudaMemcpyAsync(qframe.data(), d_frame.p, nq * 4, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(aalen.data(), d_aalen.p, nq * 4, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaStreamSynchronize(sm));
+        std::vector<int64_t> ql(nq), tl((size_t)nc * F);
+        for (int64_t i = 0; i < nq; ++i) ql[i] = aalen[i];
+        for (int64_t i = 0; i < nc; ++i) for (int f = 0; f < F; ++f) { int64_t rem = tlen_nt[i] - (f % 3); tl[i * F + f] = rem > 0 ? (rem + 2) / 3 : 0; }
+        QL = make_layout(ql); TL = make_layout(tl);
+        PB_CUDA(ctx, d_qc.alloc(QL.total + 64, sm)); PB_CUDA(ctx, d_tc.alloc(TL.total + 64, sm));
+        fill_u8<<<(unsigned)((QL.total + 64 + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), SENT, QL.total + 64);
+        fill_u8<<<(unsigned)((TL.total + 64 + 255) / 256), 256, 0, sm>>>(d_tc.as<uint8_t>(), SENT, TL.total + 64);
+        PB_CUDA(ctx, d_off1.alloc(nq * 8, sm)); PB_CUDA(ctx, d_off2.alloc(nc * F * 8, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(d_off1.p, QL.off.data(), nq * 8, cudaMemcpyHostToDevice, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), nc * F * 8, cudaMemcpyHostToDevice, sm));
+        translate_queries_kernel<<<(unsigned)std::min<int64_t>(nq, 8192), 128, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), d_frame.as<int>(), nq, table4, d_qc.as<uint8_t>());
+        translate_targets_kernel<<<(unsigned)std::min<int64_t>(nc * F, 8192), 1024, 0, sm>>>(d_tmpt.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), nc, F, table4, d_tc.as<uint8_t>());
+        PB_CUDA(ctx, cudaGetLastError()); launches += 4;
+    }
+    PB_CUDA(ctx, cudaEventRecord(e1, sm));
+
+    // ---- K1a: index ----
+    const int64_t LQ = QL.total, LT = TL.total;
+    int64_t tabsize = 1; for (int i = 0; i < spec.k; ++i) tabsize *= spec.base;
+    DevBuf d_keys, d_vals, d_keys2, d_vals2, d_table, d_cnt, d_tmp;
+    PB_CUDA(ctx, d_keys.alloc(LQ * 4, sm)); PB_CUDA(ctx, d_vals.alloc(LQ * 4, sm));
+    PB_CUDA(ctx, d_keys2.alloc(LQ * 4, sm)); PB_CUDA(ctx, d_vals2.alloc(LQ * 4, sm));
+    PB_CUDA(ctx, d_table.alloc(tabsize * 4, sm)); PB_CUDA(ctx, d_cnt.alloc(64, sm));
+    PB_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, 64, sm));
+    PB_CUDA(ctx, cudaMemsetAsync(d_table.p, 0xff, tabsize * 4, sm));
+    extract_kmers_kernel<<<(unsigned)((LQ + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), LQ, ds, d_keys.as<uint32_t>(), d_vals.as<uint32_t>(), d_cnt.as<unsigned long long>());
+    PB_CUDA(ctx, cudaGetLastError()); ++launches;
+    size_t tmpb = 0;
+    PB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmpb, d_keys.as<uint32_t>(), d_keys2.as<uint32_t>(), d_vals.as<uint32_t>(), d_vals2.as<uint32_t>(), (int)LQ, 0, 32, sm));
+    PB_CUDA(ctx, d_tmp.alloc(std::max<size_t>(tmpb, 16), sm));
+    PB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp.p, tmpb, d_keys.as<uint32_t>(), d_keys2.as<uint32_t>(), d_vals.as<uint32_t>(), d_vals2.as<uint32_t>(), (int)LQ, 0, 32, sm));
+    unsigned long long cnts[8];
+    PB_CUDA(ctx, cudaMemcpyAsync(cnts, d_cnt.p, 64, cudaMemcpyDeviceToHost, sm));
+    PB_CUDA(ctx, cudaStreamSynchronize(sm));
+    const int64_t nvalid = (int64_t)cnts[0];
+    st.n_query_kmers = nvalid;
+    if (nvalid > 0) {
+        build_table_kernel<<<(unsigned)((nvalid + 255) / 256), 256, 0, sm>>>(d_keys2.as<uint32_t>(), nvalid, d_table.as<uint32_t>());
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+    }
+    PB_CUDA(ctx, cudaEventRecord(e2, sm));
+
+    // ---- K1b: seed scan (retry with a larger candidate buffer on overflow) ----
+    std::vector<Cand> cands;
+    unsigned long long cap = std::max<unsigned long long>(1ull << 20, (unsigned long long)nq * 64);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        DevBuf d_cand;
+        PB_CUDA(ctx, d_cand.alloc(cap * sizeof(Cand), sm));
+        PB_CUDA(ctx, cudaMemsetAsync(d_cnt.as<unsigned long long>() + 1, 0, 16, sm));
+        const int grid = (int)std::min<int64_t>((LT + SCAN_TILE - 1) / SCAN_TILE, (int64_t)ctx->sm_count * 8);
+        seed_scan_kernel<<<grid, SCAN_THREADS, 0, sm>>>(d_tc.as<uint8_t>(), LT, d_qc.as<uint8_t>(), LQ, d_table.as<uint32_t>(), d_keys2.as<uint32_t>(),
+                                                         d_vals2.as<uint32_t>(), nvalid, ds, d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap,
+                                                         d_cnt.as<unsigned long long>() + 2);
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        PB_CUDA(ctx, cudaMemcpyAsync(cnts, d_cnt.p, 64, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaStreamSynchronize(sm));
+        if (cnts[1] <= cap) {
+            cands.resize(cnts[1]);
+            if (cnts[1]) PB_CUDA(ctx, cudaMemcpyAsync(cands.data(), d_cand.p, cnts[1] * sizeof(Cand), cudaMemcpyDeviceToHost, sm));
+            PB_CUDA(ctx, cudaStreamSynchronize(sm));
+            break;
+        }
+        cap = cnts[1] + (cnts[1] >> 3);
+        if (attempt == 3) { pb_set_error(ctx, "pb_search: candidate buffer overflow"); return PB_ERR_LIMIT; }
+    }
+    st.n_seed_hits = (int64_t)cnts[2]; st.n_ungapped = (int64_t)cands.size();
+    st.algo_bytes_seed = LT + 9 * LQ + 16 * (int64_t)cnts[2];
+    PB_CUDA(ctx, cudaEventRecord(e3, sm));
+
+    // ---- host: clusters -> windows ----
+    struct HC { int qid, tid; int64_t diag; int64_t ts, te; int qs, qe; };
+    std::vector<HC> hc; hc.reserve(cands.size());
+    for (const Cand& c : cands) {
+        int qid = find_seq(QL, c.qpos), tid = find_seq(TL, c.tpos);
+        HC h; h.qid = qid; h.tid = tid;
+        h.qs = (int)(c.qpos - QL.off[qid]); h.qe = h.qs + (int)c.len;
+        h.ts = (int64_t)c.tpos - TL.off[tid]; h.te = h.ts + c.len;
+        h.diag = h.ts - h.qs;
+        hc.push_back(h);
+    }
+    std::sort(hc.begin(), hc.end(), [](const HC& a, const HC& b) {
+        if (a.qid != b.qid) return a.qid < b.qid;
+        if (a.tid != b.tid) return a.tid < b.tid;
+        if (a.diag != b.diag) return a.diag < b.diag;
+        if (a.ts != b.ts) return a.ts < b.ts;
+        return a.te < b.te;
+    });
+    struct Cl { int qid, tid; int64_t tmin, tmax; int qmin, qmax; };
+    std::vector<Cl> cl;
+    for (size_t i = 0; i < hc.size();) {
+        size_t j = i; Cl c{hc[i].qid, hc[i].tid, hc[i].ts, hc[i].te, hc[i].qs, hc[i].qe};
+        const int64_t d0 = hc[i].diag;
+        while (j < hc.size() && hc[j].qid == c.qid && hc[j].tid == c.tid && hc[j].diag - d0 <= spec.diag_span) {
+            c.tmin = std::min(c.tmin, hc[j].ts); c.tmax = std::max(c.tmax, hc[j].te);
+            c.qmin = std::min(c.qmin, hc[j].qs); c.qmax = std::max(c.qmax, hc[j].qe);
+            ++j;
+        }
+        cl.push_back(c); i = j;
+    }
+    // territory: a window may not reach into the seeded extent of a neighbouring cluster of the same (query, target)
+    std::sort(cl.begin(), cl.end(), [](const Cl& a, const Cl& b) {
+        if (a.qid != b.qid) return a.qid < b.qid;
+        if (a.tid != b.tid) return a.tid < b.tid;
+        if (a.tmin != b.tmin) return a.tmin < b.tmin;
+        return a.tmax < b.tmax;
+    });
+    std::vector<Window> win; win.reserve(cl.size());
+    for (size_t i = 0; i < cl.size(); ++i) {
+        const Cl& c = cl[i];
+        const int64_t tl = TL.len[c.tid]; const int64_t qlen = QL.len[c.qid];
+        int64_t lo = c.tmin - c.qmin - spec.pad, hi = c.tmax + (qlen - c.qmax) + spec.pad;
+        if (i > 0 && cl[i - 1].qid == c.qid && cl[i - 1].tid == c.tid && cl[i - 1].tmax <= c.tmin) lo = std::max(lo, cl[i - 1].tmax);
+        if (i + 1 < cl.size() && cl[i + 1].qid == c.qid && cl[i + 1].tid == c.tid && cl[i + 1].tmin >= c.tmax) hi = std::min(hi, cl[i + 1].tmin);
+        lo = std::max<int64_t>(lo, 0); hi = std::min(hi, tl);
+        if (hi <= lo) continue;
+        win.push_back(Window{c.qid, c.tid, lo, (int)(hi - lo)});
+    }
+    st.n_windows = (int64_t)win.size();
+
+    // ---- K2: windowed Smith-Waterman with traceback ----
+    const int64_t nw = (int64_t)win.size();
+    std::vector<int32_t> score(nw), aqs(nw), aqe(nw), ats(nw), ate(nw), counts(nw * 4);
+    std::vector<int64_t> coff(nw + 1, 0);
+    uint32_t* cops = nullptr;
+    float ms_trace = 0;
+    if (nw > 0) {
+        std::vector<int64_t> qb(nw), tb(nw); std::vector<int32_t> qlv(nw), tlv(nw);
+        for (int64_t i = 0; i < nw; ++i) {
+            qb[i] = QL.off[win[i].qid]; qlv[i] = (int32_t)QL.len[win[i].qid];
+            tb[i] = TL.off[win[i].tid] + win[i].tbeg; tlv[i] = win[i].tlen;
+        }
+        pb_sw_job* J = nullptr;
+        int rc = pb_sw_job_create_views(ctx, d_qc.as<uint8_t>(), d_tc.as<uint8_t>(), qb.data(), qlv.data(), tb.data(), tlv.data(), nw, &sp, 1, &J);
+        if (rc) return rc;
+        std::unique_ptr<pb_sw_job> guard(J);
+        pb_sw_stats sst; memset(&sst, 0, sizeof(sst));
+        rc = pb_sw_job_run(ctx, J, &sst); if (rc) return rc;
+        rc = pb_sw_job_fetch(ctx, J, score.data(), aqs.data(), aqe.data(), ats.data(), ate.data()); if (rc) return rc;
+        int tl_launch = 0;
+        rc = pb_sw_trace(ctx, J, qb.data(), tb.data(), score.data(), aqs.data(), aqe.data(), ats.data(), ate.data(), counts.data(), coff.data(), &cops, &ms_trace, &tl_launch);
+        if (rc) return rc;
+        st.sw_cells = sst.cells; st.ms_sw = sst.ms_total_device; st.ms_trace = ms_trace;
+        launches += sst.kernel_launches + tl_launch;
+    }
+    std::unique_ptr<uint32_t, void (*)(void*)> cops_guard(cops, free);
+
+    // ---- host: thresholds, coordinate mapping, records ----
+    const double lam = nt ? 0.625 : 0.267, Kk = nt ? 0.41 : 0.041, emax = nt ? 1e-2 : 1.0;
+    struct Rec { pb_hit h; int64_t win; };
+    std::vector<Rec> recs; recs.reserve(nw);
+    for (int64_t i = 0; i < nw; ++i) {
+        if (score[i] <= 0) continue;
+        const Window& w = win[i];
+        const int qid = w.qid;
+        const int64_t ts = w.tbeg + ats[i], te = w.tbeg + ate[i];
+        const int nm = counts[4 * i], nx = counts[4 * i + 1], ngo = counts[4 * i + 2], ngb = counts[4 * i + 3];
+        const int cols = nm + nx + ngb;
+        pb_hit h; memset(&h, 0, sizeof(h));
+        h.q_id = qid; h.raw_score = score[i];
+        h.q_len = (int32_t)qlen_nt[qid];
+        const double m_eff = nt ? (double)qlen_nt[qid] : (double)QL.len[qid];
+        const double ev = Kk * m_eff * 5.0e6 * std::exp(-lam * (double)score[i]);
+        if (ev > emax) continue;
+        h.evalue = (float)ev;
+        if (nt) {
+            const int contig = w.tid % (int)nc; const bool minus = w.tid >= nc;
+            h.s_id = contig; h.s_len = (int32_t)tlen_nt[contig]; h.frame = 0;
+            h.q_start = aqs[i] + 1; h.q_end = aqe[i] + 1;
+            if (!minus) { h.s_start = (int32_t)ts + 1; h.s_end = (int32_t)te + 1; }
+            else { h.s_start = (int32_t)(tlen_nt[contig] - ts); h.s_end = (int32_t)(tlen_nt[contig] - te); }
+            h.aln_len = cols; h.mismatch = nx; h.gapopen = ngo;
+            h.identity = (float)((double)nm / (double)cols);
+            const int qspan = h.q_end - h.q_start + 1;
+            // same value the reference parses from blastn's 3-decimal pident column (modules/uberBlast.py:282-283)
+            const double pid = std::floor(100000.0 * (double)nm / (double)cols + 0.5) / 100000.0;
+            if (pid < prm->min_id - 0.0005 || qspan < prm->min_cov || qspan < prm->min_ratio * (double)h.q_len) continue;
+        } else {
+            const int contig = w.tid / F, f = w.tid % F;       // f: 0..5 -> frame f+1
+            const int qf = qframe[qid] + 1, rf = f + 1;
+            h.s_id = contig; h.s_len = (int32_t)tlen_nt[contig]; h.frame = rf;
+            const int64_t rl = tlen_nt[contig];
+            h.q_start = (aqs[i] + 1) * 3 + qf - 3; h.q_end = (aqe[i] + 1) * 3 + qf - 1;
+            if (rf <= 3) { h.s_start = (int32_t)((ts + 1) * 3 + rf - 3); h.s_end = (int32_t)((te + 1) * 3 + rf - 1); }
+            else { h.s_start = (int32_t)(rl - ((ts + 1) * 3 + rf - 6) + 1); h.s_end = (int32_t)(rl - ((te + 1) * 3 + rf - 4) + 1); }
+            h.aln_len = 3 * cols; h.mismatch = 3 * nx; h.gapopen = ngo;
+            const double variation = 3.0 * (double)(nx + ngb);
+            const double iden = 1.0 - std::nearbyint(variation / (3.0 * cols) * 1000.0) / 1000.0;
+            h.identity = (float)iden;
+            const int qm = aqe[i] - aqs[i] + 1;
+            if (qm * 3 < prm->min_cov || (double)qm * 3.0 / (double)h.q_len < prm->min_ratio || iden < prm->min_id - 0.0015) continue;
+        }
+        recs.push_back(Rec{h, i});
+    }
+    // duplicates (two windows converging on the same alignment) and deterministic order
+    std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) {
+        const pb_hit &x = a.h, &y = b.h;
+        if (x.q_id != y.q_id) return x.q_id < y.q_id;
+        if (x.s_id != y.s_id) return x.s_id < y.s_id;
+        if (x.s_start != y.s_start) return x.s_start < y.s_start;
+        if (x.q_start != y.q_start) return x.q_start < y.q_start;
+        if (x.s_end != y.s_end) return x.s_end < y.s_end;
+        if (x.q_end != y.q_end) return x.q_end < y.q_end;
+        return a.win < b.win;
+    });
+    std::vector<Rec> uniq; uniq.reserve(recs.size());
+    for (const Rec& r : recs) {
+        if (!uniq.empty()) {
+            const pb_hit& p = uniq.back().h;
+            if (p.q_id == r.h.q_id && p.s_id == r.h.s_id && p.s_start == r.h.s_start && p.s_end == r.h.s_end && p.q_start == r.h.q_start && p.q_end == r.h.q_end) continue;
+        }
+        uniq.push_back(r);
+    }
+    // per-query cap by raw score
+    int maxhits = prm->max_hits_per_query > 0 ? prm->max_hits_per_query : (nt ? 1000 : (prm->mode == PB_MODE_PROT6 ? 50 : 200));
+    {
+        std::vector<Rec> kept; kept.reserve(uniq.size());
+        for (size_t i = 0; i < uniq.size();) {
+            size_t j = i; while (j < uniq.size() && uniq[j].h.q_id == uniq[i].h.q_id) ++j;
+            if ((int)(j - i) > maxhits) {
+                std::vector<size_t> idx(j - i); for (size_t k = 0; k < idx.size(); ++k) idx[k] = i + k;
+                std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return uniq[a].h.raw_score > uniq[b].h.raw_score; });
+                idx.resize(maxhits); std::sort(idx.begin(), idx.end());
+                for (size_t k : idx) kept.push_back(uniq[k]);
+            } else for (size_t k = i; k < j; ++k) kept.push_back(uniq[k]);
+            i = j;
+        }
+        uniq.swap(kept);
+    }
+    int64_t ncig = 0;
+    for (const Rec& r : uniq) ncig += coff[r.win + 1] - coff[r.win];
+    pb_hit* hits = (pb_hit*)malloc(std::max<size_t>(uniq.size(), 1) * sizeof(pb_hit));
+    uint32_t* cig = (uint32_t*)malloc((size_t)std::max<int64_t>(ncig, 1) * 4);
+    if (!hits || !cig) { free(hits); free(cig); pb_set_error(ctx, "pb_search: out of host memory"); return PB_ERR_NOMEM; }
+    int64_t co = 0;
+    for (size_t i = 0; i < uniq.size(); ++i) {
+        pb_hit h = uniq[i].h;
+        const int64_t a = coff[uniq[i].win], n = coff[uniq[i].win + 1] - a;
+        h.cigar_off = (uint32_t)co; h.cigar_n = (uint32_t)n;
+        for (int64_t k = 0; k < n; ++k) {
+            uint32_t op = cops[a + k];
+            if (!nt) op = (((op >> 2) * 3) << 2) | (op & 3);      // amino-acid ops -> nucleotide units (modules/uberBlast.py:33)
+            cig[co + k] = op;
+        }
+        co += n;
+        hits[i] = h;
+    }
+    out->hits = hits; out->n_hits = (int64_t)uniq.size(); out->cigar = cig; out->n_cigar = ncig;
+    st.n_hits = out->n_hits;
+    cudaEvent_t e4 = ctx->ev[12];
+    PB_CUDA(ctx, cudaEventRecord(e4, sm));
+    PB_CUDA(ctx, cudaEventSynchronize(e4));
+    cudaEventElapsedTime(&st.ms_encode, e0, e1); cudaEventElapsedTime(&st.ms_index, e1, e2);
+    cudaEventElapsedTime(&st.ms_seed, e2, e3); cudaEventElapsedTime(&st.ms_total, e0, e4);
+    st.kernel_launches = launches;
+    if (stats) *stats = st;
+    return PB_OK;
+}

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <memory>
 #include <new>
+#include <vector>
 
 using namespace pbsw;
 
@@ -30,13 +31,13 @@ SwConfig sw_pick_config()
 // forward descriptors + sort keys.  key (descending sort): [31] needs-s32, [30:20] column blocks,
 // [19:0] query length; longest work first so the dynamic scheduler packs well, and neighbours in
 // the sorted order (which share a task / a warp) have similar shapes.
-__global__ void make_desc_fwd(const int64_t* qoff, const int64_t* toff, int n, int maxscore, int SW_W,
+__global__ void make_desc_fwd(const int64_t* qbeg, const int64_t* qend, const int64_t* tbeg, const int64_t* tend, int n, int maxscore, int SW_W,
                               PairDesc* desc, uint32_t* keys, int* ids, int* meta /*[0]=n32,[1]=maxm,[2]=maxnb*/)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    long long qo = qoff[p], to = toff[p];
-    long long m = qoff[p + 1] - qo, nn = toff[p + 1] - to;
+    long long qo = qbeg[p], to = tbeg[p];
+    long long m = qend[p] - qo, nn = tend[p] - to;
     PairDesc d;
     d.qoff = qo; d.toff = to; d.m = (int)m; d.n = (int)nn; d.target = INT_MAX; d.flags = 0;
     long long bound = (m < nn ? m : nn) * (long long)maxscore;
@@ -145,7 +146,7 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
         if (J->boundary.bytes < need) PB_CUDA(ctx, J->boundary.alloc(need, ctx->stream));
     }
     SwArgs a;
-    a.q = J->q.as<uint8_t>(); a.t = J->t.as<uint8_t>();
+    a.q = J->dq; a.t = J->dt;
     a.desc = desc; a.perm = perm;
     a.matrix = J->matrix.as<int8_t>(); a.nsym = J->params.nsym;
     a.go = J->params.gap_open; a.ge = J->params.gap_extend;
@@ -230,7 +231,64 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
     double cells = 0;
     for (int64_t p = 0; p < npairs; ++p) cells += (double)(qoff[p + 1] - qoff[p]) * (double)(toff[p + 1] - toff[p]);
     J->fwd_cells = cells;
+    J->dq = J->q.as<uint8_t>(); J->dt = J->t.as<uint8_t>();
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *job = guard.release();
+    return PB_OK;
+}
+
+// Internal: a job over "views" -- pair p aligns dq[qbeg[p] .. qbeg[p]+qlen[p]) with dt[tbeg[p] .. +tlen[p]) where dq/dt are
+// device-resident code arrays owned by the caller (used by the search path: windows of a genome, no gather).
+int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, const int64_t* qbeg, const int32_t* qlen,
+                           const int64_t* tbeg, const int32_t* tlen, int64_t npairs, const pb_score_params* params,
+                           int want_coords, pb_sw_job** job)
+{
+    if (npairs > INT_MAX / 2) { pb_set_error(ctx, "too many pairs in one batch"); return PB_ERR_LIMIT; }
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb_sw_job* J = new (std::nothrow) pb_sw_job();
+    if (!J) { pb_set_error(ctx, "out of host memory"); return PB_ERR_NOMEM; }
+    std::unique_ptr<pb_sw_job> guard(J);
+    J->npairs = npairs; J->want_coords = want_coords; J->params = *params; J->views = 1;
+    J->cfg = sw_pick_config();
+    J->dq = dq; J->dt = dt;
+    const int n = (int)npairs;
+    int8_t mat[1024]; memcpy(mat, params->matrix, 1024);
+    const int pad = params->nsym - 1;
+    int maxscore = 1;
+    for (int a = 0; a < 32; ++a) for (int b = 0; b < 32; ++b) {
+        if (a == pad || b == pad || a >= params->nsym || b >= params->nsym) mat[a * 32 + b] = PAD_SCORE;
+        else maxscore = std::max(maxscore, (int)mat[a * 32 + b]);
+    }
+    J->maxscore = maxscore;
+    PB_CUDA(ctx, J->matrix.alloc(1024, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(J->matrix.p, mat, 1024, cudaMemcpyHostToDevice, ctx->stream));
+    size_t nn = std::max(n, 1);
+    std::vector<int64_t> qe(nn), te(nn);
+    double cells = 0;
+    for (int i = 0; i < n; ++i) { qe[i] = qbeg[i] + qlen[i]; te[i] = tbeg[i] + tlen[i]; cells += (double)qlen[i] * tlen[i]; }
+    J->fwd_cells = cells;
+    PB_CUDA(ctx, J->qoff.alloc(nn * 8, ctx->stream)); PB_CUDA(ctx, J->toff.alloc(nn * 8, ctx->stream));
+    PB_CUDA(ctx, J->qend.alloc(nn * 8, ctx->stream)); PB_CUDA(ctx, J->tend.alloc(nn * 8, ctx->stream));
+    if (n) {
+        PB_CUDA(ctx, cudaMemcpyAsync(J->qoff.p, qbeg, nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->toff.p, tbeg, nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->qend.p, qe.data(), nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->tend.p, te.data(), nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PB_CUDA(ctx, J->desc.alloc(nn * sizeof(PairDesc), ctx->stream));
+    PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc), ctx->stream));
+    PB_CUDA(ctx, J->keys.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->keys_sorted.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->ids.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm_rev.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->meta.alloc(16, ctx->stream));
+    PB_CUDA(ctx, J->score.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->qe.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->te.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->qs.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->ts.alloc(nn * 4, ctx->stream));
+    PB_CUDA(ctx, J->cells.alloc(8, ctx->stream));
+    size_t tmp = 0;
+    PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, J->keys.as<uint32_t>(), J->keys_sorted.as<uint32_t>(),
+                                                            J->ids.as<int>(), J->perm.as<int>(), n, 0, 32, ctx->stream));
+    J->cub_bytes = tmp;
+    PB_CUDA(ctx, J->cub_tmp.alloc(std::max<size_t>(tmp, 16), ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
     *job = guard.release();
     return PB_OK;
 }
@@ -246,7 +304,9 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
         const int tb = 256, gb = (n + tb - 1) / tb;
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
         PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 16, ctx->stream));
-        make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(J->qoff.as<int64_t>(), J->toff.as<int64_t>(), n, J->maxscore, J->cfg.G * J->cfg.K,
+        const int64_t* qb = J->qoff.as<int64_t>(); const int64_t* tbp = J->toff.as<int64_t>();
+        const int64_t* qe_ = J->views ? J->qend.as<int64_t>() : qb + 1; const int64_t* te_ = J->views ? J->tend.as<int64_t>() : tbp + 1;
+        make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(qb, qe_, tbp, te_, n, J->maxscore, J->cfg.G * J->cfg.K,
                                                   J->desc.as<PairDesc>(), J->keys.as<uint32_t>(), J->ids.as<int>(), J->meta.as<int>());
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         size_t tmp = J->cub_bytes;

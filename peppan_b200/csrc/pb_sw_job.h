@@ -15,7 +15,10 @@ struct pb_sw_job {
     pb_score_params params;
     int maxscore = 1;
     SwConfig cfg;
-    DevBuf q, t, qoff, toff, matrix;
+    int views = 0;                       // 1: q/t are caller-owned device arrays, qoff/toff hold begins, qend/tend ends
+    const uint8_t* dq = nullptr;         // device code arrays the kernels read (owned by q/t unless views)
+    const uint8_t* dt = nullptr;
+    DevBuf q, t, qoff, toff, qend, tend, matrix;
     DevBuf desc, desc_rev, keys, keys_sorted, ids, perm, perm_rev, meta, cub_tmp;
     DevBuf score, qe, te, qs, ts, boundary, cells;
     size_t cub_bytes = 0;
@@ -23,3 +26,13 @@ struct pb_sw_job {
     int64_t qbytes = 0, tbytes = 0;
     double fwd_cells = 0;
 };
+
+int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, const int64_t* qbeg, const int32_t* qlen,
+                           const int64_t* tbeg, const int32_t* tlen, int64_t npairs, const pb_score_params* params,
+                           int want_coords, pb_sw_job** job);
+
+// Traceback over an already run job (pb_trace.cu).  qbeg/tbeg: host begins of every pair in the device code arrays.
+// Outputs as in pb_sw_align_batch.
+int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* tbeg, const int32_t* score, const int32_t* qs,
+                const int32_t* qe, const int32_t* ts, const int32_t* te, int32_t* counts, int64_t* cigar_off,
+                uint32_t** cigar_ops, float* ms_trace, int* launches);

@@ -217,33 +217,20 @@ __global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDe
 
 }  // namespace
 
-extern "C" int pb_sw_align_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t, const int64_t* toff,
-                                 int64_t npairs, const pb_score_params* params, int32_t* score, int32_t* qs, int32_t* qe,
-                                 int32_t* ts, int32_t* te, int32_t* counts, int64_t* cigar_off, uint32_t** cigar_ops,
-                                 pb_sw_stats* stats)
+int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* tbeg, const int32_t* score, const int32_t* qs,
+                const int32_t* qe, const int32_t* ts, const int32_t* te, int32_t* counts, int64_t* cigar_off,
+                uint32_t** cigar_ops, float* ms_trace_out, int* launches_out)
 {
-    if (!ctx) return PB_ERR_ARG;
-    if (!score || !qs || !qe || !ts || !te || !cigar_off || !cigar_ops) {
-        pb_set_error(ctx, "pb_sw_align_batch: score, coordinates, cigar_off and cigar_ops are required"); return PB_ERR_ARG;
-    }
+    const int64_t npairs = J->npairs;
+    const pb_score_params* params = &J->params;
     *cigar_ops = nullptr;
-    pb_sw_job* J = nullptr;
-    int rc = pb_sw_job_create(ctx, q, qoff, t, toff, npairs, params, 1, &J);
-    if (rc) return rc;
-    std::unique_ptr<pb_sw_job> guard(J);
-    pb_sw_stats st; memset(&st, 0, sizeof(st));
-    rc = pb_sw_job_run(ctx, J, &st);
-    if (rc) return rc;
-    rc = pb_sw_job_fetch(ctx, J, score, qs, qe, ts, te);
-    if (rc) return rc;
-
     // ---- traceback over the aligned pairs, in chunks bounded by the direction-buffer budget ----
     std::vector<TraceDesc> all;
     all.reserve((size_t)npairs);
     for (int64_t p = 0; p < npairs; ++p) {
         if (score[p] <= 0) continue;
         TraceDesc d;
-        d.qoff = qoff[p] + qs[p]; d.toff = toff[p] + ts[p];
+        d.qoff = qbeg[p] + qs[p]; d.toff = tbeg[p] + ts[p];
         d.M = qe[p] - qs[p] + 1; d.N = te[p] - ts[p] + 1; d.id = (int)p; d.pad = 0; d.doff = 0;
         all.push_back(d);
     }
@@ -299,7 +286,7 @@ extern "C" int pb_sw_align_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* q
         if (bstride) PB_CUDA(ctx, dbound.alloc((size_t)grid * TR_WARPS * (32 / TR_G) * bstride * sizeof(uint2), ctx->stream));
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
         TraceArgs a;
-        a.q = J->q.as<uint8_t>(); a.t = J->t.as<uint8_t>(); a.desc = ddesc.as<TraceDesc>(); a.count = (int)c.count;
+        a.q = J->dq; a.t = J->dt; a.desc = ddesc.as<TraceDesc>(); a.count = (int)c.count;
         a.counter = ctx->d_counter; a.matrix = J->matrix.as<int8_t>(); a.nsym = params->nsym; a.go = params->gap_open; a.ge = params->gap_extend;
         a.dir = ddir.as<uint32_t>(); a.boundary = bstride ? dbound.as<uint2>() : nullptr; a.bstride = bstride;
         kern<<<grid, TR_WARPS * 32, smem, ctx->stream>>>(a);
@@ -350,6 +337,34 @@ extern "C" int pb_sw_align_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* q
     }
     *cigar_ops = ops;
     if (counts) memcpy(counts, h_counts.data(), (size_t)npairs * 16);
+    if (ms_trace_out) *ms_trace_out = ms_trace;
+    if (launches_out) *launches_out = launches;
+    return PB_OK;
+}
+
+
+extern "C" int pb_sw_align_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t, const int64_t* toff,
+                                 int64_t npairs, const pb_score_params* params, int32_t* score, int32_t* qs, int32_t* qe,
+                                 int32_t* ts, int32_t* te, int32_t* counts, int64_t* cigar_off, uint32_t** cigar_ops,
+                                 pb_sw_stats* stats)
+{
+    if (!ctx) return PB_ERR_ARG;
+    if (!score || !qs || !qe || !ts || !te || !cigar_off || !cigar_ops) {
+        pb_set_error(ctx, "pb_sw_align_batch: score, coordinates, cigar_off and cigar_ops are required"); return PB_ERR_ARG;
+    }
+    *cigar_ops = nullptr;
+    pb_sw_job* J = nullptr;
+    int rc = pb_sw_job_create(ctx, q, qoff, t, toff, npairs, params, 1, &J);
+    if (rc) return rc;
+    std::unique_ptr<pb_sw_job> guard(J);
+    pb_sw_stats st; memset(&st, 0, sizeof(st));
+    rc = pb_sw_job_run(ctx, J, &st);
+    if (rc) return rc;
+    rc = pb_sw_job_fetch(ctx, J, score, qs, qe, ts, te);
+    if (rc) return rc;
+    float ms_trace = 0; int launches = 0;
+    rc = pb_sw_trace(ctx, J, qoff, toff, score, qs, qe, ts, te, counts, cigar_off, cigar_ops, &ms_trace, &launches);
+    if (rc) return rc;
     if (stats) {
         *stats = st;
         stats->ms_traceback = ms_trace;

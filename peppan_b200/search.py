@@ -1,0 +1,74 @@
+"""pb_search front-end: ctypes structures of include/peppan_b200.h and result conversion."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import ptr
+
+MODE_NT, MODE_PROT6, MODE_PROT3_SELF = 1, 2, 3
+
+
+class SeqSet(C.Structure):
+    _fields_ = [('residues', C.c_void_p), ('offsets', C.c_void_p), ('n', C.c_int64)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [('mode', C.c_int32), ('gtable', C.c_int32), ('min_id', C.c_float), ('min_cov', C.c_float),
+                ('min_ratio', C.c_float), ('max_hits_per_query', C.c_int32), ('reserved', C.c_int32 * 6)]
+
+
+class Hits(C.Structure):
+    _fields_ = [('hits', C.c_void_p), ('n_hits', C.c_int64), ('cigar', C.c_void_p), ('n_cigar', C.c_int64),
+                ('rank_offsets', C.c_void_p), ('n_ranks', C.c_int64)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [('n_query_kmers', C.c_int64), ('n_seed_hits', C.c_int64), ('n_ungapped', C.c_int64), ('n_windows', C.c_int64),
+                ('n_hits', C.c_int64), ('sw_cells', C.c_double), ('ms_encode', C.c_float), ('ms_index', C.c_float),
+                ('ms_seed', C.c_float), ('ms_sw', C.c_float), ('ms_trace', C.c_float), ('ms_total', C.c_float),
+                ('algo_bytes_seed', C.c_int64), ('kernel_launches', C.c_int32), ('reserved', C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
+
+
+HIT_DTYPE = np.dtype([('q_id', 'i4'), ('s_id', 'i4'), ('q_start', 'i4'), ('q_end', 'i4'), ('s_start', 'i4'), ('s_end', 'i4'),
+                      ('aln_len', 'i4'), ('mismatch', 'i4'), ('gapopen', 'i4'), ('raw_score', 'i4'), ('q_len', 'i4'), ('s_len', 'i4'),
+                      ('identity', 'f4'), ('evalue', 'f4'), ('frame', 'i4'), ('cigar_off', 'u4'), ('cigar_n', 'u4')])
+assert HIT_DTYPE.itemsize == 68
+
+
+def bind(lib):
+    vp = C.c_void_p
+    lib.pb_search.argtypes = [vp, C.POINTER(SeqSet), C.POINTER(SeqSet), C.POINTER(SearchParams), C.POINTER(Hits), C.POINTER(SearchStats)]
+    lib.pb_free_hits.argtypes = [C.POINTER(Hits)]
+    lib.pb_free_hits.restype = None
+    lib.pb_allgather_hits.argtypes = [vp, C.POINTER(Hits)]
+
+
+def search(ctx, q_bytes, q_off, t_bytes, t_off, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0,
+           allgather=False):
+    """Run pb_search.  Returns (hits structured array, cigar uint32 array, stats dict)."""
+    bind(ctx.lib)
+    q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8); t_bytes = np.ascontiguousarray(t_bytes, dtype=np.uint8)
+    q_off = np.ascontiguousarray(q_off, dtype=np.int64); t_off = np.ascontiguousarray(t_off, dtype=np.int64)
+    qs = SeqSet(q_bytes.ctypes.data, q_off.ctypes.data, len(q_off) - 1)
+    ts = SeqSet(t_bytes.ctypes.data, t_off.ctypes.data, len(t_off) - 1)
+    prm = SearchParams(mode=mode, gtable=gtable, min_id=min_id, min_cov=min_cov, min_ratio=min_ratio, max_hits_per_query=max_hits)
+    out, st = Hits(), SearchStats()
+    ctx.check(ctx.lib.pb_search(ctx.h, C.byref(qs), C.byref(ts), C.byref(prm), C.byref(out), C.byref(st)), 'pb_search')
+    try:
+        if allgather:
+            ctx.check(ctx.lib.pb_allgather_hits(ctx.h, C.byref(out)), 'pb_allgather_hits')
+        n, nc = out.n_hits, out.n_cigar
+        hits = np.frombuffer((C.c_char * (n * HIT_DTYPE.itemsize)).from_address(out.hits), dtype=HIT_DTYPE).copy() if n else np.zeros(0, HIT_DTYPE)
+        cigar = np.frombuffer((C.c_char * (nc * 4)).from_address(out.cigar), dtype=np.uint32).copy() if nc else np.zeros(0, np.uint32)
+        rank_off = None
+        if out.rank_offsets:
+            rank_off = np.frombuffer((C.c_char * ((out.n_ranks + 1) * 8)).from_address(out.rank_offsets), dtype=np.int64).copy()
+    finally:
+        ctx.lib.pb_free_hits(C.byref(out))
+    d = st.as_dict()
+    if allgather:
+        d['rank_offsets'] = rank_off
+    return hits, cigar, d

@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's modules/uberBlast.py on top of libpeppan_b200.
+
+Same entry points, flags and return values: ``uberBlast(args, extPool=None)``
+(modules/uberBlast.py:564-613) and ``RunBlast().run(...)`` (:326-376) whose ``tools`` dict maps
+'blastn' / 'diamond' / 'diamondself' to methods ``(ref_path, qry_path) -> ndarray(n, 15) object``
+(:327, :343-345).  Those three methods call pb_search on the GPU instead of spawning
+makeblastdb/blastn/diamond; there is no CPU fallback (a missing library or GPU raises).
+Unlike the reference (:347-349) tool errors are raised, not printed and swallowed.
+"""
+import sys
+
+import numpy as np
+
+from . import postfilter as pf
+from . import search as _search
+from . import seqio
+from ._lib import Context
+
+_CTX = None
+_OPS = 'MID'
+
+
+def get_context():
+    """Process-wide context, created on first use (after any fork: CUDA does not survive fork)."""
+    global _CTX
+    if _CTX is None:
+        _CTX = Context(0)
+    return _CTX
+
+
+def set_context(ctx):
+    global _CTX
+    _CTX = ctx
+
+
+def logger(log, pipe=sys.stderr):
+    from datetime import datetime
+    pipe.write('{0}\t{1}\n'.format(str(datetime.now()), log))
+    pipe.flush()
+
+
+def _cigar_list(cigar, off, n):
+    return [[int(o) >> 2, _OPS[int(o) & 3]] for o in cigar[off:off + n]]
+
+
+class RunBlast(object):
+    def __init__(self, ctx=None):
+        self.qrySeq = self.refSeq = None
+        self.ctx = ctx
+        self.stats = []
+
+    # ---- tools ---------------------------------------------------------------------------------
+    def _load(self, ref, qry):
+        if not self.qrySeq:
+            self.qrySeq = seqio.read_fastq(qry)
+        if not self.refSeq:
+            self.refSeq = seqio.read_fastq(ref)
+
+    def _search(self, mode):
+        ctx = self.ctx or get_context()
+        qn, qb, qo = seqio.to_seqset(self.qrySeq)
+        rn, rb, ro = seqio.to_seqset(self.refSeq)
+        hits, cigar, st = _search.search(ctx, qb, qo, rb, ro, mode, self.min_id, self.min_cov, self.min_ratio, self.table_id)
+        self.stats.append(st)
+        return qn, rn, hits, cigar
+
+    def runBlast(self, ref, qry):
+        """nt-vs-nt hits with the row layout and thresholds of runBlast + parseBlast (:482-509, :275-290)."""
+        logger('Run BLASTn starts')
+        self._load(ref, qry)
+        qn, rn, hits, cigar = self._search(_search.MODE_NT)
+        rows = []
+        for h in hits:
+            cg = _cigar_list(cigar, int(h['cigar_off']), int(h['cigar_n']))
+            gapb = sum(n for n, t in cg if t != 'M')
+            nm = int(h['aln_len']) - int(h['mismatch']) - gapb
+            iden = float('%.3f' % (100.0 * nm / int(h['aln_len']))) / 100.
+            span = int(h['q_end']) - int(h['q_start']) + 1
+            if not (iden >= self.min_id and span >= self.min_cov and span >= self.min_ratio * int(h['q_len'])):
+                continue
+            rows.append([qn[h['q_id']], rn[h['s_id']], iden, int(h['aln_len']), int(h['mismatch']), int(h['gapopen']),
+                         int(h['q_start']), int(h['q_end']), int(h['s_start']), int(h['s_end']), float(h['evalue']),
+                         int(h['raw_score']), int(h['q_len']), int(h['s_len']), cg])
+        logger('Run BLASTn finishes. Got {0} alignments'.format(len(rows)))
+        return _as_object_array(rows, 15)
+
+    def runDiamondSELF(self, ref, qry):
+        return self.runDiamond(ref, qry, mode=_search.MODE_PROT3_SELF)
+
+    def runDiamond(self, ref, qry, mode=_search.MODE_PROT6):
+        """protein-vs-translated-nt hits with the row layout of parseDiamond (:16-70)."""
+        logger('Run diamond starts')
+        self._load(ref, qry)
+        qn, rn, hits, cigar = self._search(mode)
+        rows = []
+        for h in hits:
+            cg = _cigar_list(cigar, int(h['cigar_off']), int(h['cigar_n']))
+            cl = sum(n for n, t in cg)
+            cd = [n for n, t in cg if t != 'M']
+            variation = float(int(h['mismatch']) + sum(cd))          # 3 * NM
+            iden = 1 - round(variation / cl, 3)
+            if iden < self.min_id:
+                continue
+            rows.append([qn[h['q_id']], rn[h['s_id']], iden, cl, int(variation - sum(cd)), len(cd),
+                         int(h['q_start']), int(h['q_end']), int(h['s_start']), int(h['s_end']), 0.0,
+                         int(h['raw_score']), int(h['q_len']), int(h['s_len']), cg])
+        logger('Run diamond finishes. Got {0} alignments'.format(len(rows)))
+        return _as_object_array(rows, 15)
+
+    # ---- driver --------------------------------------------------------------------------------
+    def run(self, ref, qry, methods, min_id, min_cov, min_ratio, table_id=11, n_thread=8, useProcess=False, re_score=0,
+            filter=[False, 0.9, 0.], linear_merge=[False, 300., 1.2], return_overlap=[True, 300, 0.6], fix_end=[6., 6.]):
+        tools = dict(blastn=self.runBlast, diamond=self.runDiamond, diamondself=self.runDiamondSELF)
+        self.min_id, self.min_cov, self.min_ratio, self.table_id, self.n_thread = min_id, min_cov, min_ratio, table_id, n_thread
+        # n_thread / useProcess (the reference's Pool / ThreadPool / caller's pool, :333-338) are accepted and ignored:
+        # the work runs on the GPU of this process
+        tabs = []
+        for method in methods:
+            if method.lower() in tools:
+                tabs.append(tools[method.lower()](ref, qry))
+        tabs = [b for b in tabs if b.shape[0] > 0]
+        if not tabs:
+            if return_overlap[0]:
+                return np.empty([0, 16], dtype=object), np.empty([0, 3], dtype=int)
+            return np.empty([0, 16], dtype=object)
+        rows = [list(r) for b in tabs for r in b]
+        for i, r in enumerate(rows):
+            r.append(i)
+        if re_score:
+            ref_enc = {k: pf.encode_nuc(v) for k, v in self.refSeq.items()}
+            qry_enc = {k: pf.encode_nuc(v) for k, v in self.qrySeq.items()}
+            rows = pf.rescore(rows, ref_enc, qry_enc, re_score, min_id, table_id)
+        if filter[0]:
+            rows = pf.ovl_filter(rows, filter[1], filter[2])
+        if linear_merge[0]:
+            rows = pf.linear_merge(rows, linear_merge[1], linear_merge[2])
+        pf.fix_end(rows, *fix_end)
+        overlap = pf.overlaps(rows, return_overlap[1], return_overlap[2]) if return_overlap[0] else None
+        rows = pf.final_sort(rows)
+        ncol = 17 if linear_merge[0] else 16
+        blastab = _as_object_array(rows, ncol)
+        if return_overlap[0]:
+            return blastab, overlap
+        return blastab
+
+
+def _as_object_array(rows, ncol):
+    arr = np.empty([len(rows), ncol], dtype=object)
+    for i, r in enumerate(rows):
+        for j in range(ncol):
+            arr[i, j] = r[j]
+    return arr
+
+
+def uberBlast(args, extPool=None):
+    """Argument set identical to the reference's (modules/uberBlast.py:566-593)."""
+    import argparse
+    parser = argparse.ArgumentParser(description='Five different alignment methods. ')
+    parser.add_argument('-r', '--reference', help='[INPUT; REQUIRED] filename for the reference. This is normally a genomic assembly. ', required=True)
+    parser.add_argument('-q', '--query', help='[INPUT; REQUIRED] filename for the query. This can be short-reads or genes or genomic assemblies. ', required=True)
+    parser.add_argument('-o', '--output', help='[OUTPUT; Default: None] save result to a file or to screen (stdout). Default do nothing. ', default=None)
+    parser.add_argument('--blastn', help='Run BLASTn. Slowest. Good for identities between [70, 100]', action='store_true', default=False)
+    parser.add_argument('--diamond', help='Run diamond on tBLASTn mode. Fast. Good for identities between [30-100]', action='store_true', default=False)
+    parser.add_argument('--diamondSELF', help='Run diamond on tBLASTn mode. Fast. Good for identities between [30-100]', action='store_true', default=False)
+    parser.add_argument('--gtable', help='[DEFAULT: 11] genetic table to use. 11 for bacterial genomes and 4 for Mycoplasma', default=11, type=int)
+    parser.add_argument('--min_id', help='[DEFAULT: 0.3] Minimum identity before reScore for an alignment to be kept', type=float, default=0.3)
+    parser.add_argument('--min_cov', help='[DEFAULT: 40] Minimum length for an alignment to be kept', type=float, default=40.)
+    parser.add_argument('--min_ratio', help='[DEFAULT: 0.05] Minimum length for an alignment to be kept, proportional to the length of the query', type=float, default=0.05)
+    parser.add_argument('-s', '--re_score', help='[DEFAULT: 0] Re-interpret alignment scores and identities. 0: No rescore; 1: Rescore with nucleotides; 2: Rescore with amino acid; 3: Rescore with codons', type=int, default=0)
+    parser.add_argument('-f', '--filter', help='[DEFAULT: False] Remove secondary alignments if they overlap with any other regions', default=False, action='store_true')
+    parser.add_argument('--filter_cov', help='[DEFAULT: 0.9] ', default=0.9, type=float)
+    parser.add_argument('--filter_score', help='[DEFAULT: 0] ', default=0., type=float)
+    parser.add_argument('-m', '--linear_merge', help='[DEFAULT: False] Merge consecutive alignments', default=False, action='store_true')
+    parser.add_argument('--merge_gap', help='[DEFAULT: 600] ', default=600., type=float)
+    parser.add_argument('--merge_diff', help='[DEFAULT: 1.5] ', default=1.5, type=float)
+    parser.add_argument('-O', '--return_overlap', help='[DEFAULT: False] Report overlapped alignments', default=False, action='store_true')
+    parser.add_argument('--overlap_length', help='[DEFAULT: 300] Minimum overlap to report', default=300, type=float)
+    parser.add_argument('--overlap_proportion', help='[DEFAULT: 0.6] Minimum overlap proportion to report', default=0.6, type=float)
+    parser.add_argument('-e', '--fix_end', help='[FORMAT: L,R; DEFAULT: 0,0] Extend alignment to the edges if the un-aligned regions are <= [L,R] basepairs.', default='0,0')
+    parser.add_argument('-t', '--n_thread', help='[DEFAULT: 8] Number of threads to use. ', type=int, default=1)
+    parser.add_argument('-p', '--process', help='[DEFAULT: False] Use processes instead of threads. ', action='store_true', default=False)
+    args = parser.parse_args(args)
+    if extPool is not None:
+        args.process = extPool
+    methods = [m for m in ('blastn', 'diamond', 'diamondSELF') if getattr(args, m)]
+    fix_end = list(map(float, args.fix_end.split(',')[-2:]))
+    data = RunBlast().run(args.reference, args.query, methods, args.min_id, args.min_cov, args.min_ratio, args.gtable, args.n_thread,
+                          args.process, args.re_score,
+                          [args.filter, args.filter_cov, args.filter_score],
+                          [args.linear_merge, args.merge_gap, args.merge_diff],
+                          [args.return_overlap, args.overlap_length, args.overlap_proportion], fix_end)
+    if args.output:
+        fout = sys.stdout if args.output.upper() == 'STDOUT' else open(args.output, 'w')
+        for t in (data[0] if args.return_overlap else data):
+            fout.write('\t'.join([str(tt) for tt in t]) + '\n')
+        if fout is not sys.stdout:
+            fout.close()
+    return data
+
+
+if __name__ == '__main__':
+    uberBlast(sys.argv[1:])

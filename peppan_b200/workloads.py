@@ -80,3 +80,82 @@ def random_pairs(npairs, seed, nsym_real=20, min_len=1, max_len=400, related=0.5
             tt = rng.integers(0, nsym_real, size=n, dtype=np.uint8)
         qs.append(qq); ts.append(tt)
     return qs, ts
+
+
+# ---- synthetic bacterial genomes (BASELINE.json configs[2..4]) ------------------------
+_STOPS = {(3, 0, 0), (3, 0, 2), (3, 2, 0)}          # TAA TAG TGA in A0 C1 G2 T3
+_NT = np.frombuffer(b'ACGT', dtype=np.uint8)
+
+
+def _random_gene(rng, length):
+    """codes (A0 C1 G2 T3) of an ORF: ATG, no internal stop, stop codon at the end; length % 3 == 0"""
+    nc = length // 3
+    cod = rng.integers(0, 4, size=(nc, 3), dtype=np.uint8)
+    stop = (cod[:, 0] == 3) & (((cod[:, 1] == 0) & ((cod[:, 2] == 0) | (cod[:, 2] == 2))) | ((cod[:, 1] == 2) & (cod[:, 2] == 0)))
+    cod[stop, 0] = 1                                  # TAA/TAG/TGA -> CAA/CAG/CGA
+    cod[0] = (0, 3, 2)
+    cod[-1] = (3, 0, 0)
+    return cod.reshape(-1)
+
+
+def _diverge(rng, gene, identity):
+    """substitute bases to the requested nt identity; codons that would become stops are restored"""
+    g = gene.copy()
+    mask = rng.random(g.size) >= identity
+    mask[:3] = False; mask[-3:] = False
+    g[mask] = (g[mask] + rng.integers(1, 4, size=int(mask.sum()), dtype=np.uint8)) % 4
+    cod = g.reshape(-1, 3)
+    stop = (cod[:, 0] == 3) & (((cod[:, 1] == 0) & ((cod[:, 2] == 0) | (cod[:, 2] == 2))) | ((cod[:, 1] == 2) & (cod[:, 2] == 0)))
+    stop[-1] = False
+    if stop.any():
+        cod[stop] = gene.reshape(-1, 3)[stop]
+    return cod.reshape(-1)
+
+
+def _rc_codes(c):
+    return (3 - c)[::-1]
+
+
+class GenePool(object):
+    """Ancestral pool: n_core core + n_acc accessory genes; lengths log-normal fitted to the
+    bundled E. coli examples (median 789 nt, clipped to [120, 9492], multiples of 3)."""
+
+    def __init__(self, n_core=3000, n_acc=12000, seed=SEED):
+        rng = np.random.default_rng(seed)
+        n = n_core + n_acc
+        ln = np.exp(rng.normal(np.log(789.0), 0.62, size=n))
+        ln = np.clip(ln, 120, 9492).astype(np.int64)
+        ln -= ln % 3
+        self.n_core, self.n_acc = n_core, n_acc
+        self.genes = [_random_gene(rng, int(x)) for x in ln]
+
+    def fasta_items(self):
+        return [(str(i), _NT[g].tobytes().decode()) for i, g in enumerate(self.genes)]
+
+
+def synth_genome(pool, index, n_acc_per_genome=1500, density=0.86, seed=SEED):
+    """One genome: all core genes + a random accessory subset, each copy diverged to nt identity
+    U[0.90,1.00] (2 % of copies U[0.5,0.9]; 1 % truncated pseudogenes), random strand and order,
+    random intergenic spacers for the requested coding density, one contig.
+    Returns (contig sequence str, [(ancestor id, start0, end0_exclusive, strand, identity)])."""
+    rng = np.random.default_rng(seed + 1 + index)
+    acc = pool.n_core + rng.choice(pool.n_acc, size=min(n_acc_per_genome, pool.n_acc), replace=False)
+    ids = np.concatenate([np.arange(pool.n_core), acc])
+    rng.shuffle(ids)
+    parts, annot, pos = [], [], 0
+    mean_sp = 914.0 * (1.0 / density - 1.0)
+    for gid in ids:
+        sp = int(rng.exponential(mean_sp)) + 10
+        parts.append(rng.integers(0, 4, size=sp, dtype=np.uint8)); pos += sp
+        r = rng.random()
+        iden = rng.uniform(0.5, 0.9) if r < 0.02 else rng.uniform(0.90, 1.0)
+        g = _diverge(rng, pool.genes[gid], iden)
+        if 0.02 <= r < 0.03 and g.size > 300:                       # pseudogene: truncated copy
+            g = g[:int(g.size * rng.uniform(0.4, 0.8))]
+        strand = 1 if rng.random() < 0.5 else -1
+        parts.append(g if strand > 0 else _rc_codes(g))
+        annot.append((int(gid), pos, pos + g.size, strand, float(iden)))
+        pos += g.size
+    parts.append(rng.integers(0, 4, size=50, dtype=np.uint8))
+    seq = _NT[np.concatenate(parts)].tobytes().decode()
+    return seq, annot
