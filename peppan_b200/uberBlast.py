@@ -12,7 +12,7 @@ import sys
 import numpy as np
 
 from . import postfilter as pf
-from . import search as _search
+from . import search as _srch
 from . import seqio
 from ._lib import Context
 
@@ -60,7 +60,7 @@ class RunBlast(object):
         ctx = self.ctx or get_context()
         qn, qb, qo = seqio.to_seqset(self.qrySeq)
         rn, rb, ro = seqio.to_seqset(self.refSeq)
-        hits, cigar, st = _search.search(ctx, qb, qo, rb, ro, mode, self.min_id, self.min_cov, self.min_ratio, self.table_id)
+        hits, cigar, st = _srch.search(ctx, qb, qo, rb, ro, mode, self.min_id, self.min_cov, self.min_ratio, self.table_id)
         self.stats.append(st)
         return qn, rn, hits, cigar
 
@@ -68,7 +68,7 @@ class RunBlast(object):
         """nt-vs-nt hits with the row layout and thresholds of runBlast + parseBlast (:482-509, :275-290)."""
         logger('Run BLASTn starts')
         self._load(ref, qry)
-        qn, rn, hits, cigar = self._search(_search.MODE_NT)
+        qn, rn, hits, cigar = self._search(_srch.MODE_NT)
         rows = []
         for h in hits:
             cg = _cigar_list(cigar, int(h['cigar_off']), int(h['cigar_n']))
@@ -85,9 +85,9 @@ class RunBlast(object):
         return _as_object_array(rows, 15)
 
     def runDiamondSELF(self, ref, qry):
-        return self.runDiamond(ref, qry, mode=_search.MODE_PROT3_SELF)
+        return self.runDiamond(ref, qry, mode=_srch.MODE_PROT3_SELF)
 
-    def runDiamond(self, ref, qry, mode=_search.MODE_PROT6):
+    def runDiamond(self, ref, qry, mode=_srch.MODE_PROT6):
         """protein-vs-translated-nt hits with the row layout of parseDiamond (:16-70)."""
         logger('Run diamond starts')
         self._load(ref, qry)
