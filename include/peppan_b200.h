@@ -176,6 +176,24 @@ void pb_free_hits(pb_hits* hits);
  * per-genome result files merged by the parent process (PEPPAN.py:922-990). */
 int  pb_allgather_hits(pb_ctx* ctx, pb_hits* inout);
 
+/* ---- gene clustering ------------------------------------------------------------------ */
+typedef struct {
+    int64_t n_blocks, n_pairs_verified, n_edges, n_reps;
+    double  sw_cells;
+    float   ms_total;
+    int32_t greedy_rounds;
+    int32_t kernel_launches;
+    int32_t reserved;
+} pb_cluster_stats;
+
+/* Replaces mmseqs createdb / linclust --min-seq-id min_id -c min_cov / createtsv and the
+ * representative re-election of getClust (modules/clust.py:54-92).  genes: ASCII nucleotide
+ * sequences in priority order (the order of the input file, PEPPAN.py:1023-1039).  rep_of
+ * (caller-allocated, n entries) receives for every gene the index of its representative; a
+ * representative maps to itself and is always the first member of its cluster. */
+int  pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int32_t* rep_of,
+                pb_cluster_stats* stats /* nullable */);
+
 /* Measures the issue rate of dependent-free DPX chains on all SMs (lane-ops/s): the roofline
  * denominator of the extension kernels.  which: 0 = viaddmax_s16x2, 1 = s32. */
 int pb_measure_dpx_peak(pb_ctx* ctx, int which, double* lane_ops_per_s);

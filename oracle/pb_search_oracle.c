@@ -113,7 +113,9 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                    int mode, int gtable, double min_id, double min_cov, double min_ratio, int maxhits, const int8_t* matrix21,
                    orc_hit* hits, int64_t cap, uint32_t* cigar, int64_t cigar_cap, int64_t* ncigar_out)
 {
-    const int nt = mode == 1, F = nt ? 2 : (mode == 2 ? 6 : 3), table4 = gtable == 4;
+    const int plus_only = (mode & 256) != 0;        /* clustering: coding strand only */
+    mode &= 255;
+    const int nt = mode == 1, F = nt ? (plus_only ? 1 : 2) : (mode == 2 ? 6 : 3), table4 = gtable == 4;
     const int K = nt ? 12 : 7, BASE = nt ? 4 : 10, XDROP = nt ? 20 : 12, MINU = nt ? 32 : 38, SPAN = nt ? 16 : 12, PAD = nt ? 32 : 24;
     const int go = nt ? 6 : 11, ge = nt ? 2 : 1;
     uint8_t seedmap[32]; memset(seedmap, 255, 32);
@@ -151,9 +153,12 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
         uint8_t* c = malloc(L + 1);
         for (int64_t k = 0; k < L; ++k) c[k] = ntcode(a[k]);
         if (nt) {
-            uint8_t* r = malloc(L + 1);
-            for (int64_t k = 0; k < L; ++k) r[L - 1 - k] = c[k] < 4 ? 3 - c[k] : c[k];
-            tsq[s] = c; tlen[s] = L; tsq[nc + s] = r; tlen[nc + s] = L;
+            tsq[s] = c; tlen[s] = L;
+            if (!plus_only) {
+                uint8_t* r = malloc(L + 1);
+                for (int64_t k = 0; k < L; ++k) r[L - 1 - k] = c[k] < 4 ? 3 - c[k] : c[k];
+                tsq[nc + s] = r; tlen[nc + s] = L;
+            }
         } else {
             for (int f = 0; f < F; ++f) {
                 int64_t rem = L - (f % 3), na = rem > 0 ? (rem + 2) / 3 : 0;

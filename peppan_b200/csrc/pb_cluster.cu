@@ -1,0 +1,144 @@
+// Gene clustering: pb_cluster.  Stands in for what getClust obtains from
+// `mmseqs createdb / linclust --min-seq-id I -c C / createtsv` (modules/clust.py:62-66) together
+// with the outcome rule getClust imposes on top of it: the representative of a cluster is its
+// first member in input (priority) order (modules/clust.py:72-85).
+//
+// Definition (restated by the scalar greedy of the CPU oracle): genes are visited in input
+// order; gene b joins the EARLIEST representative a < b that has a verified edge to it, else b
+// becomes a representative.  An edge (a, b) is verified when the local alignment found by the
+// nucleotide search (coding strand only) has identity >= I and covers >= C of both genes
+// (MMseqs2 --cov-mode 0).  Because only representatives can be joined, genes are processed in
+// blocks and each block is searched against {representatives so far} + {the block itself}: the
+// work is linear in the number of genes for redundant inputs, like linclust, and the result is
+// identical to the all-vs-all greedy.
+//
+// The greedy assignment itself runs on the device as a monotone fixed-point iteration: a gene is
+// decided once all its earlier neighbours are decided (K3).
+#include "pb_common.h"
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+enum : int { UNDECIDED = 0, REP = 1, MEMBER = 2 };
+
+// nodes: genes of the current block (local index x -> global first + x).  adj: CSR of earlier neighbours (global ids,
+// ascending).  Neighbours < first are representatives by construction.
+__global__ void greedy_round_kernel(const int* adj_off, const int* adj, int nb, int first, int* state, int* rep_of, int* n_changed)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nb || state[x] != UNDECIDED) return;
+    int decided = REP, rep = first + x;
+    for (int e = adj_off[x]; e < adj_off[x + 1]; ++e) {
+        const int a = adj[e];
+        int sa = a < first ? REP : state[a - first];
+        if (sa == REP) { decided = MEMBER; rep = a; break; }
+        if (sa == UNDECIDED) { decided = UNDECIDED; break; }
+    }
+    if (decided != UNDECIDED) {
+        rep_of[x] = rep;
+        __threadfence();
+        state[x] = decided;
+        atomicAdd(n_changed, 1);
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int32_t* rep_of, pb_cluster_stats* stats)
+{
+    if (!ctx || !genes || !rep_of || genes->n < 0) { pb_set_error(ctx, "pb_cluster: invalid argument"); return PB_ERR_ARG; }
+    pb_cluster_stats st; memset(&st, 0, sizeof(st));
+    const int64_t n = genes->n;
+    if (n == 0) { if (stats) *stats = st; return PB_OK; }
+    if (n > 0x7fffffff) { pb_set_error(ctx, "pb_cluster: too many genes for one call"); return PB_ERR_LIMIT; }
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t sm = ctx->stream;
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev[13], sm));
+    int64_t BLOCK_RES = 24ll << 20;                // residues of new genes per block (PB_CLUSTER_BLOCK overrides: test aid)
+    if (const char* e = getenv("PB_CLUSTER_BLOCK")) { long long v = atoll(e); if (v > 0) BLOCK_RES = v; }
+    std::vector<int> reps;                          // global ids of the representatives so far
+    std::vector<uint8_t> tbuf; std::vector<int64_t> toff;
+    std::vector<uint8_t> rep_bytes; std::vector<int64_t> rep_off(1, 0);
+    int64_t first = 0;
+    while (first < n) {
+        int64_t last = first, res = 0;
+        while (last < n && (last == first || res + (genes->offsets[last + 1] - genes->offsets[last]) <= BLOCK_RES)) {
+            res += genes->offsets[last + 1] - genes->offsets[last]; ++last;
+        }
+        const int nb = (int)(last - first), nr = (int)reps.size();
+        // targets: representatives so far, then the block
+        tbuf.assign(rep_bytes.begin(), rep_bytes.end());
+        toff.assign(rep_off.begin(), rep_off.end());
+        const uint8_t* bsrc = genes->residues + genes->offsets[first];
+        tbuf.insert(tbuf.end(), bsrc, bsrc + res);
+        for (int64_t i = first; i < last; ++i) toff.push_back(toff.back() + (genes->offsets[i + 1] - genes->offsets[i]));
+        std::vector<int64_t> qoff(nb + 1);
+        for (int i = 0; i <= nb; ++i) qoff[i] = genes->offsets[first + i] - genes->offsets[first];
+        pb_seqset qs{bsrc, qoff.data(), nb}, ts{tbuf.data(), toff.data(), (int64_t)toff.size() - 1};
+        pb_search_params prm; memset(&prm, 0, sizeof(prm));
+        prm.mode = PB_MODE_NT; prm.gtable = 11; prm.min_id = min_id - 0.005f; prm.min_cov = 0; prm.min_ratio = std::max(0.f, min_cov - 0.005f);
+        prm.max_hits_per_query = 1000; prm.reserved[0] = 1;
+        pb_hits hits; pb_search_stats sst;
+        int rc = pb_search(ctx, &qs, &ts, &prm, &hits, &sst);
+        if (rc) return rc;
+        st.n_pairs_verified += sst.n_windows; st.sw_cells += sst.sw_cells; st.kernel_launches += sst.kernel_launches;
+        // verified edges (a earlier than b)
+        std::vector<std::pair<int, int>> edges;      // (b local, a global)
+        for (int64_t h = 0; h < hits.n_hits; ++h) {
+            const pb_hit& x = hits.hits[h];
+            const int b = x.q_id;
+            const int a = x.s_id < nr ? reps[x.s_id] : (int)(first + (x.s_id - nr));
+            if (a >= first + b) continue;
+            int gapb = 0;
+            for (uint32_t k = 0; k < x.cigar_n; ++k) { uint32_t op = hits.cigar[x.cigar_off + k]; if (op & 3) gapb += (int)(op >> 2); }
+            const int nm = x.aln_len - x.mismatch - gapb;
+            const double iden = (double)nm / (double)x.aln_len;
+            const double qc = (double)(x.q_end - x.q_start + 1) / (double)x.q_len, sc = (double)(x.s_end - x.s_start + 1) / (double)x.s_len;
+            if (iden + 1e-9 >= (double)min_id && qc + 1e-9 >= (double)min_cov && sc + 1e-9 >= (double)min_cov) edges.emplace_back(b, a);
+        }
+        pb_free_hits(&hits);
+        std::sort(edges.begin(), edges.end());
+        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+        st.n_edges += (int64_t)edges.size();
+        std::vector<int> adj_off(nb + 1, 0), adj(edges.size());
+        for (auto& e : edges) adj_off[e.first + 1]++;
+        for (int i = 0; i < nb; ++i) adj_off[i + 1] += adj_off[i];
+        for (size_t i = 0; i < edges.size(); ++i) adj[i] = edges[i].second;
+        // K3: greedy fixed point on the device
+        DevBuf d_off, d_adj, d_state, d_rep, d_cnt;
+        PB_CUDA(ctx, d_off.alloc((nb + 1) * 4, sm)); PB_CUDA(ctx, d_adj.alloc(std::max<size_t>(adj.size(), 1) * 4, sm));
+        PB_CUDA(ctx, d_state.alloc(nb * 4, sm)); PB_CUDA(ctx, d_rep.alloc(nb * 4, sm)); PB_CUDA(ctx, d_cnt.alloc(4, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(d_off.p, adj_off.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, sm));
+        if (!adj.empty()) PB_CUDA(ctx, cudaMemcpyAsync(d_adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, sm));
+        PB_CUDA(ctx, cudaMemsetAsync(d_state.p, 0, nb * 4, sm));
+        int decided = 0;
+        while (decided < nb) {
+            PB_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, 4, sm));
+            greedy_round_kernel<<<(nb + 255) / 256, 256, 0, sm>>>(d_off.as<int>(), d_adj.as<int>(), nb, (int)first, d_state.as<int>(), d_rep.as<int>(), d_cnt.as<int>());
+            PB_CUDA(ctx, cudaGetLastError());
+            int c = 0;
+            PB_CUDA(ctx, cudaMemcpyAsync(&c, d_cnt.p, 4, cudaMemcpyDeviceToHost, sm));
+            PB_CUDA(ctx, cudaStreamSynchronize(sm));
+            if (c == 0) { pb_set_error(ctx, "pb_cluster: greedy iteration made no progress"); return PB_ERR_LIMIT; }
+            decided += c; st.greedy_rounds++; st.kernel_launches++;
+        }
+        PB_CUDA(ctx, cudaMemcpyAsync(rep_of + first, d_rep.p, nb * 4, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaStreamSynchronize(sm));
+        for (int i = 0; i < nb; ++i)
+            if (rep_of[first + i] == first + i) {
+                reps.push_back((int)(first + i));
+                const int64_t a = genes->offsets[first + i], L = genes->offsets[first + i + 1] - a;
+                rep_bytes.insert(rep_bytes.end(), genes->residues + a, genes->residues + a + L);
+                rep_off.push_back(rep_off.back() + L);
+            }
+        st.n_blocks++;
+        first = last;
+    }
+    st.n_reps = (int64_t)reps.size();
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev[14], sm));
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->ev[14]));
+    cudaEventElapsedTime(&st.ms_total, ctx->ev[13], ctx->ev[14]);
+    if (stats) *stats = st;
+    return PB_OK;
+}

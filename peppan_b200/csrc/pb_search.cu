@@ -370,12 +370,13 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t sm = ctx->stream;
     const bool nt = prm->mode == PB_MODE_NT;
-    const int F = nt ? 2 : (prm->mode == PB_MODE_PROT6 ? 6 : 3);
+    const bool plus_only = nt && (prm->reserved[0] & 1);     // clustering: coding-strand comparisons only
+    const int F = nt ? (plus_only ? 1 : 2) : (prm->mode == PB_MODE_PROT6 ? 6 : 3);
     const int table4 = prm->gtable == 4;
     const SeedSpec spec = nt ? nt_spec() : aa_spec();
     const int64_t nq = query->n, nc = target->n;
     const int64_t qbytes = query->offsets[nq], tbytes = target->offsets[nc];
-    if (qbytes >= (int64_t)0xfffffff0 || tbytes * (nt ? 2 : 1) >= (int64_t)0xfffffff0) {
+    if (qbytes >= (int64_t)0xfffffff0 || tbytes * 2 >= (int64_t)0xfffffff0) {
         pb_set_error(ctx, "pb_search: a single call is limited to 4 G residues per side; block the input"); return PB_ERR_LIMIT;
     }
     cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10], e3 = ctx->ev[11];
@@ -414,17 +415,17 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     DevBuf d_qc, d_tc, d_tmpq, d_tmpt, d_off1, d_off2, d_frame, d_aalen;
     if (nt) {
         QL = make_layout(qlen_nt);
-        std::vector<int64_t> tl2(2 * nc);
-        for (int64_t i = 0; i < nc; ++i) { tl2[i] = tlen_nt[i]; tl2[nc + i] = tlen_nt[i]; }
+        std::vector<int64_t> tl2((size_t)F * nc);
+        for (int64_t i = 0; i < nc; ++i) for (int f = 0; f < F; ++f) tl2[f * nc + i] = tlen_nt[i];
         TL = make_layout(tl2);
         PB_CUDA(ctx, d_qc.alloc(QL.total + 64, sm)); PB_CUDA(ctx, d_tc.alloc(TL.total + 64, sm));
         fill_u8<<<(unsigned)((QL.total + 64 + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), SENT, QL.total + 64);
         fill_u8<<<(unsigned)((TL.total + 64 + 255) / 256), 256, 0, sm>>>(d_tc.as<uint8_t>(), SENT, TL.total + 64);
-        PB_CUDA(ctx, d_off1.alloc(nq * 8, sm)); PB_CUDA(ctx, d_off2.alloc(2 * nc * 8, sm));
+        PB_CUDA(ctx, d_off1.alloc(nq * 8, sm)); PB_CUDA(ctx, d_off2.alloc((size_t)F * nc * 8, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off1.p, QL.off.data(), nq * 8, cudaMemcpyHostToDevice, sm));
-        PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), 2 * nc * 8, cudaMemcpyHostToDevice, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), (size_t)F * nc * 8, cudaMemcpyHostToDevice, sm));
         encode_nt_kernel<<<(unsigned)std::min<int64_t>(nq, 4096), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), nullptr, nq, d_qc.as<uint8_t>());
-        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nc, 4096), 1024, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), d_off2.as<int64_t>() + nc, nc, d_tc.as<uint8_t>());
+        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nc, 4096), 1024, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), plus_only ? nullptr : d_off2.as<int64_t>() + nc, nc, d_tc.as<uint8_t>());
         PB_CUDA(ctx, cudaGetLastError()); launches += 4;
     } else {
         // codon table in amino-acid codes
