@@ -73,6 +73,23 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def profiled_traffic():
+    """dram bytes per launch of the forward kernel from the committed ncu --set full summary, or None"""
+    path = os.path.join(ROOT, 'profiles', 'r01_sw_kernel_ncu_full.txt')
+    try:
+        rd = wr = None
+        for line in open(path):
+            if 'REV' in line or line.startswith('void pbsw'):
+                pass
+            if line.startswith('dram__bytes_read.sum') and rd is None:
+                rd = float(line.split()[1]) * 1e6
+            if line.startswith('dram__bytes_write.sum') and wr is None:
+                wr = float(line.split()[1]) * 1e6
+        return None if rd is None or wr is None else rd + wr
+    except Exception:
+        return None
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -238,10 +255,11 @@ def main():
                    'forward_ms_per_step': fwd_ms / args.steps, 'reverse_ms_per_step': rev_ms / args.steps,
                    'forward_gcups': cells / (fwd_ms / args.steps * 1e-3) / 1e9, 'score_checksum': checksum,
                    'sm_count': info['sm_count']},
-        'roofline': {'bound': 'int_dpx', 'kernel': 'sw_kernel<16,19,packed,forward>', 'achieved': fwd_rate / 1e12, 'peak': peak / 1e12,
-                     'unit': 'T lane-instr/s', 'frac': fwd_rate / peak, 'traffic': None,
+        'roofline': {'bound': 'int_dpx', 'kernel': 'sw_kernel<G16,K19,R2,long-chain,s16x2,forward>', 'achieved': fwd_rate / 1e12, 'peak': peak / 1e12,
+                     'unit': 'T lane-instr/s', 'frac': fwd_rate / peak, 'traffic': profiled_traffic(),
                      'note': 'achieved = 3.5 DPX instr/cell (SURVEY 8d) x cells / forward-kernel time; peak = live dependent-free '
-                             'VIADDMNMX.S16x2 issue rate on all SMs (pb_measure_dpx_peak); HBM is not the bound (2 B/pair-cell row)'},
+                             'VIADDMNMX.S16x2 issue rate on all SMs (pb_measure_dpx_peak); traffic = dram bytes per forward launch from '
+                             'profiles/r01_sw_kernel_ncu_full.txt (1M pairs): ~ the 0.6 GB of sequences, HBM is not the bound'},
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(est['h2d_bytes']), 'd2h_bytes_per_step': int(est['d2h_bytes']),
                 'ms_per_step': e2e_ms / args.steps},
