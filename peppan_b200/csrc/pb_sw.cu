@@ -173,9 +173,12 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     return PB_OK;
 }
 
-extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t,
-                                const int64_t* toff, int64_t npairs, const pb_score_params* params,
-                                int want_coords, pb_sw_job** job)
+// up == nullptr: uploads on the context stream and the call returns synchronised.  Otherwise the uploads are
+// enqueued on `up` (after the allocations, ordered by ev_alloc) and ev_ready is recorded behind them; pb_sw_job_run
+// makes the context stream wait for it, so the copy overlaps whatever the context stream is still computing.
+static int sw_job_create_impl(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t,
+                              const int64_t* toff, int64_t npairs, const pb_score_params* params,
+                              int want_coords, pb_sw_job** job, cudaStream_t up, cudaEvent_t ev_alloc, cudaEvent_t ev_ready)
 {
     if (!ctx || !job || !params || npairs < 0 || (npairs > 0 && (!q || !qoff || !t || !toff))) {
         pb_set_error(ctx, "pb_sw_job_create: invalid argument"); return PB_ERR_ARG;
@@ -208,12 +211,16 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
     PB_CUDA(ctx, J->t.alloc(std::max<int64_t>(J->tbytes, 16), ctx->stream));
     PB_CUDA(ctx, J->qoff.alloc((npairs + 1) * 8, ctx->stream));
     PB_CUDA(ctx, J->toff.alloc((npairs + 1) * 8, ctx->stream));
+    cudaStream_t us = up ? up : ctx->stream;
+    if (up) { PB_CUDA(ctx, cudaEventRecord(ev_alloc, ctx->stream)); PB_CUDA(ctx, cudaStreamWaitEvent(up, ev_alloc, 0)); }
     if (npairs) {
-        PB_CUDA(ctx, cudaMemcpyAsync(J->q.p, q, J->qbytes, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(J->t.p, t, J->tbytes, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(J->qoff.p, qoff, (npairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(J->toff.p, toff, (npairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        // offsets first: they may live in pageable memory (a blocking staged copy) and must not wait behind the bulk copies
+        PB_CUDA(ctx, cudaMemcpyAsync(J->qoff.p, qoff, (npairs + 1) * 8, cudaMemcpyHostToDevice, us));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->toff.p, toff, (npairs + 1) * 8, cudaMemcpyHostToDevice, us));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->q.p, q, J->qbytes, cudaMemcpyHostToDevice, us));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->t.p, t, J->tbytes, cudaMemcpyHostToDevice, us));
     }
+    if (up) { PB_CUDA(ctx, cudaEventRecord(ev_ready, up)); J->ev_ready = ev_ready; }
     size_t nn = std::max(n, 1);
     PB_CUDA(ctx, J->desc.alloc(nn * sizeof(PairDesc), ctx->stream));
     PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc), ctx->stream));
@@ -232,9 +239,16 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
     for (int64_t p = 0; p < npairs; ++p) cells += (double)(qoff[p + 1] - qoff[p]) * (double)(toff[p + 1] - toff[p]);
     J->fwd_cells = cells;
     J->dq = J->q.as<uint8_t>(); J->dt = J->t.as<uint8_t>();
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!up) PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *job = guard.release();
     return PB_OK;
+}
+
+extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, const uint8_t* t,
+                                const int64_t* toff, int64_t npairs, const pb_score_params* params,
+                                int want_coords, pb_sw_job** job)
+{
+    return sw_job_create_impl(ctx, q, qoff, t, toff, npairs, params, want_coords, job, nullptr, nullptr, nullptr);
 }
 
 // Internal: a job over "views" -- pair p aligns dq[qbeg[p] .. qbeg[p]+qlen[p]) with dt[tbeg[p] .. +tlen[p]) where dq/dt are
@@ -302,6 +316,7 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
     float ms_f = 0, ms_r = 0;
     if (n > 0) {
         const int tb = 256, gb = (n + tb - 1) / tb;
+        if (J->ev_ready) { PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, J->ev_ready, 0)); J->ev_ready = nullptr; }
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
         PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 16, ctx->stream));
         const int64_t* qb = J->qoff.as<int64_t>(); const int64_t* tbp = J->toff.as<int64_t>();
@@ -380,30 +395,57 @@ extern "C" int pb_sw_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, c
 {
     if (!ctx) return PB_ERR_ARG;
     if (!score) { pb_set_error(ctx, "pb_sw_batch: score output is required"); return PB_ERR_ARG; }
-    pb_sw_job* J = nullptr;
+    if (npairs < 0 || (npairs > 0 && (!q || !qoff || !t || !toff)) || !params) { pb_set_error(ctx, "pb_sw_batch: invalid argument"); return PB_ERR_ARG; }
     const int want = (qs || ts) ? 1 : 0;
-    cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // Large batches are cut into chunks and software-pipelined: chunk c+1 is uploaded on the copy stream while the
+    // kernels of chunk c run on the context stream.
+    int64_t CHUNK = 1 << 18;
+    if (const char* e = getenv("PB_SW_CHUNK")) { long long v = atoll(e); if (v > 0) CHUNK = v; }
+    const int64_t nchunk = npairs <= CHUNK + CHUNK / 2 ? 1 : (npairs + CHUNK - 1) / CHUNK;
+    cudaEvent_t e0 = ctx->ev[4], e3 = ctx->ev[7];
     PB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    int rc = pb_sw_job_create(ctx, q, qoff, t, toff, npairs, params, want, &J);
+    pb_sw_stats tot; memset(&tot, 0, sizeof(tot));
+    struct Slot { pb_sw_job* J = nullptr; std::vector<int64_t> qo, to; int64_t first = 0, n = 0; };
+    Slot slots[2];
+    auto destroy = [&](Slot& s) { if (s.J) { pb_sw_job_destroy(ctx, s.J); s.J = nullptr; } };
+    auto stage = [&](int64_t c, Slot& s) -> int {
+        s.first = c * ((npairs + nchunk - 1) / nchunk);
+        s.n = std::min<int64_t>((npairs + nchunk - 1) / nchunk, npairs - s.first);
+        if (s.n < 0) s.n = 0;
+        const int64_t* qo = qoff + s.first; const int64_t* to = toff + s.first;
+        if (nchunk > 1) {
+            s.qo.resize(s.n + 1); s.to.resize(s.n + 1);
+            for (int64_t i = 0; i <= s.n; ++i) { s.qo[i] = qo[i] - qo[0]; s.to[i] = to[i] - to[0]; }
+        }
+        return sw_job_create_impl(ctx, npairs ? q + qo[0] : q, nchunk > 1 ? s.qo.data() : qo, npairs ? t + to[0] : t, nchunk > 1 ? s.to.data() : to,
+                                  s.n, params, want, &s.J, nchunk > 1 ? ctx->copy_stream : nullptr,
+                                  ctx->ev_pipe[2 * (c & 1)], ctx->ev_pipe[2 * (c & 1) + 1]);
+    };
+    int rc = stage(0, slots[0]);
     if (rc) return rc;
-    PB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-    pb_sw_stats st; memset(&st, 0, sizeof(st));
-    rc = pb_sw_job_run(ctx, J, &st);
-    if (rc) { pb_sw_job_destroy(ctx, J); return rc; }
-    PB_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
-    rc = pb_sw_job_fetch(ctx, J, score, qs, qe, ts, te);
-    if (rc) { pb_sw_job_destroy(ctx, J); return rc; }
+    for (int64_t c = 0; c < nchunk; ++c) {
+        Slot& cur = slots[c & 1];
+        if (c + 1 < nchunk) { rc = stage(c + 1, slots[(c + 1) & 1]); if (rc) { destroy(cur); return rc; } }
+        pb_sw_stats st; memset(&st, 0, sizeof(st));
+        rc = pb_sw_job_run(ctx, cur.J, &st);
+        if (!rc) rc = pb_sw_job_fetch(ctx, cur.J, score + cur.first, qs ? qs + cur.first : nullptr, qe ? qe + cur.first : nullptr,
+                                      ts ? ts + cur.first : nullptr, te ? te + cur.first : nullptr);
+        if (rc) { destroy(slots[0]); destroy(slots[1]); return rc; }
+        tot.cells += st.cells; tot.cells_reverse += st.cells_reverse; tot.ms_forward += st.ms_forward; tot.ms_reverse += st.ms_reverse;
+        tot.ms_total_device += st.ms_total_device; tot.kernel_launches += st.kernel_launches; tot.n_s32_pairs += st.n_s32_pairs;
+        destroy(cur);
+    }
     PB_CUDA(ctx, cudaEventRecord(e3, ctx->stream));
     PB_CUDA(ctx, cudaEventSynchronize(e3));
     if (stats) {
-        *stats = st;
-        cudaEventElapsedTime(&stats->ms_h2d, e0, e1);
-        cudaEventElapsedTime(&stats->ms_d2h, e2, e3);
-        stats->h2d_bytes = J->qbytes + J->tbytes + 16 * (npairs + 1) + 1024;
+        *stats = tot;
+        float ms_all = 0; cudaEventElapsedTime(&ms_all, e0, e3);
+        stats->ms_h2d = 0; stats->ms_d2h = 0;          // overlapped with the kernels; see ms_total_device vs wall time
+        stats->h2d_bytes = (npairs ? qoff[npairs] + toff[npairs] : 0) + 16 * (npairs + nchunk) + 1024 * nchunk;
         int nout = 1 + (qe ? 1 : 0) + (te ? 1 : 0) + (want ? ((qs ? 1 : 0) + (ts ? 1 : 0)) : 0);
         stats->d2h_bytes = (int64_t)nout * 4 * npairs;
     }
-    pb_sw_job_destroy(ctx, J);
     return PB_OK;
 }
 

@@ -25,6 +25,7 @@ struct pb_sw_job {
     int n32 = 0;
     int64_t qbytes = 0, tbytes = 0;
     double fwd_cells = 0;
+    cudaEvent_t ev_ready = nullptr;      // uploads enqueued on the copy stream finish here (pipelined pb_sw_batch)
 };
 
 int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, const int64_t* qbeg, const int32_t* qlen,
