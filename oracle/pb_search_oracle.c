@@ -12,10 +12,12 @@
  *
  * Specification (constants must match peppan_b200/csrc/pb_search.cu):
  *  nucleotide: codes A0 C1 G2 T3 other 4; targets = every contig and its reverse complement;
- *     seeds = exact 12-mers without ambiguous bases; +2/-3; X-drop 20; ungapped cut-off 32;
+ *     seeds = exact 12-mers without ambiguous bases; +2/-3; X-drop 20; ungapped cut-off 32; a cluster
+ *     opens a window if its best HSP >= 44 or its distinct HSPs sum to >= 56;
  *     diag span 16; window pad 32; SW +2/-3 gap 6/2; E <= 1e-2 with lambda 0.625 K 0.41.
  *  protein: codes ARNDCQEGHILKMFPSTWYVX; queries = best forward frame; targets = 6 (or 3) frames;
- *     seeds = 7-mers over {AST}{RK}{ND}{C}{QE}{G}{H}{ILVM}{FYW}{P}; BLOSUM62; X-drop 12; cut-off 38;
+ *     seeds = 7-mers over {AST}{RK}{ND}{C}{QE}{G}{H}{ILVM}{FYW}{P}; BLOSUM62; X-drop 12; cut-off 45;
+ *     window if best HSP >= 56 or sum >= 90;
  *     diag span 12; pad 24; SW BLOSUM62 gap 11/1; E <= 1 with lambda 0.267 K 0.041.
  *  common: a seed is extended only if the residues preceding it on both sequences do NOT agree
  *     in the seed alphabet (leftmost seed of a run); HSPs of one (query, target) sorted by
@@ -67,7 +69,7 @@ static uint8_t codon_aa(const uint8_t* nt, int64_t L, int64_t p0, int rev, int t
     return (uint8_t)(strchr(AA, CODON11[idx]) - AA);
 }
 
-typedef struct { int qid, tid; int64_t diag, ts, te; int qs, qe; } hsp_t;
+typedef struct { int qid, tid; int64_t diag, ts, te; int qs, qe; int score; } hsp_t;
 typedef struct { int qid, tid; int64_t tmin, tmax; int qmin, qmax; } clu_t;
 
 static int cmp_hsp(const void* a, const void* b)
@@ -116,8 +118,8 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
     const int plus_only = (mode & 256) != 0;        /* clustering: coding strand only */
     mode &= 255;
     const int nt = mode == 1, F = nt ? (plus_only ? 1 : 2) : (mode == 2 ? 6 : 3), table4 = gtable == 4;
-    const int K = nt ? 12 : 7, BASE = nt ? 4 : 10, XDROP = nt ? 20 : 12, MINU = nt ? 32 : 38, SPAN = nt ? 16 : 12, PAD = nt ? 32 : 24;
-    const int go = nt ? 6 : 11, ge = nt ? 2 : 1;
+    const int K = nt ? 12 : 7, BASE = nt ? 4 : 10, XDROP = nt ? 20 : 12, MINU = nt ? 32 : 45, SPAN = nt ? 16 : 12, PAD = nt ? 32 : 24;
+    const int go = nt ? 6 : 11, ge = nt ? 2 : 1, CMAX = nt ? 44 : 56, CSUM = nt ? 56 : 90;
     uint8_t seedmap[32]; memset(seedmap, 255, 32);
     int8_t mat[1024]; memset(mat, 0, 1024);
     if (nt) {
@@ -219,7 +221,7 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                         if (lbest < MINU) continue;
                         if (nh == hcap) { hcap *= 2; hs = realloc(hs, sizeof(hsp_t) * hcap); }
                         hsp_t h; h.qid = qi; h.tid = (int)t; h.qs = (int)(qp - llen); h.qe = h.qs + rlen + llen;
-                        h.ts = tp - llen; h.te = h.ts + rlen + llen; h.diag = h.ts - h.qs;
+                        h.ts = tp - llen; h.te = h.ts + rlen + llen; h.diag = h.ts - h.qs; h.score = lbest;
                         hs[nh++] = h;
                     }
                 }
@@ -229,12 +231,16 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
             clu_t* cl = malloc(sizeof(clu_t) * (nh + 1)); int64_t ncl = 0;
             for (int64_t i = 0; i < nh;) {
                 clu_t c = {hs[i].qid, hs[i].tid, hs[i].ts, hs[i].te, hs[i].qs, hs[i].qe}; int64_t d0 = hs[i].diag, j = i;
+                int smax = 0; long long ssum = 0;
                 while (j < nh && hs[j].qid == c.qid && hs[j].tid == c.tid && hs[j].diag - d0 <= SPAN) {
+                    int dup = j > i && hs[j].diag == hs[j - 1].diag && hs[j].ts == hs[j - 1].ts && hs[j].te == hs[j - 1].te;
+                    if (!dup) { if (hs[j].score > smax) smax = hs[j].score; ssum += hs[j].score; }
                     if (hs[j].ts < c.tmin) c.tmin = hs[j].ts; if (hs[j].te > c.tmax) c.tmax = hs[j].te;
                     if (hs[j].qs < c.qmin) c.qmin = hs[j].qs; if (hs[j].qe > c.qmax) c.qmax = hs[j].qe;
                     ++j;
                 }
-                cl[ncl++] = c; i = j;
+                if (smax >= CMAX || ssum >= CSUM) cl[ncl++] = c;
+                i = j;
             }
             qsort(cl, ncl, sizeof(clu_t), cmp_clu);
             rec_t* recs = malloc(sizeof(rec_t) * (ncl + 1)); int64_t nr = 0, nwin = 0;

@@ -20,6 +20,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <memory>
 #include <vector>
 
@@ -36,6 +37,7 @@ struct SeedSpec {
     int min_ungapped;    // ungapped HSP score needed to open a window
     int diag_span;       // HSPs of one (query, target) whose diagonals differ by <= this share a window
     int pad;             // window slack on both sides
+    int clu_max, clu_sum; // a cluster opens a window if its best HSP scores >= clu_max or its distinct HSPs sum to >= clu_sum
     uint8_t seedmap[32]; // scoring code -> seed code, 255 = cannot seed
 };
 
@@ -45,20 +47,21 @@ struct DevSpec {
     int8_t score[1024];
 };
 
-// nucleotide: exact 12-mers (a superset of blastn -word_size 17 seeds), +2/-3, X-drop 20, cut-off 32
+// nucleotide: exact 12-mers (a superset of blastn -word_size 17 seeds), +2/-3, X-drop 20, HSP cut-off 32,
+// window if best HSP >= 44 or HSPs sum >= 56
 SeedSpec nt_spec()
 {
-    SeedSpec s{12, 4, 20, 32, 16, 32, {}};
+    SeedSpec s{12, 4, 20, 32, 16, 32, 44, 56, {}};
     for (int i = 0; i < 32; ++i) s.seedmap[i] = 255;
     for (int i = 0; i < 4; ++i) s.seedmap[i] = (uint8_t)i;
     return s;
 }
 
 // protein: 7-mers over the reduced alphabet {AST}{RK}{ND}{C}{QE}{G}{H}{ILVM}{FYW}{P}, BLOSUM62
-// ungapped X-drop 12, cut-off 38.  Codes follow seqcodec.AA = ARNDCQEGHILKMFPSTWYVX.
+// ungapped X-drop 12, HSP cut-off 45, window if best HSP >= 56 or HSPs sum >= 90.  Codes follow seqcodec.AA.
 SeedSpec aa_spec()
 {
-    SeedSpec s{7, 10, 12, 38, 12, 24, {}};
+    SeedSpec s{7, 10, 12, 45, 12, 24, 56, 90, {}};
     for (int i = 0; i < 32; ++i) s.seedmap[i] = 255;
     const char* aa = "ARNDCQEGHILKMFPSTWYV";
     const char* grp[10] = {"AST", "RK", "ND", "C", "QE", "G", "H", "ILVM", "FYW", "P"};
@@ -77,16 +80,21 @@ __device__ __forceinline__ uint8_t nt_code(uint8_t c)
                  case 'T': case 't': return 3; default: return 4; }
 }
 
-// one block per sequence: dst[doff[s] .. ) = codes, optionally also the reverse complement at roff[s]
+// dst[doff[s] .. ) = codes of sequence s, optionally also the reverse complement at roff[s].  Work items are
+// (sequence, 4 KB chunk) pairs so that a few long contigs still fill the machine; chunk_off[s] = first work item of s.
 __global__ void encode_nt_kernel(const uint8_t* src, const int64_t* soff, const int64_t* doff, const int64_t* roff, int64_t nseq,
                                  uint8_t* dst)
 {
-    for (int64_t s = blockIdx.x; s < nseq; s += gridDim.x) {
+    constexpr int64_t CH = 4096;
+    for (int64_t s = blockIdx.y; s < nseq; s += gridDim.y) {
         const int64_t a = soff[s], L = soff[s + 1] - a, d = doff[s];
-        for (int64_t i = threadIdx.x; i < L; i += blockDim.x) {
-            uint8_t c = nt_code(src[a + i]);
-            dst[d + i] = c;
-            if (roff) dst[roff[s] + (L - 1 - i)] = c < 4 ? (uint8_t)(3 - c) : c;
+        for (int64_t c0 = (int64_t)blockIdx.x * CH; c0 < L; c0 += (int64_t)gridDim.x * CH) {
+            const int64_t hi = c0 + CH < L ? c0 + CH : L;
+            for (int64_t i = c0 + threadIdx.x; i < hi; i += blockDim.x) {
+                uint8_t c = nt_code(src[a + i]);
+                dst[d + i] = c;
+                if (roff) dst[roff[s] + (L - 1 - i)] = c < 4 ? (uint8_t)(3 - c) : c;
+            }
         }
     }
 }
@@ -124,16 +132,16 @@ __device__ __forceinline__ uint8_t translate_codon(const uint8_t* nt, int64_t L,
     return c_codon[idx];
 }
 
-// targets: frame f (1..6) of contig s -> dst[doff[s*F + f-1] ..)
+// targets: frame f (1..6) of contig s -> dst[doff[s*F + f-1] ..); grid (chunks, contig*frame)
 __global__ void translate_targets_kernel(const uint8_t* nt, const int64_t* ntoff, const int64_t* doff, int64_t nseq, int F,
                                          int table4, uint8_t* dst)
 {
-    for (int64_t sf = blockIdx.x; sf < nseq * F; sf += gridDim.x) {
+    for (int64_t sf = blockIdx.y; sf < nseq * F; sf += gridDim.y) {
         const int64_t s = sf / F; const int f = (int)(sf % F);
         const int64_t a = ntoff[s], L = ntoff[s + 1] - a;
         const int off = f % 3; const bool rev = f >= 3;
         const int64_t rem = L - off, na = rem > 0 ? (rem + 2) / 3 : 0;
-        for (int64_t i = threadIdx.x; i < na; i += blockDim.x)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += (int64_t)gridDim.x * blockDim.x)
             dst[doff[sf] + i] = translate_codon(nt + a, L, off + 3 * i, rev, table4);
     }
 }
@@ -424,8 +432,8 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         PB_CUDA(ctx, d_off1.alloc(nq * 8, sm)); PB_CUDA(ctx, d_off2.alloc((size_t)F * nc * 8, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off1.p, QL.off.data(), nq * 8, cudaMemcpyHostToDevice, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), (size_t)F * nc * 8, cudaMemcpyHostToDevice, sm));
-        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nq, 4096), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), nullptr, nq, d_qc.as<uint8_t>());
-        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nc, 4096), 1024, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), plus_only ? nullptr : d_off2.as<int64_t>() + nc, nc, d_tc.as<uint8_t>());
+        encode_nt_kernel<<<dim3(1, (unsigned)std::min<int64_t>(nq, 32768)), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), nullptr, nq, d_qc.as<uint8_t>());
+        encode_nt_kernel<<<dim3(256, (unsigned)std::min<int64_t>(nc, 256)), 256, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), plus_only ? nullptr : d_off2.as<int64_t>() + nc, nc, d_tc.as<uint8_t>());
         PB_CUDA(ctx, cudaGetLastError()); launches += 4;
     } else {
         // codon table in amino-acid codes
@@ -435,8 +443,8 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         PB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_codon, codon, 64, 0, cudaMemcpyHostToDevice, sm));
         // nucleotide codes of both sets (plain, no sentinels) as translation input
         PB_CUDA(ctx, d_tmpq.alloc(std::max<int64_t>(qbytes, 16), sm)); PB_CUDA(ctx, d_tmpt.alloc(std::max<int64_t>(tbytes, 16), sm));
-        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nq, 4096), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_qsoff.as<int64_t>(), nullptr, nq, d_tmpq.as<uint8_t>());
-        encode_nt_kernel<<<(unsigned)std::min<int64_t>(nc, 4096), 1024, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_tsoff.as<int64_t>(), nullptr, nc, d_tmpt.as<uint8_t>());
+        encode_nt_kernel<<<dim3(1, (unsigned)std::min<int64_t>(nq, 32768)), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_qsoff.as<int64_t>(), nullptr, nq, d_tmpq.as<uint8_t>());
+        encode_nt_kernel<<<dim3(256, (unsigned)std::min<int64_t>(nc, 256)), 256, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_tsoff.as<int64_t>(), nullptr, nc, d_tmpt.as<uint8_t>());
         PB_CUDA(ctx, d_frame.alloc(nq * 4, sm)); PB_CUDA(ctx, d_aalen.alloc(nq * 4, sm));
         choose_frame_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), nq, table4, d_frame.as<int>(), d_aalen.as<int>());
         PB_CUDA(ctx, cudaGetLastError()); launches += 3;
@@ -455,7 +463,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         PB_CUDA(ctx, cudaMemcpyAsync(d_off1.p, QL.off.data(), nq * 8, cudaMemcpyHostToDevice, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), nc * F * 8, cudaMemcpyHostToDevice, sm));
         translate_queries_kernel<<<(unsigned)std::min<int64_t>(nq, 8192), 128, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), d_frame.as<int>(), nq, table4, d_qc.as<uint8_t>());
-        translate_targets_kernel<<<(unsigned)std::min<int64_t>(nc * F, 8192), 1024, 0, sm>>>(d_tmpt.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), nc, F, table4, d_tc.as<uint8_t>());
+        translate_targets_kernel<<<dim3(128, (unsigned)std::min<int64_t>(nc * F, 1024)), 256, 0, sm>>>(d_tmpt.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), nc, F, table4, d_tc.as<uint8_t>());
         PB_CUDA(ctx, cudaGetLastError()); launches += 4;
     }
     PB_CUDA(ctx, cudaEventRecord(e1, sm));
@@ -513,15 +521,18 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     st.algo_bytes_seed = LT + 9 * LQ + 16 * (int64_t)cnts[2];
     PB_CUDA(ctx, cudaEventRecord(e3, sm));
 
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const bool dbg = getenv("PB_DEBUG_TIMING") != nullptr;
+    double h0 = now();
     // ---- host: clusters -> windows ----
-    struct HC { int qid, tid; int64_t diag; int64_t ts, te; int qs, qe; };
+    struct HC { int qid, tid; int64_t diag; int64_t ts, te; int qs, qe; int score; };
     std::vector<HC> hc; hc.reserve(cands.size());
     for (const Cand& c : cands) {
         int qid = find_seq(QL, c.qpos), tid = find_seq(TL, c.tpos);
         HC h; h.qid = qid; h.tid = tid;
         h.qs = (int)(c.qpos - QL.off[qid]); h.qe = h.qs + (int)c.len;
         h.ts = (int64_t)c.tpos - TL.off[tid]; h.te = h.ts + c.len;
-        h.diag = h.ts - h.qs;
+        h.diag = h.ts - h.qs; h.score = c.score;
         hc.push_back(h);
     }
     std::sort(hc.begin(), hc.end(), [](const HC& a, const HC& b) {
@@ -536,12 +547,16 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     for (size_t i = 0; i < hc.size();) {
         size_t j = i; Cl c{hc[i].qid, hc[i].tid, hc[i].ts, hc[i].te, hc[i].qs, hc[i].qe};
         const int64_t d0 = hc[i].diag;
+        int smax = 0; long long ssum = 0;
         while (j < hc.size() && hc[j].qid == c.qid && hc[j].tid == c.tid && hc[j].diag - d0 <= spec.diag_span) {
+            const bool dup = j > i && hc[j].diag == hc[j - 1].diag && hc[j].ts == hc[j - 1].ts && hc[j].te == hc[j - 1].te;
+            if (!dup) { smax = std::max(smax, hc[j].score); ssum += hc[j].score; }
             c.tmin = std::min(c.tmin, hc[j].ts); c.tmax = std::max(c.tmax, hc[j].te);
             c.qmin = std::min(c.qmin, hc[j].qs); c.qmax = std::max(c.qmax, hc[j].qe);
             ++j;
         }
-        cl.push_back(c); i = j;
+        if (smax >= spec.clu_max || ssum >= spec.clu_sum) cl.push_back(c);
+        i = j;
     }
     // territory: a window may not reach into the seeded extent of a neighbouring cluster of the same (query, target)
     std::sort(cl.begin(), cl.end(), [](const Cl& a, const Cl& b) {
@@ -562,6 +577,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         win.push_back(Window{c.qid, c.tid, lo, (int)(hi - lo)});
     }
     st.n_windows = (int64_t)win.size();
+    double h1 = now();
 
     // ---- K2: windowed Smith-Waterman with traceback ----
     const int64_t nw = (int64_t)win.size();
@@ -582,6 +598,18 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         pb_sw_stats sst; memset(&sst, 0, sizeof(sst));
         rc = pb_sw_job_run(ctx, J, &sst); if (rc) return rc;
         rc = pb_sw_job_fetch(ctx, J, score.data(), aqs.data(), aqe.data(), ats.data(), ate.data()); if (rc) return rc;
+        // thresholds that do not need the path (E-value, aligned query span) are applied before the traceback
+        {
+            const double lam0 = nt ? 0.625 : 0.267, K0 = nt ? 0.41 : 0.041, emax0 = nt ? 1e-2 : 1.0;
+            for (int64_t i = 0; i < nw; ++i) {
+                if (score[i] <= 0) continue;
+                const int qid = win[i].qid;
+                const double m_eff = nt ? (double)qlen_nt[qid] : (double)QL.len[qid];
+                const double ev = K0 * m_eff * 5.0e6 * std::exp(-lam0 * (double)score[i]);
+                const double qspan = (double)(aqe[i] - aqs[i] + 1) * (nt ? 1.0 : 3.0);
+                if (ev > emax0 || qspan < prm->min_cov || qspan < prm->min_ratio * (double)qlen_nt[qid]) score[i] = 0;
+            }
+        }
         int tl_launch = 0;
         rc = pb_sw_trace(ctx, J, qb.data(), tb.data(), score.data(), aqs.data(), aqe.data(), ats.data(), ate.data(), counts.data(), coff.data(), &cops, &ms_trace, &tl_launch);
         if (rc) return rc;
@@ -589,6 +617,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         launches += sst.kernel_launches + tl_launch;
     }
     std::unique_ptr<uint32_t, void (*)(void*)> cops_guard(cops, free);
+    double h2 = now();
 
     // ---- host: thresholds, coordinate mapping, records ----
     const double lam = nt ? 0.625 : 0.267, Kk = nt ? 0.41 : 0.041, emax = nt ? 1e-2 : 1.0;
@@ -698,6 +727,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     cudaEventElapsedTime(&st.ms_encode, e0, e1); cudaEventElapsedTime(&st.ms_index, e1, e2);
     cudaEventElapsedTime(&st.ms_seed, e2, e3); cudaEventElapsedTime(&st.ms_total, e0, e4);
     st.kernel_launches = launches;
+    if (dbg) fprintf(stderr, "[pb_search] host: cluster/window %.1f ms, sw+trace (incl. host) %.1f ms, records %.1f ms\n", h1 - h0, h2 - h1, now() - h2);
     if (stats) *stats = st;
     return PB_OK;
 }
