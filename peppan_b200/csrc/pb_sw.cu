@@ -13,6 +13,8 @@ using namespace pbsw;
 namespace {
 
 constexpr int PAD_SCORE = -16;
+constexpr int WAVE_G = 32, WAVE_K = 19, WAVE_W = WAVE_G * WAVE_K, WAVE_WARPS = 8;
+constexpr int LONG_COLS = 4 * WAVE_W - 1, LONG_ROWS = 1024;      // pairs beyond this shape use the wavefront kernel
 
 SwConfig sw_pick_config()
 {
@@ -44,13 +46,14 @@ __global__ void make_desc_fwd(const int64_t* qbeg, const int64_t* qend, const in
     int s32 = bound > 32000 ? 1 : 0;
     int nb = (int)((nn + SW_W - 1) / SW_W);
     if (m <= 0 || nn <= 0) { nb = 0; s32 = 0; }
-    d.flags = s32;
+    const int lng = (nn > LONG_COLS && m > LONG_ROWS && nn < (1 << 20) && m < (1 << 20)) ? 1 : 0;   // long alignments go to the wavefront kernel
+    d.flags = s32 | (lng << 1);
     desc[p] = d;
-    keys[p] = ((uint32_t)s32 << 31) | ((uint32_t)min(nb, 2047) << 20) | (uint32_t)min((long long)0xfffff, m);
+    keys[p] = ((uint32_t)s32 << 31) | ((uint32_t)lng << 30) | ((uint32_t)min(nb, 1023) << 20) | (uint32_t)min((long long)0xfffff, m);
     ids[p] = p;
     if (s32) atomicAdd(&meta[0], 1);
-    if (nb > 1) { atomicMax(&meta[1], (int)m); }
-    atomicMax(&meta[2], nb);
+    if (lng) { atomicAdd(&meta[s32 ? 3 : 4], 1); atomicMax(&meta[5], (int)m); atomicMax(&meta[6], (int)((nn + WAVE_W - 1) / WAVE_W)); }
+    else { if (nb > 1) atomicMax(&meta[1], (int)m); atomicMax(&meta[2], nb); }
 }
 
 // reverse descriptors: prefixes ending at the forward end cell, looking for the forward score.
@@ -66,12 +69,21 @@ __global__ void make_desc_rev(const PairDesc* fwd, const int* score, const int* 
     if (S > 0) { d.m = qe[p] + 1; d.n = te[p] + 1; d.target = S; }
     else { d.m = 0; d.n = 0; d.target = 0; }
     int nb = (d.n + SW_W - 1) / SW_W;
+    const int s32 = d.flags & 1;
+    const int lng = (d.n > LONG_COLS && d.m > LONG_ROWS && d.n < (1 << 20) && d.m < (1 << 20)) ? 1 : 0;
+    d.flags = s32 | (lng << 1);
     desc[p] = d;
-    keys[p] = ((uint32_t)(d.flags & 1) << 31) | ((uint32_t)min(nb, 32767) << 16) | (uint32_t)min(S, 65535);
+    keys[p] = ((uint32_t)s32 << 31) | ((uint32_t)lng << 30) | ((uint32_t)min(nb, 16383) << 16) | (uint32_t)min(S, 65535);
     ids[p] = p;
-    if (d.flags & 1) atomicAdd(&meta[0], 1);
-    if (nb > 1) atomicMax(&meta[1], d.m);
-    atomicMax(&meta[2], nb);
+    if (s32) atomicAdd(&meta[0], 1);
+    if (lng) { atomicAdd(&meta[s32 ? 3 : 4], 1); atomicMax(&meta[5], d.m); atomicMax(&meta[6], (d.n + WAVE_W - 1) / WAVE_W); }
+    else { if (nb > 1) atomicMax(&meta[1], d.m); atomicMax(&meta[2], nb); }
+}
+
+__global__ void gather_shapes(const PairDesc* desc, const int* perm, int first, int count, int2* out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { PairDesc d = desc[perm[first + i]]; out[i] = make_int2(d.m, d.n); }
 }
 
 __global__ void fill_int(int* p, int v, int n)
@@ -107,10 +119,10 @@ size_t sw_smem_bytes(const SwConfig& c, bool packed, int nsym)
     return 1024 + (size_t)c.WARPS * NG * (packed ? 2 : 1) * nsym * c.G * KP;
 }
 
-template <int G, int K, int R, bool LONG, int WARPS, bool PACKED, bool REV>
+template <int G, int K, int R, bool LONG, int WARPS, bool PACKED, bool REV, bool WAVE>
 cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = sw_kernel<G, K, R, LONG, PACKED, REV, WARPS>;
+    auto k = sw_kernel<G, K, R, LONG, PACKED, REV, WARPS, WAVE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, WARPS * 32, smem, st>>>(a);
@@ -120,9 +132,8 @@ cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t s
 template <bool PACKED, bool REV>
 cudaError_t sw_dispatch(const SwConfig& c, const SwArgs& a, int grid, size_t smem, cudaStream_t st)
 {
-#define PB_CFG(g, k, r, lg, w) if (c.G == g && c.K == k && c.R == r && c.LONG == lg) return sw_launch_one<g, k, r, (lg != 0), w, PACKED, REV>(a, grid, smem, st);
-    PB_CFG(16, 19, 1, 0, 8) PB_CFG(16, 19, 2, 0, 8) PB_CFG(16, 19, 2, 1, 8) PB_CFG(16, 19, 1, 1, 8)
-    PB_CFG(8, 19, 2, 0, 8) PB_CFG(8, 19, 2, 1, 8) PB_CFG(8, 38, 1, 0, 4)
+#define PB_CFG(g, k, r, lg, w) if (c.G == g && c.K == k && c.R == r && c.LONG == lg) return sw_launch_one<g, k, r, (lg != 0), w, PACKED, REV, false>(a, grid, smem, st);
+    PB_CFG(16, 19, 2, 1, 8) PB_CFG(16, 19, 1, 0, 8) PB_CFG(16, 19, 2, 0, 8)
 #undef PB_CFG
     return cudaErrorInvalidValue;
 }
@@ -133,11 +144,12 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
 {
     const int n = (int)J->npairs;
     const SwConfig& c = J->cfg;
-    // boundary buffer sized from the device-side maxima; count of s32 pairs (they sort first)
-    int meta[3];
+    // device-side maxima and class counts: [0] s32 pairs, [1] max m / [2] max column blocks of the regular class,
+    // [3] s32 long pairs, [4] s16 long pairs, [5] max m / [6] max column blocks of the long (wavefront) class
+    int meta[8];
     PB_CUDA(ctx, cudaMemcpyAsync(meta, J->meta.p, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int n32 = meta[0];
+    const int n32 = meta[0], n32L = meta[3], n16L = meta[4];
     J->n32 = n32;
     int bstride = meta[2] > 1 ? ((meta[1] + 63) / 64) * 64 : 0;
     const int grid = ctx->sm_count;
@@ -150,24 +162,74 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     a.desc = desc; a.perm = perm;
     a.matrix = J->matrix.as<int8_t>(); a.nsym = J->params.nsym;
     a.go = J->params.gap_open; a.ge = J->params.gap_extend;
-    a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride;
     a.out_score = J->score.as<int>();
     a.out_a = rev ? J->qs.as<int>() : J->qe.as<int>();
     a.out_b = rev ? J->ts.as<int>() : J->te.as<int>();
     a.cells = rev ? J->cells.as<unsigned long long>() : nullptr;
+    a.progress = nullptr; a.wsub = nullptr; a.wbase = nullptr; a.nsub = 0; a.wkey = nullptr; a.wdone = nullptr;
     a.dbg = getenv("PB_SW_DBG") ? atoi(getenv("PB_SW_DBG")) : 0;
     PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
 
     const size_t smem16 = sw_smem_bytes(c, true, J->params.nsym), smem32 = sw_smem_bytes(c, false, J->params.nsym);
     if (smem16 > ctx->smem_optin) { pb_set_error(ctx, "nsym=%d needs %zu B shared memory (> %zu)", J->params.nsym, smem16, ctx->smem_optin); return PB_ERR_LIMIT; }
-    if (n32 > 0) {
-        a.first = 0; a.count = n32; a.counter = ctx->d_counter + (rev ? 2 : 0);
-        PB_CUDA(ctx, rev ? (sw_dispatch<false, true>(c, a, grid, smem32, ctx->stream)) : (sw_dispatch<false, false>(c, a, grid, smem32, ctx->stream)));
-        ++*launches;
-    }
-    if (n - n32 > 0) {
-        a.first = n32; a.count = n - n32; a.counter = ctx->d_counter + (rev ? 3 : 1);
-        PB_CUDA(ctx, rev ? (sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream)) : (sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream)));
+    // sorted order: [s32 long][s32 regular][s16 long][s16 regular]
+    struct Range { int first, count; bool packed, wave; };
+    const Range ranges[4] = { {0, n32L, false, true}, {n32L, n32 - n32L, false, false}, {n32, n16L, true, true}, {n32 + n16L, n - n32 - n16L, true, false} };
+    int slot = 0;
+    for (const Range& r : ranges) {
+        if (r.count <= 0) continue;
+        a.first = r.first; a.count = r.count; a.counter = ctx->d_counter + (rev ? 8 : 0) + slot++;
+        cudaError_t e;
+        if (r.wave) {
+            // wavefront kernel: sub-tasks = (task, column block) in task-major order, one warp each
+            const int npair = r.packed ? 2 : 1;
+            const int ntask = (r.count + npair - 1) / npair;
+            DevBuf d_shape;
+            PB_CUDA(ctx, d_shape.alloc((size_t)r.count * sizeof(int2), ctx->stream));
+            gather_shapes<<<(r.count + 255) / 256, 256, 0, ctx->stream>>>(desc, perm, r.first, r.count, d_shape.as<int2>());
+            PB_CUDA(ctx, cudaGetLastError()); ++*launches;
+            std::vector<int2> shp(r.count);
+            PB_CUDA(ctx, cudaMemcpyAsync(shp.data(), d_shape.p, (size_t)r.count * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            std::vector<int> base(ntask + 1, 0);
+            std::vector<int2> sub;
+            int maxm = 1;
+            for (int t = 0; t < ntask; ++t) {
+                int nmax = 0;
+                for (int k = 0; k < npair && t * npair + k < r.count; ++k) { nmax = std::max(nmax, shp[t * npair + k].y); maxm = std::max(maxm, shp[t * npair + k].x); }
+                const int nb = std::max(1, (nmax + WAVE_W - 1) / WAVE_W);
+                base[t + 1] = base[t] + nb;
+                for (int b = 0; b < nb; ++b) sub.push_back(make_int2(t, b));
+            }
+            const int wstride = ((maxm + 63) / 64) * 64;
+            const size_t nslot = (size_t)base[ntask];
+            if (nslot * wstride * sizeof(uint2) > ((size_t)24 << 30)) { pb_set_error(ctx, "long-alignment border buffer would need %zu bytes; split the batch", nslot * wstride * sizeof(uint2)); return PB_ERR_LIMIT; }
+            DevBuf& wb = J->wbound; DevBuf& wp = J->wprog;
+            if (wb.bytes < nslot * wstride * sizeof(uint2)) PB_CUDA(ctx, wb.alloc(nslot * wstride * sizeof(uint2), ctx->stream));
+            // progress | done | keys | base | sub in one scratch buffer
+            const size_t o_done = nslot * 4, o_key = ((o_done + (size_t)ntask * 4 + 7) / 8) * 8, o_base = o_key + (size_t)ntask * 16,
+                         o_sub = ((o_base + (size_t)(ntask + 1) * 4 + 7) / 8) * 8, total = o_sub + sub.size() * sizeof(int2);
+            if (wp.bytes < total) PB_CUDA(ctx, wp.alloc(total, ctx->stream));
+            PB_CUDA(ctx, cudaMemsetAsync(wp.p, 0, o_base, ctx->stream));
+            PB_CUDA(ctx, cudaMemcpyAsync((char*)wp.p + o_base, base.data(), (size_t)(ntask + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+            PB_CUDA(ctx, cudaMemcpyAsync((char*)wp.p + o_sub, sub.data(), sub.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+            PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // host staging vectors are released below
+            a.boundary = wb.as<uint2>(); a.bstride = wstride;
+            a.progress = (int*)wp.p; a.wdone = (int*)((char*)wp.p + o_done); a.wkey = (unsigned long long*)((char*)wp.p + o_key);
+            a.wbase = (const int*)((char*)wp.p + o_base); a.wsub = (const int2*)((char*)wp.p + o_sub); a.nsub = (int)sub.size();
+            const SwConfig wc{WAVE_G, WAVE_K, 2, 1, WAVE_WARPS};
+            const int wgrid = std::max(1, std::min(grid, (int)((sub.size() + WAVE_WARPS - 1) / WAVE_WARPS)));
+            const size_t smem = sw_smem_bytes(wc, r.packed, J->params.nsym);
+            if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, true, true, true>(a, wgrid, smem, ctx->stream)
+                                  : sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, true, false, true>(a, wgrid, smem, ctx->stream);
+            else e = rev ? sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, false, true, true>(a, wgrid, smem, ctx->stream)
+                         : sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, false, false, true>(a, wgrid, smem, ctx->stream);
+        } else {
+            a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride; a.progress = nullptr; a.nsub = 0;
+            if (r.packed) e = rev ? sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream) : sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream);
+            else e = rev ? sw_dispatch<false, true>(c, a, grid, smem32, ctx->stream) : sw_dispatch<false, false>(c, a, grid, smem32, ctx->stream);
+        }
+        PB_CUDA(ctx, e);
         ++*launches;
     }
     return PB_OK;
@@ -226,7 +288,7 @@ static int sw_job_create_impl(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff
     PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc), ctx->stream));
     PB_CUDA(ctx, J->keys.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->keys_sorted.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->ids.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm_rev.alloc(nn * 4, ctx->stream));
-    PB_CUDA(ctx, J->meta.alloc(16, ctx->stream));
+    PB_CUDA(ctx, J->meta.alloc(32, ctx->stream));
     PB_CUDA(ctx, J->score.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->qe.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->te.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->qs.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->ts.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->cells.alloc(8, ctx->stream));
@@ -293,7 +355,7 @@ int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, co
     PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc), ctx->stream));
     PB_CUDA(ctx, J->keys.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->keys_sorted.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->ids.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->perm_rev.alloc(nn * 4, ctx->stream));
-    PB_CUDA(ctx, J->meta.alloc(16, ctx->stream));
+    PB_CUDA(ctx, J->meta.alloc(32, ctx->stream));
     PB_CUDA(ctx, J->score.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->qe.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->te.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->qs.alloc(nn * 4, ctx->stream)); PB_CUDA(ctx, J->ts.alloc(nn * 4, ctx->stream));
     PB_CUDA(ctx, J->cells.alloc(8, ctx->stream));
@@ -318,7 +380,7 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
         const int tb = 256, gb = (n + tb - 1) / tb;
         if (J->ev_ready) { PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, J->ev_ready, 0)); J->ev_ready = nullptr; }
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-        PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 16, ctx->stream));
+        PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 32, ctx->stream));
         const int64_t* qb = J->qoff.as<int64_t>(); const int64_t* tbp = J->toff.as<int64_t>();
         const int64_t* qe_ = J->views ? J->qend.as<int64_t>() : qb + 1; const int64_t* te_ = J->views ? J->tend.as<int64_t>() : tbp + 1;
         make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(qb, qe_, tbp, te_, n, J->maxscore, J->cfg.G * J->cfg.K,
@@ -331,7 +393,7 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
         if (rc) return rc;
         PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
         if (J->want_coords) {
-            PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 16, ctx->stream));
+            PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 32, ctx->stream));
             PB_CUDA(ctx, cudaMemsetAsync(J->cells.p, 0, 8, ctx->stream));
             fill_int<<<gb, tb, 0, ctx->stream>>>(J->qs.as<int>(), -1, n);
             fill_int<<<gb, tb, 0, ctx->stream>>>(J->ts.as<int>(), -1, n);

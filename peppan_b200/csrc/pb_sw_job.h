@@ -5,8 +5,7 @@
 
 // Kernel shapes: G lanes per task, K columns per lane, WARPS per (persistent, 1/SM) block.
 struct SwConfig { int G, K, R, LONG, WARPS; };
-static constexpr SwConfig SW_CONFIGS[] = { {16, 19, 2, 1, 8}, {16, 19, 1, 0, 8}, {16, 19, 2, 0, 8}, {16, 19, 1, 1, 8},
-                                    {8, 19, 2, 0, 8}, {8, 19, 2, 1, 8}, {8, 38, 1, 0, 4} };
+static constexpr SwConfig SW_CONFIGS[] = { {16, 19, 2, 1, 8}, {16, 19, 1, 0, 8}, {16, 19, 2, 0, 8} };
 
 
 struct pb_sw_job {
@@ -20,7 +19,7 @@ struct pb_sw_job {
     const uint8_t* dt = nullptr;
     DevBuf q, t, qoff, toff, qend, tend, matrix;
     DevBuf desc, desc_rev, keys, keys_sorted, ids, perm, perm_rev, meta, cub_tmp;
-    DevBuf score, qe, te, qs, ts, boundary, cells;
+    DevBuf score, qe, te, qs, ts, boundary, wbound, wprog, cells;
     size_t cub_bytes = 0;
     int n32 = 0;
     int64_t qbytes = 0, tbytes = 0;

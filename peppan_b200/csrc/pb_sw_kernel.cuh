@@ -39,6 +39,14 @@
 // strip into K spare registers (moves issue on the FMA pipe, which the DP leaves idle).  After
 // the last block the winning lane scans its snapshot for the first column holding the maximum.
 //
+// WAVE = true is the long-alignment variant: the unit of work is one column block (608 columns) of one task, taken
+// by a whole warp (G = 32) from a global list in (task, block) order.  The blocks of a task run as a pipeline spread
+// over the machine: the warp owning block b starts a row as soon as the warp owning block b-1 has published the border
+// cells of that row (global buffer + release/acquire progress counter, polled by lane 0 only, >= 32 rows behind so
+// one acquire covers many steps).  A 10 kb x 10 kb alignment then takes ~m/R + 32*blocks steps instead of
+// blocks * m/R.  Producers are always fetched before their consumers and never wait on them, so there is no deadlock.
+// The per-block maxima of a task are combined with a 64-bit atomicMax on (score, ~row, ~col).
+//
 // REV = true runs the same DP on the reversed prefixes q[0..m) and t[0..n) (m = qe+1, n = te+1
 // from the forward pass) and stops once the known score has been seen and every lane has passed
 // that row: this yields the alignment start (oracle/pb_oracle.c, "start").
@@ -72,10 +80,21 @@ struct SwArgs {
     int* out_a;
     int* out_b;
     unsigned long long* cells;   // REV: DP cells actually swept (statistic), nullable
+    int* progress;          // WAVE: rows published per (task, column block) border (zeroed before launch)
+    const int2* wsub;       // WAVE: sub-task list (task, column block) in launch order
+    const int* wbase;       // WAVE: first border slot of every task (prefix sum of its column blocks)
+    int nsub;
+    unsigned long long* wkey;   // WAVE: per (task, pair) packed best cell, combined with atomicMax (zeroed before launch)
+    int* wdone;             // WAVE: finished sub-tasks per task (zeroed before launch)
     int dbg;                // tuning aid (PB_SW_DBG): bit0 skip max tracking, bit1 skip shuffles -- results invalid
 };
 
 __device__ __forceinline__ uint32_t shfl_up_g(uint32_t v, int G) { return __shfl_up_sync(0xffffffffu, v, 1, G); }
+
+// release / acquire on a progress counter in global memory (WAVE hand-off between warps)
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) { uint2 v; asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory"); return v; }
 
 // prmt.b32 in its default mode: selector nibble bit 3 replicates the sign of the chosen byte
 // (the __byte_perm intrinsic only documents the low 3 bits, so the PTX form is used directly).
@@ -115,7 +134,7 @@ template <> struct Ops<false> {
     static __device__ __forceinline__ int lo(uint32_t) { return 0; }
 };
 
-template <int G, int K, int R, bool LONG, bool PACKED, bool REV, int WARPS>
+template <int G, int K, int R, bool LONG, bool PACKED, bool REV, int WARPS, bool WAVE>
 __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
 {
     using O = Ops<PACKED>;
@@ -126,6 +145,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     constexpr int W = G * K;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int BIGROW = 0x3fffffff;
+    static_assert(!WAVE || G == 32, "the wavefront variant uses whole warps");
 
     extern __shared__ __align__(16) uint8_t smem[];
     int8_t* smat = reinterpret_cast<int8_t*>(smem);
@@ -140,7 +160,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     const int pairBytes = nsym * rowBytes;
     uint8_t* prof = smem + 1024 + (size_t)((warp * NG + g) * NPAIR) * pairBytes;
     const int gwarp = blockIdx.x * WARPS + warp;
-    uint2* mybound = a.boundary ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
+    uint2* mybound = (a.boundary && !WAVE) ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
+    uint2* wavebound = nullptr;
+    int* waveprog = nullptr;
 
     const uint32_t NEG_GE = O::bcast(-a.ge);
     const uint32_t GOE = O::bcast(a.go + a.ge);
@@ -148,9 +170,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     const int ntasks = (a.count + NPAIR - 1) / NPAIR;
 
     for (;;) {
-        int bundle = 0;
+        int bundle = 0, wblock = 0;
         if (lane == 0) bundle = atomicAdd(a.counter, 1);
         bundle = __shfl_sync(FULL, bundle, 0);
+        if (WAVE) {
+            if (bundle >= a.nsub) break;
+            const int2 sub = a.wsub[bundle];
+            bundle = sub.x; wblock = sub.y;
+            wavebound = a.boundary + (size_t)a.wbase[sub.x] * a.bstride;
+            waveprog = a.progress + a.wbase[sub.x];
+        }
         if (bundle * NG >= ntasks) break;
         const int task = bundle * NG + g;
 
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
         int bvalid = mw;                       // rows of the block border written by the previous block
         unsigned long long swept = 0;
 
-        for (int b = 0; b < nblocks; ++b) {
+        for (int b = WAVE ? wblock : 0; b < (WAVE ? wblock + 1 : nblocks); ++b) {
             // ---- build the lane-private profile columns of this block ----
             const int col0 = b * W + l * K;
             {
@@ -230,6 +259,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             const int rows_here = min(mw, rowcap);
             int slimit = (rows_here + R - 1) / R + G - 1;
             bool armed = false;
+            int published = 0;                  // WAVE: rows of the left border known to be complete
+            uint2 pref[R];                      // WAVE: border cells of the next step, loaded one step ahead
+            bool pref_ok = false;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) pref[rr] = make_uint2(0u, 0u);
+            if (WAVE) { mybound = wavebound + (size_t)b * a.bstride; }
+            const uint2* leftbound = WAVE ? (b > 0 ? wavebound + (size_t)(b - 1) * a.bstride : nullptr) : mybound;
 
             // prefetch the row symbols of step 0
             int cA[R], cB[R];
@@ -277,9 +313,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 }
                 if (b > 0) {
                     if (l == 0) {
+                        if (WAVE) {
+                            // the warp owning block b-1 publishes its progress every 16 steps; stay >= 32 rows behind it
+                            // so that one acquire covers many steps and the border cells can be loaded a step ahead
+                            const int need = min(r0 + R, mw);
+                            if (published < need) {
+                                const int want = min(r0 + R + 32, mw);
+                                while ((published = ld_acquire(waveprog + (b - 1))) < want) __nanosleep(200);
+                                pref_ok = false;
+                            }
 #pragma unroll
-                        for (int rr = 0; rr < R; ++rr)
-                            if ((unsigned)(r0 + rr) < (unsigned)bvalid) { uint2 v = mybound[r0 + rr]; hl[rr] = v.x; fh[rr] = v.y; }
+                            for (int rr = 0; rr < R; ++rr)
+                                if ((unsigned)(r0 + rr) < (unsigned)mw) {
+                                    uint2 v = pref_ok ? pref[rr] : ld_volatile_u2(leftbound + r0 + rr);
+                                    hl[rr] = v.x; fh[rr] = v.y;
+                                }
+                            const int nr0 = r0 + R;
+                            pref_ok = (nr0 < mw) && (min(nr0 + R, mw) <= published);
+                            if (pref_ok) {
+#pragma unroll
+                                for (int rr = 0; rr < R; ++rr)
+                                    if ((unsigned)(nr0 + rr) < (unsigned)mw) pref[rr] = ld_volatile_u2(leftbound + nr0 + rr);
+                            }
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < R; ++rr)
+                                if ((unsigned)(r0 + rr) < (unsigned)bvalid) { uint2 v = leftbound[r0 + rr]; hl[rr] = v.x; fh[rr] = v.y; }
+                        }
                     }
                 }
                 uint32_t hdiag[R];
@@ -338,6 +398,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
 #pragma unroll
                         for (int rr = 0; rr < R; ++rr)
                             if ((unsigned)(r0 + rr) < (unsigned)mw) mybound[r0 + rr] = make_uint2(hlast[rr], fout[rr]);
+                        if (WAVE && r0 + R > 0 && ((s & 15) == 15 || r0 + R >= mw)) st_release(waveprog + b, min(r0 + R, mw));
                     }
                 }
 
@@ -350,7 +411,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
 #pragma unroll
                     for (int rr = 0; rr < R; ++rr) fin = O::max2(fin, stepmax[rr]);
                     uint32_t ch = fin ^ best;
-                    if (b > 0) {   // a later block may hold an equal maximum on an earlier row
+                    if (!WAVE && b > 0) {   // a later block of this lane may hold an equal maximum on an earlier row
 #pragma unroll
                         for (int rr = R - 1; rr >= 0; --rr) {
                             if (O::hi(stepmax[rr]) == O::hi(best) && r0 + rr < browA && O::hi(best) > 0) ch |= PACKED ? 0xffff0000u : 1u;
@@ -386,7 +447,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                         }
                     }
                 }
-                if (REV) {
+                if (REV && !WAVE) {
                     bool fa = (O::hi(best) >= tgtA);
                     bool fb = PACKED ? (O::lo(best) >= tgtB) : true;
                     unsigned ba = __ballot_sync(FULL, fa), bb = __ballot_sync(FULL, fb);
@@ -403,7 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 swept += (unsigned long long)min((slimit - (G - 1)) * R, mw) * (unsigned long long)min(nw - b * W, W);
                 if (armed) rowcap = min(rowcap, (slimit - (G - 1)) * R);
             }
-            bvalid = min(mw, (slimit - (G - 1)) * R);
+            if (!WAVE) bvalid = min(mw, (slimit - (G - 1)) * R);
             __syncwarp();
         }
 
@@ -432,6 +493,44 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 unsigned long long other = __shfl_xor_sync(FULL, key, o);
                 key = other < key ? other : key;
             }
+            bool writer = (l == 0);
+            if (WAVE) {
+                // combine the blocks of the task: larger score wins, then the row-major-first cell; the warp that
+                // finishes last decodes the result
+                if (lane == 0) {
+                    if (S > 0 && key != ~0ull) {
+                        const unsigned long long row = key >> 32, col = key & 0xffffffffull;
+                        atomicMax(a.wkey + (size_t)task * 2 + h, ((unsigned long long)S << 40) | ((0xfffffull - row) << 20) | (0xfffffull - col));
+                    }
+                    __threadfence();
+                    int fin = 0;
+                    if (h == NPAIR - 1) fin = atomicAdd(a.wdone + task, 1) + 1;
+                    writer = (h == NPAIR - 1) && (fin == nblocks);
+                }
+                writer = __shfl_sync(FULL, (int)writer, 0) != 0;
+                if (!writer) continue;
+            }
+            if (WAVE) {
+                // the last finisher writes both pairs of the task
+#pragma unroll
+                for (int h2 = 0; h2 < NPAIR; ++h2) {
+                    __threadfence();
+                    const unsigned long long pk = *reinterpret_cast<volatile unsigned long long*>(a.wkey + (size_t)task * 2 + h2);
+                    const int S2 = (int)(pk >> 40);
+                    const int id2 = (h2 == 0) ? idA : idB; const int mm2 = (h2 == 0) ? mA : mB, nn2 = (h2 == 0) ? nA : nB;
+                    if (l == 0 && id2 >= 0) {
+                        int row = -1, col = -1;
+                        if (S2 > 0 && mm2 > 0) { row = (int)(0xfffffull - ((pk >> 20) & 0xfffffull)); col = (int)(0xfffffull - (pk & 0xfffffull)); }
+                        if (!REV) { a.out_score[id2] = (mm2 > 0) ? S2 : 0; a.out_a[id2] = row; a.out_b[id2] = col; }
+                        else {
+                            const int tgt2 = (h2 == 0) ? tgtA : tgtB;
+                            if (mm2 > 0 && S2 == tgt2 && row >= 0) { a.out_a[id2] = mm2 - 1 - row; a.out_b[id2] = nn2 - 1 - col; }
+                            else if (mm2 > 0) { a.out_a[id2] = -2; a.out_b[id2] = -2; }
+                        }
+                    }
+                }
+                continue;
+            }
             const int id = (h == 0) ? idA : idB;
             const int mm = (h == 0) ? mA : mB, nn = (h == 0) ? nA : nB;
             if (l == 0 && id >= 0) {
@@ -448,7 +547,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 }
             }
         }
-        if (REV && a.cells && l == 0) atomicAdd(a.cells, swept);
+        if (REV && a.cells && l == 0) atomicAdd(a.cells, WAVE ? (unsigned long long)mw * (unsigned long long)min(nw - wblock * W, W) : swept);
     }
 }
 

@@ -112,3 +112,20 @@ def test_traceback_config2_sample_10k(ctx, oracle):
     flat = np.concatenate(cigs) if len(cigs) else np.zeros(0, np.uint32)
     assert np.array_equal(out['cigar_ops'], flat)
     assert np.array_equal(out['cigar_off'][1:], np.cumsum([len(c) for c in cigs]))
+
+
+def test_long_alignments_take_the_wavefront_kernel(ctx, oracle):
+    # pairs beyond 2431 columns x 1024 rows are pipelined across the warps of a CTA (WAVE); results must not change
+    qs, ts = workloads.random_pairs(9, seed=31, nsym_real=4, min_len=2600, max_len=7000, related=0.8)
+    qs2, ts2 = workloads.random_pairs(40, seed=32, nsym_real=4, min_len=50, max_len=900, related=0.8)
+    out, st = _compare(ctx, oracle, qs + qs2, ts + ts2, seqcodec.nt_params(), seqcodec.nt_matrix().reshape(-1), 6, 2)
+    _compare_align(ctx, oracle, qs[:4] + qs2[:6], ts[:4] + ts2[:6], seqcodec.nt_params(), seqcodec.nt_matrix().reshape(-1), 6, 2)
+
+
+def test_long_protein_s32_wavefront(ctx, oracle):
+    rng = np.random.default_rng(33)
+    big = rng.integers(0, 20, 3300).astype(np.uint8)
+    mut = big.copy(); mask = rng.random(3300) < 0.3; mut[mask] = rng.integers(0, 20, int(mask.sum()))
+    qs = [big, mut[:3200], big[100:3000]]
+    ts = [mut, big, np.concatenate([rng.integers(0, 20, 50).astype(np.uint8), big])]
+    out, _ = _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
