@@ -10,8 +10,14 @@
 // The DP kernel uses the same systolic strip layout as the score kernel (group of G lanes, K
 // columns per lane in registers, rows streamed, profile in shared memory), in s32, one pair per
 // group.  Direction words are written step-major ([block][step][lane][word]) so that every step
-// of a group is one contiguous, coalesced store.  A second kernel (one thread per pair) walks the
-// directions from the start cell to the origin, which emits the ops in alignment order.
+// of a group is one contiguous, coalesced store.  A second kernel (one warp per pair) walks the
+// directions from the start cell to the origin, which emits the ops in alignment order; the warp
+// reads 32 cells along the current diagonal at once and consumes the whole diagonal run with ballots.
+//
+// Long boxes (WAVE): as in the score kernel, the column blocks of one pair are taken by different warps
+// (G = 32, 512 columns each) and run as a pipeline over the machine, each block a few rows behind its left
+// neighbour (border column + release/acquire progress counter in global memory), so that one 9.5 kb x 9.5 kb
+// box takes ~M + 32 * blocks steps instead of blocks * M.
 #include "pb_sw_job.h"
 #include <algorithm>
 #include <vector>
@@ -24,15 +30,25 @@ namespace {
 constexpr int TR_G = 16, TR_K = 16, TR_WARPS = 8;
 constexpr int TR_W = TR_G * TR_K;
 constexpr int TR_KW8 = TR_K / 8;        // direction words per lane per step
-constexpr int PAD_SCORE = -16;
+constexpr int TRW_G = 32, TRW_W = TRW_G * TR_K;          // wavefront variant: whole warps, 512 columns per block
+constexpr int WAVE_MIN_COLS = 4 * TR_W + 1, WAVE_MIN_ROWS = 768;   // boxes at least this large are pipelined across warps
 
 struct TraceDesc {
     long long qoff, toff;   // start of the box in the code arrays
     long long doff;         // offset (words) of this pair's direction block
     int M, N;               // box rows / columns
     int id;                 // pair id
+    int wave;               // 1: direction block laid out by the wavefront variant (G = 32)
+    int wslot;              // WAVE: first border / progress slot of the pair
     int pad;
 };
+
+inline bool is_wave(int M, int N) { return N >= WAVE_MIN_COLS && M >= WAVE_MIN_ROWS; }
+inline size_t dir_words(int M, int N, bool wave)
+{
+    const int G = wave ? TRW_G : TR_G, W = G * TR_K;
+    return (size_t)((N + W - 1) / W) * (size_t)(M + G - 1) * G * TR_KW8;
+}
 
 struct TraceArgs {
     const uint8_t* q;
@@ -45,11 +61,15 @@ struct TraceArgs {
     uint32_t* dir;
     uint2* boundary;
     int bstride;
+    int* progress;          // WAVE: rows published per (pair, column block) border (zeroed before launch)
+    const int2* wsub;       // WAVE: (pair, column block) sub-tasks in launch order
+    int nsub;
 };
 
-template <int G, int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs a)
+template <int G, int K, int WARPS, bool WAVE>
+__global__ void __launch_bounds__(WARPS * 32, 2) sw_trace_kernel(const TraceArgs a)
 {
+    static_assert(!WAVE || G == 32, "the wavefront variant uses whole warps");
     constexpr int KW = (K + 3) / 4, KP = KW * 4, NG = 32 / G, W = G * K, KW8 = K / 8;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -61,22 +81,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs
     const int nsym = a.nsym, PAD = nsym - 1, rowBytes = G * KP;
     uint8_t* prof = smem + 1024 + (size_t)(warp * NG + g) * nsym * rowBytes;
     const int gwarp = blockIdx.x * WARPS + warp;
-    uint2* mybound = a.boundary ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
+    uint2* mybound = (a.boundary && !WAVE) ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
     const int ge = a.ge, goe = a.go + a.ge;
 
     for (;;) {
-        int bundle = 0;
+        int bundle = 0, wblock = 0;
         if (lane == 0) bundle = atomicAdd(a.counter, 1);
         bundle = __shfl_sync(FULL, bundle, 0);
+        if (WAVE) {
+            if (bundle >= a.nsub) break;
+            const int2 sub = a.wsub[bundle];
+            bundle = sub.x; wblock = sub.y;
+        }
         if (bundle * NG >= a.count) break;
         const int task = bundle * NG + g;
-        int M = 0, N = 0;
+        int M = 0, N = 0, wslot = 0;
         const uint8_t *qb = a.q, *tb = a.t;
         long long doff = 0;
         if (task < a.count) {
             TraceDesc d = a.desc[task];
-            M = d.M; N = d.N; qb = a.q + d.qoff; tb = a.t + d.toff; doff = d.doff;
+            M = d.M; N = d.N; qb = a.q + d.qoff; tb = a.t + d.toff; doff = d.doff; wslot = d.wslot;
         }
+        uint2* wavebound = WAVE ? a.boundary + (size_t)wslot * a.bstride : nullptr;
+        int* waveprog = WAVE ? a.progress + wslot : nullptr;
         int mw = M, nw = N;
 #pragma unroll
         for (int o = 16; o >= G; o >>= 1) {
@@ -86,7 +113,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs
         const int nblocks = (nw + W - 1) / W;
         const int nsteps_own = M + G - 1;
 
-        for (int b = 0; b < nblocks; ++b) {
+        for (int b = WAVE ? wblock : 0; b < (WAVE ? wblock + 1 : nblocks); ++b) {
             const int col0 = b * W + l * K;
             {
                 int tc[K];
@@ -114,6 +141,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs
             uint32_t* dbase = a.dir + doff + (size_t)b * nsteps_own * G * KW8;
             int i0 = -l;
             int cq = ((unsigned)i0 < (unsigned)M) ? (int)__ldg(qb + (M - 1 - i0)) : PAD;
+            if (WAVE) mybound = wavebound + (size_t)b * a.bstride;
+            const uint2* leftbound = WAVE ? (b > 0 ? wavebound + (size_t)(b - 1) * a.bstride : nullptr) : mybound;
+            int published = 0;                  // WAVE: rows of the left border known to be complete
+            uint2 pref = make_uint2(0u, 0u);    // WAVE: border cell of the next step, loaded one step ahead
+            bool pref_ok = false;
             for (int s = 0; s < slimit; ++s) {
                 const int i = s - l;
                 uint32_t w[KW];
@@ -124,7 +156,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs
                 int hl = __shfl_up_sync(FULL, hlast, 1, G), fh = __shfl_up_sync(FULL, fout, 1, G);
                 if (l == 0) {
                     hl = 0; fh = 0;
-                    if (b > 0 && (unsigned)i < (unsigned)mw) { uint2 v = mybound[i]; hl = (int)v.x; fh = (int)v.y; }
+                    if (b > 0 && (unsigned)i < (unsigned)mw) {
+                        if (WAVE) {
+                            // stay >= 32 rows behind the warp that owns block b-1: one acquire then covers many steps
+                            if (published < i + 1) {
+                                const int want = min(i + 1 + 32, mw);
+                                while ((published = ld_acquire(waveprog + (b - 1))) < want) __nanosleep(100);
+                                pref_ok = false;
+                            }
+                            const uint2 v = pref_ok ? pref : ld_volatile_u2(leftbound + i);
+                            hl = (int)v.x; fh = (int)v.y;
+                            pref_ok = (i + 1 < mw) && (i + 2 <= published);
+                            if (pref_ok) pref = ld_volatile_u2(leftbound + i + 1);
+                        } else { uint2 v = leftbound[i]; hl = (int)v.x; fh = (int)v.y; }
+                    }
                 }
                 int hdiag = hl_prev; hl_prev = hl;
                 int hleft = hl;
@@ -151,7 +196,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs
                     hdiag = hup; H[p] = hn; hleft = hn;
                 }
                 hlast = hleft; fout = fh;
-                if (nblocks > 1 && l == G - 1 && b + 1 < nblocks && (unsigned)i < (unsigned)mw) mybound[i] = make_uint2((uint32_t)hlast, (uint32_t)fout);
+                if (nblocks > 1 && l == G - 1 && b + 1 < nblocks && (unsigned)i < (unsigned)mw) {
+                    mybound[i] = make_uint2((uint32_t)hlast, (uint32_t)fout);
+                    if (WAVE && ((i & 15) == 15 || i + 1 >= mw)) st_release(waveprog + b, i + 1);
+                }
                 if (in_block && s < nsteps_own) {
                     uint32_t* dst = dbase + ((size_t)s * G + l) * KW8;
 #pragma unroll
@@ -163,53 +211,68 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_trace_kernel(const TraceArgs
     }
 }
 
-// One thread per pair: walk the direction words from the start cell (M-1, N-1 in reverse
-// coordinates) to the origin.  WRITE = false counts ops and match statistics, WRITE = true
-// stores the run-length ops at ops[ooff[pair]].
+// One warp per pair: walk the direction words from the start cell (M-1, N-1 in reverse coordinates) to the
+// origin.  In the H state lane k looks at cell (i-k, j-k); the run of leading "diagonal" cells is consumed at once
+// (ballot), gap cells are walked one at a time with a warp-uniform load.  WRITE = false counts ops and match
+// statistics, WRITE = true stores the run-length ops at ops[ooff[pair]].
 template <bool WRITE>
 __global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDesc* desc, int count, const uint32_t* dir,
                                int* nops, int* counts, const long long* ooff, uint32_t* ops)
 {
-    constexpr int G = TR_G, K = TR_K, W = TR_W, KW8 = TR_KW8;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int K = TR_K, KW8 = TR_KW8;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (x >= count) return;
     const TraceDesc d = desc[x];
+    const int G = d.wave ? TRW_G : TR_G, W = G * K;
     const uint8_t* qb = q + d.qoff; const uint8_t* tb = t + d.toff;
     const int nsteps = d.M + G - 1;
     const uint32_t* base = dir + d.doff;
+    auto fetch = [&](int ii, int jj) -> int {
+        const int b = jj / W, jr = jj - b * W, l = jr / K, p = jr - l * K;
+        const uint32_t wv = base[((size_t)b * nsteps + (ii + l)) * G * KW8 + (size_t)l * KW8 + (p >> 3)];
+        return (int)((wv >> (4 * (p & 7))) & 15);
+    };
     int i = d.M - 1, j = d.N - 1, state = 0;
     int cur = -1, len = 0, n = 0, nm = 0, nx = 0, ngo = 0, ngb = 0;
     uint32_t* out = WRITE ? ops + ooff[x] : nullptr;
+    auto emit = [&](int op, int cnt) {
+        if (op == cur) { len += cnt; return; }
+        if (cur >= 0) { if (WRITE && lane == 0) out[n] = ((uint32_t)len << 2) | (uint32_t)cur; ++n; }
+        cur = op; len = cnt;
+    };
     while (i >= 0 && j >= 0) {
-        const int b = j / W, jj = j - b * W, l = jj / K, p = jj - l * K;
-        const uint32_t wv = base[((size_t)b * nsteps + (i + l)) * G * KW8 + (size_t)l * KW8 + (p >> 3)];
-        const int code = (wv >> (4 * (p & 7))) & 15;
-        int op;
         if (state == 0) {
-            const int h = code & 3;
-            if (h == 0) break;
-            if (h == 1) {
-                op = 0;
-                if (!WRITE) { if (qb[d.M - 1 - i] == tb[d.N - 1 - j]) ++nm; else ++nx; }
-                --i; --j;
-            } else { state = (h == 2) ? 1 : 2; continue; }
-        } else if (state == 1) {
-            op = 1; if (cur != 1) ++ngo; ++ngb;
-            if (code & 4) state = 0;
-            --i;
+            const int ii = i - lane, jj = j - lane;
+            const bool valid = ii >= 0 && jj >= 0;
+            const int code = valid ? fetch(ii, jj) : 0;
+            const unsigned dm = __ballot_sync(FULL, valid && (code & 3) == 1);
+            const int run = (dm == FULL) ? 32 : __ffs(~dm) - 1;
+            if (run > 0) {
+                if (!WRITE) {
+                    const bool match = valid && qb[d.M - 1 - ii] == tb[d.N - 1 - jj];
+                    const unsigned mm = __ballot_sync(FULL, match) & (run == 32 ? FULL : ((1u << run) - 1u));
+                    nm += __popc(mm); nx += run - __popc(mm);
+                }
+                emit(0, run);
+                i -= run; j -= run;
+            }
+            if (run < 32) {
+                const int c2 = __shfl_sync(FULL, code, run);
+                const int v2 = __shfl_sync(FULL, (int)valid, run);
+                if (!v2) break;                        // left the box
+                const int h = c2 & 3;
+                if (h == 0) break;
+                state = (h == 2) ? 1 : 2;
+            }
         } else {
-            op = 2; if (cur != 2) ++ngo; ++ngb;
-            if (code & 8) state = 0;
-            --j;
-        }
-        if (op == cur) ++len;
-        else {
-            if (cur >= 0) { if (WRITE) out[n] = ((uint32_t)len << 2) | (uint32_t)cur; ++n; }
-            cur = op; len = 1;
+            const int code = fetch(i, j);
+            if (state == 1) { if (cur != 1) ++ngo; ++ngb; emit(1, 1); if (code & 4) state = 0; --i; }
+            else { if (cur != 2) ++ngo; ++ngb; emit(2, 1); if (code & 8) state = 0; --j; }
         }
     }
-    if (cur >= 0) { if (WRITE) out[n] = ((uint32_t)len << 2) | (uint32_t)cur; ++n; }
-    if (!WRITE) {
+    if (cur >= 0) { if (WRITE && lane == 0) out[n] = ((uint32_t)len << 2) | (uint32_t)cur; ++n; }
+    if (!WRITE && lane == 0) {
         nops[x] = n;
         counts[4 * x + 0] = nm; counts[4 * x + 1] = nx; counts[4 * x + 2] = ngo; counts[4 * x + 3] = ngb;
     }
@@ -231,11 +294,13 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         if (score[p] <= 0) continue;
         TraceDesc d;
         d.qoff = qbeg[p] + qs[p]; d.toff = tbeg[p] + ts[p];
-        d.M = qe[p] - qs[p] + 1; d.N = te[p] - ts[p] + 1; d.id = (int)p; d.pad = 0; d.doff = 0;
+        d.M = qe[p] - qs[p] + 1; d.N = te[p] - ts[p] + 1; d.id = (int)p; d.pad = 0; d.doff = 0; d.wslot = 0;
+        d.wave = is_wave(d.M, d.N) ? 1 : 0;
         all.push_back(d);
     }
-    // longest boxes first: similar shapes share a warp, and the dynamic scheduler packs well
+    // pipelined (wave) boxes first, then longest boxes first: similar shapes share a warp, and the dynamic scheduler packs well
     std::sort(all.begin(), all.end(), [](const TraceDesc& a, const TraceDesc& b) {
+        if (a.wave != b.wave) return a.wave > b.wave;
         int ba = (a.N + TR_W - 1) / TR_W, bb = (b.N + TR_W - 1) / TR_W;
         if (ba != bb) return ba > bb;
         if (a.M != b.M) return a.M > b.M;
@@ -244,28 +309,38 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     std::vector<int> h_nops((size_t)npairs, 0);
     std::vector<int> h_counts((size_t)npairs * 4, 0);
     const size_t budget_words = (size_t)std::min<int64_t>(ctx->hbm_bytes / 8, (int64_t)12 << 30) / 4;
-    const int grid = ctx->sm_count;
     const size_t smem = 1024 + (size_t)TR_WARPS * (32 / TR_G) * params->nsym * TR_G * (((TR_K + 3) / 4) * 4);
-    auto kern = sw_trace_kernel<TR_G, TR_K, TR_WARPS>;
+    const size_t smem_w = 1024 + (size_t)TR_WARPS * params->nsym * TRW_G * (((TR_K + 3) / 4) * 4);
+    auto kern = sw_trace_kernel<TR_G, TR_K, TR_WARPS, false>;
+    auto kern_w = sw_trace_kernel<TRW_G, TR_K, TR_WARPS, true>;
     PB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB_CUDA(ctx, cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    // persistent grids: every CTA resident at once (the wavefront variant spins on its left neighbour)
+    int occ = 1, occ_w = 1;
+    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TR_WARPS * 32, smem));
+    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, kern_w, TR_WARPS * 32, smem_w));
+    const int grid = ctx->sm_count * std::max(1, std::min(occ, 2)), grid_w = ctx->sm_count * std::max(1, std::min(occ_w, 2));
     float ms_trace = 0;
     int launches = 0;
     PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 
-    struct Chunk { size_t first, count; size_t words; int maxM; int maxNB; };
+    struct Chunk { size_t first, count, nwave; size_t words; int maxM; int maxNB; int waveM; size_t wslots; };
     std::vector<Chunk> chunks;
     {
         size_t i = 0;
         while (i < all.size()) {
-            Chunk c{i, 0, 0, 0, 0};
+            Chunk c{i, 0, 0, 0, 0, 0, 0, 0};
             while (i < all.size()) {
                 TraceDesc& d = all[i];
-                int nb = (d.N + TR_W - 1) / TR_W;
-                size_t w = (size_t)nb * (d.M + TR_G - 1) * TR_G * TR_KW8;
+                const size_t w = dir_words(d.M, d.N, d.wave != 0);
                 if (w > budget_words) { pb_set_error(ctx, "pb_sw_align_batch: a single alignment box needs %zu direction words", w); return PB_ERR_LIMIT; }
                 if (c.count > 0 && c.words + w > budget_words) break;
                 d.doff = (long long)c.words;
-                c.words += w; c.count++; c.maxM = std::max(c.maxM, d.M); c.maxNB = std::max(c.maxNB, nb);
+                c.words += w; c.count++;
+                if (d.wave) {
+                    d.wslot = (int)c.wslots; c.wslots += (size_t)((d.N + TRW_W - 1) / TRW_W);
+                    c.nwave++; c.waveM = std::max(c.waveM, d.M);
+                } else { c.maxM = std::max(c.maxM, d.M); c.maxNB = std::max(c.maxNB, (d.N + TR_W - 1) / TR_W); }
                 ++i;
             }
             chunks.push_back(c);
@@ -276,22 +351,49 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     std::vector<std::vector<long long>> chunk_ooff(chunks.size());
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk& c = chunks[ci];
-        DevBuf ddesc, ddir, dnops, dcounts, dooff, dops, dbound;
+        DevBuf ddesc, ddir, dnops, dcounts, dooff, dops, dbound, dwbound, dwprog;
         PB_CUDA(ctx, ddesc.alloc(c.count * sizeof(TraceDesc), ctx->stream));
         PB_CUDA(ctx, ddir.alloc(std::max<size_t>(c.words, 4) * 4, ctx->stream));
         PB_CUDA(ctx, dnops.alloc(c.count * 4, ctx->stream));
         PB_CUDA(ctx, dcounts.alloc(c.count * 16, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(ddesc.p, all.data() + c.first, c.count * sizeof(TraceDesc), cudaMemcpyHostToDevice, ctx->stream));
-        int bstride = c.maxNB > 1 ? ((c.maxM + 63) / 64) * 64 : 0;
-        if (bstride) PB_CUDA(ctx, dbound.alloc((size_t)grid * TR_WARPS * (32 / TR_G) * bstride * sizeof(uint2), ctx->stream));
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
         TraceArgs a;
         a.q = J->dq; a.t = J->dt; a.desc = ddesc.as<TraceDesc>(); a.count = (int)c.count;
         a.counter = ctx->d_counter; a.matrix = J->matrix.as<int8_t>(); a.nsym = params->nsym; a.go = params->gap_open; a.ge = params->gap_extend;
-        a.dir = ddir.as<uint32_t>(); a.boundary = bstride ? dbound.as<uint2>() : nullptr; a.bstride = bstride;
-        kern<<<grid, TR_WARPS * 32, smem, ctx->stream>>>(a);
-        PB_CUDA(ctx, cudaGetLastError()); ++launches;
-        const int tb = 128, gb = (int)((c.count + tb - 1) / tb);
+        a.dir = ddir.as<uint32_t>(); a.boundary = nullptr; a.bstride = 0; a.progress = nullptr; a.wsub = nullptr; a.nsub = 0;
+        std::vector<int2> sub;
+        if (c.nwave > 0) {
+            // wavefront launch over the (pair, column block) sub-tasks of the long boxes, pair-major
+            for (size_t k = 0; k < c.nwave; ++k) {
+                const TraceDesc& d = all[c.first + k];
+                for (int b = 0; b < (d.N + TRW_W - 1) / TRW_W; ++b) sub.push_back(make_int2((int)k, b));
+            }
+            const int wstride = ((c.waveM + 63) / 64) * 64;
+            const size_t bbytes = c.wslots * (size_t)wstride * sizeof(uint2);
+            if (bbytes > ((size_t)24 << 30)) { pb_set_error(ctx, "pb_sw_align_batch: long-alignment border buffer would need %zu bytes; split the batch", bbytes); return PB_ERR_LIMIT; }
+            PB_CUDA(ctx, dwbound.alloc(bbytes, ctx->stream));
+            const size_t o_sub = ((c.wslots * 4 + 7) / 8) * 8;
+            PB_CUDA(ctx, dwprog.alloc(o_sub + sub.size() * sizeof(int2), ctx->stream));
+            PB_CUDA(ctx, cudaMemsetAsync(dwprog.p, 0, o_sub, ctx->stream));
+            PB_CUDA(ctx, cudaMemcpyAsync((char*)dwprog.p + o_sub, sub.data(), sub.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+            TraceArgs w = a;
+            w.count = (int)c.nwave; w.boundary = dwbound.as<uint2>(); w.bstride = wstride; w.progress = (int*)dwprog.p;
+            w.wsub = (const int2*)((char*)dwprog.p + o_sub); w.nsub = (int)sub.size(); w.counter = ctx->d_counter + 1;
+            const int wgrid = std::max(1, std::min(grid_w, (int)((sub.size() + TR_WARPS - 1) / TR_WARPS)));
+            kern_w<<<wgrid, TR_WARPS * 32, smem_w, ctx->stream>>>(w);
+            PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        }
+        if (c.count > c.nwave) {
+            const int bstride = c.maxNB > 1 ? ((c.maxM + 63) / 64) * 64 : 0;
+            if (bstride) PB_CUDA(ctx, dbound.alloc((size_t)grid * TR_WARPS * (32 / TR_G) * bstride * sizeof(uint2), ctx->stream));
+            TraceArgs r = a;
+            r.desc = a.desc + c.nwave; r.count = (int)(c.count - c.nwave);
+            r.boundary = bstride ? dbound.as<uint2>() : nullptr; r.bstride = bstride;
+            kern<<<grid, TR_WARPS * 32, smem, ctx->stream>>>(r);
+            PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        }
+        const int tb = 128, gb = (int)((c.count * 32 + tb - 1) / tb);
         sw_walk_kernel<false><<<gb, tb, 0, ctx->stream>>>(a.q, a.t, a.desc, a.count, a.dir, dnops.as<int>(), dcounts.as<int>(), nullptr, nullptr);
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         std::vector<int> nops(c.count), cnt(c.count * 4);
