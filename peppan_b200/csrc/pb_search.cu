@@ -305,6 +305,112 @@ __global__ void __launch_bounds__(SCAN_THREADS) seed_scan_kernel(const uint8_t* 
     if (myseeds) atomicAdd(nseed, myseeds);
 }
 
+// ---- K1c: diagonal binning of the ungapped HSPs -> clusters -> target windows (all on the device) -----------
+struct HspD { int qid, tid, diag, ts, te, qs, qe, score; };
+struct ClD { int qid, tid, tmin, tmax, qmin, qmax; };
+struct Window { int qid, tid; int64_t tbeg; int tlen; int pad; };
+
+__device__ __forceinline__ int find_seq_dev(const int64_t* __restrict__ off, int n, int64_t pos)
+{
+    int lo = 0, hi = n;                     // last sequence whose begin is <= pos
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (off[mid] <= pos) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+
+__global__ void hsp_annotate_kernel(const Cand* __restrict__ cand, int n, const int64_t* __restrict__ qoff, int nq,
+                                    const int64_t* __restrict__ toff, int nt, HspD* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Cand c = cand[i];
+    HspD h;
+    h.qid = find_seq_dev(qoff, nq, c.qpos); h.tid = find_seq_dev(toff, nt, c.tpos);
+    h.qs = (int)(c.qpos - qoff[h.qid]); h.qe = h.qs + (int)c.len;
+    h.ts = (int)(c.tpos - toff[h.tid]); h.te = h.ts + (int)c.len;
+    h.diag = h.ts - h.qs; h.score = c.score;
+    out[i] = h;
+}
+
+// sort keys, least significant pass first (three stable 64-bit radix passes give the full lexicographic order)
+__device__ __forceinline__ uint64_t pack2(int hi, int lo) { return ((uint64_t)((uint32_t)hi ^ 0x80000000u) << 32) | ((uint32_t)lo ^ 0x80000000u); }
+__device__ __forceinline__ uint64_t sort_key(const HspD& h, int pass)
+{
+    return pass == 0 ? pack2(0, h.te) : pass == 1 ? pack2(h.diag, h.ts) : pack2(h.qid, h.tid);
+}
+__device__ __forceinline__ uint64_t sort_key(const ClD& c, int pass)
+{
+    if (c.qid < 0) return ~0ull;            // unused slot: sorts behind every cluster
+    return pass == 0 ? pack2(c.qmin, c.qmax) : pass == 1 ? pack2(c.tmin, c.tmax) : pack2(c.qid, c.tid);
+}
+
+template <class T>
+__global__ void make_keys_kernel(const T* __restrict__ items, const uint32_t* __restrict__ perm, int n, int pass, uint64_t* keys, uint32_t* vals)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t i = perm ? perm[k] : (uint32_t)k;
+    keys[k] = sort_key(items[i], pass); vals[k] = i;
+}
+
+template <class T>
+__global__ void gather_kernel(const T* __restrict__ items, const uint32_t* __restrict__ perm, int n, T* out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = items[perm[k]];
+}
+
+// One thread per (query, target) segment of the sorted HSPs: greedy partition by diagonal (a cluster holds the HSPs
+// whose diagonal is within diag_span of the cluster's first), duplicates counted once; clusters that pass the score rule
+// are written at the slot of their first HSP; every other slot stays unused (qid = -1, preset by the caller).
+__global__ void hsp_cluster_kernel(const HspD* __restrict__ h, int n, int diag_span, int clu_max, int clu_sum, ClD* cl, unsigned int* ncl)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (k > 0 && h[k - 1].qid == h[k].qid && h[k - 1].tid == h[k].tid) return;      // not a segment head
+    const int qid = h[k].qid, tid = h[k].tid;
+    int i = k;
+    unsigned int found = 0;
+    while (i < n && h[i].qid == qid && h[i].tid == tid) {
+        ClD c{qid, tid, h[i].ts, h[i].te, h[i].qs, h[i].qe};
+        const int d0 = h[i].diag;
+        int smax = 0; long long ssum = 0;
+        int j = i;
+        while (j < n && h[j].qid == qid && h[j].tid == tid && h[j].diag - d0 <= diag_span) {
+            const bool dup = j > i && h[j].diag == h[j - 1].diag && h[j].ts == h[j - 1].ts && h[j].te == h[j - 1].te;
+            if (!dup) { smax = max(smax, h[j].score); ssum += h[j].score; }
+            c.tmin = min(c.tmin, h[j].ts); c.tmax = max(c.tmax, h[j].te);
+            c.qmin = min(c.qmin, h[j].qs); c.qmax = max(c.qmax, h[j].qe);
+            ++j;
+        }
+        if (smax >= clu_max || ssum >= clu_sum) { cl[i] = c; ++found; }
+        i = j;
+    }
+    if (found) atomicAdd(ncl, found);
+}
+
+// territory + window of every cluster (sorted by query, target, tmin, tmax): a window may not reach into the seeded
+// extent of a neighbouring cluster of the same (query, target).  Empty windows keep their slot with tlen = 0.
+__global__ void window_kernel(const ClD* __restrict__ cl, int n, int pad, const int64_t* __restrict__ qoff, int nq, int64_t qtotal,
+                              const int64_t* __restrict__ toff, int nt, int64_t ttotal, Window* win,
+                              int64_t* qbeg, int64_t* qend, int64_t* tbeg, int64_t* tend)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ClD c = cl[i];
+    const int64_t tl = (c.tid + 1 < nt ? toff[c.tid + 1] : ttotal) - toff[c.tid] - 1;
+    const int64_t qlen = (c.qid + 1 < nq ? qoff[c.qid + 1] : qtotal) - qoff[c.qid] - 1;
+    int64_t lo = (int64_t)c.tmin - c.qmin - pad, hi = (int64_t)c.tmax + (qlen - c.qmax) + pad;
+    if (i > 0) { const ClD p = cl[i - 1]; if (p.qid == c.qid && p.tid == c.tid && p.tmax <= c.tmin) lo = max(lo, (int64_t)p.tmax); }
+    if (i + 1 < n) { const ClD x = cl[i + 1]; if (x.qid == c.qid && x.tid == c.tid && x.tmin >= c.tmax) hi = min(hi, (int64_t)x.tmin); }
+    lo = max(lo, (int64_t)0); hi = min(hi, tl);
+    if (hi < lo) hi = lo;
+    Window w; w.qid = c.qid; w.tid = c.tid; w.tbeg = lo; w.tlen = (int)(hi - lo); w.pad = 0;
+    win[i] = w;
+    const bool empty = hi <= lo;
+    qbeg[i] = qoff[c.qid]; qend[i] = qoff[c.qid] + (empty ? 0 : qlen);
+    tbeg[i] = toff[c.tid] + lo; tend[i] = toff[c.tid] + hi;
+}
+
 // ---- host helpers -------------------------------------------------------------------------------
 struct SeqLayout {
     std::vector<int64_t> off;     // begin of every sequence in the device code array
@@ -328,7 +434,25 @@ inline int find_seq(const SeqLayout& L, int64_t pos)
     return (int)i - 1;
 }
 
-struct Window { int qid, tid; int64_t tbeg; int tlen; };
+// items[perm[0..n)] in lexicographic order of sort_key passes 2, 1, 0 (three stable LSD radix passes over 64-bit keys)
+template <class T>
+int sort_by_keys(pb_ctx* ctx, const T* items, int n, DevBuf& perm, int* launches)
+{
+    cudaStream_t sm = ctx->stream;
+    DevBuf k1, k2, v1, tmp;
+    PB_CUDA(ctx, k1.alloc((size_t)n * 8, sm)); PB_CUDA(ctx, k2.alloc((size_t)n * 8, sm));
+    PB_CUDA(ctx, v1.alloc((size_t)n * 4, sm)); PB_CUDA(ctx, perm.alloc((size_t)n * 4, sm));
+    size_t tb = 0;
+    PB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.as<uint64_t>(), k2.as<uint64_t>(), v1.as<uint32_t>(), perm.as<uint32_t>(), n, 0, 64, sm));
+    PB_CUDA(ctx, tmp.alloc(std::max<size_t>(tb, 16), sm));
+    for (int pass = 0; pass < 3; ++pass) {
+        make_keys_kernel<T><<<(n + 255) / 256, 256, 0, sm>>>(items, pass ? perm.as<uint32_t>() : nullptr, n, pass, k1.as<uint64_t>(), v1.as<uint32_t>());
+        PB_CUDA(ctx, cudaGetLastError());
+        PB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1.as<uint64_t>(), k2.as<uint64_t>(), v1.as<uint32_t>(), perm.as<uint32_t>(), n, 0, 64, sm));
+        *launches += 2;
+    }
+    return PB_OK;
+}
 
 const char* CODON11 = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVVXYXYSSSSXCWCLFLF";
 
@@ -495,10 +619,9 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     PB_CUDA(ctx, cudaEventRecord(e2, sm));
 
     // ---- K1b: seed scan (retry with a larger candidate buffer on overflow) ----
-    std::vector<Cand> cands;
+    DevBuf d_cand;
     unsigned long long cap = std::max<unsigned long long>(1ull << 20, (unsigned long long)nq * 64);
     for (int attempt = 0; attempt < 4; ++attempt) {
-        DevBuf d_cand;
         PB_CUDA(ctx, d_cand.alloc(cap * sizeof(Cand), sm));
         PB_CUDA(ctx, cudaMemsetAsync(d_cnt.as<unsigned long long>() + 1, 0, 16, sm));
         const int grid = (int)std::min<int64_t>((LT + SCAN_TILE - 1) / SCAN_TILE, (int64_t)ctx->sm_count * 8);
@@ -508,75 +631,54 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         PB_CUDA(ctx, cudaMemcpyAsync(cnts, d_cnt.p, 64, cudaMemcpyDeviceToHost, sm));
         PB_CUDA(ctx, cudaStreamSynchronize(sm));
-        if (cnts[1] <= cap) {
-            cands.resize(cnts[1]);
-            if (cnts[1]) PB_CUDA(ctx, cudaMemcpyAsync(cands.data(), d_cand.p, cnts[1] * sizeof(Cand), cudaMemcpyDeviceToHost, sm));
-            PB_CUDA(ctx, cudaStreamSynchronize(sm));
-            break;
-        }
+        if (cnts[1] <= cap) break;
         cap = cnts[1] + (cnts[1] >> 3);
         if (attempt == 3) { pb_set_error(ctx, "pb_search: candidate buffer overflow"); return PB_ERR_LIMIT; }
     }
-    st.n_seed_hits = (int64_t)cnts[2]; st.n_ungapped = (int64_t)cands.size();
+    if (cnts[1] > 0x7fffffffull) { pb_set_error(ctx, "pb_search: too many ungapped HSPs in one call; block the input"); return PB_ERR_LIMIT; }
+    const int nh = (int)cnts[1];
+    st.n_seed_hits = (int64_t)cnts[2]; st.n_ungapped = nh;
     st.algo_bytes_seed = LT + 9 * LQ + 16 * (int64_t)cnts[2];
     PB_CUDA(ctx, cudaEventRecord(e3, sm));
 
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const bool dbg = getenv("PB_DEBUG_TIMING") != nullptr;
     double h0 = now();
-    // ---- host: clusters -> windows ----
-    struct HC { int qid, tid; int64_t diag; int64_t ts, te; int qs, qe; int score; };
-    std::vector<HC> hc; hc.reserve(cands.size());
-    for (const Cand& c : cands) {
-        int qid = find_seq(QL, c.qpos), tid = find_seq(TL, c.tpos);
-        HC h; h.qid = qid; h.tid = tid;
-        h.qs = (int)(c.qpos - QL.off[qid]); h.qe = h.qs + (int)c.len;
-        h.ts = (int64_t)c.tpos - TL.off[tid]; h.te = h.ts + c.len;
-        h.diag = h.ts - h.qs; h.score = c.score;
-        hc.push_back(h);
-    }
-    std::sort(hc.begin(), hc.end(), [](const HC& a, const HC& b) {
-        if (a.qid != b.qid) return a.qid < b.qid;
-        if (a.tid != b.tid) return a.tid < b.tid;
-        if (a.diag != b.diag) return a.diag < b.diag;
-        if (a.ts != b.ts) return a.ts < b.ts;
-        return a.te < b.te;
-    });
-    struct Cl { int qid, tid; int64_t tmin, tmax; int qmin, qmax; };
-    std::vector<Cl> cl;
-    for (size_t i = 0; i < hc.size();) {
-        size_t j = i; Cl c{hc[i].qid, hc[i].tid, hc[i].ts, hc[i].te, hc[i].qs, hc[i].qe};
-        const int64_t d0 = hc[i].diag;
-        int smax = 0; long long ssum = 0;
-        while (j < hc.size() && hc[j].qid == c.qid && hc[j].tid == c.tid && hc[j].diag - d0 <= spec.diag_span) {
-            const bool dup = j > i && hc[j].diag == hc[j - 1].diag && hc[j].ts == hc[j - 1].ts && hc[j].te == hc[j - 1].te;
-            if (!dup) { smax = std::max(smax, hc[j].score); ssum += hc[j].score; }
-            c.tmin = std::min(c.tmin, hc[j].ts); c.tmax = std::max(c.tmax, hc[j].te);
-            c.qmin = std::min(c.qmin, hc[j].qs); c.qmax = std::max(c.qmax, hc[j].qe);
-            ++j;
+    // ---- K1c: HSPs -> diagonal clusters -> windows, on the device ----
+    std::vector<Window> win;
+    DevBuf d_win, d_wqb, d_wqe, d_wtb, d_wte;
+    const int nqi = (int)nq, nti = (int)TL.off.size();
+    if (nh > 0) {
+        DevBuf d_h, d_hs, d_perm, d_cl, d_cls, d_perm2;
+        PB_CUDA(ctx, d_h.alloc((size_t)nh * sizeof(HspD), sm)); PB_CUDA(ctx, d_hs.alloc((size_t)nh * sizeof(HspD), sm));
+        hsp_annotate_kernel<<<(nh + 255) / 256, 256, 0, sm>>>(d_cand.as<Cand>(), nh, d_off1.as<int64_t>(), nqi, d_off2.as<int64_t>(), nti, d_h.as<HspD>());
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        int rc = sort_by_keys<HspD>(ctx, d_h.as<HspD>(), nh, d_perm, &launches); if (rc) return rc;
+        gather_kernel<HspD><<<(nh + 255) / 256, 256, 0, sm>>>(d_h.as<HspD>(), d_perm.as<uint32_t>(), nh, d_hs.as<HspD>());
+        PB_CUDA(ctx, d_cl.alloc((size_t)nh * sizeof(ClD), sm)); PB_CUDA(ctx, d_cls.alloc((size_t)nh * sizeof(ClD), sm));
+        PB_CUDA(ctx, cudaMemsetAsync(d_cnt.as<unsigned long long>() + 4, 0, 8, sm));
+        PB_CUDA(ctx, cudaMemsetAsync(d_cl.p, 0xff, (size_t)nh * sizeof(ClD), sm));
+        hsp_cluster_kernel<<<(nh + 127) / 128, 128, 0, sm>>>(d_hs.as<HspD>(), nh, spec.diag_span, spec.clu_max, spec.clu_sum, d_cl.as<ClD>(),
+                                                             reinterpret_cast<unsigned int*>(d_cnt.as<unsigned long long>() + 4));
+        PB_CUDA(ctx, cudaGetLastError()); launches += 2;
+        rc = sort_by_keys<ClD>(ctx, d_cl.as<ClD>(), nh, d_perm2, &launches); if (rc) return rc;
+        gather_kernel<ClD><<<(nh + 255) / 256, 256, 0, sm>>>(d_cl.as<ClD>(), d_perm2.as<uint32_t>(), nh, d_cls.as<ClD>());
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        unsigned int ncl = 0;
+        PB_CUDA(ctx, cudaMemcpyAsync(&ncl, d_cnt.as<unsigned long long>() + 4, 4, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaStreamSynchronize(sm));
+        if (ncl > 0) {
+            PB_CUDA(ctx, d_win.alloc((size_t)ncl * sizeof(Window), sm));
+            PB_CUDA(ctx, d_wqb.alloc((size_t)ncl * 8, sm)); PB_CUDA(ctx, d_wqe.alloc((size_t)ncl * 8, sm));
+            PB_CUDA(ctx, d_wtb.alloc((size_t)ncl * 8, sm)); PB_CUDA(ctx, d_wte.alloc((size_t)ncl * 8, sm));
+            window_kernel<<<(ncl + 255) / 256, 256, 0, sm>>>(d_cls.as<ClD>(), (int)ncl, spec.pad, d_off1.as<int64_t>(), nqi, QL.total, d_off2.as<int64_t>(), nti, TL.total,
+                                                            d_win.as<Window>(), d_wqb.as<int64_t>(), d_wqe.as<int64_t>(), d_wtb.as<int64_t>(), d_wte.as<int64_t>());
+            PB_CUDA(ctx, cudaGetLastError()); ++launches;
+            win.resize(ncl);
+            PB_CUDA(ctx, cudaMemcpyAsync(win.data(), d_win.p, (size_t)ncl * sizeof(Window), cudaMemcpyDeviceToHost, sm));
+            PB_CUDA(ctx, cudaStreamSynchronize(sm));
         }
-        if (smax >= spec.clu_max || ssum >= spec.clu_sum) cl.push_back(c);
-        i = j;
     }
-    // territory: a window may not reach into the seeded extent of a neighbouring cluster of the same (query, target)
-    std::sort(cl.begin(), cl.end(), [](const Cl& a, const Cl& b) {
-        if (a.qid != b.qid) return a.qid < b.qid;
-        if (a.tid != b.tid) return a.tid < b.tid;
-        if (a.tmin != b.tmin) return a.tmin < b.tmin;
-        return a.tmax < b.tmax;
-    });
-    std::vector<Window> win; win.reserve(cl.size());
-    for (size_t i = 0; i < cl.size(); ++i) {
-        const Cl& c = cl[i];
-        const int64_t tl = TL.len[c.tid]; const int64_t qlen = QL.len[c.qid];
-        int64_t lo = c.tmin - c.qmin - spec.pad, hi = c.tmax + (qlen - c.qmax) + spec.pad;
-        if (i > 0 && cl[i - 1].qid == c.qid && cl[i - 1].tid == c.tid && cl[i - 1].tmax <= c.tmin) lo = std::max(lo, cl[i - 1].tmax);
-        if (i + 1 < cl.size() && cl[i + 1].qid == c.qid && cl[i + 1].tid == c.tid && cl[i + 1].tmin >= c.tmax) hi = std::min(hi, cl[i + 1].tmin);
-        lo = std::max<int64_t>(lo, 0); hi = std::min(hi, tl);
-        if (hi <= lo) continue;
-        win.push_back(Window{c.qid, c.tid, lo, (int)(hi - lo)});
-    }
-    st.n_windows = (int64_t)win.size();
     double h1 = now();
 
     // ---- K2: windowed Smith-Waterman with traceback ----
@@ -586,13 +688,15 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     uint32_t* cops = nullptr;
     float ms_trace = 0;
     if (nw > 0) {
-        std::vector<int64_t> qb(nw), tb(nw); std::vector<int32_t> qlv(nw), tlv(nw);
+        std::vector<int64_t> qb(nw), tb(nw);
+        double cells = 0;
         for (int64_t i = 0; i < nw; ++i) {
-            qb[i] = QL.off[win[i].qid]; qlv[i] = (int32_t)QL.len[win[i].qid];
-            tb[i] = TL.off[win[i].tid] + win[i].tbeg; tlv[i] = win[i].tlen;
+            qb[i] = QL.off[win[i].qid]; tb[i] = TL.off[win[i].tid] + win[i].tbeg;
+            if (win[i].tlen > 0) { cells += (double)QL.len[win[i].qid] * (double)win[i].tlen; ++st.n_windows; }
         }
         pb_sw_job* J = nullptr;
-        int rc = pb_sw_job_create_views(ctx, d_qc.as<uint8_t>(), d_tc.as<uint8_t>(), qb.data(), qlv.data(), tb.data(), tlv.data(), nw, &sp, 1, &J);
+        int rc = pb_sw_job_create_views_dev(ctx, d_qc.as<uint8_t>(), d_tc.as<uint8_t>(), d_wqb.as<int64_t>(), d_wqe.as<int64_t>(), d_wtb.as<int64_t>(),
+                                            d_wte.as<int64_t>(), nw, cells, &sp, 1, &J);
         if (rc) return rc;
         std::unique_ptr<pb_sw_job> guard(J);
         pb_sw_stats sst; memset(&sst, 0, sizeof(sst));

@@ -313,11 +313,13 @@ extern "C" int pb_sw_job_create(pb_ctx* ctx, const uint8_t* q, const int64_t* qo
     return sw_job_create_impl(ctx, q, qoff, t, toff, npairs, params, want_coords, job, nullptr, nullptr, nullptr);
 }
 
-// Internal: a job over "views" -- pair p aligns dq[qbeg[p] .. qbeg[p]+qlen[p]) with dt[tbeg[p] .. +tlen[p]) where dq/dt are
+// Internal: a job over "views" -- pair p aligns dq[qbeg[p] .. qend[p]) with dt[tbeg[p] .. tend[p]) where dq/dt are
 // device-resident code arrays owned by the caller (used by the search path: windows of a genome, no gather).
-int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, const int64_t* qbeg, const int32_t* qlen,
-                           const int64_t* tbeg, const int32_t* tlen, int64_t npairs, const pb_score_params* params,
-                           int want_coords, pb_sw_job** job)
+// The four int64 arrays are DEVICE arrays (the window kernel of pb_search writes them); `cells` is the caller's count of
+// DP cells (statistic only).
+int pb_sw_job_create_views_dev(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, const int64_t* d_qbeg, const int64_t* d_qend,
+                               const int64_t* d_tbeg, const int64_t* d_tend, int64_t npairs, double cells,
+                               const pb_score_params* params, int want_coords, pb_sw_job** job)
 {
     if (npairs > INT_MAX / 2) { pb_set_error(ctx, "too many pairs in one batch"); return PB_ERR_LIMIT; }
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -339,17 +341,14 @@ int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, co
     PB_CUDA(ctx, J->matrix.alloc(1024, ctx->stream));
     PB_CUDA(ctx, cudaMemcpyAsync(J->matrix.p, mat, 1024, cudaMemcpyHostToDevice, ctx->stream));
     size_t nn = std::max(n, 1);
-    std::vector<int64_t> qe(nn), te(nn);
-    double cells = 0;
-    for (int i = 0; i < n; ++i) { qe[i] = qbeg[i] + qlen[i]; te[i] = tbeg[i] + tlen[i]; cells += (double)qlen[i] * tlen[i]; }
     J->fwd_cells = cells;
     PB_CUDA(ctx, J->qoff.alloc(nn * 8, ctx->stream)); PB_CUDA(ctx, J->toff.alloc(nn * 8, ctx->stream));
     PB_CUDA(ctx, J->qend.alloc(nn * 8, ctx->stream)); PB_CUDA(ctx, J->tend.alloc(nn * 8, ctx->stream));
     if (n) {
-        PB_CUDA(ctx, cudaMemcpyAsync(J->qoff.p, qbeg, nn * 8, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(J->toff.p, tbeg, nn * 8, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(J->qend.p, qe.data(), nn * 8, cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(J->tend.p, te.data(), nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->qoff.p, d_qbeg, nn * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->toff.p, d_tbeg, nn * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->qend.p, d_qend, nn * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaMemcpyAsync(J->tend.p, d_tend, nn * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     PB_CUDA(ctx, J->desc.alloc(nn * sizeof(PairDesc), ctx->stream));
     PB_CUDA(ctx, J->desc_rev.alloc(nn * sizeof(PairDesc), ctx->stream));
@@ -364,7 +363,6 @@ int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, co
                                                             J->ids.as<int>(), J->perm.as<int>(), n, 0, 32, ctx->stream));
     J->cub_bytes = tmp;
     PB_CUDA(ctx, J->cub_tmp.alloc(std::max<size_t>(tmp, 16), ctx->stream));
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
     *job = guard.release();
     return PB_OK;
 }

@@ -27,9 +27,9 @@ struct pb_sw_job {
     cudaEvent_t ev_ready = nullptr;      // uploads enqueued on the copy stream finish here (pipelined pb_sw_batch)
 };
 
-int pb_sw_job_create_views(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, const int64_t* qbeg, const int32_t* qlen,
-                           const int64_t* tbeg, const int32_t* tlen, int64_t npairs, const pb_score_params* params,
-                           int want_coords, pb_sw_job** job);
+int pb_sw_job_create_views_dev(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt, const int64_t* d_qbeg, const int64_t* d_qend,
+                               const int64_t* d_tbeg, const int64_t* d_tend, int64_t npairs, double cells,
+                               const pb_score_params* params, int want_coords, pb_sw_job** job);
 
 // Traceback over an already run job (pb_trace.cu).  qbeg/tbeg: host begins of every pair in the device code arrays.
 // Outputs as in pb_sw_align_batch.
