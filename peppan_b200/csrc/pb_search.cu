@@ -19,6 +19,7 @@
 #include "pb_sw_job.h"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <chrono>
 #include <memory>
@@ -203,20 +204,40 @@ __global__ void build_table_kernel(const uint32_t* keys, int64_t nvalid, uint32_
     if (i == 0 || keys[i] != keys[i - 1]) table[keys[i]] = (uint32_t)i;
 }
 
+// ends[first slot of a key] = one past its last slot (written by the last element of every run)
+__global__ void build_ends_kernel(const uint32_t* keys, int64_t nvalid, const uint32_t* table, uint32_t* ends)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvalid) return;
+    if (i + 1 == nvalid || keys[i + 1] != keys[i]) ends[table[keys[i]]] = (uint32_t)(i + 1);
+}
+
 // ---- K1b: seed scan + ungapped X-drop ---------------------------------------------------------------
-// Each block stages a tile of the target codes in shared memory with 128-bit loads; every thread
-// then owns SCAN_PER_THREAD consecutive positions and rolls the k-mer key across them.
+// Each block stages a tile of the target codes in shared memory with 128-bit loads; every thread owns SCAN_PER_THREAD
+// consecutive positions, rolls the k-mer key across them and looks the table up (phase 1).  The (position, slot range)
+// pairs are then expanded densely over the block with a prefix sum (phase 2): every lane takes one seed, so lanes stay
+// busy however unevenly the seeds are spread over the positions.  A seed is extended by its lane for at most
+// T1 residues per side, which settles the random seeds; seeds that are still alive go to a queue that
+// xdrop_warp_kernel extends with one warp per seed, 32 residues per step (prefix sums and prefix maxima by shuffles).
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+constexpr int T1 = 16;
+
+struct SeedQ { uint32_t qpos, tpos; };
 
 __global__ void __launch_bounds__(SCAN_THREADS) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
                                                                  const uint8_t* __restrict__ qcodes, int64_t qn,
-                                                                 const uint32_t* __restrict__ table, const uint32_t* __restrict__ keys,
-                                                                 const uint32_t* __restrict__ vals, int64_t nvalid, DevSpec sp,
+                                                                 const uint32_t* __restrict__ table, const uint32_t* __restrict__ ends,
+                                                                 const uint32_t* __restrict__ vals, DevSpec sp,
                                                                  Cand* cand, unsigned long long* ncand, unsigned long long cap,
-                                                                 unsigned long long* nseed)
+                                                                 unsigned long long* nseed, SeedQ* longq, unsigned long long* nlong)
 {
     __shared__ __align__(16) uint8_t tile[SCAN_TILE + 64];
     __shared__ int8_t sscore[1024];
+    __shared__ uint32_t s_start[SCAN_TILE];
+    __shared__ uint32_t s_off[SCAN_TILE];
+    typedef cub::BlockScan<uint32_t, SCAN_THREADS> BlockScan;
+    __shared__ typename BlockScan::TempStorage scan_tmp;
+    __shared__ uint32_t s_total;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t*>(sscore)[i] = reinterpret_cast<const uint32_t*>(sp.score)[i];
     uint32_t pw = 1;
     for (int i = 1; i < sp.k; ++i) pw *= sp.base;          // base^(k-1)
@@ -232,77 +253,161 @@ __global__ void __launch_bounds__(SCAN_THREADS) seed_scan_kernel(const uint8_t* 
             *reinterpret_cast<uint4*>(tile + i) = v;
         }
         __syncthreads();
+        // ---- phase 1: keys and slot ranges of this thread's positions ----
         const int base_i = threadIdx.x * SCAN_PER_THREAD;
-        uint32_t key = 0; int bad = 0;        // bad = number of positions until the window is free of invalid residues
+        uint32_t key = 0; int bad = 0;
         for (int i = 0; i < sp.k - 1; ++i) {
             uint8_t c = tile[base_i + i];
             uint8_t sc = c < 32 ? sp.seedmap[c] : 255;
             if (sc == 255) { bad = i + 1; sc = 0; }
             key = key * sp.base + sc;
         }
-        // after the loop `bad` holds (index of last invalid)+1 within the first k-1 residues
         int last_bad = bad - 1;                  // position (relative to base_i) of the last invalid residue, -1 if none
+        uint32_t cnt[SCAN_PER_THREAD], st[SCAN_PER_THREAD];
+#pragma unroll
         for (int j = 0; j < SCAN_PER_THREAD; ++j) {
             const int pos = base_i + j;
             uint8_t c = tile[pos + sp.k - 1];
             uint8_t sc = c < 32 ? sp.seedmap[c] : 255;
             if (sc == 255) { last_bad = j + sp.k - 1; sc = 0; }
             key = key * sp.base + sc;            // key now covers [pos, pos+k)
-            const int64_t tpos = t0 + pos;
-            if (last_bad < j && tpos + sp.k <= tn) {
-                uint32_t slot = table[key];
-                if (slot != NOKEY) {
-                    for (int64_t o = slot; o < nvalid && keys[o] == key; ++o) {
-                        const int64_t qpos = vals[o];
-                        ++myseeds;
-                        // leftmost seed of a match run only: if the preceding residues agree in the seed alphabet the
-                        // preceding k-mer is a seed on the same diagonal and extends to the same HSP
-                        if (qpos > 0 && tpos > 0) {
-                            uint8_t a = qcodes[qpos - 1], b = tcodes[tpos - 1];
-                            uint8_t sa = a < 32 ? sp.seedmap[a] : 255, sb = b < 32 ? sp.seedmap[b] : 255;
-                            if (sa != 255 && sa == sb) continue;
-                        }
-                        // seed score
-                        int score = 0;
-                        for (int i = 0; i < sp.k; ++i) score += sscore[qcodes[qpos + i] * 32 + tile[pos + i]];
-                        int best = score, cur = score, rlen = sp.k;
-                        // extend right
-                        for (int64_t x = sp.k;; ++x) {
-                            if (qpos + x >= qn || tpos + x >= tn) break;
-                            uint8_t a = qcodes[qpos + x], b = tcodes[tpos + x];
-                            if (a == SENT || b == SENT) break;
-                            cur += sscore[a * 32 + b];
-                            if (cur > best) { best = cur; rlen = (int)x + 1; }
-                            else if (best - cur > sp.xdrop) break;
-                        }
-                        // extend left
-                        int lbest = best, llen = 0; cur = best;
-                        for (int64_t x = 1;; ++x) {
-                            if (qpos - x < 0 || tpos - x < 0) break;
-                            uint8_t a = qcodes[qpos - x], b = tcodes[tpos - x];
-                            if (a == SENT || b == SENT) break;
-                            cur += sscore[a * 32 + b];
-                            if (cur > lbest) { lbest = cur; llen = (int)x; }
-                            else if (lbest - cur > sp.xdrop) break;
-                        }
-                        if (lbest >= sp.min_ungapped) {
-                            unsigned long long slot2 = atomicAdd(ncand, 1ull);
-                            if (slot2 < cap) {
-                                Cand cd; cd.qpos = (uint32_t)(qpos - llen); cd.tpos = (uint32_t)(tpos - llen); cd.len = (uint32_t)(rlen + llen); cd.score = lbest;
-                                cand[slot2] = cd;
-                            }
-                        }
-                    }
-                }
+            cnt[j] = 0; st[j] = 0;
+            if (last_bad < j && t0 + pos + sp.k <= tn) {
+                const uint32_t slot = __ldg(table + key);
+                if (slot != NOKEY) { st[j] = slot; cnt[j] = __ldg(ends + slot) - slot; }
             }
-            // roll: drop the leading residue
             uint8_t c0 = tile[pos];
             uint8_t s0 = c0 < 32 ? sp.seedmap[c0] : 255;
             if (s0 == 255) s0 = 0;
             key -= s0 * pw;
         }
+        uint32_t off[SCAN_PER_THREAD], total;
+        BlockScan(scan_tmp).ExclusiveSum(cnt, off, total);
+#pragma unroll
+        for (int j = 0; j < SCAN_PER_THREAD; ++j) { s_start[base_i + j] = st[j]; s_off[base_i + j] = off[j]; }
+        if (threadIdx.x == 0) s_total = total;
+        __syncthreads();
+        const uint32_t H = s_total;
+        if (threadIdx.x == 0) myseeds += H;
+        // ---- phase 2: one seed per lane ----
+        for (uint32_t h = threadIdx.x; h < H; h += SCAN_THREADS) {
+            int lo = 0, hi = SCAN_TILE;              // last position whose exclusive offset is <= h
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= h) lo = mid + 1; else hi = mid; }
+            const int pos = lo - 1;
+            const uint32_t o = s_start[pos] + (h - s_off[pos]);
+            const int64_t qpos = __ldg(vals + o);
+            const int64_t tpos = t0 + pos;
+            // leftmost seed of a match run only: if the preceding residues agree in the seed alphabet the
+            // preceding k-mer is a seed on the same diagonal and extends to the same HSP
+            if (qpos > 0 && tpos > 0) {
+                uint8_t a = qcodes[qpos - 1], b = tcodes[tpos - 1];
+                uint8_t sa = a < 32 ? sp.seedmap[a] : 255, sb = b < 32 ? sp.seedmap[b] : 255;
+                if (sa != 255 && sa == sb) continue;
+            }
+            int score = 0;
+            for (int i = 0; i < sp.k; ++i) score += sscore[qcodes[qpos + i] * 32 + tile[pos + i]];
+            int best = score, cur = score, rlen = sp.k;
+            bool open = true;                        // extension still running when the lane's budget ended
+            for (int x = sp.k; x < sp.k + T1; ++x) {
+                if (qpos + x >= qn || tpos + x >= tn) { open = false; break; }
+                uint8_t a = qcodes[qpos + x], b = tcodes[tpos + x];
+                if (a == SENT || b == SENT) { open = false; break; }
+                cur += sscore[a * 32 + b];
+                if (cur > best) { best = cur; rlen = x + 1; }
+                else if (best - cur > sp.xdrop) { open = false; break; }
+            }
+            int lbest = best, llen = 0;
+            if (!open) {
+                cur = best; open = true;
+                for (int x = 1; x <= T1; ++x) {
+                    if (qpos - x < 0 || tpos - x < 0) { open = false; break; }
+                    uint8_t a = qcodes[qpos - x], b = tcodes[tpos - x];
+                    if (a == SENT || b == SENT) { open = false; break; }
+                    cur += sscore[a * 32 + b];
+                    if (cur > lbest) { lbest = cur; llen = x; }
+                    else if (lbest - cur > sp.xdrop) { open = false; break; }
+                }
+            }
+            if (open) {
+                const unsigned long long slot2 = atomicAdd(nlong, 1ull);
+                if (slot2 < cap) { SeedQ e; e.qpos = (uint32_t)qpos; e.tpos = (uint32_t)tpos; longq[slot2] = e; }
+            } else if (lbest >= sp.min_ungapped) {
+                const unsigned long long slot2 = atomicAdd(ncand, 1ull);
+                if (slot2 < cap) {
+                    Cand cd; cd.qpos = (uint32_t)(qpos - llen); cd.tpos = (uint32_t)(tpos - llen); cd.len = (uint32_t)(rlen + llen); cd.score = lbest;
+                    cand[slot2] = cd;
+                }
+            }
+        }
     }
     if (myseeds) atomicAdd(nseed, myseeds);
+}
+
+// One warp per queued seed: the same X-drop extension (right, then left from the right-extended best), 32 residues per
+// step.  With c_i the running score after residue i of the step and b_i the running best (inclusive prefix maximum,
+// seeded with the best so far), the scalar loop stops at the first i that is out of range / a sentinel, or has
+// b_i - c_i > xdrop; the best and its (first) position are those of the residues before the stop.
+__global__ void __launch_bounds__(256) xdrop_warp_kernel(const uint8_t* __restrict__ tcodes, int64_t tn, const uint8_t* __restrict__ qcodes, int64_t qn,
+                                                         DevSpec sp, const SeedQ* __restrict__ longq, unsigned long long nlong,
+                                                         Cand* cand, unsigned long long* ncand, unsigned long long cap)
+{
+    __shared__ int8_t sscore[1024];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t*>(sscore)[i] = reinterpret_cast<const uint32_t*>(sp.score)[i];
+    __syncthreads();
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nlong; w += nwarps) {
+        const int64_t qpos = longq[w].qpos, tpos = longq[w].tpos;
+        int score = 0;
+        if (lane < sp.k) score = sscore[qcodes[qpos + lane] * 32 + tcodes[tpos + lane]];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) score += __shfl_xor_sync(FULL, score, o);
+        int best = score, blen = sp.k;           // right extension: best score and residues covered
+        for (int dir = 0; dir < 2; ++dir) {
+            int cur = best, len = 0;             // len: residues of this side covered by the best
+            int sidebest = best;
+            for (int64_t x0 = 0;; x0 += 32) {
+                const int64_t x = x0 + lane;
+                const int64_t qi = dir == 0 ? qpos + sp.k + x : qpos - 1 - x, ti = dir == 0 ? tpos + sp.k + x : tpos - 1 - x;
+                bool valid = qi >= 0 && ti >= 0 && qi < qn && ti < tn;
+                int sc = 0;
+                if (valid) {
+                    const uint8_t a = qcodes[qi], b = tcodes[ti];
+                    if (a == SENT || b == SENT) valid = false; else sc = sscore[a * 32 + b];
+                }
+                int c = sc;                      // inclusive prefix sum of the step's scores
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, c, o); if (lane >= o) c += v; }
+                c += cur;
+                int bmax = c;                    // inclusive prefix maximum, seeded with the best so far
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, bmax, o); if (lane >= o) bmax = max(bmax, v); }
+                bmax = max(bmax, sidebest);
+                const unsigned stopm = __ballot_sync(FULL, !valid || bmax - c > sp.xdrop);
+                const int nstep = stopm ? __ffs(stopm) - 1 : 32;          // residues consumed before the stop
+                // best among the consumed residues: first lane that reaches a value above the previous best
+                const int cand_v = lane < nstep ? c : INT_MIN;
+                int mx = cand_v;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+                if (mx > sidebest) {
+                    const unsigned who = __ballot_sync(FULL, cand_v == mx);
+                    sidebest = mx; len = (int)x0 + __ffs(who);
+                }
+                if (nstep < 32) break;
+                cur = __shfl_sync(FULL, c, 31);
+            }
+            if (dir == 0) { best = sidebest; blen = sp.k + len; }
+            else if (lane == 0 && sidebest >= sp.min_ungapped) {
+                const unsigned long long slot2 = atomicAdd(ncand, 1ull);
+                if (slot2 < cap) {
+                    Cand cd; cd.qpos = (uint32_t)(qpos - len); cd.tpos = (uint32_t)(tpos - len); cd.len = (uint32_t)(blen + len); cd.score = sidebest;
+                    cand[slot2] = cd;
+                }
+            }
+        }
+    }
 }
 
 // ---- K1c: diagonal binning of the ungapped HSPs -> clusters -> target windows (all on the device) -----------
@@ -614,25 +719,39 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     st.n_query_kmers = nvalid;
     if (nvalid > 0) {
         build_table_kernel<<<(unsigned)((nvalid + 255) / 256), 256, 0, sm>>>(d_keys2.as<uint32_t>(), nvalid, d_table.as<uint32_t>());
-        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        // the unsorted key array is free again: it now holds the end slot of every key's run
+        build_ends_kernel<<<(unsigned)((nvalid + 255) / 256), 256, 0, sm>>>(d_keys2.as<uint32_t>(), nvalid, d_table.as<uint32_t>(), d_keys.as<uint32_t>());
+        PB_CUDA(ctx, cudaGetLastError()); launches += 2;
     }
     PB_CUDA(ctx, cudaEventRecord(e2, sm));
 
     // ---- K1b: seed scan (retry with a larger candidate buffer on overflow) ----
-    DevBuf d_cand;
+    DevBuf d_cand, d_longq;
     unsigned long long cap = std::max<unsigned long long>(1ull << 20, (unsigned long long)nq * 64);
     for (int attempt = 0; attempt < 4; ++attempt) {
         PB_CUDA(ctx, d_cand.alloc(cap * sizeof(Cand), sm));
-        PB_CUDA(ctx, cudaMemsetAsync(d_cnt.as<unsigned long long>() + 1, 0, 16, sm));
-        const int grid = (int)std::min<int64_t>((LT + SCAN_TILE - 1) / SCAN_TILE, (int64_t)ctx->sm_count * 8);
-        seed_scan_kernel<<<grid, SCAN_THREADS, 0, sm>>>(d_tc.as<uint8_t>(), LT, d_qc.as<uint8_t>(), LQ, d_table.as<uint32_t>(), d_keys2.as<uint32_t>(),
-                                                         d_vals2.as<uint32_t>(), nvalid, ds, d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap,
-                                                         d_cnt.as<unsigned long long>() + 2);
+        PB_CUDA(ctx, d_longq.alloc(cap * sizeof(SeedQ), sm));
+        PB_CUDA(ctx, cudaMemsetAsync(d_cnt.as<unsigned long long>() + 1, 0, 24, sm));
+        int occ = 1;
+        PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seed_scan_kernel, SCAN_THREADS, 0));
+        const int grid = (int)std::min<int64_t>((LT + SCAN_TILE - 1) / SCAN_TILE, (int64_t)ctx->sm_count * std::max(occ, 1));
+        seed_scan_kernel<<<grid, SCAN_THREADS, 0, sm>>>(d_tc.as<uint8_t>(), LT, d_qc.as<uint8_t>(), LQ, d_table.as<uint32_t>(), d_keys.as<uint32_t>(),
+                                                         d_vals2.as<uint32_t>(), ds, d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap,
+                                                         d_cnt.as<unsigned long long>() + 2, d_longq.as<SeedQ>(), d_cnt.as<unsigned long long>() + 3);
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         PB_CUDA(ctx, cudaMemcpyAsync(cnts, d_cnt.p, 64, cudaMemcpyDeviceToHost, sm));
         PB_CUDA(ctx, cudaStreamSynchronize(sm));
-        if (cnts[1] <= cap) break;
-        cap = cnts[1] + (cnts[1] >> 3);
+        if (cnts[3] <= cap && cnts[3] > 0) {
+            const unsigned long long nlong = cnts[3];
+            const int xgrid = (int)std::min<unsigned long long>((nlong + 7) / 8, (unsigned long long)ctx->sm_count * 8);
+            xdrop_warp_kernel<<<xgrid, 256, 0, sm>>>(d_tc.as<uint8_t>(), LT, d_qc.as<uint8_t>(), LQ, ds, d_longq.as<SeedQ>(), nlong,
+                                                     d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap);
+            PB_CUDA(ctx, cudaGetLastError()); ++launches;
+            PB_CUDA(ctx, cudaMemcpyAsync(cnts, d_cnt.p, 64, cudaMemcpyDeviceToHost, sm));
+            PB_CUDA(ctx, cudaStreamSynchronize(sm));
+        }
+        if (cnts[1] <= cap && cnts[3] <= cap) break;
+        cap = std::max(cnts[1], cnts[3]); cap += cap >> 3;
         if (attempt == 3) { pb_set_error(ctx, "pb_search: candidate buffer overflow"); return PB_ERR_LIMIT; }
     }
     if (cnts[1] > 0x7fffffffull) { pb_set_error(ctx, "pb_search: too many ungapped HSPs in one call; block the input"); return PB_ERR_LIMIT; }
