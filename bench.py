@@ -140,6 +140,84 @@ def cpu_oracle_leg(npairs_sample, threads, seed_rank=0):
     return cells / dt / 1e9, dt
 
 
+def search_world(n_core, n_acc, genome_index):
+    """Exemplar gene pool + one synthetic genome (SURVEY.md 8d generator) as seqsets of ASCII bytes."""
+    from peppan_b200 import seqio, workloads
+    pool = workloads.GenePool(n_core, n_acc)
+    seq, annot = workloads.synth_genome(pool, genome_index, n_acc_per_genome=n_acc // 8)
+    qn, qb, qo = seqio.to_seqset(pool.fasta_items())
+    rn, rb, ro = seqio.to_seqset([('g%d' % genome_index, seq)])
+    return qb, qo, rb, ro, len(annot)
+
+
+def search_leg(ctx, rank, pg, steps, with_cpu):
+    """Second hot-path measurement: the per-genome uberBlast search (BASELINE.json configs[2..3] unit of work): 15,000
+    exemplar genes against one synthetic ~5 Mbp genome of 4,500 genes through pb_search with HOST buffers, nucleotide
+    mode (runBlast) + protein-vs-6-frame mode (runDiamond); one genome per rank (independent units)."""
+    from peppan_b200 import search
+    qb, qo, rb, ro, ngenes = search_world(3000, 12000, rank)
+    q = ctx.pinned_empty(qb.shape, np.uint8); q[:] = qb
+    r = ctx.pinned_empty(rb.shape, np.uint8); r[:] = rb
+    modes = (('nt', search.MODE_NT), ('prot6', search.MODE_PROT6))
+    for _ in range(2):
+        for _, m in modes:
+            search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25)
+    barrier(pg)
+    t0 = time.perf_counter()
+    acc = {k: {} for k, _ in modes}
+    launches = 0
+    for _ in range(steps):
+        for k, m in modes:
+            hits, cig, st = search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25)
+            launches += st['kernel_launches']
+            for f in ('ms_encode', 'ms_index', 'ms_seed', 'ms_sw', 'ms_trace', 'ms_total'):
+                acc[k][f] = acc[k].get(f, 0.0) + st[f] / steps
+            acc[k].update(hits=int(len(hits)), windows=int(st['n_windows']), seed_hits=int(st['n_seed_hits']), sw_cells=float(st['sw_cells']),
+                          algo_bytes_seed=int(st['algo_bytes_seed']))
+    barrier(pg)
+    wall = allmax(pg, time.perf_counter() - t0)
+    nq = len(qo) - 1
+    total_q = allsum(pg, float(nq)) * steps
+    out = {'workload': 'per-genome search: %d exemplar genes vs one synthetic genome (%d bp, %d genes) per GPU, nt + protein 6-frame, '
+                       'min_id 0.4 min_cov 50 min_ratio 0.25 (iter_map_bsn thresholds)' % (nq, len(rb), ngenes),
+           'genes_per_s': total_q / wall, 'ms_per_genome': 1e3 * wall / steps, 'steps': steps,
+           'h2d_bytes_per_genome': int(2 * (len(qb) + len(rb) + 8 * (len(qo) + len(ro)))), 'gpu_launches': launches}
+    hbm = 6545.6
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:
+        pass
+    for k, _ in modes:
+        a = acc[k]
+        a['gcups_sw'] = a['sw_cells'] / max(a['ms_sw'], 1e-9) / 1e6
+        gbs = a['algo_bytes_seed'] / max(a['ms_seed'], 1e-9) / 1e6
+        a['seed_roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
+                              'note': 'algorithmic bytes (SURVEY 8d: target + 9 x query residues + 16 x seed hits) / seed-stage time'}
+        out[k] = a
+    if with_cpu and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import pb_oracle
+        from peppan_b200 import seqcodec
+        sqb, sqo, srb, sro, sg = search_world(300, 600, 0)
+        c0 = time.perf_counter()
+        nh = 0
+        for _, m in modes:
+            h, _c = pb_oracle.search(sqb, sqo, srb, sro, m, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
+            nh += len(h)
+        cdt = time.perf_counter() - c0
+        g0 = time.perf_counter()
+        ng = 0
+        for _, m in modes:
+            h, _c, _s = search.search(ctx, sqb, sqo, srb, sro, m, 0.4, 50, 0.25)
+            ng += len(h)
+        gdt = time.perf_counter() - g0
+        out['cpu_baseline'] = {'value': (len(sqo) - 1) / cdt, 'unit': 'genes/s', 'cores': 1, 'kind': 'port',
+                               'sample': '%d genes vs a %d bp genome, scalar search oracle (same search specification), 1 thread, %.1f s; '
+                                         'the GPU path on this same sample: %.0f genes/s; hit counts %d / %d' %
+                                         (len(sqo) - 1, len(srb), cdt, (len(sqo) - 1) / gdt, nh, ng)}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -178,6 +256,7 @@ def main():
     ap.add_argument('--pairs', type=int, default=1000000, help='pairs per GPU per step (config 2: 1,000,000)')
     ap.add_argument('--cpu-pairs', type=int, default=400000, help='pairs in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-search', action='store_true', help='skip the per-genome search leg (extra "search" object of the JSON line)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -234,6 +313,10 @@ def main():
     e2e_value = total_cells / (e2e_ms * 1e-3) / 1e9
     assert int(out['score'].astype(np.int64).sum()) == checksum
 
+    srch = None
+    if not args.no_search:
+        srch = search_leg(ctx, rank, pg, max(1, min(args.steps, 3)), not args.no_cpu_baseline)
+
     if rank != 0:
         return 0
     # roofline of the dominant kernel (forward s16x2 DP kernel): DPX issue peak, measured live
@@ -265,6 +348,7 @@ def main():
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': launches,
         'clocks': clocks,
+        'search': srch,
     }
     print(json.dumps(line))
     ctx.close()

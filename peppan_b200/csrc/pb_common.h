@@ -16,7 +16,9 @@ struct pb_ctx {
     int64_t hbm_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of the next chunk while the context stream computes
+    cudaStream_t aux_stream = nullptr;   // long-alignment (wavefront) kernels run beside the regular batch kernels
     cudaEvent_t ev_pipe[4] = {};
+    cudaEvent_t ev_aux[2] = {};          // fork / join of the aux stream
     cudaEvent_t ev[16] = {};   // 0-3 SW job, 4-7 pb_sw_batch, 8-13 search / cluster
     std::string err;
     void* nccl_comm = nullptr;      // ncclComm_t when world > 1
@@ -43,8 +45,6 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // H2D of the next chunk while the context stream computes
-    cudaEvent_t ev_pipe[4] = {};
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;

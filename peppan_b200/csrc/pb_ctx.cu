@@ -88,7 +88,9 @@ extern "C" int pb_init(int device, int rank, int world, const void* nccl_uid, pb
     ctx->hbm_bytes = (int64_t)prop.totalGlobalMem;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev_pipe) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : ctx->ev_aux) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
     CK(cudaMalloc(&ctx->d_counter, 64 * sizeof(int)));
     {
@@ -127,7 +129,9 @@ extern "C" void pb_destroy(pb_ctx* ctx)
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_pipe) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_aux) if (ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -13,8 +13,8 @@ using namespace pbsw;
 namespace {
 
 constexpr int PAD_SCORE = -16;
-constexpr int WAVE_G = 32, WAVE_K = 19, WAVE_W = WAVE_G * WAVE_K, WAVE_WARPS = 8;
-constexpr int LONG_COLS = 4 * WAVE_W - 1, LONG_ROWS = 1024;      // pairs beyond this shape use the wavefront kernel
+constexpr int WAVE_G = 32, WAVE_K = 8, WAVE_R = 2, WAVE_W = WAVE_G * WAVE_K, WAVE_WARPS = 8;   // thin strips: latency of one long pair matters, not throughput
+constexpr int LONG_COLS = 2431, LONG_ROWS = 1024;      // pairs beyond this shape use the wavefront kernel
 
 SwConfig sw_pick_config()
 {
@@ -175,13 +175,20 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     // sorted order: [s32 long][s32 regular][s16 long][s16 regular]
     struct Range { int first, count; bool packed, wave; };
     const Range ranges[4] = { {0, n32L, false, true}, {n32L, n32 - n32L, false, false}, {n32, n16L, true, true}, {n32 + n16L, n - n32 - n16L, true, false} };
+    // The long (wavefront) classes go first, on the aux stream: a handful of long pairs keep only a few SMs busy for
+    // milliseconds, so they run beside the regular kernels instead of in front of them.
     int slot = 0;
-    for (const Range& r : ranges) {
+    DevBuf wbs[2], wps[2];
+    bool forked = false;
+    static const int order[4] = {0, 2, 1, 3};
+    for (int oi = 0; oi < 4; ++oi) {
+        const Range& r = ranges[order[oi]];
         if (r.count <= 0) continue;
         a.first = r.first; a.count = r.count; a.counter = ctx->d_counter + (rev ? 8 : 0) + slot++;
         cudaError_t e;
         if (r.wave) {
             // wavefront kernel: sub-tasks = (task, column block) in task-major order, one warp each
+            const int wave_k = WAVE_K, wave_r = WAVE_R, wave_w = WAVE_W;
             const int npair = r.packed ? 2 : 1;
             const int ntask = (r.count + npair - 1) / npair;
             DevBuf d_shape;
@@ -197,19 +204,19 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
             for (int t = 0; t < ntask; ++t) {
                 int nmax = 0;
                 for (int k = 0; k < npair && t * npair + k < r.count; ++k) { nmax = std::max(nmax, shp[t * npair + k].y); maxm = std::max(maxm, shp[t * npair + k].x); }
-                const int nb = std::max(1, (nmax + WAVE_W - 1) / WAVE_W);
+                const int nb = std::max(1, (nmax + wave_w - 1) / wave_w);
                 base[t + 1] = base[t] + nb;
                 for (int b = 0; b < nb; ++b) sub.push_back(make_int2(t, b));
             }
             const int wstride = ((maxm + 63) / 64) * 64;
             const size_t nslot = (size_t)base[ntask];
             if (nslot * wstride * sizeof(uint2) > ((size_t)24 << 30)) { pb_set_error(ctx, "long-alignment border buffer would need %zu bytes; split the batch", nslot * wstride * sizeof(uint2)); return PB_ERR_LIMIT; }
-            DevBuf& wb = J->wbound; DevBuf& wp = J->wprog;
-            if (wb.bytes < nslot * wstride * sizeof(uint2)) PB_CUDA(ctx, wb.alloc(nslot * wstride * sizeof(uint2), ctx->stream));
+            DevBuf& wb = wbs[oi]; DevBuf& wp = wps[oi];
+            PB_CUDA(ctx, wb.alloc(nslot * wstride * sizeof(uint2), ctx->stream));
             // progress | done | keys | base | sub in one scratch buffer
             const size_t o_done = nslot * 4, o_key = ((o_done + (size_t)ntask * 4 + 7) / 8) * 8, o_base = o_key + (size_t)ntask * 16,
                          o_sub = ((o_base + (size_t)(ntask + 1) * 4 + 7) / 8) * 8, total = o_sub + sub.size() * sizeof(int2);
-            if (wp.bytes < total) PB_CUDA(ctx, wp.alloc(total, ctx->stream));
+            PB_CUDA(ctx, wp.alloc(total, ctx->stream));
             PB_CUDA(ctx, cudaMemsetAsync(wp.p, 0, o_base, ctx->stream));
             PB_CUDA(ctx, cudaMemcpyAsync((char*)wp.p + o_base, base.data(), (size_t)(ntask + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
             PB_CUDA(ctx, cudaMemcpyAsync((char*)wp.p + o_sub, sub.data(), sub.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
@@ -217,13 +224,17 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
             a.boundary = wb.as<uint2>(); a.bstride = wstride;
             a.progress = (int*)wp.p; a.wdone = (int*)((char*)wp.p + o_done); a.wkey = (unsigned long long*)((char*)wp.p + o_key);
             a.wbase = (const int*)((char*)wp.p + o_base); a.wsub = (const int2*)((char*)wp.p + o_sub); a.nsub = (int)sub.size();
-            const SwConfig wc{WAVE_G, WAVE_K, 2, 1, WAVE_WARPS};
+            const SwConfig wc{WAVE_G, wave_k, wave_r, 1, WAVE_WARPS};
             const int wgrid = std::max(1, std::min(grid, (int)((sub.size() + WAVE_WARPS - 1) / WAVE_WARPS)));
             const size_t smem = sw_smem_bytes(wc, r.packed, J->params.nsym);
-            if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, true, true, true>(a, wgrid, smem, ctx->stream)
-                                  : sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, true, false, true>(a, wgrid, smem, ctx->stream);
-            else e = rev ? sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, false, true, true>(a, wgrid, smem, ctx->stream)
-                         : sw_launch_one<WAVE_G, WAVE_K, 2, true, WAVE_WARPS, false, false, true>(a, wgrid, smem, ctx->stream);
+            PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[0], ctx->stream));
+            PB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux[0], 0));
+            forked = true;
+            cudaStream_t ws = ctx->aux_stream;
+            if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, true, true>(a, wgrid, smem, ws)
+                                  : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, false, true>(a, wgrid, smem, ws);
+            else e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, true, true>(a, wgrid, smem, ws)
+                         : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, false, true>(a, wgrid, smem, ws);
         } else {
             a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride; a.progress = nullptr; a.nsub = 0;
             if (r.packed) e = rev ? sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream) : sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream);
@@ -231,6 +242,10 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
         }
         PB_CUDA(ctx, e);
         ++*launches;
+    }
+    if (forked) {
+        PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[1], ctx->aux_stream));
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[1], 0));
     }
     return PB_OK;
 }

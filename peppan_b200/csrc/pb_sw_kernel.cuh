@@ -42,8 +42,8 @@
 // WAVE = true is the long-alignment variant: the unit of work is one column block (608 columns) of one task, taken
 // by a whole warp (G = 32) from a global list in (task, block) order.  The blocks of a task run as a pipeline spread
 // over the machine: the warp owning block b starts a row as soon as the warp owning block b-1 has published the border
-// cells of that row (global buffer + release/acquire progress counter, polled by lane 0 only, >= 32 rows behind so
-// one acquire covers many steps).  A 10 kb x 10 kb alignment then takes ~m/R + 32*blocks steps instead of
+// cells of that row (global buffer + release/acquire progress counter; the consumer stays >= 32 rows behind and
+// fetches the border in coalesced batches of 32 rows, so the L2 round trip is paid once per batch, not per step).  A 10 kb x 10 kb alignment then takes ~m/R + 32*blocks steps instead of
 // blocks * m/R.  Producers are always fetched before their consumers and never wait on them, so there is no deadlock.
 // The per-block maxima of a task are combined with a 64-bit atomicMax on (score, ~row, ~col).
 //
@@ -260,10 +260,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             int slimit = (rows_here + R - 1) / R + G - 1;
             bool armed = false;
             int published = 0;                  // WAVE: rows of the left border known to be complete
-            uint2 pref[R];                      // WAVE: border cells of the next step, loaded one step ahead
-            bool pref_ok = false;
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) pref[rr] = make_uint2(0u, 0u);
+            int bat0 = -32;                     // WAVE: first row of the border batch held in `bat` (lane j: row bat0 + j)
+            uint2 bat = make_uint2(0u, 0u);
             if (WAVE) { mybound = wavebound + (size_t)b * a.bstride; }
             const uint2* leftbound = WAVE ? (b > 0 ? wavebound + (size_t)(b - 1) * a.bstride : nullptr) : mybound;
 
@@ -311,35 +309,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                     else { hl[rr] = shfl_up_g(hlast[rr], G); fh[rr] = shfl_up_g(fout[rr], G); }
                     if (l == 0) { hl[rr] = 0; fh[rr] = 0; }
                 }
-                if (b > 0) {
-                    if (l == 0) {
-                        if (WAVE) {
-                            // the warp owning block b-1 publishes its progress every 16 steps; stay >= 32 rows behind it
-                            // so that one acquire covers many steps and the border cells can be loaded a step ahead
-                            const int need = min(r0 + R, mw);
-                            if (published < need) {
-                                const int want = min(r0 + R + 32, mw);
-                                while ((published = ld_acquire(waveprog + (b - 1))) < want) __nanosleep(200);
-                                pref_ok = false;
-                            }
-#pragma unroll
-                            for (int rr = 0; rr < R; ++rr)
-                                if ((unsigned)(r0 + rr) < (unsigned)mw) {
-                                    uint2 v = pref_ok ? pref[rr] : ld_volatile_u2(leftbound + r0 + rr);
-                                    hl[rr] = v.x; fh[rr] = v.y;
+                if (WAVE) {
+                    if (b > 0) {
+                        // border cells of block b-1 come in batches of 32 rows: one coalesced load by the whole warp,
+                        // lane 0 then takes its rows by shuffle.  The warp stays >= 32 rows behind the owner of block
+                        // b-1 (which publishes its progress every 16 steps), so a batch is complete when it is needed.
+                        const int row0 = s * R;                         // rows of lane 0 in this step (warp-uniform)
+                        if (row0 < mw) {
+                            if (row0 >= bat0 + 32) {
+                                const int want = min(row0 + 32, mw);
+                                while (published < want) {
+                                    published = ld_acquire(waveprog + (b - 1));
+                                    if (published < want) __nanosleep(100);
                                 }
-                            const int nr0 = r0 + R;
-                            pref_ok = (nr0 < mw) && (min(nr0 + R, mw) <= published);
-                            if (pref_ok) {
-#pragma unroll
-                                for (int rr = 0; rr < R; ++rr)
-                                    if ((unsigned)(nr0 + rr) < (unsigned)mw) pref[rr] = ld_volatile_u2(leftbound + nr0 + rr);
+                                bat0 = row0;
+                                const int row = bat0 + lane;
+                                bat = (row < mw) ? ld_volatile_u2(leftbound + row) : make_uint2(0u, 0u);
                             }
-                        } else {
 #pragma unroll
-                            for (int rr = 0; rr < R; ++rr)
-                                if ((unsigned)(r0 + rr) < (unsigned)bvalid) { uint2 v = leftbound[r0 + rr]; hl[rr] = v.x; fh[rr] = v.y; }
+                            for (int rr = 0; rr < R; ++rr) {
+                                const uint32_t vx = __shfl_sync(FULL, bat.x, row0 + rr - bat0), vy = __shfl_sync(FULL, bat.y, row0 + rr - bat0);
+                                if (l == 0 && row0 + rr < mw) { hl[rr] = vx; fh[rr] = vy; }
+                            }
                         }
+                    }
+                } else if (b > 0) {
+                    if (l == 0) {
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr)
+                            if ((unsigned)(r0 + rr) < (unsigned)bvalid) { uint2 v = leftbound[r0 + rr]; hl[rr] = v.x; fh[rr] = v.y; }
                     }
                 }
                 uint32_t hdiag[R];

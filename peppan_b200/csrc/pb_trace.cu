@@ -30,7 +30,7 @@ namespace {
 constexpr int TR_G = 16, TR_K = 16, TR_WARPS = 8;
 constexpr int TR_W = TR_G * TR_K;
 constexpr int TR_KW8 = TR_K / 8;        // direction words per lane per step
-constexpr int TRW_G = 32, TRW_W = TRW_G * TR_K;          // wavefront variant: whole warps, 512 columns per block
+constexpr int TRW_G = 32, TRW_K = 8, TRW_W = TRW_G * TRW_K;   // wavefront variant: whole warps, thin strips (256 columns per block)
 constexpr int WAVE_MIN_COLS = 4 * TR_W + 1, WAVE_MIN_ROWS = 768;   // boxes at least this large are pipelined across warps
 
 struct TraceDesc {
@@ -46,8 +46,8 @@ struct TraceDesc {
 inline bool is_wave(int M, int N) { return N >= WAVE_MIN_COLS && M >= WAVE_MIN_ROWS; }
 inline size_t dir_words(int M, int N, bool wave)
 {
-    const int G = wave ? TRW_G : TR_G, W = G * TR_K;
-    return (size_t)((N + W - 1) / W) * (size_t)(M + G - 1) * G * TR_KW8;
+    const int G = wave ? TRW_G : TR_G, K = wave ? TRW_K : TR_K, W = G * K;
+    return (size_t)((N + W - 1) / W) * (size_t)(M + G - 1) * G * (K / 8);
 }
 
 struct TraceArgs {
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) sw_trace_kernel(const TraceArgs
             if (WAVE) mybound = wavebound + (size_t)b * a.bstride;
             const uint2* leftbound = WAVE ? (b > 0 ? wavebound + (size_t)(b - 1) * a.bstride : nullptr) : mybound;
             int published = 0;                  // WAVE: rows of the left border known to be complete
-            uint2 pref = make_uint2(0u, 0u);    // WAVE: border cell of the next step, loaded one step ahead
-            bool pref_ok = false;
+            int bat0 = -32;                     // WAVE: first row of the border batch held in `bat`
+            uint2 bat = make_uint2(0u, 0u);
             for (int s = 0; s < slimit; ++s) {
                 const int i = s - l;
                 uint32_t w[KW];
@@ -154,23 +154,24 @@ __global__ void __launch_bounds__(WARPS * 32, 2) sw_trace_kernel(const TraceArgs
                 for (int x = 0; x < KW; ++x) w[x] = r[x];
                 { int in = i + 1; cq = ((unsigned)in < (unsigned)M) ? (int)__ldg(qb + (M - 1 - in)) : PAD; }
                 int hl = __shfl_up_sync(FULL, hlast, 1, G), fh = __shfl_up_sync(FULL, fout, 1, G);
-                if (l == 0) {
-                    hl = 0; fh = 0;
-                    if (b > 0 && (unsigned)i < (unsigned)mw) {
-                        if (WAVE) {
-                            // stay >= 32 rows behind the warp that owns block b-1: one acquire then covers many steps
-                            if (published < i + 1) {
-                                const int want = min(i + 1 + 32, mw);
-                                while ((published = ld_acquire(waveprog + (b - 1))) < want) __nanosleep(100);
-                                pref_ok = false;
+                if (l == 0) { hl = 0; fh = 0; }
+                if (WAVE) {
+                    // border cells of block b-1 in coalesced batches of 32 rows (lane j holds row bat0 + j); the warp stays
+                    // >= 32 rows behind the owner of block b-1, so a batch is complete when it is needed
+                    if (b > 0 && s < mw) {                 // s = row of lane 0 (warp-uniform)
+                        if (s >= bat0 + 32) {
+                            const int want = min(s + 32, mw);
+                            while (published < want) {
+                                published = ld_acquire(waveprog + (b - 1));
+                                if (published < want) __nanosleep(100);
                             }
-                            const uint2 v = pref_ok ? pref : ld_volatile_u2(leftbound + i);
-                            hl = (int)v.x; fh = (int)v.y;
-                            pref_ok = (i + 1 < mw) && (i + 2 <= published);
-                            if (pref_ok) pref = ld_volatile_u2(leftbound + i + 1);
-                        } else { uint2 v = leftbound[i]; hl = (int)v.x; fh = (int)v.y; }
+                            bat0 = s;
+                            bat = (bat0 + lane < mw) ? ld_volatile_u2(leftbound + bat0 + lane) : make_uint2(0u, 0u);
+                        }
+                        const uint32_t vx = __shfl_sync(FULL, bat.x, s - bat0), vy = __shfl_sync(FULL, bat.y, s - bat0);
+                        if (l == 0) { hl = (int)vx; fh = (int)vy; }
                     }
-                }
+                } else if (l == 0 && b > 0 && (unsigned)i < (unsigned)mw) { uint2 v = leftbound[i]; hl = (int)v.x; fh = (int)v.y; }
                 int hdiag = hl_prev; hl_prev = hl;
                 int hleft = hl;
                 uint32_t codes[KW8];
@@ -219,12 +220,11 @@ template <bool WRITE>
 __global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDesc* desc, int count, const uint32_t* dir,
                                int* nops, int* counts, const long long* ooff, uint32_t* ops)
 {
-    constexpr int K = TR_K, KW8 = TR_KW8;
     constexpr unsigned FULL = 0xffffffffu;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (x >= count) return;
     const TraceDesc d = desc[x];
-    const int G = d.wave ? TRW_G : TR_G, W = G * K;
+    const int G = d.wave ? TRW_G : TR_G, K = d.wave ? TRW_K : TR_K, KW8 = K / 8, W = G * K;
     const uint8_t* qb = q + d.qoff; const uint8_t* tb = t + d.toff;
     const int nsteps = d.M + G - 1;
     const uint32_t* base = dir + d.doff;
@@ -310,9 +310,9 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     std::vector<int> h_counts((size_t)npairs * 4, 0);
     const size_t budget_words = (size_t)std::min<int64_t>(ctx->hbm_bytes / 8, (int64_t)12 << 30) / 4;
     const size_t smem = 1024 + (size_t)TR_WARPS * (32 / TR_G) * params->nsym * TR_G * (((TR_K + 3) / 4) * 4);
-    const size_t smem_w = 1024 + (size_t)TR_WARPS * params->nsym * TRW_G * (((TR_K + 3) / 4) * 4);
+    const size_t smem_w = 1024 + (size_t)TR_WARPS * params->nsym * TRW_G * (((TRW_K + 3) / 4) * 4);
     auto kern = sw_trace_kernel<TR_G, TR_K, TR_WARPS, false>;
-    auto kern_w = sw_trace_kernel<TRW_G, TR_K, TR_WARPS, true>;
+    auto kern_w = sw_trace_kernel<TRW_G, TRW_K, TR_WARPS, true>;
     PB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PB_CUDA(ctx, cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     // persistent grids: every CTA resident at once (the wavefront variant spins on its left neighbour)
@@ -381,8 +381,12 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
             w.count = (int)c.nwave; w.boundary = dwbound.as<uint2>(); w.bstride = wstride; w.progress = (int*)dwprog.p;
             w.wsub = (const int2*)((char*)dwprog.p + o_sub); w.nsub = (int)sub.size(); w.counter = ctx->d_counter + 1;
             const int wgrid = std::max(1, std::min(grid_w, (int)((sub.size() + TR_WARPS - 1) / TR_WARPS)));
-            kern_w<<<wgrid, TR_WARPS * 32, smem_w, ctx->stream>>>(w);
+            // the few long boxes run on the aux stream beside the regular launch below
+            PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[0], ctx->stream));
+            PB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux[0], 0));
+            kern_w<<<wgrid, TR_WARPS * 32, smem_w, ctx->aux_stream>>>(w);
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
+            PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[1], ctx->aux_stream));
         }
         if (c.count > c.nwave) {
             const int bstride = c.maxNB > 1 ? ((c.maxM + 63) / 64) * 64 : 0;
@@ -393,6 +397,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
             kern<<<grid, TR_WARPS * 32, smem, ctx->stream>>>(r);
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
         }
+        if (c.nwave > 0) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[1], 0));
         const int tb = 128, gb = (int)((c.count * 32 + tb - 1) / tb);
         sw_walk_kernel<false><<<gb, tb, 0, ctx->stream>>>(a.q, a.t, a.desc, a.count, a.dir, dnops.as<int>(), dcounts.as<int>(), nullptr, nullptr);
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
