@@ -8,9 +8,11 @@
 // becomes a representative.  An edge (a, b) is verified when the local alignment found by the
 // nucleotide search (coding strand only) has identity >= I and covers >= C of both genes
 // (MMseqs2 --cov-mode 0).  Because only representatives can be joined, genes are processed in
-// blocks and each block is searched against {representatives so far} + {the block itself}: the
-// work is linear in the number of genes for redundant inputs, like linclust, and the result is
-// identical to the all-vs-all greedy.
+// blocks, each in two phases: the block is searched against the representatives so far (a gene
+// with a verified edge joins the earliest such representative -- all of them precede the block),
+// and only the genes nobody claimed are compared all against all.  The work is linear in the
+// number of genes for redundant inputs, like linclust, and the result is identical to the
+// all-vs-all greedy.
 //
 // The greedy assignment itself runs on the device as a monotone fixed-point iteration: a gene is
 // decided once all its earlier neighbours are decided (K3).
@@ -67,64 +69,89 @@ extern "C" int pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, flo
             res += genes->offsets[last + 1] - genes->offsets[last]; ++last;
         }
         const int nb = (int)(last - first), nr = (int)reps.size();
-        // targets: representatives so far, then the block
-        tbuf.assign(rep_bytes.begin(), rep_bytes.end());
-        toff.assign(rep_off.begin(), rep_off.end());
         const uint8_t* bsrc = genes->residues + genes->offsets[first];
-        tbuf.insert(tbuf.end(), bsrc, bsrc + res);
-        for (int64_t i = first; i < last; ++i) toff.push_back(toff.back() + (genes->offsets[i + 1] - genes->offsets[i]));
         std::vector<int64_t> qoff(nb + 1);
         for (int i = 0; i <= nb; ++i) qoff[i] = genes->offsets[first + i] - genes->offsets[first];
-        pb_seqset qs{bsrc, qoff.data(), nb}, ts{tbuf.data(), toff.data(), (int64_t)toff.size() - 1};
         pb_search_params prm; memset(&prm, 0, sizeof(prm));
         prm.mode = PB_MODE_NT; prm.gtable = 11; prm.min_id = min_id - 0.005f; prm.min_cov = 0; prm.min_ratio = std::max(0.f, min_cov - 0.005f);
         prm.max_hits_per_query = 1000; prm.reserved[0] = 1;
-        pb_hits hits; pb_search_stats sst;
-        int rc = pb_search(ctx, &qs, &ts, &prm, &hits, &sst);
-        if (rc) return rc;
-        st.n_pairs_verified += sst.n_windows; st.sw_cells += sst.sw_cells; st.kernel_launches += sst.kernel_launches;
-        // verified edges (a earlier than b)
-        std::vector<std::pair<int, int>> edges;      // (b local, a global)
-        for (int64_t h = 0; h < hits.n_hits; ++h) {
-            const pb_hit& x = hits.hits[h];
-            const int b = x.q_id;
-            const int a = x.s_id < nr ? reps[x.s_id] : (int)(first + (x.s_id - nr));
-            if (a >= first + b) continue;
+        auto verified = [&](const pb_hits& hits, const pb_hit& x) {
             int gapb = 0;
             for (uint32_t k = 0; k < x.cigar_n; ++k) { uint32_t op = hits.cigar[x.cigar_off + k]; if (op & 3) gapb += (int)(op >> 2); }
             const int nm = x.aln_len - x.mismatch - gapb;
             const double iden = (double)nm / (double)x.aln_len;
             const double qc = (double)(x.q_end - x.q_start + 1) / (double)x.q_len, sc = (double)(x.s_end - x.s_start + 1) / (double)x.s_len;
-            if (iden + 1e-9 >= (double)min_id && qc + 1e-9 >= (double)min_cov && sc + 1e-9 >= (double)min_cov) edges.emplace_back(b, a);
+            return iden + 1e-9 >= (double)min_id && qc + 1e-9 >= (double)min_cov && sc + 1e-9 >= (double)min_cov;
+        };
+        // phase 1: the block against the representatives so far.  Every representative precedes every gene of the block, so
+        // a gene with a verified edge to one joins the earliest such representative whatever happens inside the block.
+        std::vector<int> joined(nb, -1);
+        if (nr > 0) {
+            pb_seqset qs{bsrc, qoff.data(), nb}, ts{rep_bytes.data(), rep_off.data(), nr};
+            pb_hits hits; pb_search_stats sst;
+            int rc = pb_search(ctx, &qs, &ts, &prm, &hits, &sst);
+            if (rc) return rc;
+            st.n_pairs_verified += sst.n_windows; st.sw_cells += sst.sw_cells; st.kernel_launches += sst.kernel_launches;
+            for (int64_t h = 0; h < hits.n_hits; ++h) {
+                const pb_hit& x = hits.hits[h];
+                if (!verified(hits, x)) continue;
+                ++st.n_edges;
+                const int a = reps[x.s_id];
+                if (joined[x.q_id] < 0 || a < joined[x.q_id]) joined[x.q_id] = a;
+            }
+            pb_free_hits(&hits);
         }
-        pb_free_hits(&hits);
-        std::sort(edges.begin(), edges.end());
-        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
-        st.n_edges += (int64_t)edges.size();
-        std::vector<int> adj_off(nb + 1, 0), adj(edges.size());
-        for (auto& e : edges) adj_off[e.first + 1]++;
-        for (int i = 0; i < nb; ++i) adj_off[i + 1] += adj_off[i];
-        for (size_t i = 0; i < edges.size(); ++i) adj[i] = edges[i].second;
-        // K3: greedy fixed point on the device
-        DevBuf d_off, d_adj, d_state, d_rep, d_cnt;
-        PB_CUDA(ctx, d_off.alloc((nb + 1) * 4, sm)); PB_CUDA(ctx, d_adj.alloc(std::max<size_t>(adj.size(), 1) * 4, sm));
-        PB_CUDA(ctx, d_state.alloc(nb * 4, sm)); PB_CUDA(ctx, d_rep.alloc(nb * 4, sm)); PB_CUDA(ctx, d_cnt.alloc(4, sm));
-        PB_CUDA(ctx, cudaMemcpyAsync(d_off.p, adj_off.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, sm));
-        if (!adj.empty()) PB_CUDA(ctx, cudaMemcpyAsync(d_adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, sm));
-        PB_CUDA(ctx, cudaMemsetAsync(d_state.p, 0, nb * 4, sm));
-        int decided = 0;
-        while (decided < nb) {
-            PB_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, 4, sm));
-            greedy_round_kernel<<<(nb + 255) / 256, 256, 0, sm>>>(d_off.as<int>(), d_adj.as<int>(), nb, (int)first, d_state.as<int>(), d_rep.as<int>(), d_cnt.as<int>());
-            PB_CUDA(ctx, cudaGetLastError());
-            int c = 0;
-            PB_CUDA(ctx, cudaMemcpyAsync(&c, d_cnt.p, 4, cudaMemcpyDeviceToHost, sm));
+        // phase 2: the genes no representative claimed, all against all; greedy fixed point on the device
+        std::vector<int> novel;
+        for (int i = 0; i < nb; ++i) { if (joined[i] >= 0) rep_of[first + i] = joined[i]; else novel.push_back(i); }
+        const int nn = (int)novel.size();
+        if (nn > 0) {
+            tbuf.clear(); toff.assign(1, 0);
+            for (int i : novel) {
+                tbuf.insert(tbuf.end(), bsrc + qoff[i], bsrc + qoff[i + 1]);
+                toff.push_back(toff.back() + (qoff[i + 1] - qoff[i]));
+            }
+            pb_seqset ns{tbuf.data(), toff.data(), nn};
+            pb_hits hits; pb_search_stats sst;
+            int rc = pb_search(ctx, &ns, &ns, &prm, &hits, &sst);
+            if (rc) return rc;
+            st.n_pairs_verified += sst.n_windows; st.sw_cells += sst.sw_cells; st.kernel_launches += sst.kernel_launches;
+            std::vector<std::pair<int, int>> edges;      // (b, a) in novel-local indices, a earlier than b
+            for (int64_t h = 0; h < hits.n_hits; ++h) {
+                const pb_hit& x = hits.hits[h];
+                if (x.s_id >= x.q_id) continue;
+                if (verified(hits, x)) edges.emplace_back(x.q_id, x.s_id);
+            }
+            pb_free_hits(&hits);
+            std::sort(edges.begin(), edges.end());
+            edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+            st.n_edges += (int64_t)edges.size();
+            std::vector<int> adj_off(nn + 1, 0), adj(edges.size());
+            for (auto& e : edges) adj_off[e.first + 1]++;
+            for (int i = 0; i < nn; ++i) adj_off[i + 1] += adj_off[i];
+            for (size_t i = 0; i < edges.size(); ++i) adj[i] = edges[i].second;
+            DevBuf d_off, d_adj, d_state, d_rep, d_cnt;
+            PB_CUDA(ctx, d_off.alloc((nn + 1) * 4, sm)); PB_CUDA(ctx, d_adj.alloc(std::max<size_t>(adj.size(), 1) * 4, sm));
+            PB_CUDA(ctx, d_state.alloc(nn * 4, sm)); PB_CUDA(ctx, d_rep.alloc(nn * 4, sm)); PB_CUDA(ctx, d_cnt.alloc(4, sm));
+            PB_CUDA(ctx, cudaMemcpyAsync(d_off.p, adj_off.data(), (nn + 1) * 4, cudaMemcpyHostToDevice, sm));
+            if (!adj.empty()) PB_CUDA(ctx, cudaMemcpyAsync(d_adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, sm));
+            PB_CUDA(ctx, cudaMemsetAsync(d_state.p, 0, nn * 4, sm));
+            int decided = 0;
+            while (decided < nn) {
+                PB_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, 4, sm));
+                greedy_round_kernel<<<(nn + 255) / 256, 256, 0, sm>>>(d_off.as<int>(), d_adj.as<int>(), nn, 0, d_state.as<int>(), d_rep.as<int>(), d_cnt.as<int>());
+                PB_CUDA(ctx, cudaGetLastError());
+                int c = 0;
+                PB_CUDA(ctx, cudaMemcpyAsync(&c, d_cnt.p, 4, cudaMemcpyDeviceToHost, sm));
+                PB_CUDA(ctx, cudaStreamSynchronize(sm));
+                if (c == 0) { pb_set_error(ctx, "pb_cluster: greedy iteration made no progress"); return PB_ERR_LIMIT; }
+                decided += c; st.greedy_rounds++; st.kernel_launches++;
+            }
+            std::vector<int> lrep(nn);
+            PB_CUDA(ctx, cudaMemcpyAsync(lrep.data(), d_rep.p, nn * 4, cudaMemcpyDeviceToHost, sm));
             PB_CUDA(ctx, cudaStreamSynchronize(sm));
-            if (c == 0) { pb_set_error(ctx, "pb_cluster: greedy iteration made no progress"); return PB_ERR_LIMIT; }
-            decided += c; st.greedy_rounds++; st.kernel_launches++;
+            for (int x = 0; x < nn; ++x) rep_of[first + novel[x]] = (int)first + novel[lrep[x]];
         }
-        PB_CUDA(ctx, cudaMemcpyAsync(rep_of + first, d_rep.p, nb * 4, cudaMemcpyDeviceToHost, sm));
-        PB_CUDA(ctx, cudaStreamSynchronize(sm));
         for (int i = 0; i < nb; ++i)
             if (rep_of[first + i] == first + i) {
                 reps.push_back((int)(first + i));

@@ -187,8 +187,9 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
         a.first = r.first; a.count = r.count; a.counter = ctx->d_counter + (rev ? 8 : 0) + slot++;
         cudaError_t e;
         if (r.wave) {
-            // wavefront kernel: sub-tasks = (task, column block) in task-major order, one warp each
-            const int wave_k = WAVE_K, wave_r = WAVE_R, wave_w = WAVE_W;
+            // wavefront kernel: sub-tasks = (task, column block) in task-major order, one warp each.  Tasks are cut into
+            // chunks whose border buffers fit a fixed budget; the chunks run back to back on the aux stream.
+            const int wave_w = WAVE_W;
             const int npair = r.packed ? 2 : 1;
             const int ntask = (r.count + npair - 1) / npair;
             DevBuf d_shape;
@@ -198,43 +199,73 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
             std::vector<int2> shp(r.count);
             PB_CUDA(ctx, cudaMemcpyAsync(shp.data(), d_shape.p, (size_t)r.count * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
             PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            std::vector<int> base(ntask + 1, 0);
-            std::vector<int2> sub;
-            int maxm = 1;
-            for (int t = 0; t < ntask; ++t) {
-                int nmax = 0;
-                for (int k = 0; k < npair && t * npair + k < r.count; ++k) { nmax = std::max(nmax, shp[t * npair + k].y); maxm = std::max(maxm, shp[t * npair + k].x); }
-                const int nb = std::max(1, (nmax + wave_w - 1) / wave_w);
-                base[t + 1] = base[t] + nb;
-                for (int b = 0; b < nb; ++b) sub.push_back(make_int2(t, b));
+            struct WChunk { int t0, t1; size_t slot0, nslot, sub0, nsub; int stride; };
+            std::vector<WChunk> chunks;
+            std::vector<int> base;              // per chunk: ntask_chunk + 1 prefix sums of column blocks, starting at 0
+            std::vector<int2> sub;              // (chunk-local task, column block)
+            const size_t BUDGET = (size_t)2 << 30;
+            size_t total_slots = 0, max_bytes = 0;
+            {
+                WChunk c{0, 0, 0, 0, 0, 0, 0};
+                int cmax = 1;
+                auto close = [&](int t_end) {
+                    c.t1 = t_end; c.stride = ((cmax + 63) / 64) * 64;
+                    max_bytes = std::max(max_bytes, c.nslot * (size_t)c.stride * sizeof(uint2));
+                    chunks.push_back(c);
+                    total_slots += c.nslot;
+                };
+                base.push_back(0);
+                for (int t = 0; t < ntask; ++t) {
+                    int nmax = 0, mmax = 1;
+                    for (int k = 0; k < npair && t * npair + k < r.count; ++k) { nmax = std::max(nmax, shp[t * npair + k].y); mmax = std::max(mmax, shp[t * npair + k].x); }
+                    const int nb = std::max(1, (nmax + wave_w - 1) / wave_w);
+                    const int nmaxm = std::max(cmax, mmax);
+                    if (t > c.t0 && (c.nslot + nb) * (size_t)(((nmaxm + 63) / 64) * 64) * sizeof(uint2) > BUDGET) {
+                        close(t);
+                        c = WChunk{t, t, total_slots, 0, sub.size(), 0, 0}; cmax = 1;
+                        base.push_back(0);
+                    }
+                    cmax = std::max(cmax, mmax);
+                    for (int bb = 0; bb < nb; ++bb) sub.push_back(make_int2(t - c.t0, bb));
+                    c.nslot += nb; c.nsub += nb;
+                    base.push_back((int)c.nslot);
+                }
+                close(ntask);
             }
-            const int wstride = ((maxm + 63) / 64) * 64;
-            const size_t nslot = (size_t)base[ntask];
-            if (nslot * wstride * sizeof(uint2) > ((size_t)24 << 30)) { pb_set_error(ctx, "long-alignment border buffer would need %zu bytes; split the batch", nslot * wstride * sizeof(uint2)); return PB_ERR_LIMIT; }
+            if (max_bytes > ((size_t)24 << 30)) { pb_set_error(ctx, "long-alignment border buffer would need %zu bytes; split the batch", max_bytes); return PB_ERR_LIMIT; }
             DevBuf& wb = wbs[oi]; DevBuf& wp = wps[oi];
-            PB_CUDA(ctx, wb.alloc(nslot * wstride * sizeof(uint2), ctx->stream));
-            // progress | done | keys | base | sub in one scratch buffer
-            const size_t o_done = nslot * 4, o_key = ((o_done + (size_t)ntask * 4 + 7) / 8) * 8, o_base = o_key + (size_t)ntask * 16,
-                         o_sub = ((o_base + (size_t)(ntask + 1) * 4 + 7) / 8) * 8, total = o_sub + sub.size() * sizeof(int2);
+            PB_CUDA(ctx, wb.alloc(max_bytes, ctx->stream));
+            // control block: progress[total_slots] | done[ntask] | counters[nchunks] | keys[2 * ntask] (u64) | base | sub
+            const size_t nch = chunks.size();
+            const size_t o_done = total_slots * 4, o_cnt = o_done + (size_t)ntask * 4, o_key = ((o_cnt + nch * 4 + 7) / 8) * 8,
+                         o_base = o_key + (size_t)ntask * 16, o_sub = ((o_base + base.size() * 4 + 7) / 8) * 8, total = o_sub + sub.size() * sizeof(int2);
             PB_CUDA(ctx, wp.alloc(total, ctx->stream));
             PB_CUDA(ctx, cudaMemsetAsync(wp.p, 0, o_base, ctx->stream));
-            PB_CUDA(ctx, cudaMemcpyAsync((char*)wp.p + o_base, base.data(), (size_t)(ntask + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+            PB_CUDA(ctx, cudaMemcpyAsync((char*)wp.p + o_base, base.data(), base.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             PB_CUDA(ctx, cudaMemcpyAsync((char*)wp.p + o_sub, sub.data(), sub.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
             PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // host staging vectors are released below
-            a.boundary = wb.as<uint2>(); a.bstride = wstride;
-            a.progress = (int*)wp.p; a.wdone = (int*)((char*)wp.p + o_done); a.wkey = (unsigned long long*)((char*)wp.p + o_key);
-            a.wbase = (const int*)((char*)wp.p + o_base); a.wsub = (const int2*)((char*)wp.p + o_sub); a.nsub = (int)sub.size();
-            const SwConfig wc{WAVE_G, wave_k, wave_r, 1, WAVE_WARPS};
-            const int wgrid = std::max(1, std::min(grid, (int)((sub.size() + WAVE_WARPS - 1) / WAVE_WARPS)));
-            const size_t smem = sw_smem_bytes(wc, r.packed, J->params.nsym);
             PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[0], ctx->stream));
             PB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux[0], 0));
             forked = true;
             cudaStream_t ws = ctx->aux_stream;
-            if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, true, true>(a, wgrid, smem, ws)
-                                  : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, false, true>(a, wgrid, smem, ws);
-            else e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, true, true>(a, wgrid, smem, ws)
-                         : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, false, true>(a, wgrid, smem, ws);
+            const SwConfig wc{WAVE_G, WAVE_K, WAVE_R, 1, WAVE_WARPS};
+            const size_t smem = sw_smem_bytes(wc, r.packed, J->params.nsym);
+            e = cudaSuccess;
+            for (size_t ci = 0; ci < nch && e == cudaSuccess; ++ci) {
+                const WChunk& c = chunks[ci];
+                a.first = r.first + c.t0 * npair; a.count = std::min(r.count - c.t0 * npair, (c.t1 - c.t0) * npair);
+                a.counter = (int*)((char*)wp.p + o_cnt) + ci;
+                a.boundary = wb.as<uint2>(); a.bstride = c.stride;
+                a.progress = (int*)wp.p + c.slot0; a.wdone = (int*)((char*)wp.p + o_done) + c.t0;
+                a.wkey = (unsigned long long*)((char*)wp.p + o_key) + 2 * (size_t)c.t0;
+                a.wbase = (const int*)((char*)wp.p + o_base) + c.t0 + ci; a.wsub = (const int2*)((char*)wp.p + o_sub) + c.sub0; a.nsub = (int)c.nsub;
+                const int wgrid = std::max(1, std::min(grid, (int)((c.nsub + WAVE_WARPS - 1) / WAVE_WARPS)));
+                if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, true, true>(a, wgrid, smem, ws)
+                                      : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, false, true>(a, wgrid, smem, ws);
+                else e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, true, true>(a, wgrid, smem, ws)
+                             : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, false, true>(a, wgrid, smem, ws);
+                if (ci + 1 < nch) ++*launches;
+            }
         } else {
             a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride; a.progress = nullptr; a.nsub = 0;
             if (r.packed) e = rev ? sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream) : sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream);
