@@ -469,9 +469,9 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
     return PB_OK;
 }
 
-extern "C" int pb_sw_job_fetch(pb_ctx* ctx, pb_sw_job* J, int32_t* score, int32_t* qs, int32_t* qe, int32_t* ts, int32_t* te)
+// enqueue the device-to-host copies of a job's results on the context stream (no synchronisation)
+static int sw_job_fetch_enqueue(pb_ctx* ctx, pb_sw_job* J, int32_t* score, int32_t* qs, int32_t* qe, int32_t* ts, int32_t* te)
 {
-    if (!ctx || !J) { pb_set_error(ctx, "pb_sw_job_fetch: invalid argument"); return PB_ERR_ARG; }
     size_t b = (size_t)J->npairs * 4;
     if (b == 0) return PB_OK;
     if (score) PB_CUDA(ctx, cudaMemcpyAsync(score, J->score.p, b, cudaMemcpyDeviceToHost, ctx->stream));
@@ -481,11 +481,23 @@ extern "C" int pb_sw_job_fetch(pb_ctx* ctx, pb_sw_job* J, int32_t* score, int32_
         if (qs) PB_CUDA(ctx, cudaMemcpyAsync(qs, J->qs.p, b, cudaMemcpyDeviceToHost, ctx->stream));
         if (ts) PB_CUDA(ctx, cudaMemcpyAsync(ts, J->ts.p, b, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    return PB_OK;
+}
+
+static int sw_check_starts(pb_ctx* ctx, const int32_t* qs, int64_t n)
+{
+    for (int64_t p = 0; p < n; ++p)
+        if (qs[p] == -2) { pb_set_error(ctx, "internal: reverse pass did not reproduce the forward score for pair %lld", (long long)p); return PB_ERR_LIMIT; }
+    return PB_OK;
+}
+
+extern "C" int pb_sw_job_fetch(pb_ctx* ctx, pb_sw_job* J, int32_t* score, int32_t* qs, int32_t* qe, int32_t* ts, int32_t* te)
+{
+    if (!ctx || !J) { pb_set_error(ctx, "pb_sw_job_fetch: invalid argument"); return PB_ERR_ARG; }
+    int rc = sw_job_fetch_enqueue(ctx, J, score, qs, qe, ts, te);
+    if (rc) return rc;
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (J->want_coords && qs) {
-        for (int64_t p = 0; p < J->npairs; ++p)
-            if (qs[p] == -2) { pb_set_error(ctx, "internal: reverse pass did not reproduce the forward score for pair %lld", (long long)p); return PB_ERR_LIMIT; }
-    }
+    if (J->want_coords && qs) return sw_check_starts(ctx, qs, J->npairs);
     return PB_OK;
 }
 
@@ -505,10 +517,29 @@ extern "C" int pb_sw_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, c
     const int want = (qs || ts) ? 1 : 0;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     // Large batches are cut into chunks and software-pipelined: chunk c+1 is uploaded on the copy stream while the
-    // kernels of chunk c run on the context stream.
+    // kernels of chunk c run on the context stream.  The first chunk is small so that the kernels start early; when the
+    // caller's output arrays are page-locked the results of a chunk are copied out asynchronously behind its kernels.
     int64_t CHUNK = 1 << 18;
     if (const char* e = getenv("PB_SW_CHUNK")) { long long v = atoll(e); if (v > 0) CHUNK = v; }
-    const int64_t nchunk = npairs <= CHUNK + CHUNK / 2 ? 1 : (npairs + CHUNK - 1) / CHUNK;
+    std::vector<int64_t> cuts(1, 0);                    // chunk boundaries
+    if (npairs <= CHUNK + CHUNK / 2) cuts.push_back(npairs);
+    else {
+        // geometric ramp: the kernels of a chunk last about as long as the upload of a four times larger one
+        cuts.push_back(CHUNK / 4);
+        cuts.push_back(CHUNK / 4 + CHUNK);
+        const int64_t done = CHUNK / 4 + CHUNK, rest = npairs - done, k = (rest + 4 * CHUNK - 1) / (4 * CHUNK);
+        for (int64_t i = 1; i <= k; ++i) cuts.push_back(done + rest * i / k);
+    }
+    const int64_t nchunk = (int64_t)cuts.size() - 1;
+    bool pinned_out = true;
+    {
+        const void* outs[5] = {score, qs, qe, ts, te};
+        for (const void* o : outs) {
+            if (!o) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, o) != cudaSuccess || at.type != cudaMemoryTypeHost) { pinned_out = false; cudaGetLastError(); }
+        }
+    }
     cudaEvent_t e0 = ctx->ev[4], e3 = ctx->ev[7];
     PB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     pb_sw_stats tot; memset(&tot, 0, sizeof(tot));
@@ -516,9 +547,8 @@ extern "C" int pb_sw_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, c
     Slot slots[2];
     auto destroy = [&](Slot& s) { if (s.J) { pb_sw_job_destroy(ctx, s.J); s.J = nullptr; } };
     auto stage = [&](int64_t c, Slot& s) -> int {
-        s.first = c * ((npairs + nchunk - 1) / nchunk);
-        s.n = std::min<int64_t>((npairs + nchunk - 1) / nchunk, npairs - s.first);
-        if (s.n < 0) s.n = 0;
+        s.first = cuts[c];
+        s.n = cuts[c + 1] - cuts[c];
         const int64_t* qo = qoff + s.first; const int64_t* to = toff + s.first;
         if (nchunk > 1) {
             s.qo.resize(s.n + 1); s.to.resize(s.n + 1);
@@ -535,8 +565,12 @@ extern "C" int pb_sw_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, c
         if (c + 1 < nchunk) { rc = stage(c + 1, slots[(c + 1) & 1]); if (rc) { destroy(cur); return rc; } }
         pb_sw_stats st; memset(&st, 0, sizeof(st));
         rc = pb_sw_job_run(ctx, cur.J, &st);
-        if (!rc) rc = pb_sw_job_fetch(ctx, cur.J, score + cur.first, qs ? qs + cur.first : nullptr, qe ? qe + cur.first : nullptr,
-                                      ts ? ts + cur.first : nullptr, te ? te + cur.first : nullptr);
+        if (!rc) {
+            int32_t* o_qs = qs ? qs + cur.first : nullptr; int32_t* o_qe = qe ? qe + cur.first : nullptr;
+            int32_t* o_ts = ts ? ts + cur.first : nullptr; int32_t* o_te = te ? te + cur.first : nullptr;
+            rc = pinned_out ? sw_job_fetch_enqueue(ctx, cur.J, score + cur.first, o_qs, o_qe, o_ts, o_te)
+                            : pb_sw_job_fetch(ctx, cur.J, score + cur.first, o_qs, o_qe, o_ts, o_te);
+        }
         if (rc) { destroy(slots[0]); destroy(slots[1]); return rc; }
         tot.cells += st.cells; tot.cells_reverse += st.cells_reverse; tot.ms_forward += st.ms_forward; tot.ms_reverse += st.ms_reverse;
         tot.ms_total_device += st.ms_total_device; tot.kernel_launches += st.kernel_launches; tot.n_s32_pairs += st.n_s32_pairs;
@@ -544,6 +578,7 @@ extern "C" int pb_sw_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* qoff, c
     }
     PB_CUDA(ctx, cudaEventRecord(e3, ctx->stream));
     PB_CUDA(ctx, cudaEventSynchronize(e3));
+    if (pinned_out && want && qs) { rc = sw_check_starts(ctx, qs, npairs); if (rc) return rc; }
     if (stats) {
         *stats = tot;
         float ms_all = 0; cudaEventElapsedTime(&ms_all, e0, e3);

@@ -15,13 +15,19 @@ def concat(seqs):
     return np.ascontiguousarray(flat), off
 
 
-def sw_batch(ctx, q, qoff, t, toff, params, coords=True):
+def sw_batch(ctx, q, qoff, t, toff, params, coords=True, out=None):
     """Align pair p = (q[qoff[p]:qoff[p+1]], t[toff[p]:toff[p+1]]).  Returns dict of int32 arrays
-    (score, qs, qe, ts, te; 0-based inclusive, -1 where score == 0) and the call's stats."""
+    (score, qs, qe, ts, te; 0-based inclusive, -1 where score == 0) and the call's stats.
+    `out`: optional dict of preallocated int32[n] arrays (e.g. page-locked ones from
+    Context.pinned_empty, which the library fills asynchronously behind the kernels)."""
     n = len(qoff) - 1
     q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
     qoff = np.ascontiguousarray(qoff, dtype=np.int64); toff = np.ascontiguousarray(toff, dtype=np.int64)
-    out = {k: np.full(n, -1, dtype=np.int32) for k in ('score', 'qs', 'qe', 'ts', 'te')}
+    if out is None:
+        out = {k: np.full(n, -1, dtype=np.int32) for k in ('score', 'qs', 'qe', 'ts', 'te')}
+    else:
+        for k in ('score', 'qs', 'qe', 'ts', 'te'):
+            assert out[k].dtype == np.int32 and out[k].size == n and out[k].flags.c_contiguous
     st = SwStats()
     rc = ctx.lib.pb_sw_batch(ctx.h, ptr(q), ptr(qoff), ptr(t), ptr(toff), n, C.byref(params),
                              ptr(out['score']), ptr(out['qs']) if coords else None, ptr(out['qe']),
