@@ -150,7 +150,7 @@ def search_world(n_core, n_acc, genome_index):
     return qb, qo, rb, ro, len(annot)
 
 
-def search_leg(ctx, rank, pg, steps, with_cpu):
+def search_leg(ctx, rank, world, pg, steps, with_cpu):
     """Second hot-path measurement: the per-genome uberBlast search (BASELINE.json configs[2..3] unit of work): 15,000
     exemplar genes against one synthetic ~5 Mbp genome of 4,500 genes through pb_search with HOST buffers, nucleotide
     mode (runBlast) + protein-vs-6-frame mode (runDiamond); one genome per rank (independent units)."""
@@ -161,18 +161,19 @@ def search_leg(ctx, rank, pg, steps, with_cpu):
     modes = (('nt', search.MODE_NT), ('prot6', search.MODE_PROT6))
     for _ in range(2):
         for _, m in modes:
-            search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25)
+            search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1)
     barrier(pg)
     t0 = time.perf_counter()
     acc = {k: {} for k, _ in modes}
     launches = 0
     for _ in range(steps):
         for k, m in modes:
-            hits, cig, st = search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25)
+            # N > 1: the per-rank hit tables are merged by one NCCL allgather (identical table on every rank)
+            hits, cig, st = search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1)
             launches += st['kernel_launches']
             for f in ('ms_encode', 'ms_index', 'ms_seed', 'ms_sw', 'ms_trace', 'ms_total'):
                 acc[k][f] = acc[k].get(f, 0.0) + st[f] / steps
-            acc[k].update(hits=int(len(hits)), windows=int(st['n_windows']), seed_hits=int(st['n_seed_hits']), sw_cells=float(st['sw_cells']),
+            acc[k].update(hits=int(len(hits)), allgather='nccl' if world > 1 else None, windows=int(st['n_windows']), seed_hits=int(st['n_seed_hits']), sw_cells=float(st['sw_cells']),
                           algo_bytes_seed=int(st['algo_bytes_seed']))
     barrier(pg)
     wall = allmax(pg, time.perf_counter() - t0)
@@ -262,9 +263,10 @@ def main():
         return run_reference(args)
 
     rank, world, local, pg = dist_setup(args.gpus)
-    from peppan_b200 import seqcodec, sw, workloads
+    from peppan_b200 import dist as pbd, seqcodec, sw, workloads
     from peppan_b200._lib import Context
-    ctx = Context(local)
+    # N > 1: the context carries an NCCL communicator (unique id handed out over gloo) for the hit-table allgather
+    ctx = pbd.init_context_from_env(pg) if world > 1 else Context(local)
     info = ctx.device_info()
     params = seqcodec.protein_params()
     npairs = args.pairs
@@ -316,7 +318,7 @@ def main():
 
     srch = None
     if not args.no_search:
-        srch = search_leg(ctx, rank, pg, max(1, min(args.steps, 3)), not args.no_cpu_baseline)
+        srch = search_leg(ctx, rank, world, pg, max(1, min(args.steps, 3)), not args.no_cpu_baseline)
 
     if rank != 0:
         return 0
