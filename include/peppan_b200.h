@@ -194,6 +194,21 @@ typedef struct {
 int  pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int32_t* rep_of,
                 pb_cluster_stats* stats /* nullable */);
 
+/* pb_cluster with the `translate` switch of clust -a / params['translate'] (modules/clust.py:28,38-46):
+ * translate != 0 compares the genes as proteins (frame 1 of every gene against frame 1 of the others,
+ * BLOSUM62 11/1; identity and coverage over the protein alignment), gtable as in pb_search. */
+int  pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int translate, int gtable,
+                   int32_t* rep_of, pb_cluster_stats* stats /* nullable */);
+
+/* transeq (modules/configure.py:160-194) on the device: for every sequence s and every requested frame
+ * frames[k] (1..3 forward, 4..6 reverse complement) the amino-acid letters of its codons, index
+ * b0<<4|b1<<2|b2 into the table of :167-170 (gtable 4: TGA -> W; mark_starts: GTG / TTG -> M, :171-172);
+ * a codon holding '-' gives '-', any other non-ACGT base or the padded tail gives 'X' (:186-191).
+ * out_off[s * nframes + k] is where the translation of (s, frames[k]) starts in out (caller-computed:
+ * its length is ceil((len - (f-1)%3) / 3), 0 when the sequence is shorter than the offset). */
+int  pb_transeq(pb_ctx* ctx, const pb_seqset* nt, const int32_t* frames, int nframes, int gtable, int mark_starts,
+                uint8_t* out, const int64_t* out_off);
+
 /* Measures the issue rate of dependent-free DPX chains on all SMs (lane-ops/s): the roofline
  * denominator of the extension kernels.  which: 0 = viaddmax_s16x2, 1 = s32. */
 int pb_measure_dpx_peak(pb_ctx* ctx, int which, double* lane_ops_per_s);

@@ -28,16 +28,16 @@ class ClusterStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
 
 
-def cluster(ctx, seq_bytes, seq_off, identity, coverage):
-    """pb_cluster on a seqset in priority order -> (rep_of int32[n], stats dict)"""
+def cluster(ctx, seq_bytes, seq_off, identity, coverage, translate=False, gtable=11):
+    """pb_cluster_ex on a seqset in priority order -> (rep_of int32[n], stats dict)"""
     lib = ctx.lib
-    lib.pb_cluster.argtypes = [C.c_void_p, C.POINTER(SeqSet), C.c_float, C.c_float, C.c_void_p, C.POINTER(ClusterStats)]
+    lib.pb_cluster_ex.argtypes = [C.c_void_p, C.POINTER(SeqSet), C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.POINTER(ClusterStats)]
     seq_bytes = np.ascontiguousarray(seq_bytes, dtype=np.uint8); seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
     n = len(seq_off) - 1
     rep = np.zeros(n, dtype=np.int32)
     ss = SeqSet(seq_bytes.ctypes.data, seq_off.ctypes.data, n)
     st = ClusterStats()
-    ctx.check(lib.pb_cluster(ctx.h, C.byref(ss), identity, coverage, ptr(rep), C.byref(st)), 'pb_cluster')
+    ctx.check(lib.pb_cluster_ex(ctx.h, C.byref(ss), identity, coverage, 1 if translate else 0, gtable, ptr(rep), C.byref(st)), 'pb_cluster_ex')
     return rep, st.as_dict()
 
 
@@ -57,16 +57,18 @@ def _read_records(path):
 
 
 def getClust(prefix, genes, params):
-    if params.get('translate'):
-        raise NotImplementedError('translated clustering (-a) is not available in peppan_b200 yet; PEPPAN itself calls '
-                                  'getClust with translate=False (PEPPAN.py:1884)')
+    translate = bool(params.get('translate'))
     recs = _read_records(genes)
     names, buf, off = seqio.to_seqset([(n, s) for n, _, s in recs])
-    rep, st = cluster(get_context(), buf, off, float(params['identity']), float(params['coverage']))
+    # translate (-a, modules/clust.py:38-46): frame-1 proteins are compared on the device; no seq.aa file is written
+    rep, st = cluster(get_context(), buf, off, float(params['identity']), float(params['coverage']), translate=translate)
     exemplar, tab = '{0}.clust.exemplar'.format(prefix), '{0}.clust.tab'.format(prefix)
     with open(exemplar, 'w') as fout:
         for i, (n, lines, s) in enumerate(recs):
             if rep[i] == i:
+                if translate:                       # the reference re-emits the nucleotide records one per line (:95-100)
+                    fout.write('>{0}\n{1}\n'.format(n, s))
+                    continue
                 for line in lines:
                     fout.write(line)
     groups = {names[i]: names[rep[i]] for i in range(len(names))}

@@ -49,6 +49,12 @@ __global__ void greedy_round_kernel(const int* adj_off, const int* adj, int nb, 
 
 extern "C" int pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int32_t* rep_of, pb_cluster_stats* stats)
 {
+    return pb_cluster_ex(ctx, genes, min_id, min_cov, 0, 11, rep_of, stats);
+}
+
+extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int translate, int gtable,
+                             int32_t* rep_of, pb_cluster_stats* stats)
+{
     if (!ctx || !genes || !rep_of || genes->n < 0) { pb_set_error(ctx, "pb_cluster: invalid argument"); return PB_ERR_ARG; }
     pb_cluster_stats st; memset(&st, 0, sizeof(st));
     const int64_t n = genes->n;
@@ -73,9 +79,13 @@ extern "C" int pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, flo
         std::vector<int64_t> qoff(nb + 1);
         for (int i = 0; i <= nb; ++i) qoff[i] = genes->offsets[first + i] - genes->offsets[first];
         pb_search_params prm; memset(&prm, 0, sizeof(prm));
-        prm.mode = PB_MODE_NT; prm.gtable = 11; prm.min_id = min_id - 0.005f; prm.min_cov = 0; prm.min_ratio = std::max(0.f, min_cov - 0.005f);
-        prm.max_hits_per_query = 1000; prm.reserved[0] = 1;
+        // translate: genes compared as proteins, frame 1 against frame 1 (clust -a translates frame 1 only, modules/clust.py:42);
+        // reserved[0] bit 1 pins the query frame to 1, hits on target frames 2 / 3 are ignored below
+        prm.mode = translate ? PB_MODE_PROT3_SELF : PB_MODE_NT; prm.gtable = gtable; prm.min_id = min_id - 0.005f; prm.min_cov = 0;
+        prm.min_ratio = std::max(0.f, min_cov - 0.005f);
+        prm.max_hits_per_query = 1000; prm.reserved[0] = translate ? 2 : 1;
         auto verified = [&](const pb_hits& hits, const pb_hit& x) {
+            if (translate && x.frame != 1) return false;
             int gapb = 0;
             for (uint32_t k = 0; k < x.cigar_n; ++k) { uint32_t op = hits.cigar[x.cigar_off + k]; if (op & 3) gapb += (int)(op >> 2); }
             const int nm = x.aln_len - x.mismatch - gapb;

@@ -149,14 +149,14 @@ __global__ void translate_targets_kernel(const uint8_t* nt, const int64_t* ntoff
 
 // queries: choose the forward frame with the fewest 'X'-separated pieces, counted on the frame
 // without its last residue (modules/uberBlast.py:528); ties -> lowest frame.  One warp per gene.
-__global__ void choose_frame_kernel(const uint8_t* nt, const int64_t* ntoff, int64_t nseq, int table4, int* frame, int* aalen)
+__global__ void choose_frame_kernel(const uint8_t* nt, const int64_t* ntoff, int64_t nseq, int table4, int force1, int* frame, int* aalen)
 {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nseq) return;
     const int64_t a = ntoff[w], L = ntoff[w + 1] - a;
     int best = 0, bestx = 0x7fffffff, bestlen = 0;
-    for (int f = 0; f < 3; ++f) {
+    for (int f = 0; f < (force1 ? 1 : 3); ++f) {
         const int64_t rem = L - f, na = rem > 0 ? (rem + 2) / 3 : 0;
         int nx = 0;
         for (int64_t i = lane; i < na - 1; i += 32) nx += translate_codon(nt + a, L, f + 3 * i, false, table4) == 20;
@@ -589,6 +589,77 @@ const int8_t PB_BLOSUM62_21[21 * 21] = {
 }  // namespace
 
 // ==================================================================================================
+namespace {
+// transeq proper (ASCII in, ASCII out): one thread per codon of one (sequence, frame); grid.y walks the pairs
+__global__ void transeq_ascii_kernel(const uint8_t* __restrict__ nt, const int64_t* __restrict__ ntoff, int64_t nseq,
+                                     const int32_t* __restrict__ frames, int nframes, const int64_t* __restrict__ ooff,
+                                     const uint8_t* __restrict__ table65, uint8_t* out)
+{
+    for (int64_t sf = blockIdx.y; sf < nseq * nframes; sf += gridDim.y) {
+        const int64_t s = sf / nframes; const int f = frames[sf % nframes] - 1;      // 0..5
+        const int64_t a = ntoff[s], L = ntoff[s + 1] - a;
+        const int off = f % 3; const bool rev = f >= 3;
+        const int64_t rem = L - off, na = rem > 0 ? (rem + 2) / 3 : 0;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += (int64_t)gridDim.x * blockDim.x) {
+            int idx = 0; bool gap = false, bad = false;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                const int64_t p = off + 3 * i + x;
+                int c = 4;                                     // padded tail counts as ambiguous
+                if (p < L) {
+                    const uint8_t ch = rev ? nt[a + L - 1 - p] : nt[a + p];
+                    if (ch == '-') gap = true;
+                    c = nt_code(ch);
+                    if (rev && c < 4) c = 3 - c;
+                }
+                if (c >= 4) bad = true;
+                idx = (idx << 2) | (c & 3);
+            }
+            out[ooff[sf] + i] = gap ? (uint8_t)'-' : (bad ? (uint8_t)'X' : table65[idx]);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int pb_transeq(pb_ctx* ctx, const pb_seqset* nt, const int32_t* frames, int nframes, int gtable, int mark_starts,
+                          uint8_t* out, const int64_t* out_off)
+{
+    if (!ctx || !nt || !frames || nframes <= 0 || nframes > 6 || !out_off || nt->n < 0) { pb_set_error(ctx, "pb_transeq: invalid argument"); return PB_ERR_ARG; }
+    for (int k = 0; k < nframes; ++k) if (frames[k] < 1 || frames[k] > 6) { pb_set_error(ctx, "pb_transeq: frame %d out of 1..6", frames[k]); return PB_ERR_ARG; }
+    const int64_t n = nt->n;
+    if (n == 0) return PB_OK;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t sm = ctx->stream;
+    const int64_t nbytes = nt->offsets[n];
+    int64_t total = 0;
+    for (int64_t s = 0; s < n; ++s)
+        for (int k = 0; k < nframes; ++k) {
+            const int64_t rem = (nt->offsets[s + 1] - nt->offsets[s]) - (frames[k] - 1) % 3;
+            total = std::max(total, out_off[s * nframes + k] + (rem > 0 ? (rem + 2) / 3 : 0));
+        }
+    if (total == 0) return PB_OK;
+    if (!out) { pb_set_error(ctx, "pb_transeq: output buffer missing"); return PB_ERR_ARG; }
+    uint8_t table[64];
+    memcpy(table, CODON11, 64);
+    if (gtable == 4) table[56] = 'W';
+    if (mark_starts) { table[46] = 'M'; table[62] = 'M'; }
+    DevBuf d_nt, d_off, d_fr, d_ooff, d_tab, d_out;
+    PB_CUDA(ctx, d_nt.alloc(std::max<int64_t>(nbytes, 16), sm)); PB_CUDA(ctx, d_off.alloc((n + 1) * 8, sm));
+    PB_CUDA(ctx, d_fr.alloc(nframes * 4, sm)); PB_CUDA(ctx, d_ooff.alloc((size_t)n * nframes * 8, sm));
+    PB_CUDA(ctx, d_tab.alloc(64, sm)); PB_CUDA(ctx, d_out.alloc((size_t)total, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_nt.p, nt->residues, nbytes, cudaMemcpyHostToDevice, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_off.p, nt->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_fr.p, frames, nframes * 4, cudaMemcpyHostToDevice, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_ooff.p, out_off, (size_t)n * nframes * 8, cudaMemcpyHostToDevice, sm));
+    PB_CUDA(ctx, cudaMemcpyAsync(d_tab.p, table, 64, cudaMemcpyHostToDevice, sm));
+    transeq_ascii_kernel<<<dim3(64, (unsigned)std::min<int64_t>(n * nframes, 4096)), 256, 0, sm>>>(
+        d_nt.as<uint8_t>(), d_off.as<int64_t>(), n, d_fr.as<int32_t>(), nframes, d_ooff.as<int64_t>(), d_tab.as<uint8_t>(), d_out.as<uint8_t>());
+    PB_CUDA(ctx, cudaGetLastError());
+    PB_CUDA(ctx, cudaMemcpyAsync(out, d_out.p, (size_t)total, cudaMemcpyDeviceToHost, sm));
+    PB_CUDA(ctx, cudaStreamSynchronize(sm));
+    return PB_OK;
+}
+
 extern "C" void pb_free_hits(pb_hits* h)
 {
     if (!h) return;
@@ -675,7 +746,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         encode_nt_kernel<<<dim3(1, (unsigned)std::min<int64_t>(nq, 32768)), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_qsoff.as<int64_t>(), nullptr, nq, d_tmpq.as<uint8_t>());
         encode_nt_kernel<<<dim3(256, (unsigned)std::min<int64_t>(nc, 256)), 256, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_tsoff.as<int64_t>(), nullptr, nc, d_tmpt.as<uint8_t>());
         PB_CUDA(ctx, d_frame.alloc(nq * 4, sm)); PB_CUDA(ctx, d_aalen.alloc(nq * 4, sm));
-        choose_frame_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), nq, table4, d_frame.as<int>(), d_aalen.as<int>());
+        choose_frame_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), nq, table4, (prm->reserved[0] & 2) ? 1 : 0, d_frame.as<int>(), d_aalen.as<int>());
         PB_CUDA(ctx, cudaGetLastError()); launches += 3;
         std::vector<int> aalen(nq);
         PB_CUDA(ctx, cudaMemcpyAsync(qframe.data(), d_frame.p, nq * 4, cudaMemcpyDeviceToHost, sm));

@@ -101,3 +101,40 @@ def protein_params():
 def nt_params():
     """+2/-3, gap 6/2: blastn flags at modules/uberBlast.py:294."""
     return score_params(nt_matrix(), NT_NSYM, 6, 2)
+
+
+def transeq(seq, frame=7, transl_table=None, markStarts=False, ctx=None):
+    """Mirror of modules/configure.py:160-194 on the device (pb_transeq): `seq` is a dict name -> nucleotide string
+    or a list of (name, string); returns the same container with a list of amino-acid strings per requested frame
+    ('F' = 1-3, 'R' = 4-6, '7' = 1-6, or comma-separated numbers).  No CPU fallback."""
+    import ctypes as C
+    from ._lib import ptr
+    from .search import SeqSet
+    if ctx is None:
+        from .uberBlast import get_context
+        ctx = get_context()
+    frames = {'F': [1, 2, 3], 'R': [4, 5, 6], '7': [1, 2, 3, 4, 5, 6]}.get(str(frame).upper(), None)
+    if frames is None:
+        frames = [int(f) for f in str(frame).split(',')]
+    items = list(seq.items()) if isinstance(seq, dict) else list(seq)
+    n, nf = len(items), len(frames)
+    enc = [s.upper().encode() for _, s in items]
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        off[1:] = np.cumsum([len(b) for b in enc])
+    buf = np.frombuffer(b''.join(enc), dtype=np.uint8) if n and off[-1] else np.zeros(0, np.uint8)
+    lens = np.diff(off)
+    rem = lens[:, None] - (np.array(frames, dtype=np.int64)[None, :] - 1) % 3
+    alen = np.where(rem > 0, (rem + 2) // 3, 0).reshape(-1)
+    ooff = np.zeros(n * nf + 1, dtype=np.int64)
+    ooff[1:] = np.cumsum(alen)
+    out = np.zeros(max(int(ooff[-1]), 1), dtype=np.uint8)
+    fr = np.array(frames, dtype=np.int32)
+    lib = ctx.lib
+    lib.pb_transeq.argtypes = [C.c_void_p, C.POINTER(SeqSet), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    ss = SeqSet(buf.ctypes.data if buf.size else None, off.ctypes.data, n)
+    ctx.check(lib.pb_transeq(ctx.h, C.byref(ss), ptr(fr), nf, 4 if transl_table == 4 else 11, 1 if markStarts else 0, ptr(out), ptr(ooff)),
+              'pb_transeq')
+    raw = out.tobytes()
+    res = [[name, [raw[ooff[i * nf + k]:ooff[i * nf + k + 1]].decode() for k in range(nf)]] for i, (name, _) in enumerate(items)]
+    return dict(res) if isinstance(seq, dict) else res

@@ -25,14 +25,14 @@ def _genes(seed, n_anc=60, copies=4):
     return [(str(i), s) for i, s in enumerate(items)]
 
 
-def _oracle_clusters(oracle, items, identity, coverage):
+def _oracle_clusters(oracle, items, identity, coverage, translate=False):
     names, buf, off = seqio.to_seqset(items)
-    hits, cig = oracle.search(buf, off, buf, off, 1 | 256, seqcodec.BLOSUM62.reshape(-1), min_id=identity - 0.005, min_cov=0,
-                              min_ratio=max(0.0, coverage - 0.005), max_hits=1000)
+    hits, cig = oracle.search(buf, off, buf, off, 3 if translate else (1 | 256), seqcodec.BLOSUM62.reshape(-1), min_id=identity - 0.005,
+                              min_cov=0, min_ratio=max(0.0, coverage - 0.005), max_hits=1000)
     ea, eb = [], []
     for h in hits:
         a, b = int(h['s_id']), int(h['q_id'])
-        if a >= b:
+        if a >= b or (translate and int(h['frame']) != 1):
             continue
         ops = cig[int(h['cigar_off']):int(h['cigar_off']) + int(h['cigar_n'])]
         gapb = int(sum(int(o) >> 2 for o in ops if int(o) & 3))
@@ -54,6 +54,17 @@ def test_cluster_matches_oracle_greedy(ctx, oracle, identity, coverage):
     assert np.array_equal(rep, want)
     assert (rep <= np.arange(len(rep))).all() and (rep[rep] == rep).all()
     assert st['n_reps'] == int((rep == np.arange(len(rep))).sum()) and st['kernel_launches'] > 0
+
+
+@pytest.mark.parametrize('identity,coverage', [(0.9, 0.8), (0.7, 0.5)])
+def test_translated_cluster_matches_oracle_greedy(ctx, oracle, identity, coverage):
+    # clust -a: genes compared as frame-1 proteins (modules/clust.py:38-46)
+    items = _genes(4, n_anc=50)
+    names, buf, off = seqio.to_seqset(items)
+    rep, st = clust.cluster(ctx, buf, off, identity, coverage, translate=True)
+    want = _oracle_clusters(oracle, items, identity, coverage, translate=True)
+    assert np.array_equal(rep, want)
+    assert 0 < st['n_reps'] < len(items)
 
 
 def test_cluster_blocked_equals_single_block(ctx, monkeypatch):
@@ -87,3 +98,11 @@ def test_getclust_files(ctx, tmp_path):
     # the CLI wrapper produces the same files
     ex2, tab2 = clust.clust(['-i', fa, '-p', prefix + '2', '-d', '0.9', '-c', '0.8'])
     assert open(tab2).read() == open(tab).read()
+    # -a: translated clustering; exemplar records are re-emitted as one-line nucleotide records (modules/clust.py:95-100)
+    ex3, tab3 = clust.clust(['-i', fa, '-p', prefix + '3', '-d', '0.9', '-c', '0.8', '-a'])
+    pairs3 = [l.rstrip('\n').split('\t') for l in open(tab3)]
+    reps3 = set(p[1] for p in pairs3)
+    lines3 = open(ex3).read().split('\n')
+    seqs = dict(items)
+    assert [l[1:] for l in lines3 if l.startswith('>')] == [n for n, _ in items if n in reps3]
+    assert all(lines3[i + 1] == seqs[lines3[i][1:]] for i in range(0, len(lines3) - 1, 2))

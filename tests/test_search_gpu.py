@@ -82,3 +82,24 @@ def test_ambiguous_bases_gtable4_and_empty(ctx, oracle):
     junk = [('j%d' % i, ''.join(rng.choice(list('ACGT'), size=300).tolist())) for i in range(5)]
     hits, st = _check(ctx, oracle, junk, contigs, search.MODE_NT, min_id=0.4, min_cov=50, min_ratio=0.25)
     assert len(hits) == 0
+
+
+def test_transeq_device_matches_reference_golden(ctx):
+    """seqcodec.transeq (pb_transeq on the device) against the vectors generated from modules/configure.py:160-194"""
+    import json, os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'transeq.json')))
+    n = 0
+    for c in cases:
+        got = seqcodec.transeq({'a': c['seq']}, frame=c['frame'], transl_table=c['table'], ctx=ctx)['a']
+        assert got == c['out'], (c['seq'][:30], c['frame'], c['table'])
+        n += len(got)
+    assert n > 300
+    # batched call, list container, markStarts (SURVEY.md Appendix C-3)
+    seqs = [(str(i), c['seq']) for i, c in enumerate(cases) if c['frame'] == '7' and c['table'] == 11]
+    got = seqcodec.transeq(seqs, frame='7', transl_table=11, ctx=ctx)
+    want = [c['out'] for c in cases if c['frame'] == '7' and c['table'] == 11]
+    assert [g[1] for g in got] == want and [g[0] for g in got] == [s[0] for s in seqs]
+    assert seqcodec.transeq({'a': 'TAATAGTGAATGGTGTTGCTGATTATCATA'}, frame='1', transl_table=11, markStarts=True, ctx=ctx)['a'] == ['XXXMMMLIII']
+    assert seqcodec.transeq({'a': 'ATGNNNAC-GTA'}, frame='1', ctx=ctx)['a'] == ['MX-V']
+    assert seqcodec.transeq({'a': 'TAATAGTGAATGGTGTTGCTG'}, frame='1', transl_table=4, ctx=ctx)['a'] == ['XXWMVLL']
+    assert seqcodec.transeq({}, frame='7', ctx=ctx) == {}
