@@ -129,3 +129,53 @@ def test_long_protein_s32_wavefront(ctx, oracle):
     qs = [big, mut[:3200], big[100:3000]]
     ts = [mut, big, np.concatenate([rng.integers(0, 20, 50).astype(np.uint8), big])]
     out, _ = _compare(ctx, oracle, qs, ts, seqcodec.protein_params(), _prot_mat_with_pad(), 11, 1)
+
+
+def test_pipelined_chunks_with_pinned_outputs(ctx, oracle, monkeypatch):
+    # pb_sw_batch cuts large batches into chunks (upload of chunk c+1 under the kernels of chunk c) and, for page-locked
+    # outputs, copies results out asynchronously; a tiny chunk size forces that path on a batch the oracle can check
+    monkeypatch.setenv('PB_SW_CHUNK', '512')
+    qs, ts = workloads.random_pairs(3000, seed=41, max_len=200)
+    q, qoff = sw.concat(qs); t, toff = sw.concat(ts)
+    res = {k: ctx.pinned_empty((len(qs),), np.int32) for k in ('score', 'qs', 'qe', 'ts', 'te')}
+    for k in res:
+        res[k][:] = -7
+    out, st = sw.sw_batch(ctx, q, qoff, t, toff, seqcodec.protein_params(), out=res)
+    ref, _ = oracle.sw_batch(q, qoff, t, toff, _prot_mat_with_pad(), 11, 1, with_cigar=False, nthreads=8)
+    for k in ('score', 'qe', 'te', 'qs', 'ts'):
+        assert np.array_equal(out[k], ref[k]), k
+    assert st['kernel_launches'] >= 5 * 4            # several chunks, each with its own launches
+    out2, _ = sw.sw_batch(ctx, q, qoff, t, toff, seqcodec.protein_params())      # pageable outputs, same chunks
+    for k in ('score', 'qe', 'te', 'qs', 'ts'):
+        assert np.array_equal(out2[k], ref[k]), k
+
+
+def test_config2_full_size_properties(ctx, oracle):
+    # BASELINE.json configs[1] at full size (1,000,000 pairs x 300 x 300): properties that do not need the oracle on
+    # every pair, plus the oracle on a strided sample of the same batch
+    n = 1000000
+    q, qoff, t, toff = workloads.sw_microbench_pairs(n)
+    prm = seqcodec.protein_params()
+    out, st = sw.sw_batch(ctx, q, qoff, t, toff, prm)
+    assert st['cells'] == float(n) * 300 * 300
+    s = out['score']
+    assert (s > 0).all()
+    for a, b in (('qs', 'qe'), ('ts', 'te')):
+        assert (out[a] >= 0).all() and (out[a] <= out[b]).all() and (out[b] < 300).all()
+    # local alignment score is symmetric in its arguments (BLOSUM62 is symmetric): swap query and target
+    swp, _ = sw.sw_batch(ctx, t, toff, q, qoff, prm, coords=False)
+    assert np.array_equal(swp['score'], s)
+    # a pair's score never exceeds the self-score of either sequence, and related pairs (even) beat unrelated ones (odd)
+    diag = np.diag(seqcodec.BLOSUM62)[:20].astype(np.int64)
+    selfq = diag[q.reshape(n, 300)].sum(1); selft = diag[t.reshape(n, 300)].sum(1)
+    assert (s <= np.minimum(selfq, selft)).all()
+    assert np.median(s[0::2]) > 4 * np.median(s[1::2])
+    # deterministic: the checksum the bench prints for this seed
+    assert int(s.astype(np.int64).sum()) == 539403904
+    # oracle on every 977th pair
+    idx = np.arange(0, n, 977)
+    qq = q.reshape(n, 300)[idx].reshape(-1); tt = t.reshape(n, 300)[idx].reshape(-1)
+    off = np.arange(len(idx) + 1, dtype=np.int64) * 300
+    ref, _ = oracle.sw_batch(qq, off, tt, off, _prot_mat_with_pad(), 11, 1, with_cigar=False, nthreads=8)
+    for k in ('score', 'qe', 'te', 'qs', 'ts'):
+        assert np.array_equal(out[k][idx], ref[k]), k
