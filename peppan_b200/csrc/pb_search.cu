@@ -43,7 +43,7 @@ struct SeedSpec {
 };
 
 struct DevSpec {
-    int k, base, xdrop, min_ungapped;
+    int k, base, xdrop, min_ungapped, lane_budget;
     uint8_t seedmap[32];
     int8_t score[1024];
 };
@@ -217,10 +217,9 @@ __global__ void build_ends_kernel(const uint32_t* keys, int64_t nvalid, const ui
 // consecutive positions, rolls the k-mer key across them and looks the table up (phase 1).  The (position, slot range)
 // pairs are then expanded densely over the block with a prefix sum (phase 2): every lane takes one seed, so lanes stay
 // busy however unevenly the seeds are spread over the positions.  A seed is extended by its lane for at most
-// T1 residues per side, which settles the random seeds; seeds that are still alive go to a queue that
+// lane_budget residues per side, which settles the random seeds; seeds that are still alive go to a queue that
 // xdrop_warp_kernel extends with one warp per seed, 32 residues per step (prefix sums and prefix maxima by shuffles).
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
-constexpr int T1 = 16;
 
 struct SeedQ { uint32_t qpos, tpos; };
 
@@ -308,6 +307,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) seed_scan_kernel(const uint8_t* 
             for (int i = 0; i < sp.k; ++i) score += sscore[qcodes[qpos + i] * 32 + tile[pos + i]];
             int best = score, cur = score, rlen = sp.k;
             bool open = true;                        // extension still running when the lane's budget ended
+            const int T1 = sp.lane_budget;
             for (int x = sp.k; x < sp.k + T1; ++x) {
                 if (qpos + x >= qn || tpos + x >= tn) { open = false; break; }
                 uint8_t a = qcodes[qpos + x], b = tcodes[tpos + x];
@@ -695,6 +695,9 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     pb_score_params sp; memset(&sp, 0, sizeof(sp));
     DevSpec ds; memset(&ds, 0, sizeof(ds));
     ds.k = spec.k; ds.base = spec.base; ds.xdrop = spec.xdrop; ds.min_ungapped = spec.min_ungapped;
+    // residues per side a lane extends before handing the seed to the warp-per-seed kernel: long enough for random seeds to
+    // die (expected drift -1.75 / base against X-drop 20 for nucleotides, about -1 / residue against 12 for proteins)
+    ds.lane_budget = nt ? 40 : 32;
     memcpy(ds.seedmap, spec.seedmap, 32);
     if (nt) {
         sp.nsym = 6; sp.gap_open = 6; sp.gap_extend = 2;
@@ -826,6 +829,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         if (attempt == 3) { pb_set_error(ctx, "pb_search: candidate buffer overflow"); return PB_ERR_LIMIT; }
     }
     if (cnts[1] > 0x7fffffffull) { pb_set_error(ctx, "pb_search: too many ungapped HSPs in one call; block the input"); return PB_ERR_LIMIT; }
+    if (getenv("PB_DEBUG_TIMING")) fprintf(stderr, "[pb_search] seeds %llu, ungapped HSPs %llu, seeds handed to the warp kernel %llu, capacity %llu\n", cnts[2], cnts[1], cnts[3], cap);
     const int nh = (int)cnts[1];
     st.n_seed_hits = (int64_t)cnts[2]; st.n_ungapped = nh;
     st.algo_bytes_seed = LT + 9 * LQ + 16 * (int64_t)cnts[2];

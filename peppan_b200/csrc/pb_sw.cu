@@ -14,7 +14,11 @@ namespace {
 
 constexpr int PAD_SCORE = -16;
 constexpr int WAVE_G = 32, WAVE_K = 8, WAVE_R = 2, WAVE_W = WAVE_G * WAVE_K, WAVE_WARPS = 8;   // thin strips: latency of one long pair matters, not throughput
-constexpr int LONG_COLS = 2431, LONG_ROWS = 1024;      // pairs beyond this shape use the wavefront kernel
+// Pairs beyond (cols, rows) use the wavefront kernel.  In a big batch only the very long ones do (the regular kernel is the
+// efficient one and its tail is amortised); in a small batch -- fewer pairs than a few per 16-lane group of the machine, e.g.
+// the windows of one genome -- every group holds about one task, the launch lasts as long as its largest task, and
+// mid-size pairs are worth spreading over warps as well.
+constexpr int LONG_COLS = 2431, LONG_ROWS = 1024, MID_COLS = 1216, MID_ROWS = 768;
 
 SwConfig sw_pick_config()
 {
@@ -34,7 +38,7 @@ SwConfig sw_pick_config()
 // [19:0] query length; longest work first so the dynamic scheduler packs well, and neighbours in
 // the sorted order (which share a task / a warp) have similar shapes.
 __global__ void make_desc_fwd(const int64_t* qbeg, const int64_t* qend, const int64_t* tbeg, const int64_t* tend, int n, int maxscore, int SW_W,
-                              PairDesc* desc, uint32_t* keys, int* ids, int* meta /*[0]=n32,[1]=maxm,[2]=maxnb*/)
+                              int long_cols, int long_rows, PairDesc* desc, uint32_t* keys, int* ids, int* meta /*[0]=n32,[1]=maxm,[2]=maxnb*/)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -46,7 +50,7 @@ __global__ void make_desc_fwd(const int64_t* qbeg, const int64_t* qend, const in
     int s32 = bound > 32000 ? 1 : 0;
     int nb = (int)((nn + SW_W - 1) / SW_W);
     if (m <= 0 || nn <= 0) { nb = 0; s32 = 0; }
-    const int lng = (nn > LONG_COLS && m > LONG_ROWS && nn < (1 << 20) && m < (1 << 20)) ? 1 : 0;   // long alignments go to the wavefront kernel
+    const int lng = (nn > long_cols && m > long_rows && nn < (1 << 20) && m < (1 << 20)) ? 1 : 0;   // long alignments go to the wavefront kernel
     d.flags = s32 | (lng << 1);
     desc[p] = d;
     keys[p] = ((uint32_t)s32 << 31) | ((uint32_t)lng << 30) | ((uint32_t)min(nb, 1023) << 20) | (uint32_t)min((long long)0xfffff, m);
@@ -60,7 +64,7 @@ __global__ void make_desc_fwd(const int64_t* qbeg, const int64_t* qend, const in
 // key: [31] s32, [30:16] column blocks, [15:0] score (alignment length grows with the score, so
 // neighbours terminate their early-exit reverse sweep at similar rows).
 __global__ void make_desc_rev(const PairDesc* fwd, const int* score, const int* qe, const int* te, int n, int SW_W,
-                              PairDesc* desc, uint32_t* keys, int* ids, int* meta)
+                              int long_cols, int long_rows, PairDesc* desc, uint32_t* keys, int* ids, int* meta)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -70,7 +74,7 @@ __global__ void make_desc_rev(const PairDesc* fwd, const int* score, const int* 
     else { d.m = 0; d.n = 0; d.target = 0; }
     int nb = (d.n + SW_W - 1) / SW_W;
     const int s32 = d.flags & 1;
-    const int lng = (d.n > LONG_COLS && d.m > LONG_ROWS && d.n < (1 << 20) && d.m < (1 << 20)) ? 1 : 0;
+    const int lng = (d.n > long_cols && d.m > long_rows && d.n < (1 << 20) && d.m < (1 << 20)) ? 1 : 0;
     d.flags = s32 | (lng << 1);
     desc[p] = d;
     keys[p] = ((uint32_t)s32 << 31) | ((uint32_t)lng << 30) | ((uint32_t)min(nb, 16383) << 16) | (uint32_t)min(S, 65535);
@@ -427,7 +431,9 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
         PB_CUDA(ctx, cudaMemsetAsync(J->meta.p, 0, 32, ctx->stream));
         const int64_t* qb = J->qoff.as<int64_t>(); const int64_t* tbp = J->toff.as<int64_t>();
         const int64_t* qe_ = J->views ? J->qend.as<int64_t>() : qb + 1; const int64_t* te_ = J->views ? J->tend.as<int64_t>() : tbp + 1;
-        make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(qb, qe_, tbp, te_, n, J->maxscore, J->cfg.G * J->cfg.K,
+        const bool small_batch = n < 32 * ctx->sm_count * 16;
+        const int long_cols = small_batch ? MID_COLS : LONG_COLS, long_rows = small_batch ? MID_ROWS : LONG_ROWS;
+        make_desc_fwd<<<gb, tb, 0, ctx->stream>>>(qb, qe_, tbp, te_, n, J->maxscore, J->cfg.G * J->cfg.K, long_cols, long_rows,
                                                   J->desc.as<PairDesc>(), J->keys.as<uint32_t>(), J->ids.as<int>(), J->meta.as<int>());
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         size_t tmp = J->cub_bytes;
@@ -442,7 +448,7 @@ extern "C" int pb_sw_job_run(pb_ctx* ctx, pb_sw_job* J, pb_sw_stats* stats)
             fill_int<<<gb, tb, 0, ctx->stream>>>(J->qs.as<int>(), -1, n);
             fill_int<<<gb, tb, 0, ctx->stream>>>(J->ts.as<int>(), -1, n);
             launches += 2;
-            make_desc_rev<<<gb, tb, 0, ctx->stream>>>(J->desc.as<PairDesc>(), J->score.as<int>(), J->qe.as<int>(), J->te.as<int>(), n, J->cfg.G * J->cfg.K,
+            make_desc_rev<<<gb, tb, 0, ctx->stream>>>(J->desc.as<PairDesc>(), J->score.as<int>(), J->qe.as<int>(), J->te.as<int>(), n, J->cfg.G * J->cfg.K, long_cols, long_rows,
                                                       J->desc_rev.as<PairDesc>(), J->keys.as<uint32_t>(), J->ids.as<int>(), J->meta.as<int>());
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
             tmp = J->cub_bytes;

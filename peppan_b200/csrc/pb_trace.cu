@@ -27,10 +27,10 @@ using namespace pbsw;
 
 namespace {
 
-constexpr int TR_G = 16, TR_K = 16, TR_WARPS = 8;
+constexpr int TR_G = 16, TR_K = 16, TR_R = 2, TR_WARPS = 8;     // R rows per step, interleaved one column apart (ILP, as in the score kernel)
 constexpr int TR_W = TR_G * TR_K;
 constexpr int TR_KW8 = TR_K / 8;        // direction words per lane per step
-constexpr int TRW_G = 32, TRW_K = 8, TRW_W = TRW_G * TRW_K;   // wavefront variant: whole warps, thin strips (256 columns per block)
+constexpr int TRW_G = 32, TRW_K = 8, TRW_R = 2, TRW_W = TRW_G * TRW_K;   // wavefront variant: whole warps, thin strips (256 columns per block)
 constexpr int WAVE_MIN_COLS = 4 * TR_W + 1, WAVE_MIN_ROWS = 768;   // boxes at least this large are pipelined across warps
 
 struct TraceDesc {
@@ -46,8 +46,8 @@ struct TraceDesc {
 inline bool is_wave(int M, int N) { return N >= WAVE_MIN_COLS && M >= WAVE_MIN_ROWS; }
 inline size_t dir_words(int M, int N, bool wave)
 {
-    const int G = wave ? TRW_G : TR_G, K = wave ? TRW_K : TR_K, W = G * K;
-    return (size_t)((N + W - 1) / W) * (size_t)(M + G - 1) * G * (K / 8);
+    const int G = wave ? TRW_G : TR_G, K = wave ? TRW_K : TR_K, R = wave ? TRW_R : TR_R, W = G * K;
+    return (size_t)((N + W - 1) / W) * (size_t)((M + R - 1) / R + G - 1) * G * R * (K / 8);
 }
 
 struct TraceArgs {
@@ -66,10 +66,11 @@ struct TraceArgs {
     int nsub;
 };
 
-template <int G, int K, int WARPS, bool WAVE>
-__global__ void __launch_bounds__(WARPS * 32, 2) sw_trace_kernel(const TraceArgs a)
+template <int G, int K, int R, int WARPS, int MINB, bool WAVE>
+__global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceArgs a)
 {
     static_assert(!WAVE || G == 32, "the wavefront variant uses whole warps");
+    static_assert(32 % R == 0, "border batches hold whole steps");
     constexpr int KW = (K + 3) / 4, KP = KW * 4, NG = 32 / G, W = G * K, KW8 = K / 8;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) sw_trace_kernel(const TraceArgs
             nw = max(nw, __shfl_xor_sync(FULL, nw, o));
         }
         const int nblocks = (nw + W - 1) / W;
-        const int nsteps_own = M + G - 1;
+        const int nsteps_own = (M + R - 1) / R + G - 1;
 
         for (int b = WAVE ? wblock : 0; b < (WAVE ? wblock + 1 : nblocks); ++b) {
             const int col0 = b * W + l * K;
@@ -132,79 +133,117 @@ __global__ void __launch_bounds__(WARPS * 32, 2) sw_trace_kernel(const TraceArgs
                 }
             }
             __syncwarp();
-            int H[K], E[K];     // E holds E + goe, as in the score kernel
+            int H[K], E[K];     // last finished row of the strip; E holds E + goe, as in the score kernel
 #pragma unroll
             for (int p = 0; p < K; ++p) { H[p] = 0; E[p] = 0; }
-            int hlast = 0, fout = 0, hl_prev = 0;
-            const int slimit = mw + G - 1;
+            int hlast[R], fout[R], hl_prev = 0;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) { hlast[rr] = 0; fout[rr] = 0; }
+            const int slimit = (mw + R - 1) / R + G - 1;
             const bool in_block = (b * W < N);       // this pair has real columns in this block
-            uint32_t* dbase = a.dir + doff + (size_t)b * nsteps_own * G * KW8;
-            int i0 = -l;
-            int cq = ((unsigned)i0 < (unsigned)M) ? (int)__ldg(qb + (M - 1 - i0)) : PAD;
+            uint32_t* dbase = a.dir + doff + (size_t)b * nsteps_own * G * R * KW8;
+            int cq[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) { const int i0 = -l * R + rr; cq[rr] = ((unsigned)i0 < (unsigned)M) ? (int)__ldg(qb + (M - 1 - i0)) : PAD; }
             if (WAVE) mybound = wavebound + (size_t)b * a.bstride;
             const uint2* leftbound = WAVE ? (b > 0 ? wavebound + (size_t)(b - 1) * a.bstride : nullptr) : mybound;
             int published = 0;                  // WAVE: rows of the left border known to be complete
             int bat0 = -32;                     // WAVE: first row of the border batch held in `bat`
             uint2 bat = make_uint2(0u, 0u);
             for (int s = 0; s < slimit; ++s) {
-                const int i = s - l;
-                uint32_t w[KW];
-                const uint32_t* r = reinterpret_cast<const uint32_t*>(prof + cq * rowBytes + l * KP);
+                const int r0 = (s - l) * R;
+                uint32_t w[R][KW];
 #pragma unroll
-                for (int x = 0; x < KW; ++x) w[x] = r[x];
-                { int in = i + 1; cq = ((unsigned)in < (unsigned)M) ? (int)__ldg(qb + (M - 1 - in)) : PAD; }
-                int hl = __shfl_up_sync(FULL, hlast, 1, G), fh = __shfl_up_sync(FULL, fout, 1, G);
-                if (l == 0) { hl = 0; fh = 0; }
+                for (int rr = 0; rr < R; ++rr) {
+                    const uint32_t* r = reinterpret_cast<const uint32_t*>(prof + cq[rr] * rowBytes + l * KP);
+#pragma unroll
+                    for (int x = 0; x < KW; ++x) w[rr][x] = r[x];
+                }
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) { const int in = r0 + R + rr; cq[rr] = ((unsigned)in < (unsigned)M) ? (int)__ldg(qb + (M - 1 - in)) : PAD; }
+                int hl[R], fh[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    hl[rr] = __shfl_up_sync(FULL, hlast[rr], 1, G); fh[rr] = __shfl_up_sync(FULL, fout[rr], 1, G);
+                    if (l == 0) { hl[rr] = 0; fh[rr] = 0; }
+                }
                 if (WAVE) {
                     // border cells of block b-1 in coalesced batches of 32 rows (lane j holds row bat0 + j); the warp stays
                     // >= 32 rows behind the owner of block b-1, so a batch is complete when it is needed
-                    if (b > 0 && s < mw) {                 // s = row of lane 0 (warp-uniform)
-                        if (s >= bat0 + 32) {
-                            const int want = min(s + 32, mw);
+                    const int row0 = s * R;                // rows of lane 0 in this step (warp-uniform)
+                    if (b > 0 && row0 < mw) {
+                        if (row0 >= bat0 + 32) {
+                            const int want = min(row0 + 32, mw);
                             while (published < want) {
                                 published = ld_acquire(waveprog + (b - 1));
                                 if (published < want) __nanosleep(100);
                             }
-                            bat0 = s;
+                            bat0 = row0;
                             bat = (bat0 + lane < mw) ? ld_volatile_u2(leftbound + bat0 + lane) : make_uint2(0u, 0u);
                         }
-                        const uint32_t vx = __shfl_sync(FULL, bat.x, s - bat0), vy = __shfl_sync(FULL, bat.y, s - bat0);
-                        if (l == 0) { hl = (int)vx; fh = (int)vy; }
-                    }
-                } else if (l == 0 && b > 0 && (unsigned)i < (unsigned)mw) { uint2 v = leftbound[i]; hl = (int)v.x; fh = (int)v.y; }
-                int hdiag = hl_prev; hl_prev = hl;
-                int hleft = hl;
-                uint32_t codes[KW8];
 #pragma unroll
-                for (int x = 0; x < KW8; ++x) codes[x] = 0;
+                        for (int rr = 0; rr < R; ++rr) {
+                            const uint32_t vx = __shfl_sync(FULL, bat.x, row0 + rr - bat0), vy = __shfl_sync(FULL, bat.y, row0 + rr - bat0);
+                            if (l == 0 && row0 + rr < mw) { hl[rr] = (int)vx; fh[rr] = (int)vy; }
+                        }
+                    }
+                } else if (l == 0 && b > 0) {
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr)
+                        if ((unsigned)(r0 + rr) < (unsigned)mw) { uint2 v = leftbound[r0 + rr]; hl[rr] = (int)v.x; fh[rr] = (int)v.y; }
+                }
+                // diagonal / left neighbours of column 0: row rr takes its diagonal from the left lane's row rr-1
+                int hdiag[R], hleft[R];
+                hdiag[0] = hl_prev;
+#pragma unroll
+                for (int rr = 1; rr < R; ++rr) hdiag[rr] = hl[rr - 1];
+                hl_prev = hl[R - 1];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) hleft[rr] = hl[rr];
+                uint32_t codes[R][KW8];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                    for (int x = 0; x < KW8; ++x) codes[rr][x] = 0;
 #pragma unroll
                 for (int p = 0; p < K; ++p) {
-                    const int sc = (int)(int8_t)((w[p >> 2] >> (8 * (p & 3))) & 0xff);
-                    const int hup = H[p];
-                    // F + goe of this cell from the cell to the left; E + goe from the cell above
-                    const int fext = fh - ge;
-                    const int fopen = (hleft >= fext);            // tie -> opened here
-                    fh = max(fext, hleft);
-                    const int eext = E[p] - ge;
-                    const int eopen = (hup >= eext);
-                    const int eh = max(eext, hup);
-                    E[p] = eh;
-                    const int d = hdiag + sc, et = eh - goe, ft = fh - goe;
-                    const int hn = max(max(0, d), max(et, ft));
-                    int code = (hn == 0) ? 0 : ((hn == d) ? 1 : ((hn == et) ? 2 : 3));
-                    code |= (eopen << 2) | (fopen << 3);
-                    codes[p >> 3] |= (uint32_t)code << (4 * (p & 7));
-                    hdiag = hup; H[p] = hn; hleft = hn;
+                    int hup = H[p], eprev = E[p];
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const int sc = (int)(int8_t)((w[rr][p >> 2] >> (8 * (p & 3))) & 0xff);
+                        // F + goe of this cell from the cell to the left; E + goe from the cell above
+                        const int fext = fh[rr] - ge;
+                        const int fopen = (hleft[rr] >= fext);            // tie -> opened here
+                        fh[rr] = max(fext, hleft[rr]);
+                        const int eext = eprev - ge;
+                        const int eopen = (hup >= eext);
+                        const int eh = max(eext, hup);
+                        const int d = hdiag[rr] + sc, et = eh - goe, ft = fh[rr] - goe;
+                        const int hn = max(max(0, d), max(et, ft));
+                        int code = (hn == 0) ? 0 : ((hn == d) ? 1 : ((hn == et) ? 2 : 3));
+                        code |= (eopen << 2) | (fopen << 3);
+                        codes[rr][p >> 3] |= (uint32_t)code << (4 * (p & 7));
+                        hdiag[rr] = hup;          // diagonal of the next column in this row
+                        hleft[rr] = hn;
+                        hup = hn; eprev = eh;     // the row below sees this cell as "up"
+                    }
+                    H[p] = hup; E[p] = eprev;
                 }
-                hlast = hleft; fout = fh;
-                if (nblocks > 1 && l == G - 1 && b + 1 < nblocks && (unsigned)i < (unsigned)mw) {
-                    mybound[i] = make_uint2((uint32_t)hlast, (uint32_t)fout);
-                    if (WAVE && ((i & 15) == 15 || i + 1 >= mw)) st_release(waveprog + b, i + 1);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) { hlast[rr] = hleft[rr]; fout[rr] = fh[rr]; }
+                if (nblocks > 1 && l == G - 1 && b + 1 < nblocks) {
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr)
+                        if ((unsigned)(r0 + rr) < (unsigned)mw) mybound[r0 + rr] = make_uint2((uint32_t)hlast[rr], (uint32_t)fout[rr]);
+                    const int st = s - l;                  // step index of this lane's rows
+                    if (WAVE && r0 >= 0 && r0 < mw && ((st & 15) == 15 || r0 + R >= mw)) st_release(waveprog + b, min(r0 + R, mw));
                 }
                 if (in_block && s < nsteps_own) {
-                    uint32_t* dst = dbase + ((size_t)s * G + l) * KW8;
+                    uint32_t* dst = dbase + ((size_t)s * G + l) * R * KW8;
 #pragma unroll
-                    for (int x = 0; x < KW8; ++x) dst[x] = codes[x];
+                    for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                        for (int x = 0; x < KW8; ++x) dst[rr * KW8 + x] = codes[rr][x];
                 }
             }
             __syncwarp();
@@ -224,13 +263,14 @@ __global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDe
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (x >= count) return;
     const TraceDesc d = desc[x];
-    const int G = d.wave ? TRW_G : TR_G, K = d.wave ? TRW_K : TR_K, KW8 = K / 8, W = G * K;
+    const int G = d.wave ? TRW_G : TR_G, K = d.wave ? TRW_K : TR_K, R = d.wave ? TRW_R : TR_R, KW8 = K / 8, W = G * K;
     const uint8_t* qb = q + d.qoff; const uint8_t* tb = t + d.toff;
-    const int nsteps = d.M + G - 1;
+    const int nsteps = (d.M + R - 1) / R + G - 1;
     const uint32_t* base = dir + d.doff;
     auto fetch = [&](int ii, int jj) -> int {
         const int b = jj / W, jr = jj - b * W, l = jr / K, p = jr - l * K;
-        const uint32_t wv = base[((size_t)b * nsteps + (ii + l)) * G * KW8 + (size_t)l * KW8 + (p >> 3)];
+        const int st = ii / R + l, rr = ii - (ii / R) * R;
+        const uint32_t wv = base[((((size_t)b * nsteps + st) * G + l) * R + rr) * KW8 + (p >> 3)];
         return (int)((wv >> (4 * (p & 7))) & 15);
     };
     int i = d.M - 1, j = d.N - 1, state = 0;
@@ -311,8 +351,8 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     const size_t budget_words = (size_t)std::min<int64_t>(ctx->hbm_bytes / 8, (int64_t)12 << 30) / 4;
     const size_t smem = 1024 + (size_t)TR_WARPS * (32 / TR_G) * params->nsym * TR_G * (((TR_K + 3) / 4) * 4);
     const size_t smem_w = 1024 + (size_t)TR_WARPS * params->nsym * TRW_G * (((TRW_K + 3) / 4) * 4);
-    auto kern = sw_trace_kernel<TR_G, TR_K, TR_WARPS, false>;
-    auto kern_w = sw_trace_kernel<TRW_G, TRW_K, TR_WARPS, true>;
+    auto kern = sw_trace_kernel<TR_G, TR_K, TR_R, TR_WARPS, 2, false>;
+    auto kern_w = sw_trace_kernel<TRW_G, TRW_K, TRW_R, TR_WARPS, 2, true>;
     PB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PB_CUDA(ctx, cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     // persistent grids: every CTA resident at once (the wavefront variant spins on its left neighbour)
