@@ -20,6 +20,7 @@
 // box takes ~M + 32 * blocks steps instead of blocks * M.
 #include "pb_sw_job.h"
 #include <algorithm>
+#include <chrono>
 #include <vector>
 #include <memory>
 
@@ -30,7 +31,7 @@ namespace {
 constexpr int TR_G = 16, TR_K = 16, TR_R = 2, TR_WARPS = 8;     // R rows per step, interleaved one column apart (ILP, as in the score kernel)
 constexpr int TR_W = TR_G * TR_K;
 constexpr int TR_KW8 = TR_K / 8;        // direction words per lane per step
-constexpr int TRW_G = 32, TRW_K = 8, TRW_R = 2, TRW_W = TRW_G * TRW_K;   // wavefront variant: whole warps, thin strips (256 columns per block)
+constexpr int TRW_G = 32, TRW_K = 16, TRW_R = 2, TRW_W = TRW_G * TRW_K;   // wavefront variant: whole warps, thin strips (256 columns per block)
 constexpr int WAVE_MIN_COLS = 4 * TR_W + 1, WAVE_MIN_ROWS = 768;   // boxes at least this large are pipelined across warps
 
 struct TraceDesc {
@@ -210,19 +211,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceA
                     int hup = H[p], eprev = E[p];
 #pragma unroll
                     for (int rr = 0; rr < R; ++rr) {
-                        const int sc = (int)(int8_t)((w[rr][p >> 2] >> (8 * (p & 3))) & 0xff);
-                        // F + goe of this cell from the cell to the left; E + goe from the cell above
-                        const int fext = fh[rr] - ge;
-                        const int fopen = (hleft[rr] >= fext);            // tie -> opened here
-                        fh[rr] = max(fext, hleft[rr]);
-                        const int eext = eprev - ge;
-                        const int eopen = (hup >= eext);
-                        const int eh = max(eext, hup);
-                        const int d = hdiag[rr] + sc, et = eh - goe, ft = fh[rr] - goe;
-                        const int hn = max(max(0, d), max(et, ft));
-                        int code = (hn == 0) ? 0 : ((hn == d) ? 1 : ((hn == et) ? 2 : 3));
-                        code |= (eopen << 2) | (fopen << 3);
-                        codes[rr][p >> 3] |= (uint32_t)code << (4 * (p & 7));
+                        int sc;
+                        switch (p & 3) {                       // sign-extended byte p of the profile word: one PRMT
+                            case 0: sc = (int)prmt(w[rr][p >> 2], 0u, 0x8880u); break;
+                            case 1: sc = (int)prmt(w[rr][p >> 2], 0u, 0x9991u); break;
+                            case 2: sc = (int)prmt(w[rr][p >> 2], 0u, 0xaaa2u); break;
+                            default: sc = (int)prmt(w[rr][p >> 2], 0u, 0xbbb3u); break;
+                        }
+                        // F + goe of this cell from the cell to the left; E + goe from the cell above; a tie means "opened here"
+                        const int fnew = __viaddmax_s32(fh[rr], -ge, hleft[rr]);
+                        const bool fopen = (fnew == hleft[rr]);
+                        fh[rr] = fnew;
+                        const int eh = __viaddmax_s32(eprev, -ge, hup);
+                        const bool eopen = (eh == hup);
+                        const int mg = __vimax3_s32(eh, fnew, goe) - goe;     // max(0, E, F)
+                        const int d = hdiag[rr] + sc;
+                        const int hn = max(d, mg);
+                        // H source: stop (H == 0) > diagonal > E > F
+                        uint32_t code = (eh == hn + goe) ? 2u : 3u;
+                        code = (hn == d) ? 1u : code;
+                        code = (hn == 0) ? 0u : code;
+                        uint32_t cw = codes[rr][p >> 3] + (code << (4 * (p & 7)));
+                        if (eopen) cw |= 4u << (4 * (p & 7));
+                        if (fopen) cw |= 8u << (4 * (p & 7));
+                        codes[rr][p >> 3] = cw;
                         hdiag[rr] = hup;          // diagonal of the next column in this row
                         hleft[rr] = hn;
                         hup = hn; eprev = eh;     // the row below sees this cell as "up"
@@ -327,6 +339,10 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     const int64_t npairs = J->npairs;
     const pb_score_params* params = &J->params;
     *cigar_ops = nullptr;
+    const bool dbg = getenv("PB_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tm[8] = {0}; double t_last = now();
+    auto lap = [&](int k) { if (dbg) { cudaStreamSynchronize(ctx->stream); double t = now(); tm[k] += t - t_last; t_last = t; } };
     // ---- traceback over the aligned pairs, in chunks bounded by the direction-buffer budget ----
     std::vector<TraceDesc> all;
     all.reserve((size_t)npairs);
@@ -364,6 +380,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     int launches = 0;
     PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
 
+    lap(0);
     struct Chunk { size_t first, count, nwave; size_t words; int maxM; int maxNB; int waveM; size_t wslots; };
     std::vector<Chunk> chunks;
     {
@@ -398,6 +415,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         PB_CUDA(ctx, dcounts.alloc(c.count * 16, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(ddesc.p, all.data() + c.first, c.count * sizeof(TraceDesc), cudaMemcpyHostToDevice, ctx->stream));
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
+        lap(1);
         TraceArgs a;
         a.q = J->dq; a.t = J->dt; a.desc = ddesc.as<TraceDesc>(); a.count = (int)c.count;
         a.counter = ctx->d_counter; a.matrix = J->matrix.as<int8_t>(); a.nsym = params->nsym; a.go = params->gap_open; a.ge = params->gap_extend;
@@ -438,6 +456,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
         }
         if (c.nwave > 0) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[1], 0));
+        lap(2);
         const int tb = 128, gb = (int)((c.count * 32 + tb - 1) / tb);
         sw_walk_kernel<false><<<gb, tb, 0, ctx->stream>>>(a.q, a.t, a.desc, a.count, a.dir, dnops.as<int>(), dcounts.as<int>(), nullptr, nullptr);
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
@@ -445,6 +464,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         PB_CUDA(ctx, cudaMemcpyAsync(nops.data(), dnops.p, c.count * 4, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaMemcpyAsync(cnt.data(), dcounts.p, c.count * 16, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        lap(3);
         std::vector<long long>& ooff = chunk_ooff[ci];
         ooff.resize(c.count + 1);
         long long tot = 0;
@@ -463,6 +483,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         chunk_ops[ci].resize((size_t)tot);
         if (tot) PB_CUDA(ctx, cudaMemcpyAsync(chunk_ops[ci].data(), dops.p, (size_t)tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        lap(4);
     }
     PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     PB_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
@@ -482,6 +503,9 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
             if (n) memcpy(ops + cigar_off[id], chunk_ops[ci].data() + o, (size_t)n * 4);
         }
     }
+    lap(5);
+    if (dbg) fprintf(stderr, "[pb_sw_trace] desc+sort %.2f, alloc+upload %.2f, dp kernels %.2f, count walk+d2h %.2f, write walk+d2h %.2f, assemble %.2f ms (%zu chunks, %zu boxes)\n",
+                     tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], chunks.size(), all.size());
     *cigar_ops = ops;
     if (counts) memcpy(counts, h_counts.data(), (size_t)npairs * 16);
     if (ms_trace_out) *ms_trace_out = ms_trace;

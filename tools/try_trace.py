@@ -15,7 +15,7 @@ def mk(npairs, lo, hi, iden=0.92):
         t = np.concatenate([rng.integers(0, 4, 40).astype(np.uint8), t, rng.integers(0, 4, 40).astype(np.uint8)])
         qs.append(q); ts.append(t)
     return qs, ts
-for name, (n, lo, hi) in dict(one9k=(1, 9400, 9500), long20=(20, 5000, 9500), mid4000=(4000, 300, 2400), mix=(4500, 200, 2400)).items():
+for name, (n, lo, hi) in dict(one9k=(1, 9400, 9500), mid4000=(4000, 300, 2400), mix=(4500, 200, 2400), bulk=(20000, 500, 1000), bulk2k=(6000, 1500, 2400)).items():
     qs, ts = mk(n, lo, hi)
     if name == 'mix':
         q2, t2 = mk(25, 2500, 9500); qs += q2; ts += t2
