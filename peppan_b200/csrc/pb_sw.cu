@@ -13,7 +13,7 @@ using namespace pbsw;
 namespace {
 
 constexpr int PAD_SCORE = -16;
-constexpr int WAVE_G = 32, WAVE_K = 8, WAVE_R = 2, WAVE_W = WAVE_G * WAVE_K, WAVE_WARPS = 8;   // thin strips: latency of one long pair matters, not throughput
+constexpr int WAVE_G = 32, WAVE_K = 16, WAVE_R = 2, WAVE_W = WAVE_G * WAVE_K, WAVE_WARPS = 8;   // thin strips: latency of one long pair matters, not throughput
 // Pairs beyond (cols, rows) use the wavefront kernel.  In a big batch only the very long ones do (the regular kernel is the
 // efficient one and its tail is amortised); in a small batch -- fewer pairs than a few per 16-lane group of the machine, e.g.
 // the windows of one genome -- every group holds about one task, the launch lasts as long as its largest task, and
