@@ -219,6 +219,33 @@ def search_leg(ctx, rank, world, pg, steps, with_cpu):
     return out
 
 
+def cluster_leg(ctx, rank, world, pg, n_genomes=5):
+    """Third hot-path measurement: greedy representative clustering (getClust / pb_cluster) of the genes of `n_genomes`
+    synthetic genomes per GPU in priority (length) order, identity 0.9 / coverage 0.8 (iterClust's last rung)."""
+    from peppan_b200 import clust, seqio, workloads
+    pool = workloads.GenePool(3000, 12000)
+    comp = bytes.maketrans(b'ACGT', b'TGCA')
+    genes = []
+    for g in range(n_genomes):
+        seq, annot = workloads.synth_genome(pool, rank * n_genomes + g)
+        sb = seq.encode()
+        for (gid, a, b, strand, idn) in annot:
+            x = sb[a:b]
+            genes.append(x if strand > 0 else x.translate(comp)[::-1])
+    genes.sort(key=lambda x: -len(x))
+    names, buf, off = seqio.to_seqset([(str(i), s.decode()) for i, s in enumerate(genes)])
+    clust.cluster(ctx, buf, off, 0.9, 0.8)                      # warm-up
+    barrier(pg)
+    t0 = time.perf_counter()
+    rep, st = clust.cluster(ctx, buf, off, 0.9, 0.8)
+    barrier(pg)
+    wall = allmax(pg, time.perf_counter() - t0)
+    total = allsum(pg, float(len(genes)))
+    return {'workload': 'pb_cluster: %d genes (%d synthetic genomes) per GPU, priority order, identity 0.9, coverage 0.8' % (len(genes), n_genomes),
+            'genes_per_s': total / wall, 'seconds': wall, 'clusters': int(st['n_reps']), 'pairs_verified': int(st['n_pairs_verified']),
+            'sw_cells': float(st['sw_cells']), 'gcups': float(st['sw_cells']) / wall / 1e9, 'gpu_launches': int(st['kernel_launches'])}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -320,6 +347,10 @@ def main():
     if not args.no_search:
         srch = search_leg(ctx, rank, world, pg, max(1, min(args.steps, 3)), not args.no_cpu_baseline)
 
+    clu = None
+    if not args.no_search:
+        clu = cluster_leg(ctx, rank, world, pg)
+
     if rank != 0:
         return 0
     # roofline of the dominant kernel (forward s16x2 DP kernel): DPX issue peak, measured live
@@ -352,6 +383,7 @@ def main():
         'gpu_launches': launches,
         'clocks': clocks,
         'search': srch,
+        'cluster': clu,
     }
     print(json.dumps(line))
     ctx.close()
