@@ -200,6 +200,16 @@ int  pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov
 int  pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int translate, int gtable,
                    int32_t* rep_of, pb_cluster_stats* stats /* nullable */);
 
+/* reScore + cigar2score mode 1 (modules/uberBlast.py:397-415, :243-249) for a whole hit table at once, on the host (it is
+ * bookkeeping over the CIGARs, not a kernel; no context needed).  Sequences are the ASCII seqsets handed to pb_search;
+ * coordinates are 1-based inclusive, s_start > s_end = minus strand; cigar ops (len<<2)|{0:M,1:I,2:D} in nucleotide units
+ * at cigar[cigar_off[h] .. cigar_off[h+1]).  Bases are compared in the reference's nucEncoder classes (A, C, G, T, other;
+ * :270-271).  iden[h] = nMatch / (nMatch + nMismatch + gapBases - gapBases_of_gaps_longer_than_3), score[h] = 3 nMatch -
+ * nMismatch - 5 nGaps - gapBases, both unrounded.  Returns PB_ERR_ARG when a CIGAR runs past its sequence slice. */
+int  pb_rescore_m1(const pb_seqset* query, const pb_seqset* target, int64_t n_hits, const int32_t* q_id, const int32_t* s_id,
+                   const int32_t* q_start, const int32_t* q_end, const int32_t* s_start, const int32_t* s_end,
+                   const int64_t* cigar_off, const uint32_t* cigar, double* iden, double* score);
+
 /* transeq (modules/configure.py:160-194) on the device: for every sequence s and every requested frame
  * frames[k] (1..3 forward, 4..6 reverse complement) the amino-acid letters of its codons, index
  * b0<<4|b1<<2|b2 into the table of :167-170 (gtable 4: TGA -> W; mark_starts: GTG / TTG -> M, :171-172);

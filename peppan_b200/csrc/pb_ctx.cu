@@ -225,3 +225,44 @@ extern "C" int pb_allgather_hits(pb_ctx* ctx, pb_hits* io)
     io->hits = hits; io->n_hits = toth; io->cigar = cig; io->n_cigar = totc; io->rank_offsets = roff; io->n_ranks = W;
     return PB_OK;
 }
+
+// ---- host-side hit-table bookkeeping ---------------------------------------------------------------------------
+extern "C" int pb_rescore_m1(const pb_seqset* query, const pb_seqset* target, int64_t n_hits, const int32_t* q_id, const int32_t* s_id,
+                             const int32_t* q_start, const int32_t* q_end, const int32_t* s_start, const int32_t* s_end,
+                             const int64_t* cigar_off, const uint32_t* cigar, double* iden, double* score)
+{
+    if (n_hits < 0 || (n_hits > 0 && (!query || !target || !q_id || !s_id || !q_start || !q_end || !s_start || !s_end || !cigar_off || !iden || !score))) {
+        pb_set_error(nullptr, "pb_rescore_m1: invalid argument"); return PB_ERR_ARG;
+    }
+    // nucEncoder classes of modules/uberBlast.py:270-271: A0 C1 G3 T4, everything else 2, so that 4 - code is the complement
+    uint8_t enc[256];
+    for (int i = 0; i < 256; ++i) enc[i] = 2;
+    enc[(int)'A'] = 0; enc[(int)'C'] = 1; enc[(int)'G'] = 3; enc[(int)'T'] = 4;
+    for (int64_t h = 0; h < n_hits; ++h) {
+        if (q_id[h] < 0 || q_id[h] >= query->n || s_id[h] < 0 || s_id[h] >= target->n) { pb_set_error(nullptr, "pb_rescore_m1: hit %lld names an unknown sequence", (long long)h); return PB_ERR_ARG; }
+        const uint8_t* q = query->residues + query->offsets[q_id[h]];
+        const uint8_t* t = target->residues + target->offsets[s_id[h]];
+        const int64_t qlen = query->offsets[q_id[h] + 1] - query->offsets[q_id[h]], tlen = target->offsets[s_id[h] + 1] - target->offsets[s_id[h]];
+        const bool minus = s_start[h] > s_end[h];
+        const int64_t qa = q_start[h] - 1, qn = (int64_t)q_end[h] - qa;                       // query slice [qa, qa + qn)
+        const int64_t ta = (minus ? s_end[h] : s_start[h]) - 1, tn = (int64_t)(minus ? s_start[h] : s_end[h]) - ta;
+        if (qa < 0 || qa + qn > qlen || ta < 0 || ta + tn > tlen) { pb_set_error(nullptr, "pb_rescore_m1: hit %lld lies outside its sequences", (long long)h); return PB_ERR_ARG; }
+        int64_t qi = 0, ri = 0, nmatch = 0, ncol = 0, ngap = 0, bgap = 0, mgap = 0;
+        for (int64_t k = cigar_off[h]; k < cigar_off[h + 1]; ++k) {
+            const int64_t len = cigar[k] >> 2; const int op = cigar[k] & 3;
+            if (op == 0) {
+                if (qi + len > qn || ri + len > tn) { pb_set_error(nullptr, "pb_rescore_m1: CIGAR of hit %lld runs past its alignment slice", (long long)h); return PB_ERR_ARG; }
+                if (!minus) { for (int64_t x = 0; x < len; ++x) nmatch += enc[q[qa + qi + x]] == enc[t[ta + ri + x]]; }
+                else { for (int64_t x = 0; x < len; ++x) nmatch += enc[q[qa + qi + x]] == 4 - enc[t[ta + tn - 1 - (ri + x)]]; }
+                ncol += len; qi += len; ri += len;
+            } else {
+                ++ngap; bgap += len; if (len > 3) mgap += len;
+                if (op == 2) ri += len; else qi += len;
+            }
+        }
+        const int64_t nmis = ncol - nmatch;
+        iden[h] = (double)nmatch / (double)(nmatch + nmis + bgap - mgap);
+        score[h] = (double)(nmatch * 3 - nmis - (ngap * 5 + bgap));
+    }
+    return PB_OK;
+}

@@ -116,6 +116,44 @@ def rescore(rows, ref_enc, qry_enc, mode, min_id, table_id=11):
     return out
 
 
+_OPCODE = {'M': 0, 'I': 1, 'D': 2}
+
+
+def rescore_m1_table(rows, qry_set, ref_set, min_id):
+    """reScore with mode 1 for the whole table through the library (pb_rescore_m1: one pass in C over sequences and
+    CIGARs instead of numpy work per hit).  qry_set / ref_set: (names, ASCII uint8 buffer, int64 offsets) as handed to
+    pb_search.  Same result as rescore(rows, ..., mode=1): identity / score replaced, rounded half-to-even to 3 dp,
+    hits below min_id dropped."""
+    import ctypes as C
+    from ._lib import load, ptr
+    from .search import SeqSet
+    n = len(rows)
+    if n == 0:
+        return rows
+    (qn, qb, qo), (rn, rb, ro) = qry_set, ref_set
+    qidx = {str(k): i for i, k in enumerate(qn)}; ridx = {str(k): i for i, k in enumerate(rn)}
+    cols = np.array([(qidx[str(t[0])], ridx[str(t[1])], t[6], t[7], t[8], t[9]) for t in rows], dtype=np.int32)
+    coff = np.zeros(n + 1, dtype=np.int64)
+    coff[1:] = np.cumsum([len(t[14]) for t in rows])
+    ops = np.fromiter(((int(k) << 2) | _OPCODE[o] for t in rows for k, o in t[14]), dtype=np.uint32, count=int(coff[-1]))
+    c = [np.ascontiguousarray(cols[:, j]) for j in range(6)]
+    iden = np.zeros(n, dtype=np.float64); score = np.zeros(n, dtype=np.float64)
+    lib = load()
+    lib.pb_rescore_m1.argtypes = [C.POINTER(SeqSet), C.POINTER(SeqSet), C.c_int64] + [C.c_void_p] * 10
+    qs = SeqSet(qb.ctypes.data, qo.ctypes.data, len(qo) - 1); rs = SeqSet(rb.ctypes.data, ro.ctypes.data, len(ro) - 1)
+    rc = lib.pb_rescore_m1(C.byref(qs), C.byref(rs), n, ptr(c[0]), ptr(c[1]), ptr(c[2]), ptr(c[3]), ptr(c[4]), ptr(c[5]),
+                           ptr(coff), ptr(ops), ptr(iden), ptr(score))
+    if rc != 0:
+        raise RuntimeError('pb_rescore_m1 failed (%d): %s' % (rc, lib.pb_last_error(None).decode()))
+    iden = np.round(iden, 3); score = np.round(score, 3)
+    out = []
+    for t, i, s_ in zip(rows, iden.tolist(), score.tolist()):
+        t[2] = i; t[11] = s_
+        if i >= min_id:
+            out.append(t)
+    return out
+
+
 def _flip_minus(rows):
     for t in rows:
         if t[8] > t[9]:

@@ -56,10 +56,15 @@ class RunBlast(object):
         if not self.refSeq:
             self.refSeq = seqio.read_fastq(ref)
 
+    def _sets(self):
+        """(names, ASCII buffer, offsets) of queries and references, built once per run"""
+        if getattr(self, '_qset', None) is None:
+            self._qset = seqio.to_seqset(self.qrySeq); self._rset = seqio.to_seqset(self.refSeq)
+        return self._qset, self._rset
+
     def _search(self, mode):
         ctx = self.ctx or get_context()
-        qn, qb, qo = seqio.to_seqset(self.qrySeq)
-        rn, rb, ro = seqio.to_seqset(self.refSeq)
+        (qn, qb, qo), (rn, rb, ro) = self._sets()
         hits, cigar, st = _srch.search(ctx, qb, qo, rb, ro, mode, self.min_id, self.min_cov, self.min_ratio, self.table_id)
         self.stats.append(st)
         return qn, rn, hits, cigar
@@ -126,7 +131,13 @@ class RunBlast(object):
         rows = [list(r) for b in tabs for r in b]
         for i, r in enumerate(rows):
             r.append(i)
-        if re_score:
+        if re_score == 1:
+            # the mode PEPPAN uses: one pass over the table in the library (pb_rescore_m1)
+            if not self.qrySeq or not self.refSeq:
+                self._load(ref, qry)
+            qset, rset = self._sets()
+            rows = pf.rescore_m1_table(rows, qset, rset, min_id)
+        elif re_score:
             ref_enc = {k: pf.encode_nuc(v) for k, v in self.refSeq.items()}
             qry_enc = {k: pf.encode_nuc(v) for k, v in self.qrySeq.items()}
             rows = pf.rescore(rows, ref_enc, qry_enc, re_score, min_id, table_id)

@@ -61,3 +61,61 @@ def test_post_chain_matches_reference(scen):
         _same(rows, run['tab_out'], 'tab')
         if ovl is not None:
             _same(ovl.tolist(), run['overlap_out'], 'overlap')
+
+
+def test_rescore_m1_table_equals_cigar2score():
+    """pb_rescore_m1 (library, whole table) against the per-hit Python mirror pinned to the reference above"""
+    rng = np.random.default_rng(7)
+    nt = np.frombuffer(b'ACGTN', dtype=np.uint8)
+    contigs = {'c%d' % i: nt[rng.choice(5, 3000, p=[.24, .24, .24, .24, .04])].tobytes().decode() for i in range(3)}
+    genes, rows = {}, []
+    comp = str.maketrans('ACGTN', 'TGCAN')
+    for h in range(200):
+        cname = 'c%d' % rng.integers(3); ctg = contigs[cname]
+        # random alignment: M / I / D runs
+        cig, qlen, slen = [], 0, 0
+        for k in range(int(rng.integers(1, 8))):
+            n = int(rng.integers(1, 120)); cig.append([n, 'M']); qlen += n; slen += n
+            if rng.random() < 0.7:
+                g = int(rng.integers(1, 9)); op = 'I' if rng.random() < 0.5 else 'D'
+                cig.append([g, op]); qlen += g if op == 'I' else 0; slen += g if op == 'D' else 0
+        if cig[-1][1] != 'M':
+            cig.append([5, 'M']); qlen += 5; slen += 5
+        s0 = int(rng.integers(0, 3000 - slen)); minus = rng.random() < 0.5
+        sub = ctg[s0:s0 + slen]
+        if minus:
+            sub = sub.translate(comp)[::-1]
+        # query: the subject bases along the path with some substitutions
+        q, ri = [], 0
+        for n, op in cig:
+            if op == 'M':
+                seg = np.frombuffer(sub[ri:ri + n].encode(), dtype=np.uint8).copy()
+                m = rng.random(n) < 0.15; seg[m] = nt[rng.integers(0, 5, int(m.sum()))]
+                q.append(seg.tobytes().decode()); ri += n
+            elif op == 'D':
+                ri += n
+            else:
+                q.append(nt[rng.integers(0, 4, n)].tobytes().decode())
+        pre, post = int(rng.integers(0, 10)), int(rng.integers(0, 10))
+        gname = str(h)
+        genes[gname] = 'A' * pre + ''.join(q) + 'C' * post
+        ss, se = (s0 + 1, s0 + slen) if not minus else (s0 + slen, s0 + 1)
+        rows.append([gname, cname, 0.5, 0, 0, 0, pre + 1, pre + qlen, ss, se, 0.0, 1, len(genes[gname]), 3000, cig, h])
+    from peppan_b200 import seqio
+    want = pf.rescore(copy.deepcopy(rows), {k: pf.encode_nuc(v) for k, v in contigs.items()}, {k: pf.encode_nuc(v) for k, v in genes.items()}, 1, 0.8)
+    got = pf.rescore_m1_table(copy.deepcopy(rows), seqio.to_seqset(genes), seqio.to_seqset(contigs), 0.8)
+    assert 0 < len(want) < len(rows)
+    _same([list(t) for t in got], [list(t) for t in want])
+    assert all(type(t[2]) is float and type(t[11]) is float for t in got)
+    # the golden post-chain scenarios with re_score = 1 through the table path
+    for g in _load('post_chain'):
+        for run in g['runs']:
+            if run['opts']['re_score'] != 1:
+                continue
+            rows_in = copy.deepcopy(g['rows_in'])
+            for i, t in enumerate(rows_in):
+                t.append(i)
+            a = pf.rescore(copy.deepcopy(rows_in), {k: pf.encode_nuc(v) for k, v in g['contigs'].items()},
+                           {k: pf.encode_nuc(v) for k, v in g['genes'].items()}, 1, g['min_id'])
+            b = pf.rescore_m1_table(copy.deepcopy(rows_in), seqio.to_seqset(g['genes']), seqio.to_seqset(g['contigs']), g['min_id'])
+            _same([list(t) for t in b], [list(t) for t in a])
