@@ -13,4 +13,4 @@ uberBlast(args)
 t0 = time.time(); pr = cProfile.Profile(); pr.enable()
 tab, ovl = uberBlast(args)
 pr.disable(); print('uberBlast wall %.2f s, rows %d overlaps %d' % (time.time() - t0, len(tab), len(ovl)))
-pstats.Stats(pr).sort_stats('cumulative').print_stats(14)
+pstats.Stats(pr).sort_stats('cumulative').print_stats(30)
