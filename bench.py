@@ -102,6 +102,43 @@ def dist_setup(n_gpus):
     return rank, world, local, pg
 
 
+_ABANDONED = []
+
+
+def nccl_context(pg, local, rank, world, timeout_s=120.0):
+    """Context with an NCCL communicator, created under a watchdog: communicator set-up and a first (empty) hit-table
+    allgather run in a helper thread; if any rank has not finished after `timeout_s` every rank falls back to a context
+    without NCCL and the search leg reports the allgather as skipped, instead of the whole benchmark hanging."""
+    import ctypes as C
+    import torch
+    from peppan_b200 import search as _s
+    from peppan_b200._lib import Context, nccl_unique_id
+    obj = [nccl_unique_id() if rank == 0 else None]
+    pg.broadcast_object_list(obj, src=0)
+    box = {}
+
+    def work():
+        try:
+            c = Context(local, rank, world, obj[0])
+            _s.bind(c.lib)
+            h = _s.Hits()
+            c.check(c.lib.pb_allgather_hits(c.h, C.byref(h)), 'pb_allgather_hits')
+            c.lib.pb_free_hits(C.byref(h))
+            box['ctx'] = c
+        except Exception as e:          # reported below; the fallback context is created by the caller's thread
+            box['err'] = repr(e)
+
+    th = threading.Thread(target=work, daemon=True)
+    th.start(); th.join(timeout_s)
+    ok = torch.tensor([1.0 if 'ctx' in box else 0.0], dtype=torch.float64)
+    pg.all_reduce(ok, op=pg.ReduceOp.MIN)
+    if float(ok[0]) == 1.0:
+        return box['ctx'], None
+    _ABANDONED.append(box)      # keep a half-made communicator alive: destroying it could block as well
+    return Context(local), 'NCCL communicator / first allgather not ready on every rank after %.0f s (%s): hit tables not gathered' % (
+        timeout_s, box.get('err', 'timeout' if 'ctx' not in box else 'another rank'))
+
+
 def barrier(pg):
     if pg is not None:
         pg.barrier()
@@ -150,7 +187,7 @@ def search_world(n_core, n_acc, genome_index):
     return qb, qo, rb, ro, len(annot)
 
 
-def search_leg(ctx, rank, world, pg, steps, with_cpu):
+def search_leg(ctx, rank, world, pg, steps, with_cpu, gather=True):
     """Second hot-path measurement: the per-genome uberBlast search (BASELINE.json configs[2..3] unit of work): 15,000
     exemplar genes against one synthetic ~5 Mbp genome of 4,500 genes through pb_search with HOST buffers, nucleotide
     mode (runBlast) + protein-vs-6-frame mode (runDiamond); one genome per rank (independent units)."""
@@ -161,7 +198,7 @@ def search_leg(ctx, rank, world, pg, steps, with_cpu):
     modes = (('nt', search.MODE_NT), ('prot6', search.MODE_PROT6))
     for _ in range(2):
         for _, m in modes:
-            search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1)
+            search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1 and gather)
     barrier(pg)
     t0 = time.perf_counter()
     acc = {k: {} for k, _ in modes}
@@ -169,11 +206,11 @@ def search_leg(ctx, rank, world, pg, steps, with_cpu):
     for _ in range(steps):
         for k, m in modes:
             # N > 1: the per-rank hit tables are merged by one NCCL allgather (identical table on every rank)
-            hits, cig, st = search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1)
+            hits, cig, st = search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1 and gather)
             launches += st['kernel_launches']
             for f in ('ms_encode', 'ms_index', 'ms_seed', 'ms_sw', 'ms_trace', 'ms_total'):
                 acc[k][f] = acc[k].get(f, 0.0) + st[f] / steps
-            acc[k].update(hits=int(len(hits)), allgather='nccl' if world > 1 else None, windows=int(st['n_windows']), seed_hits=int(st['n_seed_hits']), sw_cells=float(st['sw_cells']),
+            acc[k].update(hits=int(len(hits)), allgather=('nccl' if gather else 'skipped') if world > 1 else None, windows=int(st['n_windows']), seed_hits=int(st['n_seed_hits']), sw_cells=float(st['sw_cells']),
                           algo_bytes_seed=int(st['algo_bytes_seed']))
     barrier(pg)
     wall = allmax(pg, time.perf_counter() - t0)
@@ -293,7 +330,7 @@ def main():
     from peppan_b200 import dist as pbd, seqcodec, sw, workloads
     from peppan_b200._lib import Context
     # N > 1: the context carries an NCCL communicator (unique id handed out over gloo) for the hit-table allgather
-    ctx = pbd.init_context_from_env(pg) if world > 1 else Context(local)
+    ctx, nccl_note = (Context(local), None) if world == 1 else nccl_context(pg, local, rank, world)
     info = ctx.device_info()
     params = seqcodec.protein_params()
     npairs = args.pairs
@@ -345,13 +382,17 @@ def main():
 
     srch = None
     if not args.no_search:
-        srch = search_leg(ctx, rank, world, pg, max(1, min(args.steps, 3)), not args.no_cpu_baseline)
+        srch = search_leg(ctx, rank, world, pg, max(1, min(args.steps, 3)), not args.no_cpu_baseline, gather=nccl_note is None)
+        if nccl_note:
+            srch['allgather_note'] = nccl_note
 
     clu = None
     if not args.no_search:
         clu = cluster_leg(ctx, rank, world, pg)
 
     if rank != 0:
+        if nccl_note is not None:
+            os._exit(0)        # a helper thread may still sit inside NCCL
         return 0
     # roofline of the dominant kernel (forward s16x2 DP kernel): DPX issue peak, measured live
     fwd_rate = ALGO_INSTR_PER_CELL * cells / (fwd_ms / args.steps * 1e-3)
@@ -385,8 +426,11 @@ def main():
         'search': srch,
         'cluster': clu,
     }
-    print(json.dumps(line))
-    ctx.close()
+    print(json.dumps(line), flush=True)
+    if nccl_note is None:
+        ctx.close()
+    else:
+        os._exit(0)            # a helper thread may still sit inside NCCL
     return 0
 
 
