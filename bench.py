@@ -102,43 +102,6 @@ def dist_setup(n_gpus):
     return rank, world, local, pg
 
 
-_ABANDONED = []
-
-
-def nccl_context(pg, local, rank, world, timeout_s=120.0):
-    """Context with an NCCL communicator, created under a watchdog: communicator set-up and a first (empty) hit-table
-    allgather run in a helper thread; if any rank has not finished after `timeout_s` every rank falls back to a context
-    without NCCL and the search leg reports the allgather as skipped, instead of the whole benchmark hanging."""
-    import ctypes as C
-    import torch
-    from peppan_b200 import search as _s
-    from peppan_b200._lib import Context, nccl_unique_id
-    obj = [nccl_unique_id() if rank == 0 else None]
-    pg.broadcast_object_list(obj, src=0)
-    box = {}
-
-    def work():
-        try:
-            c = Context(local, rank, world, obj[0])
-            _s.bind(c.lib)
-            h = _s.Hits()
-            c.check(c.lib.pb_allgather_hits(c.h, C.byref(h)), 'pb_allgather_hits')
-            c.lib.pb_free_hits(C.byref(h))
-            box['ctx'] = c
-        except Exception as e:          # reported below; the fallback context is created by the caller's thread
-            box['err'] = repr(e)
-
-    th = threading.Thread(target=work, daemon=True)
-    th.start(); th.join(timeout_s)
-    ok = torch.tensor([1.0 if 'ctx' in box else 0.0], dtype=torch.float64)
-    pg.all_reduce(ok, op=pg.ReduceOp.MIN)
-    if float(ok[0]) == 1.0:
-        return box['ctx'], None
-    _ABANDONED.append(box)      # keep a half-made communicator alive: destroying it could block as well
-    return Context(local), 'NCCL communicator / first allgather not ready on every rank after %.0f s (%s): hit tables not gathered' % (
-        timeout_s, box.get('err', 'timeout' if 'ctx' not in box else 'another rank'))
-
-
 def barrier(pg):
     if pg is not None:
         pg.barrier()
@@ -330,7 +293,7 @@ def main():
     from peppan_b200 import dist as pbd, seqcodec, sw, workloads
     from peppan_b200._lib import Context
     # N > 1: the context carries an NCCL communicator (unique id handed out over gloo) for the hit-table allgather
-    ctx, nccl_note = (Context(local), None) if world == 1 else nccl_context(pg, local, rank, world)
+    ctx, nccl_note = (Context(local), None) if world == 1 else pbd.init_context_watchdog(pg, local, rank, world)
     info = ctx.device_info()
     params = seqcodec.protein_params()
     npairs = args.pairs
