@@ -119,3 +119,18 @@ def test_rescore_m1_table_equals_cigar2score():
                            {k: pf.encode_nuc(v) for k, v in g['genes'].items()}, 1, g['min_id'])
             b = pf.rescore_m1_table(copy.deepcopy(rows_in), seqio.to_seqset(g['genes']), seqio.to_seqset(g['contigs']), g['min_id'])
             _same([list(t) for t in b], [list(t) for t in a])
+
+
+def test_rescore_m1_table_rejects_inconsistent_rows():
+    """a CIGAR that runs past its coordinate slice, or coordinates outside the sequence, are errors, not silent garbage"""
+    from peppan_b200 import seqio
+    genes = {'g': 'ACGTACGTACGTACGTACGT'}; contigs = {'c': 'TTACGTACGTACGTACGTACGTTT'}
+    good = ['g', 'c', 0.0, 0, 0, 0, 1, 20, 3, 22, 0.0, 0, 20, 24, [[20, 'M']], 0]
+    out = pf.rescore_m1_table([list(good)], seqio.to_seqset(genes), seqio.to_seqset(contigs), 0.5)
+    assert out[0][2] == 1.0 and out[0][11] == 60.0
+    for bad in (dict(cig=[[25, 'M']]), dict(send=30), dict(qend=40)):
+        row = list(good)
+        row[14] = bad.get('cig', row[14]); row[9] = bad.get('send', row[9]); row[7] = bad.get('qend', row[7])
+        with pytest.raises(RuntimeError):
+            pf.rescore_m1_table([row], seqio.to_seqset(genes), seqio.to_seqset(contigs), 0.5)
+    assert pf.rescore_m1_table([], seqio.to_seqset(genes), seqio.to_seqset(contigs), 0.5) == []
