@@ -210,6 +210,31 @@ int  pb_rescore_m1(const pb_seqset* query, const pb_seqset* target, int64_t n_hi
                    const int32_t* q_start, const int32_t* q_end, const int32_t* s_start, const int32_t* s_end,
                    const int64_t* cigar_off, const uint32_t* cigar, double* iden, double* score);
 
+/* The rest of RunBlast.run's post-search chain on a columnar hit table, on the host (sorts and short sweeps over a few
+ * thousand rows: bookkeeping, not a kernel): ovlFilter (modules/uberBlast.py:417-452), linearMerge / _linearMerge (:453-460,
+ * :100-218), fixEnd (:462-480), returnOverlap / tab2overlaps (:378-395, :73-97) and the final sort (:372), in that order.
+ * q_rank / s_rank: rank of the row's query / subject NAME in the order of the names as strings (equal names, equal ranks);
+ * iden / score: columns 2 and 11 (after reScore); coordinates 1-based inclusive, s_start > s_end = minus strand; hit_id:
+ * column 15; cigar as in pb_rescore_m1.  Coordinates and the first / last CIGAR op of a row are updated in place by fixEnd.
+ * Result (library-allocated, release with pb_free_post): row[k] = input row of output row k in final order; for linearMerge
+ * the merge group of output row k (column 16) is (grp_score[k], grp_iden[k], grp_len[k], grp_ids[grp_off[k] .. grp_off[k+1]));
+ * overlaps = n_overlaps x 3 (hit id 1, hit id 2, overlap). */
+typedef struct {
+    int32_t do_filter;  double filter_cov, filter_delta;
+    int32_t do_merge;   double merge_gap, merge_diff;
+    double  fix_start, fix_end;
+    int32_t do_overlap; double ovl_len, ovl_prop;
+} pb_post_params;
+typedef struct {
+    int64_t n_rows; int32_t* row;
+    int64_t* grp_off; int32_t* grp_ids; double* grp_score; double* grp_iden; int64_t* grp_len;
+    int64_t n_overlaps; int64_t* overlaps;
+} pb_post_result;
+int  pb_post_chain(int64_t n, const int32_t* q_rank, const int32_t* s_rank, const double* iden, const double* score,
+                   int32_t* q_start, int32_t* q_end, int32_t* s_start, int32_t* s_end, const int32_t* q_len, const int32_t* s_len,
+                   const int32_t* hit_id, const int64_t* cigar_off, uint32_t* cigar, const pb_post_params* prm, pb_post_result* out);
+void pb_free_post(pb_post_result* r);
+
 /* transeq (modules/configure.py:160-194) on the device: for every sequence s and every requested frame
  * frames[k] (1..3 forward, 4..6 reverse complement) the amino-acid letters of its codons, index
  * b0<<4|b1<<2|b2 into the table of :167-170 (gtable 4: TGA -> W; mark_starts: GTG / TTG -> M, :171-172);

@@ -154,6 +154,78 @@ def rescore_m1_table(rows, qry_set, ref_set, min_id):
     return out
 
 
+def post_chain_table(rows, filter_opt, merge_opt, fix_end_opt, overlap_opt):
+    """ovl_filter -> linear_merge -> fix_end -> overlaps -> final_sort for the whole table in one library call
+    (pb_post_chain, host C++).  `rows` as for the functions below (column 15 = hit id; identity / score already final);
+    options as RunBlast.run takes them: [on, cov, delta], [on, gap, diff], [start, end], [on, length, proportion].
+    Returns (rows in final order with the CIGAR rendered as a string and, with merging, column 16; overlap array or None)."""
+    import ctypes as C
+    from ._lib import load, ptr
+
+    class Params(C.Structure):
+        _fields_ = [('do_filter', C.c_int32), ('filter_cov', C.c_double), ('filter_delta', C.c_double),
+                    ('do_merge', C.c_int32), ('merge_gap', C.c_double), ('merge_diff', C.c_double),
+                    ('fix_start', C.c_double), ('fix_end', C.c_double),
+                    ('do_overlap', C.c_int32), ('ovl_len', C.c_double), ('ovl_prop', C.c_double)]
+
+    class Result(C.Structure):
+        _fields_ = [('n_rows', C.c_int64), ('row', C.POINTER(C.c_int32)), ('grp_off', C.POINTER(C.c_int64)), ('grp_ids', C.POINTER(C.c_int32)),
+                    ('grp_score', C.POINTER(C.c_double)), ('grp_iden', C.POINTER(C.c_double)), ('grp_len', C.POINTER(C.c_int64)),
+                    ('n_overlaps', C.c_int64), ('overlaps', C.POINTER(C.c_int64))]
+
+    n = len(rows)
+    qrank = {k: i for i, k in enumerate(sorted(set(str(t[0]) for t in rows)))}
+    srank = {k: i for i, k in enumerate(sorted(set(str(t[1]) for t in rows)))}
+    ints = np.array([(qrank[str(t[0])], srank[str(t[1])], t[6], t[7], t[8], t[9], t[12], t[13], t[15]) for t in rows], dtype=np.int32).reshape(n, 9)
+    col = [np.ascontiguousarray(ints[:, j]) for j in range(9)]
+    iden = np.array([t[2] for t in rows], dtype=np.float64); score = np.array([t[11] for t in rows], dtype=np.float64)
+    coff = np.zeros(n + 1, dtype=np.int64)
+    coff[1:] = np.cumsum([len(t[14]) for t in rows])
+    ops = np.fromiter(((int(k) << 2) | _OPCODE[o] for t in rows for k, o in t[14]), dtype=np.uint32, count=int(coff[-1]))
+    if ops.size == 0:
+        ops = np.zeros(1, dtype=np.uint32)
+    prm = Params(int(bool(filter_opt[0])), float(filter_opt[1]), float(filter_opt[2]), int(bool(merge_opt[0])), float(merge_opt[1]), float(merge_opt[2]),
+                 float(fix_end_opt[0]), float(fix_end_opt[1]), int(bool(overlap_opt[0])), float(overlap_opt[1]), float(overlap_opt[2]))
+    res = Result()
+    lib = load()
+    lib.pb_post_chain.argtypes = [C.c_int64] + [C.c_void_p] * 13 + [C.POINTER(Params), C.POINTER(Result)]
+    lib.pb_free_post.argtypes = [C.POINTER(Result)]
+    lib.pb_free_post.restype = None
+    rc = lib.pb_post_chain(n, ptr(col[0]), ptr(col[1]), ptr(iden), ptr(score), ptr(col[2]), ptr(col[3]), ptr(col[4]), ptr(col[5]),
+                           ptr(col[6]), ptr(col[7]), ptr(col[8]), ptr(coff), ptr(ops), C.byref(prm), C.byref(res))
+    if rc != 0:
+        raise RuntimeError('pb_post_chain failed (%d): %s' % (rc, lib.pb_last_error(None).decode()))
+    try:
+        m = res.n_rows
+        order = np.ctypeslib.as_array(res.row, shape=(max(m, 1),))[:m].tolist()
+        goff = np.ctypeslib.as_array(res.grp_off, shape=(m + 1,)).tolist()
+        gids = np.ctypeslib.as_array(res.grp_ids, shape=(max(goff[-1], 1),)).tolist()
+        gscore = np.ctypeslib.as_array(res.grp_score, shape=(max(m, 1),)).tolist()
+        giden = np.ctypeslib.as_array(res.grp_iden, shape=(max(m, 1),)).tolist()
+        glen = np.ctypeslib.as_array(res.grp_len, shape=(max(m, 1),)).tolist()
+        ovl = None
+        if overlap_opt[0]:
+            ovl = np.ctypeslib.as_array(res.overlaps, shape=(max(res.n_overlaps, 1) * 3,))[:res.n_overlaps * 3].copy().reshape(-1, 3)
+    finally:
+        lib.pb_free_post(C.byref(res))
+    qs, qe, ss, se = col[2].tolist(), col[3].tolist(), col[4].tolist(), col[5].tolist()
+    lens = (ops >> 2).tolist(); kinds = (ops & 3).tolist()
+    coff = coff.tolist()
+    out = []
+    for k, r in enumerate(order):
+        t = rows[r]
+        t[6], t[7], t[8], t[9] = qs[r], qe[r], ss[r], se[r]
+        t[14] = ''.join('%d%s' % (lens[x], 'MID'[kinds[x]]) for x in range(coff[r], coff[r + 1]))
+        if merge_opt[0]:
+            grp = [gscore[k], giden[k], glen[k]] + gids[goff[k]:goff[k + 1]] if goff[k + 1] > goff[k] else []
+            if len(t) > 16:
+                t[16] = grp
+            else:
+                t.append(grp)
+        out.append(t)
+    return out, ovl
+
+
 def _flip_minus(rows):
     for t in rows:
         if t[8] > t[9]:

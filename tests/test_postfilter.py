@@ -134,3 +134,113 @@ def test_rescore_m1_table_rejects_inconsistent_rows():
         with pytest.raises(RuntimeError):
             pf.rescore_m1_table([row], seqio.to_seqset(genes), seqio.to_seqset(contigs), 0.5)
     assert pf.rescore_m1_table([], seqio.to_seqset(genes), seqio.to_seqset(contigs), 0.5) == []
+
+
+def _python_chain(rows, o):
+    if o['filter'][0]:
+        rows = pf.ovl_filter(rows, o['filter'][1], o['filter'][2])
+    if o['linear_merge'][0]:
+        rows = pf.linear_merge(rows, o['linear_merge'][1], o['linear_merge'][2])
+    pf.fix_end(rows, o['fix_end'][0], o['fix_end'][1])
+    ovl = pf.overlaps(rows, o['return_overlap'][1], o['return_overlap'][2]) if o['return_overlap'][0] else None
+    return pf.final_sort(rows), ovl
+
+
+@pytest.mark.parametrize('scen', range(14))
+def test_library_post_chain_matches_reference_golden(scen):
+    """pb_post_chain (host C++, whole table) on the reference's golden scenarios"""
+    g = _load('post_chain')[scen]
+    ref_enc = {k: pf.encode_nuc(v) for k, v in g['contigs'].items()}
+    qry_enc = {k: pf.encode_nuc(v) for k, v in g['genes'].items()}
+    for run in g['runs']:
+        o = run['opts']
+        rows = copy.deepcopy(g['rows_in'])
+        for i, t in enumerate(rows):
+            t.append(i)
+        if o['re_score']:
+            rows = pf.rescore(rows, ref_enc, qry_enc, o['re_score'], g['min_id'])
+        rows, ovl = pf.post_chain_table(rows, o['filter'], o['linear_merge'], o['fix_end'], o['return_overlap'])
+        _same(rows, run['tab_out'], 'tab')
+        if o['return_overlap'][0]:
+            _same(ovl.tolist(), run['overlap_out'], 'overlap')
+
+
+def _random_table(rng, n_genes, n_contigs, n_rows):
+    """hits that overlap, nest, chain and sit at contig ends often enough to reach every branch of the chain"""
+    rows = []
+    clen = [int(rng.integers(3000, 9000)) for _ in range(n_contigs)]
+    glen = [int(rng.integers(150, 1500)) for _ in range(n_genes)]
+    anchors = [(int(rng.integers(n_contigs)), int(rng.integers(0, 2)), float(rng.random())) for _ in range(n_genes)]
+    for h in range(n_rows):
+        gi = int(rng.integers(n_genes)); L = glen[gi]
+        ci, minus, pos = anchors[gi] if rng.random() < 0.8 else (int(rng.integers(n_contigs)), int(rng.integers(0, 2)), float(rng.random()))
+        qa = int(rng.integers(1, max(2, L // 2))) if rng.random() < 0.6 else int(rng.integers(1, 8))
+        qb = int(rng.integers(qa + 30, L + 1)) if qa + 30 < L else L
+        span = qb - qa + 1
+        cig = [[span, 'M']]
+        sspan = span
+        if rng.random() < 0.4 and span > 40:
+            a = int(rng.integers(10, span - 10)); g_ = int(rng.integers(1, 12))
+            if rng.random() < 0.5:
+                cig = [[a, 'M'], [g_, 'D'], [span - a, 'M']]; sspan = span + g_
+            else:
+                cig = [[a, 'M'], [g_, 'I'], [span - a - g_, 'M']] if span - a - g_ > 0 else [[span, 'M']]
+                sspan = span - g_ if len(cig) == 3 else span
+        C_ = clen[ci]
+        base = int(pos * (C_ - 2 * L - 700)) + 300 if rng.random() < 0.85 else int(rng.integers(1, 40))
+        base = max(1, min(base, C_ - sspan - 1))
+        s0 = base + (qa if not minus else (L - qb)) + int(rng.integers(-3, 4)) * int(rng.random() < 0.3)
+        s0 = max(1, min(s0, C_ - sspan + 1))
+        ss, se = (s0, s0 + sspan - 1) if not minus else (s0 + sspan - 1, s0)
+        iden = round(float(rng.uniform(0.45, 1.0)), 3)
+        score = round(float(span * (4 * iden - 1) + rng.integers(-5, 6)), 3)
+        rows.append([str(100 + gi), 'ctg%d' % ci, iden, sum(k for k, _ in cig), 0, len(cig) // 2, qa, qb, ss, se, 1e-50, score, L, C_, cig, h])
+    return rows
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_library_post_chain_equals_python_mirror_on_random_tables(seed):
+    rng = np.random.default_rng(1000 + seed)
+    rows = _random_table(rng, n_genes=int(rng.integers(3, 25)), n_contigs=int(rng.integers(1, 4)), n_rows=int(rng.integers(5, 160)))
+    for o in (dict(filter=[True, 0.9, 0.], linear_merge=[True, 600., 1.5], fix_end=[0., 3.], return_overlap=[True, 300, 0.6]),
+              dict(filter=[False, 0.9, 0.], linear_merge=[False, 300., 1.2], fix_end=[3., 3.], return_overlap=[False, 300, 0.6]),
+              dict(filter=[True, 0.5, 10.], linear_merge=[True, 300., 1.2], fix_end=[6., 6.], return_overlap=[True, 100, 0.3]),
+              dict(filter=[False, 0.9, 0.], linear_merge=[True, 2000., 3.0], fix_end=[0., 0.], return_overlap=[True, 300, 0.6])):
+        want, wovl = _python_chain(copy.deepcopy(rows), o)
+        got, govl = pf.post_chain_table(copy.deepcopy(rows), o['filter'], o['linear_merge'], o['fix_end'], o['return_overlap'])
+        _same([list(t) for t in got], [list(t) for t in want], 'seed %d' % seed)
+        if o['return_overlap'][0]:
+            # with >= 32 hits of one query the Python code walks a set of row indices whose order is a CPython hash-table
+            # detail; it only permutes the rows of the overlap table (pb_post.cu header)
+            many = max(np.unique([t[0] for t in rows], return_counts=True)[1]) >= 32
+            assert (sorted(map(tuple, govl.tolist())) == sorted(map(tuple, wovl.tolist()))) if many else (govl.tolist() == wovl.tolist())
+        else:
+            assert govl is None
+
+
+@pytest.mark.parametrize('scen', range(14))
+def test_runblast_run_wiring_on_golden_scenarios(scen):
+    """RunBlast.run with the search tool replaced by the scenario's rows (as tests/golden/make_golden.py did with the
+    reference's own class): the whole host chain of the shim -- library re-scoring, library post-chain, object array --
+    must reproduce the reference's output table and overlap list."""
+    from peppan_b200.uberBlast import RunBlast
+    g = _load('post_chain')[scen]
+
+    class Fake(RunBlast):
+        def runBlast(self, ref, qry):
+            arr = np.empty([len(g['rows_in']), 15], dtype=object)
+            for i, r in enumerate(copy.deepcopy(g['rows_in'])):
+                for j in range(15):
+                    arr[i, j] = r[j]
+            return arr
+
+    for run in g['runs']:
+        o = run['opts']
+        rb = Fake()
+        rb.qrySeq = dict(g['genes']); rb.refSeq = dict(g['contigs'])
+        res = rb.run('unused_ref', 'unused_qry', ['blastn'], g['min_id'], g['min_cov'], g['min_ratio'], re_score=o['re_score'],
+                     filter=o['filter'], linear_merge=o['linear_merge'], return_overlap=o['return_overlap'], fix_end=o['fix_end'])
+        tab, ovl = res if o['return_overlap'][0] else (res, None)
+        _same([list(r) for r in tab], run['tab_out'], 'tab')
+        if ovl is not None:
+            _same(ovl.tolist(), run['overlap_out'], 'overlap')
