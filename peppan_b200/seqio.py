@@ -10,16 +10,21 @@ def _open(path):
     return gzip.open(path, 'rt') if str(path).lower().endswith('gz') else open(path)
 
 
-def read_fasta(path):
+def _read_fasta_lines(fin):
+    """readFasta (modules/configure.py:118-129), line by line (a whole-file split was tried and was slower)"""
     seqs, name = {}, None
-    with _open(path) as fin:
-        for line in fin:
-            if line.startswith('>'):
-                name = line[1:].strip().split()[0]
-                seqs[name] = []
-            elif len(line) > 0 and not line.startswith('#') and name is not None:
-                seqs[name].extend(line.strip().split())
+    for line in fin:
+        if line.startswith('>'):
+            name = line[1:].strip().split()[0]
+            seqs[name] = []
+        elif len(line) > 0 and not line.startswith('#') and name is not None:
+            seqs[name].extend(line.strip().split())
     return {n: ''.join(s).upper() for n, s in seqs.items()}
+
+
+def read_fasta(path):
+    with _open(path) as fin:
+        return _read_fasta_lines(fin)
 
 
 def read_fastq(path):
