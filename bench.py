@@ -90,6 +90,19 @@ def profiled_traffic():
         return None
 
 
+def hbm_view(algo_bytes, ms):
+    """the same kernel against the HBM roofline: algorithmic bytes per launch (sequences read once + 32-B descriptor +
+    three 4-B results per pair) / launch time, against the measured copy bandwidth of MEASURED_PEAKS.json"""
+    peak, src = 6545.6, 'fallback 6545.6 GB/s'
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']); src = 'MEASURED_PEAKS.json'
+    except Exception:
+        pass
+    gbs = algo_bytes / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'peak_source': src,
+            'note': 'far below 1: the kernel is bound by integer / DPX issue, not by HBM'}
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -378,6 +391,7 @@ def main():
                    'sm_count': info['sm_count']},
         'roofline': {'bound': 'int_dpx', 'kernel': 'sw_kernel<G16,K19,R2,long-chain,s16x2,forward>', 'achieved': fwd_rate / 1e12, 'peak': peak / 1e12,
                      'unit': 'T lane-instr/s', 'frac': fwd_rate / peak, 'traffic': profiled_traffic(),
+                     'hbm': hbm_view(float(npairs) * (600 + 32 + 12), fwd_ms / args.steps),
                      'note': 'achieved = 3.5 DPX instr/cell (SURVEY 8d) x cells / forward-kernel time; peak = live dependent-free '
                              'VIADDMNMX.S16x2 issue rate on all SMs (pb_measure_dpx_peak); traffic = dram bytes per forward launch from '
                              'profiles/r01_sw_kernel_ncu_full.txt (1M pairs): ~ the 0.6 GB of sequences, HBM is not the bound'},
