@@ -106,3 +106,45 @@ def test_greedy_cluster_contract(oracle):
     # 0 is a rep; 1 joins 0; 2 has an edge only to member 1 (not a rep) -> new rep; 3 joins earliest rep among {0,2}
     rep = oracle.greedy_cluster(4, [0, 1, 0, 2], [1, 2, 3, 3])
     assert rep.tolist() == [0, 0, 2, 0]
+
+
+def _gotoh_first_max(q, t, mat, go, ge):
+    """independent pure-Python Gotoh local DP (gap of length L costs go + L*ge): (max H, first cell in row-major order)"""
+    m, n = len(q), len(t)
+    NEG = -10 ** 9
+    Hp = [0] * (n + 1); Ep = [NEG] * (n + 1)
+    best, cell = 0, (-1, -1)
+    for i in range(1, m + 1):
+        Hc = [0] * (n + 1); Ec = [NEG] * (n + 1)
+        F = NEG
+        for j in range(1, n + 1):
+            Ec[j] = max(Ep[j] - ge, Hp[j] - go - ge)
+            F = max(F - ge, Hc[j - 1] - go - ge)
+            h = max(0, Hp[j - 1] + int(mat[q[i - 1], t[j - 1]]), Ec[j], F)
+            Hc[j] = h
+            if h > best:
+                best, cell = h, (i - 1, j - 1)
+        Hp, Ep = Hc, Ec
+    return best, cell
+
+
+def test_sw_oracle_equals_independent_dp(oracle):
+    """score, end cell (row-major-first maximum) and start cell (the same rule on the reversed prefixes)
+    of the C oracle against an independent pure-Python DP, protein and nucleotide scoring"""
+    for (mat, go, ge, nsym, seed) in ((seqcodec.protein_matrix(), 11, 1, 20, 3), (seqcodec.nt_matrix(), 6, 2, 4, 4)):
+        qs, ts = workloads.random_pairs(120, seed=seed, nsym_real=nsym, max_len=70, related=0.7)
+        q, qoff = oracle.concat(qs); t, toff = oracle.concat(ts)
+        aln, _ = oracle.sw_batch(q, qoff, t, toff, mat.reshape(-1), go, ge, with_cigar=False)
+        nz = 0
+        for p in range(len(qs)):
+            S, (qe, te) = _gotoh_first_max(qs[p], ts[p], mat, go, ge)
+            assert aln['score'][p] == S
+            if S == 0:
+                assert aln['qe'][p] == -1 and aln['qs'][p] == -1
+                continue
+            nz += 1
+            assert (aln['qe'][p], aln['te'][p]) == (qe, te)
+            # start: first row-major cell of the DP on the reversed prefixes that reaches S
+            S2, (ri, rj) = _gotoh_first_max(qs[p][:qe + 1][::-1], ts[p][:te + 1][::-1], mat, go, ge)
+            assert S2 == S and (aln['qs'][p], aln['ts'][p]) == (qe - ri, te - rj)
+        assert nz > 60
