@@ -1,0 +1,116 @@
+"""The uberBlast() shim end to end on the CPU: pb_search is replaced -- in this test only -- by the scalar search oracle
+(whose hit tables the GPU path reproduces bit for bit, tests/test_search_gpu.py), so the host side of the shim (row
+construction, library re-scoring and post-chain, object arrays, flags, output file) is exercised without a GPU and compared
+with an independent pass through the readable Python mirror of the same stages."""
+import copy
+import os
+import re
+
+import numpy as np
+import pytest
+
+from peppan_b200 import postfilter as pf
+from peppan_b200 import seqcodec, seqio, uberBlast as ub, workloads
+
+
+@pytest.fixture(scope='module')
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp('ubc')
+    pool = workloads.GenePool(50, 70, seed=workloads.SEED + 21)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=25, seed=workloads.SEED + 21)
+    qry = os.path.join(d, 'exemplar.fa'); ref = os.path.join(d, 'genome.fa')
+    with open(qry, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    with open(ref, 'w') as f:
+        f.write('>contig1 test\n')
+        for i in range(0, len(seq), 70):
+            f.write(seq[i:i + 70] + '\n')
+    return dict(qry=qry, ref=ref, pool=pool, annot=annot, glen=len(seq))
+
+
+@pytest.fixture()
+def oracle_search(monkeypatch, oracle):
+    calls = []
+
+    def fake_search(ctx, qb, qo, rb, ro, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
+        hits, cigar = oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov,
+                                    min_ratio=min_ratio, gtable=gtable, max_hits=max_hits)
+        calls.append(mode)
+        return hits, cigar, dict(kernel_launches=0)
+
+    monkeypatch.setattr(ub._srch, 'search', fake_search)
+    monkeypatch.setattr(ub, 'get_context', lambda: None)
+    return calls
+
+
+def _cigar_spans(c):
+    q = s = 0
+    for n, t in re.findall(r'(\d+)([MID])', c):
+        n = int(n)
+        if t in 'MI':
+            q += n
+        if t in 'MD':
+            s += n
+    return q, s
+
+
+def test_iter_map_bsn_flags_cpu(files, oracle_search):
+    args = '-r {ref} -q {qry} -f -m -O --blastn --diamond --min_id 0.4 --min_cov 50 --min_ratio 0.25 --merge_gap 600 --merge_diff 1.5 -t 1 -s 1 -e 0,3 --gtable 11'.format(**files).split()
+    blastab, overlap = ub.uberBlast(args)
+    assert oracle_search == [1, 2]
+    assert blastab.dtype == object and blastab.shape[1] == 17 and overlap.shape[1] == 3 and overlap.dtype.kind == 'i'
+    assert len(blastab) > 60
+    keys = [(r[0], r[1], r[11]) for r in blastab]
+    assert keys == sorted(keys)
+    for r in blastab:
+        assert isinstance(r[0], str) and isinstance(r[1], str) and isinstance(r[14], str) and isinstance(r[15], int)
+        assert 0.4 <= r[2] <= 1.0 and round(r[2], 3) == r[2]
+        assert 1 <= r[6] <= r[7] <= r[12] and 1 <= min(r[8], r[9]) and max(r[8], r[9]) <= r[13] == files['glen']
+        qspan, sspan = _cigar_spans(r[14])
+        assert qspan == r[7] - r[6] + 1 and sspan == abs(r[9] - r[8]) + 1
+        assert r[16][0] >= r[11] - 1e-9 and r[15] in r[16][3:]
+    # the same rows through the readable Python mirror of every stage
+    rb = ub.RunBlast()
+    rb.min_id, rb.min_cov, rb.min_ratio, rb.table_id = 0.4, 50., 0.25, 11
+    tabs = [rb.runBlast(files['ref'], files['qry']), rb.runDiamond(files['ref'], files['qry'])]
+    rows = [list(r) for b in tabs for r in b]
+    for i, r in enumerate(rows):
+        r.append(i)
+    ref_enc = {k: pf.encode_nuc(v) for k, v in rb.refSeq.items()}; qry_enc = {k: pf.encode_nuc(v) for k, v in rb.qrySeq.items()}
+    rows = pf.rescore(rows, ref_enc, qry_enc, 1, 0.4, 11)
+    rows = pf.ovl_filter(rows, 0.9, 0.)
+    rows = pf.linear_merge(rows, 600., 1.5)
+    pf.fix_end(rows, 0., 3.)
+    want_ovl = pf.overlaps(rows, 300, 0.6)
+    rows = pf.final_sort(rows)
+    assert len(rows) == len(blastab)
+    for a, b in zip(blastab, rows):
+        assert list(a[:2]) == b[:2] and list(a[3:11]) == b[3:11] and list(a[12:16]) == b[12:16]
+        assert abs(a[2] - b[2]) < 1e-12 and abs(a[11] - b[11]) < 1e-9
+        assert a[16][:2] == pytest.approx(b[16][:2]) and a[16][2:] == b[16][2:]
+    assert overlap.tolist() == want_ovl.tolist()
+    # planted genes are found
+    got = {}
+    for r in blastab:
+        got[int(r[0])] = max(got.get(int(r[0]), 0), (r[7] - r[6] + 1) / float(r[12]))
+    planted = [a for a in files['annot'] if a[4] >= 0.9 and (a[2] - a[1]) >= 0.99 * len(files['pool'].genes[a[0]])]
+    assert sum(1 for a in planted if got.get(a[0], 0) >= 0.8) == len(planted)
+
+
+def test_get_similar_pairs_flags_cpu(files, oracle_search):
+    args = '-r {qry} -q {qry} --blastn --diamond -s 1 --min_id 0.45 --min_cov 50 -t 4 --min_ratio 0.25 -e 3,3 -p --gtable 11'.format(**files).split()
+    blastab = ub.uberBlast(args, extPool='ignored')
+    assert blastab.shape[1] == 16
+    selfhits = [r for r in blastab if r[0] == r[1] and r[6] == 1 and r[7] == r[12]]
+    assert len(set(r[0] for r in selfhits)) == 120 and all(r[2] == 1.0 for r in selfhits)
+
+
+def test_raw_scores_and_output_file_cpu(files, oracle_search, tmp_path):
+    # no re-scoring: integer raw scores keep their type through the Python stages; -o writes one line per row
+    path = os.path.join(tmp_path, 'o.tsv')
+    res = ub.uberBlast(['-r', files['ref'], '-q', files['qry'], '--diamondSELF', '--blastn', '-o', path, '-e', '0,0'])
+    assert oracle_search == [1, 3] and res.shape[1] == 16 and len(res) > 0
+    assert all(isinstance(r[11], int) for r in res)
+    assert len(open(path).read().strip().split('\n')) == len(res)
+    assert ub.uberBlast(['-r', files['ref'], '-q', files['qry']]).shape == (0, 16)
