@@ -43,6 +43,51 @@ def _cigar_list(cigar, off, n):
     return [[int(o) >> 2, _OPS[int(o) & 3]] for o in cigar[off:off + n]]
 
 
+def _hit_columns(hits, cigar):
+    """columns of the record array as Python lists + per-hit CIGAR lists and gap statistics (one numpy pass)"""
+    cigar = np.asarray(cigar, dtype=np.uint32)
+    lens = (cigar >> 2).astype(np.int64); kinds = (cigar & 3)
+    off = hits['cigar_off'].astype(np.int64); end = off + hits['cigar_n'].astype(np.int64)
+    c_all = np.concatenate([[0], np.cumsum(lens)]); c_gap = np.concatenate([[0], np.cumsum(np.where(kinds != 0, lens, 0))])
+    c_ngap = np.concatenate([[0], np.cumsum(kinds != 0)])
+    pairs = [[n, _OPS[k]] for n, k in zip(lens.tolist(), kinds.tolist())]
+    cg = [pairs[a:b] for a, b in zip(off.tolist(), end.tolist())]
+    col = {k: hits[k].tolist() for k in ('q_id', 's_id', 'aln_len', 'mismatch', 'gapopen', 'q_start', 'q_end', 's_start', 's_end',
+                                         'evalue', 'raw_score', 'q_len', 's_len')}
+    return col, cg, (c_all[end] - c_all[off]).tolist(), (c_gap[end] - c_gap[off]).tolist(), (c_ngap[end] - c_ngap[off]).tolist()
+
+
+def rows_from_nt_hits(hits, cigar, qn, rn, min_id, min_cov, min_ratio):
+    """15-column rows of parseBlast (:275-290) from nucleotide-mode records: identity as blastn prints it (pident with three
+    decimals, / 100), rows below min_id / min_cov / min_ratio dropped (:283)"""
+    c, cg, _, gapb, _ = _hit_columns(hits, cigar)
+    rows = []
+    for i in range(len(hits)):
+        alen = c['aln_len'][i]
+        iden = float('%.3f' % (100.0 * (alen - c['mismatch'][i] - gapb[i]) / alen)) / 100.
+        span = c['q_end'][i] - c['q_start'][i] + 1
+        if not (iden >= min_id and span >= min_cov and span >= min_ratio * c['q_len'][i]):
+            continue
+        rows.append([qn[c['q_id'][i]], rn[c['s_id'][i]], iden, alen, c['mismatch'][i], c['gapopen'][i], c['q_start'][i], c['q_end'][i],
+                     c['s_start'][i], c['s_end'][i], c['evalue'][i], c['raw_score'][i], c['q_len'][i], c['s_len'][i], cg[i]])
+    return rows
+
+
+def rows_from_prot_hits(hits, cigar, qn, rn, min_id):
+    """15-column rows of parseDiamond (:16-70) from protein-mode records: identity 1 - round(3 NM / columns, 3) (:38),
+    mismatch = 3 NM - gap bases, gapopen = number of gap runs (:55-58), e-value forced to 0.0"""
+    c, cg, cl, gapb, ngap = _hit_columns(hits, cigar)
+    rows = []
+    for i in range(len(hits)):
+        variation = float(c['mismatch'][i] + gapb[i])          # 3 * NM
+        iden = 1 - round(variation / cl[i], 3)
+        if iden < min_id:
+            continue
+        rows.append([qn[c['q_id'][i]], rn[c['s_id'][i]], iden, cl[i], int(variation - gapb[i]), ngap[i], c['q_start'][i], c['q_end'][i],
+                     c['s_start'][i], c['s_end'][i], 0.0, c['raw_score'][i], c['q_len'][i], c['s_len'][i], cg[i]])
+    return rows
+
+
 class RunBlast(object):
     def __init__(self, ctx=None):
         self.qrySeq = self.refSeq = None
@@ -74,18 +119,7 @@ class RunBlast(object):
         logger('Run BLASTn starts')
         self._load(ref, qry)
         qn, rn, hits, cigar = self._search(_srch.MODE_NT)
-        rows = []
-        for h in hits:
-            cg = _cigar_list(cigar, int(h['cigar_off']), int(h['cigar_n']))
-            gapb = sum(n for n, t in cg if t != 'M')
-            nm = int(h['aln_len']) - int(h['mismatch']) - gapb
-            iden = float('%.3f' % (100.0 * nm / int(h['aln_len']))) / 100.
-            span = int(h['q_end']) - int(h['q_start']) + 1
-            if not (iden >= self.min_id and span >= self.min_cov and span >= self.min_ratio * int(h['q_len'])):
-                continue
-            rows.append([qn[h['q_id']], rn[h['s_id']], iden, int(h['aln_len']), int(h['mismatch']), int(h['gapopen']),
-                         int(h['q_start']), int(h['q_end']), int(h['s_start']), int(h['s_end']), float(h['evalue']),
-                         int(h['raw_score']), int(h['q_len']), int(h['s_len']), cg])
+        rows = rows_from_nt_hits(hits, cigar, qn, rn, self.min_id, self.min_cov, self.min_ratio)
         logger('Run BLASTn finishes. Got {0} alignments'.format(len(rows)))
         return _as_object_array(rows, 15)
 
@@ -97,18 +131,7 @@ class RunBlast(object):
         logger('Run diamond starts')
         self._load(ref, qry)
         qn, rn, hits, cigar = self._search(mode)
-        rows = []
-        for h in hits:
-            cg = _cigar_list(cigar, int(h['cigar_off']), int(h['cigar_n']))
-            cl = sum(n for n, t in cg)
-            cd = [n for n, t in cg if t != 'M']
-            variation = float(int(h['mismatch']) + sum(cd))          # 3 * NM
-            iden = 1 - round(variation / cl, 3)
-            if iden < self.min_id:
-                continue
-            rows.append([qn[h['q_id']], rn[h['s_id']], iden, cl, int(variation - sum(cd)), len(cd),
-                         int(h['q_start']), int(h['q_end']), int(h['s_start']), int(h['s_end']), 0.0,
-                         int(h['raw_score']), int(h['q_len']), int(h['s_len']), cg])
+        rows = rows_from_prot_hits(hits, cigar, qn, rn, self.min_id)
         logger('Run diamond finishes. Got {0} alignments'.format(len(rows)))
         return _as_object_array(rows, 15)
 

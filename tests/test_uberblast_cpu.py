@@ -114,3 +114,53 @@ def test_raw_scores_and_output_file_cpu(files, oracle_search, tmp_path):
     assert all(isinstance(r[11], int) for r in res)
     assert len(open(path).read().strip().split('\n')) == len(res)
     assert ub.uberBlast(['-r', files['ref'], '-q', files['qry']]).shape == (0, 16)
+
+
+def _loop_rows_nt(hits, cigar, qn, rn, min_id, min_cov, min_ratio):
+    """the per-hit statement the column version replaced"""
+    rows = []
+    for h in hits:
+        cg = ub._cigar_list(cigar, int(h['cigar_off']), int(h['cigar_n']))
+        gapb = sum(n for n, t in cg if t != 'M')
+        nm = int(h['aln_len']) - int(h['mismatch']) - gapb
+        iden = float('%.3f' % (100.0 * nm / int(h['aln_len']))) / 100.
+        span = int(h['q_end']) - int(h['q_start']) + 1
+        if not (iden >= min_id and span >= min_cov and span >= min_ratio * int(h['q_len'])):
+            continue
+        rows.append([qn[h['q_id']], rn[h['s_id']], iden, int(h['aln_len']), int(h['mismatch']), int(h['gapopen']),
+                     int(h['q_start']), int(h['q_end']), int(h['s_start']), int(h['s_end']), float(h['evalue']),
+                     int(h['raw_score']), int(h['q_len']), int(h['s_len']), cg])
+    return rows
+
+
+def _loop_rows_prot(hits, cigar, qn, rn, min_id):
+    rows = []
+    for h in hits:
+        cg = ub._cigar_list(cigar, int(h['cigar_off']), int(h['cigar_n']))
+        cl = sum(n for n, t in cg)
+        cd = [n for n, t in cg if t != 'M']
+        variation = float(int(h['mismatch']) + sum(cd))
+        iden = 1 - round(variation / cl, 3)
+        if iden < min_id:
+            continue
+        rows.append([qn[h['q_id']], rn[h['s_id']], iden, cl, int(variation - sum(cd)), len(cd),
+                     int(h['q_start']), int(h['q_end']), int(h['s_start']), int(h['s_end']), 0.0,
+                     int(h['raw_score']), int(h['q_len']), int(h['s_len']), cg])
+    return rows
+
+
+def test_row_builders_equal_the_per_hit_statement(files, oracle):
+    qn, qb, qo = seqio.to_seqset(seqio.read_fasta(files['qry'])); rn, rb, ro = seqio.to_seqset(seqio.read_fasta(files['ref']))
+    for mode in (1, 2, 3):
+        tb, to, tn = (rb, ro, rn) if mode != 3 else (qb, qo, qn)
+        hits, cigar = oracle.search(qb, qo, tb, to, mode, seqcodec.BLOSUM62.reshape(-1), min_id=0.3, min_cov=40, min_ratio=0.05)
+        assert len(hits) > 50
+        for min_id in (0.3, 0.8, 0.95):
+            if mode == 1:
+                got = ub.rows_from_nt_hits(hits, cigar, qn, tn, min_id, 60, 0.5); want = _loop_rows_nt(hits, cigar, qn, tn, min_id, 60, 0.5)
+            else:
+                got = ub.rows_from_prot_hits(hits, cigar, qn, tn, min_id); want = _loop_rows_prot(hits, cigar, qn, tn, min_id)
+            assert got == want and len(got) > 0
+            assert all(type(a) is type(b) for r1, r2 in zip(got, want) for a, b in zip(r1, r2))
+    empty = hits[:0]
+    assert ub.rows_from_nt_hits(empty, cigar[:0], qn, rn, 0.3, 40, 0.05) == [] and ub.rows_from_prot_hits(empty, cigar[:0], qn, rn, 0.3) == []
