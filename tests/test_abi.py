@@ -45,3 +45,14 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 for needle in ('import pb_oracle', 'from pb_oracle', 'libpb_oracle', 'oracle/pb_oracle.py', '#include "../../oracle', 'orc_'):
                     assert needle not in txt, '%s references the oracle (%s)' % (fn, needle)
+
+
+def test_plain_c_client_links_and_runs(tmp_path):
+    """tests/c/abi_smoke.c: a C99 program against include/peppan_b200.h and the shared library"""
+    import subprocess
+    exe = os.path.join(tmp_path, 'abi_smoke')
+    libdir = os.path.join(ROOT, 'peppan_b200')
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), os.path.join(ROOT, 'tests', 'c', 'abi_smoke.c'),
+                           '-L', libdir, '-lpeppan_b200', '-Wl,-rpath,' + libdir, '-o', exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and 'C ABI OK' in out.stdout, out.stdout + out.stderr
