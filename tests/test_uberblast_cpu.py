@@ -164,3 +164,19 @@ def test_row_builders_equal_the_per_hit_statement(files, oracle):
             assert all(type(a) is type(b) for r1, r2 in zip(got, want) for a, b in zip(r1, r2))
     empty = hits[:0]
     assert ub.rows_from_nt_hits(empty, cigar[:0], qn, rn, 0.3, 40, 0.05) == [] and ub.rows_from_prot_hits(empty, cigar[:0], qn, rn, 0.3) == []
+
+
+def test_nucl_flag_sets_cpu(files, oracle_search):
+    """PEPPAN --nucl: blastn only, no re-scoring (PEPPAN.py:226, :768) -- raw integer scores through filter / merge / overlap"""
+    args = '-r {ref} -q {qry} -f -m -O --blastn --min_id 0.4 --min_cov 50 --min_ratio 0.25 --merge_gap 600 --merge_diff 1.5 -t 1 -e 0,3 --gtable 11'.format(**files).split()
+    blastab, overlap = ub.uberBlast(args)
+    assert oracle_search == [1] and blastab.shape[1] == 17 and overlap.shape[1] == 3 and len(blastab) > 60
+    for r in blastab:
+        assert isinstance(r[11], int) and isinstance(r[14], str) and r[15] in r[16][3:]
+        qspan, sspan = _cigar_spans(r[14])
+        assert qspan == r[7] - r[6] + 1 and sspan == abs(r[9] - r[8]) + 1
+    keys = [(r[0], r[1], r[11]) for r in blastab]
+    assert keys == sorted(keys)
+    args = '-r {qry} -q {qry} --blastn --min_id 0.45 --min_cov 50 -t 4 --min_ratio 0.25 -e 3,3 -p --gtable 11'.format(**files).split()
+    self_bsn = ub.uberBlast(args)
+    assert self_bsn.shape[1] == 16 and len(set(r[0] for r in self_bsn if r[0] == r[1] and r[6] == 1 and r[7] == r[12])) == 120
