@@ -1,0 +1,165 @@
+"""Drop-in check at the consumer: the REFERENCE'S OWN PEPPAN.iter_map_bsn (PEPPAN.py:759-867) and compare_prediction
+(:869-902) are executed on the output of this repository's uberBlast() shim (module swap of INTEGRATION.md 1).  The reference
+is imported from /root/reference (present in the authoring container only -- the test is skipped elsewhere; nothing is
+copied), with an `ete3` stub and four no-op tool stubs on PATH as tests/golden/make_golden.py does.  pb_search is replaced, in
+this test only, by the scalar search oracle so that the test needs no GPU."""
+import os
+import stat
+import sys
+import tempfile
+import types
+
+import numpy as np
+import pytest
+
+from peppan_b200 import seqcodec, uberBlast as ub, workloads
+
+REF = os.environ.get('PEPPAN_REFERENCE', '/root/reference')
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'PEPPAN.py')), reason='reference checkout not present')
+
+
+@pytest.fixture(scope='module')
+def PEPPAN():
+    stubs = tempfile.mkdtemp(prefix='pb_stubs_')
+    for name in ('mmseqs', 'makeblastdb', 'diamond', 'blastn'):
+        p = os.path.join(stubs, name)
+        with open(p, 'w') as f:
+            f.write('#!/bin/sh\nexit 0\n')
+        os.chmod(p, os.stat(p).st_mode | stat.S_IEXEC)
+    os.environ['PATH'] = stubs + os.pathsep + os.path.join(REF, 'dependencies') + os.pathsep + os.environ['PATH']
+    if 'ete3' not in sys.modules:
+        m = types.ModuleType('ete3'); m.Tree = object
+        sys.modules['ete3'] = m
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        import PEPPAN as P
+    return P
+
+
+def test_reference_iter_map_bsn_consumes_the_shim_output(PEPPAN, oracle, monkeypatch, tmp_path):
+    def fake_search(ctx, qb, qo, rb, ro, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
+        hits, cigar = oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov,
+                                    min_ratio=min_ratio, gtable=gtable, max_hits=max_hits)
+        return hits, cigar, dict(kernel_launches=0)
+    monkeypatch.setattr(ub._srch, 'search', fake_search)
+    monkeypatch.setattr(ub, 'get_context', lambda: None)
+    monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)          # the module swap: PEPPAN calls our shim
+    if not hasattr(np.lib.npyio, 'format'):                          # the reference predates numpy 2 (PEPPAN.py:41, :89)
+        monkeypatch.setattr(np.lib.npyio, 'format', np.lib.format, raising=False)
+
+    # exemplar genes with integer names (encodeNames, PEPPAN.py:1766-1775) and one genome of two contigs
+    pool = workloads.GenePool(40, 40, seed=workloads.SEED + 31)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=20, seed=workloads.SEED + 31)
+    cut = len(seq) // 2
+    contigs = [(1001, seq[:cut]), (1002, seq[cut:])]
+    clust = os.path.join(tmp_path, 'exemplar.fa')
+    with open(clust, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    # old annotation store: the planted genes of contig 1001, as [gene, start, end, strand] rows per contig
+    old = os.path.join(tmp_path, 'old.npz')
+    store = PEPPAN.MapBsn(old, 'w')
+    rows = [[a[0], a[1] + 1, a[2], '+' if a[3] > 0 else '-'] for a in annot if a[2] <= cut]
+    store._save(store.conn, '1001', np.array(sorted(rows, key=lambda r: r[1]), dtype=object))
+    store.conn.close()
+    ortho = os.path.join(tmp_path, 'ortho.npy')
+    np.save(ortho, np.zeros([0, 3], dtype=int), allow_pickle=True)
+    params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+    prefix = os.path.join(tmp_path, 'run')
+    out = PEPPAN.iter_map_bsn((prefix, clust, 0, 'taxon', contigs, ortho, old, params))
+    assert out == prefix + '.0' and not os.path.exists(prefix + '.0.genome')
+    res = np.load(out + '.bsn.npz', allow_pickle=True)
+    bsn, ovl = res['bsn'], res['ovl']
+    assert bsn.ndim == 2 and bsn.shape[1] == 7 and ovl.shape[1] in (2, 3)
+    found = set(int(g[0]) for g in bsn)
+    planted = set(a[0] for a in annot if a[4] >= 0.9 and (a[2] - a[1]) >= 0.99 * len(pool.genes[a[0]]) and not (a[1] < cut < a[2]))
+    assert planted <= found, sorted(planted - found)[:5]
+    for g in bsn:
+        assert g[1] in (1001, 1002) and g[2] > 0 and 0.5 <= g[3] <= 1.0 and g[4].dtype == np.uint8 and len(g[6]) >= 1
+        for tab in g[6]:
+            assert len(tab) == 16 and isinstance(tab[14], str) and 0 < tab[10] <= 1.0        # column 10 rewritten by compare_prediction
+    # hits that coincide with an old annotation on contig 1001 carry its overlap fraction in column 10 (:899-900)
+    assert sum(1 for g in bsn for tab in g[6] if tab[1] == 1001 and tab[10] > 0.6) >= 0.8 * len(rows)
+
+
+def test_reference_get_similar_pairs_consumes_the_shim_output(PEPPAN, oracle, monkeypatch, tmp_path):
+    """PEPPAN.get_similar_pairs (PEPPAN.py:194-294): exemplar-vs-exemplar all-vs-all through the shim (-s 1 -e 3,3 -p)"""
+    def fake_search(ctx, qb, qo, rb, ro, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
+        hits, cigar = oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov,
+                                    min_ratio=min_ratio, gtable=gtable, max_hits=max_hits)
+        return hits, cigar, dict(kernel_launches=0)
+    monkeypatch.setattr(ub._srch, 'search', fake_search)
+    monkeypatch.setattr(ub, 'get_context', lambda: None)
+    monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)
+    monkeypatch.setattr(PEPPAN, 'pool', None, raising=False)         # the worker pool PEPPAN hands over as extPool (ignored by the shim)
+
+    rng = np.random.default_rng(77)
+    gp = workloads.GenePool(30, 0, seed=workloads.SEED + 41)
+    genes = {i: g for i, g in enumerate(gp.genes)}
+    near = {100 + i: workloads._diverge(rng, gp.genes[i], 0.95) for i in range(0, 10)}        # same length, >= clust_identity: merged
+    far = {200 + i: workloads._diverge(rng, gp.genes[i], 0.75) for i in range(10, 20)}        # similar, not mergeable: ortholog pairs
+    allg = dict(genes); allg.update(near); allg.update(far)
+    clust = os.path.join(tmp_path, 'x.clust.exemplar')
+    with open(clust, 'w') as f:
+        for n, g in allg.items():
+            f.write('>%d\n%s\n' % (n, workloads._NT[g].tobytes().decode()))
+    np.save(os.path.join(tmp_path, 'x.clust.npy'), np.zeros([0, 3], dtype=int))
+    priorities = {n: [0, n] for n in allg}
+    params = dict(clust=clust, incompleteCDS='', noDiamond=False, n_thread=2, gtable=11, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400., clust_identity=0.9, clust_match_prop=0.8)
+    pairs = PEPPAN.get_similar_pairs(clust, priorities, params)
+    assert pairs.ndim == 2 and pairs.shape[1] == 3 and pairs.dtype.kind == 'i'
+    got = set((int(a), int(b)) for a, b, v in pairs if v > 0)
+    want = set((i, 200 + i) for i in range(10, 20))
+    assert want <= got, sorted(want - got)
+    assert all(5000 <= v <= 10000 for a, b, v in pairs if v > 0)
+    # near-identical copies were merged into their exemplar: dropped from the exemplar file, recorded in the .npy
+    kept = set(int(l[1:].split()[0]) for l in open(clust) if l.startswith('>'))
+    clu = np.load(os.path.join(tmp_path, 'x.clust.npy'), allow_pickle=True)
+    merged = set(int(x) for x in clu[:, 1])
+    assert len(merged) == 10 and not (merged & kept) and all(({int(a), int(b)} & kept) for a, b, _ in clu)
+    assert all(({i, 100 + i} & merged) for i in range(10)) and all(9000 <= int(v) <= 10000 for v in clu[:, 2])
+
+
+def test_reference_iterclust_drives_the_getclust_shim(PEPPAN, oracle, monkeypatch, tmp_path):
+    """PEPPAN.iterClust (PEPPAN.py:1777-1792): the identity ladder 1.00 .. 0.90 through this repository's getClust (module
+    swap), pb_cluster standing in by the oracle's search + greedy (test only)"""
+    from peppan_b200 import clust as pclust
+    from test_clust_gpu import _oracle_clusters
+
+    def fake_cluster(ctx, buf, off, identity, coverage, translate=False, gtable=11):
+        n = len(off) - 1
+        items = [(str(i), buf[off[i]:off[i + 1]].tobytes().decode()) for i in range(n)]
+        rep = _oracle_clusters(oracle, items, float(identity), float(coverage), translate=translate)
+        return rep, dict(n_reps=int((rep == np.arange(n)).sum()))
+    monkeypatch.setattr(pclust, 'cluster', fake_cluster)
+    monkeypatch.setattr(pclust, 'get_context', lambda: None)
+    monkeypatch.setattr(PEPPAN, 'getClust', pclust.getClust)
+
+    rng = np.random.default_rng(5)
+    gp = workloads.GenePool(12, 0, seed=workloads.SEED + 51)
+    seqs = []
+    for a in range(12):
+        seqs.append(gp.genes[a])
+        for iden in (1.0, 0.985, 0.93):                                  # copies that merge on different rungs of the ladder
+            seqs.append(workloads._diverge(rng, gp.genes[a], iden))
+    seqs.sort(key=lambda g: -g.size)                                      # PEPPAN orders by priority, then longer first
+    genes = os.path.join(tmp_path, 'genes.fa')
+    with open(genes, 'w') as f:
+        for i, g in enumerate(seqs):
+            f.write('>%d\n%s\n' % (i, workloads._NT[g].tobytes().decode()))
+    prefix = os.path.join(tmp_path, 'run')
+    groups = []
+    exemplar = PEPPAN.iterClust(prefix, genes, groups, dict(identity=0.9, coverage=0.8, n_thread=2, translate=False))
+    assert exemplar == prefix + '.clust.exemplar'
+    left = [int(l[1:].split()[0]) for l in open(exemplar) if l.startswith('>')]
+    assert len(left) == 12                                               # one exemplar per ancestral gene at identity 0.9
+    clu = np.load(prefix + '.clust.npy', allow_pickle=True)
+    assert clu.shape[1] == 3 and clu.dtype.kind == 'i' and set(clu[:, 2].tolist()) <= set(range(9050, 10001, 100)) | {10000}
+    # exact copies merge on the first rung, the 98.5 % copies two rungs later, the 93 % copies near the bottom
+    assert (clu[:, 2] == 10000).sum() >= 11 and ((clu[:, 2] < 10000) & (clu[:, 2] >= 9800)).sum() >= 8 and (clu[:, 2] < 9500).sum() >= 8
+    assert set(clu[:, 0].tolist()) | set(left) >= set(left) and not (set(clu[:, 1].tolist()) & set(left))
