@@ -163,3 +163,92 @@ def test_reference_iterclust_drives_the_getclust_shim(PEPPAN, oracle, monkeypatc
     # exact copies merge on the first rung, the 98.5 % copies two rungs later, the 93 % copies near the bottom
     assert (clu[:, 2] == 10000).sum() >= 11 and ((clu[:, 2] < 10000) & (clu[:, 2] >= 9800)).sum() >= 8 and (clu[:, 2] < 9500).sum() >= 8
     assert set(clu[:, 0].tolist()) | set(left) >= set(left) and not (set(clu[:, 1].tolist()) & set(left))
+
+
+def test_reference_parseblast_reads_our_hits_as_blastn_output(PEPPAN, oracle, tmp_path):
+    """The process-level seam: our nucleotide hits are written in blastn's `-outfmt 6 ... qseq sseq` layout
+    by a stand-in `blastn` executable and read by the REFERENCE'S poolBlast / parseBlast / getCIGAR
+    (modules/uberBlast.py:274-320); the rows it builds must equal the rows of this repository's runBlast."""
+    import stat as _stat
+    from peppan_b200 import seqio
+    refmod = sys.modules['modules.uberBlast'] if 'modules.uberBlast' in sys.modules else __import__('modules.uberBlast', fromlist=['x'])
+    pool = workloads.GenePool(40, 40, seed=workloads.SEED + 61)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=20, seed=workloads.SEED + 61)
+    qitems = pool.fasta_items(); titems = [('7', seq)]
+    qn, qb, qo = seqio.to_seqset(qitems); tn, tb, to = seqio.to_seqset(titems)
+    hits, cigar = oracle.search(qb, qo, tb, to, 1, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
+    assert len(hits) > 40 and (hits['s_start'] > hits['s_end']).any()
+    comp = str.maketrans('ACGT', 'TGCA')
+    qd = dict(qitems)
+    lines = []
+    for h in hits:
+        q = qd[qn[h['q_id']]][h['q_start'] - 1:h['q_end']]
+        s = seq[h['s_start'] - 1:h['s_end']] if h['s_start'] < h['s_end'] else seq[h['s_end'] - 1:h['s_start']].translate(comp)[::-1]
+        qa, sa, qi, si = [], [], 0, 0
+        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        for op in ops:
+            n, k = int(op) >> 2, int(op) & 3
+            if k == 0:
+                qa.append(q[qi:qi + n]); sa.append(s[si:si + n]); qi += n; si += n
+            elif k == 1:                      # I: extra bases in the query
+                qa.append(q[qi:qi + n]); sa.append('-' * n); qi += n
+            else:                             # D: extra bases in the subject
+                qa.append('-' * n); sa.append(s[si:si + n]); si += n
+        assert qi == len(q) and si == len(s)
+        gapb = sum(int(o) >> 2 for o in ops if int(o) & 3)
+        pident = '%.3f' % (100.0 * (int(h['aln_len']) - int(h['mismatch']) - gapb) / int(h['aln_len']))
+        lines.append('\t'.join(str(x) for x in (qn[h['q_id']], tn[h['s_id']], pident, h['aln_len'], h['mismatch'], h['gapopen'], h['q_start'], h['q_end'],
+                                                 h['s_start'], h['s_end'], '%.3g' % h['evalue'], h['raw_score'], h['q_len'], h['s_len'], ''.join(qa), ''.join(sa))))
+    qry = os.path.join(tmp_path, 'qry.fa')
+    prepared = os.path.join(tmp_path, 'prepared.tsv')
+    open(prepared, 'w').write('\n'.join(lines) + '\n')
+    fake = os.path.join(tmp_path, 'blastn')
+    with open(fake, 'w') as f:
+        f.write('#!/bin/sh\ncp %s %s.bsn\n' % (prepared, qry))
+    os.chmod(fake, os.stat(fake).st_mode | _stat.S_IEXEC)
+    out = refmod.poolBlast((fake, 'unused_db', qry, 0.4, 50, 0.25))
+    got = np.load(out, allow_pickle=True)
+    want = ub.rows_from_nt_hits(hits, cigar, qn, tn, 0.4, 50, 0.25)
+    assert len(got) == len(want) > 40
+    for g, w in zip(got, want):
+        assert [str(g[0]), str(g[1])] == w[:2] and abs(float(g[2]) - w[2]) < 1e-12
+        assert [int(x) for x in g[3:10]] == w[3:10] and [int(x) for x in g[11:14]] == w[11:14]
+        assert [[int(n), str(t)] for n, t in g[14]] == w[14]
+
+
+def test_reference_parsediamond_reads_our_hits_as_sam(PEPPAN, oracle, tmp_path):
+    """Our protein-vs-6-frame hits rendered as DIAMOND `--outfmt 101` SAM lines and read by the REFERENCE'S parseDiamond
+    (modules/uberBlast.py:14-70): the rows it builds (coordinates on both strands, identity, mismatch, gap count, CIGAR x 3,
+    raw score) must equal the rows of this repository's runDiamond."""
+    from peppan_b200 import seqio
+    refmod = sys.modules['modules.uberBlast'] if 'modules.uberBlast' in sys.modules else __import__('modules.uberBlast', fromlist=['x'])
+    pool = workloads.GenePool(40, 40, seed=workloads.SEED + 71)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=20, seed=workloads.SEED + 71)
+    qitems = pool.fasta_items(); titems = [('7', seq)]
+    qn, qb, qo = seqio.to_seqset(qitems); tn, tb, to = seqio.to_seqset(titems)
+    hits, cigar = oracle.search(qb, qo, tb, to, 2, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
+    assert len(hits) > 40 and (hits['frame'] > 3).any() and (hits['frame'] <= 3).any()
+    rl = len(seq)
+    lines = ['@HD\tVN:1.5']
+    for h in hits:
+        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        assert all((int(o) >> 2) % 3 == 0 for o in ops)
+        aacig = ''.join('%d%s' % ((int(o) >> 2) // 3, 'MID'[int(o) & 3]) for o in ops)
+        qf = (int(h['q_start']) - 1) % 3 + 1; rf = int(h['frame'])
+        qs_aa = (int(h['q_start']) - qf) // 3 + 1
+        qm = (int(h['q_end']) - int(h['q_start']) + 1) // 3
+        rs = (int(h['s_start']) - rf + 3) // 3 if rf <= 3 else (rl + 7 - int(h['s_start']) - rf) // 3
+        gap_aa = sum((int(o) >> 2) // 3 for o in ops if int(o) & 3)
+        nm = int(h['mismatch']) // 3 + gap_aa
+        lines.append('\t'.join(str(x) for x in ('%s:%d' % (qn[h['q_id']], qf), 0, '%s:%d:0' % (tn[h['s_id']], rf), rs, 255, aacig, '*', 0, 0, 'A' * qm, '*',
+                                                 'AS:i:0', 'NM:i:%d' % nm, 'ZL:i:0', 'ZR:i:%d' % h['raw_score'], 'ZE:f:0', 'ZI:i:0', 'ZF:i:1', 'ZS:i:%d' % qs_aa)))
+    fn = os.path.join(tmp_path, 'aaMatch.0')
+    open(fn, 'w').write('\n'.join(lines) + '\n')
+    out = refmod.parseDiamond([fn, dict(titems), dict(qitems), 0.4, 50, 0.25])
+    got = np.load(out, allow_pickle=True)
+    want = ub.rows_from_prot_hits(hits, cigar, qn, tn, 0.4)
+    assert len(got) == len(want) > 40
+    for g, w in zip(got, want):
+        assert [str(g[0]), str(g[1])] == w[:2] and abs(float(g[2]) - w[2]) < 1e-12
+        assert [int(x) for x in g[3:10]] == w[3:10] and float(g[10]) == 0.0 and [int(x) for x in g[11:14]] == w[11:14]
+        assert [[int(n), str(t)] for n, t in g[14]] == w[14]
