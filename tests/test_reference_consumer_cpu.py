@@ -252,3 +252,127 @@ def test_reference_parsediamond_reads_our_hits_as_sam(PEPPAN, oracle, tmp_path):
         assert [str(g[0]), str(g[1])] == w[:2] and abs(float(g[2]) - w[2]) < 1e-12
         assert [int(x) for x in g[3:10]] == w[3:10] and float(g[10]) == 0.0 and [int(x) for x in g[11:14]] == w[11:14]
         assert [[int(n), str(t)] for n, t in g[14]] == w[14]
+
+
+_FAKE_BLASTN = r'''#!{py}
+import sys
+a = sys.argv[1:]
+qry, out = a[a.index('-query') + 1], a[a.index('-out') + 1]
+names = set(l[1:].strip().split()[0] for l in open(qry) if l.startswith('>'))
+with open(out, 'w') as f:
+    for line in open({tsv!r}):
+        if line.split('\t', 1)[0] in names:
+            f.write(line)
+'''
+
+_FAKE_DIAMOND = r'''#!{py}
+import json, sys
+a = sys.argv[1:]
+if a[0] != 'blastp':
+    sys.exit(0)
+db, out = a[a.index('--db') + 1], a[a.index('--out') + 1]
+chunks, name = {{}}, None
+for line in open(db):
+    if line.startswith('>'):
+        name = line[1:].strip()
+    else:
+        n, rf, ci = name.rsplit(':', 2)
+        chunks.setdefault((n, int(rf)), []).append((int(ci), len(line.strip())))
+with open(out, 'w') as f:
+    f.write('@HD\tVN:1.5\n')
+    for h in json.load(open({js!r})):
+        for ci, ln in chunks.get((h['contig'], h['rf']), []):
+            if ci < h['rs'] and h['rs'] + h['rm'] - 1 <= ci + ln:
+                f.write('\t'.join([h['qname'], '0', '%s:%d:%d' % (h['contig'], h['rf'], ci), str(h['rs'] - ci)] + h['rest']) + '\n')
+'''
+
+
+def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(PEPPAN, oracle, monkeypatch, tmp_path):
+    """The whole of the reference's modules/uberBlast.py (uberBlast -> RunBlast.run -> runBlast / runDiamond -> poolBlast /
+    parseDiamond -> reScore -> ovlFilter -> linearMerge -> fixEnd -> returnOverlap) is executed with its three external
+    tools replaced by stand-ins that answer with OUR hits in the tools' own output formats; its final table and overlap
+    list must equal what this repository's uberBlast() returns for the same command line (hit ids aside, which number the
+    rows in tool-output order)."""
+    import json
+    import stat as _stat
+    from peppan_b200 import seqio
+    refmod = sys.modules['modules.uberBlast'] if 'modules.uberBlast' in sys.modules else __import__('modules.uberBlast', fromlist=['x'])
+    pool = workloads.GenePool(40, 40, seed=workloads.SEED + 81)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=20, seed=workloads.SEED + 81)
+    cut = len(seq) // 2
+    qitems = pool.fasta_items(); titems = [('7', seq[:cut]), ('8', seq[cut:])]
+    qry = os.path.join(tmp_path, 'exemplar.fa'); ref = os.path.join(tmp_path, 'genome.fa')
+    open(qry, 'w').write(''.join('>%s\n%s\n' % x for x in qitems)); open(ref, 'w').write(''.join('>%s\n%s\n' % x for x in titems))
+    qn, qb, qo = seqio.to_seqset(qitems); tn, tb, to = seqio.to_seqset(titems)
+    qd, td = dict(qitems), dict(titems)
+    comp = str.maketrans('ACGT', 'TGCA')
+    # ---- our hits in the tools' formats
+    hits, cigar = oracle.search(qb, qo, tb, to, 1, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
+    lines = []
+    for h in hits:
+        s_all = td[tn[h['s_id']]]
+        q = qd[qn[h['q_id']]][h['q_start'] - 1:h['q_end']]
+        s = s_all[h['s_start'] - 1:h['s_end']] if h['s_start'] < h['s_end'] else s_all[h['s_end'] - 1:h['s_start']].translate(comp)[::-1]
+        qa, sa, qi, si = [], [], 0, 0
+        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        for op in ops:
+            n, k = int(op) >> 2, int(op) & 3
+            if k == 0:
+                qa.append(q[qi:qi + n]); sa.append(s[si:si + n]); qi += n; si += n
+            elif k == 1:
+                qa.append(q[qi:qi + n]); sa.append('-' * n); qi += n
+            else:
+                qa.append('-' * n); sa.append(s[si:si + n]); si += n
+        gapb = sum(int(o) >> 2 for o in ops if int(o) & 3)
+        pident = '%.3f' % (100.0 * (int(h['aln_len']) - int(h['mismatch']) - gapb) / int(h['aln_len']))
+        lines.append('\t'.join(str(x) for x in (qn[h['q_id']], tn[h['s_id']], pident, h['aln_len'], h['mismatch'], h['gapopen'], h['q_start'], h['q_end'],
+                                                 h['s_start'], h['s_end'], '%.3g' % h['evalue'], h['raw_score'], h['q_len'], h['s_len'], ''.join(qa), ''.join(sa))))
+    tsv = os.path.join(tmp_path, 'prepared.tsv'); open(tsv, 'w').write('\n'.join(lines) + '\n')
+    phits, pcigar = oracle.search(qb, qo, tb, to, 2, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
+    recs = []
+    for h in phits:
+        ops = pcigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        rl = int(h['s_len'])
+        qf = (int(h['q_start']) - 1) % 3 + 1; rf = int(h['frame'])
+        qm = (int(h['q_end']) - int(h['q_start']) + 1) // 3
+        rs = (int(h['s_start']) - rf + 3) // 3 if rf <= 3 else (rl + 7 - int(h['s_start']) - rf) // 3
+        rm = sum((int(o) >> 2) // 3 for o in ops if (int(o) & 3) in (0, 2))
+        nm = int(h['mismatch']) // 3 + sum((int(o) >> 2) // 3 for o in ops if int(o) & 3)
+        aacig = ''.join('%d%s' % ((int(o) >> 2) // 3, 'MID'[int(o) & 3]) for o in ops)
+        recs.append(dict(qname='%s:%d' % (qn[h['q_id']], qf), contig=tn[h['s_id']], rf=rf, rs=rs, rm=rm,
+                         rest=['255', aacig, '*', '0', '0', 'A' * qm, '*', 'AS:i:0', 'NM:i:%d' % nm, 'ZL:i:0', 'ZR:i:%d' % h['raw_score'],
+                               'ZE:f:0', 'ZI:i:0', 'ZF:i:1', 'ZS:i:%d' % ((int(h['q_start']) - qf) // 3 + 1)]))
+    js = os.path.join(tmp_path, 'prepared.json'); json.dump(recs, open(js, 'w'))
+    tools = {}
+    for name, body in (('blastn', _FAKE_BLASTN.format(py=sys.executable, tsv=tsv)), ('diamond', _FAKE_DIAMOND.format(py=sys.executable, js=js)),
+                       ('makeblastdb', '#!/bin/sh\nexit 0\n')):
+        p = os.path.join(tmp_path, name)
+        open(p, 'w').write(body); os.chmod(p, os.stat(p).st_mode | _stat.S_IEXEC)
+        tools[name] = p
+        monkeypatch.setattr(refmod, name, p)
+    monkeypatch.chdir(tmp_path)
+    args = '-r {0} -q {1} -f -m -O --blastn --diamond --min_id 0.4 --min_cov 50 --min_ratio 0.25 --merge_gap 600 --merge_diff 1.5 -t 1 -s 1 -e 0,3 --gtable 11'.format(ref, qry).split()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        rtab, rovl = refmod.uberBlast(args)
+
+    def fake_search(ctx, qb_, qo_, rb_, ro_, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
+        h_, c_ = oracle.search(qb_, qo_, rb_, ro_, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov, min_ratio=min_ratio,
+                               gtable=gtable, max_hits=max_hits)
+        return h_, c_, dict(kernel_launches=0)
+    monkeypatch.setattr(ub._srch, 'search', fake_search)
+    monkeypatch.setattr(ub, 'get_context', lambda: None)
+    otab, oovl = ub.uberBlast(args)
+
+    def canon(tab, ovl):
+        key = {int(r[15]): (str(r[0]), str(r[1]), int(r[6]), int(r[7]), int(r[8]), int(r[9]), str(r[14])) for r in tab}
+        rows = sorted((str(r[0]), str(r[1]), round(float(r[2]), 6), int(r[3]), int(r[4]), int(r[5]), int(r[6]), int(r[7]), int(r[8]), int(r[9]),
+                       round(float(r[11]), 6), int(r[12]), int(r[13]), str(r[14]),
+                       (round(float(r[16][0]), 6), round(float(r[16][1]), 6), int(r[16][2]), tuple(key[int(i)] for i in r[16][3:]))) for r in tab)
+        ov = sorted((key[int(a)], key[int(b)], int(c)) for a, b, c in ovl)
+        return rows, ov
+    rrows, rov = canon(rtab, rovl); orows, oov = canon(otab, oovl)
+    assert len(orows) >= 40 and len(rrows) == len(orows)
+    assert rrows == orows
+    assert rov == oov
