@@ -376,3 +376,65 @@ def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(P
     assert len(orows) >= 40 and len(rrows) == len(orows)
     assert rrows == orows
     assert rov == oov
+
+
+_FAKE_MMSEQS = r'''#!{py}
+# stand-in for `mmseqs createdb / linclust / createtsv` (modules/clust.py:62-66): clusters with the oracle's search + scalar greedy
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'oracle')); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+a = sys.argv[1:]
+state = {state!r}
+if a[0] == 'createdb':
+    open(state, 'w').write(a[1])
+elif a[0] == 'linclust':
+    open(state, 'a').write('\n%s\n%s' % (a[a.index('--min-seq-id') + 1], a[a.index('-c') + 1]))
+elif a[0] == 'createtsv':
+    import numpy as np
+    import pb_oracle
+    from peppan_b200 import seqio
+    from test_clust_gpu import _oracle_clusters
+    genes, iden, cov = open(state).read().split('\n')
+    items = list(seqio.read_fasta(genes).items())
+    rep = _oracle_clusters(pb_oracle, items, float(iden), float(cov))
+    with open(a[4], 'w') as f:
+        # mmseqs names a cluster after a member of its own choosing: use the LAST member to make the re-election matter
+        last = {{}}
+        for i, r in enumerate(rep):
+            last[int(r)] = i
+        for i, r in enumerate(rep):
+            f.write('%s\t%s\n' % (items[last[int(r)]][0], items[i][0]))
+'''
+
+
+def test_reference_getclust_with_mmseqs_emulated_from_our_clustering_equals_the_shim(PEPPAN, oracle, monkeypatch, tmp_path):
+    """The reference's getClust (modules/clust.py:34-111: three rounds of createdb / linclust / createtsv, re-election of the
+    first member in file order, closure) driven by a stand-in `mmseqs` that clusters like pb_cluster; its two output files
+    must equal the files of this repository's getClust."""
+    import stat as _stat
+    from peppan_b200 import clust as pclust
+    from test_clust_gpu import _genes, _oracle_clusters
+    refclust = sys.modules['modules.clust'] if 'modules.clust' in sys.modules else __import__('modules.clust', fromlist=['x'])
+    items = _genes(6, n_anc=20)
+    fa = os.path.join(tmp_path, 'genes.fa')
+    with open(fa, 'w') as f:
+        for n, s in items:
+            f.write('>%s\n%s\n' % (n, s))
+    fake = os.path.join(tmp_path, 'mmseqs')
+    open(fake, 'w').write(_FAKE_MMSEQS.format(py=sys.executable, root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                              state=os.path.join(tmp_path, 'mmseqs.state')))
+    os.chmod(fake, os.stat(fake).st_mode | _stat.S_IEXEC)
+    monkeypatch.setitem(refclust.externals, 'mmseqs', fake)
+    monkeypatch.chdir(tmp_path)
+    rex, rtab = refclust.getClust(os.path.join(tmp_path, 'ref'), fa, dict(identity=0.9, coverage=0.8, n_thread=2, translate=False))
+
+    def fake_cluster(ctx, buf, off, identity, coverage, translate=False, gtable=11):
+        n = len(off) - 1
+        its = [(str(i), buf[off[i]:off[i + 1]].tobytes().decode()) for i in range(n)]
+        rep = _oracle_clusters(oracle, its, float(identity), float(coverage), translate=translate)
+        return rep, dict(n_reps=int((rep == np.arange(n)).sum()))
+    monkeypatch.setattr(pclust, 'cluster', fake_cluster)
+    monkeypatch.setattr(pclust, 'get_context', lambda: None)
+    oex, otab = pclust.getClust(os.path.join(tmp_path, 'ours'), fa, dict(identity=0.9, coverage=0.8, n_thread=2, translate=False))
+    assert open(rtab).read() == open(otab).read()
+    assert open(rex).read() == open(oex).read()
+    assert 20 <= sum(1 for l in open(oex) if l.startswith('>')) < len(items)
