@@ -376,6 +376,55 @@ def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(P
     assert len(orows) >= 40 and len(rrows) == len(orows)
     assert rrows == orows
     assert rov == oov
+    # get_similar_pairs' command line on the same files (genome as both sides would be odd: exemplars vs exemplars), with the
+    # reference's process pool (-p) and four query chunks (-t 4): 16 columns, no merge groups, no overlap list
+    hits2, cigar2 = oracle.search(qb, qo, qb, qo, 1, seqcodec.BLOSUM62.reshape(-1), min_id=0.45, min_cov=50, min_ratio=0.25)
+    lines = []
+    for h in hits2:
+        q = qd[qn[h['q_id']]][h['q_start'] - 1:h['q_end']]
+        s_all = qd[qn[h['s_id']]]
+        s = s_all[h['s_start'] - 1:h['s_end']] if h['s_start'] < h['s_end'] else s_all[h['s_end'] - 1:h['s_start']].translate(comp)[::-1]
+        qa, sa, qi, si = [], [], 0, 0
+        ops = cigar2[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        for op in ops:
+            n, k = int(op) >> 2, int(op) & 3
+            if k == 0:
+                qa.append(q[qi:qi + n]); sa.append(s[si:si + n]); qi += n; si += n
+            elif k == 1:
+                qa.append(q[qi:qi + n]); sa.append('-' * n); qi += n
+            else:
+                qa.append('-' * n); sa.append(s[si:si + n]); si += n
+        gapb = sum(int(o) >> 2 for o in ops if int(o) & 3)
+        pident = '%.3f' % (100.0 * (int(h['aln_len']) - int(h['mismatch']) - gapb) / int(h['aln_len']))
+        lines.append('\t'.join(str(x) for x in (qn[h['q_id']], qn[h['s_id']], pident, h['aln_len'], h['mismatch'], h['gapopen'], h['q_start'], h['q_end'],
+                                                 h['s_start'], h['s_end'], '%.3g' % h['evalue'], h['raw_score'], h['q_len'], h['s_len'], ''.join(qa), ''.join(sa))))
+    open(tsv, 'w').write('\n'.join(lines) + '\n')
+    phits2, pcigar2 = oracle.search(qb, qo, qb, qo, 2, seqcodec.BLOSUM62.reshape(-1), min_id=0.45, min_cov=50, min_ratio=0.25)
+    recs = []
+    for h in phits2:
+        ops = pcigar2[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        rl = int(h['s_len'])
+        qf = (int(h['q_start']) - 1) % 3 + 1; rf = int(h['frame'])
+        qm = (int(h['q_end']) - int(h['q_start']) + 1) // 3
+        rs = (int(h['s_start']) - rf + 3) // 3 if rf <= 3 else (rl + 7 - int(h['s_start']) - rf) // 3
+        rm = sum((int(o) >> 2) // 3 for o in ops if (int(o) & 3) in (0, 2))
+        nm = int(h['mismatch']) // 3 + sum((int(o) >> 2) // 3 for o in ops if int(o) & 3)
+        aacig = ''.join('%d%s' % ((int(o) >> 2) // 3, 'MID'[int(o) & 3]) for o in ops)
+        recs.append(dict(qname='%s:%d' % (qn[h['q_id']], qf), contig=qn[h['s_id']], rf=rf, rs=rs, rm=rm,
+                         rest=['255', aacig, '*', '0', '0', 'A' * qm, '*', 'AS:i:0', 'NM:i:%d' % nm, 'ZL:i:0', 'ZR:i:%d' % h['raw_score'],
+                               'ZE:f:0', 'ZI:i:0', 'ZF:i:1', 'ZS:i:%d' % ((int(h['q_start']) - qf) // 3 + 1)]))
+    json.dump(recs, open(js, 'w'))
+    args2 = '-r {0} -q {0} --blastn --diamond -s 1 --min_id 0.45 --min_cov 50 -t 4 --min_ratio 0.25 -e 3,3 -p --gtable 11'.format(qry).split()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        rtab2 = refmod.uberBlast(args2)
+    otab2 = ub.uberBlast(args2)
+
+    def canon16(tab):
+        return sorted((str(r[0]), str(r[1]), round(float(r[2]), 6), int(r[3]), int(r[4]), int(r[5]), int(r[6]), int(r[7]), int(r[8]), int(r[9]),
+                       round(float(r[11]), 6), int(r[12]), int(r[13]), str(r[14])) for r in tab)
+    assert rtab2.shape[1] == 16 and otab2.shape[1] == 16 and len(otab2) >= 160
+    assert canon16(rtab2) == canon16(otab2)
 
 
 _FAKE_MMSEQS = r'''#!{py}
