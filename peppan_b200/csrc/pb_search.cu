@@ -7,9 +7,11 @@
 //       (frame choice of modules/uberBlast.py:527-529, codon table of modules/configure.py:167-170)
 //   K1a query index: every valid k-mer (k = 12 over ACGT; k = 7 over a 10-letter reduced amino-
 //       acid alphabet) -> (key, position), radix sort, direct-address table key -> first slot
-//   K1b seed scan over the target: table lookup per position, keep only the leftmost seed of an
-//       exact-match run, ungapped X-drop extension in place, emit ungapped HSPs above a cut-off
-//   host  cluster HSPs by (query, target, diagonal) and cut one target window per cluster
+//   K1b seed scan over the target: table lookup per position, seeds expanded densely over the block, only the
+//       leftmost seed of an exact-match run kept, ungapped X-drop extension by the lane for a bounded number of
+//       residues, survivors by one warp per seed; ungapped HSPs above a cut-off are emitted
+//   K1c diagonal binning: HSPs sorted by (query, target, diagonal, position), clustered per (query, target), one
+//       territory-clipped target window cut per cluster, all on the device (the host reads one counter)
 //   K2  windowed Smith-Waterman (score, end, start, traceback) through the batched SW job on
 //       views of the device-resident code arrays (no gather)
 //   host  map to nucleotide coordinates, apply the reference's thresholds, build the hit table
