@@ -39,12 +39,13 @@
 // strip into K spare registers (moves issue on the FMA pipe, which the DP leaves idle).  After
 // the last block the winning lane scans its snapshot for the first column holding the maximum.
 //
-// WAVE = true is the long-alignment variant: the unit of work is one column block (608 columns) of one task, taken
-// by a whole warp (G = 32) from a global list in (task, block) order.  The blocks of a task run as a pipeline spread
-// over the machine: the warp owning block b starts a row as soon as the warp owning block b-1 has published the border
-// cells of that row (global buffer + release/acquire progress counter; the consumer stays >= 32 rows behind and
-// fetches the border in coalesced batches of 32 rows, so the L2 round trip is paid once per batch, not per step).  A 10 kb x 10 kb alignment then takes ~m/R + 32*blocks steps instead of
-// blocks * m/R.  Producers are always fetched before their consumers and never wait on them, so there is no deadlock.
+// WAVE = true is the long-alignment variant: the unit of work is one column block (G * K = 512 columns with the shape
+// pb_sw.cu instantiates) of one task, taken by a whole warp (G = 32) from a global list in (task, block) order.  The
+// blocks of a task run as a pipeline spread over the machine: the warp owning block b starts a row as soon as the warp
+// owning block b-1 has published the border cells of that row (global buffer + release/acquire progress counter; the
+// consumer stays >= 32 rows behind and fetches the border in coalesced batches of 32 rows, so the L2 round trip is paid
+// once per batch, not per step).  A 10 kb x 10 kb alignment then takes ~m/R + 55*blocks steps instead of blocks * m/R.
+// Producers are always fetched before their consumers and never wait on them, so there is no deadlock.
 // The per-block maxima of a task are combined with a 64-bit atomicMax on (score, ~row, ~col).
 //
 // REV = true runs the same DP on the reversed prefixes q[0..m) and t[0..n) (m = qe+1, n = te+1
