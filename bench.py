@@ -297,11 +297,21 @@ def main():
     ap.add_argument('--pairs', type=int, default=1000000, help='pairs per GPU per step (config 2: 1,000,000)')
     ap.add_argument('--cpu-pairs', type=int, default=400000, help='pairs in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--max-seconds', type=int, default=1200, help='hard limit for the whole run (watchdog)')
     ap.add_argument('--no-search', action='store_true', help='skip the per-genome search leg (extra "search" object of the JSON line)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
 
+    # a run that is still going after --max-seconds is wrong (a normal run takes 1-3 minutes): fail fast and loudly instead of
+    # holding the node -- under torchrun the non-zero exit of one rank takes the others down as well
+    def _too_long():
+        sys.stderr.write('bench.py: still running after %d s, giving up (rank %s)\n' % (args.max_seconds, os.environ.get('RANK', '0')))
+        sys.stderr.flush()
+        os._exit(3)
+    wd = threading.Timer(args.max_seconds, _too_long)
+    wd.daemon = True
+    wd.start()
     rank, world, local, pg = dist_setup(args.gpus)
     from peppan_b200 import dist as pbd, seqcodec, sw, workloads
     from peppan_b200._lib import Context
