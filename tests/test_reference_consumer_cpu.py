@@ -39,6 +39,56 @@ def PEPPAN():
     return P
 
 
+_COMP = str.maketrans('ACGT', 'TGCA')
+
+
+def _blastn_tsv_lines(hits, cigar, qn, tn, qseqs, tseqs):
+    """our nucleotide records as blastn `-outfmt "6 qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue
+    score qlen slen qseq sseq"` lines (modules/uberBlast.py:294): gapped qseq / sseq rebuilt from the CIGAR"""
+    lines = []
+    for h in hits:
+        q = qseqs[qn[h['q_id']]][h['q_start'] - 1:h['q_end']]
+        s_all = tseqs[tn[h['s_id']]]
+        s = s_all[h['s_start'] - 1:h['s_end']] if h['s_start'] < h['s_end'] else s_all[h['s_end'] - 1:h['s_start']].translate(_COMP)[::-1]
+        qa, sa, qi, si = [], [], 0, 0
+        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        for op in ops:
+            n, k = int(op) >> 2, int(op) & 3
+            if k == 0:
+                qa.append(q[qi:qi + n]); sa.append(s[si:si + n]); qi += n; si += n
+            elif k == 1:                      # I: extra bases in the query
+                qa.append(q[qi:qi + n]); sa.append('-' * n); qi += n
+            else:                             # D: extra bases in the subject
+                qa.append('-' * n); sa.append(s[si:si + n]); si += n
+        assert qi == len(q) and si == len(s)
+        gapb = sum(int(o) >> 2 for o in ops if int(o) & 3)
+        pident = '%.3f' % (100.0 * (int(h['aln_len']) - int(h['mismatch']) - gapb) / int(h['aln_len']))
+        lines.append('\t'.join(str(x) for x in (qn[h['q_id']], tn[h['s_id']], pident, h['aln_len'], h['mismatch'], h['gapopen'], h['q_start'], h['q_end'],
+                                                 h['s_start'], h['s_end'], '%.3g' % h['evalue'], h['raw_score'], h['q_len'], h['s_len'], ''.join(qa), ''.join(sa))))
+    return lines
+
+
+def _diamond_sam_records(hits, cigar, qn, tn):
+    """our protein records in the terms of a DIAMOND `--outfmt 101` SAM line (modules/uberBlast.py:14-70): query name with its
+    frame, target frame, 1-based amino-acid start on the frame translation, aligned target residues, and the remaining
+    fields (MAPQ, amino-acid CIGAR, ..., NM / ZR / ZS tags at the positions parseDiamond reads them from)"""
+    recs = []
+    for h in hits:
+        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
+        assert all((int(o) >> 2) % 3 == 0 for o in ops)
+        rl = int(h['s_len'])
+        qf = (int(h['q_start']) - 1) % 3 + 1; rf = int(h['frame'])
+        qm = (int(h['q_end']) - int(h['q_start']) + 1) // 3
+        rs = (int(h['s_start']) - rf + 3) // 3 if rf <= 3 else (rl + 7 - int(h['s_start']) - rf) // 3
+        rm = sum((int(o) >> 2) // 3 for o in ops if (int(o) & 3) in (0, 2))
+        nm = int(h['mismatch']) // 3 + sum((int(o) >> 2) // 3 for o in ops if int(o) & 3)
+        aacig = ''.join('%d%s' % ((int(o) >> 2) // 3, 'MID'[int(o) & 3]) for o in ops)
+        recs.append(dict(qname='%s:%d' % (qn[h['q_id']], qf), contig=tn[h['s_id']], rf=rf, rs=rs, rm=rm,
+                         rest=['255', aacig, '*', '0', '0', 'A' * qm, '*', 'AS:i:0', 'NM:i:%d' % nm, 'ZL:i:0', 'ZR:i:%d' % h['raw_score'],
+                               'ZE:f:0', 'ZI:i:0', 'ZF:i:1', 'ZS:i:%d' % ((int(h['q_start']) - qf) // 3 + 1)]))
+    return recs
+
+
 def test_reference_iter_map_bsn_consumes_the_shim_output(PEPPAN, oracle, monkeypatch, tmp_path):
     def fake_search(ctx, qb, qo, rb, ro, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
         hits, cigar = oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov,
@@ -178,27 +228,7 @@ def test_reference_parseblast_reads_our_hits_as_blastn_output(PEPPAN, oracle, tm
     qn, qb, qo = seqio.to_seqset(qitems); tn, tb, to = seqio.to_seqset(titems)
     hits, cigar = oracle.search(qb, qo, tb, to, 1, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
     assert len(hits) > 40 and (hits['s_start'] > hits['s_end']).any()
-    comp = str.maketrans('ACGT', 'TGCA')
-    qd = dict(qitems)
-    lines = []
-    for h in hits:
-        q = qd[qn[h['q_id']]][h['q_start'] - 1:h['q_end']]
-        s = seq[h['s_start'] - 1:h['s_end']] if h['s_start'] < h['s_end'] else seq[h['s_end'] - 1:h['s_start']].translate(comp)[::-1]
-        qa, sa, qi, si = [], [], 0, 0
-        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
-        for op in ops:
-            n, k = int(op) >> 2, int(op) & 3
-            if k == 0:
-                qa.append(q[qi:qi + n]); sa.append(s[si:si + n]); qi += n; si += n
-            elif k == 1:                      # I: extra bases in the query
-                qa.append(q[qi:qi + n]); sa.append('-' * n); qi += n
-            else:                             # D: extra bases in the subject
-                qa.append('-' * n); sa.append(s[si:si + n]); si += n
-        assert qi == len(q) and si == len(s)
-        gapb = sum(int(o) >> 2 for o in ops if int(o) & 3)
-        pident = '%.3f' % (100.0 * (int(h['aln_len']) - int(h['mismatch']) - gapb) / int(h['aln_len']))
-        lines.append('\t'.join(str(x) for x in (qn[h['q_id']], tn[h['s_id']], pident, h['aln_len'], h['mismatch'], h['gapopen'], h['q_start'], h['q_end'],
-                                                 h['s_start'], h['s_end'], '%.3g' % h['evalue'], h['raw_score'], h['q_len'], h['s_len'], ''.join(qa), ''.join(sa))))
+    lines = _blastn_tsv_lines(hits, cigar, qn, tn, dict(qitems), dict(titems))
     qry = os.path.join(tmp_path, 'qry.fa')
     prepared = os.path.join(tmp_path, 'prepared.tsv')
     open(prepared, 'w').write('\n'.join(lines) + '\n')
@@ -228,20 +258,8 @@ def test_reference_parsediamond_reads_our_hits_as_sam(PEPPAN, oracle, tmp_path):
     qn, qb, qo = seqio.to_seqset(qitems); tn, tb, to = seqio.to_seqset(titems)
     hits, cigar = oracle.search(qb, qo, tb, to, 2, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
     assert len(hits) > 40 and (hits['frame'] > 3).any() and (hits['frame'] <= 3).any()
-    rl = len(seq)
-    lines = ['@HD\tVN:1.5']
-    for h in hits:
-        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
-        assert all((int(o) >> 2) % 3 == 0 for o in ops)
-        aacig = ''.join('%d%s' % ((int(o) >> 2) // 3, 'MID'[int(o) & 3]) for o in ops)
-        qf = (int(h['q_start']) - 1) % 3 + 1; rf = int(h['frame'])
-        qs_aa = (int(h['q_start']) - qf) // 3 + 1
-        qm = (int(h['q_end']) - int(h['q_start']) + 1) // 3
-        rs = (int(h['s_start']) - rf + 3) // 3 if rf <= 3 else (rl + 7 - int(h['s_start']) - rf) // 3
-        gap_aa = sum((int(o) >> 2) // 3 for o in ops if int(o) & 3)
-        nm = int(h['mismatch']) // 3 + gap_aa
-        lines.append('\t'.join(str(x) for x in ('%s:%d' % (qn[h['q_id']], qf), 0, '%s:%d:0' % (tn[h['s_id']], rf), rs, 255, aacig, '*', 0, 0, 'A' * qm, '*',
-                                                 'AS:i:0', 'NM:i:%d' % nm, 'ZL:i:0', 'ZR:i:%d' % h['raw_score'], 'ZE:f:0', 'ZI:i:0', 'ZF:i:1', 'ZS:i:%d' % qs_aa)))
+    lines = ['@HD\tVN:1.5'] + ['\t'.join([r['qname'], '0', '%s:%d:0' % (r['contig'], r['rf']), str(r['rs'])] + r['rest'])
+                               for r in _diamond_sam_records(hits, cigar, qn, tn)]
     fn = os.path.join(tmp_path, 'aaMatch.0')
     open(fn, 'w').write('\n'.join(lines) + '\n')
     out = refmod.parseDiamond([fn, dict(titems), dict(qitems), 0.4, 50, 0.25])
@@ -305,43 +323,12 @@ def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(P
     open(qry, 'w').write(''.join('>%s\n%s\n' % x for x in qitems)); open(ref, 'w').write(''.join('>%s\n%s\n' % x for x in titems))
     qn, qb, qo = seqio.to_seqset(qitems); tn, tb, to = seqio.to_seqset(titems)
     qd, td = dict(qitems), dict(titems)
-    comp = str.maketrans('ACGT', 'TGCA')
     # ---- our hits in the tools' formats
     hits, cigar = oracle.search(qb, qo, tb, to, 1, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
-    lines = []
-    for h in hits:
-        s_all = td[tn[h['s_id']]]
-        q = qd[qn[h['q_id']]][h['q_start'] - 1:h['q_end']]
-        s = s_all[h['s_start'] - 1:h['s_end']] if h['s_start'] < h['s_end'] else s_all[h['s_end'] - 1:h['s_start']].translate(comp)[::-1]
-        qa, sa, qi, si = [], [], 0, 0
-        ops = cigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
-        for op in ops:
-            n, k = int(op) >> 2, int(op) & 3
-            if k == 0:
-                qa.append(q[qi:qi + n]); sa.append(s[si:si + n]); qi += n; si += n
-            elif k == 1:
-                qa.append(q[qi:qi + n]); sa.append('-' * n); qi += n
-            else:
-                qa.append('-' * n); sa.append(s[si:si + n]); si += n
-        gapb = sum(int(o) >> 2 for o in ops if int(o) & 3)
-        pident = '%.3f' % (100.0 * (int(h['aln_len']) - int(h['mismatch']) - gapb) / int(h['aln_len']))
-        lines.append('\t'.join(str(x) for x in (qn[h['q_id']], tn[h['s_id']], pident, h['aln_len'], h['mismatch'], h['gapopen'], h['q_start'], h['q_end'],
-                                                 h['s_start'], h['s_end'], '%.3g' % h['evalue'], h['raw_score'], h['q_len'], h['s_len'], ''.join(qa), ''.join(sa))))
+    lines = _blastn_tsv_lines(hits, cigar, qn, tn, qd, td)
     tsv = os.path.join(tmp_path, 'prepared.tsv'); open(tsv, 'w').write('\n'.join(lines) + '\n')
     phits, pcigar = oracle.search(qb, qo, tb, to, 2, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
-    recs = []
-    for h in phits:
-        ops = pcigar[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
-        rl = int(h['s_len'])
-        qf = (int(h['q_start']) - 1) % 3 + 1; rf = int(h['frame'])
-        qm = (int(h['q_end']) - int(h['q_start']) + 1) // 3
-        rs = (int(h['s_start']) - rf + 3) // 3 if rf <= 3 else (rl + 7 - int(h['s_start']) - rf) // 3
-        rm = sum((int(o) >> 2) // 3 for o in ops if (int(o) & 3) in (0, 2))
-        nm = int(h['mismatch']) // 3 + sum((int(o) >> 2) // 3 for o in ops if int(o) & 3)
-        aacig = ''.join('%d%s' % ((int(o) >> 2) // 3, 'MID'[int(o) & 3]) for o in ops)
-        recs.append(dict(qname='%s:%d' % (qn[h['q_id']], qf), contig=tn[h['s_id']], rf=rf, rs=rs, rm=rm,
-                         rest=['255', aacig, '*', '0', '0', 'A' * qm, '*', 'AS:i:0', 'NM:i:%d' % nm, 'ZL:i:0', 'ZR:i:%d' % h['raw_score'],
-                               'ZE:f:0', 'ZI:i:0', 'ZF:i:1', 'ZS:i:%d' % ((int(h['q_start']) - qf) // 3 + 1)]))
+    recs = _diamond_sam_records(phits, pcigar, qn, tn)
     js = os.path.join(tmp_path, 'prepared.json'); json.dump(recs, open(js, 'w'))
     tools = {}
     for name, body in (('blastn', _FAKE_BLASTN.format(py=sys.executable, tsv=tsv)), ('diamond', _FAKE_DIAMOND.format(py=sys.executable, js=js)),
@@ -379,40 +366,10 @@ def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(P
     # get_similar_pairs' command line on the same files (genome as both sides would be odd: exemplars vs exemplars), with the
     # reference's process pool (-p) and four query chunks (-t 4): 16 columns, no merge groups, no overlap list
     hits2, cigar2 = oracle.search(qb, qo, qb, qo, 1, seqcodec.BLOSUM62.reshape(-1), min_id=0.45, min_cov=50, min_ratio=0.25)
-    lines = []
-    for h in hits2:
-        q = qd[qn[h['q_id']]][h['q_start'] - 1:h['q_end']]
-        s_all = qd[qn[h['s_id']]]
-        s = s_all[h['s_start'] - 1:h['s_end']] if h['s_start'] < h['s_end'] else s_all[h['s_end'] - 1:h['s_start']].translate(comp)[::-1]
-        qa, sa, qi, si = [], [], 0, 0
-        ops = cigar2[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
-        for op in ops:
-            n, k = int(op) >> 2, int(op) & 3
-            if k == 0:
-                qa.append(q[qi:qi + n]); sa.append(s[si:si + n]); qi += n; si += n
-            elif k == 1:
-                qa.append(q[qi:qi + n]); sa.append('-' * n); qi += n
-            else:
-                qa.append('-' * n); sa.append(s[si:si + n]); si += n
-        gapb = sum(int(o) >> 2 for o in ops if int(o) & 3)
-        pident = '%.3f' % (100.0 * (int(h['aln_len']) - int(h['mismatch']) - gapb) / int(h['aln_len']))
-        lines.append('\t'.join(str(x) for x in (qn[h['q_id']], qn[h['s_id']], pident, h['aln_len'], h['mismatch'], h['gapopen'], h['q_start'], h['q_end'],
-                                                 h['s_start'], h['s_end'], '%.3g' % h['evalue'], h['raw_score'], h['q_len'], h['s_len'], ''.join(qa), ''.join(sa))))
+    lines = _blastn_tsv_lines(hits2, cigar2, qn, qn, qd, qd)
     open(tsv, 'w').write('\n'.join(lines) + '\n')
     phits2, pcigar2 = oracle.search(qb, qo, qb, qo, 2, seqcodec.BLOSUM62.reshape(-1), min_id=0.45, min_cov=50, min_ratio=0.25)
-    recs = []
-    for h in phits2:
-        ops = pcigar2[h['cigar_off']:h['cigar_off'] + h['cigar_n']]
-        rl = int(h['s_len'])
-        qf = (int(h['q_start']) - 1) % 3 + 1; rf = int(h['frame'])
-        qm = (int(h['q_end']) - int(h['q_start']) + 1) // 3
-        rs = (int(h['s_start']) - rf + 3) // 3 if rf <= 3 else (rl + 7 - int(h['s_start']) - rf) // 3
-        rm = sum((int(o) >> 2) // 3 for o in ops if (int(o) & 3) in (0, 2))
-        nm = int(h['mismatch']) // 3 + sum((int(o) >> 2) // 3 for o in ops if int(o) & 3)
-        aacig = ''.join('%d%s' % ((int(o) >> 2) // 3, 'MID'[int(o) & 3]) for o in ops)
-        recs.append(dict(qname='%s:%d' % (qn[h['q_id']], qf), contig=qn[h['s_id']], rf=rf, rs=rs, rm=rm,
-                         rest=['255', aacig, '*', '0', '0', 'A' * qm, '*', 'AS:i:0', 'NM:i:%d' % nm, 'ZL:i:0', 'ZR:i:%d' % h['raw_score'],
-                               'ZE:f:0', 'ZI:i:0', 'ZF:i:1', 'ZS:i:%d' % ((int(h['q_start']) - qf) // 3 + 1)]))
+    recs = _diamond_sam_records(phits2, pcigar2, qn, qn)
     json.dump(recs, open(js, 'w'))
     args2 = '-r {0} -q {0} --blastn --diamond -s 1 --min_id 0.45 --min_cov 50 -t 4 --min_ratio 0.25 -e 3,3 -p --gtable 11'.format(qry).split()
     with warnings.catch_warnings():
