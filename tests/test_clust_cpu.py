@@ -7,21 +7,10 @@ import pytest
 
 from peppan_b200 import clust, seqio
 
-from test_clust_gpu import _genes, _oracle_clusters
+from test_clust_gpu import _genes
 
 
-@pytest.fixture()
-def oracle_cluster(monkeypatch, oracle):
-    def fake_cluster(ctx, buf, off, identity, coverage, translate=False, gtable=11):
-        n = len(off) - 1
-        items = [(str(i), buf[off[i]:off[i + 1]].tobytes().decode()) for i in range(n)]
-        rep = _oracle_clusters(oracle, items, identity, coverage, translate=translate)
-        return rep, dict(n_reps=int((rep == np.arange(n)).sum()))
-    monkeypatch.setattr(clust, 'cluster', fake_cluster)
-    monkeypatch.setattr(clust, 'get_context', lambda: None)
-
-
-def test_getclust_files_cpu(oracle_cluster, tmp_path):
+def test_getclust_files_cpu(oracle_as_cluster, tmp_path):
     items = _genes(3, n_anc=25)
     fa = os.path.join(tmp_path, 'genes.fa')
     with open(fa, 'w') as f:

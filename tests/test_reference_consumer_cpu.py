@@ -89,13 +89,7 @@ def _diamond_sam_records(hits, cigar, qn, tn):
     return recs
 
 
-def test_reference_iter_map_bsn_consumes_the_shim_output(PEPPAN, oracle, monkeypatch, tmp_path):
-    def fake_search(ctx, qb, qo, rb, ro, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
-        hits, cigar = oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov,
-                                    min_ratio=min_ratio, gtable=gtable, max_hits=max_hits)
-        return hits, cigar, dict(kernel_launches=0)
-    monkeypatch.setattr(ub._srch, 'search', fake_search)
-    monkeypatch.setattr(ub, 'get_context', lambda: None)
+def test_reference_iter_map_bsn_consumes_the_shim_output(PEPPAN, oracle_as_search, monkeypatch, tmp_path):
     monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)          # the module swap: PEPPAN calls our shim
     if not hasattr(np.lib.npyio, 'format'):                          # the reference predates numpy 2 (PEPPAN.py:41, :89)
         monkeypatch.setattr(np.lib.npyio, 'format', np.lib.format, raising=False)
@@ -136,14 +130,8 @@ def test_reference_iter_map_bsn_consumes_the_shim_output(PEPPAN, oracle, monkeyp
     assert sum(1 for g in bsn for tab in g[6] if tab[1] == 1001 and tab[10] > 0.6) >= 0.8 * len(rows)
 
 
-def test_reference_get_similar_pairs_consumes_the_shim_output(PEPPAN, oracle, monkeypatch, tmp_path):
+def test_reference_get_similar_pairs_consumes_the_shim_output(PEPPAN, oracle_as_search, monkeypatch, tmp_path):
     """PEPPAN.get_similar_pairs (PEPPAN.py:194-294): exemplar-vs-exemplar all-vs-all through the shim (-s 1 -e 3,3 -p)"""
-    def fake_search(ctx, qb, qo, rb, ro, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
-        hits, cigar = oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov,
-                                    min_ratio=min_ratio, gtable=gtable, max_hits=max_hits)
-        return hits, cigar, dict(kernel_launches=0)
-    monkeypatch.setattr(ub._srch, 'search', fake_search)
-    monkeypatch.setattr(ub, 'get_context', lambda: None)
     monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)
     monkeypatch.setattr(PEPPAN, 'pool', None, raising=False)         # the worker pool PEPPAN hands over as extPool (ignored by the shim)
 
@@ -175,19 +163,10 @@ def test_reference_get_similar_pairs_consumes_the_shim_output(PEPPAN, oracle, mo
     assert all(({i, 100 + i} & merged) for i in range(10)) and all(9000 <= int(v) <= 10000 for v in clu[:, 2])
 
 
-def test_reference_iterclust_drives_the_getclust_shim(PEPPAN, oracle, monkeypatch, tmp_path):
+def test_reference_iterclust_drives_the_getclust_shim(PEPPAN, oracle_as_cluster, monkeypatch, tmp_path):
     """PEPPAN.iterClust (PEPPAN.py:1777-1792): the identity ladder 1.00 .. 0.90 through this repository's getClust (module
     swap), pb_cluster standing in by the oracle's search + greedy (test only)"""
     from peppan_b200 import clust as pclust
-    from test_clust_gpu import _oracle_clusters
-
-    def fake_cluster(ctx, buf, off, identity, coverage, translate=False, gtable=11):
-        n = len(off) - 1
-        items = [(str(i), buf[off[i]:off[i + 1]].tobytes().decode()) for i in range(n)]
-        rep = _oracle_clusters(oracle, items, float(identity), float(coverage), translate=translate)
-        return rep, dict(n_reps=int((rep == np.arange(n)).sum()))
-    monkeypatch.setattr(pclust, 'cluster', fake_cluster)
-    monkeypatch.setattr(pclust, 'get_context', lambda: None)
     monkeypatch.setattr(PEPPAN, 'getClust', pclust.getClust)
 
     rng = np.random.default_rng(5)
@@ -305,7 +284,7 @@ with open(out, 'w') as f:
 '''
 
 
-def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(PEPPAN, oracle, monkeypatch, tmp_path):
+def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(PEPPAN, oracle, oracle_as_search, monkeypatch, tmp_path):
     """The whole of the reference's modules/uberBlast.py (uberBlast -> RunBlast.run -> runBlast / runDiamond -> poolBlast /
     parseDiamond -> reScore -> ovlFilter -> linearMerge -> fixEnd -> returnOverlap) is executed with its three external
     tools replaced by stand-ins that answer with OUR hits in the tools' own output formats; its final table and overlap
@@ -344,12 +323,6 @@ def test_reference_uberblast_with_tools_emulated_from_our_hits_equals_the_shim(P
         warnings.simplefilter('ignore')
         rtab, rovl = refmod.uberBlast(args)
 
-    def fake_search(ctx, qb_, qo_, rb_, ro_, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
-        h_, c_ = oracle.search(qb_, qo_, rb_, ro_, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov, min_ratio=min_ratio,
-                               gtable=gtable, max_hits=max_hits)
-        return h_, c_, dict(kernel_launches=0)
-    monkeypatch.setattr(ub._srch, 'search', fake_search)
-    monkeypatch.setattr(ub, 'get_context', lambda: None)
     otab, oovl = ub.uberBlast(args)
 
     def canon(tab, ovl):
@@ -412,13 +385,13 @@ elif a[0] == 'createtsv':
 '''
 
 
-def test_reference_getclust_with_mmseqs_emulated_from_our_clustering_equals_the_shim(PEPPAN, oracle, monkeypatch, tmp_path):
+def test_reference_getclust_with_mmseqs_emulated_from_our_clustering_equals_the_shim(PEPPAN, oracle_as_cluster, monkeypatch, tmp_path):
     """The reference's getClust (modules/clust.py:34-111: three rounds of createdb / linclust / createtsv, re-election of the
     first member in file order, closure) driven by a stand-in `mmseqs` that clusters like pb_cluster; its two output files
     must equal the files of this repository's getClust."""
     import stat as _stat
     from peppan_b200 import clust as pclust
-    from test_clust_gpu import _genes, _oracle_clusters
+    from test_clust_gpu import _genes
     refclust = sys.modules['modules.clust'] if 'modules.clust' in sys.modules else __import__('modules.clust', fromlist=['x'])
     items = _genes(6, n_anc=20)
     fa = os.path.join(tmp_path, 'genes.fa')
@@ -433,13 +406,6 @@ def test_reference_getclust_with_mmseqs_emulated_from_our_clustering_equals_the_
     monkeypatch.chdir(tmp_path)
     rex, rtab = refclust.getClust(os.path.join(tmp_path, 'ref'), fa, dict(identity=0.9, coverage=0.8, n_thread=2, translate=False))
 
-    def fake_cluster(ctx, buf, off, identity, coverage, translate=False, gtable=11):
-        n = len(off) - 1
-        its = [(str(i), buf[off[i]:off[i + 1]].tobytes().decode()) for i in range(n)]
-        rep = _oracle_clusters(oracle, its, float(identity), float(coverage), translate=translate)
-        return rep, dict(n_reps=int((rep == np.arange(n)).sum()))
-    monkeypatch.setattr(pclust, 'cluster', fake_cluster)
-    monkeypatch.setattr(pclust, 'get_context', lambda: None)
     oex, otab = pclust.getClust(os.path.join(tmp_path, 'ours'), fa, dict(identity=0.9, coverage=0.8, n_thread=2, translate=False))
     assert open(rtab).read() == open(otab).read()
     assert open(rex).read() == open(oex).read()

@@ -29,21 +29,6 @@ def files(tmp_path_factory):
     return dict(qry=qry, ref=ref, pool=pool, annot=annot, glen=len(seq))
 
 
-@pytest.fixture()
-def oracle_search(monkeypatch, oracle):
-    calls = []
-
-    def fake_search(ctx, qb, qo, rb, ro, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0, allgather=False):
-        hits, cigar = oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=min_id, min_cov=min_cov,
-                                    min_ratio=min_ratio, gtable=gtable, max_hits=max_hits)
-        calls.append(mode)
-        return hits, cigar, dict(kernel_launches=0)
-
-    monkeypatch.setattr(ub._srch, 'search', fake_search)
-    monkeypatch.setattr(ub, 'get_context', lambda: None)
-    return calls
-
-
 def _cigar_spans(c):
     q = s = 0
     for n, t in re.findall(r'(\d+)([MID])', c):
@@ -55,10 +40,10 @@ def _cigar_spans(c):
     return q, s
 
 
-def test_iter_map_bsn_flags_cpu(files, oracle_search):
+def test_iter_map_bsn_flags_cpu(files, oracle_as_search):
     args = '-r {ref} -q {qry} -f -m -O --blastn --diamond --min_id 0.4 --min_cov 50 --min_ratio 0.25 --merge_gap 600 --merge_diff 1.5 -t 1 -s 1 -e 0,3 --gtable 11'.format(**files).split()
     blastab, overlap = ub.uberBlast(args)
-    assert oracle_search == [1, 2]
+    assert oracle_as_search == [1, 2]
     assert blastab.dtype == object and blastab.shape[1] == 17 and overlap.shape[1] == 3 and overlap.dtype.kind == 'i'
     assert len(blastab) > 60
     keys = [(r[0], r[1], r[11]) for r in blastab]
@@ -98,7 +83,7 @@ def test_iter_map_bsn_flags_cpu(files, oracle_search):
     assert sum(1 for a in planted if got.get(a[0], 0) >= 0.8) == len(planted)
 
 
-def test_get_similar_pairs_flags_cpu(files, oracle_search):
+def test_get_similar_pairs_flags_cpu(files, oracle_as_search):
     args = '-r {qry} -q {qry} --blastn --diamond -s 1 --min_id 0.45 --min_cov 50 -t 4 --min_ratio 0.25 -e 3,3 -p --gtable 11'.format(**files).split()
     blastab = ub.uberBlast(args, extPool='ignored')
     assert blastab.shape[1] == 16
@@ -106,11 +91,11 @@ def test_get_similar_pairs_flags_cpu(files, oracle_search):
     assert len(set(r[0] for r in selfhits)) == 120 and all(r[2] == 1.0 for r in selfhits)
 
 
-def test_raw_scores_and_output_file_cpu(files, oracle_search, tmp_path):
+def test_raw_scores_and_output_file_cpu(files, oracle_as_search, tmp_path):
     # no re-scoring: integer raw scores keep their type through the Python stages; -o writes one line per row
     path = os.path.join(tmp_path, 'o.tsv')
     res = ub.uberBlast(['-r', files['ref'], '-q', files['qry'], '--diamondSELF', '--blastn', '-o', path, '-e', '0,0'])
-    assert oracle_search == [1, 3] and res.shape[1] == 16 and len(res) > 0
+    assert oracle_as_search == [1, 3] and res.shape[1] == 16 and len(res) > 0
     assert all(isinstance(r[11], int) for r in res)
     assert len(open(path).read().strip().split('\n')) == len(res)
     assert ub.uberBlast(['-r', files['ref'], '-q', files['qry']]).shape == (0, 16)
@@ -166,11 +151,11 @@ def test_row_builders_equal_the_per_hit_statement(files, oracle):
     assert ub.rows_from_nt_hits(empty, cigar[:0], qn, rn, 0.3, 40, 0.05) == [] and ub.rows_from_prot_hits(empty, cigar[:0], qn, rn, 0.3) == []
 
 
-def test_nucl_flag_sets_cpu(files, oracle_search):
+def test_nucl_flag_sets_cpu(files, oracle_as_search):
     """PEPPAN --nucl: blastn only, no re-scoring (PEPPAN.py:226, :768) -- raw integer scores through filter / merge / overlap"""
     args = '-r {ref} -q {qry} -f -m -O --blastn --min_id 0.4 --min_cov 50 --min_ratio 0.25 --merge_gap 600 --merge_diff 1.5 -t 1 -e 0,3 --gtable 11'.format(**files).split()
     blastab, overlap = ub.uberBlast(args)
-    assert oracle_search == [1] and blastab.shape[1] == 17 and overlap.shape[1] == 3 and len(blastab) > 60
+    assert oracle_as_search == [1] and blastab.shape[1] == 17 and overlap.shape[1] == 3 and len(blastab) > 60
     for r in blastab:
         assert isinstance(r[11], int) and isinstance(r[14], str) and r[15] in r[16][3:]
         qspan, sspan = _cigar_spans(r[14])
