@@ -29,6 +29,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -197,8 +198,16 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
             free(fill);
             /* ---- seed scan + ungapped extension ---- */
             int64_t nh = 0, hcap = 1 << 16; hsp_t* hs = malloc(sizeof(hsp_t) * hcap);
+            /* EXPERIMENT (off unless ORC_DIAG_COVERED=1; not part of the specification the GPU path implements): the
+             * BLAST-style rule "a seed that lies inside the HSP last produced on its (query, diagonal) is not extended again".
+             * Used by tools/diag_rule_study.py to measure what the rule would save and whether it changes the hit table. */
+            const int diag_rule = getenv("ORC_DIAG_COVERED") && atoi(getenv("ORC_DIAG_COVERED")) != 0;
+            const int64_t DH = 1 << 22;                     /* open-addressing table (query, diagonal) -> covered end */
+            int64_t* dkey = NULL; int64_t* dend = NULL; long long n_ext = 0, n_skip = 0;
+            if (diag_rule) { dkey = malloc(sizeof(int64_t) * DH); dend = malloc(sizeof(int64_t) * DH); }
             for (int64_t t = 0; t < NT; ++t) {
                 const uint8_t* T = tsq[t]; int64_t TL = tlen[t];
+                if (diag_rule) memset(dkey, 0xff, sizeof(int64_t) * DH);
                 for (int64_t tp = 0; tp + K <= TL; ++tp) {
                     int64_t key = 0; int ok = 1;
                     for (int x = 0; x < K; ++x) { uint8_t sc = seedmap[T[tp + x]]; if (sc == 255) { ok = 0; break; } key = key * BASE + sc; }
@@ -206,6 +215,15 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                     for (int64_t o = head[key]; o < head[key + 1]; ++o) {
                         int qi = eq[o]; int64_t qp = ep[o]; const uint8_t* Q = qs[qi]; int64_t QL = qlen[qi];
                         if (qp > 0 && tp > 0) { uint8_t sa = seedmap[Q[qp - 1]], sb = seedmap[T[tp - 1]]; if (sa != 255 && sa == sb) continue; }
+                        int64_t dslot = -1;
+                        if (diag_rule) {
+                            const int64_t dk = ((int64_t)qi << 32) | (uint32_t)(int32_t)(tp - qp);
+                            dslot = (int64_t)(((uint64_t)dk * 0x9E3779B97F4A7C15ull) >> 42);
+                            while (dkey[dslot] != -1 && dkey[dslot] != dk) dslot = (dslot + 1) & (DH - 1);
+                            if (dkey[dslot] == dk && tp + K <= dend[dslot]) { ++n_skip; continue; }
+                            dkey[dslot] = dk; dend[dslot] = 0;
+                        }
+                        ++n_ext;
                         int score = 0;
                         for (int x = 0; x < K; ++x) score += mat[Q[qp + x] * 32 + T[tp + x]];
                         int best = score, cur = score, rlen = K;
@@ -218,6 +236,7 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                             cur += mat[Q[qp - x] * 32 + T[tp - x]];
                             if (cur > lbest) { lbest = cur; llen = (int)x; } else if (lbest - cur > XDROP) break;
                         }
+                        if (diag_rule) dend[dslot] = tp + rlen;      /* right end of what this seed reached on the diagonal */
                         if (lbest < MINU) continue;
                         if (nh == hcap) { hcap *= 2; hs = realloc(hs, sizeof(hsp_t) * hcap); }
                         hsp_t h; h.qid = qi; h.tid = (int)t; h.qs = (int)(qp - llen); h.qe = h.qs + rlen + llen;
@@ -226,6 +245,8 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                     }
                 }
             }
+            if (getenv("ORC_SEED_STATS")) fprintf(stderr, "[orc_search] mode %d: seeds extended %lld, skipped by the diagonal rule %lld, ungapped HSPs %lld\n", mode, n_ext, n_skip, (long long)nh);
+            free(dkey); free(dend);
             /* ---- clusters -> windows -> SW ---- */
             qsort(hs, nh, sizeof(hsp_t), cmp_hsp);
             clu_t* cl = malloc(sizeof(clu_t) * (nh + 1)); int64_t ncl = 0;
