@@ -202,6 +202,10 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
              * BLAST-style rule "a seed that lies inside the HSP last produced on its (query, diagonal) is not extended again".
              * Used by tools/diag_rule_study.py to measure what the rule would save and whether it changes the hit table. */
             const int diag_rule = getenv("ORC_DIAG_COVERED") && atoi(getenv("ORC_DIAG_COVERED")) != 0;
+            /* EXPERIMENT (off unless ORC_MIN_SEED_SCORE is set): seeds whose own substitution score is below a threshold are
+             * not extended -- what a cheaper pre-filter in front of the X-drop extension would do (tools/seed_filter_study.py) */
+            const int min_seed_score = getenv("ORC_MIN_SEED_SCORE") ? atoi(getenv("ORC_MIN_SEED_SCORE")) : -1000000;
+            long long n_lowseed = 0;
             const int64_t DH = 1 << 22;                     /* open-addressing table (query, diagonal) -> covered end */
             int64_t* dkey = NULL; int64_t* dend = NULL; long long n_ext = 0, n_skip = 0;
             if (diag_rule) { dkey = malloc(sizeof(int64_t) * DH); dend = malloc(sizeof(int64_t) * DH); }
@@ -223,9 +227,10 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                             if (dkey[dslot] == dk && tp + K <= dend[dslot]) { ++n_skip; continue; }
                             dkey[dslot] = dk; dend[dslot] = 0;
                         }
-                        ++n_ext;
                         int score = 0;
                         for (int x = 0; x < K; ++x) score += mat[Q[qp + x] * 32 + T[tp + x]];
+                        if (score < min_seed_score) { ++n_lowseed; continue; }     /* EXPERIMENT, off by default (threshold INT_MIN) */
+                        ++n_ext;
                         int best = score, cur = score, rlen = K;
                         for (int64_t x = K; qp + x < QL && tp + x < TL; ++x) {
                             cur += mat[Q[qp + x] * 32 + T[tp + x]];
@@ -245,7 +250,7 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                     }
                 }
             }
-            if (getenv("ORC_SEED_STATS")) fprintf(stderr, "[orc_search] mode %d: seeds extended %lld, skipped by the diagonal rule %lld, ungapped HSPs %lld\n", mode, n_ext, n_skip, (long long)nh);
+            if (getenv("ORC_SEED_STATS")) fprintf(stderr, "[orc_search] mode %d: seeds extended %lld, skipped by the diagonal rule %lld, ungapped HSPs %lld, below the seed-score threshold %lld\n", mode, n_ext, n_skip, (long long)nh, n_lowseed);
             free(dkey); free(dend);
             /* ---- clusters -> windows -> SW ---- */
             qsort(hs, nh, sizeof(hsp_t), cmp_hsp);
