@@ -158,6 +158,64 @@ int orc_sw_align(const uint8_t* q, int m, const uint8_t* t, int n, const int8_t*
     return needed;
 }
 
+/*
+ * VERIFICATION AID for the exact score-bounded band (not used by any parity test of the product):
+ * the traceback of orc_sw_align recomputed on the alignment box only (q[0..M), t[0..N) = the aligned segments, score S)
+ * with the reverse DP restricted to the cells whose diagonal offset j - i lies in [-imax, +dmax]; cells outside the band
+ * count as H = 0, E = F = -inf.  If the band holds every co-optimal path the CIGAR must equal the full-matrix one.
+ * Returns the number of ops, or -1 if the banded DP does not reach S at the box corner.
+ */
+int orc_band_trace(const uint8_t* q, int M, const uint8_t* t, int N, const int8_t* mat, int go, int ge, int S, int imax_, int dmax_,
+                   uint32_t* cigar, int cigar_cap)
+{
+    int goe = go + ge;
+    size_t cells = (size_t)(M + 1) * (size_t)(N + 1);
+    int* H = (int*)malloc(sizeof(int) * cells * 3);
+    int* E = H + cells; int* F = E + cells;
+#define IDX(i, j) ((size_t)(i) * (size_t)(N + 1) + (size_t)(j))
+    for (size_t k = 0; k < cells; ++k) { H[k] = 0; E[k] = ORC_NEG; F[k] = ORC_NEG; }
+    for (int i = 1; i <= M; ++i) {
+        const int8_t* row = mat + 32 * q[M - i];
+        int jlo = i - imax_ < 1 ? 1 : i - imax_, jhi = i + dmax_ > N ? N : i + dmax_;
+        for (int j = jlo; j <= jhi; ++j) {
+            int e = imax(E[IDX(i - 1, j)] - ge, H[IDX(i - 1, j)] - goe);
+            int f = imax(F[IDX(i, j - 1)] - ge, H[IDX(i, j - 1)] - goe);
+            int h = imax(imax(0, H[IDX(i - 1, j - 1)] + row[t[N - j]]), imax(e, f));
+            H[IDX(i, j)] = h; E[IDX(i, j)] = e; F[IDX(i, j)] = f;
+        }
+    }
+    if (H[IDX(M, N)] != S) { free(H); return -1; }
+    int nops = 0, i = M, j = N, state = 0, cur_op = -1, cur_len = 0;
+#define EMIT(op) do { if (cur_op == (op)) cur_len++; else { \
+        if (cur_op >= 0) { if (cigar && nops < cigar_cap) cigar[nops] = ((uint32_t)cur_len << 2) | (uint32_t)cur_op; nops++; } \
+        cur_op = (op); cur_len = 1; } } while (0)
+    while (i > 0 && j > 0) {
+        if (state == 0) {
+            int h = H[IDX(i, j)];
+            if (h == 0) break;
+            int a = q[M - i], b = t[N - j];
+            if (h == H[IDX(i - 1, j - 1)] + mat[32 * a + b]) { EMIT(0); i--; j--; }
+            else if (h == E[IDX(i, j)]) state = 1;
+            else state = 2;
+        } else if (state == 1) {
+            int e = E[IDX(i, j)];
+            EMIT(1);
+            if (e == H[IDX(i - 1, j)] - goe) state = 0;
+            i--;
+        } else {
+            int f = F[IDX(i, j)];
+            EMIT(2);
+            if (f == H[IDX(i, j - 1)] - goe) state = 0;
+            j--;
+        }
+    }
+    if (cur_op >= 0) { if (cigar && nops < cigar_cap) cigar[nops] = ((uint32_t)cur_len << 2) | (uint32_t)cur_op; nops++; }
+    free(H);
+#undef IDX
+#undef EMIT
+    return nops;
+}
+
 /* Score + end only (what the forward CUDA kernel computes). */
 void orc_sw_score(const uint8_t* q, int m, const uint8_t* t, int n, const int8_t* mat,
                   int go, int ge, int32_t* S, int32_t* qe, int32_t* te)

@@ -76,6 +76,18 @@ def sw_score_batch(q, qoff, t, toff, mat, go, ge, nthreads=1):
     return S, qe, te
 
 
+def band_trace(q_box, t_box, mat, go, ge, S, imax, dmax):
+    """orc_band_trace: CIGAR of the alignment box recomputed inside the diagonal band [-imax, +dmax]; None if the banded DP
+    misses the score"""
+    q_box = np.ascontiguousarray(q_box, dtype=np.uint8); t_box = np.ascontiguousarray(t_box, dtype=np.uint8)
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    cap = len(q_box) + len(t_box) + 2
+    cg = np.zeros(cap, dtype=np.uint32)
+    n = lib().orc_band_trace(_p(q_box), C.c_int(len(q_box)), _p(t_box), C.c_int(len(t_box)), _p(mat), C.c_int(go), C.c_int(ge), C.c_int(int(S)),
+                             C.c_int(int(imax)), C.c_int(int(dmax)), _p(cg), C.c_int(cap))
+    return None if n < 0 else cg[:n].copy()
+
+
 def transeq_frame(nt_ascii, frame, table=11):
     nt = np.frombuffer(nt_ascii.upper().encode(), dtype=np.uint8) if isinstance(nt_ascii, str) else nt_ascii
     nt = np.ascontiguousarray(nt)
