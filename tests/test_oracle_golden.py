@@ -193,3 +193,31 @@ def test_score_bounded_band_reproduces_the_traceback(oracle):
             n += 1
         assert n > 100
     assert narrow_fail > 20
+
+
+def test_strip_layout_model_of_the_banded_traceback(oracle):
+    """tools/model_banded_trace.py -- the block / lane / step / word-address arithmetic planned for the banded CUDA traceback --
+    reproduces the oracle's CIGARs through its own direction-word buffer, for several strip shapes"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    from model_banded_trace import banded_trace
+    checked = 0
+    for (mat, go, ge, nsym, seed) in ((seqcodec.protein_matrix(), 11, 1, 20, 23), (seqcodec.nt_matrix(), 6, 2, 4, 24)):
+        m2 = mat.reshape(32, 32).astype(int).tolist()
+        self_scores = np.diag(mat.reshape(32, 32)).astype(int)
+        s_min = int(self_scores[:nsym].min())
+        qs, ts = workloads.random_pairs(40, seed=seed, nsym_real=nsym, min_len=20, max_len=150, related=0.9)
+        q, qoff = oracle.concat(qs); t, toff = oracle.concat(ts)
+        aln, cigs = oracle.sw_batch(q, qoff, t, toff, mat.reshape(-1), go, ge)
+        for p in range(len(qs)):
+            a = aln[p]
+            if a['score'] <= 0:
+                continue
+            qbox = qs[p][a['qs']:a['qe'] + 1].tolist(); tbox = ts[p][a['ts']:a['te'] + 1].tolist()
+            i_max, d_max = _band_bounds(qbox, len(qbox), len(tbox), int(a['score']), self_scores, s_min, go, ge)
+            want = [(int(o) >> 2, int(o) & 3) for o in cigs[p]]
+            for G, K in ((4, 8), (2, 16), (8, 8)):
+                got = banded_trace(qbox, tbox, m2, go, ge, int(a['score']), int(i_max), int(d_max), G=G, K=K)
+                assert got == want, (p, G, K, len(qbox), len(tbox), i_max, d_max)
+            checked += 1
+    assert checked > 50
