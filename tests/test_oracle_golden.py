@@ -221,3 +221,27 @@ def test_strip_layout_model_of_the_banded_traceback(oracle):
                 assert got == want, (p, G, K, len(qbox), len(tbox), i_max, d_max)
             checked += 1
     assert checked > 50
+
+
+def test_model_of_counts_carried_through_the_reverse_pass(oracle):
+    """tools/model_carried_counts.py: match / mismatch / gap-run / gap-base counts carried through the reverse DP equal the
+    counts of the oracle's traceback (the plan for identity without sw_trace_kernel in pb_cluster)"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    from model_carried_counts import carried_counts
+    n = gaps = 0
+    for (mat, go, ge, nsym, seed) in ((seqcodec.protein_matrix(), 11, 1, 20, 33), (seqcodec.nt_matrix(), 6, 2, 4, 34)):
+        m2 = mat.reshape(32, 32).astype(int).tolist()
+        qs, ts = workloads.random_pairs(120, seed=seed, nsym_real=nsym, min_len=5, max_len=120, related=0.8)
+        q, qoff = oracle.concat(qs); t, toff = oracle.concat(ts)
+        aln, _ = oracle.sw_batch(q, qoff, t, toff, mat.reshape(-1), go, ge, with_cigar=False)
+        for p in range(len(qs)):
+            S, coords, counts = carried_counts(qs[p].tolist(), ts[p].tolist(), m2, go, ge)
+            a = aln[p]
+            assert S == a['score']
+            if S == 0:
+                continue
+            assert coords == (a['qs'], a['qe'], a['ts'], a['te'])
+            assert counts == (a['n_match'], a['n_mismatch'], a['n_gapopen'], a['n_gapbases']), (p, counts, a)
+            n += 1; gaps += a['n_gapopen'] > 0
+    assert n > 150 and gaps > 40
