@@ -245,3 +245,44 @@ def test_model_of_counts_carried_through_the_reverse_pass(oracle):
             assert counts == (a['n_match'], a['n_mismatch'], a['n_gapopen'], a['n_gapbases']), (p, counts, a)
             n += 1; gaps += a['n_gapopen'] > 0
     assert n > 150 and gaps > 40
+
+
+def test_score_bounded_band_preserves_the_start_cell(oracle):
+    """The reverse (start-finding) pass restricted to the diagonal band that any alignment of score S ending at the end cell
+    must stay in -- at most D = (U - S - go) / ge extra subject residues and I = (U - S - go) / (s_min + ge) inserted query
+    residues, U the self-score of the whole query prefix -- finds the same first row-major cell."""
+    NEG = -10 ** 9
+    n = narrowed = 0
+    for (mat, go, ge, nsym, seed) in ((seqcodec.protein_matrix(), 11, 1, 20, 43), (seqcodec.nt_matrix(), 6, 2, 4, 44)):
+        m2 = mat.reshape(32, 32).astype(int)
+        self_scores = np.diag(m2); s_min = int(self_scores[:nsym].min())
+        qs, ts = workloads.random_pairs(80, seed=seed, nsym_real=nsym, min_len=10, max_len=110, related=0.85)
+        q, qoff = oracle.concat(qs); t, toff = oracle.concat(ts)
+        aln, _ = oracle.sw_batch(q, qoff, t, toff, mat.reshape(-1), go, ge, with_cigar=False)
+        for p in range(len(qs)):
+            a = aln[p]
+            S = int(a['score'])
+            if S <= 0:
+                continue
+            qr = qs[p][:a['qe'] + 1][::-1].tolist(); tr = ts[p][:a['te'] + 1][::-1].tolist()
+            M, N = len(qr), len(tr)
+            U = int(sum(int(self_scores[c]) for c in qr))
+            slack = U - S - go
+            D = max(0, slack // ge) if slack >= 0 else 0
+            I = max(0, slack // (s_min + ge)) if slack >= 0 else 0
+            narrowed += (I + D + 1) < min(M, N)
+            goe = go + ge
+            Hp = [0] * (N + 1); Ep = [NEG] * (N + 1); found = None
+            for i in range(1, M + 1):
+                Hc = [0] * (N + 1); Ec = [NEG] * (N + 1); f = NEG
+                for j in range(max(1, i - I), min(N, i + D) + 1):
+                    Ec[j] = max(Ep[j] - ge, Hp[j] - goe); f = max(f - ge, Hc[j - 1] - goe)
+                    Hc[j] = max(0, Hp[j - 1] + int(m2[qr[i - 1], tr[j - 1]]), Ec[j], f)
+                    if Hc[j] == S:
+                        found = (i, j); break
+                if found:
+                    break
+                Hp, Ep = Hc, Ec
+            assert found is not None and (a['qe'] - (found[0] - 1), a['te'] - (found[1] - 1)) == (a['qs'], a['ts']), (p, M, N, I, D)
+            n += 1
+    assert n > 100 and narrowed > 30
