@@ -118,7 +118,9 @@ typedef struct {
 typedef enum {
     PB_MODE_NT = 1,              /* runBlast: blastn, nt vs nt, both strands (:482-509, flags :294) */
     PB_MODE_PROT6 = 2,           /* runDiamond: best forward frame of each query vs 6 frames (:513-560) */
-    PB_MODE_PROT3_SELF = 3       /* runDiamondSELF: vs the 3 forward frames, no self hits, k=200 (:511-512) */
+    PB_MODE_PROT3_SELF = 3       /* runDiamondSELF: vs the 3 forward frames, k=200 (:511-512).  Self hits (q_id == s_id) are
+                                    KEPT: the reference passes --no-self-hits, but its query titles ('n:1') and target titles
+                                    ('n:1:0') differ (:529, :543), so diamond never suppresses them there either */
 } pb_search_mode;
 
 typedef struct {
@@ -169,6 +171,16 @@ typedef struct {
 int  pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target,
                const pb_search_params* params, pb_hits* out, pb_search_stats* stats /* nullable */);
 void pb_free_hits(pb_hits* hits);
+
+/* Many genomes per call: the unit the reference fans out one worker process at a time (PEPPAN.py:922, one iter_map_bsn ->
+ * uberBlast -> blastn / diamond run per genome) batched so that one launch sequence covers all of them (a single ~5 Mbp
+ * genome cannot fill a B200).  target holds the contigs of n_groups genomes, target_group[c] (non-decreasing, < n_groups) =
+ * genome of contig c.  The result is exactly the concatenation, in group order, of what pb_search returns for every genome
+ * on its own (the per-query hit cap applies per genome); s_id stays the index into `target`; group_off (caller-allocated,
+ * n_groups + 1) receives the first hit of every group. */
+int  pb_search_grouped(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const int32_t* target_group,
+                       int32_t n_groups, const pb_search_params* params, pb_hits* out, int64_t* group_off,
+                       pb_search_stats* stats /* nullable */);
 
 /* Multi-GPU: every rank contributes its hit table and receives the concatenation of all ranks'
  * tables in rank order (one NCCL allgather of counts, one of the padded records, one of the CIGAR

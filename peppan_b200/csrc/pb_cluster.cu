@@ -83,7 +83,9 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
         // reserved[0] bit 1 pins the query frame to 1, hits on target frames 2 / 3 are ignored below
         prm.mode = translate ? PB_MODE_PROT3_SELF : PB_MODE_NT; prm.gtable = gtable; prm.min_id = min_id - 0.005f; prm.min_cov = 0;
         prm.min_ratio = std::max(0.f, min_cov - 0.005f);
-        prm.max_hits_per_query = 1000; prm.reserved[0] = translate ? 2 : 1;
+        // no per-query cap: the cap of pb_search is by raw score over ALL targets, applied before later genes / members are
+        // discarded here, so in a family of > 1000 genes it could cut the edge to the earliest representative
+        prm.max_hits_per_query = 0x7fffffff; prm.reserved[0] = translate ? 2 : 1;
         auto verified = [&](const pb_hits& hits, const pb_hit& x) {
             if (translate && x.frame != 1) return false;
             int gapb = 0;

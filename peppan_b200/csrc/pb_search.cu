@@ -669,10 +669,20 @@ extern "C" void pb_free_hits(pb_hits* h)
     h->hits = nullptr; h->cigar = nullptr; h->rank_offsets = nullptr; h->n_hits = 0; h->n_cigar = 0; h->n_ranks = 0;
 }
 
-extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const pb_search_params* prm,
-                         pb_hits* out, pb_search_stats* stats)
+// group (nullable): group[c] = genome of target sequence c, non-decreasing, < n_groups; the per-query hit cap and the output
+// order are then per group, and group_off (n_groups + 1) receives the first hit of every group.
+static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const pb_search_params* prm,
+                       const int32_t* group, int32_t n_groups, pb_hits* out, int64_t* group_off, pb_search_stats* stats)
 {
     if (!ctx || !query || !target || !prm || !out) { pb_set_error(ctx, "pb_search: invalid argument"); return PB_ERR_ARG; }
+    if (group) {
+        if (n_groups <= 0 || !group_off) { pb_set_error(ctx, "pb_search_grouped: invalid argument"); return PB_ERR_ARG; }
+        for (int64_t c = 0; c < target->n; ++c)
+            if (group[c] < 0 || group[c] >= n_groups || (c > 0 && group[c] < group[c - 1])) {
+                pb_set_error(ctx, "pb_search_grouped: target groups must be non-decreasing and below n_groups"); return PB_ERR_ARG;
+            }
+        for (int32_t g = 0; g <= n_groups; ++g) group_off[g] = 0;
+    }
     if (prm->mode < PB_MODE_NT || prm->mode > PB_MODE_PROT3_SELF) { pb_set_error(ctx, "pb_search: unknown mode %d", prm->mode); return PB_ERR_ARG; }
     out->hits = nullptr; out->cigar = nullptr; out->n_hits = 0; out->n_cigar = 0; out->rank_offsets = nullptr; out->n_ranks = 0;
     pb_search_stats st; memset(&st, 0, sizeof(st));
@@ -686,8 +696,10 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     const SeedSpec spec = nt ? nt_spec() : aa_spec();
     const int64_t nq = query->n, nc = target->n;
     const int64_t qbytes = query->offsets[nq], tbytes = target->offsets[nc];
-    if (qbytes >= (int64_t)0xfffffff0 || tbytes * 2 >= (int64_t)0xfffffff0) {
-        pb_set_error(ctx, "pb_search: a single call is limited to 4 G residues per side; block the input"); return PB_ERR_LIMIT;
+    // positions are 32-bit: the query layout (sorted with 32-bit item counts) stays below 2^31 residues, the target layout
+    // (both strands / all frames + one separator per sequence) below 2^32
+    if (qbytes + nq + 64 >= (int64_t)0x7fffffff || tbytes * 2 + (int64_t)6 * nc + 64 >= (int64_t)0xfffffff0) {
+        pb_set_error(ctx, "pb_search: a single call is limited to 2 G query and 2 G target residues; block the input"); return PB_ERR_LIMIT;
     }
     cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10], e3 = ctx->ev[11];
     int launches = 0;
@@ -803,7 +815,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
 
     // ---- K1b: seed scan (retry with a larger candidate buffer on overflow) ----
     DevBuf d_cand, d_longq;
-    unsigned long long cap = std::max<unsigned long long>(1ull << 20, (unsigned long long)nq * 64);
+    unsigned long long cap = std::max<unsigned long long>(std::max<unsigned long long>(1ull << 20, (unsigned long long)nq * 64), (unsigned long long)LT / 8);
     for (int attempt = 0; attempt < 4; ++attempt) {
         PB_CUDA(ctx, d_cand.alloc(cap * sizeof(Cand), sm));
         PB_CUDA(ctx, d_longq.alloc(cap * sizeof(SeedQ), sm));
@@ -921,7 +933,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
 
     // ---- host: thresholds, coordinate mapping, records ----
     const double lam = nt ? 0.625 : 0.267, Kk = nt ? 0.41 : 0.041, emax = nt ? 1e-2 : 1.0;
-    struct Rec { pb_hit h; int64_t win; };
+    struct Rec { pb_hit h; int64_t win; int32_t grp; };
     std::vector<Rec> recs; recs.reserve(nw);
     for (int64_t i = 0; i < nw; ++i) {
         if (score[i] <= 0) continue;
@@ -964,11 +976,12 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
             const int qm = aqe[i] - aqs[i] + 1;
             if (qm * 3 < prm->min_cov || (double)qm * 3.0 / (double)h.q_len < prm->min_ratio || iden < prm->min_id - 0.0015) continue;
         }
-        recs.push_back(Rec{h, i});
+        recs.push_back(Rec{h, i, group ? group[h.s_id] : 0});
     }
     // duplicates (two windows converging on the same alignment) and deterministic order
     std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) {
         const pb_hit &x = a.h, &y = b.h;
+        if (a.grp != b.grp) return a.grp < b.grp;
         if (x.q_id != y.q_id) return x.q_id < y.q_id;
         if (x.s_id != y.s_id) return x.s_id < y.s_id;
         if (x.s_start != y.s_start) return x.s_start < y.s_start;
@@ -990,7 +1003,7 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     {
         std::vector<Rec> kept; kept.reserve(uniq.size());
         for (size_t i = 0; i < uniq.size();) {
-            size_t j = i; while (j < uniq.size() && uniq[j].h.q_id == uniq[i].h.q_id) ++j;
+            size_t j = i; while (j < uniq.size() && uniq[j].h.q_id == uniq[i].h.q_id && uniq[j].grp == uniq[i].grp) ++j;
             if ((int)(j - i) > maxhits) {
                 std::vector<size_t> idx(j - i); for (size_t k = 0; k < idx.size(); ++k) idx[k] = i + k;
                 std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return uniq[a].h.raw_score > uniq[b].h.raw_score; });
@@ -1018,7 +1031,9 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
         }
         co += n;
         hits[i] = h;
+        if (group) group_off[uniq[i].grp + 1]++;
     }
+    if (group) for (int32_t g = 0; g < n_groups; ++g) group_off[g + 1] += group_off[g];
     out->hits = hits; out->n_hits = (int64_t)uniq.size(); out->cigar = cig; out->n_cigar = ncig;
     st.n_hits = out->n_hits;
     cudaEvent_t e4 = ctx->ev[12];
@@ -1030,4 +1045,17 @@ extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* t
     if (dbg) fprintf(stderr, "[pb_search] host: cluster/window %.1f ms, sw+trace (incl. host) %.1f ms, records %.1f ms\n", h1 - h0, h2 - h1, now() - h2);
     if (stats) *stats = st;
     return PB_OK;
+}
+
+extern "C" int pb_search(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const pb_search_params* prm,
+                         pb_hits* out, pb_search_stats* stats)
+{
+    return search_impl(ctx, query, target, prm, nullptr, 0, out, nullptr, stats);
+}
+
+extern "C" int pb_search_grouped(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const int32_t* target_group,
+                                 int32_t n_groups, const pb_search_params* prm, pb_hits* out, int64_t* group_off, pb_search_stats* stats)
+{
+    if (!target_group) { pb_set_error(ctx, "pb_search_grouped: target_group missing"); return PB_ERR_ARG; }
+    return search_impl(ctx, query, target, prm, target_group, n_groups, out, group_off, stats);
 }

@@ -44,6 +44,8 @@ def bind(lib):
     lib.pb_free_hits.argtypes = [C.POINTER(Hits)]
     lib.pb_free_hits.restype = None
     lib.pb_allgather_hits.argtypes = [vp, C.POINTER(Hits)]
+    lib.pb_search_grouped.argtypes = [vp, C.POINTER(SeqSet), C.POINTER(SeqSet), vp, C.c_int32, C.POINTER(SearchParams), C.POINTER(Hits),
+                                      vp, C.POINTER(SearchStats)]
 
 
 def search(ctx, q_bytes, q_off, t_bytes, t_off, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0,
@@ -72,3 +74,51 @@ def search(ctx, q_bytes, q_off, t_bytes, t_off, mode, min_id=0.3, min_cov=40., m
     if allgather:
         d['rank_offsets'] = rank_off
     return hits, cigar, d
+
+
+def _take(out):
+    n, nc = out.n_hits, out.n_cigar
+    hits = np.frombuffer((C.c_char * (n * HIT_DTYPE.itemsize)).from_address(out.hits), dtype=HIT_DTYPE).copy() if n else np.zeros(0, HIT_DTYPE)
+    cigar = np.frombuffer((C.c_char * (nc * 4)).from_address(out.cigar), dtype=np.uint32).copy() if nc else np.zeros(0, np.uint32)
+    return hits, cigar
+
+
+def search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0):
+    """pb_search_grouped: many genomes in one call.  Returns (hits, cigar, group_off, stats): the concatenated table in group
+    order, s_id = index into the concatenated target set."""
+    bind(ctx.lib)
+    q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8); t_bytes = np.ascontiguousarray(t_bytes, dtype=np.uint8)
+    q_off = np.ascontiguousarray(q_off, dtype=np.int64); t_off = np.ascontiguousarray(t_off, dtype=np.int64)
+    groups = np.ascontiguousarray(groups, dtype=np.int32)
+    assert len(groups) == len(t_off) - 1
+    ng = int(groups.max()) + 1 if len(groups) else 0
+    qs = SeqSet(q_bytes.ctypes.data, q_off.ctypes.data, len(q_off) - 1)
+    ts = SeqSet(t_bytes.ctypes.data, t_off.ctypes.data, len(t_off) - 1)
+    prm = SearchParams(mode=mode, gtable=gtable, min_id=min_id, min_cov=min_cov, min_ratio=min_ratio, max_hits_per_query=max_hits)
+    out, st = Hits(), SearchStats()
+    goff = np.zeros(ng + 1, np.int64)
+    ctx.check(ctx.lib.pb_search_grouped(ctx.h, C.byref(qs), C.byref(ts), ptr(groups), ng, C.byref(prm), C.byref(out), ptr(goff), C.byref(st)),
+              'pb_search_grouped')
+    try:
+        hits, cigar = _take(out)
+    finally:
+        ctx.lib.pb_free_hits(C.byref(out))
+    return hits, cigar, goff, st.as_dict()
+
+
+def search_grouped(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, **kw):
+    """Per-genome tables of a grouped search: [(hits, cigar)] with s_id local to the genome and cigar_off rebased, i.e. what
+    search() returns for every genome on its own."""
+    hits, cigar, goff, st = search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, **kw)
+    groups = np.asarray(groups)
+    first = np.searchsorted(groups, np.arange(len(goff) - 1), side='left')
+    res = []
+    for g in range(len(goff) - 1):
+        h = hits[goff[g]:goff[g + 1]].copy()
+        if len(h):
+            c0 = int(h['cigar_off'][0]); c1 = int(h['cigar_off'][-1]) + int(h['cigar_n'][-1])
+            h['cigar_off'] -= np.uint32(c0); h['s_id'] -= np.int32(first[g])
+            res.append((h, cigar[c0:c1].copy()))
+        else:
+            res.append((h, np.zeros(0, np.uint32)))
+    return res, st

@@ -80,7 +80,9 @@ def rows_from_prot_hits(hits, cigar, qn, rn, min_id):
     rows = []
     for i in range(len(hits)):
         variation = float(c['mismatch'][i] + gapb[i])          # 3 * NM
-        iden = 1 - round(variation / cl[i], 3)
+        # parseDiamond rounds a numpy scalar (cl is np.int64 there): numpy's multiply-rint-divide rounding, which differs from
+        # Python's round() on half-way quotients such as 3/240 = 0.0125 (:38)
+        iden = 1 - float(np.round(np.float64(variation) / np.int64(cl[i]), 3))
         if iden < min_id:
             continue
         rows.append([qn[c['q_id'][i]], rn[c['s_id'][i]], iden, cl[i], int(variation - gapb[i]), ngap[i], c['q_start'][i], c['q_end'][i],

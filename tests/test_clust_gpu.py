@@ -28,7 +28,7 @@ def _genes(seed, n_anc=60, copies=4):
 def _oracle_clusters(oracle, items, identity, coverage, translate=False):
     names, buf, off = seqio.to_seqset(items)
     hits, cig = oracle.search(buf, off, buf, off, 3 if translate else (1 | 256), seqcodec.BLOSUM62.reshape(-1), min_id=identity - 0.005,
-                              min_cov=0, min_ratio=max(0.0, coverage - 0.005), max_hits=1000)
+                              min_cov=0, min_ratio=max(0.0, coverage - 0.005), max_hits=0x7fffffff)
     ea, eb = [], []
     for h in hits:
         a, b = int(h['s_id']), int(h['q_id'])
@@ -65,6 +65,23 @@ def test_translated_cluster_matches_oracle_greedy(ctx, oracle, identity, coverag
     want = _oracle_clusters(oracle, items, identity, coverage, translate=True)
     assert np.array_equal(rep, want)
     assert 0 < st['n_reps'] < len(items)
+
+
+def test_family_larger_than_any_hit_cap_stays_one_cluster(ctx):
+    # 1,100 alleles of one gene: gene 0 carries three SNPs, every other gene one SNP of its own, so each later gene scores
+    # higher against its ~1,100 siblings than against gene 0 -- a per-query top-1000 by score would cut the edge to the only
+    # representative and split the family.  Identity to gene 0 is 146/150 = 0.973 >= 0.97: one cluster.
+    rng = np.random.default_rng(5)
+    base = workloads._random_gene(rng, 150)
+    genes = []
+    for k in range(1100):
+        g = base.copy()
+        for p in ([10, 50, 90] if k == 0 else [12 + (k % 120)]):
+            g[p] = (g[p] + 1 + (k // 120) % 3) % 4 if k else (g[p] + 1) % 4
+        genes.append(workloads._NT[g].tobytes().decode())
+    names, buf, off = seqio.to_seqset([(str(i), s) for i, s in enumerate(genes)])
+    rep, st = clust.cluster(ctx, buf, off, 0.97, 0.8)
+    assert (rep == 0).all() and st['n_reps'] == 1
 
 
 def test_cluster_blocked_equals_single_block(ctx, monkeypatch):

@@ -1,7 +1,6 @@
 """Real sequences: 164 CDS of one bundled E. coli genome against the syntenic 138 kb of another (tests/golden/real_slice.json.gz,
-cut by tests/golden/make_real_slice.py).  The oracle half runs everywhere; the GPU half (pb_search == oracle on real
-sequences) is opt-in for now (PB_REAL_DATA=1): it was written after the round's GPU budget was spent and has not been run
-on a GPU yet -- it is the first parity item of the next round."""
+cut by tests/golden/make_real_slice.py).  The oracle half runs everywhere; the GPU half checks pb_search == oracle on these
+real sequences, all three modes, with the oracle run live (the whole-genome version is tests/test_real_genomes.py)."""
 import gzip
 import json
 import os
@@ -32,7 +31,6 @@ def test_oracle_finds_the_real_orthologs(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get('PB_REAL_DATA') != '1', reason='opt-in until it has been run on a GPU once (PB_REAL_DATA=1)')
 @pytest.mark.parametrize('mode', [1, 2, 3])
 def test_gpu_search_equals_oracle_on_real_sequences(ctx, oracle, mode):
     from peppan_b200 import search

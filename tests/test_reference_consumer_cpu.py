@@ -410,3 +410,21 @@ def test_reference_getclust_with_mmseqs_emulated_from_our_clustering_equals_the_
     assert open(rtab).read() == open(otab).read()
     assert open(rex).read() == open(oex).read()
     assert 20 <= sum(1 for l in open(oex) if l.startswith('>')) < len(items)
+
+
+def test_halfway_identity_rounds_like_the_reference(PEPPAN, tmp_path):
+    """An 80-aa alignment with one mismatch: 3 NM / cl = 3 / 240 = 0.0125 sits half-way at three decimals.  parseDiamond
+    rounds a numpy scalar (modules/uberBlast.py:34-38: cl is np.int64), i.e. multiply-rint-divide, which gives 0.988 where
+    Python's round() gives 0.987; the shim's row must carry the reference's value."""
+    from peppan_b200 import search
+    refmod = sys.modules['modules.uberBlast'] if 'modules.uberBlast' in sys.modules else __import__('modules.uberBlast', fromlist=['x'])
+    contig = 'ACGT' * 300
+    qry = {'5': contig[0:240]}
+    fn = os.path.join(tmp_path, 'aaMatch.0')
+    sam = '5:1\t0\t7:1:0\t1\t255\t80M\t*\t0\t0\t' + 'A' * 80 + '\t*\tAS:i:100\tNM:i:1\tZL:i:400\tZR:i:400\tZE:f:0\tZI:i:98\tZF:i:1\tZS:i:1'
+    open(fn, 'w').write('@HD\tVN:1.5\n' + sam + '\n')
+    got = np.load(refmod.parseDiamond([fn, {'7': contig}, qry, 0.3, 40, 0.05]), allow_pickle=True)
+    hits = np.zeros(1, search.HIT_DTYPE)
+    hits[0] = (0, 0, 1, 240, 1, 240, 240, 3, 0, 400, 240, 1200, 0.988, 0.0, 1, 0, 1)
+    rows = ub.rows_from_prot_hits(hits, np.array([(240 << 2) | 0], np.uint32), ['5'], ['7'], 0.3)
+    assert float(got[0][2]) == rows[0][2] == 0.988
