@@ -1,23 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of peppan_b200 (contract: see DESIGN.md "Measurement").
+"""bench.py -- benchmark of peppan_b200 (contract: DESIGN.md "Measurement").
 
-Workload (N=1): BASELINE.json configs[1] -- the Smith-Waterman extension micro-bench, 1,000,000
-synthetic protein pairs of length 300, BLOSUM62 gap 11/1, every pair reporting score + end + start
-coordinates (bit-exact against oracle/).  One "step" = one pass of the path over the whole batch.
-`value` = GCUPS with inputs already resident in HBM (device time from CUDA events on the library's
-stream); `e2e` = the same metric through the C-ABI call pb_sw_batch with host buffers (pinned),
-H2D and D2H inside the timed region.  N>1: every rank runs the same-size shard with its own seed
+One JSON line.  Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[1] -- the Smith-Waterman extension
+micro-bench, 1,000,000 synthetic protein pairs of length 300, BLOSUM62 gap 11/1, every pair reporting score + end + start
+(bit-exact against oracle/).  One "step" = one pass of the path over the whole batch.  `value` = GCUPS with inputs already
+resident in HBM (CUDA events on the library's stream); `e2e` = the same metric through the C-ABI call pb_sw_batch with
+page-locked HOST buffers, H2D and D2H inside the timed region.  N>1: every rank runs a same-size shard with its own seed
 (independent units, no data-path collective -> weak scaling).
 
---impl reference times the CPU arm: the reference's blastn/diamond binaries are absent from
-/root/reference and cannot be built here (prebuilt third-party tools), so the arm is the scalar
-oracle port on all host cores, on a bounded sample of the same workload.
+The same line carries the genome-scale legs (BASELINE.json configs[2..3]; synthetic genomes of 4,500 genes,
+~5 Mbp; 15,000 exemplar genes as queries):
+  config4   --genomes G (default 1000) genomes sharded g mod world, searched nucleotide + protein-6-frame against the
+            replicated exemplars in batches of --batch genomes per pb_search_grouped call; N>1: one NCCL allgather of the
+            hit tables per batch, verified (every rank holds the same table, equal to the rank-order concatenation);
+            strong scaling (total work fixed).  genes/s, ms per genome, per-stage device ms, rooflines per stage.
+  config3   --c3-genomes (default 10; 100 = the named size, also `--config 3`) genomes: the 11-rung identity ladder of
+            iterClust (PEPPAN.py:1777-1792) through pb_cluster + the per-genome search of those genomes.
+  uberblast the reference-level call uberBlast(argv) (files in, blastab rows out) per genome.
+
+--impl reference times the CPU arm.  The reference's own hot path is the blastn / diamond / mmseqs binaries; they are
+looked for on PATH and under baseline/_ref/ and, when present, timed with the reference's command lines
+(modules/uberBlast.py:294,550, modules/clust.py:62-66).  They are absent from the reference checkout (and this image), so
+the arm is the oracle port on all host cores, on the same workload definition.
 """
 import argparse
+import faulthandler
+import hashlib
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -29,6 +43,9 @@ sys.path.insert(0, ROOT)
 METRIC = 'GCUPS (Smith-Waterman extension, score+coords, uberBlast hot path)'
 UNIT = 'GCUPS'
 ALGO_INSTR_PER_CELL = 3.5     # DPX-fused s16x2 instructions per DP cell
+ALGO_INSTR_PER_CELL_S32 = 7.0
+N_CORE, N_ACC = 3000, 12000   # exemplar pool of the genome-scale legs
+THRESH = dict(min_id=0.4, min_cov=50, min_ratio=0.25)     # iter_map_bsn thresholds (PEPPAN.py:767-772)
 
 
 class ClockSampler(threading.Thread):
@@ -73,43 +90,45 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']), 'MEASURED_PEAKS.json'
+    except Exception:
+        return 6545.6, 'fallback 6545.6 GB/s (B200_PROFILING.md)'
+
+
 def profiled_traffic():
     """dram bytes per launch of the forward kernel from the committed ncu --set full summary, or None"""
-    path = os.path.join(ROOT, 'profiles', 'r01_sw_kernel_ncu_full.txt')
-    try:
-        rd = wr = None
-        for line in open(path):
-            if 'REV' in line or line.startswith('void pbsw'):
-                pass
-            if line.startswith('dram__bytes_read.sum') and rd is None:
-                rd = float(line.split()[1]) * 1e6
-            if line.startswith('dram__bytes_write.sum') and wr is None:
-                wr = float(line.split()[1]) * 1e6
-        return None if rd is None or wr is None else rd + wr
-    except Exception:
-        return None
+    for name in ('r02_sw_kernel_ncu_full.txt', 'r01_sw_kernel_ncu_full.txt'):
+        path = os.path.join(ROOT, 'profiles', name)
+        try:
+            rd = wr = None
+            for line in open(path):
+                if line.startswith('dram__bytes_read.sum') and rd is None:
+                    rd = float(line.split()[1]) * 1e6
+                if line.startswith('dram__bytes_write.sum') and wr is None:
+                    wr = float(line.split()[1]) * 1e6
+            if rd is not None and wr is not None:
+                return rd + wr, name
+        except Exception:
+            continue
+    return None, None
 
 
 def hbm_view(algo_bytes, ms):
-    """the same kernel against the HBM roofline: algorithmic bytes per launch (sequences read once + 32-B descriptor +
-    three 4-B results per pair) / launch time, against the measured copy bandwidth of MEASURED_PEAKS.json"""
-    peak, src = 6545.6, 'fallback 6545.6 GB/s'
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']); src = 'MEASURED_PEAKS.json'
-    except Exception:
-        pass
+    peak, src = hbm_peak()
     gbs = algo_bytes / (ms * 1e-3) / 1e9
     return {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'peak_source': src,
             'note': 'far below 1: the kernel is bound by integer / DPX issue, not by HBM'}
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     pg = None
     if world > 1:
-        import torch.distributed as dist     # plumbing only: barrier + max over ranks (gloo, CPU tensors)
+        import torch.distributed as dist     # plumbing only: barrier, max over ranks, NCCL unique id (gloo, CPU tensors)
         dist.init_process_group('gloo', rank=rank, world_size=world)
         pg = dist
     return rank, world, local, pg
@@ -120,143 +139,98 @@ def barrier(pg):
         pg.barrier()
 
 
-def allmax(pg, x):
+def _allreduce(pg, x, op):
     if pg is None:
         return x
     import torch
     t = torch.tensor([x], dtype=torch.float64)
-    pg.all_reduce(t, op=pg.ReduceOp.MAX)
+    pg.all_reduce(t, op=getattr(pg.ReduceOp, op))
     return float(t[0])
+
+
+def allmax(pg, x):
+    return _allreduce(pg, x, 'MAX')
 
 
 def allsum(pg, x):
-    if pg is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64)
-    pg.all_reduce(t, op=pg.ReduceOp.SUM)
-    return float(t[0])
+    return _allreduce(pg, x, 'SUM')
 
 
-def cpu_oracle_leg(npairs_sample, threads, seed_rank=0):
-    """The scalar oracle port on `threads` host threads over the first pairs of the workload."""
+def allmin(pg, x):
+    return _allreduce(pg, x, 'MIN')
+
+
+# ---- CPU arms --------------------------------------------------------------------------------------------------------
+def find_reference_tools():
+    """blastn / makeblastdb / diamond / mmseqs on PATH or under baseline/_ref/ """
+    found = {}
+    extra = [os.path.join(ROOT, 'baseline', '_ref'), os.path.join(ROOT, 'baseline', '_ref', 'bin'), os.path.join(ROOT, 'baseline', '_ref', 'dependencies')]
+    for tool in ('blastn', 'makeblastdb', 'diamond', 'mmseqs'):
+        p = shutil.which(tool)
+        for d in extra:
+            if p is None and os.access(os.path.join(d, tool), os.X_OK):
+                p = os.path.join(d, tool)
+        found[tool] = p
+    return found
+
+
+def reference_tools_leg(threads):
+    """Times the reference's own command lines when its binaries exist; otherwise says so."""
+    tools = find_reference_tools()
+    missing = [t for t, p in tools.items() if p is None]
+    if missing:
+        return {'available': False, 'note': 'reference binaries unavailable (%s not on PATH or under baseline/_ref/): the CPU arm is the oracle port' % ', '.join(missing)}
+    from peppan_b200 import workloads
+    tmp = tempfile.mkdtemp(prefix='pb_ref_')
+    out = {'available': True, 'tools': tools}
+    try:
+        pool = workloads.GenePool(N_CORE, N_ACC)
+        seq, annot = workloads.synth_genome(pool, 0)
+        qry, ref = os.path.join(tmp, 'qry.fa'), os.path.join(tmp, 'refNA')
+        with open(qry, 'w') as f:
+            for n, s in pool.fasta_items():
+                f.write('>%s\n%s\n' % (n, s))
+        with open(ref, 'w') as f:
+            f.write('>g0\n%s\n' % seq)
+        t0 = time.perf_counter()
+        subprocess.check_call([tools['makeblastdb'], '-dbtype', 'nucl', '-in', ref, '-out', ref], stdout=subprocess.DEVNULL)
+        # modules/uberBlast.py:294
+        subprocess.check_call([tools['blastn'], '-db', ref, '-query', qry, '-word_size', '17', '-out', qry + '.bsn', '-perc_identity', '40',
+                               '-outfmt', '6 qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue score qlen slen qseq sseq',
+                               '-qcov_hsp_perc', '25', '-num_alignments', '1000', '-task', 'blastn', '-evalue', '1e-2', '-dbsize', '5000000',
+                               '-reward', '2', '-penalty', '-3', '-gapopen', '6', '-gapextend', '2', '-num_threads', str(threads)])
+        out['blastn_seconds_per_genome'] = time.perf_counter() - t0
+        out['blastn_genes_per_s'] = (N_CORE + N_ACC) / out['blastn_seconds_per_genome']
+        # modules/clust.py:62-66
+        t0 = time.perf_counter()
+        subprocess.check_call([tools['mmseqs'], 'createdb', qry, os.path.join(tmp, 'seq.db'), '-v', '0'])
+        subprocess.check_call([tools['mmseqs'], 'linclust', os.path.join(tmp, 'seq.db'), os.path.join(tmp, 'seq.lc'), os.path.join(tmp, 'tmp'),
+                               '--min-seq-id', '0.9', '-c', '0.8', '--threads', str(threads), '-v', '0'])
+        out['mmseqs_linclust_seconds'] = time.perf_counter() - t0
+    except Exception as e:      # a tool that is present but fails is reported, not hidden
+        out['error'] = repr(e)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+def cpu_sw_leg(npairs_sample, threads, seed_rank=0):
+    """The CPU Smith-Waterman arm on `threads` host threads over the first pairs of the config-2 workload (score + end + start)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import pb_oracle
     from peppan_b200 import seqcodec, workloads
     q, qoff, t, toff = workloads.sw_microbench_pairs(npairs_sample, seed=workloads.SEED + seed_rank)
     mat = seqcodec.protein_matrix().reshape(-1)
-    pb_oracle.sw_batch(q[:300 * 64], qoff[:65], t[:300 * 64], toff[:65], mat, 11, 1, with_cigar=False, nthreads=threads)
+    fn, kind = pb_oracle.sw_batch, 'scalar C (-O3), one pair per call'
+    if hasattr(pb_oracle, 'sw_batch_simd') and pb_oracle.simd_lanes() > 1:
+        fn = pb_oracle.sw_batch_simd
+        kind = 'striped int16 SIMD (%d lanes), same results as the scalar oracle' % pb_oracle.simd_lanes()
+    fn(q[:300 * 64], qoff[:65], t[:300 * 64], toff[:65], mat, 11, 1, with_cigar=False, nthreads=threads)
     t0 = time.perf_counter()
-    pb_oracle.sw_batch(q, qoff, t, toff, mat, 11, 1, with_cigar=False, nthreads=threads)
+    fn(q, qoff, t, toff, mat, 11, 1, with_cigar=False, nthreads=threads)
     dt = time.perf_counter() - t0
     cells = float(npairs_sample) * 300 * 300
-    return cells / dt / 1e9, dt
-
-
-def search_world(n_core, n_acc, genome_index):
-    """Exemplar gene pool + one synthetic genome (SURVEY.md 8d generator) as seqsets of ASCII bytes."""
-    from peppan_b200 import seqio, workloads
-    pool = workloads.GenePool(n_core, n_acc)
-    seq, annot = workloads.synth_genome(pool, genome_index, n_acc_per_genome=n_acc // 8)
-    qn, qb, qo = seqio.to_seqset(pool.fasta_items())
-    rn, rb, ro = seqio.to_seqset([('g%d' % genome_index, seq)])
-    return qb, qo, rb, ro, len(annot)
-
-
-def search_leg(ctx, rank, world, pg, steps, with_cpu, gather=True):
-    """Second hot-path measurement: the per-genome uberBlast search (BASELINE.json configs[2..3] unit of work): 15,000
-    exemplar genes against one synthetic ~5 Mbp genome of 4,500 genes through pb_search with HOST buffers, nucleotide
-    mode (runBlast) + protein-vs-6-frame mode (runDiamond); one genome per rank (independent units)."""
-    from peppan_b200 import search
-    qb, qo, rb, ro, ngenes = search_world(3000, 12000, rank)
-    q = ctx.pinned_empty(qb.shape, np.uint8); q[:] = qb
-    r = ctx.pinned_empty(rb.shape, np.uint8); r[:] = rb
-    modes = (('nt', search.MODE_NT), ('prot6', search.MODE_PROT6))
-    for _ in range(2):
-        for _, m in modes:
-            search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1 and gather)
-    barrier(pg)
-    t0 = time.perf_counter()
-    acc = {k: {} for k, _ in modes}
-    launches = 0
-    for _ in range(steps):
-        for k, m in modes:
-            # N > 1: the per-rank hit tables are merged by one NCCL allgather (identical table on every rank)
-            hits, cig, st = search.search(ctx, q, qo, r, ro, m, 0.4, 50, 0.25, allgather=world > 1 and gather)
-            launches += st['kernel_launches']
-            for f in ('ms_encode', 'ms_index', 'ms_seed', 'ms_sw', 'ms_trace', 'ms_total'):
-                acc[k][f] = acc[k].get(f, 0.0) + st[f] / steps
-            acc[k].update(hits=int(len(hits)), allgather=('nccl' if gather else 'skipped') if world > 1 else None, windows=int(st['n_windows']), seed_hits=int(st['n_seed_hits']), sw_cells=float(st['sw_cells']),
-                          algo_bytes_seed=int(st['algo_bytes_seed']))
-    barrier(pg)
-    wall = allmax(pg, time.perf_counter() - t0)
-    nq = len(qo) - 1
-    total_q = allsum(pg, float(nq)) * steps
-    out = {'workload': 'per-genome search: %d exemplar genes vs one synthetic genome (%d bp, %d genes) per GPU, nt + protein 6-frame, '
-                       'min_id 0.4 min_cov 50 min_ratio 0.25 (iter_map_bsn thresholds)' % (nq, len(rb), ngenes),
-           'genes_per_s': total_q / wall, 'ms_per_genome': 1e3 * wall / steps, 'steps': steps,
-           'h2d_bytes_per_genome': int(2 * (len(qb) + len(rb) + 8 * (len(qo) + len(ro)))), 'gpu_launches': launches}
-    hbm = 6545.6
-    try:
-        hbm = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
-    except Exception:
-        pass
-    for k, _ in modes:
-        a = acc[k]
-        a['gcups_sw'] = a['sw_cells'] / max(a['ms_sw'], 1e-9) / 1e6
-        gbs = a['algo_bytes_seed'] / max(a['ms_seed'], 1e-9) / 1e6
-        a['seed_roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
-                              'note': 'algorithmic bytes (SURVEY 8d: target + 9 x query residues + 16 x seed hits) / seed-stage time'}
-        out[k] = a
-    if with_cpu and rank == 0:
-        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-        import pb_oracle
-        from peppan_b200 import seqcodec
-        sqb, sqo, srb, sro, sg = search_world(300, 600, 0)
-        c0 = time.perf_counter()
-        nh = 0
-        for _, m in modes:
-            h, _c = pb_oracle.search(sqb, sqo, srb, sro, m, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25)
-            nh += len(h)
-        cdt = time.perf_counter() - c0
-        g0 = time.perf_counter()
-        ng = 0
-        for _, m in modes:
-            h, _c, _s = search.search(ctx, sqb, sqo, srb, sro, m, 0.4, 50, 0.25)
-            ng += len(h)
-        gdt = time.perf_counter() - g0
-        out['cpu_baseline'] = {'value': (len(sqo) - 1) / cdt, 'unit': 'genes/s', 'cores': 1, 'kind': 'port',
-                               'sample': '%d genes vs a %d bp genome, scalar search oracle (same search specification), 1 thread, %.1f s; '
-                                         'the GPU path on this same sample: %.0f genes/s; hit counts %d / %d' %
-                                         (len(sqo) - 1, len(srb), cdt, (len(sqo) - 1) / gdt, nh, ng)}
-    return out
-
-
-def cluster_leg(ctx, rank, world, pg, n_genomes=5):
-    """Third hot-path measurement: greedy representative clustering (getClust / pb_cluster) of the genes of `n_genomes`
-    synthetic genomes per GPU in priority (length) order, identity 0.9 / coverage 0.8 (iterClust's last rung)."""
-    from peppan_b200 import clust, seqio, workloads
-    pool = workloads.GenePool(3000, 12000)
-    comp = bytes.maketrans(b'ACGT', b'TGCA')
-    genes = []
-    for g in range(n_genomes):
-        seq, annot = workloads.synth_genome(pool, rank * n_genomes + g)
-        sb = seq.encode()
-        for (gid, a, b, strand, idn) in annot:
-            x = sb[a:b]
-            genes.append(x if strand > 0 else x.translate(comp)[::-1])
-    genes.sort(key=lambda x: -len(x))
-    names, buf, off = seqio.to_seqset([(str(i), s.decode()) for i, s in enumerate(genes)])
-    clust.cluster(ctx, buf, off, 0.9, 0.8)                      # warm-up
-    barrier(pg)
-    t0 = time.perf_counter()
-    rep, st = clust.cluster(ctx, buf, off, 0.9, 0.8)
-    barrier(pg)
-    wall = allmax(pg, time.perf_counter() - t0)
-    total = allsum(pg, float(len(genes)))
-    return {'workload': 'pb_cluster: %d genes (%d synthetic genomes) per GPU, priority order, identity 0.9, coverage 0.8' % (len(genes), n_genomes),
-            'genes_per_s': total / wall, 'seconds': wall, 'clusters': int(st['n_reps']), 'pairs_verified': int(st['n_pairs_verified']),
-            'sw_cells': float(st['sw_cells']), 'gcups': float(st['sw_cells']) / wall / 1e9, 'gpu_launches': int(st['kernel_launches'])}
+    return cells / dt / 1e9, dt, kind
 
 
 def run_reference(args):
@@ -265,27 +239,259 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     sample = args.cpu_pairs
-    vals = []
-    for _ in range(args.warmup):
-        cpu_oracle_leg(min(sample, 2048), threads)
-    t_tot = 0.0
+    for _ in range(min(args.warmup, 1)):
+        cpu_sw_leg(min(sample, 4096), threads)
+    vals, t_tot, kind = [], 0.0, ''
     for _ in range(args.steps):
-        v, dt = cpu_oracle_leg(sample, threads)
+        v, dt, kind = cpu_sw_leg(sample, threads)
         vals.append(v); t_tot += dt
     value = float(np.mean(vals))
+    tools = reference_tools_leg(threads)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / max(args.steps, 1), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: SW extension micro-bench, protein pairs of length 300, BLOSUM62 11/1',
-                   'pairs_per_step': sample, 'note': 'bounded sample of the 1M-pair workload'},
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16 / int32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: SW extension micro-bench, protein pairs of length 300, BLOSUM62 11/1, score+end+start',
+                   'pairs_per_step': sample, 'note': 'per-cell metric; bounded sample of the 1M-pair workload (same generator, same pair shape)'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                         'sample': '%d pairs x 300x300 cells per step (score + end + start), scalar oracle on all host threads; '
-                                   'reference blastn/diamond binaries are absent from the reference checkout' % sample},
+                         'sample': '%d pairs x 300x300 cells per step (score + end + start); %s on all host threads; '
+                                   'reference blastn/diamond binaries: %s' % (sample, kind, 'timed, see reference_tools' if tools.get('available') else 'unavailable')},
+        'reference_tools': tools,
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
     return 0
+
+
+# ---- genome-scale legs -----------------------------------------------------------------------------------------------
+def exemplar_set():
+    from peppan_b200 import seqio, workloads
+    pool = workloads.GenePool(N_CORE, N_ACC)
+    qn, qb, qo = seqio.to_seqset(pool.fasta_items())
+    return pool, qb, qo
+
+
+def pack_genomes(ctx, genomes):
+    """genomes of this rank as one page-locked byte array + offsets (one contig each)"""
+    total = int(sum(len(g[1]) for g in genomes))
+    buf = ctx.pinned_empty((max(total, 1),), np.uint8)
+    off = np.zeros(len(genomes) + 1, np.int64)
+    p = 0
+    for i, (_, seq, _) in enumerate(genomes):
+        buf[p:p + len(seq)] = seq; p += len(seq); off[i + 1] = p
+    return buf, off
+
+
+def table_digest(tables):
+    h = hashlib.blake2b(digest_size=8)
+    for hits, cig in tables:
+        h.update(np.ascontiguousarray(hits).tobytes()); h.update(np.ascontiguousarray(cig).tobytes())
+    return int.from_bytes(h.digest(), 'little') >> 1
+
+
+def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cpu):
+    """BASELINE.json configs[3]: `n_total` genomes sharded g mod world (the reference's own unit of parallelism, one genome
+    per worker, PEPPAN.py:922), searched against the replicated exemplar set in nucleotide mode (runBlast) and protein
+    vs 6 frames (runDiamond) with --batch genomes per pb_search_grouped call (host buffers in, per-genome hit tables out).
+    N>1: the hit tables of every batch are merged by one NCCL allgather per mode inside the timed region."""
+    from peppan_b200 import dist as pbd, search
+    tbuf, toff = pack_genomes(ctx, genomes)
+    ng = len(genomes)
+    nsteps = int(allmax(pg, float((ng + batch - 1) // batch)))
+    modes = (('nt', search.MODE_NT), ('prot6', search.MODE_PROT6))
+    gather = world > 1
+
+    def run_batch(bi, m):
+        g0, g1 = min(bi * batch, ng), min((bi + 1) * batch, ng)
+        # a rank whose shard ran out keeps the collective aligned with an empty target set
+        tb = tbuf[toff[g0]:toff[g1]] if g1 > g0 else np.zeros(0, np.uint8)
+        to = (toff[g0:g1 + 1] - toff[g0]) if g1 > g0 else np.zeros(1, np.int64)
+        groups = np.arange(g1 - g0, dtype=np.int32)
+        return search.search_grouped_raw(ctx, qpin, qo, tb, to, groups, m, allgather=gather, **THRESH), (g0, g1)
+
+    # ---- warm-up on the first batch + verification of the exchange (untimed) ----
+    verified = None
+    recovered = None
+    for k, m in modes:
+        (hits, cig, goff, st), (g0, g1) = run_batch(0, m)
+        if gather:
+            (lh, lc, lgoff, lst), _ = (search.search_grouped_raw(ctx, qpin, qo, tbuf[toff[g0]:toff[g1]], toff[g0:g1 + 1] - toff[g0],
+                                                                 np.arange(g1 - g0, dtype=np.int32), m, **THRESH), None)
+            parts = [None] * world
+            pg.all_gather_object(parts, (lh, lc))
+            eh, ec, eoff = pbd.merge_hit_tables(parts)
+            same = len(eh) == len(hits) and eh.tobytes() == hits.tobytes() and np.array_equal(ec, cig) and np.array_equal(eoff, st['rank_offsets'])
+            dig = [None] * world
+            pg.all_gather_object(dig, table_digest([(hits, cig)]))
+            ok = bool(same and len(set(dig)) == 1)
+            verified = ok if verified is None else (verified and ok)
+        elif k == 'prot6' and g1 > g0:
+            # planted genes recovered over >= 80 % of their length (protein mode), first batch
+            found = planted = 0
+            for g in range(g0, g1):
+                h = hits[goff[g - g0]:goff[g - g0 + 1]]
+                good = set(h['q_id'][(h['q_end'] - h['q_start'] + 1) >= 0.8 * h['q_len']].tolist())
+                present = set(genomes[g][2][:, 0].tolist())
+                found += len(good & present); planted += len(present)
+            recovered = found / max(planted, 1)
+    if gather:
+        verified = bool(allmin(pg, 1.0 if verified else 0.0) == 1.0)
+
+    # ---- timed region ----
+    acc = {k: {} for k, _ in modes}
+    launches = 0
+    kept = []
+    barrier(pg)
+    t0 = time.perf_counter()
+    for bi in range(nsteps):
+        for k, m in modes:
+            (hits, cig, goff, st), (g0, g1) = run_batch(bi, m)
+            launches += st['kernel_launches']
+            a = acc[k]
+            for f in ('ms_encode', 'ms_index', 'ms_seed', 'ms_sw', 'ms_trace', 'ms_total', 'sw_cells', 'n_windows', 'n_seed_hits', 'algo_bytes_seed'):
+                a[f] = a.get(f, 0.0) + float(st[f])
+            a['hits'] = a.get('hits', 0) + int(len(hits))
+            if gather:
+                kept.append((hits, cig))
+    barrier(pg)
+    wall = allmax(pg, time.perf_counter() - t0)
+    if gather:
+        # every rank must have received the same tables in every batch of the timed region
+        dig = [None] * world
+        pg.all_gather_object(dig, table_digest(kept))
+        verified = bool(verified and len(set(dig)) == 1)
+        del kept
+    nq = len(qo) - 1
+    genome_bp = float(toff[-1]) / max(ng, 1)
+    out = {'workload': 'configs[3]: %d synthetic genomes (4,500 genes, ~%.2f Mbp) sharded g mod %d vs %d replicated exemplar genes, nt + protein 6-frame, '
+                       '%d genomes per pb_search_grouped call, min_id 0.4 min_cov 50 min_ratio 0.25' % (n_total, genome_bp / 1e6, world, nq, batch),
+           'genomes': n_total, 'scaling': 'strong (total work fixed; genomes sharded over the ranks)', 'seconds': wall,
+           'genomes_per_s': n_total / wall, 'genes_per_s': n_total * nq / wall, 'ms_per_genome': 1e3 * wall / max(n_total, 1),
+           'ms_per_genome_per_gpu': 1e3 * wall / max(ng, 1), 'h2d_bytes_per_genome': int(2 * (genome_bp + len(qpin) / max(batch, 1))),
+           'gpu_launches': launches, 'allgather': 'nccl, one per batch and mode' if gather else None, 'allgather_verified': verified,
+           'planted_genes_recovered_ge80pct_span_first_batch': recovered, 'timing': 'host wall clock around the C-ABI calls, barrier on both sides, max over ranks'}
+    hbm, _ = hbm_peak()
+    for k, _ in modes:
+        a = acc[k]
+        per = {f: a[f] / max(ng, 1) for f in ('ms_encode', 'ms_index', 'ms_seed', 'ms_sw', 'ms_trace', 'ms_total')}
+        per.update(hits_rank0_view=a['hits'], windows_per_genome=a['n_windows'] / max(ng, 1), seed_hits_per_genome=a['n_seed_hits'] / max(ng, 1),
+                   sw_cells_per_genome=a['sw_cells'] / max(ng, 1))
+        per['gcups_sw'] = a['sw_cells'] / max(a['ms_sw'], 1e-9) / 1e6
+        per['gcups_sw_plus_trace'] = a['sw_cells'] / max(a['ms_sw'] + a['ms_trace'], 1e-9) / 1e6
+        gbs = a['algo_bytes_seed'] / max(a['ms_seed'], 1e-9) / 1e6
+        per['seed_roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
+                                'note': 'algorithmic bytes (SURVEY 8d: target + 9 x query residues + 16 x seed hits) / seed-stage device time'}
+        out[k] = per
+    if with_cpu and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import pb_oracle
+        from peppan_b200 import seqcodec, seqio, workloads
+        spool = workloads.GenePool(300, 600)
+        sseq, _ = workloads.synth_genome(spool, 0, n_acc_per_genome=75)
+        sqn, sqb, sqo = seqio.to_seqset(spool.fasta_items()); srn, srb, sro = seqio.to_seqset([('g0', sseq)])
+        c0 = time.perf_counter()
+        nh = 0
+        for _, m in modes:
+            h, _c = pb_oracle.search(sqb, sqo, srb, sro, m, seqcodec.BLOSUM62.reshape(-1), **THRESH)
+            nh += len(h)
+        cdt = time.perf_counter() - c0
+        g0 = time.perf_counter()
+        ngh = 0
+        for _, m in modes:
+            h, _c, _s = search.search(ctx, sqb, sqo, srb, sro, m, THRESH['min_id'], THRESH['min_cov'], THRESH['min_ratio'])
+            ngh += len(h)
+        gdt = time.perf_counter() - g0
+        out['cpu_baseline'] = {'value': (len(sqo) - 1) / cdt, 'unit': 'genes/s', 'cores': 1, 'kind': 'port',
+                               'sample': '%d genes vs a %d bp genome, scalar search oracle (same search specification), 1 thread, %.1f s; '
+                                         'the GPU path on this same sample: %.0f genes/s; hit counts %d / %d' %
+                                         (len(sqo) - 1, len(srb), cdt, (len(sqo) - 1) / gdt, nh, ngh)}
+    return out
+
+
+def genes_of(genomes):
+    """the annotated genes of the genomes in coding orientation, longest first (PEPPAN's priority order, PEPPAN.py:1027)"""
+    comp = bytes.maketrans(b'ACGT', b'TGCA')
+    genes = []
+    for _, seq, annot in genomes:
+        sb = seq.tobytes()
+        for gid, a, b, strand in annot.tolist():
+            x = sb[a:b]
+            genes.append(x if strand > 0 else x.translate(comp)[::-1])
+    genes.sort(key=lambda x: -len(x))
+    return genes
+
+
+def config3_leg(ctx, rank, world, pg, genomes, qpin, qo, batch):
+    """BASELINE.json configs[2]: all-vs-all clustering of the genes of the genomes (the identity ladder of iterClust,
+    PEPPAN.py:1777-1792: getClust at 1.00, 0.99, ... 0.90 on the shrinking exemplar set, coverage 0.8) + the per-genome
+    search of the same genomes.  Every rank works on its own genomes (N>1: independent replicas of the leg)."""
+    from peppan_b200 import clust, search, seqio
+    genes = genes_of(genomes)
+    n0 = len(genes)
+    buf = np.frombuffer(b''.join(genes), dtype=np.uint8)
+    off = np.zeros(n0 + 1, np.int64); off[1:] = np.cumsum([len(g) for g in genes])
+    rungs = []
+    barrier(pg)
+    t0 = time.perf_counter()
+    cells = pairs = launches = 0
+    for iden in np.arange(1.0, 0.895, -0.01):
+        r0 = time.perf_counter()
+        rep, st = clust.cluster(ctx, buf, off, float(round(iden, 2)), 0.8)
+        keep = np.nonzero(rep == np.arange(len(rep)))[0]
+        lens = np.diff(off)[keep]
+        nb = np.concatenate([buf[off[i]:off[i + 1]] for i in keep]) if len(keep) else np.zeros(0, np.uint8)
+        no = np.zeros(len(keep) + 1, np.int64); no[1:] = np.cumsum(lens)
+        rungs.append({'identity': float(round(iden, 2)), 'genes_in': int(len(rep)), 'exemplars_out': int(len(keep)), 'seconds': time.perf_counter() - r0,
+                      'pairs_verified': int(st['n_pairs_verified']), 'sw_cells': float(st['sw_cells'])})
+        cells += st['sw_cells']; pairs += st['n_pairs_verified']; launches += st['kernel_launches']
+        buf, off = np.ascontiguousarray(nb), no
+    barrier(pg)
+    t_clu = allmax(pg, time.perf_counter() - t0)
+    # per-genome search of the same genomes against the exemplar pool
+    tbuf, toff = pack_genomes(ctx, genomes)
+    ng = len(genomes)
+    barrier(pg)
+    t0 = time.perf_counter()
+    nh = 0
+    for g0 in range(0, ng, batch):
+        g1 = min(ng, g0 + batch)
+        for m in (search.MODE_NT, search.MODE_PROT6):
+            hits, cig, goff, st = search.search_grouped_raw(ctx, qpin, qo, tbuf[toff[g0]:toff[g1]], toff[g0:g1 + 1] - toff[g0],
+                                                            np.arange(g1 - g0, dtype=np.int32), m, **THRESH)
+            nh += len(hits); launches += st['kernel_launches']
+    barrier(pg)
+    t_srch = allmax(pg, time.perf_counter() - t0)
+    return {'workload': 'configs[2]: %d synthetic genomes per GPU (%d genes): 11-rung identity ladder of iterClust through pb_cluster (coverage 0.8) '
+                        '+ per-genome search (nt + protein 6-frame) of the same genomes vs %d exemplars' % (ng, n0, len(qo) - 1),
+            'genomes_per_gpu': ng, 'named_size': ng >= 100, 'ladder_seconds': t_clu, 'genes_clustered_per_s': allsum(pg, float(n0)) / t_clu,
+            'ladder_gcups': cells / t_clu / 1e9, 'ladder_pairs_verified': int(pairs), 'final_exemplars': int(len(off) - 1), 'rungs': rungs,
+            'search_seconds': t_srch, 'search_genes_per_s': allsum(pg, float(ng)) * (len(qo) - 1) / t_srch, 'search_hits': int(nh), 'gpu_launches': int(launches)}
+
+
+def uberblast_leg(ctx, genomes, pool, n=2):
+    """The reference-level call: uberBlast(argv) with iter_map_bsn's flag set (PEPPAN.py:771), files in, blastab + overlaps out."""
+    from peppan_b200 import uberBlast as ub
+    ub.set_context(ctx)
+    tmp = tempfile.mkdtemp(prefix='pb_bench_')
+    try:
+        qry = os.path.join(tmp, 'exemplars.fa')
+        with open(qry, 'w') as f:
+            for name, s in pool.fasta_items():
+                f.write('>%s\n%s\n' % (name, s))
+        times, rows = [], 0
+        for gi, (idx, seq, _) in enumerate(genomes[:n + 1]):
+            ref = os.path.join(tmp, 'g%d.fa' % idx)
+            with open(ref, 'w') as f:
+                f.write('>g%d\n%s\n' % (idx, seq.tobytes().decode()))
+            t0 = time.perf_counter()
+            tab, ovl = ub.uberBlast(['-r', ref, '-q', qry, '-f', '-m', '-O', '--blastn', '--diamond', '--min_id', '0.4', '--min_cov', '50', '--min_ratio', '0.25',
+                                     '--merge_gap', '600', '--merge_diff', '1.5', '-t', '1', '-s', '1', '-e', '0,3', '--gtable', '11'])
+            if gi > 0:                       # the first call warms the file cache and the allocator
+                times.append(time.perf_counter() - t0); rows += len(tab)
+        return {'call': 'uberBlast(-r genome -q exemplars -f -m -O --blastn --diamond -s 1 -e 0,3 ...) = iter_map_bsn flag set (PEPPAN.py:771), FASTA files in, blastab rows + overlap table out',
+                'seconds_per_genome': float(np.mean(times)), 'genes_per_s': (N_CORE + N_ACC) / float(np.mean(times)), 'rows_per_genome': rows / max(len(times), 1), 'genomes_timed': len(times)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def main():
@@ -297,31 +503,42 @@ def main():
     ap.add_argument('--pairs', type=int, default=1000000, help='pairs per GPU per step (config 2: 1,000,000)')
     ap.add_argument('--cpu-pairs', type=int, default=400000, help='pairs in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--max-seconds', type=int, default=1200, help='hard limit for the whole run (watchdog)')
-    ap.add_argument('--no-search', action='store_true', help='skip the per-genome search leg (extra "search" object of the JSON line)')
+    ap.add_argument('--max-seconds', type=int, default=1500, help='hard limit for the whole run: all thread stacks are dumped and the run exits non-zero')
+    ap.add_argument('--config', type=int, default=0, choices=[0, 3, 4], help='3: config-3 leg at its named size (100 genomes); 4: config-4 leg only')
+    ap.add_argument('--genomes', type=int, default=1000, help='genomes of the config-4 leg (total over all ranks)')
+    ap.add_argument('--c3-genomes', type=int, default=10, help='genomes per GPU of the config-3 leg (named size: 100)')
+    ap.add_argument('--batch', type=int, default=16, help='genomes per pb_search_grouped call')
+    ap.add_argument('--no-search', action='store_true', help='skip the genome-scale legs')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.config == 3:
+        args.c3_genomes = max(args.c3_genomes, 100)
 
-    # a run that is still going after --max-seconds is wrong (a normal run takes 1-3 minutes): fail fast and loudly instead of
-    # holding the node -- under torchrun the non-zero exit of one rank takes the others down as well
-    def _too_long():
-        sys.stderr.write('bench.py: still running after %d s, giving up (rank %s)\n' % (args.max_seconds, os.environ.get('RANK', '0')))
-        sys.stderr.flush()
-        os._exit(3)
-    wd = threading.Timer(args.max_seconds, _too_long)
-    wd.daemon = True
-    wd.start()
-    rank, world, local, pg = dist_setup(args.gpus)
+    # a run still going after --max-seconds is wrong (a normal run takes a few minutes): dump every thread's stack (the
+    # diagnosis) and exit non-zero; under torchrun the failing rank takes the others down
+    faulthandler.dump_traceback_later(args.max_seconds, exit=True)
+    rank, world, local, pg = dist_setup()
     from peppan_b200 import dist as pbd, seqcodec, sw, workloads
     from peppan_b200._lib import Context
+
+    # ---- synthetic genomes of this rank (worker processes; before the CUDA context exists) ----
+    t_syn = time.perf_counter()
+    genomes, c3_genomes = [], []
+    if not args.no_search:
+        procs = max(1, min(16, (os.cpu_count() or 1) // world))
+        mine = pbd.shard_indices(args.genomes, rank, world) if args.config != 3 else []
+        extra = [args.genomes + rank * args.c3_genomes + i for i in range(args.c3_genomes)] if args.config != 4 else []
+        made = workloads.synth_genomes_parallel(mine + extra, N_CORE, N_ACC, procs=procs)
+        genomes, c3_genomes = made[:len(mine)], made[len(mine):]
+    t_syn = time.perf_counter() - t_syn
+
     # N > 1: the context carries an NCCL communicator (unique id handed out over gloo) for the hit-table allgather
-    ctx, nccl_note = (Context(local), None) if world == 1 else pbd.init_context_watchdog(pg, local, rank, world)
+    ctx = pbd.init_context_from_env(pg)
     info = ctx.device_info()
     params = seqcodec.protein_params()
     npairs = args.pairs
     q0, qoff0, t0, toff0 = workloads.sw_microbench_pairs(npairs, seed=workloads.SEED + rank)
-    # pinned host copies for the end-to-end leg
     q = ctx.pinned_empty(q0.shape, np.uint8); q[:] = q0
     t = ctx.pinned_empty(t0.shape, np.uint8); t[:] = t0
     qoff = ctx.pinned_empty(qoff0.shape, np.int64); qoff[:] = qoff0
@@ -366,29 +583,33 @@ def main():
     e2e_value = total_cells / (e2e_ms * 1e-3) / 1e9
     assert int(out['score'].astype(np.int64).sum()) == checksum
 
-    srch = None
+    c4 = c3 = ubl = None
     if not args.no_search:
-        srch = search_leg(ctx, rank, world, pg, max(1, min(args.steps, 3)), not args.no_cpu_baseline, gather=nccl_note is None)
-        if nccl_note:
-            srch['allgather_note'] = nccl_note
+        pool, qb, qo = exemplar_set()
+        qpin = ctx.pinned_empty(qb.shape, np.uint8); qpin[:] = qb
+        if args.config != 3:
+            c4 = config4_leg(ctx, rank, world, pg, genomes, args.genomes, qpin, qo, args.batch, not args.no_cpu_baseline)
+            c4['genome_synthesis_seconds_untimed'] = t_syn
+        if args.config != 4:
+            c3 = config3_leg(ctx, rank, world, pg, c3_genomes, qpin, qo, args.batch)
+        if rank == 0 and (genomes or c3_genomes):
+            ubl = uberblast_leg(ctx, genomes or c3_genomes, pool)
 
-    clu = None
-    if not args.no_search:
-        clu = cluster_leg(ctx, rank, world, pg)
-
+    barrier(pg)
     if rank != 0:
-        if nccl_note is not None:
-            os._exit(0)        # a helper thread may still sit inside NCCL
+        ctx.close()
         return 0
     # roofline of the dominant kernel (forward s16x2 DP kernel): DPX issue peak, measured live
     fwd_rate = ALGO_INSTR_PER_CELL * cells / (fwd_ms / args.steps * 1e-3)
+    step_rate = ALGO_INSTR_PER_CELL * cells / (dev_ms / args.steps * 1e-3)
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt = cpu_oracle_leg(args.cpu_pairs, threads)
+        v, dt, kind = cpu_sw_leg(args.cpu_pairs, threads)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': 'first %d pairs of the workload (score + end + start), scalar oracle port on %d threads, %.1f s' %
-                         (args.cpu_pairs, threads, dt)}
+               'sample': 'first %d pairs of the workload (score + end + start), %s, %d threads, %.1f s' % (args.cpu_pairs, kind, threads, dt),
+               'reference_tools': reference_tools_leg(threads)}
+    traffic, traffic_src = profiled_traffic()
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -399,25 +620,23 @@ def main():
                    'forward_ms_per_step': fwd_ms / args.steps, 'reverse_ms_per_step': rev_ms / args.steps,
                    'forward_gcups': cells / (fwd_ms / args.steps * 1e-3) / 1e9, 'score_checksum': checksum,
                    'sm_count': info['sm_count']},
-        'roofline': {'bound': 'int_dpx', 'kernel': 'sw_kernel<G16,K19,R2,long-chain,s16x2,forward>', 'achieved': fwd_rate / 1e12, 'peak': peak / 1e12,
-                     'unit': 'T lane-instr/s', 'frac': fwd_rate / peak, 'traffic': profiled_traffic(),
+        'roofline': {'bound': 'int_dpx', 'kernel': 'sw_kernel<s16x2,forward>', 'achieved': fwd_rate / 1e12, 'peak': peak / 1e12,
+                     'unit': 'T lane-instr/s', 'frac': fwd_rate / peak, 'frac_whole_step': step_rate / peak, 'traffic': traffic,
                      'hbm': hbm_view(float(npairs) * (600 + 32 + 12), fwd_ms / args.steps),
                      'note': 'achieved = 3.5 DPX instr/cell (SURVEY 8d) x cells / forward-kernel time; peak = live dependent-free '
-                             'VIADDMNMX.S16x2 issue rate on all SMs (pb_measure_dpx_peak); traffic = dram bytes per forward launch from '
-                             'profiles/r01_sw_kernel_ncu_full.txt (1M pairs): ~ the 0.6 GB of sequences, HBM is not the bound'},
+                             'VIADDMNMX.S16x2 issue rate on all SMs (pb_measure_dpx_peak); frac_whole_step = the same count over forward + '
+                             'reverse (start-finding) time; traffic = dram bytes per forward launch from profiles/%s' % traffic_src},
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(est['h2d_bytes']), 'd2h_bytes_per_step': int(est['d2h_bytes']),
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': launches,
         'clocks': clocks,
-        'search': srch,
-        'cluster': clu,
+        'config4': c4,
+        'config3': c3,
+        'uberblast': ubl,
     }
     print(json.dumps(line), flush=True)
-    if nccl_note is None:
-        ctx.close()
-    else:
-        os._exit(0)            # a helper thread may still sit inside NCCL
+    ctx.close()
     return 0
 
 

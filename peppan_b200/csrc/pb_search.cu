@@ -903,14 +903,16 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
             if (win[i].tlen > 0) { cells += (double)QL.len[win[i].qid] * (double)win[i].tlen; ++st.n_windows; }
         }
         pb_sw_job* J = nullptr;
+        // forward pass (score + end cell) for every window; the start cell and the path come from one banded reverse pass
         int rc = pb_sw_job_create_views_dev(ctx, d_qc.as<uint8_t>(), d_tc.as<uint8_t>(), d_wqb.as<int64_t>(), d_wqe.as<int64_t>(), d_wtb.as<int64_t>(),
-                                            d_wte.as<int64_t>(), nw, cells, &sp, 1, &J);
+                                            d_wte.as<int64_t>(), nw, cells, &sp, 0, &J);
         if (rc) return rc;
         std::unique_ptr<pb_sw_job> guard(J);
         pb_sw_stats sst; memset(&sst, 0, sizeof(sst));
         rc = pb_sw_job_run(ctx, J, &sst); if (rc) return rc;
-        rc = pb_sw_job_fetch(ctx, J, score.data(), aqs.data(), aqe.data(), ats.data(), ate.data()); if (rc) return rc;
-        // thresholds that do not need the path (E-value, aligned query span) are applied before the traceback
+        rc = pb_sw_job_fetch(ctx, J, score.data(), nullptr, aqe.data(), nullptr, ate.data()); if (rc) return rc;
+        // thresholds that the forward result already decides (E-value; the aligned query span cannot exceed the end row + 1)
+        // are applied before the reverse pass
         {
             const double lam0 = nt ? 0.625 : 0.267, K0 = nt ? 0.41 : 0.041, emax0 = nt ? 1e-2 : 1.0;
             for (int64_t i = 0; i < nw; ++i) {
@@ -918,13 +920,14 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
                 const int qid = win[i].qid;
                 const double m_eff = nt ? (double)qlen_nt[qid] : (double)QL.len[qid];
                 const double ev = K0 * m_eff * 5.0e6 * std::exp(-lam0 * (double)score[i]);
-                const double qspan = (double)(aqe[i] - aqs[i] + 1) * (nt ? 1.0 : 3.0);
-                if (ev > emax0 || qspan < prm->min_cov || qspan < prm->min_ratio * (double)qlen_nt[qid]) score[i] = 0;
+                const double qspan_max = (double)(aqe[i] + 1) * (nt ? 1.0 : 3.0);
+                if (ev > emax0 || qspan_max < prm->min_cov || qspan_max < prm->min_ratio * (double)qlen_nt[qid]) score[i] = 0;
             }
         }
-        int tl_launch = 0;
-        rc = pb_sw_trace(ctx, J, qb.data(), tb.data(), score.data(), aqs.data(), aqe.data(), ats.data(), ate.data(), counts.data(), coff.data(), &cops, &ms_trace, &tl_launch);
+        pb_trace_stats tst; memset(&tst, 0, sizeof(tst));
+        rc = pb_sw_trace(ctx, J, qb.data(), tb.data(), score.data(), aqe.data(), ate.data(), aqs.data(), ats.data(), counts.data(), coff.data(), &cops, &tst);
         if (rc) return rc;
+        ms_trace = tst.ms; const int tl_launch = tst.launches;
         st.sw_cells = sst.cells; st.ms_sw = sst.ms_total_device; st.ms_trace = ms_trace;
         launches += sst.kernel_launches + tl_launch;
     }

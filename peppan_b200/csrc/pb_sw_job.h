@@ -31,8 +31,10 @@ int pb_sw_job_create_views_dev(pb_ctx* ctx, const uint8_t* dq, const uint8_t* dt
                                const int64_t* d_tbeg, const int64_t* d_tend, int64_t npairs, double cells,
                                const pb_score_params* params, int want_coords, pb_sw_job** job);
 
-// Traceback over an already run job (pb_trace.cu).  qbeg/tbeg: host begins of every pair in the device code arrays.
-// Outputs as in pb_sw_align_batch.
-int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* tbeg, const int32_t* score, const int32_t* qs,
-                const int32_t* qe, const int32_t* ts, const int32_t* te, int32_t* counts, int64_t* cigar_off,
-                uint32_t** cigar_ops, float* ms_trace, int* launches);
+// Alignment start + traceback over a job whose forward pass has run (pb_trace.cu: one banded reverse pass that finds the
+// start cell and records the path).  qbeg/tbeg: host begins of every pair in the device code arrays; score/qe/te: forward
+// results on the host (pairs with score <= 0 are skipped).  Outputs as in pb_sw_align_batch.
+struct pb_trace_stats { float ms; int launches; double band_cells, prefix_cells; };
+int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* tbeg, const int32_t* score, const int32_t* qe,
+                const int32_t* te, int32_t* qs, int32_t* ts, int32_t* counts, int64_t* cigar_off,
+                uint32_t** cigar_ops, pb_trace_stats* stats);

@@ -1,23 +1,36 @@
-// Traceback (CIGAR) for aligned pairs: pb_sw_align_batch.
+// Alignment start + traceback (CIGAR) for pairs whose forward pass is done: pb_sw_trace, pb_sw_align_batch.
 //
-// After the forward and reverse passes the alignment box [qs..qe] x [ts..te] of every pair is
-// known.  The oracle defines the path as the traceback of the REVERSE DP (oracle/pb_oracle.c), so
-// this file recomputes that DP restricted to the box (a prefix rectangle of the reverse DP, hence
-// identical values), records 4 direction bits per cell, and walks them:
-//   bits 0-1  H source: 0 stop (H == 0), 1 diagonal, 2 E, 3 F  (priority diagonal > E > F)
-//   bit  2    E came from H (gap opened here; preferred over extension on ties)
-//   bit  3    F came from H
-// The DP kernel uses the same systolic strip layout as the score kernel (group of G lanes, K
-// columns per lane in registers, rows streamed, profile in shared memory), in s32, one pair per
-// group.  Direction words are written step-major ([block][step][lane][word]) so that every step
-// of a group is one contiguous, coalesced store.  A second kernel (one warp per pair) walks the
-// directions from the start cell to the origin, which emits the ops in alignment order; the warp
-// reads 32 cells along the current diagonal at once and consumes the whole diagonal run with ballots.
+// The oracle defines start cell and path through the REVERSE DP (oracle/pb_oracle.c): the same recurrences run from the
+// forward end cell (qe, te) over the reversed prefixes; the start is the first cell in row-major order holding the forward
+// score S, the path is the traceback from that cell.  One kernel does both here, inside an EXACT score-bounded band:
 //
-// Long boxes (WAVE): as in the score kernel, the column blocks of one pair are taken by different warps
-// (G = 32, 512 columns each) and run as a pipeline over the machine, each block a few rows behind its left
-// neighbour (border column + release/acquire progress counter in global memory), so that one 9.5 kb x 9.5 kb
-// box takes ~M + 32 * blocks steps instead of blocks * M.
+//   every alignment that ends in (qe, te) with score S leaves at most
+//       I <= (Uq - S - go) / (f + ge)   query residues and   D <= (Uq - S - go) / ge   target residues unaligned,
+//       D <= (Ut - S - go) / (f + ge)                         I <= (Ut - S - go) / ge
+//   where Uq (Ut) is the sum over the query (target) prefix of r(c) = max(best score symbol c can reach, f) and f the
+//   smallest positive such best score: an aligned residue earns at most r(c), an unaligned one forfeits at least f, the
+//   first gap costs go and every gap residue ge.  Cells of the reverse DP off the diagonals [-I, +D] therefore lie on no
+//   co-optimal path; treating them as empty (H = 0) can only lower the values of cells that are themselves on no
+//   co-optimal path, so the cells holding S, the values along every co-optimal path and all tie-breaks (which compare
+//   only candidates that reach the cell's value) are those of the full matrix (checked against the oracle's full
+//   traceback by tests/test_sw_gpu.py and tests/test_search_gpu.py; on the CPU by orc_band_trace).
+//
+// Layout: systolic strips as in the score kernel (pb_sw_kernel.cuh) -- a group of G lanes owns one pair, lane l keeps K
+// columns of H and E in registers, rows are streamed R = 2 per step, lane l runs one step behind lane l-1 -- but a column
+// block b (W = G*K columns) only visits the rows the band can touch, [b*W - D, (b+1)*W - 1 + I]; rows above are empty,
+// the column border between blocks lives in a small global buffer.  s32 values, one pair per group.  Four direction bits per
+// cell are kept as four bit planes (one 32-bit word per plane, lane and step: R = 2 rows x 16 columns), each bit the SIGN of
+// a difference the recurrences have at hand, shifted into its plane by one funnel shift:
+//   plane 0  d - H        set: H did not come from the diagonal          (H source priority: diagonal > E > F; a path
+//   plane 1  E - H        set: H did not come from E                      cell never holds H == 0, see below)
+//   plane 2  Hup - E'     set: E extended a gap (clear: opened here; opening is preferred on ties)
+//   plane 3  Hleft - F'   set: F extended a gap
+// (A co-optimal path cannot pass through a cell with H == 0 other than by leaving the matrix at the origin: the rest of the
+// path would be an alignment with the full score S ending in an earlier row or column than the forward end cell, which is
+// the row-major-first maximum.  So no "stop" state is recorded.)
+// The first row-major cell with H == S is tracked exactly; once it is known, later blocks stop at its row.
+// A second kernel (one warp per pair) walks the directions from that cell to the origin, which emits the ops in alignment
+// order; the warp reads 32 cells along the current diagonal at once and consumes the whole diagonal run with ballots.
 #include "pb_sw_job.h"
 #include <algorithm>
 #include <chrono>
@@ -28,33 +41,32 @@ using namespace pbsw;
 
 namespace {
 
-constexpr int TR_G = 16, TR_K = 16, TR_R = 2, TR_WARPS = 8;     // R rows per step, interleaved one column apart (ILP, as in the score kernel)
-constexpr int TR_W = TR_G * TR_K;
-constexpr int TR_KW8 = TR_K / 8;        // direction words per lane per step
-constexpr int TRW_G = 32, TRW_K = 16, TRW_R = 2, TRW_W = TRW_G * TRW_K;   // wavefront variant: whole warps, thin strips (256 columns per block)
-constexpr int WAVE_MIN_COLS = 4 * TR_W + 1, WAVE_MIN_ROWS = 768;   // boxes at least this large are pipelined across warps
+constexpr int TB_R = 2, TB_WARPS = 8;
+struct TbShape { int G, K; };
+constexpr TbShape TB_NARROW{4, 16};        // W = 64: little overshoot around a narrow band
+constexpr TbShape TB_WIDE{16, 16};         // W = 256: fewer, longer blocks for wide bands
+constexpr TbShape TB_XWIDE{32, 16};        // W = 512: a whole warp per pair for very wide bands / very long pairs (latency of the tail)
+__host__ __device__ inline TbShape tb_shape(int cls) { return cls == 0 ? TbShape{4, 16} : (cls == 1 ? TbShape{16, 16} : TbShape{32, 16}); }
 
-struct TraceDesc {
-    long long qoff, toff;   // start of the box in the code arrays
+struct BandDesc {
+    long long qoff, toff;   // start of the pair's query / target view in the code arrays
     long long doff;         // offset (words) of this pair's direction block
-    int M, N;               // box rows / columns
+    int qe, te;             // forward end cell; reverse DP row i <-> query qe - i, column j <-> target te - j
+    int S;                  // forward score
+    int imax, dmax;         // band: -imax <= j - i <= dmax
     int id;                 // pair id
-    int wave;               // 1: direction block laid out by the wavefront variant (G = 32)
-    int wslot;              // WAVE: first border / progress slot of the pair
+    int smax;               // steps reserved per column block
+    int nblk;               // column blocks
+    int wide;               // shape class: 0 TB_NARROW, 1 TB_WIDE, 2 TB_XWIDE
     int pad;
 };
 
-inline bool is_wave(int M, int N) { return N >= WAVE_MIN_COLS && M >= WAVE_MIN_ROWS; }
-inline size_t dir_words(int M, int N, bool wave)
-{
-    const int G = wave ? TRW_G : TR_G, K = wave ? TRW_K : TR_K, R = wave ? TRW_R : TR_R, W = G * K;
-    return (size_t)((N + W - 1) / W) * (size_t)((M + R - 1) / R + G - 1) * G * R * (K / 8);
-}
+struct BandTab { int8_t rq[32], rt[32]; int floor_q, floor_t, go, ge; };
 
 struct TraceArgs {
     const uint8_t* q;
     const uint8_t* t;
-    const TraceDesc* desc;
+    const BandDesc* desc;
     int count;
     int* counter;
     const int8_t* matrix;
@@ -62,17 +74,39 @@ struct TraceArgs {
     uint32_t* dir;
     uint2* boundary;
     int bstride;
-    int* progress;          // WAVE: rows published per (pair, column block) border (zeroed before launch)
-    const int2* wsub;       // WAVE: (pair, column block) sub-tasks in launch order
-    int nsub;
+    int2* start;            // per pair: (row, col) of the first row-major cell holding S, (-1, -1) if none
 };
 
-template <int G, int K, int R, int WARPS, int MINB, bool WAVE>
-__global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceArgs a)
+// one warp per pair: Uq, Ut over the prefixes -> band
+__global__ void band_bounds_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ t, BandDesc* desc, int count, BandTab tab)
 {
-    static_assert(!WAVE || G == 32, "the wavefront variant uses whole warps");
-    static_assert(32 % R == 0, "border batches hold whole steps");
-    constexpr int KW = (K + 3) / 4, KP = KW * 4, NG = 32 / G, W = G * K, KW8 = K / 8;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (x >= count) return;
+    BandDesc d = desc[x];
+    long long uq = 0, ut = 0;
+    for (int i = lane; i <= d.qe; i += 32) uq += tab.rq[q[d.qoff + i] & 31];
+    for (int j = lane; j <= d.te; j += 32) ut += tab.rt[t[d.toff + j] & 31];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { uq += __shfl_xor_sync(0xffffffffu, uq, o); ut += __shfl_xor_sync(0xffffffffu, ut, o); }
+    if (lane == 0) {
+        long long imax = d.qe, dmax = d.te;                      // full matrix
+        if (tab.floor_q > 0) {
+            const long long b = uq - d.S - tab.go;
+            imax = min(imax, b >= 0 ? b / (tab.floor_q + tab.ge) : 0ll); dmax = min(dmax, b >= 0 ? b / tab.ge : 0ll);
+        }
+        if (tab.floor_t > 0) {
+            const long long b = ut - d.S - tab.go;
+            dmax = min(dmax, b >= 0 ? b / (tab.floor_t + tab.ge) : 0ll); imax = min(imax, b >= 0 ? b / tab.ge : 0ll);
+        }
+        desc[x].imax = (int)imax; desc[x].dmax = (int)dmax;
+    }
+}
+
+template <int G, int K, int R, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) sw_band_trace_kernel(const TraceArgs a)
+{
+    static_assert(R == 2 && K <= 16, "direction planes hold two rows of at most 16 columns per word");
+    constexpr int KW = (K + 3) / 4, KP = KW * 4, NG = 32 / G, W = G * K;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint8_t smem[];
     int8_t* smat = reinterpret_cast<int8_t*>(smem);
@@ -83,44 +117,43 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceA
     const int nsym = a.nsym, PAD = nsym - 1, rowBytes = G * KP;
     uint8_t* prof = smem + 1024 + (size_t)(warp * NG + g) * nsym * rowBytes;
     const int gwarp = blockIdx.x * WARPS + warp;
-    uint2* mybound = (a.boundary && !WAVE) ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
+    uint2* mybound = a.boundary + ((size_t)gwarp * NG + g) * a.bstride;
     const int ge = a.ge, goe = a.go + a.ge;
 
     for (;;) {
-        int bundle = 0, wblock = 0;
+        int bundle = 0;
         if (lane == 0) bundle = atomicAdd(a.counter, 1);
         bundle = __shfl_sync(FULL, bundle, 0);
-        if (WAVE) {
-            if (bundle >= a.nsub) break;
-            const int2 sub = a.wsub[bundle];
-            bundle = sub.x; wblock = sub.y;
-        }
         if (bundle * NG >= a.count) break;
         const int task = bundle * NG + g;
-        int M = 0, N = 0, wslot = 0;
+        int mcap = 0, ncol = 0, S = 0x7fffffff, imax = 0, dmax = 0, smax = 0, nblk = 0, qe = 0, te = 0;
         const uint8_t *qb = a.q, *tb = a.t;
         long long doff = 0;
         if (task < a.count) {
-            TraceDesc d = a.desc[task];
-            M = d.M; N = d.N; qb = a.q + d.qoff; tb = a.t + d.toff; doff = d.doff; wslot = d.wslot;
+            const BandDesc d = a.desc[task];
+            qe = d.qe; te = d.te; mcap = d.qe + 1; ncol = d.te + 1; S = d.S; imax = d.imax; dmax = d.dmax; smax = d.smax; nblk = d.nblk;
+            qb = a.q + d.qoff; tb = a.t + d.toff; doff = d.doff;
         }
-        uint2* wavebound = WAVE ? a.boundary + (size_t)wslot * a.bstride : nullptr;
-        int* waveprog = WAVE ? a.progress + wslot : nullptr;
-        int mw = M, nw = N;
+        int nblk_w = nblk;
 #pragma unroll
-        for (int o = 16; o >= G; o >>= 1) {
-            mw = max(mw, __shfl_xor_sync(FULL, mw, o));
-            nw = max(nw, __shfl_xor_sync(FULL, nw, o));
-        }
-        const int nblocks = (nw + W - 1) / W;
-        const int nsteps_own = (M + R - 1) / R + G - 1;
+        for (int o = 16; o >= G; o >>= 1) nblk_w = max(nblk_w, __shfl_xor_sync(FULL, nblk_w, o));
+        int brow = 0x7fffffff, bcol = 0x7fffffff;          // first row-major cell holding S seen by this lane
 
-        for (int b = WAVE ? wblock : 0; b < (WAVE ? wblock + 1 : nblocks); ++b) {
+        for (int b = 0; b < nblk_w; ++b) {
+            // rows of this block for this group's pair; a group without work in the block idles through it
+            const int rlo = max(0, b * W - dmax), rhi = min(mcap - 1, (b + 1) * W - 1 + imax);
+            const bool act = b < nblk && rlo <= rhi;
+            const int steps_own = act ? (rhi - rlo + R) / R + G - 1 : 0;
+            int slimit = steps_own;
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) slimit = max(slimit, __shfl_xor_sync(FULL, slimit, o));
+            if (slimit == 0) continue;
+            const int hi_prev = min(mcap - 1, b * W - 1 + imax);      // last row the previous block wrote that is still in range
             const int col0 = b * W + l * K;
             {
                 int tc[K];
 #pragma unroll
-                for (int p = 0; p < K; ++p) { int j = col0 + p; tc[p] = (j < N) ? (int)__ldg(tb + (N - 1 - j)) : PAD; }
+                for (int p = 0; p < K; ++p) { const int j = col0 + p; tc[p] = (act && j < ncol) ? (int)__ldg(tb + (te - j)) : PAD; }
                 for (int c = 0; c < nsym; ++c) {
                     const int8_t* mrow = smat + c * 32;
                     uint32_t* dst = reinterpret_cast<uint32_t*>(prof + c * rowBytes + l * KP);
@@ -128,7 +161,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceA
                     for (int w = 0; w < KW; ++w) {
                         uint32_t v = 0;
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) { int p = w * 4 + x; if (p < K) v |= ((uint32_t)(uint8_t)mrow[tc[p]]) << (8 * x); }
+                        for (int x = 0; x < 4; ++x) { const int p = w * 4 + x; if (p < K) v |= ((uint32_t)(uint8_t)mrow[tc[p]]) << (8 * x); }
                         dst[w] = v;
                     }
                 }
@@ -137,22 +170,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceA
             int H[K], E[K];     // last finished row of the strip; E holds E + goe, as in the score kernel
 #pragma unroll
             for (int p = 0; p < K; ++p) { H[p] = 0; E[p] = 0; }
-            int hlast[R], fout[R], hl_prev = 0;
+            int hlast[R], fout[R];
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) { hlast[rr] = 0; fout[rr] = 0; }
-            const int slimit = (mw + R - 1) / R + G - 1;
-            const bool in_block = (b * W < N);       // this pair has real columns in this block
-            uint32_t* dbase = a.dir + doff + (size_t)b * nsteps_own * G * R * KW8;
+            // diagonal neighbour of the block's first cell: (rlo - 1, b*W - 1) sits on the band edge and comes from the border
+            int hl_prev = 0;
+            if (l == 0 && act && b > 0 && rlo >= 1 && rlo - 1 <= hi_prev) hl_prev = (int)mybound[rlo - 1].x;
+            uint32_t* dbase = a.dir + doff + (size_t)b * smax * G * 4;
             int cq[R];
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) { const int i0 = -l * R + rr; cq[rr] = ((unsigned)i0 < (unsigned)M) ? (int)__ldg(qb + (M - 1 - i0)) : PAD; }
-            if (WAVE) mybound = wavebound + (size_t)b * a.bstride;
-            const uint2* leftbound = WAVE ? (b > 0 ? wavebound + (size_t)(b - 1) * a.bstride : nullptr) : mybound;
-            int published = 0;                  // WAVE: rows of the left border known to be complete
-            int bat0 = -32;                     // WAVE: first row of the border batch held in `bat`
-            uint2 bat = make_uint2(0u, 0u);
+            for (int rr = 0; rr < R; ++rr) { const int i0 = rlo - l * R + rr; cq[rr] = (act && l == 0 && i0 <= rhi) ? (int)__ldg(qb + (qe - i0)) : PAD; }
+            const bool lead = l == 0 && b > 0 && act;       // this lane reads the block's left border
+            uint2 bnext[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) bnext[rr] = (lead && rlo + rr <= hi_prev) ? mybound[rlo + rr] : make_uint2(0u, 0u);
             for (int s = 0; s < slimit; ++s) {
-                const int r0 = (s - l) * R;
+                const int r0 = rlo + (s - l) * R;
                 uint32_t w[R][KW];
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
@@ -161,37 +194,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceA
                     for (int x = 0; x < KW; ++x) w[rr][x] = r[x];
                 }
 #pragma unroll
-                for (int rr = 0; rr < R; ++rr) { const int in = r0 + R + rr; cq[rr] = ((unsigned)in < (unsigned)M) ? (int)__ldg(qb + (M - 1 - in)) : PAD; }
+                for (int rr = 0; rr < R; ++rr) {
+                    const int in = r0 + R + rr;
+                    cq[rr] = (act && s + 1 >= l && in <= rhi) ? (int)__ldg(qb + (qe - in)) : PAD;
+                }
                 int hl[R], fh[R];
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
                     hl[rr] = __shfl_up_sync(FULL, hlast[rr], 1, G); fh[rr] = __shfl_up_sync(FULL, fout[rr], 1, G);
                     if (l == 0) { hl[rr] = 0; fh[rr] = 0; }
                 }
-                if (WAVE) {
-                    // border cells of block b-1 in coalesced batches of 32 rows (lane j holds row bat0 + j); the warp stays
-                    // >= 32 rows behind the owner of block b-1, so a batch is complete when it is needed
-                    const int row0 = s * R;                // rows of lane 0 in this step (warp-uniform)
-                    if (b > 0 && row0 < mw) {
-                        if (row0 >= bat0 + 32) {
-                            const int want = min(row0 + 32, mw);
-                            while (published < want) {
-                                published = ld_acquire(waveprog + (b - 1));
-                                if (published < want) __nanosleep(100);
-                            }
-                            bat0 = row0;
-                            bat = (bat0 + lane < mw) ? ld_volatile_u2(leftbound + bat0 + lane) : make_uint2(0u, 0u);
-                        }
+                if (lead) {
+                    // border cells of this step were requested one step ago; request the next step's now (L2 latency off the chain)
 #pragma unroll
-                        for (int rr = 0; rr < R; ++rr) {
-                            const uint32_t vx = __shfl_sync(FULL, bat.x, row0 + rr - bat0), vy = __shfl_sync(FULL, bat.y, row0 + rr - bat0);
-                            if (l == 0 && row0 + rr < mw) { hl[rr] = (int)vx; fh[rr] = (int)vy; }
-                        }
+                    for (int rr = 0; rr < R; ++rr) {
+                        if (r0 + rr <= hi_prev) { hl[rr] = (int)bnext[rr].x; fh[rr] = (int)bnext[rr].y; }
+                        if (r0 + R + rr <= hi_prev) bnext[rr] = mybound[r0 + R + rr];
                     }
-                } else if (l == 0 && b > 0) {
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr)
-                        if ((unsigned)(r0 + rr) < (unsigned)mw) { uint2 v = leftbound[r0 + rr]; hl[rr] = (int)v.x; fh[rr] = (int)v.y; }
                 }
                 // diagonal / left neighbours of column 0: row rr takes its diagonal from the left lane's row rr-1
                 int hdiag[R], hleft[R];
@@ -201,11 +220,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceA
                 hl_prev = hl[R - 1];
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) hleft[rr] = hl[rr];
-                uint32_t codes[R][KW8];
+                uint32_t pl[R][4];                   // direction bit planes of the step's rows
+                int rmax[R];
+                int hrow[R > 1 ? R - 1 : 1][K];      // H of the non-final rows of the step (read only when S shows up)
 #pragma unroll
-                for (int rr = 0; rr < R; ++rr)
+                for (int rr = 0; rr < R; ++rr) {
+                    rmax[rr] = 0;
 #pragma unroll
-                    for (int x = 0; x < KW8; ++x) codes[rr][x] = 0;
+                    for (int x = 0; x < 4; ++x) pl[rr][x] = 0;
+                }
 #pragma unroll
                 for (int p = 0; p < K; ++p) {
                     int hup = H[p], eprev = E[p];
@@ -218,74 +241,95 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_trace_kernel(const TraceA
                             case 2: sc = (int)prmt(w[rr][p >> 2], 0u, 0xaaa2u); break;
                             default: sc = (int)prmt(w[rr][p >> 2], 0u, 0xbbb3u); break;
                         }
-                        // F + goe of this cell from the cell to the left; E + goe from the cell above; a tie means "opened here"
+                        // F + goe of this cell from the cell to the left; E + goe from the cell above
                         const int fnew = __viaddmax_s32(fh[rr], -ge, hleft[rr]);
-                        const bool fopen = (fnew == hleft[rr]);
-                        fh[rr] = fnew;
                         const int eh = __viaddmax_s32(eprev, -ge, hup);
-                        const bool eopen = (eh == hup);
-                        const int mg = __vimax3_s32(eh, fnew, goe) - goe;     // max(0, E, F)
+                        const int m3 = __vimax3_s32(eh, fnew, goe);           // max(0, E, F) + goe
                         const int d = hdiag[rr] + sc;
-                        const int hn = max(d, mg);
-                        // H source: stop (H == 0) > diagonal > E > F
-                        uint32_t code = (eh == hn + goe) ? 2u : 3u;
-                        code = (hn == d) ? 1u : code;
-                        code = (hn == 0) ? 0u : code;
-                        uint32_t cw = codes[rr][p >> 3] + (code << (4 * (p & 7)));
-                        if (eopen) cw |= 4u << (4 * (p & 7));
-                        if (fopen) cw |= 8u << (4 * (p & 7));
-                        codes[rr][p >> 3] = cw;
+                        const int hn = max(d, m3 - goe);
+                        pl[rr][0] = __funnelshift_l((uint32_t)(d - hn), pl[rr][0], 1);
+                        pl[rr][1] = __funnelshift_l((uint32_t)(eh - (hn + goe)), pl[rr][1], 1);
+                        pl[rr][2] = __funnelshift_l((uint32_t)(hup - eh), pl[rr][2], 1);
+                        pl[rr][3] = __funnelshift_l((uint32_t)(hleft[rr] - fnew), pl[rr][3], 1);
+                        fh[rr] = fnew;
                         hdiag[rr] = hup;          // diagonal of the next column in this row
                         hleft[rr] = hn;
                         hup = hn; eprev = eh;     // the row below sees this cell as "up"
+                        if (rr < R - 1) hrow[rr][p] = hn;
+                        if (p & 1) rmax[rr] = __vimax3_s32(rmax[rr], hn, (rr < R - 1) ? hrow[rr][p - 1] : H[p - 1]);
+                        else if (p == K - 1) rmax[rr] = max(rmax[rr], hn);
                     }
                     H[p] = hup; E[p] = eprev;
                 }
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) { hlast[rr] = hleft[rr]; fout[rr] = fh[rr]; }
-                if (nblocks > 1 && l == G - 1 && b + 1 < nblocks) {
+                if (l == G - 1 && act && b + 1 < nblk) {
 #pragma unroll
                     for (int rr = 0; rr < R; ++rr)
-                        if ((unsigned)(r0 + rr) < (unsigned)mw) mybound[r0 + rr] = make_uint2((uint32_t)hlast[rr], (uint32_t)fout[rr]);
-                    const int st = s - l;                  // step index of this lane's rows
-                    if (WAVE && r0 >= 0 && r0 < mw && ((st & 15) == 15 || r0 + R >= mw)) st_release(waveprog + b, min(r0 + R, mw));
+                        if (r0 + rr >= rlo && r0 + rr <= rhi) mybound[r0 + rr] = make_uint2((uint32_t)hlast[rr], (uint32_t)fout[rr]);
                 }
-                if (in_block && s < nsteps_own) {
-                    uint32_t* dst = dbase + ((size_t)s * G + l) * R * KW8;
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr)
-#pragma unroll
-                        for (int x = 0; x < KW8; ++x) dst[rr * KW8 + x] = codes[rr][x];
+                if (act && s < steps_own) {
+                    // row 0 of the step in the high half, row 1 in the low half; column p at bit K - 1 - p of its half
+                    uint32_t* dst = dbase + ((size_t)s * G + l) * 4;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4((pl[0][0] << 16) | pl[R - 1][0], (pl[0][1] << 16) | pl[R - 1][1],
+                                                                (pl[0][2] << 16) | pl[R - 1][2], (pl[0][3] << 16) | pl[R - 1][3]);
                 }
+                // the forward score can only show up on a real row of the band (S is the maximum of the whole matrix): rare
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const int r = r0 + rr;
+                    if (rmax[rr] >= S && act && r >= rlo && r <= rhi && r < brow) {
+#pragma unroll
+                        for (int p = K - 1; p >= 0; --p) {
+                            const int hv = (rr < R - 1) ? hrow[rr][p] : H[p];
+                            if (hv == S && col0 + p < ncol) { brow = r; bcol = col0 + p; }
+                        }
+                    }
+                }
+            }
+            // the group's first cell so far; later blocks need not go below its row
+            {
+                int fr = brow, fc = bcol;
+#pragma unroll
+                for (int o = G / 2; o >= 1; o >>= 1) {
+                    const int orow = __shfl_xor_sync(FULL, fr, o), ocol = __shfl_xor_sync(FULL, fc, o);
+                    if (orow < fr || (orow == fr && ocol < fc)) { fr = orow; fc = ocol; }
+                }
+                brow = fr; bcol = fc;
+                if (fr != 0x7fffffff) mcap = min(mcap, fr + 1);
             }
             __syncwarp();
         }
+        if (l == 0 && task < a.count) a.start[task] = (brow != 0x7fffffff) ? make_int2(brow, bcol) : make_int2(-1, -1);
     }
 }
 
-// One warp per pair: walk the direction words from the start cell (M-1, N-1 in reverse coordinates) to the
-// origin.  In the H state lane k looks at cell (i-k, j-k); the run of leading "diagonal" cells is consumed at once
-// (ballot), gap cells are walked one at a time with a warp-uniform load.  WRITE = false counts ops and match
-// statistics, WRITE = true stores the run-length ops at ops[ooff[pair]].
+// One warp per pair: walk the direction words from the start cell to the origin.  In the H state lane k looks at cell
+// (i-k, j-k); the run of leading "diagonal" cells is consumed at once (ballot), gap cells are walked one at a time with a
+// warp-uniform load.  WRITE = false counts ops and match statistics, WRITE = true stores the run-length ops at ops[ooff[pair]].
 template <bool WRITE>
-__global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDesc* desc, int count, const uint32_t* dir,
+__global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const BandDesc* desc, const int2* start, int count, const uint32_t* dir,
                                int* nops, int* counts, const long long* ooff, uint32_t* ops)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int R = TB_R;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (x >= count) return;
-    const TraceDesc d = desc[x];
-    const int G = d.wave ? TRW_G : TR_G, K = d.wave ? TRW_K : TR_K, R = d.wave ? TRW_R : TR_R, KW8 = K / 8, W = G * K;
+    const BandDesc d = desc[x];
+    const int2 st0 = start[x];
+    const int G = tb_shape(d.wide).G, K = tb_shape(d.wide).K, W = G * K;
     const uint8_t* qb = q + d.qoff; const uint8_t* tb = t + d.toff;
-    const int nsteps = (d.M + R - 1) / R + G - 1;
     const uint32_t* base = dir + d.doff;
+    // bit 0: H from the diagonal, bit 1: H from E, bit 2: E opened here, bit 3: F opened here (planes store the negations)
     auto fetch = [&](int ii, int jj) -> int {
         const int b = jj / W, jr = jj - b * W, l = jr / K, p = jr - l * K;
-        const int st = ii / R + l, rr = ii - (ii / R) * R;
-        const uint32_t wv = base[((((size_t)b * nsteps + st) * G + l) * R + rr) * KW8 + (p >> 3)];
-        return (int)((wv >> (4 * (p & 7))) & 15);
+        const int rl = max(0, b * W - d.dmax), ro = ii - rl;
+        const int st = ro / R + l, rr = ro - (ro / R) * R;
+        const uint4 wv = *reinterpret_cast<const uint4*>(base + (((size_t)b * d.smax + st) * G + l) * 4);
+        const int sh = (rr == 0 ? 16 : 0) + (K - 1 - p);
+        return (int)((((~wv.x) >> sh) & 1u) | ((((~wv.y) >> sh) & 1u) << 1) | ((((~wv.z) >> sh) & 1u) << 2) | ((((~wv.w) >> sh) & 1u) << 3));
     };
-    int i = d.M - 1, j = d.N - 1, state = 0;
+    int i = st0.x, j = st0.y, state = 0;
     int cur = -1, len = 0, n = 0, nm = 0, nx = 0, ngo = 0, ngb = 0;
     uint32_t* out = WRITE ? ops + ooff[x] : nullptr;
     auto emit = [&](int op, int cnt) {
@@ -298,11 +342,11 @@ __global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDe
             const int ii = i - lane, jj = j - lane;
             const bool valid = ii >= 0 && jj >= 0;
             const int code = valid ? fetch(ii, jj) : 0;
-            const unsigned dm = __ballot_sync(FULL, valid && (code & 3) == 1);
+            const unsigned dm = __ballot_sync(FULL, valid && (code & 1));
             const int run = (dm == FULL) ? 32 : __ffs(~dm) - 1;
             if (run > 0) {
                 if (!WRITE) {
-                    const bool match = valid && qb[d.M - 1 - ii] == tb[d.N - 1 - jj];
+                    const bool match = valid && qb[d.qe - ii] == tb[d.te - jj];
                     const unsigned mm = __ballot_sync(FULL, match) & (run == 32 ? FULL : ((1u << run) - 1u));
                     nm += __popc(mm); nx += run - __popc(mm);
                 }
@@ -312,10 +356,8 @@ __global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDe
             if (run < 32) {
                 const int c2 = __shfl_sync(FULL, code, run);
                 const int v2 = __shfl_sync(FULL, (int)valid, run);
-                if (!v2) break;                        // left the box
-                const int h = c2 & 3;
-                if (h == 0) break;
-                state = (h == 2) ? 1 : 2;
+                if (!v2) break;                        // left the matrix at the origin: done
+                state = (c2 & 2) ? 1 : 2;
             }
         } else {
             const int code = fetch(i, j);
@@ -330,11 +372,31 @@ __global__ void sw_walk_kernel(const uint8_t* q, const uint8_t* t, const TraceDe
     }
 }
 
+// blocks, steps per block and total steps of a pair laid out with shape class `cls`
+inline void band_shape(BandDesc& d, int cls)
+{
+    const long long mcap = d.qe + 1;
+    const long long ncols = std::min<long long>(d.te + 1, mcap + d.dmax);
+    d.wide = cls;
+    const int G = tb_shape(cls).G, W = G * tb_shape(cls).K;
+    d.nblk = (int)((ncols + W - 1) / W);
+    const long long rows = std::min<long long>(mcap, (long long)W + d.imax + d.dmax);
+    d.smax = (int)((rows + TB_R - 1) / TB_R) + G - 1 + 1;       // + 1: an odd first row splits one more row pair
+}
+inline long long band_steps(const BandDesc& d) { return (long long)d.nblk * d.smax; }
+inline size_t band_words(const BandDesc& d)
+{
+    return (size_t)d.nblk * (size_t)d.smax * tb_shape(d.wide).G * 4;
+}
+
 }  // namespace
 
-int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* tbeg, const int32_t* score, const int32_t* qs,
-                const int32_t* qe, const int32_t* ts, const int32_t* te, int32_t* counts, int64_t* cigar_off,
-                uint32_t** cigar_ops, float* ms_trace_out, int* launches_out)
+// qbeg / tbeg: host begins of every pair's query / target view in the job's device code arrays; score / qe / te: forward
+// results (pairs with score <= 0 are skipped and get qs = ts = -1, no ops).  Outputs: qs, ts (alignment start), counts
+// (4 per pair, nullable), cigar_off (npairs + 1), *cigar_ops (malloc'ed).
+int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* tbeg, const int32_t* score, const int32_t* qe,
+                const int32_t* te, int32_t* qs, int32_t* ts, int32_t* counts, int64_t* cigar_off,
+                uint32_t** cigar_ops, pb_trace_stats* tstats)
 {
     const int64_t npairs = J->npairs;
     const pb_score_params* params = &J->params;
@@ -343,149 +405,187 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double tm[8] = {0}; double t_last = now();
     auto lap = [&](int k) { if (dbg) { cudaStreamSynchronize(ctx->stream); double t = now(); tm[k] += t - t_last; t_last = t; } };
-    // ---- traceback over the aligned pairs, in chunks bounded by the direction-buffer budget ----
-    std::vector<TraceDesc> all;
+    cudaStream_t sm = ctx->stream;
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], sm));
+    std::vector<BandDesc> all;
     all.reserve((size_t)npairs);
     for (int64_t p = 0; p < npairs; ++p) {
+        qs[p] = -1; ts[p] = -1;
         if (score[p] <= 0) continue;
-        TraceDesc d;
-        d.qoff = qbeg[p] + qs[p]; d.toff = tbeg[p] + ts[p];
-        d.M = qe[p] - qs[p] + 1; d.N = te[p] - ts[p] + 1; d.id = (int)p; d.pad = 0; d.doff = 0; d.wslot = 0;
-        d.wave = is_wave(d.M, d.N) ? 1 : 0;
+        BandDesc d; memset(&d, 0, sizeof(d));
+        d.qoff = qbeg[p]; d.toff = tbeg[p]; d.qe = qe[p]; d.te = te[p]; d.S = score[p]; d.id = (int)p;
         all.push_back(d);
     }
-    // pipelined (wave) boxes first, then longest boxes first: similar shapes share a warp, and the dynamic scheduler packs well
-    std::sort(all.begin(), all.end(), [](const TraceDesc& a, const TraceDesc& b) {
-        if (a.wave != b.wave) return a.wave > b.wave;
-        int ba = (a.N + TR_W - 1) / TR_W, bb = (b.N + TR_W - 1) / TR_W;
-        if (ba != bb) return ba > bb;
-        if (a.M != b.M) return a.M > b.M;
-        return a.id < b.id;
-    });
     std::vector<int> h_nops((size_t)npairs, 0);
     std::vector<int> h_counts((size_t)npairs * 4, 0);
-    const size_t budget_words = (size_t)std::min<int64_t>(ctx->hbm_bytes / 8, (int64_t)12 << 30) / 4;
-    const size_t smem = 1024 + (size_t)TR_WARPS * (32 / TR_G) * params->nsym * TR_G * (((TR_K + 3) / 4) * 4);
-    const size_t smem_w = 1024 + (size_t)TR_WARPS * params->nsym * TRW_G * (((TRW_K + 3) / 4) * 4);
-    auto kern = sw_trace_kernel<TR_G, TR_K, TR_R, TR_WARPS, 2, false>;
-    auto kern_w = sw_trace_kernel<TRW_G, TRW_K, TRW_R, TR_WARPS, 2, true>;
-    PB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PB_CUDA(ctx, cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-    // persistent grids: every CTA resident at once (the wavefront variant spins on its left neighbour)
-    int occ = 1, occ_w = 1;
-    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TR_WARPS * 32, smem));
-    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, kern_w, TR_WARPS * 32, smem_w));
-    const int grid = ctx->sm_count * std::max(1, std::min(occ, 2)), grid_w = ctx->sm_count * std::max(1, std::min(occ_w, 2));
-    float ms_trace = 0;
     int launches = 0;
-    PB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-
-    lap(0);
-    struct Chunk { size_t first, count, nwave; size_t words; int maxM; int maxNB; int waveM; size_t wslots; };
+    double band_cells = 0, box_cells = 0;
+    std::vector<std::vector<uint32_t>> chunk_ops;
+    std::vector<std::vector<long long>> chunk_ooff;
+    struct Chunk { size_t first, count, ncls[3]; size_t words; int maxM; };
     std::vector<Chunk> chunks;
-    {
+    if (!all.empty()) {
+        // ---- band of every pair (device: sums over the prefixes), then shapes, work order and chunks on the host ----
+        BandTab tab; memset(&tab, 0, sizeof(tab));
+        {
+            const int ns = params->nsym - 1;             // real symbols
+            int fq = 0, ft = 0;
+            int rq[32], rt[32];
+            for (int c = 0; c < 32; ++c) {
+                int bq = -128, bt = -128;
+                for (int o = 0; o < ns; ++o) if (c < ns) { bq = std::max(bq, (int)params->matrix[c * 32 + o]); bt = std::max(bt, (int)params->matrix[o * 32 + c]); }
+                rq[c] = bq; rt[c] = bt;
+                if (bq > 0 && (fq == 0 || bq < fq)) fq = bq;
+                if (bt > 0 && (ft == 0 || bt < ft)) ft = bt;
+            }
+            for (int c = 0; c < 32; ++c) { tab.rq[c] = (int8_t)std::max(rq[c], fq); tab.rt[c] = (int8_t)std::max(rt[c], ft); }
+            tab.floor_q = fq; tab.floor_t = ft; tab.go = params->gap_open; tab.ge = params->gap_extend;
+        }
+        DevBuf dall;
+        PB_CUDA(ctx, dall.alloc(all.size() * sizeof(BandDesc), sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(dall.p, all.data(), all.size() * sizeof(BandDesc), cudaMemcpyHostToDevice, sm));
+        band_bounds_kernel<<<(unsigned)((all.size() * 32 + 255) / 256), 256, 0, sm>>>(J->dq, J->dt, dall.as<BandDesc>(), (int)all.size(), tab);
+        PB_CUDA(ctx, cudaGetLastError()); ++launches;
+        PB_CUDA(ctx, cudaMemcpyAsync(all.data(), dall.p, all.size() * sizeof(BandDesc), cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaStreamSynchronize(sm));
+        if (getenv("PB_TRACE_FULL")) for (BandDesc& d : all) { d.imax = d.qe; d.dmax = d.te; }      // test aid: no band
+        // Narrow strips (W = 64) compute the fewest cells around a band and are the throughput shape.  A pair is given a
+        // wider shape (more lanes, fewer sequential steps) only when its own step count would outlast the share of the
+        // whole batch that falls on one group of the resident grid, i.e. when it would be the tail of the launch.
+        {
+            long long total = 0;
+            for (BandDesc& d : all) { band_shape(d, 0); total += band_steps(d); }
+            const long long groups = (long long)ctx->sm_count * 2 * TB_WARPS * (32 / tb_shape(0).G);
+            const long long share = std::max<long long>(total / groups, 1500);
+            for (BandDesc& d : all) {
+                if (band_steps(d) <= 2 * share) continue;
+                band_shape(d, 1);
+                if (band_steps(d) > 2 * share) band_shape(d, 2);
+            }
+        }
+        // widest shapes first, then most blocks / steps first: similar shapes share a warp, the dynamic scheduler packs well
+        // (sorted through 16-byte keys, then one gather: cheaper than moving the descriptors around)
+        {
+            struct Key { uint64_t k; uint32_t id, idx; };
+            std::vector<Key> keys(all.size());
+            for (size_t i = 0; i < all.size(); ++i) {
+                const BandDesc& d = all[i];
+                keys[i] = Key{~(((uint64_t)d.wide << 60) | ((uint64_t)std::min(d.nblk, 0xfffffff) << 32) | (uint32_t)d.smax), (uint32_t)d.id, (uint32_t)i};
+            }
+            std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.k != b.k ? a.k < b.k : a.id < b.id; });
+            std::vector<BandDesc> sorted(all.size());
+            for (size_t i = 0; i < all.size(); ++i) sorted[i] = all[keys[i].idx];
+            all.swap(sorted);
+        }
+        lap(0);
+        const size_t budget_words = (size_t)std::min<int64_t>(ctx->hbm_bytes / 8, (int64_t)12 << 30) / 4;
         size_t i = 0;
         while (i < all.size()) {
-            Chunk c{i, 0, 0, 0, 0, 0, 0, 0};
+            Chunk c{i, 0, {0, 0, 0}, 0, 0};
             while (i < all.size()) {
-                TraceDesc& d = all[i];
-                const size_t w = dir_words(d.M, d.N, d.wave != 0);
-                if (w > budget_words) { pb_set_error(ctx, "pb_sw_align_batch: a single alignment box needs %zu direction words", w); return PB_ERR_LIMIT; }
+                BandDesc& d = all[i];
+                const size_t w = band_words(d);
+                if (w > budget_words) { pb_set_error(ctx, "pb_sw_align_batch: a single alignment needs %zu direction words", w); return PB_ERR_LIMIT; }
                 if (c.count > 0 && c.words + w > budget_words) break;
                 d.doff = (long long)c.words;
-                c.words += w; c.count++;
-                if (d.wave) {
-                    d.wslot = (int)c.wslots; c.wslots += (size_t)((d.N + TRW_W - 1) / TRW_W);
-                    c.nwave++; c.waveM = std::max(c.waveM, d.M);
-                } else { c.maxM = std::max(c.maxM, d.M); c.maxNB = std::max(c.maxNB, (d.N + TR_W - 1) / TR_W); }
+                c.words += w; c.count++; c.ncls[d.wide]++; c.maxM = std::max(c.maxM, d.qe + 1);
+                box_cells += (double)(d.qe + 1) * (double)(d.te + 1);
+                band_cells += (double)(d.qe + 1) * (double)std::min<long long>(d.te + 1, (long long)d.imax + d.dmax + 1);
                 ++i;
             }
             chunks.push_back(c);
         }
     }
-    // cigar ops: first pass counts, then ops are written per chunk into a device buffer and copied out
-    std::vector<std::vector<uint32_t>> chunk_ops(chunks.size());
-    std::vector<std::vector<long long>> chunk_ooff(chunks.size());
+    const int nsym = params->nsym;
+    auto smem_of = [&](TbShape s) { return 1024 + (size_t)TB_WARPS * (32 / s.G) * nsym * s.G * (((s.K + 3) / 4) * 4); };
+    typedef void (*kern_t)(const TraceArgs);
+    const kern_t kern[3] = { sw_band_trace_kernel<TB_NARROW.G, TB_NARROW.K, TB_R, TB_WARPS, 2>, sw_band_trace_kernel<TB_WIDE.G, TB_WIDE.K, TB_R, TB_WARPS, 2>,
+                             sw_band_trace_kernel<TB_XWIDE.G, TB_XWIDE.K, TB_R, TB_WARPS, 2> };
+    size_t smem_c[3]; int grid_c[3];
+    for (int k = 0; k < 3 && !chunks.empty(); ++k) {
+        smem_c[k] = smem_of(tb_shape(k));
+        PB_CUDA(ctx, cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c[k]));
+        int occ = 1;
+        PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], TB_WARPS * 32, smem_c[k]));
+        grid_c[k] = ctx->sm_count * std::max(1, std::min(occ, 2));
+    }
+    chunk_ops.resize(chunks.size()); chunk_ooff.resize(chunks.size());
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk& c = chunks[ci];
-        DevBuf ddesc, ddir, dnops, dcounts, dooff, dops, dbound, dwbound, dwprog;
-        PB_CUDA(ctx, ddesc.alloc(c.count * sizeof(TraceDesc), ctx->stream));
-        PB_CUDA(ctx, ddir.alloc(std::max<size_t>(c.words, 4) * 4, ctx->stream));
-        PB_CUDA(ctx, dnops.alloc(c.count * 4, ctx->stream));
-        PB_CUDA(ctx, dcounts.alloc(c.count * 16, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(ddesc.p, all.data() + c.first, c.count * sizeof(TraceDesc), cudaMemcpyHostToDevice, ctx->stream));
-        PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
+        DevBuf ddesc, ddir, dnops, dcounts, dooff, dops, dstart;
+        PB_CUDA(ctx, ddesc.alloc(c.count * sizeof(BandDesc), sm));
+        PB_CUDA(ctx, ddir.alloc(std::max<size_t>(c.words, 4) * 4, sm));
+        PB_CUDA(ctx, dnops.alloc(c.count * 4, sm));
+        PB_CUDA(ctx, dcounts.alloc(c.count * 16, sm));
+        PB_CUDA(ctx, dstart.alloc(c.count * sizeof(int2), sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(ddesc.p, all.data() + c.first, c.count * sizeof(BandDesc), cudaMemcpyHostToDevice, sm));
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), sm));
         lap(1);
+        const int bstride = ((c.maxM + 63) / 64) * 64;
         TraceArgs a;
-        a.q = J->dq; a.t = J->dt; a.desc = ddesc.as<TraceDesc>(); a.count = (int)c.count;
-        a.counter = ctx->d_counter; a.matrix = J->matrix.as<int8_t>(); a.nsym = params->nsym; a.go = params->gap_open; a.ge = params->gap_extend;
-        a.dir = ddir.as<uint32_t>(); a.boundary = nullptr; a.bstride = 0; a.progress = nullptr; a.wsub = nullptr; a.nsub = 0;
-        std::vector<int2> sub;
-        if (c.nwave > 0) {
-            // wavefront launch over the (pair, column block) sub-tasks of the long boxes, pair-major
-            for (size_t k = 0; k < c.nwave; ++k) {
-                const TraceDesc& d = all[c.first + k];
-                for (int b = 0; b < (d.N + TRW_W - 1) / TRW_W; ++b) sub.push_back(make_int2((int)k, b));
-            }
-            const int wstride = ((c.waveM + 63) / 64) * 64;
-            const size_t bbytes = c.wslots * (size_t)wstride * sizeof(uint2);
-            if (bbytes > ((size_t)24 << 30)) { pb_set_error(ctx, "pb_sw_align_batch: long-alignment border buffer would need %zu bytes; split the batch", bbytes); return PB_ERR_LIMIT; }
-            PB_CUDA(ctx, dwbound.alloc(bbytes, ctx->stream));
-            const size_t o_sub = ((c.wslots * 4 + 7) / 8) * 8;
-            PB_CUDA(ctx, dwprog.alloc(o_sub + sub.size() * sizeof(int2), ctx->stream));
-            PB_CUDA(ctx, cudaMemsetAsync(dwprog.p, 0, o_sub, ctx->stream));
-            PB_CUDA(ctx, cudaMemcpyAsync((char*)dwprog.p + o_sub, sub.data(), sub.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-            TraceArgs w = a;
-            w.count = (int)c.nwave; w.boundary = dwbound.as<uint2>(); w.bstride = wstride; w.progress = (int*)dwprog.p;
-            w.wsub = (const int2*)((char*)dwprog.p + o_sub); w.nsub = (int)sub.size(); w.counter = ctx->d_counter + 1;
-            const int wgrid = std::max(1, std::min(grid_w, (int)((sub.size() + TR_WARPS - 1) / TR_WARPS)));
-            // the few long boxes run on the aux stream beside the regular launch below
-            PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[0], ctx->stream));
-            PB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux[0], 0));
-            kern_w<<<wgrid, TR_WARPS * 32, smem_w, ctx->aux_stream>>>(w);
-            PB_CUDA(ctx, cudaGetLastError()); ++launches;
-            PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[1], ctx->aux_stream));
-        }
-        if (c.count > c.nwave) {
-            const int bstride = c.maxNB > 1 ? ((c.maxM + 63) / 64) * 64 : 0;
-            if (bstride) PB_CUDA(ctx, dbound.alloc((size_t)grid * TR_WARPS * (32 / TR_G) * bstride * sizeof(uint2), ctx->stream));
+        a.q = J->dq; a.t = J->dt; a.matrix = J->matrix.as<int8_t>(); a.nsym = nsym; a.go = params->gap_open; a.ge = params->gap_extend;
+        a.dir = ddir.as<uint32_t>(); a.bstride = bstride;
+        // sorted order inside the chunk: [xwide][wide][narrow].  The few long / wide pairs go to the aux stream and run beside
+        // the narrow ones.
+        DevBuf dbound[3];
+        bool forked[3] = {false, false, false};
+        cudaStream_t side[3] = {sm, ctx->copy_stream, ctx->aux_stream};
+        size_t first = 0;
+        for (int k = 2; k >= 0; --k) {
+            const size_t cnt = c.ncls[k];
+            if (cnt == 0) continue;
+            const int NG = 32 / tb_shape(k).G;
+            const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid_c[k], (cnt + (size_t)TB_WARPS * NG - 1) / ((size_t)TB_WARPS * NG)));
+            PB_CUDA(ctx, dbound[k].alloc((size_t)grid * TB_WARPS * NG * bstride * sizeof(uint2), sm));
             TraceArgs r = a;
-            r.desc = a.desc + c.nwave; r.count = (int)(c.count - c.nwave);
-            r.boundary = bstride ? dbound.as<uint2>() : nullptr; r.bstride = bstride;
-            kern<<<grid, TR_WARPS * 32, smem, ctx->stream>>>(r);
+            r.desc = ddesc.as<BandDesc>() + first; r.count = (int)cnt; r.counter = ctx->d_counter + k;
+            r.boundary = dbound[k].as<uint2>(); r.start = dstart.as<int2>() + first;
+            cudaStream_t ks = sm;
+            if (k > 0 && cnt < c.count) {            // the few long / wide pairs run beside the rest on their own streams
+                PB_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[k], sm)); PB_CUDA(ctx, cudaStreamWaitEvent(side[k], ctx->ev_pipe[k], 0));
+                forked[k] = true; ks = side[k];
+            }
+            kern[k]<<<grid, TB_WARPS * 32, smem_c[k], ks>>>(r);
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
+            first += cnt;
         }
-        if (c.nwave > 0) PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[1], 0));
+        for (int k = 1; k < 3; ++k)
+            if (forked[k]) { PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[k - 1], side[k])); PB_CUDA(ctx, cudaStreamWaitEvent(sm, ctx->ev_aux[k - 1], 0)); }
         lap(2);
         const int tb = 128, gb = (int)((c.count * 32 + tb - 1) / tb);
-        sw_walk_kernel<false><<<gb, tb, 0, ctx->stream>>>(a.q, a.t, a.desc, a.count, a.dir, dnops.as<int>(), dcounts.as<int>(), nullptr, nullptr);
+        sw_walk_kernel<false><<<gb, tb, 0, sm>>>(a.q, a.t, ddesc.as<BandDesc>(), dstart.as<int2>(), (int)c.count, a.dir, dnops.as<int>(), dcounts.as<int>(), nullptr, nullptr);
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         std::vector<int> nops(c.count), cnt(c.count * 4);
-        PB_CUDA(ctx, cudaMemcpyAsync(nops.data(), dnops.p, c.count * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(cnt.data(), dcounts.p, c.count * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<int2> start(c.count);
+        PB_CUDA(ctx, cudaMemcpyAsync(nops.data(), dnops.p, c.count * 4, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(cnt.data(), dcounts.p, c.count * 16, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(start.data(), dstart.p, c.count * sizeof(int2), cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaStreamSynchronize(sm));
         lap(3);
         std::vector<long long>& ooff = chunk_ooff[ci];
         ooff.resize(c.count + 1);
         long long tot = 0;
         for (size_t k = 0; k < c.count; ++k) {
             ooff[k] = tot; tot += nops[k];
-            int id = all[c.first + k].id;
-            h_nops[id] = nops[k];
-            memcpy(&h_counts[(size_t)id * 4], &cnt[k * 4], 16);
+            const BandDesc& d = all[c.first + k];
+            if (start[k].x < 0) { pb_set_error(ctx, "internal: the banded reverse pass did not reproduce the forward score of pair %d", d.id); return PB_ERR_LIMIT; }
+            h_nops[d.id] = nops[k];
+            qs[d.id] = d.qe - start[k].x; ts[d.id] = d.te - start[k].y;
+            memcpy(&h_counts[(size_t)d.id * 4], &cnt[k * 4], 16);
         }
         ooff[c.count] = tot;
-        PB_CUDA(ctx, dooff.alloc((c.count + 1) * 8, ctx->stream));
-        PB_CUDA(ctx, dops.alloc(std::max<long long>(tot, 1) * 4, ctx->stream));
-        PB_CUDA(ctx, cudaMemcpyAsync(dooff.p, ooff.data(), (c.count + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        sw_walk_kernel<true><<<gb, tb, 0, ctx->stream>>>(a.q, a.t, a.desc, a.count, a.dir, nullptr, nullptr, dooff.as<long long>(), dops.as<uint32_t>());
+        PB_CUDA(ctx, dooff.alloc((c.count + 1) * 8, sm));
+        PB_CUDA(ctx, dops.alloc(std::max<long long>(tot, 1) * 4, sm));
+        PB_CUDA(ctx, cudaMemcpyAsync(dooff.p, ooff.data(), (c.count + 1) * 8, cudaMemcpyHostToDevice, sm));
+        sw_walk_kernel<true><<<gb, tb, 0, sm>>>(a.q, a.t, ddesc.as<BandDesc>(), dstart.as<int2>(), (int)c.count, a.dir, nullptr, nullptr, dooff.as<long long>(), dops.as<uint32_t>());
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
         chunk_ops[ci].resize((size_t)tot);
-        if (tot) PB_CUDA(ctx, cudaMemcpyAsync(chunk_ops[ci].data(), dops.p, (size_t)tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (tot) PB_CUDA(ctx, cudaMemcpyAsync(chunk_ops[ci].data(), dops.p, (size_t)tot * 4, cudaMemcpyDeviceToHost, sm));
+        PB_CUDA(ctx, cudaStreamSynchronize(sm));
         lap(4);
     }
-    PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    float ms_trace = 0;
+    PB_CUDA(ctx, cudaEventRecord(ctx->ev[1], sm));
     PB_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
     PB_CUDA(ctx, cudaEventElapsedTime(&ms_trace, ctx->ev[0], ctx->ev[1]));
 
@@ -498,18 +598,18 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk& c = chunks[ci];
         for (size_t k = 0; k < c.count; ++k) {
-            int id = all[c.first + k].id;
-            long long o = chunk_ooff[ci][k], n = chunk_ooff[ci][k + 1] - o;
+            const int id = all[c.first + k].id;
+            const long long o = chunk_ooff[ci][k], n = chunk_ooff[ci][k + 1] - o;
             if (n) memcpy(ops + cigar_off[id], chunk_ops[ci].data() + o, (size_t)n * 4);
         }
     }
     lap(5);
-    if (dbg) fprintf(stderr, "[pb_sw_trace] desc+sort %.2f, alloc+upload %.2f, dp kernels %.2f, count walk+d2h %.2f, write walk+d2h %.2f, assemble %.2f ms (%zu chunks, %zu boxes)\n",
-                     tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], chunks.size(), all.size());
+    if (dbg) fprintf(stderr, "[pb_sw_trace] bands+sort %.2f, alloc+upload %.2f, dp kernels %.2f, count walk+d2h %.2f, write walk+d2h %.2f, assemble %.2f ms "
+                             "(%zu chunks, %zu pairs, band / prefix cells %.3f)\n",
+                     tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], chunks.size(), all.size(), band_cells / std::max(box_cells, 1.0));
     *cigar_ops = ops;
     if (counts) memcpy(counts, h_counts.data(), (size_t)npairs * 16);
-    if (ms_trace_out) *ms_trace_out = ms_trace;
-    if (launches_out) *launches_out = launches;
+    if (tstats) { tstats->ms = ms_trace; tstats->launches = launches; tstats->band_cells = band_cells; tstats->prefix_cells = box_cells; }
     return PB_OK;
 }
 
@@ -525,22 +625,25 @@ extern "C" int pb_sw_align_batch(pb_ctx* ctx, const uint8_t* q, const int64_t* q
     }
     *cigar_ops = nullptr;
     pb_sw_job* J = nullptr;
-    int rc = pb_sw_job_create(ctx, q, qoff, t, toff, npairs, params, 1, &J);
+    // forward pass only: the start cell comes out of the banded reverse pass that also records the path
+    int rc = pb_sw_job_create(ctx, q, qoff, t, toff, npairs, params, 0, &J);
     if (rc) return rc;
     std::unique_ptr<pb_sw_job> guard(J);
     pb_sw_stats st; memset(&st, 0, sizeof(st));
     rc = pb_sw_job_run(ctx, J, &st);
     if (rc) return rc;
-    rc = pb_sw_job_fetch(ctx, J, score, qs, qe, ts, te);
+    rc = pb_sw_job_fetch(ctx, J, score, nullptr, qe, nullptr, te);
     if (rc) return rc;
-    float ms_trace = 0; int launches = 0;
-    rc = pb_sw_trace(ctx, J, qoff, toff, score, qs, qe, ts, te, counts, cigar_off, cigar_ops, &ms_trace, &launches);
+    pb_trace_stats tst; memset(&tst, 0, sizeof(tst));
+    rc = pb_sw_trace(ctx, J, qoff, toff, score, qe, te, qs, ts, counts, cigar_off, cigar_ops, &tst);
     if (rc) return rc;
+    for (int64_t p = 0; p < npairs; ++p) if (score[p] <= 0) { qe[p] = -1; te[p] = -1; }
     if (stats) {
         *stats = st;
-        stats->ms_traceback = ms_trace;
-        stats->ms_total_device = st.ms_total_device + ms_trace;
-        stats->kernel_launches = st.kernel_launches + launches;
+        stats->cells_reverse = tst.band_cells;
+        stats->ms_traceback = tst.ms;
+        stats->ms_total_device = st.ms_total_device + tst.ms;
+        stats->kernel_launches = st.kernel_launches + tst.launches;
     }
     return PB_OK;
 }

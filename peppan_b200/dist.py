@@ -40,50 +40,3 @@ def init_context_from_env(backend_pg=None):
     obj = [nccl_unique_id() if rank == 0 else None]
     backend_pg.broadcast_object_list(obj, src=0)
     return Context(local, rank, world, obj[0])
-
-
-_ABANDONED = []
-
-
-def init_context_watchdog(pg, local, rank, world, timeout_s=120.0, make_uid=None, make_nccl_ctx=None, make_plain_ctx=None):
-    """Context with an NCCL communicator, created under a watchdog.  The communicator set-up and a first (empty)
-    hit-table allgather run in a helper thread; if ANY rank has not finished after `timeout_s` (or failed), EVERY rank
-    falls back to a context without NCCL -- the decision is taken with a MIN all-reduce over `pg` (gloo) -- so a
-    collective that cannot be established costs a bounded wait instead of hanging the job.
-    Returns (ctx, None) or (plain ctx, note).  The make_* hooks exist for the CPU test of this control flow."""
-    import threading
-    import torch
-    from ._lib import Context, nccl_unique_id
-
-    def _nccl_ctx(uid):
-        import ctypes as C
-        from . import search as _s
-        c = Context(local, rank, world, uid)
-        _s.bind(c.lib)
-        h = _s.Hits()
-        c.check(c.lib.pb_allgather_hits(c.h, C.byref(h)), 'pb_allgather_hits')
-        c.lib.pb_free_hits(C.byref(h))
-        return c
-
-    make_uid = make_uid or nccl_unique_id
-    make_nccl_ctx = make_nccl_ctx or _nccl_ctx
-    make_plain_ctx = make_plain_ctx or (lambda: Context(local))
-    obj = [make_uid() if rank == 0 else None]
-    pg.broadcast_object_list(obj, src=0)
-    box = {}
-
-    def work():
-        try:
-            box['ctx'] = make_nccl_ctx(obj[0])
-        except Exception as e:          # reported in the note; the fallback context is made by the caller's thread
-            box['err'] = repr(e)
-
-    th = threading.Thread(target=work, daemon=True)
-    th.start(); th.join(timeout_s)
-    ok = torch.tensor([1.0 if 'ctx' in box else 0.0], dtype=torch.float64)
-    pg.all_reduce(ok, op=pg.ReduceOp.MIN)
-    if float(ok[0]) == 1.0:
-        return box['ctx'], None
-    _ABANDONED.append(box)              # keep a half-made communicator alive: destroying it could block as well
-    why = box.get('err') or ('timeout' if 'ctx' not in box else 'another rank was not ready')
-    return make_plain_ctx(), 'NCCL communicator / first allgather not ready on every rank after %.0f s (%s): hit tables not gathered' % (timeout_s, why)

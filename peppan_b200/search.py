@@ -83,9 +83,11 @@ def _take(out):
     return hits, cigar
 
 
-def search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0):
+def search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0,
+                       allgather=False):
     """pb_search_grouped: many genomes in one call.  Returns (hits, cigar, group_off, stats): the concatenated table in group
-    order, s_id = index into the concatenated target set."""
+    order, s_id = index into the concatenated target set.  allgather: the table is then merged over the ranks of the context
+    (pb_allgather_hits, one exchange for the whole batch); group_off stays this rank's, stats['rank_offsets'] delimits the ranks."""
     bind(ctx.lib)
     q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8); t_bytes = np.ascontiguousarray(t_bytes, dtype=np.uint8)
     q_off = np.ascontiguousarray(q_off, dtype=np.int64); t_off = np.ascontiguousarray(t_off, dtype=np.int64)
@@ -99,11 +101,15 @@ def search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id
     goff = np.zeros(ng + 1, np.int64)
     ctx.check(ctx.lib.pb_search_grouped(ctx.h, C.byref(qs), C.byref(ts), ptr(groups), ng, C.byref(prm), C.byref(out), ptr(goff), C.byref(st)),
               'pb_search_grouped')
+    d = st.as_dict()
     try:
+        if allgather:
+            ctx.check(ctx.lib.pb_allgather_hits(ctx.h, C.byref(out)), 'pb_allgather_hits')
+            d['rank_offsets'] = np.frombuffer((C.c_char * ((out.n_ranks + 1) * 8)).from_address(out.rank_offsets), dtype=np.int64).copy() if out.rank_offsets else None
         hits, cigar = _take(out)
     finally:
         ctx.lib.pb_free_hits(C.byref(out))
-    return hits, cigar, goff, st.as_dict()
+    return hits, cigar, goff, d
 
 
 def search_grouped(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, **kw):

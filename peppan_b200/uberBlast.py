@@ -166,18 +166,9 @@ class RunBlast(object):
             ref_enc = {k: pf.encode_nuc(v) for k, v in self.refSeq.items()}
             qry_enc = {k: pf.encode_nuc(v) for k, v in self.qrySeq.items()}
             rows = pf.rescore(rows, ref_enc, qry_enc, re_score, min_id, table_id)
-        if re_score:
-            # identity / score are floats now: the rest of the chain is one library call (pb_post_chain, host C++)
-            rows, overlap = pf.post_chain_table(rows, filter, linear_merge, fix_end, return_overlap)
-        else:
-            # raw integer scores keep their Python types through the readable mirror of the same stages
-            if filter[0]:
-                rows = pf.ovl_filter(rows, filter[1], filter[2])
-            if linear_merge[0]:
-                rows = pf.linear_merge(rows, linear_merge[1], linear_merge[2])
-            pf.fix_end(rows, *fix_end)
-            overlap = pf.overlaps(rows, return_overlap[1], return_overlap[2]) if return_overlap[0] else None
-            rows = pf.final_sort(rows)
+        # the rest of the chain (ovlFilter, linearMerge, fixEnd, returnOverlap, final sort) is one library call on the columnar
+        # table (pb_post_chain, host C++), for rescored and raw tables alike
+        rows, overlap = pf.post_chain_table(rows, filter, linear_merge, fix_end, return_overlap)
         ncol = 17 if linear_merge[0] else 16
         blastab = _as_object_array(rows, ncol)
         if return_overlap[0]:

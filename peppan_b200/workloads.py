@@ -159,3 +159,32 @@ def synth_genome(pool, index, n_acc_per_genome=1500, density=0.86, seed=SEED):
     parts.append(rng.integers(0, 4, size=50, dtype=np.uint8))
     seq = _NT[np.concatenate(parts)].tobytes().decode()
     return seq, annot
+
+
+# ---- many genomes at once (bench legs for BASELINE.json configs[2..3]): synthesis spread over worker processes ----------
+_WORKER_POOL = None
+
+
+def _worker_init(n_core, n_acc, seed):
+    global _WORKER_POOL
+    _WORKER_POOL = GenePool(n_core, n_acc, seed=seed)
+
+
+def _worker_genome(index):
+    seq, annot = synth_genome(_WORKER_POOL, index)
+    return index, np.frombuffer(seq.encode(), dtype=np.uint8), np.array([(a[0], a[1], a[2], a[3]) for a in annot], dtype=np.int64)
+
+
+def synth_genomes_parallel(indices, n_core=3000, n_acc=12000, seed=SEED, procs=1):
+    """[(index, ASCII uint8 array, annot int64 (n, 4): ancestor id, start, end, strand)] for the requested genome indices; the
+    same genomes synth_genome() makes one by one.  Uses fork()ed workers: call it before creating a CUDA context."""
+    indices = list(indices)
+    if not indices:
+        return []
+    if procs <= 1 or len(indices) < 4:
+        _worker_init(n_core, n_acc, seed)
+        return [_worker_genome(i) for i in indices]
+    import multiprocessing as mp
+    with mp.get_context('fork').Pool(procs, initializer=_worker_init, initargs=(n_core, n_acc, seed)) as pool:
+        out = pool.map(_worker_genome, indices, chunksize=max(1, len(indices) // (4 * procs)))
+    return out

@@ -68,47 +68,3 @@ def test_shard_indices_partition():
 class _FakeCtx(object):
     def __init__(self, kind):
         self.kind = kind
-
-
-def _watchdog_worker(rank, world, port, out, scenario):
-    sys.path.insert(0, ROOT)
-    import time
-    import torch.distributed as dist
-    from peppan_b200 import dist as pbd
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-    dist.init_process_group('gloo', rank=rank, world_size=world)
-
-    def make_nccl(uid):
-        assert uid == b'uid-from-rank-0'
-        if scenario == 'hang' and rank == 1:
-            time.sleep(30)                       # a communicator that never comes up on one rank
-        if scenario == 'error' and rank == 0:
-            raise RuntimeError('no NCCL here')
-        return _FakeCtx('nccl')
-
-    t0 = time.time()
-    ctx, note = pbd.init_context_watchdog(dist, 0, rank, world, timeout_s=1.5, make_uid=lambda: b'uid-from-rank-0',
-                                          make_nccl_ctx=make_nccl, make_plain_ctx=lambda: _FakeCtx('plain'))
-    dt = time.time() - t0
-    if scenario == 'fine':
-        ok = ctx.kind == 'nccl' and note is None
-    else:
-        ok = ctx.kind == 'plain' and note is not None and dt < 20
-        if scenario == 'error' and rank == 0:
-            ok = ok and 'no NCCL here' in note
-    t = __import__('torch').tensor([1.0 if ok else 0.0])
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        open(out, 'w').write('ok' if float(t[0]) == 1.0 else 'bad')
-    dist.barrier()
-    if scenario == 'hang':
-        os._exit(0)                              # as bench.py does: a helper thread is still asleep
-    dist.destroy_process_group()
-
-
-def test_nccl_watchdog_agrees_on_fallback(tmp_path):
-    """every rank ends with the same decision: NCCL context when all ranks made one in time, plain context otherwise"""
-    for scenario in ('fine', 'error', 'hang'):
-        out = os.path.join(tmp_path, 'wd_%s.txt' % scenario)
-        mp.spawn(_watchdog_worker, args=(2, _free_port(), out, scenario), nprocs=2, join=True)
-        assert open(out).read() == 'ok', scenario

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from peppan_b200 import postfilter as pf
+import postfilter_mirror as pfm
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -52,12 +53,12 @@ def test_post_chain_matches_reference(scen):
         if o['re_score']:
             rows = pf.rescore(rows, ref_enc, qry_enc, o['re_score'], g['min_id'])
         if o['filter'][0]:
-            rows = pf.ovl_filter(rows, o['filter'][1], o['filter'][2])
+            rows = pfm.ovl_filter(rows, o['filter'][1], o['filter'][2])
         if o['linear_merge'][0]:
-            rows = pf.linear_merge(rows, o['linear_merge'][1], o['linear_merge'][2])
-        pf.fix_end(rows, o['fix_end'][0], o['fix_end'][1])
-        ovl = pf.overlaps(rows, o['return_overlap'][1], o['return_overlap'][2]) if o['return_overlap'][0] else None
-        rows = pf.final_sort(rows)
+            rows = pfm.linear_merge(rows, o['linear_merge'][1], o['linear_merge'][2])
+        pfm.fix_end(rows, o['fix_end'][0], o['fix_end'][1])
+        ovl = pfm.overlaps(rows, o['return_overlap'][1], o['return_overlap'][2]) if o['return_overlap'][0] else None
+        rows = pfm.final_sort(rows)
         _same(rows, run['tab_out'], 'tab')
         if ovl is not None:
             _same(ovl.tolist(), run['overlap_out'], 'overlap')
@@ -138,12 +139,12 @@ def test_rescore_m1_table_rejects_inconsistent_rows():
 
 def _python_chain(rows, o):
     if o['filter'][0]:
-        rows = pf.ovl_filter(rows, o['filter'][1], o['filter'][2])
+        rows = pfm.ovl_filter(rows, o['filter'][1], o['filter'][2])
     if o['linear_merge'][0]:
-        rows = pf.linear_merge(rows, o['linear_merge'][1], o['linear_merge'][2])
-    pf.fix_end(rows, o['fix_end'][0], o['fix_end'][1])
-    ovl = pf.overlaps(rows, o['return_overlap'][1], o['return_overlap'][2]) if o['return_overlap'][0] else None
-    return pf.final_sort(rows), ovl
+        rows = pfm.linear_merge(rows, o['linear_merge'][1], o['linear_merge'][2])
+    pfm.fix_end(rows, o['fix_end'][0], o['fix_end'][1])
+    ovl = pfm.overlaps(rows, o['return_overlap'][1], o['return_overlap'][2]) if o['return_overlap'][0] else None
+    return pfm.final_sort(rows), ovl
 
 
 @pytest.mark.parametrize('scen', range(14))

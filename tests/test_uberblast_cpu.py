@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from peppan_b200 import postfilter as pf
+import postfilter_mirror as pfm
 from peppan_b200 import seqcodec, seqio, uberBlast as ub, workloads
 
 
@@ -64,11 +65,11 @@ def test_iter_map_bsn_flags_cpu(files, oracle_as_search):
         r.append(i)
     ref_enc = {k: pf.encode_nuc(v) for k, v in rb.refSeq.items()}; qry_enc = {k: pf.encode_nuc(v) for k, v in rb.qrySeq.items()}
     rows = pf.rescore(rows, ref_enc, qry_enc, 1, 0.4, 11)
-    rows = pf.ovl_filter(rows, 0.9, 0.)
-    rows = pf.linear_merge(rows, 600., 1.5)
-    pf.fix_end(rows, 0., 3.)
-    want_ovl = pf.overlaps(rows, 300, 0.6)
-    rows = pf.final_sort(rows)
+    rows = pfm.ovl_filter(rows, 0.9, 0.)
+    rows = pfm.linear_merge(rows, 600., 1.5)
+    pfm.fix_end(rows, 0., 3.)
+    want_ovl = pfm.overlaps(rows, 300, 0.6)
+    rows = pfm.final_sort(rows)
     assert len(rows) == len(blastab)
     for a, b in zip(blastab, rows):
         assert list(a[:2]) == b[:2] and list(a[3:11]) == b[3:11] and list(a[12:16]) == b[12:16]
