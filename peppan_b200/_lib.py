@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpeppan_b200.so')
+LIB_PATH = os.environ.get('PB_LIB_PATH') or os.path.join(_HERE, 'libpeppan_b200.so')      # PB_LIB_PATH: kernel-tuning aid
 _lib = None
 
 

@@ -95,11 +95,31 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
             const double qc = (double)(x.q_end - x.q_start + 1) / (double)x.q_len, sc = (double)(x.s_end - x.s_start + 1) / (double)x.s_len;
             return iden + 1e-9 >= (double)min_id && qc + 1e-9 >= (double)min_cov && sc + 1e-9 >= (double)min_cov;
         };
+        // Multi-GPU (ctx->world > 1, every rank calls with the same genes): the queries of both phases are dealt round-robin
+        // over the ranks (genes arrive longest first, so the deal is balanced), every rank searches its share against the
+        // replicated targets, and the per-gene results are exchanged over NCCL: an element-wise maximum of joined[] after
+        // phase 1, an allgather of the verified edges after phase 2.  The greedy then runs identically on every rank.
+        const int W = ctx->world, R = ctx->rank;
+        auto my_share = [&](const std::vector<int>& idx_all, std::vector<uint8_t>& bytes, std::vector<int64_t>& off, std::vector<int>& mine) {
+            bytes.clear(); off.assign(1, 0); mine.clear();
+            for (size_t k = (size_t)R; k < idx_all.size(); k += (size_t)W) {
+                const int i = idx_all[k];
+                bytes.insert(bytes.end(), bsrc + qoff[i], bsrc + qoff[i + 1]);
+                off.push_back(off.back() + (qoff[i + 1] - qoff[i])); mine.push_back(i);
+            }
+        };
+        std::vector<uint8_t> sbytes; std::vector<int64_t> soff; std::vector<int> smine;
         // phase 1: the block against the representatives so far.  Every representative precedes every gene of the block, so
         // a gene with a verified edge to one joins the earliest such representative whatever happens inside the block.
         std::vector<int> joined(nb, -1);
         if (nr > 0) {
             pb_seqset qs{bsrc, qoff.data(), nb}, ts{rep_bytes.data(), rep_off.data(), nr};
+            if (W > 1) {
+                std::vector<int> everyone(nb);
+                for (int i = 0; i < nb; ++i) everyone[i] = i;
+                my_share(everyone, sbytes, soff, smine);
+                qs = pb_seqset{sbytes.data(), soff.data(), (int64_t)smine.size()};
+            }
             pb_hits hits; pb_search_stats sst;
             int rc = pb_search(ctx, &qs, &ts, &prm, &hits, &sst);
             if (rc) return rc;
@@ -108,10 +128,17 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
                 const pb_hit& x = hits.hits[h];
                 if (!verified(hits, x)) continue;
                 ++st.n_edges;
-                const int a = reps[x.s_id];
-                if (joined[x.q_id] < 0 || a < joined[x.q_id]) joined[x.q_id] = a;
+                const int a = reps[x.s_id], b = W > 1 ? smine[x.q_id] : x.q_id;
+                if (joined[b] < 0 || a < joined[b]) joined[b] = a;
             }
             pb_free_hits(&hits);
+            if (W > 1) {
+                // every gene was searched by exactly one rank: others hold -1; the maximum of (INT_MAX - a) keeps the earliest
+                std::vector<int32_t> v(nb);
+                for (int i = 0; i < nb; ++i) v[i] = joined[i] < 0 ? -1 : 0x7fffffff - joined[i];
+                rc = pb_allreduce_max_i32(ctx, v.data(), nb); if (rc) return rc;
+                for (int i = 0; i < nb; ++i) joined[i] = v[i] < 0 ? -1 : 0x7fffffff - v[i];
+            }
         }
         // phase 2: the genes no representative claimed, all against all; greedy fixed point on the device
         std::vector<int> novel;
@@ -123,18 +150,32 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
                 tbuf.insert(tbuf.end(), bsrc + qoff[i], bsrc + qoff[i + 1]);
                 toff.push_back(toff.back() + (qoff[i + 1] - qoff[i]));
             }
-            pb_seqset ns{tbuf.data(), toff.data(), nn};
+            pb_seqset ns{tbuf.data(), toff.data(), nn}, nq = ns;
+            // only an EARLIER gene can claim a later one: windows whose target does not precede the query are never aligned
+            pb_search_params prm2 = prm;
+            prm2.reserved[0] |= 4; prm2.reserved[1] = W; prm2.reserved[2] = R;
+            if (W > 1) {
+                std::vector<int> everyone(nn);
+                for (int i = 0; i < nn; ++i) everyone[i] = novel[i];
+                my_share(everyone, sbytes, soff, smine);
+                nq = pb_seqset{sbytes.data(), soff.data(), (int64_t)smine.size()};
+            }
             pb_hits hits; pb_search_stats sst;
-            int rc = pb_search(ctx, &ns, &ns, &prm, &hits, &sst);
+            int rc = pb_search(ctx, &nq, &ns, &prm2, &hits, &sst);
             if (rc) return rc;
             st.n_pairs_verified += sst.n_windows; st.sw_cells += sst.sw_cells; st.kernel_launches += sst.kernel_launches;
-            std::vector<std::pair<int, int>> edges;      // (b, a) in novel-local indices, a earlier than b
+            std::vector<int32_t> mine_edges;             // (b, a) in novel-local indices, a earlier than b, flattened
             for (int64_t h = 0; h < hits.n_hits; ++h) {
                 const pb_hit& x = hits.hits[h];
-                if (x.s_id >= x.q_id) continue;
-                if (verified(hits, x)) edges.emplace_back(x.q_id, x.s_id);
+                const int b = R + x.q_id * W;            // novel-local index of the query (round-robin deal)
+                if (x.s_id >= b) continue;
+                if (verified(hits, x)) { mine_edges.push_back(b); mine_edges.push_back(x.s_id); }
             }
             pb_free_hits(&hits);
+            std::vector<int32_t> all_edges;
+            rc = pb_allgather_i32(ctx, mine_edges, all_edges); if (rc) return rc;
+            std::vector<std::pair<int, int>> edges(all_edges.size() / 2);
+            for (size_t e = 0; e < edges.size(); ++e) edges[e] = std::make_pair(all_edges[2 * e], all_edges[2 * e + 1]);
             std::sort(edges.begin(), edges.end());
             edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
             st.n_edges += (int64_t)edges.size();

@@ -27,6 +27,9 @@ struct pb_ctx {
 };
 
 void pb_set_error(pb_ctx* ctx, const char* fmt, ...);
+// exchanges over the context's NCCL communicator (no-ops with world == 1); pb_ctx.cu
+int pb_allreduce_max_i32(pb_ctx* ctx, int32_t* v, int64_t n);
+int pb_allgather_i32(pb_ctx* ctx, const std::vector<int32_t>& mine, std::vector<int32_t>& all);
 
 #define PB_CUDA(ctx, call)                                                                        \
     do {                                                                                          \

@@ -226,6 +226,61 @@ extern "C" int pb_allgather_hits(pb_ctx* ctx, pb_hits* io)
     return PB_OK;
 }
 
+// ---- small exchanges used by the clustering split (pb_cluster.cu) ---------------------------------------------------
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+
+// element-wise maximum over the ranks of a host int32 array (in place)
+int pb_allreduce_max_i32(pb_ctx* ctx, int32_t* v, int64_t n)
+{
+    if (ctx->world == 1 || n == 0) return PB_OK;
+    if (!ctx->nccl_comm) { pb_set_error(ctx, "context was created without NCCL"); return PB_ERR_NCCL; }
+    auto allreduce = (nccl_allreduce_fn)dlsym(ctx->nccl_dl, "ncclAllReduce");
+    if (!allreduce) { pb_set_error(ctx, "ncclAllReduce missing"); return PB_ERR_NCCL; }
+    DevBuf d;
+    PB_CUDA(ctx, d.alloc((size_t)n * 4, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(d.p, v, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = allreduce(d.p, d.p, (size_t)n, 2 /* ncclInt32 */, 2 /* ncclMax */, ctx->nccl_comm, ctx->stream);
+    if (rc) { pb_set_error(ctx, "ncclAllReduce failed (%d)", rc); return PB_ERR_NCCL; }
+    PB_CUDA(ctx, cudaMemcpyAsync(v, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+// concatenation, in rank order, of every rank's int32 array (variable lengths)
+int pb_allgather_i32(pb_ctx* ctx, const std::vector<int32_t>& mine, std::vector<int32_t>& all)
+{
+    if (ctx->world == 1) { all = mine; return PB_OK; }
+    if (!ctx->nccl_comm) { pb_set_error(ctx, "context was created without NCCL"); return PB_ERR_NCCL; }
+    auto allgather = (nccl_allgather_fn)dlsym(ctx->nccl_dl, "ncclAllGather");
+    if (!allgather) { pb_set_error(ctx, "ncclAllGather missing"); return PB_ERR_NCCL; }
+    const int W = ctx->world;
+    cudaStream_t sm = ctx->stream;
+    DevBuf d_cnt, d_cnts;
+    PB_CUDA(ctx, d_cnt.alloc(8, sm)); PB_CUDA(ctx, d_cnts.alloc(8 * W, sm));
+    const int64_t n = (int64_t)mine.size();
+    PB_CUDA(ctx, cudaMemcpyAsync(d_cnt.p, &n, 8, cudaMemcpyHostToDevice, sm));
+    int rc = allgather(d_cnt.p, d_cnts.p, 1, 4 /* ncclInt64 */, ctx->nccl_comm, sm);
+    if (rc) { pb_set_error(ctx, "ncclAllGather(counts) failed (%d)", rc); return PB_ERR_NCCL; }
+    std::vector<int64_t> cnt(W);
+    PB_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_cnts.p, 8 * W, cudaMemcpyDeviceToHost, sm));
+    PB_CUDA(ctx, cudaStreamSynchronize(sm));
+    int64_t mx = 1, tot = 0;
+    for (int r = 0; r < W; ++r) { mx = std::max(mx, cnt[r]); tot += cnt[r]; }
+    DevBuf d_in, d_out;
+    PB_CUDA(ctx, d_in.alloc((size_t)mx * 4, sm)); PB_CUDA(ctx, d_out.alloc((size_t)mx * 4 * W, sm));
+    if (n) PB_CUDA(ctx, cudaMemcpyAsync(d_in.p, mine.data(), (size_t)n * 4, cudaMemcpyHostToDevice, sm));
+    rc = allgather(d_in.p, d_out.p, (size_t)mx, 2 /* ncclInt32 */, ctx->nccl_comm, sm);
+    if (rc) { pb_set_error(ctx, "ncclAllGather failed (%d)", rc); return PB_ERR_NCCL; }
+    all.resize((size_t)tot);
+    int64_t o = 0;
+    for (int r = 0; r < W; ++r) {
+        if (cnt[r]) PB_CUDA(ctx, cudaMemcpyAsync(all.data() + o, (char*)d_out.p + (size_t)r * mx * 4, (size_t)cnt[r] * 4, cudaMemcpyDeviceToHost, sm));
+        o += cnt[r];
+    }
+    PB_CUDA(ctx, cudaStreamSynchronize(sm));
+    return PB_OK;
+}
+
 // ---- host-side hit-table bookkeeping ---------------------------------------------------------------------------
 extern "C" int pb_rescore_m1(const pb_seqset* query, const pb_seqset* target, int64_t n_hits, const int32_t* q_id, const int32_t* s_id,
                              const int32_t* q_start, const int32_t* q_end, const int32_t* s_start, const int32_t* s_end,

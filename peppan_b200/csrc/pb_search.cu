@@ -469,12 +469,19 @@ __global__ void gather_kernel(const T* __restrict__ items, const uint32_t* __res
 // One thread per (query, target) segment of the sorted HSPs: greedy partition by diagonal (a cluster holds the HSPs
 // whose diagonal is within diag_span of the cluster's first), duplicates counted once; clusters that pass the score rule
 // are written at the slot of their first HSP; every other slot stays unused (qid = -1, preset by the caller).
-__global__ void hsp_cluster_kernel(const HspD* __restrict__ h, int n, int diag_span, int clu_max, int clu_sum, ClD* cl, unsigned int* ncl)
+// tri: lower-triangle mode of the clustering (only targets that precede the query in priority order can claim it):
+// segments whose target sequence index is >= tri.y + qid * tri.x are dropped before any alignment is made.
+__global__ void hsp_cluster_kernel(const HspD* __restrict__ h, int n, int diag_span, int clu_max, int clu_sum, ClD* cl, unsigned int* ncl,
+                                   int3 tri /* stride, offset, on */, int nt_mode, int nc, int F)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     if (k > 0 && h[k - 1].qid == h[k].qid && h[k - 1].tid == h[k].tid) return;      // not a segment head
     const int qid = h[k].qid, tid = h[k].tid;
+    if (tri.z) {
+        const int contig = nt_mode ? tid % nc : tid / F;
+        if (contig >= tri.y + qid * tri.x) return;
+    }
     int i = k;
     unsigned int found = 0;
     while (i < n && h[i].qid == qid && h[i].tid == tid) {
@@ -866,8 +873,9 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         PB_CUDA(ctx, d_cl.alloc((size_t)nh * sizeof(ClD), sm)); PB_CUDA(ctx, d_cls.alloc((size_t)nh * sizeof(ClD), sm));
         PB_CUDA(ctx, cudaMemsetAsync(d_cnt.as<unsigned long long>() + 4, 0, 8, sm));
         PB_CUDA(ctx, cudaMemsetAsync(d_cl.p, 0xff, (size_t)nh * sizeof(ClD), sm));
+        const int3 tri = make_int3(prm->reserved[1] > 0 ? prm->reserved[1] : 1, prm->reserved[2], (prm->reserved[0] & 4) ? 1 : 0);
         hsp_cluster_kernel<<<(nh + 127) / 128, 128, 0, sm>>>(d_hs.as<HspD>(), nh, spec.diag_span, spec.clu_max, spec.clu_sum, d_cl.as<ClD>(),
-                                                             reinterpret_cast<unsigned int*>(d_cnt.as<unsigned long long>() + 4));
+                                                             reinterpret_cast<unsigned int*>(d_cnt.as<unsigned long long>() + 4), tri, nt ? 1 : 0, (int)nc, F);
         PB_CUDA(ctx, cudaGetLastError()); launches += 2;
         rc = sort_by_keys<ClD>(ctx, d_cl.as<ClD>(), nh, d_perm2, &launches); if (rc) return rc;
         gather_kernel<ClD><<<(nh + 255) / 256, 256, 0, sm>>>(d_cl.as<ClD>(), d_perm2.as<uint32_t>(), nh, d_cls.as<ClD>());

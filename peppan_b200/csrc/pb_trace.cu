@@ -13,7 +13,7 @@
 //   co-optimal path; treating them as empty (H = 0) can only lower the values of cells that are themselves on no
 //   co-optimal path, so the cells holding S, the values along every co-optimal path and all tie-breaks (which compare
 //   only candidates that reach the cell's value) are those of the full matrix (checked against the oracle's full
-//   traceback by tests/test_sw_gpu.py and tests/test_search_gpu.py; on the CPU by orc_band_trace).
+//   traceback by tests/test_sw_gpu.py and tests/test_search_gpu.py; the band argument itself by a CPU test of the oracle).
 //
 // Layout: systolic strips as in the score kernel (pb_sw_kernel.cuh) -- a group of G lanes owns one pair, lane l keeps K
 // columns of H and E in registers, rows are streamed R = 2 per step, lane l runs one step behind lane l-1 -- but a column

@@ -41,7 +41,30 @@ t = torch.tensor(list(dig), dtype=torch.int64)
 ts = [torch.zeros_like(t) for _ in range(world)]
 dist.all_gather(ts, t)
 same = all(bool((x == ts[0]).all()) for x in ts)
-flag = torch.tensor([1.0 if (ok and same) else 0.0]); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+# clustering split over the ranks (queries of both phases dealt round-robin, joined[] / edges exchanged over NCCL): every
+# rank must end with the assignment a single GPU computes
+from peppan_b200 import clust
+rng = np.random.default_rng(11)
+genes = []
+for a in range(len(pool.genes)):
+    for c in range(int(rng.integers(1, 5))):
+        g = workloads._diverge(rng, pool.genes[a], float(rng.uniform(0.85, 1.0)))
+        genes.append(workloads._NT[g].tobytes().decode())
+genes.sort(key=lambda x: -len(x))
+gn, gb, go = seqio.to_seqset([(str(i), x) for i, x in enumerate(genes)])
+os.environ['PB_CLUSTER_BLOCK'] = '60000'          # several blocks, so both phases and the representative hand-over are exercised
+rep, cst = clust.cluster(ctx, gb, go, 0.9, 0.8)
+cl_ok = True
+if rank == 0:
+    rep1, _ = clust.cluster(solo, gb, go, 0.9, 0.8)
+    cl_ok = bool(np.array_equal(rep, rep1)) and cst['n_blocks'] > 2
+    print('rank0: clustering over', world, 'ranks:', int(cst['n_reps']), 'clusters in', int(cst['n_blocks']), 'blocks, equal to one GPU:', cl_ok)
+dig2 = hashlib.sha1(rep.tobytes()).digest()[:8]
+t2 = torch.tensor(list(dig2), dtype=torch.int64)
+ts2 = [torch.zeros_like(t2) for _ in range(world)]
+dist.all_gather(ts2, t2)
+same = same and all(bool((x == ts2[0]).all()) for x in ts2)
+flag = torch.tensor([1.0 if (ok and same and cl_ok) else 0.0]); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print('MGPU OK' if float(flag[0]) == 1.0 else 'MGPU FAILED', 'world', world)
 dist.barrier()
