@@ -19,7 +19,7 @@ ORC_ALN_DTYPE = np.dtype([(k, np.int32) for k in (
 
 def build(force=False):
     so = os.path.join(_HERE, 'libpb_oracle.so')
-    srcs = [os.path.join(_HERE, f) for f in ('pb_oracle.c', 'pb_search_oracle.c')]
+    srcs = [os.path.join(_HERE, f) for f in ('pb_oracle.c', 'pb_search_oracle.c', 'pb_sw_simd.c')]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(['make', '-C', _HERE, '-s', '-B'])
     return so
@@ -65,6 +65,22 @@ def sw_batch(q, qoff, t, toff, mat, go, ge, with_cigar=True, cigar_cap=None, nth
         raise RuntimeError('oracle: cigar capacity too small')
     cigars = [cg[i, :cn[i]].copy() for i in range(n)] if with_cigar else None
     return out, cigars
+
+
+def simd_lanes():
+    """int16 lanes of the vectorised CPU arm on this host (1: no AVX2, the arm falls back to the scalar routine)"""
+    return int(lib().orc_simd_lanes())
+
+
+def sw_batch_simd(q, qoff, t, toff, mat, go, ge, with_cigar=False, nthreads=1):
+    """Vectorised CPU arm (pb_sw_simd.c): score, end and start of every pair -- same values as sw_batch -- no CIGAR."""
+    assert not with_cigar
+    n = len(qoff) - 1
+    out = np.zeros(n, dtype=ORC_ALN_DTYPE)
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    nsym = int(max(int(q.max()) if len(q) else 0, int(t.max()) if len(t) else 0)) + 1
+    lib().orc_sw_batch_simd(_p(q), _p(qoff), _p(t), _p(toff), C.c_int64(n), _p(mat), C.c_int(go), C.c_int(ge), C.c_int(nsym), _p(out), C.c_int(nthreads))
+    return out, None
 
 
 def sw_score_batch(q, qoff, t, toff, mat, go, ge, nthreads=1):

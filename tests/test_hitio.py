@@ -47,3 +47,32 @@ def test_rejects_foreign_files(tmp_path):
         hitio.load_hits(p)
     with pytest.raises(ValueError):
         hitio.save_hits(p, *_table(1), ['a\nb'], ['c'])
+
+
+def test_bsn_file_round_trips_the_pipeline_tables(tmp_path, oracle_as_search):
+    """save_bsn / load_bsn (the flat replacement of `<prefix>.bsn.npz`, PEPPAN.py:866,924): the blastab uberBlast() returns for
+    iter_map_bsn's flag set (names, ints, floats, CIGAR strings, merge-group lists) and its overlap table come back cell for
+    cell with the same Python types."""
+    import os
+    from peppan_b200 import hitio, uberBlast as ub, workloads
+    pool = workloads.GenePool(30, 30, seed=workloads.SEED + 9)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=15, seed=workloads.SEED + 9)
+    ref, qry = os.path.join(tmp_path, 'g.fa'), os.path.join(tmp_path, 'q.fa')
+    open(ref, 'w').write('>g0\n%s\n' % seq)
+    open(qry, 'w').write(''.join('>%s\n%s\n' % x for x in pool.fasta_items()))
+    tab, ovl = ub.uberBlast(['-r', ref, '-q', qry, '-f', '-m', '-O', '--blastn', '--diamond', '--min_id', '0.4', '--min_cov', '50', '--min_ratio', '0.25',
+                             '-s', '1', '-e', '0,3'])
+    assert tab.shape[0] > 30 and tab.shape[1] == 17
+    path = os.path.join(tmp_path, 'x.bsn')
+    hitio.save_bsn(path, tab, ovl)
+    tab2, ovl2 = hitio.load_bsn(path)
+    assert tab2.shape == tab.shape and np.array_equal(ovl2, ovl) and ovl2.dtype == np.int64
+    for a, b in zip(tab.reshape(-1).tolist(), tab2.reshape(-1).tolist()):
+        assert type(a) is type(b) and a == b
+        if isinstance(a, list):
+            assert [type(x) for x in a] == [type(x) for x in b]
+    # raw (not rescored) tables carry integer scores next to float identities
+    tab3 = ub.uberBlast(['-r', ref, '-q', qry, '--blastn', '--min_id', '0.4', '--min_cov', '50', '--min_ratio', '0.25'])
+    hitio.save_bsn(path, tab3, np.zeros([0, 3], dtype=np.int64))
+    tab4, ovl4 = hitio.load_bsn(path)
+    assert ovl4.shape == (0, 3) and all(type(a) is type(b) and a == b for a, b in zip(tab3.reshape(-1).tolist(), tab4.reshape(-1).tolist()))

@@ -4,6 +4,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from peppan_b200 import seqcodec, workloads
 
@@ -286,3 +287,19 @@ def test_score_bounded_band_preserves_the_start_cell(oracle):
             assert found is not None and (a['qe'] - (found[0] - 1), a['te'] - (found[1] - 1)) == (a['qs'], a['ts']), (p, M, N, I, D)
             n += 1
     assert n > 100 and narrowed > 30
+
+
+def test_vectorised_cpu_arm_equals_the_scalar_oracle(oracle):
+    """oracle/pb_sw_simd.c (the timed CPU baseline of bench.py) returns the scalar oracle's score, end and start for every
+    pair: ragged lengths, related and unrelated pairs, both scoring schemes."""
+    from peppan_b200 import seqcodec, sw, workloads
+    if oracle.simd_lanes() == 1:
+        pytest.skip('host without AVX2: the arm falls back to the scalar routine')
+    for seed, nreal, params in ((3, 20, seqcodec.protein_params()), (4, 4, seqcodec.nt_params())):
+        qs, ts = workloads.random_pairs(1500, seed, nsym_real=nreal, min_len=1, max_len=500)
+        q, qo = sw.concat(qs); t, to = sw.concat(ts)
+        mat = np.frombuffer(bytes(params.matrix), dtype=np.int8)
+        a, _ = oracle.sw_batch(q, qo, t, to, mat, params.gap_open, params.gap_extend, with_cigar=False, nthreads=4)
+        b, _ = oracle.sw_batch_simd(q, qo, t, to, mat, params.gap_open, params.gap_extend, nthreads=4)
+        for k in ('score', 'qs', 'qe', 'ts', 'te'):
+            assert np.array_equal(a[k], b[k]), (seed, k)
