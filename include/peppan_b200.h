@@ -64,6 +64,10 @@ void pb_destroy(pb_ctx* ctx);
 const char* pb_last_error(pb_ctx* ctx);      /* ctx may be NULL: returns the last global error */
 int  pb_nccl_unique_id(void* uid128);
 int  pb_device_info(pb_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int64_t* hbm_bytes);
+/* Optional: make the context's device memory pool hold `bytes` now.  Every entry point takes its working memory from that
+ * pool and the pool never shrinks, so calls that follow do not pay for growing it (growing costs tens of ms per GB, more
+ * than a search of a genome).  Long-running callers (one context per worker, PEPPAN.py:922) reserve once at start-up. */
+int  pb_reserve(pb_ctx* ctx, int64_t bytes);
 
 /* ---- batched Smith-Waterman (gapped extension) --------------------------------------- */
 /* Replaces the gapped-extension + traceback arithmetic inside blastn (modules/uberBlast.py:294-296)
@@ -196,6 +200,7 @@ typedef struct {
     int32_t greedy_rounds;
     int32_t kernel_launches;
     int32_t reserved;
+    int64_t n_pairs_remembered;  /* candidate windows answered from alignments remembered by earlier calls (not aligned again) */
 } pb_cluster_stats;
 
 /* Replaces mmseqs createdb / linclust --min-seq-id min_id -c min_cov / createtsv and the
@@ -211,6 +216,12 @@ int  pb_cluster(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov
  * BLOSUM62 11/1; identity and coverage over the protein alignment), gtable as in pb_search. */
 int  pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, float min_cov, int translate, int gtable,
                    int32_t* rep_of, pb_cluster_stats* stats /* nullable */);
+
+/* pb_cluster remembers, per context, the alignment of every gene pair it has verified (keyed by sequence content), because
+ * its caller iterClust (PEPPAN.py:1777-1792) clusters nested gene sets at eleven thresholds and the alignment of a pair does
+ * not depend on the threshold.  The memory is bounded (environment PB_CLUSTER_MEMO_MB, default 4096, 0 = off) and is released
+ * with the context; pb_cluster_forget drops it earlier (e.g. between unrelated data sets, or before a timed run). */
+int  pb_cluster_forget(pb_ctx* ctx);
 
 /* reScore + cigar2score mode 1 (modules/uberBlast.py:397-415, :243-249) for a whole hit table at once, on the host (it is
  * bookkeeping over the CIGARs, not a kernel; no context needed).  Sequences are the ASCII seqsets handed to pb_search;

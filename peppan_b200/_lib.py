@@ -46,6 +46,7 @@ def load():
     lib.pb_last_error.restype = C.c_char_p
     lib.pb_nccl_unique_id.argtypes = [vp]
     lib.pb_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    lib.pb_reserve.argtypes = [vp, i64]
     lib.pb_sw_batch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ScoreParams), vp, vp, vp, vp, vp,
                                 C.POINTER(SwStats)]
     lib.pb_sw_align_batch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ScoreParams), vp, vp, vp, vp, vp, vp, vp,
@@ -92,6 +93,10 @@ class Context(object):
         sm, clk, mem = C.c_int32(), C.c_int32(), C.c_int64()
         self.check(self.lib.pb_device_info(self.h, C.byref(sm), C.byref(clk), C.byref(mem)), 'pb_device_info')
         return dict(sm_count=sm.value, clock_khz=clk.value, hbm_bytes=mem.value)
+
+    def reserve(self, nbytes):
+        """pb_reserve: let the context's device memory pool hold `nbytes` now, so that later calls do not grow it"""
+        self.check(self.lib.pb_reserve(self.h, int(nbytes)), 'pb_reserve')
 
     def dpx_peak(self, which=0):
         v = C.c_double()

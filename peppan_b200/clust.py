@@ -22,7 +22,7 @@ from .uberBlast import get_context, logger
 class ClusterStats(C.Structure):
     _fields_ = [('n_blocks', C.c_int64), ('n_pairs_verified', C.c_int64), ('n_edges', C.c_int64), ('n_reps', C.c_int64),
                 ('sw_cells', C.c_double), ('ms_total', C.c_float), ('greedy_rounds', C.c_int32), ('kernel_launches', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('reserved', C.c_int32), ('n_pairs_remembered', C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
@@ -39,6 +39,12 @@ def cluster(ctx, seq_bytes, seq_off, identity, coverage, translate=False, gtable
     st = ClusterStats()
     ctx.check(lib.pb_cluster_ex(ctx.h, C.byref(ss), identity, coverage, 1 if translate else 0, gtable, ptr(rep), C.byref(st)), 'pb_cluster_ex')
     return rep, st.as_dict()
+
+
+def forget(ctx):
+    """pb_cluster_forget: drop the pair alignments remembered from earlier cluster() calls of this context"""
+    ctx.lib.pb_cluster_forget.argtypes = [C.c_void_p]
+    ctx.check(ctx.lib.pb_cluster_forget(ctx.h), 'pb_cluster_forget')
 
 
 def _read_records(path):

@@ -17,7 +17,9 @@
 // The greedy assignment itself runs on the device as a monotone fixed-point iteration: a gene is
 // decided once all its earlier neighbours are decided (K3).
 #include "pb_common.h"
+#include "pb_memo.h"
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -65,6 +67,17 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
     PB_CUDA(ctx, cudaEventRecord(ctx->ev[13], sm));
     int64_t BLOCK_RES = 24ll << 20;                // residues of new genes per block (PB_CLUSTER_BLOCK overrides: test aid)
     if (const char* e = getenv("PB_CLUSTER_BLOCK")) { long long v = atoll(e); if (v > 0) BLOCK_RES = v; }
+    // content hash of every gene: the key under which the alignments of its pairs are remembered across calls (pb_memo.h)
+    std::vector<uint64_t> ghash((size_t)n);
+    {
+        const int nth = (int)std::min<int64_t>(8, std::max<int64_t>(1, n / 4096));
+        std::vector<std::thread> th;
+        for (int k = 0; k < nth; ++k)
+            th.emplace_back([&, k]() { for (int64_t i = k; i < n; i += nth) ghash[i] = pb_seq_hash(genes->residues + genes->offsets[i], genes->offsets[i + 1] - genes->offsets[i]) ^ (translate ? 0x5bd1e995ull : 0ull); });
+        for (auto& t : th) t.join();
+    }
+    int64_t memo_stats[2] = {0, 0};
+    std::vector<uint64_t> rep_hash, qhash, thash;
     std::vector<int> reps;                          // global ids of the representatives so far
     std::vector<uint8_t> tbuf; std::vector<int64_t> toff;
     std::vector<uint8_t> rep_bytes; std::vector<int64_t> rep_off(1, 0);
@@ -89,6 +102,7 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
         auto verified = [&](const pb_hits& hits, const pb_hit& x) {
             if (translate && x.frame != 1) return false;
             int gapb = 0;
+            if (x.cigar_n == 0) gapb = (int)x.cigar_off * (translate ? 3 : 1);       // memo path: gap bases instead of a CIGAR (pb_search_memo)
             for (uint32_t k = 0; k < x.cigar_n; ++k) { uint32_t op = hits.cigar[x.cigar_off + k]; if (op & 3) gapb += (int)(op >> 2); }
             const int nm = x.aln_len - x.mismatch - gapb;
             const double iden = (double)nm / (double)x.aln_len;
@@ -120,8 +134,11 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
                 my_share(everyone, sbytes, soff, smine);
                 qs = pb_seqset{sbytes.data(), soff.data(), (int64_t)smine.size()};
             }
+            qhash.clear();
+            if (W > 1) for (int i : smine) qhash.push_back(ghash[first + i]);
+            else for (int i = 0; i < nb; ++i) qhash.push_back(ghash[first + i]);
             pb_hits hits; pb_search_stats sst;
-            int rc = pb_search(ctx, &qs, &ts, &prm, &hits, &sst);
+            int rc = pb_search_memo(ctx, &qs, &ts, &prm, &hits, &sst, qhash.data(), rep_hash.data(), memo_stats);
             if (rc) return rc;
             st.n_pairs_verified += sst.n_windows; st.sw_cells += sst.sw_cells; st.kernel_launches += sst.kernel_launches;
             for (int64_t h = 0; h < hits.n_hits; ++h) {
@@ -160,8 +177,11 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
                 my_share(everyone, sbytes, soff, smine);
                 nq = pb_seqset{sbytes.data(), soff.data(), (int64_t)smine.size()};
             }
+            thash.clear(); qhash.clear();
+            for (int i : novel) thash.push_back(ghash[first + i]);
+            if (W > 1) for (int i : smine) qhash.push_back(ghash[first + i]); else qhash = thash;
             pb_hits hits; pb_search_stats sst;
-            int rc = pb_search(ctx, &nq, &ns, &prm2, &hits, &sst);
+            int rc = pb_search_memo(ctx, &nq, &ns, &prm2, &hits, &sst, qhash.data(), thash.data(), memo_stats);
             if (rc) return rc;
             st.n_pairs_verified += sst.n_windows; st.sw_cells += sst.sw_cells; st.kernel_launches += sst.kernel_launches;
             std::vector<int32_t> mine_edges;             // (b, a) in novel-local indices, a earlier than b, flattened
@@ -207,7 +227,7 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
         }
         for (int i = 0; i < nb; ++i)
             if (rep_of[first + i] == first + i) {
-                reps.push_back((int)(first + i));
+                reps.push_back((int)(first + i)); rep_hash.push_back(ghash[first + i]);
                 const int64_t a = genes->offsets[first + i], L = genes->offsets[first + i + 1] - a;
                 rep_bytes.insert(rep_bytes.end(), genes->residues + a, genes->residues + a + L);
                 rep_off.push_back(rep_off.back() + L);
@@ -215,7 +235,7 @@ extern "C" int pb_cluster_ex(pb_ctx* ctx, const pb_seqset* genes, float min_id, 
         st.n_blocks++;
         first = last;
     }
-    st.n_reps = (int64_t)reps.size();
+    st.n_reps = (int64_t)reps.size(); st.n_pairs_remembered = memo_stats[0];
     PB_CUDA(ctx, cudaEventRecord(ctx->ev[14], sm));
     PB_CUDA(ctx, cudaEventSynchronize(ctx->ev[14]));
     cudaEventElapsedTime(&st.ms_total, ctx->ev[13], ctx->ev[14]);

@@ -24,12 +24,24 @@ struct pb_ctx {
     void* nccl_comm = nullptr;      // ncclComm_t when world > 1
     void* nccl_dl = nullptr;        // dlopen handle of libnccl
     int* d_counter = nullptr;       // small scratch of task counters (64 ints)
+    void* memo = nullptr;           // PairMemo* of the clustering path (pb_memo.h), created on first use
+    // grow-only device scratch of the traceback (direction planes, block borders per shape class): sizes change from call to
+    // call, and growing the stream-ordered pool each time costs far more than the kernels (pb_trace.cu)
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
 };
 
 void pb_set_error(pb_ctx* ctx, const char* fmt, ...);
+// grow-only scratch slot `k` of the context with at least `bytes` (cudaMalloc; the previous block is freed after the stream drains)
+int pb_scratch(pb_ctx* ctx, int k, size_t bytes, void** out);
 // exchanges over the context's NCCL communicator (no-ops with world == 1); pb_ctx.cu
 int pb_allreduce_max_i32(pb_ctx* ctx, int32_t* v, int64_t n);
 int pb_allgather_i32(pb_ctx* ctx, const std::vector<int32_t>& mine, std::vector<int32_t>& all);
+// pb_search for the clustering path: qh / th = content hashes of the query / target sequences; windows whose alignment the
+// context's memo already holds are not aligned again, new alignments are remembered (pb_memo.h).  Hits carry no CIGAR:
+// cigar_n = 0 and cigar_off = number of gap bases.  memo_stats (nullable): [0] windows answered by the memo, [1] remembered.
+int pb_search_memo(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const pb_search_params* prm, pb_hits* out,
+                   pb_search_stats* stats, const uint64_t* qh, const uint64_t* th, int64_t* memo_stats);
 
 #define PB_CUDA(ctx, call)                                                                        \
     do {                                                                                          \

@@ -1,5 +1,6 @@
 // Context management, error reporting and NCCL plumbing of libpeppan_b200.
 #include "pb_common.h"
+#include "pb_memo.h"
 #include <cstdarg>
 #include <dlfcn.h>
 #include <mutex>
@@ -126,6 +127,8 @@ extern "C" void pb_destroy(pb_ctx* ctx)
         auto d = (nccl_destroy_fn)dlsym(ctx->nccl_dl, "ncclCommDestroy");
         if (d) d(ctx->nccl_comm);
     }
+    delete static_cast<PairMemo*>(ctx->memo);
+    for (void* p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_pipe) if (ev) cudaEventDestroy(ev);
@@ -145,7 +148,41 @@ extern "C" int pb_device_info(pb_ctx* ctx, int32_t* sm_count, int32_t* clock_khz
     return PB_OK;
 }
 
+int pb_scratch(pb_ctx* ctx, int k, size_t bytes, void** out)
+{
+    if (ctx->scratch_bytes[k] < bytes) {
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch[k]) { cudaFree(ctx->scratch[k]); ctx->scratch[k] = nullptr; ctx->scratch_bytes[k] = 0; }
+        const size_t want = bytes + bytes / 8;
+        if (cudaMalloc(&ctx->scratch[k], want) == cudaSuccess) ctx->scratch_bytes[k] = want;
+        else { cudaGetLastError(); PB_CUDA(ctx, cudaMalloc(&ctx->scratch[k], bytes)); ctx->scratch_bytes[k] = bytes; }
+    }
+    *out = ctx->scratch[k];
+    return PB_OK;
+}
+
 extern "C" void pb_free(void* p) { free(p); }
+
+extern "C" int pb_reserve(pb_ctx* ctx, int64_t bytes)
+{
+    if (!ctx || bytes < 0) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the pool keeps what it has once held (release threshold = max): holding `bytes` once makes later calls allocation-free
+    void* p = nullptr;
+    if (bytes > 0) {
+        PB_CUDA(ctx, cudaMallocAsync(&p, (size_t)bytes, ctx->stream));
+        PB_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_cluster_forget(pb_ctx* ctx)
+{
+    if (!ctx) return PB_ERR_ARG;
+    if (ctx->memo) static_cast<PairMemo*>(ctx->memo)->clear();
+    return PB_OK;
+}
 
 // Pinned host staging buffers for callers that want full-rate H2D/D2H copies.
 extern "C" int pb_host_alloc(pb_ctx* ctx, int64_t bytes, void** out)

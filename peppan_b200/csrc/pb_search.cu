@@ -19,6 +19,7 @@
 // The search specification (constants below) is restated in scalar C in oracle/pb_search_oracle.c
 // and the two are compared hit for hit by tests/test_search_gpu.py.
 #include "pb_sw_job.h"
+#include "pb_memo.h"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <climits>
@@ -678,8 +679,16 @@ extern "C" void pb_free_hits(pb_hits* h)
 
 // group (nullable): group[c] = genome of target sequence c, non-decreasing, < n_groups; the per-query hit cap and the output
 // order are then per group, and group_off (n_groups + 1) receives the first hit of every group.
+struct MemoArgs { const uint64_t* qh; const uint64_t* th; PairMemo* memo; int64_t hits, puts; };
+
+__global__ void empty_views_kernel(const uint8_t* __restrict__ mask, int n, const int64_t* __restrict__ qbeg, int64_t* qend)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && mask[i]) qend[i] = qbeg[i];
+}
+
 static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const pb_search_params* prm,
-                       const int32_t* group, int32_t n_groups, pb_hits* out, int64_t* group_off, pb_search_stats* stats)
+                       const int32_t* group, int32_t n_groups, pb_hits* out, int64_t* group_off, pb_search_stats* stats, MemoArgs* memo = nullptr)
 {
     if (!ctx || !query || !target || !prm || !out) { pb_set_error(ctx, "pb_search: invalid argument"); return PB_ERR_ARG; }
     if (group) {
@@ -910,6 +919,32 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
             qb[i] = QL.off[win[i].qid]; tb[i] = TL.off[win[i].tid] + win[i].tbeg;
             if (win[i].tlen > 0) { cells += (double)QL.len[win[i].qid] * (double)win[i].tlen; ++st.n_windows; }
         }
+        // clustering path: windows whose alignment is already known (pb_memo.h) become empty views and cost nothing
+        std::vector<uint8_t> known;
+        std::vector<MemoVal> kval;
+        std::vector<uint64_t> mk1, mk2;
+        if (memo) {
+            known.assign(nw, 0); kval.resize(nw); mk1.resize(nw); mk2.resize(nw);
+            int64_t nk = 0;
+            for (int64_t i = 0; i < nw; ++i) {
+                if (win[i].tlen <= 0) continue;
+                const int contig = nt ? win[i].tid % (int)nc : win[i].tid / F;
+                PairMemo::key(memo->qh[win[i].qid], memo->th[contig], win[i].tbeg + (int64_t)(nt ? 0 : (win[i].tid % F)) * 0x40000000ll, win[i].tlen, &mk1[i], &mk2[i]);
+                if (const MemoVal* v = memo->memo->find(mk1[i], mk2[i])) {
+                    known[i] = 1; kval[i] = *v; ++nk;
+                    cells -= (double)QL.len[win[i].qid] * (double)win[i].tlen;
+                }
+            }
+            memo->hits += nk;
+            if (nk > 0) {
+                DevBuf d_mask;
+                PB_CUDA(ctx, d_mask.alloc((size_t)nw, sm));
+                PB_CUDA(ctx, cudaMemcpyAsync(d_mask.p, known.data(), (size_t)nw, cudaMemcpyHostToDevice, sm));
+                empty_views_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, sm>>>(d_mask.as<uint8_t>(), (int)nw, d_wqb.as<int64_t>(), d_wqe.as<int64_t>());
+                PB_CUDA(ctx, cudaGetLastError()); ++launches;
+                PB_CUDA(ctx, cudaStreamSynchronize(sm));
+            }
+        }
         pb_sw_job* J = nullptr;
         // forward pass (score + end cell) for every window; the start cell and the path come from one banded reverse pass
         int rc = pb_sw_job_create_views_dev(ctx, d_qc.as<uint8_t>(), d_tc.as<uint8_t>(), d_wqb.as<int64_t>(), d_wqe.as<int64_t>(), d_wtb.as<int64_t>(),
@@ -929,13 +964,43 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
                 const double m_eff = nt ? (double)qlen_nt[qid] : (double)QL.len[qid];
                 const double ev = K0 * m_eff * 5.0e6 * std::exp(-lam0 * (double)score[i]);
                 const double qspan_max = (double)(aqe[i] + 1) * (nt ? 1.0 : 3.0);
-                if (ev > emax0 || qspan_max < prm->min_cov || qspan_max < prm->min_ratio * (double)qlen_nt[qid]) score[i] = 0;
+                if (ev > emax0 || qspan_max < prm->min_cov || qspan_max < prm->min_ratio * (double)qlen_nt[qid]) {
+                    // remembered as a forward-only result: the cuts are re-applied to it whenever it is looked up
+                    if (memo && !known[i]) { memo->memo->put(mk1[i], mk2[i], MemoVal{score[i], -1, aqe[i], -1, ate[i], 0, 0, 0, 0}); ++memo->puts; }
+                    score[i] = 0;
+                }
             }
         }
         pb_trace_stats tst; memset(&tst, 0, sizeof(tst));
         rc = pb_sw_trace(ctx, J, qb.data(), tb.data(), score.data(), aqe.data(), ate.data(), aqs.data(), ats.data(), counts.data(), coff.data(), &cops, &tst);
         if (rc) return rc;
         ms_trace = tst.ms; const int tl_launch = tst.launches;
+        if (memo) {
+            const double lam0 = nt ? 0.625 : 0.267, K0 = nt ? 0.41 : 0.041, emax0 = nt ? 1e-2 : 1.0;
+            for (int64_t i = 0; i < nw; ++i) {
+                if (known[i]) {
+                    const MemoVal& v = kval[i];
+                    score[i] = v.score; aqs[i] = v.qs; aqe[i] = v.qe; ats[i] = v.ts; ate[i] = v.te;
+                    counts[4 * i] = v.nm; counts[4 * i + 1] = v.nx; counts[4 * i + 2] = v.ngo; counts[4 * i + 3] = v.ngb;
+                    if (v.qs < 0 && v.score > 0) {
+                        // forward-only entry: it stays out unless today's cuts would let it through, which cannot be decided
+                        // without the path; with pb_cluster's fixed cuts it never does
+                        const int qid = win[i].qid;
+                        const double m_eff = nt ? (double)qlen_nt[qid] : (double)QL.len[qid];
+                        const double ev = K0 * m_eff * 5.0e6 * std::exp(-lam0 * (double)v.score);
+                        const double qspan_max = (double)(v.qe + 1) * (nt ? 1.0 : 3.0);
+                        if (!(ev > emax0 || qspan_max < prm->min_cov || qspan_max < prm->min_ratio * (double)qlen_nt[qid])) {
+                            pb_set_error(ctx, "pb_search: a remembered forward-only alignment passes the present cuts; call pb_cluster_forget when thresholds other than identity change");
+                            free(cops); return PB_ERR_ARG;
+                        }
+                        score[i] = 0;
+                    }
+                } else if (score[i] > 0 && win[i].tlen > 0) {
+                    memo->memo->put(mk1[i], mk2[i], MemoVal{score[i], aqs[i], aqe[i], ats[i], ate[i], counts[4 * i], counts[4 * i + 1], counts[4 * i + 2], counts[4 * i + 3]});
+                    ++memo->puts;
+                }
+            }
+        }
         st.sw_cells = sst.cells; st.ms_sw = sst.ms_total_device; st.ms_trace = ms_trace;
         launches += sst.kernel_launches + tl_launch;
     }
@@ -1026,7 +1091,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         uniq.swap(kept);
     }
     int64_t ncig = 0;
-    for (const Rec& r : uniq) ncig += coff[r.win + 1] - coff[r.win];
+    if (!memo) for (const Rec& r : uniq) ncig += coff[r.win + 1] - coff[r.win];
     pb_hit* hits = (pb_hit*)malloc(std::max<size_t>(uniq.size(), 1) * sizeof(pb_hit));
     uint32_t* cig = (uint32_t*)malloc((size_t)std::max<int64_t>(ncig, 1) * 4);
     if (!hits || !cig) { free(hits); free(cig); pb_set_error(ctx, "pb_search: out of host memory"); return PB_ERR_NOMEM; }
@@ -1035,6 +1100,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         pb_hit h = uniq[i].h;
         const int64_t a = coff[uniq[i].win], n = coff[uniq[i].win + 1] - a;
         h.cigar_off = (uint32_t)co; h.cigar_n = (uint32_t)n;
+        if (memo) { h.cigar_off = (uint32_t)counts[4 * uniq[i].win + 3]; h.cigar_n = 0; hits[i] = h; if (group) group_off[uniq[i].grp + 1]++; continue; }
         for (int64_t k = 0; k < n; ++k) {
             uint32_t op = cops[a + k];
             if (!nt) op = (((op >> 2) * 3) << 2) | (op & 3);      // amino-acid ops -> nucleotide units (modules/uberBlast.py:33)
@@ -1053,7 +1119,8 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
     cudaEventElapsedTime(&st.ms_encode, e0, e1); cudaEventElapsedTime(&st.ms_index, e1, e2);
     cudaEventElapsedTime(&st.ms_seed, e2, e3); cudaEventElapsedTime(&st.ms_total, e0, e4);
     st.kernel_launches = launches;
-    if (dbg) fprintf(stderr, "[pb_search] host: cluster/window %.1f ms, sw+trace (incl. host) %.1f ms, records %.1f ms\n", h1 - h0, h2 - h1, now() - h2);
+    if (dbg) fprintf(stderr, "[pb_search] device: encode %.1f, index %.1f, seed %.1f, sw %.1f, trace %.1f ms; host: cluster/window %.1f ms, sw+trace (incl. host) %.1f ms, records %.1f ms; %lld windows, %.3g cells\n",
+                     st.ms_encode, st.ms_index, st.ms_seed, st.ms_sw, st.ms_trace, h1 - h0, h2 - h1, now() - h2, (long long)st.n_windows, st.sw_cells);
     if (stats) *stats = st;
     return PB_OK;
 }
@@ -1069,4 +1136,20 @@ extern "C" int pb_search_grouped(pb_ctx* ctx, const pb_seqset* query, const pb_s
 {
     if (!target_group) { pb_set_error(ctx, "pb_search_grouped: target_group missing"); return PB_ERR_ARG; }
     return search_impl(ctx, query, target, prm, target_group, n_groups, out, group_off, stats);
+}
+
+int pb_search_memo(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* target, const pb_search_params* prm, pb_hits* out,
+                   pb_search_stats* stats, const uint64_t* qh, const uint64_t* th, int64_t* memo_stats)
+{
+    if (!ctx) return PB_ERR_ARG;
+    if (!ctx->memo) {
+        long long mb = 4096;
+        if (const char* e = getenv("PB_CLUSTER_MEMO_MB")) mb = atoll(e);
+        if (mb > 0) ctx->memo = new (std::nothrow) PairMemo((size_t)mb << 20);
+    }
+    if (!ctx->memo || !qh || !th) return search_impl(ctx, query, target, prm, nullptr, 0, out, nullptr, stats);
+    MemoArgs ma{qh, th, static_cast<PairMemo*>(ctx->memo), 0, 0};
+    const int rc = search_impl(ctx, query, target, prm, nullptr, 0, out, nullptr, stats, &ma);
+    if (memo_stats) { memo_stats[0] += ma.hits; memo_stats[1] += ma.puts; }
+    return rc;
 }

@@ -512,9 +512,10 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     chunk_ops.resize(chunks.size()); chunk_ooff.resize(chunks.size());
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk& c = chunks[ci];
-        DevBuf ddesc, ddir, dnops, dcounts, dooff, dops, dstart;
+        DevBuf ddesc, dnops, dcounts, dooff, dops, dstart;
+        void* ddir = nullptr;
+        { const int rc = pb_scratch(ctx, 0, std::max<size_t>(c.words, 4) * 4, &ddir); if (rc) return rc; }
         PB_CUDA(ctx, ddesc.alloc(c.count * sizeof(BandDesc), sm));
-        PB_CUDA(ctx, ddir.alloc(std::max<size_t>(c.words, 4) * 4, sm));
         PB_CUDA(ctx, dnops.alloc(c.count * 4, sm));
         PB_CUDA(ctx, dcounts.alloc(c.count * 16, sm));
         PB_CUDA(ctx, dstart.alloc(c.count * sizeof(int2), sm));
@@ -524,10 +525,10 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         const int bstride = ((c.maxM + 63) / 64) * 64;
         TraceArgs a;
         a.q = J->dq; a.t = J->dt; a.matrix = J->matrix.as<int8_t>(); a.nsym = nsym; a.go = params->gap_open; a.ge = params->gap_extend;
-        a.dir = ddir.as<uint32_t>(); a.bstride = bstride;
+        a.dir = reinterpret_cast<uint32_t*>(ddir); a.bstride = bstride;
         // sorted order inside the chunk: [xwide][wide][narrow].  The few long / wide pairs go to the aux stream and run beside
         // the narrow ones.
-        DevBuf dbound[3];
+        void* dbound[3] = {nullptr, nullptr, nullptr};
         bool forked[3] = {false, false, false};
         cudaStream_t side[3] = {sm, ctx->copy_stream, ctx->aux_stream};
         size_t first = 0;
@@ -536,10 +537,10 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
             if (cnt == 0) continue;
             const int NG = 32 / tb_shape(k).G;
             const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid_c[k], (cnt + (size_t)TB_WARPS * NG - 1) / ((size_t)TB_WARPS * NG)));
-            PB_CUDA(ctx, dbound[k].alloc((size_t)grid * TB_WARPS * NG * bstride * sizeof(uint2), sm));
+            { const int rc = pb_scratch(ctx, 1 + k, (size_t)grid * TB_WARPS * NG * bstride * sizeof(uint2), &dbound[k]); if (rc) return rc; }
             TraceArgs r = a;
             r.desc = ddesc.as<BandDesc>() + first; r.count = (int)cnt; r.counter = ctx->d_counter + k;
-            r.boundary = dbound[k].as<uint2>(); r.start = dstart.as<int2>() + first;
+            r.boundary = reinterpret_cast<uint2*>(dbound[k]); r.start = dstart.as<int2>() + first;
             cudaStream_t ks = sm;
             if (k > 0 && cnt < c.count) {            // the few long / wide pairs run beside the rest on their own streams
                 PB_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[k], sm)); PB_CUDA(ctx, cudaStreamWaitEvent(side[k], ctx->ev_pipe[k], 0));

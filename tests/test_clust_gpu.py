@@ -84,6 +84,28 @@ def test_family_larger_than_any_hit_cap_stays_one_cluster(ctx):
     assert (rep == 0).all() and st['n_reps'] == 1
 
 
+def test_remembered_alignments_do_not_change_the_ladder(ctx, oracle):
+    # iterClust's shape: nested gene sets at falling thresholds.  The second and third rung find most of their pairs in the
+    # context's memo (pb_cluster_forget / pb_memo.h); the assignments must be those of a context that remembers nothing,
+    # and those of the oracle.
+    items = _genes(6, n_anc=70)
+    clust.forget(ctx)
+    cur = items
+    remembered = []
+    for identity in (0.97, 0.93, 0.9):
+        names, buf, off = seqio.to_seqset(cur)
+        rep, st = clust.cluster(ctx, buf, off, identity, 0.8)
+        remembered.append(int(st['n_pairs_remembered']))
+        want = _oracle_clusters(oracle, cur, identity, 0.8)
+        assert np.array_equal(rep, want), identity
+        cur = [cur[i] for i in np.nonzero(rep == np.arange(len(rep)))[0]]
+    assert remembered[0] == 0 and remembered[1] > 0 and remembered[2] > 0
+    clust.forget(ctx)
+    names, buf, off = seqio.to_seqset(items)
+    rep, st = clust.cluster(ctx, buf, off, 0.97, 0.8)
+    assert int(st['n_pairs_remembered']) == 0
+
+
 def test_cluster_blocked_equals_single_block(ctx, monkeypatch):
     items = _genes(2, n_anc=80)
     names, buf, off = seqio.to_seqset(items)
