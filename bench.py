@@ -424,7 +424,8 @@ def genes_of(genomes):
 def config3_leg(ctx, rank, world, pg, genomes, qpin, qo, batch):
     """BASELINE.json configs[2]: all-vs-all clustering of the genes of the genomes (the identity ladder of iterClust,
     PEPPAN.py:1777-1792: getClust at 1.00, 0.99, ... 0.90 on the shrinking exemplar set, coverage 0.8) + the per-genome
-    search of the same genomes.  Every rank works on its own genomes (N>1: independent replicas of the leg)."""
+    search of the same genomes.  N>1: every rank holds the same genomes; pb_cluster deals the queries of each block over
+    the ranks and exchanges joined[] / edges over NCCL (strong scaling), the searched genomes are sharded g mod world."""
     from peppan_b200 import clust, search, seqio
     genes = genes_of(genomes)
     n0 = len(genes)
@@ -450,9 +451,16 @@ def config3_leg(ctx, rank, world, pg, genomes, qpin, qo, batch):
         buf, off = np.ascontiguousarray(nb), no
     barrier(pg)
     t_clu = allmax(pg, time.perf_counter() - t0)
-    # per-genome search of the same genomes against the exemplar pool
-    tbuf, toff = pack_genomes(ctx, genomes)
-    ng = len(genomes)
+    same = True
+    if world > 1:
+        dig = [None] * world
+        pg.all_gather_object(dig, hashlib.blake2b(buf.tobytes() + off.tobytes(), digest_size=8).hexdigest())
+        same = len(set(dig)) == 1
+    cells = allsum(pg, float(cells)); pairs = allsum(pg, float(pairs))
+    # per-genome search of the same genomes against the exemplar pool, genomes sharded over the ranks
+    mine = genomes[rank::world]
+    tbuf, toff = pack_genomes(ctx, mine)
+    ng = len(mine)
     barrier(pg)
     t0 = time.perf_counter()
     nh = 0
@@ -464,11 +472,12 @@ def config3_leg(ctx, rank, world, pg, genomes, qpin, qo, batch):
             nh += len(hits); launches += st['kernel_launches']
     barrier(pg)
     t_srch = allmax(pg, time.perf_counter() - t0)
-    return {'workload': 'configs[2]: %d synthetic genomes per GPU (%d genes): 11-rung identity ladder of iterClust through pb_cluster (coverage 0.8) '
-                        '+ per-genome search (nt + protein 6-frame) of the same genomes vs %d exemplars' % (ng, n0, len(qo) - 1),
-            'genomes_per_gpu': ng, 'named_size': ng >= 100, 'ladder_seconds': t_clu, 'genes_clustered_per_s': allsum(pg, float(n0)) / t_clu,
+    return {'workload': 'configs[2]: %d synthetic genomes (%d genes): 11-rung identity ladder of iterClust through pb_cluster (coverage 0.8; alignments of a pair are '
+                        'remembered across the rungs, the ladder starts with nothing remembered) + per-genome search (nt + protein 6-frame) of the same genomes vs %d exemplars' % (len(genomes), n0, len(qo) - 1),
+            'genomes': len(genomes), 'named_size': len(genomes) >= 100, 'scaling': 'strong (one gene set; queries of every block dealt over the ranks, NCCL exchange of joined[] and edges)' if world > 1 else None,
+            'ranks_agree': bool(same), 'ladder_seconds': t_clu, 'genes_clustered_per_s': float(n0) / t_clu,
             'ladder_gcups': cells / t_clu / 1e9, 'ladder_pairs_verified': int(pairs), 'final_exemplars': int(len(off) - 1), 'rungs': rungs,
-            'search_seconds': t_srch, 'search_genes_per_s': allsum(pg, float(ng)) * (len(qo) - 1) / t_srch, 'search_hits': int(nh), 'gpu_launches': int(launches)}
+            'search_seconds': t_srch, 'search_genes_per_s': float(len(genomes)) * (len(qo) - 1) / t_srch, 'search_hits_rank0': int(nh), 'gpu_launches': int(launches)}
 
 
 def uberblast_leg(ctx, genomes, pool, n=2):
@@ -531,7 +540,7 @@ def main():
     if not args.no_search:
         procs = max(1, min(16, (os.cpu_count() or 1) // world))
         mine = pbd.shard_indices(args.genomes, rank, world) if args.config != 3 else []
-        extra = [args.genomes + rank * args.c3_genomes + i for i in range(args.c3_genomes)] if args.config != 4 else []
+        extra = [args.genomes + i for i in range(args.c3_genomes)] if args.config != 4 else []      # the same genomes on every rank
         made = workloads.synth_genomes_parallel(mine + extra, N_CORE, N_ACC, procs=procs)
         genomes, c3_genomes = made[:len(mine)], made[len(mine):]
     t_syn = time.perf_counter() - t_syn
