@@ -121,7 +121,8 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
     const int nt = mode == 1, F = nt ? (plus_only ? 1 : 2) : (mode == 2 ? 6 : 3), table4 = gtable == 4;
     /* EXPERIMENT (off unless ORC_AA_K is set): protein seed length, for the recall study behind a longer seed */
     const int aak = getenv("ORC_AA_K") ? atoi(getenv("ORC_AA_K")) : 7;
-    const int K = nt ? 12 : aak, BASE = nt ? 4 : 10, XDROP = nt ? 20 : 12, MINU = nt ? 32 : 45, SPAN = nt ? 16 : 12, PAD = nt ? 32 : 24;
+    const int ntk = getenv("ORC_NT_K") ? atoi(getenv("ORC_NT_K")) : 12;      /* EXPERIMENT, as ORC_AA_K */
+    const int K = nt ? ntk : aak, BASE = nt ? 4 : 10, XDROP = nt ? 20 : 12, MINU = nt ? 32 : 45, SPAN = nt ? 16 : 12, PAD = nt ? 32 : 24;
     const int go = nt ? 6 : 11, ge = nt ? 2 : 1, CMAX = nt ? 44 : 56, CSUM = nt ? 56 : 90;
     uint8_t seedmap[32]; memset(seedmap, 255, 32);
     int8_t mat[1024]; memset(mat, 0, 1024);

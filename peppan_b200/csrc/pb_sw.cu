@@ -118,26 +118,28 @@ __global__ void __launch_bounds__(256) dpx_peak_kernel(unsigned* out, unsigned s
 
 size_t sw_smem_bytes(const SwConfig& c, bool packed, int nsym)
 {
-    const int KP = ((c.K + 3) / 4) * 4;
-    const int NG = 32 / c.G;
-    return 1024 + (size_t)c.WARPS * NG * (packed ? 2 : 1) * nsym * c.G * KP;
+    const int KW = (c.K + 3) / 4;       // profile words per lane per symbol; layout [pair][symbol][chunk][lane] per warp
+    return 1024 + (size_t)c.WARPS * (packed ? 2 : 1) * nsym * KW * 32 * 4;
 }
 
-template <int G, int K, int R, bool LONG, int WARPS, bool PACKED, bool REV, bool WAVE>
+template <int G, int K, int R, bool LONG, int WARPS, bool PACKED, bool REV, bool WAVE, bool MULTI>
 cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t st)
 {
-    auto k = sw_kernel<G, K, R, LONG, PACKED, REV, WARPS, WAVE>;
+    auto k = sw_kernel<G, K, R, LONG, PACKED, REV, WARPS, WAVE, MULTI>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
+// multi = false: every pair of the launch fits one column block (device-side maximum), the loop has no border code
 template <bool PACKED, bool REV>
-cudaError_t sw_dispatch(const SwConfig& c, const SwArgs& a, int grid, size_t smem, cudaStream_t st)
+cudaError_t sw_dispatch(const SwConfig& c, const SwArgs& a, int grid, size_t smem, cudaStream_t st, bool multi)
 {
-#define PB_CFG(g, k, r, lg, w) if (c.G == g && c.K == k && c.R == r && c.LONG == lg) return sw_launch_one<g, k, r, (lg != 0), w, PACKED, REV, false>(a, grid, smem, st);
-    PB_CFG(16, 19, 2, 1, 8) PB_CFG(16, 19, 1, 0, 8) PB_CFG(16, 19, 2, 0, 8)
+#define PB_CFG(g, k, r, lg, w) if (c.G == g && c.K == k && c.R == r && c.LONG == lg) \
+        return multi ? sw_launch_one<g, k, r, (lg != 0), w, PACKED, REV, false, true>(a, grid, smem, st) \
+                     : sw_launch_one<g, k, r, (lg != 0), w, PACKED, REV, false, false>(a, grid, smem, st);
+    PB_CFG(16, 19, 2, 1, 8)
 #undef PB_CFG
     return cudaErrorInvalidValue;
 }
@@ -171,7 +173,6 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     a.out_b = rev ? J->ts.as<int>() : J->te.as<int>();
     a.cells = rev ? J->cells.as<unsigned long long>() : nullptr;
     a.progress = nullptr; a.wsub = nullptr; a.wbase = nullptr; a.nsub = 0; a.wkey = nullptr; a.wdone = nullptr;
-    a.dbg = getenv("PB_SW_DBG") ? atoi(getenv("PB_SW_DBG")) : 0;
     PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
 
     const size_t smem16 = sw_smem_bytes(c, true, J->params.nsym), smem32 = sw_smem_bytes(c, false, J->params.nsym);
@@ -264,16 +265,17 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
                 a.wkey = (unsigned long long*)((char*)wp.p + o_key) + 2 * (size_t)c.t0;
                 a.wbase = (const int*)((char*)wp.p + o_base) + c.t0 + ci; a.wsub = (const int2*)((char*)wp.p + o_sub) + c.sub0; a.nsub = (int)c.nsub;
                 const int wgrid = std::max(1, std::min(grid, (int)((c.nsub + WAVE_WARPS - 1) / WAVE_WARPS)));
-                if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, true, true>(a, wgrid, smem, ws)
-                                      : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, false, true>(a, wgrid, smem, ws);
-                else e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, true, true>(a, wgrid, smem, ws)
-                             : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, false, true>(a, wgrid, smem, ws);
+                if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, true, true, true>(a, wgrid, smem, ws)
+                                      : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, false, true, true>(a, wgrid, smem, ws);
+                else e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, true, true, true>(a, wgrid, smem, ws)
+                             : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, false, true, true>(a, wgrid, smem, ws);
                 if (ci + 1 < nch) ++*launches;
             }
         } else {
             a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride; a.progress = nullptr; a.nsub = 0;
-            if (r.packed) e = rev ? sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream) : sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream);
-            else e = rev ? sw_dispatch<false, true>(c, a, grid, smem32, ctx->stream) : sw_dispatch<false, false>(c, a, grid, smem32, ctx->stream);
+            const bool multi = meta[2] > 1;
+            if (r.packed) e = rev ? sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream, multi) : sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream, multi);
+            else e = rev ? sw_dispatch<false, true>(c, a, grid, smem32, ctx->stream, multi) : sw_dispatch<false, false>(c, a, grid, smem32, ctx->stream, multi);
         }
         PB_CUDA(ctx, e);
         ++*launches;

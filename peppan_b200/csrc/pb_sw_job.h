@@ -5,7 +5,7 @@
 
 // Kernel shapes: G lanes per task, K columns per lane, WARPS per (persistent, 1/SM) block.
 struct SwConfig { int G, K, R, LONG, WARPS; };
-static constexpr SwConfig SW_CONFIGS[] = { {16, 19, 2, 1, 8}, {16, 19, 1, 0, 8}, {16, 19, 2, 0, 8} };
+static constexpr SwConfig SW_CONFIGS[] = { {16, 19, 2, 1, 8} };
 
 
 struct pb_sw_job {

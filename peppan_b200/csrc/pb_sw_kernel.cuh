@@ -35,9 +35,23 @@
 //   Fh' = viaddmax(Fh, -ge, H)                      => 5.5 ALU-pipe instructions per packed column.
 //
 // End-cell tracking (bit-exact row-major-first maximum): each lane keeps its best value and the
-// first row where it was reached; whenever a lane's best strictly increases it snapshots its H
-// strip into K spare registers (moves issue on the FMA pipe, which the DP leaves idle).  After
-// the last block the winning lane scans its snapshot for the first column holding the maximum.
+// first row where it was reached; whenever a lane's best strictly increases it snapshots the H strip
+// of that row into K spare registers.  One snapshot array serves both pairs of the packed word: a
+// 16-bit half is replaced under a mask (one LOP3 per column), so two lanes whose different pairs
+// improve in the same step share the same instructions.  After the last block the winning lane
+// scans its snapshot for the first column holding the maximum.
+//
+// Step loop, software-pipelined: the work a step needs from outside the lane -- the profile words
+// of its rows (LDS), the row symbols of the step after (LDG) and the left border cells (SHFL) -- is
+// issued at the end of the step before, ahead of that step's tracking, so that their latencies
+// are covered and the loads sit in the same basic block as the DP and fill its non-ALU issue slots.
+// MULTI = false compiles the loop without any column-block border code (all pairs of the launch
+// fit one block: the common case, decided per launch from the device-side maxima).
+//
+// Profile layout in shared memory: per warp [pair][symbol][chunk][lane] -- the KW words of a lane's
+// columns are split into 16-byte chunks (one LDS.128 each) plus single words, and within a chunk
+// the 32 lanes are contiguous, so whatever symbols the lanes look up (every lane is on a different
+// query row) the accesses of a warp fall into distinct banks.
 //
 // WAVE = true is the long-alignment variant: the unit of work is one column block (G * K = 512 columns with the shape
 // pb_sw.cu instantiates) of one task, taken by a whole warp (G = 32) from a global list in (task, block) order.  The
@@ -87,7 +101,6 @@ struct SwArgs {
     int nsub;
     unsigned long long* wkey;   // WAVE: per (task, pair) packed best cell, combined with atomicMax (zeroed before launch)
     int* wdone;             // WAVE: finished sub-tasks per task (zeroed before launch)
-    int dbg;                // tuning aid (PB_SW_DBG): bit0 skip max tracking, bit1 skip shuffles -- results invalid
 };
 
 __device__ __forceinline__ uint32_t shfl_up_g(uint32_t v, int G) { return __shfl_up_sync(0xffffffffu, v, 1, G); }
@@ -120,6 +133,8 @@ template <> struct Ops<true> {
     }
     static __device__ __forceinline__ int hi(uint32_t v) { return (int)(short)(v >> 16); }
     static __device__ __forceinline__ int lo(uint32_t v) { return (int)(short)(v & 0xffffu); }
+    // d = a - b per half with a >= b: 0xffff in every half where a > b (two ALU instructions and one multiply, no predicates)
+    static __device__ __forceinline__ uint32_t gtmask(uint32_t a, uint32_t b) { return __vmins2(__vsub2(a, b), 0x00010001u) * 0xffffu; }
 };
 
 template <> struct Ops<false> {
@@ -133,20 +148,25 @@ template <> struct Ops<false> {
     }
     static __device__ __forceinline__ int hi(uint32_t v) { return (int)v; }
     static __device__ __forceinline__ int lo(uint32_t) { return 0; }
+    static __device__ __forceinline__ uint32_t gtmask(uint32_t a, uint32_t b) { return (uint32_t)min((int)(a - b), 1) * 0xffffffffu; }
 };
 
-template <int G, int K, int R, bool LONG, bool PACKED, bool REV, int WARPS, bool WAVE>
+template <int G, int K, int R, bool LONG, bool PACKED, bool REV, int WARPS, bool WAVE, bool MULTI>
 __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
 {
     using O = Ops<PACKED>;
     constexpr int KW = (K + 3) / 4;     // profile words per lane per row
-    constexpr int KP = KW * 4;
+    constexpr int KQ = KW / 4;          // ... of which whole 16-byte chunks
+    constexpr int KR = KW % 4;          // ... and single words
     constexpr int NG = 32 / G;
     constexpr int NPAIR = PACKED ? 2 : 1;
     constexpr int W = G * K;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int BIGROW = 0x3fffffff;
     static_assert(!WAVE || G == 32, "the wavefront variant uses whole warps");
+    static_assert(!WAVE || MULTI, "the wavefront variant is a multi-block kernel");
+    constexpr uint32_t HI = PACKED ? 0xffff0000u : 0xffffffffu;
+    constexpr uint32_t LO = PACKED ? 0x0000ffffu : 0u;
 
     extern __shared__ __align__(16) uint8_t smem[];
     int8_t* smat = reinterpret_cast<int8_t*>(smem);
@@ -157,11 +177,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / G, l = lane % G;
     const int nsym = a.nsym, PAD = a.nsym - 1;
-    const int rowBytes = G * KP;
-    const int pairBytes = nsym * rowBytes;
-    uint8_t* prof = smem + 1024 + (size_t)((warp * NG + g) * NPAIR) * pairBytes;
+    const int pairWords = nsym * KW * 32;
+    uint32_t* prof = reinterpret_cast<uint32_t*>(smem + 1024) + (size_t)(warp * NPAIR) * pairWords;
     const int gwarp = blockIdx.x * WARPS + warp;
-    uint2* mybound = (a.boundary && !WAVE) ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
+    uint2* mybound = (MULTI && a.boundary && !WAVE) ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
     uint2* wavebound = nullptr;
     int* waveprog = nullptr;
 
@@ -169,6 +188,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     const uint32_t GOE = O::bcast(a.go + a.ge);
     const uint32_t NEG_GOE = O::bcast(-(a.go + a.ge));
     const int ntasks = (a.count + NPAIR - 1) / NPAIR;
+    const uint32_t nz = (l != 0) ? 1u : 0u;     // lane 0 of a group has no left neighbour: its shuffled border is multiplied away (FMA pipe)
 
     for (;;) {
         int bundle = 0, wblock = 0;
@@ -206,12 +226,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             mw = max(mw, __shfl_xor_sync(FULL, mw, o));
             nw = max(nw, __shfl_xor_sync(FULL, nw, o));
         }
-        const int nblocks = (nw + W - 1) / W;
+        const int nblocks = MULTI ? (nw + W - 1) / W : 1;
 
         uint32_t best = 0;
-        uint32_t snapA[K], snapB[K];
+        uint32_t snap[K];
 #pragma unroll
-        for (int p = 0; p < K; ++p) { snapA[p] = 0; snapB[p] = 0; }
+        for (int p = 0; p < K; ++p) snap[p] = 0;
         int browA = BIGROW, browB = BIGROW, blkA = 0, blkB = 0;
         int rowcap = mw;                       // REV: rows later blocks still have to visit
         int bvalid = mw;                       // rows of the block border written by the previous block
@@ -230,21 +250,30 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 }
                 for (int c = 0; c < nsym; ++c) {
                     const int8_t* mrow = smat + c * 32;
-                    uint32_t* dstA = reinterpret_cast<uint32_t*>(prof + c * rowBytes + l * KP);
-                    uint32_t* dstB = reinterpret_cast<uint32_t*>(prof + pairBytes + c * rowBytes + l * KP);
+                    uint32_t va[KW], vb[KW];
 #pragma unroll
                     for (int w = 0; w < KW; ++w) {
-                        uint32_t va = 0, vb = 0;
+                        va[w] = 0; vb[w] = 0;
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
                             int p = w * 4 + x;
                             if (p < K) {
-                                va |= ((uint32_t)(uint8_t)mrow[tcA[p]]) << (8 * x);
-                                if (PACKED) vb |= ((uint32_t)(uint8_t)mrow[tcB[p]]) << (8 * x);
+                                va[w] |= ((uint32_t)(uint8_t)mrow[tcA[p]]) << (8 * x);
+                                if (PACKED) vb[w] |= ((uint32_t)(uint8_t)mrow[tcB[p]]) << (8 * x);
                             }
                         }
-                        dstA[w] = va;
-                        if (PACKED) dstB[w] = vb;
+                    }
+                    uint32_t* dstA = prof + c * (KW * 32);
+                    uint32_t* dstB = dstA + pairWords;
+#pragma unroll
+                    for (int qd = 0; qd < KQ; ++qd) {
+                        reinterpret_cast<uint4*>(dstA + qd * 128)[lane] = make_uint4(va[4 * qd], va[4 * qd + 1], va[4 * qd + 2], va[4 * qd + 3]);
+                        if (PACKED) reinterpret_cast<uint4*>(dstB + qd * 128)[lane] = make_uint4(vb[4 * qd], vb[4 * qd + 1], vb[4 * qd + 2], vb[4 * qd + 3]);
+                    }
+#pragma unroll
+                    for (int x = 0; x < KR; ++x) {
+                        dstA[KQ * 128 + x * 32 + lane] = va[4 * KQ + x];
+                        if (PACKED) dstB[KQ * 128 + x * 32 + lane] = vb[4 * KQ + x];
                     }
                 }
             }
@@ -253,9 +282,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             uint32_t H[K], E[K];
 #pragma unroll
             for (int p = 0; p < K; ++p) { H[p] = 0; E[p] = 0; }
-            uint32_t hlast[R], fout[R];
+            uint32_t hl[R], fh[R];              // left border cells of the coming step (shuffled in at the end of the step before)
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) { hlast[rr] = 0; fout[rr] = 0; }
+            for (int rr = 0; rr < R; ++rr) { hl[rr] = 0; fh[rr] = 0; }
             uint32_t hl_prev = 0;
             const int rows_here = min(mw, rowcap);
             int slimit = (rows_here + R - 1) / R + G - 1;
@@ -266,50 +295,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             if (WAVE) { mybound = wavebound + (size_t)b * a.bstride; }
             const uint2* leftbound = WAVE ? (b > 0 ? wavebound + (size_t)(b - 1) * a.bstride : nullptr) : mybound;
 
-            // prefetch the row symbols of step 0
-            int cA[R], cB[R];
+            // row symbols of a step: PAD outside the pair's rows (also for lanes that have not started yet)
+            auto fetch_symbols = [&](int first_row, int (&sa)[R], int (&sb)[R]) {
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                const int i0 = -l * R + rr;
-                cA[rr] = ((unsigned)i0 < (unsigned)mA) ? (int)__ldg(qA + (REV ? mA - 1 - i0 : i0)) : PAD;
-                cB[rr] = PAD;
-                if (PACKED) cB[rr] = ((unsigned)i0 < (unsigned)mB) ? (int)__ldg(qB + (REV ? mB - 1 - i0 : i0)) : PAD;
-            }
+                for (int rr = 0; rr < R; ++rr) {
+                    const int in = first_row + rr;
+                    sa[rr] = ((unsigned)in < (unsigned)mA) ? (int)__ldg(qA + (REV ? mA - 1 - in : in)) : PAD;
+                    sb[rr] = PAD;
+                    if (PACKED) sb[rr] = ((unsigned)in < (unsigned)mB) ? (int)__ldg(qB + (REV ? mB - 1 - in : in)) : PAD;
+                }
+            };
+            // profile words of the rows whose symbols are sa / sb
+            auto fetch_profile = [&](const int (&sa)[R], const int (&sb)[R], uint32_t (&xa)[R][KW], uint32_t (&xb)[R][KW]) {
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const uint32_t* rA = prof + sa[rr] * (KW * 32);
+#pragma unroll
+                    for (int qd = 0; qd < KQ; ++qd) {
+                        const uint4 v = reinterpret_cast<const uint4*>(rA + qd * 128)[lane];
+                        xa[rr][4 * qd] = v.x; xa[rr][4 * qd + 1] = v.y; xa[rr][4 * qd + 2] = v.z; xa[rr][4 * qd + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int x = 0; x < KR; ++x) xa[rr][4 * KQ + x] = rA[KQ * 128 + x * 32 + lane];
+                    if (PACKED) {
+                        const uint32_t* rB = prof + pairWords + sb[rr] * (KW * 32);
+#pragma unroll
+                        for (int qd = 0; qd < KQ; ++qd) {
+                            const uint4 v = reinterpret_cast<const uint4*>(rB + qd * 128)[lane];
+                            xb[rr][4 * qd] = v.x; xb[rr][4 * qd + 1] = v.y; xb[rr][4 * qd + 2] = v.z; xb[rr][4 * qd + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int x = 0; x < KR; ++x) xb[rr][4 * KQ + x] = rB[KQ * 128 + x * 32 + lane];
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < KW; ++w) xb[rr][w] = 0;
+                    }
+                }
+            };
+
+            // pipeline prologue: profile words of step 0, symbols of step 1
+            int cA[R], cB[R];
+            uint32_t wA[R][KW], wB[R][KW];
+            fetch_symbols(-l * R, cA, cB);
+            fetch_profile(cA, cB, wA, wB);
+            fetch_symbols(-l * R + R, cA, cB);
 
 #pragma unroll 2
             for (int s = 0; s < slimit; ++s) {
                 const int r0 = (s - l) * R;
-                // profile rows of this step
-                uint32_t wA[R][KW], wB[R][KW];
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) {
-                    const uint32_t* rA = reinterpret_cast<const uint32_t*>(prof + cA[rr] * rowBytes + l * KP);
-#pragma unroll
-                    for (int w = 0; w < KW; ++w) wA[rr][w] = rA[w];
-                    if (PACKED) {
-                        const uint32_t* rB = reinterpret_cast<const uint32_t*>(prof + pairBytes + cB[rr] * rowBytes + l * KP);
-#pragma unroll
-                        for (int w = 0; w < KW; ++w) wB[rr][w] = rB[w];
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < KW; ++w) wB[rr][w] = 0;
-                    }
-                }
-                // prefetch next step's symbols
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) {
-                    const int in = r0 + R + rr;
-                    cA[rr] = ((unsigned)in < (unsigned)mA) ? (int)__ldg(qA + (REV ? mA - 1 - in : in)) : PAD;
-                    if (PACKED) cB[rr] = ((unsigned)in < (unsigned)mB) ? (int)__ldg(qB + (REV ? mB - 1 - in : in)) : PAD;
-                }
-                // left border: from lane l-1 (previous step) or, for lane 0, the block border
-                uint32_t hl[R], fh[R];
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) {
-                    if (a.dbg & 2) { hl[rr] = hlast[rr]; fh[rr] = fout[rr]; }
-                    else { hl[rr] = shfl_up_g(hlast[rr], G); fh[rr] = shfl_up_g(fout[rr], G); }
-                    if (l == 0) { hl[rr] = 0; fh[rr] = 0; }
-                }
+                // lane 0: the block border replaces the (zero) shuffled border
                 if (WAVE) {
                     if (b > 0) {
                         // border cells of block b-1 come in batches of 32 rows: one coalesced load by the whole warp,
@@ -334,7 +368,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                             }
                         }
                     }
-                } else if (b > 0) {
+                } else if (MULTI && b > 0) {
                     if (l == 0) {
 #pragma unroll
                         for (int rr = 0; rr < R; ++rr)
@@ -387,13 +421,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                     H[p] = up;
                     E[p] = eprev;
                 }
+                // ---- the coming step: profile words, the symbols of the step after, left border by shuffle ----
+                fetch_profile(cA, cB, wA, wB);
+                fetch_symbols(r0 + 2 * R, cA, cB);
+                uint32_t hlast[R], fout[R];
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
-                    hlast[rr] = (rr < R - 1) ? Hrow[rr][K - 1] : H[K - 1];
+                    hlast[rr] = (rr < R - 1) ? Hrow[rr < R - 1 ? rr : 0][K - 1] : H[K - 1];
                     fout[rr] = fh[rr];
+                    hl[rr] = shfl_up_g(hlast[rr], G) * nz;
+                    fh[rr] = shfl_up_g(fout[rr], G) * nz;
                 }
-                if (nblocks > 1) {
-                    if (l == G - 1 && b + 1 < nblocks) {
+                if (MULTI) {
+                    if (nblocks > 1 && l == G - 1 && b + 1 < nblocks) {
 #pragma unroll
                         for (int rr = 0; rr < R; ++rr)
                             if ((unsigned)(r0 + rr) < (unsigned)mw) mybound[r0 + rr] = make_uint2(hlast[rr], fout[rr]);
@@ -401,48 +441,43 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                     }
                 }
 
-                // ---- maximum tracking: one decision per step; among the R rows the first one that
-                // reaches the step's final value wins (row-major-first), and only that row's strip is
-                // snapshotted ----
-                if (a.dbg & 1) { best = O::max2(best, stepmax[0]); if (R > 1) best = O::max2(best, stepmax[R - 1]); }
-                else {
+                // ---- maximum tracking: one decision per step; among the R rows the first one that reaches the
+                // step's final value wins (row-major-first), and only that row's strip is snapshotted ----
+                {
                     uint32_t fin = best;
 #pragma unroll
                     for (int rr = 0; rr < R; ++rr) fin = O::max2(fin, stepmax[rr]);
-                    uint32_t ch = fin ^ best;
-                    if (!WAVE && b > 0) {   // a later block of this lane may hold an equal maximum on an earlier row
+                    uint32_t need = O::gtmask(fin, best);       // halves (pairs) of this lane whose best strictly increased
+                    if (MULTI && !WAVE && b > 0) {   // a later block of this lane may hold an equal maximum on an earlier row
 #pragma unroll
                         for (int rr = R - 1; rr >= 0; --rr) {
-                            if (O::hi(stepmax[rr]) == O::hi(best) && r0 + rr < browA && O::hi(best) > 0) ch |= PACKED ? 0xffff0000u : 1u;
-                            if (PACKED && O::lo(stepmax[rr]) == O::lo(best) && r0 + rr < browB && O::lo(best) > 0) ch |= 0x0000ffffu;
+                            if (O::hi(stepmax[rr]) == O::hi(best) && r0 + rr < browA && O::hi(best) > 0) need |= HI;
+                            if (PACKED && O::lo(stepmax[rr]) == O::lo(best) && r0 + rr < browB && O::lo(best) > 0) need |= LO;
                         }
                     }
                     best = fin;
-                    if (ch) {
-                        constexpr uint32_t HI = PACKED ? 0xffff0000u : 0xffffffffu;
-                        if (ch & HI) {
-                            int src = R - 1;
-#pragma unroll
-                            for (int rr = R - 2; rr >= 0; --rr) if (((stepmax[rr] ^ fin) & HI) == 0) src = rr;
-                            browA = r0 + src; blkA = b;
-#pragma unroll
-                            for (int rr = 0; rr < R; ++rr)
-                                if (src == rr) {
-#pragma unroll
-                                    for (int p = 0; p < K; ++p) snapA[p] = (rr < R - 1) ? Hrow[rr][p] : H[p];
-                                }
+                    if (need) {
+                        if (MULTI) {
+                            if (need & HI) blkA = b;
+                            if (PACKED && (need & LO)) blkB = b;
                         }
-                        if (PACKED && (ch & 0x0000ffffu)) {
-                            int src = R - 1;
 #pragma unroll
-                            for (int rr = R - 2; rr >= 0; --rr) if (((stepmax[rr] ^ fin) & 0x0000ffffu) == 0) src = rr;
-                            browB = r0 + src; blkB = b;
+                        for (int rr = 0; rr < R; ++rr) {
+                            uint32_t take = need;                       // the last row takes what is left
+                            if (rr < R - 1) take = need & ~O::gtmask(fin, stepmax[rr]);   // halves where this row already holds the final value
+                            need &= ~take;
+                            if (take & HI) browA = r0 + rr;
+                            if (PACKED && (take & LO)) browB = r0 + rr;
+#ifndef PB_TRACK_FLAT
+                            if (take)
+#endif
+                            {
 #pragma unroll
-                            for (int rr = 0; rr < R; ++rr)
-                                if (src == rr) {
-#pragma unroll
-                                    for (int p = 0; p < K; ++p) snapB[p] = (rr < R - 1) ? Hrow[rr][p] : H[p];
+                                for (int p = 0; p < K; ++p) {
+                                    const uint32_t v = (rr < R - 1) ? Hrow[rr < R - 1 ? rr : 0][p] : H[p];
+                                    snap[p] = (v & take) | (snap[p] & ~take);
                                 }
+                            }
                         }
                     }
                 }
@@ -481,8 +516,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 int pcol = K;
 #pragma unroll
                 for (int p = K - 1; p >= 0; --p) {
-                    uint32_t v = (h == 0) ? snapA[p] : snapB[p];
-                    int hv = (h == 0) ? O::hi(v) : O::lo(v);
+                    const int hv = (h == 0) ? O::hi(snap[p]) : O::lo(snap[p]);
                     if (hv == S) pcol = p;
                 }
                 key = ((unsigned long long)(unsigned)brow << 32) | (unsigned)(blk * W + l * K + pcol);
