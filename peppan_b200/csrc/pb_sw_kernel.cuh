@@ -36,10 +36,10 @@
 //
 // End-cell tracking (bit-exact row-major-first maximum): each lane keeps its best value and the
 // first row where it was reached; whenever a lane's best strictly increases it snapshots the H strip
-// of that row into K spare registers.  One snapshot array serves both pairs of the packed word: a
-// 16-bit half is replaced under a mask (one LOP3 per column), so two lanes whose different pairs
-// improve in the same step share the same instructions.  After the last block the winning lane
-// scans its snapshot for the first column holding the maximum.
+// of that row into K spare registers per pair (whole-register moves under a branch: they issue on
+// the FMA pipe, the DP saturates the ALU pipe).  The reverse pass knows the score it is looking for
+// and snapshots only when a pair reaches it.  After the last block the winning lane scans its
+// snapshot for the first column holding the maximum.
 //
 // Step loop, software-pipelined: the work a step needs from outside the lane -- the profile words
 // of its rows (LDS), the row symbols of the step after (LDG) and the left border cells (SHFL) -- is
@@ -229,9 +229,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
         const int nblocks = MULTI ? (nw + W - 1) / W : 1;
 
         uint32_t best = 0;
-        uint32_t snap[K];
+        uint32_t snapA[K], snapB[PACKED ? K : 1];
 #pragma unroll
-        for (int p = 0; p < K; ++p) snap[p] = 0;
+        for (int p = 0; p < K; ++p) { snapA[p] = 0; if (PACKED) snapB[p] = 0; }
         int browA = BIGROW, browB = BIGROW, blkA = 0, blkB = 0;
         int rowcap = mw;                       // REV: rows later blocks still have to visit
         int bvalid = mw;                       // rows of the block border written by the previous block
@@ -455,6 +455,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                             if (PACKED && O::lo(stepmax[rr]) == O::lo(best) && r0 + rr < browB && O::lo(best) > 0) need |= LO;
                         }
                     }
+                    if (REV) {
+                        // the only snapshot that can matter is the one taken when a pair reaches the forward score
+                        const uint32_t tg = PACKED ? ((uint32_t)tgtA << 16) | ((uint32_t)tgtB & 0xffffu) : (uint32_t)tgtA;
+                        need &= ~O::gtmask(O::max2(tg, fin), fin);
+                    }
                     best = fin;
                     if (need) {
                         if (MULTI) {
@@ -466,17 +471,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                             uint32_t take = need;                       // the last row takes what is left
                             if (rr < R - 1) take = need & ~O::gtmask(fin, stepmax[rr]);   // halves where this row already holds the final value
                             need &= ~take;
-                            if (take & HI) browA = r0 + rr;
-                            if (PACKED && (take & LO)) browB = r0 + rr;
-#ifndef PB_TRACK_FLAT
-                            if (take)
-#endif
-                            {
+                            // whole-register copies under a branch (FMA-pipe moves; the ALU pipe is the one the DP saturates)
+                            if (take & HI) {
+                                browA = r0 + rr;
 #pragma unroll
-                                for (int p = 0; p < K; ++p) {
-                                    const uint32_t v = (rr < R - 1) ? Hrow[rr < R - 1 ? rr : 0][p] : H[p];
-                                    snap[p] = (v & take) | (snap[p] & ~take);
-                                }
+                                for (int p = 0; p < K; ++p) snapA[p] = (rr < R - 1) ? Hrow[rr < R - 1 ? rr : 0][p] : H[p];
+                            }
+                            if (PACKED && (take & LO)) {
+                                browB = r0 + rr;
+#pragma unroll
+                                for (int p = 0; p < K; ++p) snapB[PACKED ? p : 0] = (rr < R - 1) ? Hrow[rr < R - 1 ? rr : 0][p] : H[p];
                             }
                         }
                     }
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 int pcol = K;
 #pragma unroll
                 for (int p = K - 1; p >= 0; --p) {
-                    const int hv = (h == 0) ? O::hi(snap[p]) : O::lo(snap[p]);
+                    const int hv = (h == 0) ? O::hi(snapA[p]) : O::lo(snapB[PACKED ? p : 0]);
                     if (hv == S) pcol = p;
                 }
                 key = ((unsigned long long)(unsigned)brow << 32) | (unsigned)(blk * W + l * K + pcol);
@@ -531,7 +535,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                 // combine the blocks of the task: larger score wins, then the row-major-first cell; the warp that
                 // finishes last decodes the result
                 if (lane == 0) {
-                    if (S > 0 && key != ~0ull) {
+                    // REV: blocks that did not reach the forward score hold no snapshot (the tracking is gated on it)
+                    if (S > 0 && key != ~0ull && (!REV || S == ((h == 0) ? tgtA : tgtB))) {
                         const unsigned long long row = key >> 32, col = key & 0xffffffffull;
                         atomicMax(a.wkey + (size_t)task * 2 + h, ((unsigned long long)S << 40) | ((0xfffffull - row) << 20) | (0xfffffull - col));
                     }
