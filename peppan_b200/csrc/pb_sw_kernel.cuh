@@ -340,8 +340,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
             fetch_profile(cA, cB, wA, wB);
             fetch_symbols(-l * R + R, cA, cB);
 
-#pragma unroll 2
-            for (int s = 0; s < slimit; ++s) {
+            auto step = [&](const int s) {
                 const int r0 = (s - l) * R;
                 // lane 0: the block border replaces the (zero) shuffled border
                 if (WAVE) {
@@ -497,7 +496,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
                     }
                     if (alldone && !armed) { armed = true; slimit = min(slimit, s + G); }
                 }
-            }
+            };
+#pragma unroll 2
+            for (int s = 0; s < slimit; ++s) step(s);
             if (REV) {
                 swept += (unsigned long long)min((slimit - (G - 1)) * R, mw) * (unsigned long long)min(nw - b * W, W);
                 if (armed) rowcap = min(rowcap, (slimit - (G - 1)) * R);
