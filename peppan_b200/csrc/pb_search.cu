@@ -216,50 +216,67 @@ __global__ void build_ends_kernel(const uint32_t* keys, int64_t nvalid, const ui
 }
 
 // ---- K1b: seed scan + ungapped X-drop ---------------------------------------------------------------
-// Each block stages a tile of the target codes in shared memory with 128-bit loads; every thread owns SCAN_PER_THREAD
-// consecutive positions, rolls the k-mer key across them and looks the table up (phase 1).  The (position, slot range)
-// pairs are then expanded densely over the block with a prefix sum (phase 2): every lane takes one seed, so lanes stay
-// busy however unevenly the seeds are spread over the positions.  A seed is extended by its lane for at most
-// lane_budget residues per side, which settles the random seeds; seeds that are still alive go to a queue that
-// xdrop_warp_kernel extends with one warp per seed, 32 residues per step (prefix sums and prefix maxima by shuffles).
+// Each block stages a tile of the target codes in shared memory with 128-bit loads (with a halo on both sides, so
+// that every residue an extension can touch comes from the tile); every thread owns SCAN_PER_THREAD consecutive
+// positions, rolls the k-mer key across them and looks the table up (phase 1).  The seeds of the tile -- (position, slot)
+// for every entry of every position's slot range -- are then worked off in batches of SCAN_QCAP through two queues in
+// shared memory:
+//   phase 2a (dense, one seed per lane): query position of the slot, leftmost-seed-of-a-run rule, score of the seed;
+//            survivors are compacted into the extension queue;
+//   phase 2b (lane state machine): a lane extends its seed one residue per iteration -- right, then left from the
+//            right-extended best, X-drop on both sides, at most lane_budget residues per side -- and takes the next seed
+//            from the queue as soon as it is done, so short (random) and long (homologous) seeds do not wait for each
+//            other.  Query residues are read in aligned 32-bit words, target residues and scores from shared memory.
+// Seeds still alive after lane_budget residues on a side go to a queue that xdrop_warp_kernel extends with one warp per
+// seed, 32 residues per step (prefix sums and prefix maxima by shuffles).  The arithmetic per seed is that of the scalar
+// loop of oracle/pb_search_oracle.c; sentinels (separators, array ends; score -100) end an extension through the X-drop.
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+constexpr int SCAN_HALO = 64;                 // >= k + lane_budget on both sides
+constexpr int SCAN_QCAP = 2048;               // seeds per batch
+constexpr int SCAN_CH = 16;                   // residues per extension chunk; lane_budget is a multiple of it
 
 struct SeedQ { uint32_t qpos, tpos; };
 
-__global__ void __launch_bounds__(SCAN_THREADS) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
+__global__ void __launch_bounds__(SCAN_THREADS, 3) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
                                                                  const uint8_t* __restrict__ qcodes, int64_t qn,
                                                                  const uint32_t* __restrict__ table, const uint32_t* __restrict__ ends,
                                                                  const uint32_t* __restrict__ vals, DevSpec sp,
                                                                  Cand* cand, unsigned long long* ncand, unsigned long long cap,
                                                                  unsigned long long* nseed, SeedQ* longq, unsigned long long* nlong)
 {
-    __shared__ __align__(16) uint8_t tile[SCAN_TILE + 64];
+    __shared__ __align__(16) uint8_t tile[SCAN_HALO + SCAN_TILE + SCAN_HALO + 16];   // tile[SCAN_HALO + i] = tcodes[t0 + i]
     __shared__ int8_t sscore[1024];
-    __shared__ uint32_t s_start[SCAN_TILE];
-    __shared__ uint32_t s_off[SCAN_TILE];
+    __shared__ uint2 q1[SCAN_QCAP];            // (tile position, slot in vals)
+    __shared__ uint2 q2[SCAN_QCAP];            // (query position, tile position | seed score << 16)
     typedef cub::BlockScan<uint32_t, SCAN_THREADS> BlockScan;
     __shared__ typename BlockScan::TempStorage scan_tmp;
-    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_total, s_n2, s_head;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t*>(sscore)[i] = reinterpret_cast<const uint32_t*>(sp.score)[i];
     uint32_t pw = 1;
     for (int i = 1; i < sp.k; ++i) pw *= sp.base;          // base^(k-1)
+    const int K = sp.k, T1 = sp.lane_budget, XD = sp.xdrop;
+    const bool exact_seed = sp.base == 4;                  // nucleotide seeds are exact matches: their score is k * match
+    const int seed_const = K * (int)sp.score[0];
     unsigned long long myseeds = 0;
     for (int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE; t0 < tn; t0 += (int64_t)gridDim.x * SCAN_TILE) {
         __syncthreads();
-        // stage tile [t0, t0 + SCAN_TILE + k) (t0 is a multiple of 16: 128-bit loads)
-        const int nload = SCAN_TILE + 64;
-        for (int i = threadIdx.x * 16; i < nload; i += blockDim.x * 16) {
+        // stage [t0 - HALO, t0 + TILE + HALO) (t0 and HALO are multiples of 16: 128-bit loads); sentinel outside the array
+        for (int i = threadIdx.x * 16; i < SCAN_TILE + 2 * SCAN_HALO; i += blockDim.x * 16) {
+            const int64_t g = t0 - SCAN_HALO + i;
             uint4 v = make_uint4(0x1f1f1f1fu, 0x1f1f1f1fu, 0x1f1f1f1fu, 0x1f1f1f1fu);
-            if (t0 + i + 16 <= tn) v = *reinterpret_cast<const uint4*>(tcodes + t0 + i);
-            else for (int x = 0; x < 16; ++x) if (t0 + i + x < tn) reinterpret_cast<uint8_t*>(&v)[x] = tcodes[t0 + i + x];
+            if (g >= 0 && g + 16 <= tn) v = *reinterpret_cast<const uint4*>(tcodes + g);
+            else for (int xx = 0; xx < 16; ++xx) if (g + xx >= 0 && g + xx < tn) reinterpret_cast<uint8_t*>(&v)[xx] = tcodes[g + xx];
             *reinterpret_cast<uint4*>(tile + i) = v;
         }
         __syncthreads();
+        const uint8_t* tl = tile + SCAN_HALO;
         // ---- phase 1: keys and slot ranges of this thread's positions ----
         const int base_i = threadIdx.x * SCAN_PER_THREAD;
         uint32_t key = 0; int bad = 0;
-        for (int i = 0; i < sp.k - 1; ++i) {
-            uint8_t c = tile[base_i + i];
+        for (int i = 0; i < K - 1; ++i) {
+            uint8_t c = tl[base_i + i];
             uint8_t sc = c < 32 ? sp.seedmap[c] : 255;
             if (sc == 255) { bad = i + 1; sc = 0; }
             key = key * sp.base + sc;
@@ -269,78 +286,137 @@ __global__ void __launch_bounds__(SCAN_THREADS) seed_scan_kernel(const uint8_t* 
 #pragma unroll
         for (int j = 0; j < SCAN_PER_THREAD; ++j) {
             const int pos = base_i + j;
-            uint8_t c = tile[pos + sp.k - 1];
+            uint8_t c = tl[pos + K - 1];
             uint8_t sc = c < 32 ? sp.seedmap[c] : 255;
-            if (sc == 255) { last_bad = j + sp.k - 1; sc = 0; }
+            if (sc == 255) { last_bad = j + K - 1; sc = 0; }
             key = key * sp.base + sc;            // key now covers [pos, pos+k)
             cnt[j] = 0; st[j] = 0;
-            if (last_bad < j && t0 + pos + sp.k <= tn) {
+            if (last_bad < j && t0 + pos + K <= tn) {
                 const uint32_t slot = __ldg(table + key);
                 if (slot != NOKEY) { st[j] = slot; cnt[j] = __ldg(ends + slot) - slot; }
             }
-            uint8_t c0 = tile[pos];
+            uint8_t c0 = tl[pos];
             uint8_t s0 = c0 < 32 ? sp.seedmap[c0] : 255;
             if (s0 == 255) s0 = 0;
             key -= s0 * pw;
         }
         uint32_t off[SCAN_PER_THREAD], total;
         BlockScan(scan_tmp).ExclusiveSum(cnt, off, total);
-#pragma unroll
-        for (int j = 0; j < SCAN_PER_THREAD; ++j) { s_start[base_i + j] = st[j]; s_off[base_i + j] = off[j]; }
         if (threadIdx.x == 0) s_total = total;
         __syncthreads();
         const uint32_t H = s_total;
         if (threadIdx.x == 0) myseeds += H;
-        // ---- phase 2: one seed per lane ----
-        for (uint32_t h = threadIdx.x; h < H; h += SCAN_THREADS) {
-            int lo = 0, hi = SCAN_TILE;              // last position whose exclusive offset is <= h
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= h) lo = mid + 1; else hi = mid; }
-            const int pos = lo - 1;
-            const uint32_t o = s_start[pos] + (h - s_off[pos]);
-            const int64_t qpos = __ldg(vals + o);
-            const int64_t tpos = t0 + pos;
-            // leftmost seed of a match run only: if the preceding residues agree in the seed alphabet the
-            // preceding k-mer is a seed on the same diagonal and extends to the same HSP
-            if (qpos > 0 && tpos > 0) {
-                uint8_t a = qcodes[qpos - 1], b = tcodes[tpos - 1];
-                uint8_t sa = a < 32 ? sp.seedmap[a] : 255, sb = b < 32 ? sp.seedmap[b] : 255;
-                if (sa != 255 && sa == sb) continue;
+
+        for (uint32_t lo = 0; lo < H; lo += SCAN_QCAP) {
+            const uint32_t hi = min(H, lo + (uint32_t)SCAN_QCAP);
+            const bool last_batch = hi == H;
+            // ---- the seeds [lo, hi) of the tile -> q1 ----
+#pragma unroll
+            for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+                const uint32_t a0 = max(off[j], lo), b0 = min(off[j] + cnt[j], hi);
+                for (uint32_t i = a0; i < b0; ++i) q1[i - lo] = make_uint2((uint32_t)(base_i + j), st[j] + (i - off[j]));
             }
-            int score = 0;
-            for (int i = 0; i < sp.k; ++i) score += sscore[qcodes[qpos + i] * 32 + tile[pos + i]];
-            int best = score, cur = score, rlen = sp.k;
-            bool open = true;                        // extension still running when the lane's budget ended
-            const int T1 = sp.lane_budget;
-            for (int x = sp.k; x < sp.k + T1; ++x) {
-                if (qpos + x >= qn || tpos + x >= tn) { open = false; break; }
-                uint8_t a = qcodes[qpos + x], b = tcodes[tpos + x];
-                if (a == SENT || b == SENT) { open = false; break; }
-                cur += sscore[a * 32 + b];
-                if (cur > best) { best = cur; rlen = x + 1; }
-                else if (best - cur > sp.xdrop) { open = false; break; }
+            if (threadIdx.x == 0) { s_n2 = 0; s_head = 0; }
+            __syncthreads();
+            // ---- phase 2a: one seed per lane: query position, leftmost-seed rule, seed score ----
+            const uint32_t n1 = hi - lo;
+            for (uint32_t e0 = 0; e0 < n1; e0 += SCAN_THREADS) {
+                const uint32_t e = e0 + threadIdx.x;
+                bool keep = false;
+                uint32_t qpos = 0; int pos = 0, score = 0;
+                if (e < n1) {
+                    const uint2 en = q1[e];
+                    pos = (int)en.x;
+                    qpos = __ldg(vals + en.y);
+                    // leftmost seed of a match run only: if the preceding residues agree in the seed alphabet the preceding
+                    // k-mer is a seed on the same diagonal and extends to the same HSP (position 0 of both arrays is a sentinel)
+                    const uint8_t pa = __ldg(qcodes + qpos - 1), pb = tl[pos - 1];
+                    const uint8_t sa = pa < 32 ? sp.seedmap[pa] : 255, sb = pb < 32 ? sp.seedmap[pb] : 255;
+                    keep = !(sa != 255 && sa == sb);
+                    if (keep) {
+                        if (exact_seed) score = seed_const;
+                        else for (int i = 0; i < K; ++i) score += sscore[__ldg(qcodes + qpos + i) * 32 + tl[pos + i]];
+                    }
+                }
+                const unsigned km = __ballot_sync(FULL, keep);
+                uint32_t wbase = 0;
+                if (lane == 0 && km) wbase = atomicAdd(&s_n2, (uint32_t)__popc(km));
+                wbase = __shfl_sync(FULL, wbase, 0);
+                if (keep) q2[wbase + __popc(km & ((1u << lane) - 1u))] = make_uint2(qpos, (uint32_t)pos | ((uint32_t)score << 16));
             }
-            int lbest = best, llen = 0;
-            if (!open) {
-                cur = best; open = true;
-                for (int x = 1; x <= T1; ++x) {
-                    if (qpos - x < 0 || tpos - x < 0) { open = false; break; }
-                    uint8_t a = qcodes[qpos - x], b = tcodes[tpos - x];
-                    if (a == SENT || b == SENT) { open = false; break; }
-                    cur += sscore[a * 32 + b];
-                    if (cur > lbest) { lbest = cur; llen = x; }
-                    else if (lbest - cur > sp.xdrop) { open = false; break; }
+            __syncthreads();
+            // ---- phase 2b: extension, one seed per lane, SCAN_CH residues per chunk, branch-free inside a chunk ----
+            const uint32_t n2 = s_n2;
+            for (uint32_t e0 = 0; e0 < n2; e0 += SCAN_THREADS) {
+                const uint32_t e = e0 + threadIdx.x;
+                const bool have = e < n2;
+                uint32_t qpos = 1; int pos = 0, best = 0;
+                if (have) { const uint2 en = q2[e]; qpos = en.x; pos = (int)(en.y & 0xffffu); best = (int)(short)(en.y >> 16); }
+                int cur = best, blen = K;
+                bool dropped = !have;
+                // right: residues qpos + K + i against tile position pos + K + i
+                for (int c0 = 0; c0 < T1; c0 += SCAN_CH) {
+                    if (!__any_sync(FULL, !dropped)) break;
+                    const uint32_t qb = qpos + K + c0;                 // first query residue of the chunk
+                    const uint32_t* qwp = reinterpret_cast<const uint32_t*>(qcodes + (qb & ~3u));
+                    uint32_t w[SCAN_CH / 4 + 1];
+#pragma unroll
+                    for (int j = 0; j <= SCAN_CH / 4; ++j) w[j] = __ldg(qwp + j);
+                    const uint32_t sh = (qb & 3u) * 8u;
+#pragma unroll
+                    for (int j = 0; j < SCAN_CH / 4; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh);
+                    const uint8_t* tp = tl + pos + K + c0;
+#pragma unroll
+                    for (int i = 0; i < SCAN_CH; ++i) {
+                        const uint32_t a = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                        cur += sscore[a * 32 + tp[i]];
+                        const bool up = !dropped && cur > best;
+                        dropped = dropped || (!up && best - cur > XD);
+                        best = up ? cur : best;
+                        blen = up ? K + c0 + i + 1 : blen;
+                    }
+                }
+                bool open = have && !dropped;                           // still alive after the lane's budget: warp-per-seed kernel
+                // left: residues qpos - 1 - i against tile position pos - 1 - i, from the right-extended best
+                int lbest = best, llen = 0;
+                cur = best;
+                bool ldropped = !have || open;
+                for (int c0 = 0; c0 < T1; c0 += SCAN_CH) {
+                    if (!__any_sync(FULL, !ldropped)) break;
+                    const int qb = (int)qpos - c0 - SCAN_CH;           // first (lowest) query residue of the chunk; below 0 only inside the leading pad
+                    const uint32_t* qwp = reinterpret_cast<const uint32_t*>(qcodes + (qb & ~3));
+                    uint32_t w[SCAN_CH / 4 + 1];
+#pragma unroll
+                    for (int j = 0; j <= SCAN_CH / 4; ++j) w[j] = __ldg(qwp + j);
+                    const uint32_t sh = (uint32_t)(qb & 3) * 8u;
+#pragma unroll
+                    for (int j = 0; j < SCAN_CH / 4; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh);
+                    const uint8_t* tp = tl + pos - c0 - SCAN_CH;
+#pragma unroll
+                    for (int i = 0; i < SCAN_CH; ++i) {
+                        const int r = SCAN_CH - 1 - i;                  // residue qb + r, i-th to the left
+                        const uint32_t a = (w[r >> 2] >> ((r & 3) * 8)) & 0xffu;
+                        cur += sscore[a * 32 + tp[r]];
+                        const bool up = !ldropped && cur > lbest;
+                        ldropped = ldropped || (!up && lbest - cur > XD);
+                        lbest = up ? cur : lbest;
+                        llen = up ? c0 + i + 1 : llen;
+                    }
+                }
+                if (have && !open && !ldropped) open = true;
+                if (open) {
+                    const unsigned long long slot2 = atomicAdd(nlong, 1ull);
+                    if (slot2 < cap) { SeedQ en; en.qpos = qpos; en.tpos = (uint32_t)(t0 + pos); longq[slot2] = en; }
+                } else if (have && lbest >= sp.min_ungapped) {
+                    const unsigned long long slot2 = atomicAdd(ncand, 1ull);
+                    if (slot2 < cap) {
+                        Cand cd; cd.qpos = qpos - (uint32_t)llen; cd.tpos = (uint32_t)(t0 + pos - llen);
+                        cd.len = (uint32_t)(blen + llen); cd.score = lbest;
+                        cand[slot2] = cd;
+                    }
                 }
             }
-            if (open) {
-                const unsigned long long slot2 = atomicAdd(nlong, 1ull);
-                if (slot2 < cap) { SeedQ e; e.qpos = (uint32_t)qpos; e.tpos = (uint32_t)tpos; longq[slot2] = e; }
-            } else if (lbest >= sp.min_ungapped) {
-                const unsigned long long slot2 = atomicAdd(ncand, 1ull);
-                if (slot2 < cap) {
-                    Cand cd; cd.qpos = (uint32_t)(qpos - llen); cd.tpos = (uint32_t)(tpos - llen); cd.len = (uint32_t)(rlen + llen); cd.score = lbest;
-                    cand[slot2] = cd;
-                }
-            }
+            __syncthreads();
         }
     }
     if (myseeds) atomicAdd(nseed, myseeds);
@@ -727,7 +803,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
     ds.k = spec.k; ds.base = spec.base; ds.xdrop = spec.xdrop; ds.min_ungapped = spec.min_ungapped;
     // residues per side a lane extends before handing the seed to the warp-per-seed kernel: long enough for random seeds to
     // die (expected drift -1.75 / base against X-drop 20 for nucleotides, about -1 / residue against 12 for proteins)
-    ds.lane_budget = nt ? 40 : 32;
+    ds.lane_budget = nt ? 48 : 32;                // multiples of SCAN_CH; k + budget <= SCAN_HALO
     memcpy(ds.seedmap, spec.seedmap, 32);
     if (nt) {
         sp.nsym = 6; sp.gap_open = 6; sp.gap_extend = 2;
@@ -754,18 +830,23 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
     SeqLayout QL, TL;
     std::vector<int> qframe(nq, 0);
     DevBuf d_qc, d_tc, d_tmpq, d_tmpt, d_off1, d_off2, d_frame, d_aalen;
+    // the query codes sit QC_LEAD bytes into their buffer, sentinels all around: the seed scan fetches whole extension chunks
+    // on both sides of a seed without bounds checks
+    constexpr int64_t QC_LEAD = 64, QC_TRAIL = 128;
+    uint8_t* qc = nullptr;
     if (nt) {
         QL = make_layout(qlen_nt);
         std::vector<int64_t> tl2((size_t)F * nc);
         for (int64_t i = 0; i < nc; ++i) for (int f = 0; f < F; ++f) tl2[f * nc + i] = tlen_nt[i];
         TL = make_layout(tl2);
-        PB_CUDA(ctx, d_qc.alloc(QL.total + 64, sm)); PB_CUDA(ctx, d_tc.alloc(TL.total + 64, sm));
-        fill_u8<<<(unsigned)((QL.total + 64 + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), SENT, QL.total + 64);
+        PB_CUDA(ctx, d_qc.alloc(QL.total + QC_LEAD + QC_TRAIL, sm)); PB_CUDA(ctx, d_tc.alloc(TL.total + 64, sm));
+        fill_u8<<<(unsigned)((QL.total + QC_LEAD + QC_TRAIL + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), SENT, QL.total + QC_LEAD + QC_TRAIL);
+        qc = d_qc.as<uint8_t>() + QC_LEAD;
         fill_u8<<<(unsigned)((TL.total + 64 + 255) / 256), 256, 0, sm>>>(d_tc.as<uint8_t>(), SENT, TL.total + 64);
         PB_CUDA(ctx, d_off1.alloc(nq * 8, sm)); PB_CUDA(ctx, d_off2.alloc((size_t)F * nc * 8, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off1.p, QL.off.data(), nq * 8, cudaMemcpyHostToDevice, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), (size_t)F * nc * 8, cudaMemcpyHostToDevice, sm));
-        encode_nt_kernel<<<dim3(1, (unsigned)std::min<int64_t>(nq, 32768)), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), nullptr, nq, d_qc.as<uint8_t>());
+        encode_nt_kernel<<<dim3(1, (unsigned)std::min<int64_t>(nq, 32768)), 128, 0, sm>>>(d_qascii.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), nullptr, nq, qc);
         encode_nt_kernel<<<dim3(256, (unsigned)std::min<int64_t>(nc, 256)), 256, 0, sm>>>(d_tascii.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), plus_only ? nullptr : d_off2.as<int64_t>() + nc, nc, d_tc.as<uint8_t>());
         PB_CUDA(ctx, cudaGetLastError()); launches += 4;
     } else {
@@ -789,13 +870,14 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         for (int64_t i = 0; i < nq; ++i) ql[i] = aalen[i];
         for (int64_t i = 0; i < nc; ++i) for (int f = 0; f < F; ++f) { int64_t rem = tlen_nt[i] - (f % 3); tl[i * F + f] = rem > 0 ? (rem + 2) / 3 : 0; }
         QL = make_layout(ql); TL = make_layout(tl);
-        PB_CUDA(ctx, d_qc.alloc(QL.total + 64, sm)); PB_CUDA(ctx, d_tc.alloc(TL.total + 64, sm));
-        fill_u8<<<(unsigned)((QL.total + 64 + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), SENT, QL.total + 64);
+        PB_CUDA(ctx, d_qc.alloc(QL.total + QC_LEAD + QC_TRAIL, sm)); PB_CUDA(ctx, d_tc.alloc(TL.total + 64, sm));
+        fill_u8<<<(unsigned)((QL.total + QC_LEAD + QC_TRAIL + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), SENT, QL.total + QC_LEAD + QC_TRAIL);
+        qc = d_qc.as<uint8_t>() + QC_LEAD;
         fill_u8<<<(unsigned)((TL.total + 64 + 255) / 256), 256, 0, sm>>>(d_tc.as<uint8_t>(), SENT, TL.total + 64);
         PB_CUDA(ctx, d_off1.alloc(nq * 8, sm)); PB_CUDA(ctx, d_off2.alloc(nc * F * 8, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off1.p, QL.off.data(), nq * 8, cudaMemcpyHostToDevice, sm));
         PB_CUDA(ctx, cudaMemcpyAsync(d_off2.p, TL.off.data(), nc * F * 8, cudaMemcpyHostToDevice, sm));
-        translate_queries_kernel<<<(unsigned)std::min<int64_t>(nq, 8192), 128, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), d_frame.as<int>(), nq, table4, d_qc.as<uint8_t>());
+        translate_queries_kernel<<<(unsigned)std::min<int64_t>(nq, 8192), 128, 0, sm>>>(d_tmpq.as<uint8_t>(), d_qsoff.as<int64_t>(), d_off1.as<int64_t>(), d_frame.as<int>(), nq, table4, qc);
         translate_targets_kernel<<<dim3(128, (unsigned)std::min<int64_t>(nc * F, 1024)), 256, 0, sm>>>(d_tmpt.as<uint8_t>(), d_tsoff.as<int64_t>(), d_off2.as<int64_t>(), nc, F, table4, d_tc.as<uint8_t>());
         PB_CUDA(ctx, cudaGetLastError()); launches += 4;
     }
@@ -810,7 +892,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
     PB_CUDA(ctx, d_table.alloc(tabsize * 4, sm)); PB_CUDA(ctx, d_cnt.alloc(64, sm));
     PB_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, 64, sm));
     PB_CUDA(ctx, cudaMemsetAsync(d_table.p, 0xff, tabsize * 4, sm));
-    extract_kmers_kernel<<<(unsigned)((LQ + 255) / 256), 256, 0, sm>>>(d_qc.as<uint8_t>(), LQ, ds, d_keys.as<uint32_t>(), d_vals.as<uint32_t>(), d_cnt.as<unsigned long long>());
+    extract_kmers_kernel<<<(unsigned)((LQ + 255) / 256), 256, 0, sm>>>(qc, LQ, ds, d_keys.as<uint32_t>(), d_vals.as<uint32_t>(), d_cnt.as<unsigned long long>());
     PB_CUDA(ctx, cudaGetLastError()); ++launches;
     size_t tmpb = 0;
     PB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmpb, d_keys.as<uint32_t>(), d_keys2.as<uint32_t>(), d_vals.as<uint32_t>(), d_vals2.as<uint32_t>(), (int)LQ, 0, 32, sm));
@@ -839,7 +921,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         int occ = 1;
         PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seed_scan_kernel, SCAN_THREADS, 0));
         const int grid = (int)std::min<int64_t>((LT + SCAN_TILE - 1) / SCAN_TILE, (int64_t)ctx->sm_count * std::max(occ, 1));
-        seed_scan_kernel<<<grid, SCAN_THREADS, 0, sm>>>(d_tc.as<uint8_t>(), LT, d_qc.as<uint8_t>(), LQ, d_table.as<uint32_t>(), d_keys.as<uint32_t>(),
+        seed_scan_kernel<<<grid, SCAN_THREADS, 0, sm>>>(d_tc.as<uint8_t>(), LT, qc, LQ, d_table.as<uint32_t>(), d_keys.as<uint32_t>(),
                                                          d_vals2.as<uint32_t>(), ds, d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap,
                                                          d_cnt.as<unsigned long long>() + 2, d_longq.as<SeedQ>(), d_cnt.as<unsigned long long>() + 3);
         PB_CUDA(ctx, cudaGetLastError()); ++launches;
@@ -848,7 +930,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         if (cnts[3] <= cap && cnts[3] > 0) {
             const unsigned long long nlong = cnts[3];
             const int xgrid = (int)std::min<unsigned long long>((nlong + 7) / 8, (unsigned long long)ctx->sm_count * 8);
-            xdrop_warp_kernel<<<xgrid, 256, 0, sm>>>(d_tc.as<uint8_t>(), LT, d_qc.as<uint8_t>(), LQ, ds, d_longq.as<SeedQ>(), nlong,
+            xdrop_warp_kernel<<<xgrid, 256, 0, sm>>>(d_tc.as<uint8_t>(), LT, qc, LQ, ds, d_longq.as<SeedQ>(), nlong,
                                                      d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap);
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
             PB_CUDA(ctx, cudaMemcpyAsync(cnts, d_cnt.p, 64, cudaMemcpyDeviceToHost, sm));
@@ -947,7 +1029,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         }
         pb_sw_job* J = nullptr;
         // forward pass (score + end cell) for every window; the start cell and the path come from one banded reverse pass
-        int rc = pb_sw_job_create_views_dev(ctx, d_qc.as<uint8_t>(), d_tc.as<uint8_t>(), d_wqb.as<int64_t>(), d_wqe.as<int64_t>(), d_wtb.as<int64_t>(),
+        int rc = pb_sw_job_create_views_dev(ctx, qc, d_tc.as<uint8_t>(), d_wqb.as<int64_t>(), d_wqe.as<int64_t>(), d_wtb.as<int64_t>(),
                                             d_wte.as<int64_t>(), nw, cells, &sp, 0, &J);
         if (rc) return rc;
         std::unique_ptr<pb_sw_job> guard(J);
