@@ -237,7 +237,7 @@ constexpr int SCAN_CH = 16;                   // residues per extension chunk; l
 
 struct SeedQ { uint32_t qpos, tpos; };
 
-__global__ void __launch_bounds__(SCAN_THREADS, 3) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
+__global__ void __launch_bounds__(SCAN_THREADS, 4) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
                                                                  const uint8_t* __restrict__ qcodes, int64_t qn,
                                                                  const uint32_t* __restrict__ table, const uint32_t* __restrict__ ends,
                                                                  const uint32_t* __restrict__ vals, DevSpec sp,
@@ -347,6 +347,23 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) seed_scan_kernel(const uint8_
             __syncthreads();
             // ---- phase 2b: extension, one seed per lane, SCAN_CH residues per chunk, branch-free inside a chunk ----
             const uint32_t n2 = s_n2;
+            constexpr int NW = SCAN_CH / 4;
+            // the SCAN_CH residues starting at byte address p (any alignment) as NW aligned-looking words
+            auto load_q = [&](const uint8_t* p, uint32_t (&w)[NW + 1]) {
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+#pragma unroll
+                for (int j = 0; j <= NW; ++j) w[j] = __ldg(wp + j);
+            };
+            auto load_t = [&](const uint8_t* p, uint32_t (&w)[NW + 1]) {
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+#pragma unroll
+                for (int j = 0; j <= NW; ++j) w[j] = wp[j];
+            };
+            auto align_words = [&](uint32_t (&w)[NW + 1], const uint8_t* p) {
+                const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+#pragma unroll
+                for (int j = 0; j < NW; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh);
+            };
             for (uint32_t e0 = 0; e0 < n2; e0 += SCAN_THREADS) {
                 const uint32_t e = e0 + threadIdx.x;
                 const bool have = e < n2;
@@ -354,22 +371,22 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) seed_scan_kernel(const uint8_
                 if (have) { const uint2 en = q2[e]; qpos = en.x; pos = (int)(en.y & 0xffffu); best = (int)(short)(en.y >> 16); }
                 int cur = best, blen = K;
                 bool dropped = !have;
+                // the first chunk of both sides is fetched up front (one exposed load latency per seed, not two)
+                uint32_t qr[NW + 1], ql[NW + 1];
+                load_q(qcodes + qpos + K, qr);
+                load_q(qcodes + (int64_t)qpos - SCAN_CH, ql);
                 // right: residues qpos + K + i against tile position pos + K + i
                 for (int c0 = 0; c0 < T1; c0 += SCAN_CH) {
                     if (!__any_sync(FULL, !dropped)) break;
-                    const uint32_t qb = qpos + K + c0;                 // first query residue of the chunk
-                    const uint32_t* qwp = reinterpret_cast<const uint32_t*>(qcodes + (qb & ~3u));
-                    uint32_t w[SCAN_CH / 4 + 1];
-#pragma unroll
-                    for (int j = 0; j <= SCAN_CH / 4; ++j) w[j] = __ldg(qwp + j);
-                    const uint32_t sh = (qb & 3u) * 8u;
-#pragma unroll
-                    for (int j = 0; j < SCAN_CH / 4; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh);
-                    const uint8_t* tp = tl + pos + K + c0;
+                    if (c0 > 0) load_q(qcodes + qpos + K + c0, qr);
+                    uint32_t tw[NW + 1];
+                    load_t(tl + pos + K + c0, tw);
+                    align_words(qr, qcodes + qpos + K + c0);
+                    align_words(tw, tl + pos + K + c0);
 #pragma unroll
                     for (int i = 0; i < SCAN_CH; ++i) {
-                        const uint32_t a = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-                        cur += sscore[a * 32 + tp[i]];
+                        const uint32_t a = (qr[i >> 2] >> ((i & 3) * 8)) & 0xffu, bb = (tw[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                        cur += sscore[a * 32 + bb];
                         const bool up = !dropped && cur > best;
                         dropped = dropped || (!up && best - cur > XD);
                         best = up ? cur : best;
@@ -383,20 +400,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) seed_scan_kernel(const uint8_
                 bool ldropped = !have || open;
                 for (int c0 = 0; c0 < T1; c0 += SCAN_CH) {
                     if (!__any_sync(FULL, !ldropped)) break;
-                    const int qb = (int)qpos - c0 - SCAN_CH;           // first (lowest) query residue of the chunk; below 0 only inside the leading pad
-                    const uint32_t* qwp = reinterpret_cast<const uint32_t*>(qcodes + (qb & ~3));
-                    uint32_t w[SCAN_CH / 4 + 1];
-#pragma unroll
-                    for (int j = 0; j <= SCAN_CH / 4; ++j) w[j] = __ldg(qwp + j);
-                    const uint32_t sh = (uint32_t)(qb & 3) * 8u;
-#pragma unroll
-                    for (int j = 0; j < SCAN_CH / 4; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh);
-                    const uint8_t* tp = tl + pos - c0 - SCAN_CH;
+                    const uint8_t* qp = qcodes + ((int64_t)qpos - c0 - SCAN_CH);   // lowest query residue of the chunk; below the array only inside the leading pad
+                    if (c0 > 0) load_q(qp, ql);
+                    uint32_t tw[NW + 1];
+                    load_t(tl + pos - c0 - SCAN_CH, tw);
+                    align_words(ql, qp);
+                    align_words(tw, tl + pos - c0 - SCAN_CH);
 #pragma unroll
                     for (int i = 0; i < SCAN_CH; ++i) {
-                        const int r = SCAN_CH - 1 - i;                  // residue qb + r, i-th to the left
-                        const uint32_t a = (w[r >> 2] >> ((r & 3) * 8)) & 0xffu;
-                        cur += sscore[a * 32 + tp[r]];
+                        const int r = SCAN_CH - 1 - i;                  // the i-th residue to the left is byte r of the chunk
+                        const uint32_t a = (ql[r >> 2] >> ((r & 3) * 8)) & 0xffu, bb = (tw[r >> 2] >> ((r & 3) * 8)) & 0xffu;
+                        cur += sscore[a * 32 + bb];
                         const bool up = !ldropped && cur > lbest;
                         ldropped = ldropped || (!up && lbest - cur > XD);
                         lbest = up ? cur : lbest;
