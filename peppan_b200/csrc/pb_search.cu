@@ -1150,18 +1150,29 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         }
         recs.push_back(Rec{h, i, group ? group[h.s_id] : 0});
     }
-    // duplicates (two windows converging on the same alignment) and deterministic order
-    std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) {
-        const pb_hit &x = a.h, &y = b.h;
-        if (a.grp != b.grp) return a.grp < b.grp;
-        if (x.q_id != y.q_id) return x.q_id < y.q_id;
-        if (x.s_id != y.s_id) return x.s_id < y.s_id;
-        if (x.s_start != y.s_start) return x.s_start < y.s_start;
-        if (x.q_start != y.q_start) return x.q_start < y.q_start;
-        if (x.s_end != y.s_end) return x.s_end < y.s_end;
-        if (x.q_end != y.q_end) return x.q_end < y.q_end;
-        return a.win < b.win;
-    });
+    // duplicates (two windows converging on the same alignment) and deterministic order: (group, query, subject, s_start,
+    // q_start, s_end, q_end, window).  Sorted through packed 64-bit keys (cheap compares), then one gather.
+    {
+        struct SK { uint64_t a, b, c; uint32_t idx; };
+        std::vector<SK> keys(recs.size());
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const pb_hit& x = recs[i].h;
+            // all fields are non-negative and below 2^31; the window index below 2^31
+            keys[i] = SK{((uint64_t)(uint32_t)recs[i].grp << 32) | (uint32_t)x.q_id, ((uint64_t)(uint32_t)x.s_id << 32) | (uint32_t)x.s_start,
+                         ((uint64_t)(uint32_t)x.q_start << 32) | (uint32_t)x.s_end, (uint32_t)i};
+        }
+        std::sort(keys.begin(), keys.end(), [&](const SK& p, const SK& q) {
+            if (p.a != q.a) return p.a < q.a;
+            if (p.b != q.b) return p.b < q.b;
+            if (p.c != q.c) return p.c < q.c;
+            const Rec &ra = recs[p.idx], &rb = recs[q.idx];
+            if (ra.h.q_end != rb.h.q_end) return ra.h.q_end < rb.h.q_end;
+            return ra.win < rb.win;
+        });
+        std::vector<Rec> sorted(recs.size());
+        for (size_t i = 0; i < keys.size(); ++i) sorted[i] = recs[keys[i].idx];
+        recs.swap(sorted);
+    }
     std::vector<Rec> uniq; uniq.reserve(recs.size());
     for (const Rec& r : recs) {
         if (!uniq.empty()) {

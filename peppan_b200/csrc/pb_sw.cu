@@ -132,6 +132,17 @@ cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t s
     return cudaGetLastError();
 }
 
+template <bool PACKED, bool REV>
+cudaError_t sw_launch_combo(const SwArgs& aw, const SwArgs& ar, int grid, size_t smem, int stride, cudaStream_t st)
+{
+    auto k = sw_combo_kernel<16, 19, 2, WAVE_G, WAVE_K, WAVE_R, PACKED, REV, 8>;
+    static_assert(WAVE_WARPS == 8, "one block shape for both bodies");
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 8 * 32, smem, st>>>(aw, ar, stride);
+    return cudaGetLastError();
+}
+
 // multi = false: every pair of the launch fits one column block (device-side maximum), the loop has no border code
 template <bool PACKED, bool REV>
 cudaError_t sw_dispatch(const SwConfig& c, const SwArgs& a, int grid, size_t smem, cudaStream_t st, bool multi)
@@ -172,7 +183,7 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     a.out_a = rev ? J->qs.as<int>() : J->qe.as<int>();
     a.out_b = rev ? J->ts.as<int>() : J->te.as<int>();
     a.cells = rev ? J->cells.as<unsigned long long>() : nullptr;
-    a.progress = nullptr; a.wsub = nullptr; a.wbase = nullptr; a.nsub = 0; a.wkey = nullptr; a.wdone = nullptr;
+    a.progress = nullptr; a.wsub = nullptr; a.wbase = nullptr; a.nsub = 0; a.wkey = nullptr; a.wdone = nullptr; a.block_base = 0;
     PB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 64 * sizeof(int), ctx->stream));
 
     const size_t smem16 = sw_smem_bytes(c, true, J->params.nsym), smem32 = sw_smem_bytes(c, false, J->params.nsym);
@@ -182,6 +193,11 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     const Range ranges[4] = { {0, n32L, false, true}, {n32L, n32 - n32L, false, false}, {n32, n16L, true, true}, {n32 + n16L, n - n32 - n16L, true, false} };
     // The long (wavefront) classes go first, on the aux stream: a handful of long pairs keep only a few SMs busy for
     // milliseconds, so they run beside the regular kernels instead of in front of them.
+    // A class (s32 / s16) that has both long and regular pairs runs as ONE persistent launch (sw_combo_kernel): warps take the
+    // wavefront sub-tasks first, then regular tasks.  (Two launches on two streams depended on which the hardware served
+    // first: when the persistent regular kernel won, the wavefront kernel only started after it.)  A class with only one
+    // kind, or with more wavefront tasks than one border-buffer budget holds, uses the separate kernels.
+    struct Pending { bool have = false; SwArgs a; size_t smem = 0; int wgrid = 0; } pend[2];     // [0] s32, [1] s16
     int slot = 0;
     DevBuf wbs[2], wps[2];
     bool forked = false;
@@ -265,6 +281,13 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
                 a.wkey = (unsigned long long*)((char*)wp.p + o_key) + 2 * (size_t)c.t0;
                 a.wbase = (const int*)((char*)wp.p + o_base) + c.t0 + ci; a.wsub = (const int2*)((char*)wp.p + o_sub) + c.sub0; a.nsub = (int)c.nsub;
                 const int wgrid = std::max(1, std::min(grid, (int)((c.nsub + WAVE_WARPS - 1) / WAVE_WARPS)));
+                const Range& reg = ranges[order[oi] + 1];       // the regular range of the same class
+                if (nch == 1 && reg.count > 0 && J->cfg.G == 16 && J->cfg.K == 19 && J->cfg.R == 2 && J->cfg.LONG == 1) {
+                    // launched together with the regular tasks of the class below
+                    Pending& pd = pend[r.packed ? 1 : 0];
+                    pd.have = true; pd.a = a; pd.smem = smem; pd.wgrid = wgrid;
+                    continue;
+                }
                 if (r.packed) e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, true, true, true>(a, wgrid, smem, ws)
                                       : sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, true, false, true, true>(a, wgrid, smem, ws);
                 else e = rev ? sw_launch_one<WAVE_G, WAVE_K, WAVE_R, true, WAVE_WARPS, false, true, true, true>(a, wgrid, smem, ws)
@@ -274,7 +297,16 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
         } else {
             a.boundary = bstride ? J->boundary.as<uint2>() : nullptr; a.bstride = bstride; a.progress = nullptr; a.nsub = 0;
             const bool multi = meta[2] > 1;
-            if (r.packed) e = rev ? sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream, multi) : sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream, multi);
+            Pending& pd = pend[r.packed ? 1 : 0];
+            if (pd.have) {
+                const int NPAIR = r.packed ? 2 : 1;
+                const int stride = std::max(NPAIR * J->params.nsym * ((c.K + 3) / 4) * 128, NPAIR * J->params.nsym * ((WAVE_K + 3) / 4) * 128);
+                const size_t smem = 1024 + (size_t)c.WARPS * stride;
+                const SwArgs aw = pd.a;          // its counter lives in the (zeroed) wavefront control block
+                e = r.packed ? (rev ? sw_launch_combo<true, true>(aw, a, grid, smem, stride, ctx->stream) : sw_launch_combo<true, false>(aw, a, grid, smem, stride, ctx->stream))
+                             : (rev ? sw_launch_combo<false, true>(aw, a, grid, smem, stride, ctx->stream) : sw_launch_combo<false, false>(aw, a, grid, smem, stride, ctx->stream));
+                pd.have = false;
+            } else if (r.packed) e = rev ? sw_dispatch<true, true>(c, a, grid, smem16, ctx->stream, multi) : sw_dispatch<true, false>(c, a, grid, smem16, ctx->stream, multi);
             else e = rev ? sw_dispatch<false, true>(c, a, grid, smem32, ctx->stream, multi) : sw_dispatch<false, false>(c, a, grid, smem32, ctx->stream, multi);
         }
         PB_CUDA(ctx, e);

@@ -101,6 +101,7 @@ struct SwArgs {
     int nsub;
     unsigned long long* wkey;   // WAVE: per (task, pair) packed best cell, combined with atomicMax (zeroed before launch)
     int* wdone;             // WAVE: finished sub-tasks per task (zeroed before launch)
+    int block_base;         // first block number of this launch among the launches sharing one task counter (border-buffer rows)
 };
 
 __device__ __forceinline__ uint32_t shfl_up_g(uint32_t v, int G) { return __shfl_up_sync(0xffffffffu, v, 1, G); }
@@ -151,8 +152,10 @@ template <> struct Ops<false> {
     static __device__ __forceinline__ uint32_t gtmask(uint32_t a, uint32_t b) { return (uint32_t)min((int)(a - b), 1) * 0xffffffffu; }
 };
 
+// The body of a kernel: the calling block has copied the 32 x 32 score matrix to smem[0 .. 1024) and synchronised; every
+// warp owns warp_stride bytes of profile space behind it.
 template <int G, int K, int R, bool LONG, bool PACKED, bool REV, int WARPS, bool WAVE, bool MULTI>
-__global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
+__device__ __forceinline__ void sw_body(const SwArgs& a, uint8_t* smem, const int warp_stride)
 {
     using O = Ops<PACKED>;
     constexpr int KW = (K + 3) / 4;     // profile words per lane per row
@@ -168,18 +171,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
     constexpr uint32_t HI = PACKED ? 0xffff0000u : 0xffffffffu;
     constexpr uint32_t LO = PACKED ? 0x0000ffffu : 0u;
 
-    extern __shared__ __align__(16) uint8_t smem[];
-    int8_t* smat = reinterpret_cast<int8_t*>(smem);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(smat)[i] = reinterpret_cast<const uint32_t*>(a.matrix)[i];
-    __syncthreads();
-
+    const int8_t* smat = reinterpret_cast<const int8_t*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / G, l = lane % G;
     const int nsym = a.nsym, PAD = a.nsym - 1;
     const int pairWords = nsym * KW * 32;
-    uint32_t* prof = reinterpret_cast<uint32_t*>(smem + 1024) + (size_t)(warp * NPAIR) * pairWords;
-    const int gwarp = blockIdx.x * WARPS + warp;
+    uint32_t* prof = reinterpret_cast<uint32_t*>(smem + 1024 + (size_t)warp * warp_stride);
+    const int gwarp = (a.block_base + (int)blockIdx.x) * WARPS + warp;
     uint2* mybound = (MULTI && a.boundary && !WAVE) ? a.boundary + ((size_t)gwarp * NG + g) * a.bstride : nullptr;
     uint2* wavebound = nullptr;
     int* waveprog = nullptr;
@@ -588,6 +586,37 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
         }
         if (REV && a.cells && l == 0) atomicAdd(a.cells, WAVE ? (unsigned long long)mw * (unsigned long long)min(nw - wblock * W, W) : swept);
     }
+}
+
+__device__ __forceinline__ void sw_stage_matrix(const int8_t* matrix, uint8_t* smem)
+{
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(matrix)[i];
+    __syncthreads();
+}
+
+template <int G, int K, int R, bool LONG, bool PACKED, bool REV, int WARPS, bool WAVE, bool MULTI>
+__global__ void __launch_bounds__(WARPS * 32, 1) sw_kernel(const SwArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    sw_stage_matrix(a.matrix, smem);
+    constexpr int NPAIR = PACKED ? 2 : 1;
+    sw_body<G, K, R, LONG, PACKED, REV, WARPS, WAVE, MULTI>(a, smem, NPAIR * a.nsym * ((K + 3) / 4) * 128);
+}
+
+// Long (wavefront) and regular tasks of one class in ONE persistent launch: every warp first takes wavefront sub-tasks
+// until their list is exhausted, then regular tasks.  The latency-bound wavefront warps (one warp per 512-column block of
+// a long pair) share their SMs with throughput-bound regular warps instead of holding SMs of their own, and no order
+// between two launches has to be hoped for.  Producers of a border are always taken before their consumers and compute
+// without waiting, so the wait of a consumer ends.
+template <int G, int K, int R, int WG, int WK, int WR, bool PACKED, bool REV, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) sw_combo_kernel(const SwArgs aw, const SwArgs ar, const int warp_stride)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    sw_stage_matrix(ar.matrix, smem);
+    sw_body<WG, WK, WR, true, PACKED, REV, WARPS, true, true>(aw, smem, warp_stride);
+    __syncwarp();
+    sw_body<G, K, R, true, PACKED, REV, WARPS, false, true>(ar, smem, warp_stride);
 }
 
 }  // namespace pbsw

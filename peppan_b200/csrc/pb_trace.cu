@@ -75,6 +75,7 @@ struct TraceArgs {
     uint2* boundary;
     int bstride;
     int2* start;            // per pair: (row, col) of the first row-major cell holding S, (-1, -1) if none
+    int block_base;         // first block number of this launch among the launches sharing one task counter (border-buffer rows)
 };
 
 // one warp per pair: Uq, Ut over the prefixes -> band
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sw_band_trace_kernel(const T
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / G, l = lane % G;
     const int nsym = a.nsym, PAD = nsym - 1, rowBytes = G * KP;
     uint8_t* prof = smem + 1024 + (size_t)(warp * NG + g) * nsym * rowBytes;
-    const int gwarp = blockIdx.x * WARPS + warp;
+    const int gwarp = (a.block_base + (int)blockIdx.x) * WARPS + warp;
     uint2* mybound = a.boundary + ((size_t)gwarp * NG + g) * a.bstride;
     const int ge = a.ge, goe = a.go + a.ge;
 
@@ -531,24 +532,51 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         void* dbound[3] = {nullptr, nullptr, nullptr};
         bool forked[3] = {false, false, false};
         cudaStream_t side[3] = {sm, ctx->copy_stream, ctx->aux_stream};
+        // The side kernels must find free SMs whichever stream the hardware serves first (the narrow kernel is persistent and
+        // would otherwise hold the whole machine until it ends): each side launch is capped at an eighth of the SMs, the
+        // narrow launch on the context stream leaves those SMs free, and a small second narrow launch queued behind every side
+        // kernel takes tasks from the same counter once its SMs are free again.
+        int side_sms[3] = {0, 0, 0};
         size_t first = 0;
+        TraceArgs narrow_args; bool have_narrow = false; int narrow_main = 0;
+        const int occ0 = std::max(1, grid_c[0] / ctx->sm_count);
         for (int k = 2; k >= 0; --k) {
             const size_t cnt = c.ncls[k];
             if (cnt == 0) continue;
             const int NG = 32 / tb_shape(k).G;
-            const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid_c[k], (cnt + (size_t)TB_WARPS * NG - 1) / ((size_t)TB_WARPS * NG)));
-            { const int rc = pb_scratch(ctx, 1 + k, (size_t)grid * TB_WARPS * NG * bstride * sizeof(uint2), &dbound[k]); if (rc) return rc; }
+            const int occk = std::max(1, grid_c[k] / ctx->sm_count);
+            const bool fork = k > 0 && cnt < c.count;      // the few long / wide pairs run beside the rest on their own streams
+            int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid_c[k], (cnt + (size_t)TB_WARPS * NG - 1) / ((size_t)TB_WARPS * NG)));
+            if (fork) { grid = std::min(grid, std::max(1, ctx->sm_count / 8) * occk); side_sms[k] = (grid + occk - 1) / occk; }
+            // border rows for every block that may run with this counter (main + helper launches of the narrow kernel)
+            { const int rc = pb_scratch(ctx, 1 + k, (size_t)(k == 0 ? grid_c[0] : grid) * TB_WARPS * NG * bstride * sizeof(uint2), &dbound[k]); if (rc) return rc; }
             TraceArgs r = a;
             r.desc = ddesc.as<BandDesc>() + first; r.count = (int)cnt; r.counter = ctx->d_counter + k;
-            r.boundary = reinterpret_cast<uint2*>(dbound[k]); r.start = dstart.as<int2>() + first;
+            r.boundary = reinterpret_cast<uint2*>(dbound[k]); r.start = dstart.as<int2>() + first; r.block_base = 0;
             cudaStream_t ks = sm;
-            if (k > 0 && cnt < c.count) {            // the few long / wide pairs run beside the rest on their own streams
+            if (fork) {
                 PB_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[k], sm)); PB_CUDA(ctx, cudaStreamWaitEvent(side[k], ctx->ev_pipe[k], 0));
                 forked[k] = true; ks = side[k];
+            }
+            if (k == 0) {
+                const int reserve = (side_sms[1] + side_sms[2]) * occ0;
+                grid = std::max(1, std::min(grid, grid_c[0] - reserve));
+                narrow_args = r; have_narrow = true; narrow_main = grid;
             }
             kern[k]<<<grid, TB_WARPS * 32, smem_c[k], ks>>>(r);
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
             first += cnt;
+        }
+        if (have_narrow) {
+            int base = narrow_main;
+            for (int k = 2; k >= 1; --k) {
+                if (!forked[k] || side_sms[k] == 0) continue;
+                TraceArgs r = narrow_args; r.block_base = base;
+                const int g = side_sms[k] * occ0;
+                kern[0]<<<g, TB_WARPS * 32, smem_c[0], side[k]>>>(r);
+                PB_CUDA(ctx, cudaGetLastError()); ++launches;
+                base += g;
+            }
         }
         for (int k = 1; k < 3; ++k)
             if (forked[k]) { PB_CUDA(ctx, cudaEventRecord(ctx->ev_aux[k - 1], side[k])); PB_CUDA(ctx, cudaStreamWaitEvent(sm, ctx->ev_aux[k - 1], 0)); }

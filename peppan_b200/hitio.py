@@ -153,3 +153,229 @@ def load_bsn(path):
             bsn[i, j] = v
     ovl = np.frombuffer(data, dtype='<i8', count=m * k, offset=pos).reshape(m, k).copy() if m * k else np.zeros([m, k], dtype=np.int64)
     return bsn, ovl
+
+
+# ---- a store with MapBsn's interface (PEPPAN.py:27-114) on one flat file ---------------------------------------------------
+# PEPPAN keeps its per-contig / per-gene tables in MapBsn: a zip of pickled, deflated .npy members.  FlatStore offers the same
+# methods (get / [] / exists / keys / items / values / delete / pop / size / save / update, context manager) over one
+# append-only file: values -- object arrays of rows whose cells are names, numbers, strings, lists and nested arrays, as
+# iter_map_bsn / get_map_bsn build them -- are written with a small recursive TYPED codec (no pickle, no deflate), the index
+# (key -> offset, length) is written behind the values when the store is closed.
+STORE_MAGIC, STORE_END = b'PBSTORE1', b'PBSTOREX'
+(_V_NONE, _V_INT, _V_FLOAT, _V_STR, _V_BOOL, _V_LIST, _V_TUPLE, _V_ARR, _V_OBJ, _V_BYTES, _V_NPINT, _V_NPFLOAT, _V_NPBOOL, _V_NPSTR) = range(14)
+
+
+def _enc(v, out):
+    import struct
+    if v is None:
+        out.append(bytes([_V_NONE]))
+    elif isinstance(v, (bool, np.bool_)):
+        out.append(bytes([_V_NPBOOL if isinstance(v, np.bool_) else _V_BOOL, 1 if v else 0]))
+    elif isinstance(v, np.integer):
+        d = np.dtype(type(v)).str.encode()
+        out.append(bytes([_V_NPINT, len(d)]) + d + struct.pack('<q', int(v)))
+    elif isinstance(v, int):
+        if -(1 << 63) <= v < (1 << 63):
+            out.append(bytes([_V_INT]) + struct.pack('<q', v))
+        else:                                   # SHA1 gene codes are 160-bit integers (PEPPAN.py:178)
+            s = str(v).encode(); out.append(bytes([_V_BYTES]) + struct.pack('<I', len(s)) + s + b'i')
+    elif isinstance(v, np.floating):
+        d = np.dtype(type(v)).str.encode()
+        out.append(bytes([_V_NPFLOAT, len(d)]) + d + struct.pack('<d', float(v)))
+    elif isinstance(v, float):
+        out.append(bytes([_V_FLOAT]) + struct.pack('<d', v))
+    elif isinstance(v, np.str_):
+        s = str(v).encode(); out.append(bytes([_V_NPSTR]) + struct.pack('<I', len(s)) + s)
+    elif isinstance(v, str):
+        s = v.encode(); out.append(bytes([_V_STR]) + struct.pack('<I', len(s)) + s)
+    elif isinstance(v, bytes):
+        out.append(bytes([_V_BYTES]) + struct.pack('<I', len(v)) + v + b'b')
+    elif isinstance(v, (list, tuple)):
+        out.append(bytes([_V_LIST if isinstance(v, list) else _V_TUPLE]) + struct.pack('<I', len(v)))
+        for x in v:
+            _enc(x, out)
+    elif isinstance(v, np.ndarray):
+        shape = struct.pack('<B', v.ndim) + b''.join(struct.pack('<q', int(n)) for n in v.shape)
+        if v.dtype == object:
+            out.append(bytes([_V_OBJ]) + shape)
+            for x in v.reshape(-1):
+                _enc(x, out)
+        else:
+            d = v.dtype.str.encode()
+            if v.dtype.kind not in 'iufbUS':
+                raise TypeError('FlatStore: arrays of dtype %s are not carried' % v.dtype)
+            out.append(bytes([_V_ARR, len(d)]) + d + shape + np.ascontiguousarray(v).tobytes())
+    else:
+        raise TypeError('FlatStore: values of type %s are not carried' % type(v).__name__)
+
+
+def _dec(buf, p):
+    import struct
+    t = buf[p]; p += 1
+    if t == _V_NONE:
+        return None, p
+    if t in (_V_BOOL, _V_NPBOOL):
+        return (bool(buf[p]) if t == _V_BOOL else np.bool_(buf[p])), p + 1
+    if t == _V_INT:
+        return struct.unpack_from('<q', buf, p)[0], p + 8
+    if t == _V_FLOAT:
+        return struct.unpack_from('<d', buf, p)[0], p + 8
+    if t in (_V_NPINT, _V_NPFLOAT):
+        n = buf[p]; d = np.dtype(bytes(buf[p + 1:p + 1 + n]).decode()); p += 1 + n
+        x = struct.unpack_from('<q' if t == _V_NPINT else '<d', buf, p)[0]
+        return d.type(x), p + 8
+    if t in (_V_STR, _V_NPSTR):
+        n = struct.unpack_from('<I', buf, p)[0]; s = bytes(buf[p + 4:p + 4 + n]).decode()
+        return (s if t == _V_STR else np.str_(s)), p + 4 + n
+    if t == _V_BYTES:
+        n = struct.unpack_from('<I', buf, p)[0]; s = bytes(buf[p + 4:p + 4 + n]); kind = buf[p + 4 + n:p + 5 + n]
+        return (int(s) if kind == b'i' else s), p + 5 + n
+    if t in (_V_LIST, _V_TUPLE):
+        n = struct.unpack_from('<I', buf, p)[0]; p += 4
+        items = []
+        for _ in range(n):
+            x, p = _dec(buf, p); items.append(x)
+        return (items if t == _V_LIST else tuple(items)), p
+    if t == _V_ARR:
+        n = buf[p]; d = np.dtype(bytes(buf[p + 1:p + 1 + n]).decode()); p += 1 + n
+        nd = buf[p]; shape = struct.unpack_from('<%dq' % nd, buf, p + 1); p += 1 + 8 * nd
+        cnt = int(np.prod(shape)) if nd else 1
+        a = np.frombuffer(buf, dtype=d, count=cnt, offset=p).reshape(shape).copy()
+        return a, p + cnt * d.itemsize
+    if t == _V_OBJ:
+        nd = buf[p]; shape = struct.unpack_from('<%dq' % nd, buf, p + 1); p += 1 + 8 * nd
+        cnt = int(np.prod(shape)) if nd else 1
+        a = np.empty(cnt, dtype=object)
+        for i in range(cnt):
+            a[i], p = _dec(buf, p)
+        return a.reshape(shape), p
+    raise ValueError('FlatStore: corrupt value (tag %d)' % t)
+
+
+def encode_value(v):
+    out = []
+    _enc(v, out)
+    return b''.join(out)
+
+
+def decode_value(blob):
+    return _dec(memoryview(blob), 0)[0]
+
+
+class FlatStore(object):
+    """MapBsn (PEPPAN.py:27-114) on one flat file.  mode 'r' / 'w' / 'a' as there."""
+
+    def __init__(self, fname, mode='r'):
+        import os
+        self.fname, self.mode = fname, mode
+        self.index = {}
+        if mode == 'w' or not os.path.exists(fname):
+            if mode == 'r':
+                raise IOError('%s does not exist' % fname)
+            self.fh = open(fname, 'w+b'); self.fh.write(STORE_MAGIC); self.end = 8
+        else:
+            self.fh = open(fname, 'r+b' if mode != 'r' else 'rb')
+            if self.fh.read(8) != STORE_MAGIC:
+                raise ValueError('%s is not a peppan_b200 store' % fname)
+            self.fh.seek(-16, 2)
+            tail = self.fh.read(16)
+            if tail[8:] != STORE_END:
+                raise ValueError('%s was not closed properly' % fname)
+            ipos = int(np.frombuffer(tail[:8], dtype='<i8')[0])
+            self.fh.seek(ipos); blob = self.fh.read()[:-16]
+            self.index = {k: (o, n) for k, o, n in decode_value(blob)}
+            self.end = ipos                                   # new values overwrite the old index
+        self.namelist = set(self.index)
+        self.dirty = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, type, value, traceback):
+        self.close()
+
+    def close(self):
+        if self.fh is None:
+            return
+        if self.mode != 'r':
+            self.fh.seek(self.end); self.fh.truncate()
+            # like the zip behind MapBsn, the file keeps every value written; delete() is a per-session view (PEPPAN.py:62-63)
+            blob = encode_value([[k, o, n] for k, (o, n) in self.index.items()])
+            self.fh.write(blob); self.fh.write(np.array([self.end], dtype='<i8').tobytes()); self.fh.write(STORE_END)
+        self.fh.close(); self.fh = None
+
+    def get(self, key, default=[]):
+        key = str(key)
+        if self.exists(key):
+            o, n = self.index[key]
+            self.fh.seek(o)
+            return decode_value(self.fh.read(n))
+        return default
+
+    def __getitem__(self, key):
+        return self.get(key)
+
+    def exists(self, key):
+        return str(key) in self.namelist
+
+    def keys(self):
+        return self.namelist
+
+    def items(self):
+        for key in self.namelist:
+            yield key, self.get(key)
+
+    def values(self):
+        for key in self.namelist:
+            yield self.get(key)
+
+    def delete(self, key):
+        self.namelist -= {str(key)}
+
+    def pop(self, key, default=[]):
+        val = self.get(key, default)
+        self.delete(key)
+        return val
+
+    def size(self):
+        return len(self.namelist)
+
+    def _save(self, db, key, val):
+        # db: the store written to (the reference passes its zip handle: `store._save(store.conn, key, val)`)
+        target = db if isinstance(db, FlatStore) else self
+        blob = encode_value(np.asanyarray(val))
+        target.fh.seek(target.end); target.fh.write(blob)
+        target.index[str(key)] = (target.end, len(blob)); target.end += len(blob); target.dirty = True
+
+    @property
+    def conn(self):
+        return self
+
+    def save(self, key, val):
+        key = str(key)
+        self._save(self, key, val)
+        self.namelist |= {key}
+
+    def update(self, dataset):
+        """rows of every table in `dataset` are appended to the table stored under its first cell (PEPPAN.py:94-114)"""
+        import os
+        new_list = set()
+        tmp_name = self.fname[:-4] + '.tmp.npz'
+        tmp = FlatStore(tmp_name, 'w')
+        for d in dataset:
+            key = str(d[0][0])
+            new_list.add(key)
+            old = self.get(key)
+            data = np.vstack([old, d]) if len(old) else d
+            tmp._save(tmp, key, data)
+        for key in list(self.keys()):
+            if key not in new_list:
+                data = self.get(key)
+                if len(data):
+                    new_list.add(key)
+                    tmp._save(tmp, key, data)
+        tmp.namelist = set(tmp.index)
+        tmp.close()
+        self.fh.close()
+        os.rename(tmp_name, self.fname)
+        self.__init__(self.fname, 'a')

@@ -95,6 +95,7 @@ class RunBlast(object):
         self.qrySeq = self.refSeq = None
         self.ctx = ctx
         self.stats = []
+        self.raw = []          # (mode, hits, cigar) of every search of this run: the record tables behind the rows
 
     # ---- tools ---------------------------------------------------------------------------------
     def _load(self, ref, qry):
@@ -114,6 +115,7 @@ class RunBlast(object):
         (qn, qb, qo), (rn, rb, ro) = self._sets()
         hits, cigar, st = _srch.search(ctx, qb, qo, rb, ro, mode, self.min_id, self.min_cov, self.min_ratio, self.table_id)
         self.stats.append(st)
+        self.raw.append((mode, hits, cigar))
         return qn, rn, hits, cigar
 
     def runBlast(self, ref, qry):
@@ -216,12 +218,26 @@ def uberBlast(args, extPool=None):
         args.process = extPool
     methods = [m for m in ('blastn', 'diamond', 'diamondSELF') if getattr(args, m)]
     fix_end = list(map(float, args.fix_end.split(',')[-2:]))
-    data = RunBlast().run(args.reference, args.query, methods, args.min_id, args.min_cov, args.min_ratio, args.gtable, args.n_thread,
+    runner = RunBlast()
+    data = runner.run(args.reference, args.query, methods, args.min_id, args.min_cov, args.min_ratio, args.gtable, args.n_thread,
                           args.process, args.re_score,
                           [args.filter, args.filter_cov, args.filter_score],
                           [args.linear_merge, args.merge_gap, args.merge_diff],
                           [args.return_overlap, args.overlap_length, args.overlap_proportion], fix_end)
-    if args.output:
+    if args.output and args.output.endswith('.pbh'):
+        # the raw record tables of the run (before the post-search chain) as one flat hit-table file (hitio.py)
+        from . import hitio
+        (qn, _, _), (rn, _, _) = runner._sets()
+        hs = [h for _, h, _ in runner.raw]; cs = [c for _, _, c in runner.raw]
+        if hs:
+            shift = np.cumsum([0] + [len(c) for c in cs[:-1]])
+            hs = [h.copy() for h in hs]
+            for h, o in zip(hs, shift):
+                h['cigar_off'] += np.uint32(o)
+            hitio.save_hits(args.output, np.concatenate(hs), np.concatenate(cs), qn, rn)
+        else:
+            hitio.save_hits(args.output, np.zeros(0, dtype=_srch.HIT_DTYPE), np.zeros(0, np.uint32), qn, rn)
+    elif args.output:
         fout = sys.stdout if args.output.upper() == 'STDOUT' else open(args.output, 'w')
         for t in (data[0] if args.return_overlap else data):
             fout.write('\t'.join([str(tt) for tt in t]) + '\n')

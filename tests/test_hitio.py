@@ -76,3 +76,86 @@ def test_bsn_file_round_trips_the_pipeline_tables(tmp_path, oracle_as_search):
     hitio.save_bsn(path, tab3, np.zeros([0, 3], dtype=np.int64))
     tab4, ovl4 = hitio.load_bsn(path)
     assert ovl4.shape == (0, 3) and all(type(a) is type(b) and a == b for a, b in zip(tab3.reshape(-1).tolist(), tab4.reshape(-1).tolist()))
+
+
+def _deep_equal(a, b):
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        if not (isinstance(a, np.ndarray) and isinstance(b, np.ndarray)) or a.shape != b.shape or a.dtype != b.dtype:
+            return False
+        if a.dtype == object:
+            return all(_deep_equal(x, y) for x, y in zip(a.reshape(-1), b.reshape(-1)))
+        return np.array_equal(a, b)
+    if isinstance(a, (list, tuple)):
+        return type(a) is type(b) and len(a) == len(b) and all(_deep_equal(x, y) for x, y in zip(a, b))
+    return type(a) is type(b) and a == b
+
+
+def test_typed_codec_round_trips_nested_pipeline_values():
+    rows = np.array([[1, 'a', 2.5, [1, 2.0, 'x'], np.arange(5, dtype=np.uint8), np.array([[1, 'q'], [2, 'r']], dtype=object)],
+                     [np.int64(7), np.str_('b'), np.float64(1.5), [], np.zeros(0), None]], dtype=object)
+    assert _deep_equal(hitio.decode_value(hitio.encode_value(rows)), rows)
+    for v in (1 << 100, -3, 2.5, 'x', None, True, (1, 'a'), np.zeros([2, 0, 3]), np.array(['ab', 'c'])):
+        assert _deep_equal(hitio.decode_value(hitio.encode_value(v)), v)
+    with pytest.raises(TypeError):
+        hitio.encode_value({'a': 1})
+
+
+def test_flat_store_behaves_like_the_references_mapbsn(tmp_path):
+    """FlatStore against the reference's own MapBsn (PEPPAN.py:27-114), operation for operation; and the reference's
+    compare_prediction (PEPPAN.py:869-902) run on a FlatStore gives the table it gives on a MapBsn."""
+    import sys
+    ref = os.environ.get('PEPPAN_REFERENCE', '/root/reference')
+    if not os.path.exists(os.path.join(ref, 'PEPPAN.py')):
+        pytest.skip('reference checkout not present')
+    from test_reference_consumer_cpu import PEPPAN as _fx
+    P = _fx.__wrapped__() if hasattr(_fx, '__wrapped__') else None
+    if P is None:
+        pytest.skip('reference fixture not importable')
+    if not hasattr(np.lib.npyio, 'format'):
+        np.lib.npyio.format = np.lib.format
+    rng = np.random.default_rng(5)
+
+    def table(key, n):
+        return np.array([[key, int(rng.integers(1, 1000)), int(rng.integers(1000, 2000)), '+-'[int(rng.integers(0, 2))], float(rng.random()),
+                          np.arange(int(rng.integers(0, 4)), dtype=np.uint8)] for _ in range(n)], dtype=object)
+    stores = (P.MapBsn(os.path.join(tmp_path, 'a.npz'), 'w'), hitio.FlatStore(os.path.join(tmp_path, 'b.npz'), 'w'))
+    t1, t2, t3 = table(11, 3), table('g2', 2), table(13, 1)
+    for s in stores:
+        s._save(s.conn, '11', t1); s._save(s.conn, 'g2', t2)
+        s.conn.close() if isinstance(s, P.MapBsn) else s.close()
+    stores = (P.MapBsn(os.path.join(tmp_path, 'a.npz'), 'a'), hitio.FlatStore(os.path.join(tmp_path, 'b.npz'), 'a'))
+    for s in stores:
+        assert s.size() == 2 and s.exists(11) and s.exists('11') and not s.exists(12) and sorted(s.keys()) == ['11', 'g2']
+        assert s.get('nope') == [] and s.get('nope', None) is None
+    assert _deep_equal(stores[0].get(11), stores[1].get(11)) and _deep_equal(stores[0]['g2'], stores[1]['g2'])
+    more = [np.array([[11, 5, 6, '+', 0.5, np.zeros(1, dtype=np.uint8)]], dtype=object), t3]
+    for s in stores:
+        s.update(more)
+    for s in stores:
+        assert sorted(s.keys()) == ['11', '13', 'g2'] and len(s.get(11)) == 4
+    for k in ('11', '13', 'g2'):
+        assert _deep_equal(stores[0].get(k), stores[1].get(k))
+    assert _deep_equal(sorted(k for k, _ in stores[0].items()), sorted(k for k, _ in stores[1].items()))
+    for s in stores:
+        assert len(s.pop('g2')) == 2 and not s.exists('g2') and s.size() == 2
+    stores[0].conn.close(); stores[1].close()
+
+    # the reference's compare_prediction on both kinds of store
+    old_rows = np.array([[7, 101, 400, '+'], [8, 900, 1500, '-']], dtype=object)
+    blastab = np.array([[1, 500, 0.9, 300, 0, 0, 1, 300, 101, 400, 0.0, 290., 300, 5000, '300M', 0],
+                        [2, 500, 0.8, 600, 0, 0, 1, 600, 1500, 901, 0.0, 500., 600, 5000, '600M', 1],
+                        [3, 500, 0.7, 100, 0, 0, 1, 100, 3000, 3099, 0.0, 90., 100, 5000, '100M', 2]], dtype=object)
+    outs = []
+    for cls, name in ((P.MapBsn, 'c.npz'), (hitio.FlatStore, 'd.npz')):
+        st = cls(os.path.join(tmp_path, name), 'w')
+        st._save(st.conn, '500', old_rows)
+        st.conn.close() if cls is P.MapBsn else st.close()
+        saved = P.MapBsn
+        P.MapBsn = cls
+        try:
+            outs.append(P.compare_prediction(blastab.copy(), os.path.join(tmp_path, name)))
+        finally:
+            P.MapBsn = saved
+    assert outs[0].shape == outs[1].shape and all(_deep_equal(x, y) for x, y in zip(outs[0].reshape(-1).tolist(), outs[1].reshape(-1).tolist()))
+    col10 = sorted(float(r[10]) for r in outs[1])
+    assert col10[0] == 0.1 and col10[1] > 0.99 and col10[2] == 1.0
