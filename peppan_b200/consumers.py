@@ -1,0 +1,180 @@
+"""Columnar form of the consumer loop behind uberBlast: what PEPPAN.iter_map_bsn does with the blastab
+after compare_prediction (PEPPAN.py:773-866) -- group the hits by merge group, score every hit from its CIGAR and the matched
+subject sequence, trim overlapping members of a group, translate the overlap table to group ids -- with the per-hit work
+(`:803-847`: CIGAR re-parsing by regex, per-run string building, codon scan for stops, base encoding) done for the whole
+table at once on flat numpy arrays instead of per character in Python.  Same inputs, same return values, cell for cell
+(tests/test_consumers.py runs the reference's own iter_map_bsn beside it).
+
+    bsn, overlap = map_bsn_groups(blastab, overlap, seq, params, ortho_pairs)
+
+blastab   object ndarray (n, 17) as compare_prediction returns it (column 10 = overlap fraction with the old annotation)
+overlap   int (m, 3) overlap table of uberBlast -O (hit id, hit id, bp)
+seq       [(contig, sequence), ...] of the genome (PEPPAN.py:760)
+params    match_identity, match_prop / match_len (+ 1, 2), gtable
+ortho_pairs  (k, 3) array [gene, gene, score] (the `orthoGroup` file of the reference, already loaded) or None
+"""
+import re
+
+import numpy as np
+
+_CIG = re.compile(r'(\d+)([A-Z])')
+_BASE = np.zeros(256, dtype=np.uint8)
+_BASE[[ord(c) for c in 'ACGT']] = (1, 2, 3, 4)                       # baseConv, PEPPAN.py:904-905
+_COMP = np.full(256, ord('N'), dtype=np.uint8)                      # rc(), modules/configure.py:152-154
+_COMP[[ord(c) for c in 'ACGT']] = [ord(c) for c in 'TGCA']
+
+
+def _excl_cumsum_within(values, first, counts):
+    """exclusive cumulative sum of `values` restarting at every segment (segments given by first index and length)"""
+    cs = np.cumsum(values) - values
+    return cs - np.repeat(cs[first], counts) if len(values) else cs
+
+
+def score_hits(rows, seq, gtable=11):
+    """Per hit of `rows` (object rows with the uberBlast columns): (sc, x) where sc is the reference's frame / stop-limited
+    match length (PEPPAN.py:818-834) and x the base-encoded matched sequence with query gaps as 0 (:835)."""
+    nh = len(rows)
+    names = [n for n, _ in seq]
+    cidx = {n: i for i, n in enumerate(names)}
+    sbuf = np.frombuffer(''.join(s for _, s in seq).encode(), dtype=np.uint8)
+    soff = np.zeros(len(names) + 1, dtype=np.int64); soff[1:] = np.cumsum([len(s) for _, s in seq])
+
+    cig = [r[14] for r in rows]
+    pairs = _CIG.findall(','.join(cig))
+    L = np.array([int(a) for a, _ in pairs], dtype=np.int64)
+    op = np.frombuffer(''.join(b for _, b in pairs).encode(), dtype=np.uint8) if pairs else np.zeros(0, np.uint8)
+    nops = np.array([len(_CIG.findall(c)) for c in cig], dtype=np.int64)
+    first = np.concatenate([[0], np.cumsum(nops)[:-1]]).astype(np.int64) if nh else np.zeros(0, np.int64)
+    hid = np.repeat(np.arange(nh), nops)
+    is_m, is_d = op == ord('M'), op == ord('D')
+    is_i = ~(is_m | is_d)                                            # every other op inserts query bases (:828-830)
+
+    # reading frame before every run: a deletion moves it back, an insertion forward (:826-830)
+    frame = _excl_cumsum_within(np.where(is_d, -L, np.where(is_i, L, 0)), first, nops) % 3
+    sc3 = np.zeros([nh, 3], dtype=np.int64)
+    np.add.at(sc3, (hid[is_m], frame[is_m]), L[is_m])
+    sc = sc3.max(axis=1) if nh else np.zeros(0, np.int64)
+
+    # matched sequence with '-' for query insertions, all hits in one flat byte array
+    sub_before = _excl_cumsum_within(np.where(is_m | is_d, L, 0), first, nops)      # subject bases consumed before the run
+    emit = is_m | is_i
+    eL, eh, em, esub = L[emit], hid[emit], is_m[emit], sub_before[emit]
+    ms_len = np.bincount(eh, weights=eL, minlength=nh).astype(np.int64)
+    ms_off = np.concatenate([[0], np.cumsum(ms_len)]).astype(np.int64)
+    total = int(ms_off[-1])
+    run_start = np.cumsum(eL) - eL
+    k = np.arange(total, dtype=np.int64) - np.repeat(run_start, eL)
+    ch_hit = np.repeat(eh, eL)
+    ch_m = np.repeat(em, eL)
+    s_start = np.array([r[8] for r in rows], dtype=np.int64); s_end = np.array([r[9] for r in rows], dtype=np.int64)
+    contig = np.array([cidx[r[1]] for r in rows], dtype=np.int64)
+    plus = s_start < s_end                                           # otherwise the reverse complement of [send, sstart] (:813)
+    idx = np.repeat(esub, eL) + k                                    # position in the matched (oriented) subject segment
+    gpos = soff[contig[ch_hit]] + np.where(plus[ch_hit], s_start[ch_hit] - 1 + idx, s_start[ch_hit] - 1 - idx)
+    gpos = np.where(ch_m, gpos, 0)
+    base = sbuf[gpos] if total else np.zeros(0, np.uint8)
+    ms = np.where(ch_m, np.where(plus[ch_hit], base, _COMP[base]), ord('-')).astype(np.uint8)
+
+    # longest stretch between in-frame stop codons, codons counted from the start of the matched string (:833)
+    ncod = ms_len // 3
+    cod_hit = np.repeat(np.arange(nh), ncod)
+    cod_k = np.arange(int(ncod.sum()), dtype=np.int64) - np.repeat(np.cumsum(ncod) - ncod, ncod)
+    c0 = ms_off[cod_hit] + 3 * cod_k
+    if len(c0):
+        a, b, c = ms[c0], ms[c0 + 1], ms[c0 + 2]
+        stop = (a == ord('T')) & (((b == ord('A')) & ((c == ord('A')) | (c == ord('G')))) | ((gtable != 4) & (b == ord('G')) & (c == ord('A'))))
+    else:
+        stop = np.zeros(0, dtype=bool)
+    sh, sp = cod_hit[stop], 3 * cod_k[stop]
+    prev = np.concatenate([[0], sp[:-1]]) if len(sp) else sp
+    prev = np.where(np.concatenate([[True], sh[1:] != sh[:-1]]) if len(sp) else np.zeros(0, bool), 0, prev)
+    sc2 = np.zeros(nh, dtype=np.int64); last = np.zeros(nh, dtype=np.int64)
+    np.maximum.at(sc2, sh, sp - prev); np.maximum.at(last, sh, sp)
+    sc2 = np.maximum(sc2, ms_len - last)
+    sc = np.minimum(sc, sc2 + 3)
+    enc = _BASE[ms]
+    return sc, [enc[ms_off[i]:ms_off[i + 1]] for i in range(nh)]
+
+
+def _passes(value, qlen, p):
+    return (value >= max(p['match_prop'] * qlen, p['match_len']) or value >= max(p['match_prop1'] * qlen, p['match_len1']) or
+            value >= max(p['match_prop2'] * qlen, p['match_len2']))
+
+
+def map_bsn_groups(blastab, overlap, seq, params, ortho_pairs=None):
+    nid = int(np.max(blastab.T[15])) + 1
+    ids = np.zeros(nid, dtype=bool)
+    singles, merged = [], {}
+    for tab in blastab:
+        g = tab[16]
+        if g[1] >= params['match_identity'] and _passes(g[2], tab[12], params):
+            ids[tab[15]] = True
+            if len(g) <= 4:
+                singles.append(tab[:2].tolist() + g[:2] + [None, 0, [tab[:16]]])
+            else:
+                if tab[2] >= params['match_identity'] and _passes(tab[7] - tab[6] + 1, tab[12], params):
+                    singles.append(tab[:2].tolist() + [tab[11], tab[2], None, 0, [tab[:16]]])
+                if g[3] not in merged:
+                    merged[g[3]] = tab[:2].tolist() + g[:2] + [None, 0, [[]] * (len(g) - 3)]
+                merged[g[3]][6][g[3:].index(tab[15])] = tab[:16]
+        else:
+            tab[2] = -1
+    groups = singles + list(merged.values())
+    overlap = overlap[ids[overlap.T[0]] & ids[overlap.T[1]], :2]
+    conv_a, conv_b = np.tile(-1, nid), np.tile(-1, nid)
+
+    members = [t for g in groups for t in g[6]]
+    sc, enc = score_hits(members, seq, params.get('gtable', 11))
+    qs = np.array([t[6] for t in members], dtype=np.int64); qe = np.array([t[7] for t in members], dtype=np.int64)
+    qlen = np.array([t[12] for t in members], dtype=np.int64)
+    iden = np.array([t[2] for t in members], dtype=np.float64); ovl = np.array([t[10] for t in members], dtype=np.float64)
+    scf = sc.astype(np.float64)
+    r = np.sqrt(scf / qlen * ovl)                                    # :838-840
+    msc = (sc * iden) * np.sqrt(sc * r)
+    amsc = msc / (qe - qs + 1)
+    at = 0
+    for gid, group in enumerate(groups):
+        n = len(group[6])
+        group[4] = np.zeros(group[6][0][12], dtype=np.uint8)
+        group[5] = gid
+        group[6] = np.array(group[6])
+        hit_ids = group[6].T[15].astype(int)
+        (conv_a if n == 1 else conv_b)[hit_ids] = gid
+        spans = []
+        for j in range(at, at + n):
+            group[4][qs[j] - 1:qs[j] + len(enc[j]) - 1] = enc[j]
+            spans.append([members[j][6], members[j][7], amsc[j], msc[j]])
+        # members of a merge group that overlap on the query: the better average score keeps the shared part (:842-850;
+        # np.max(x, 0) of a scalar is x itself -- the products are not clamped)
+        for i in range(1, n):
+            p, c = spans[i - 1], spans[i]
+            if c[0] < p[1]:
+                if c[2] > p[2]:
+                    p[1] = c[0] - 1; p[3] = np.max(p[2] * (p[1] - p[0] + 1), 0)
+                else:
+                    c[0] = p[1] + 1; c[3] = np.max(c[2] * (c[1] - c[0] + 1), 0)
+        group[2] = np.sum([c[3] for c in spans])
+        at += n
+    o0, o1 = overlap.T[0], overlap.T[1]
+    overlap = np.vstack([np.vstack([m, n]).T[(m >= 0) & (n >= 0)] for m in (conv_a[o0], conv_b[o0]) for n in (conv_a[o1], conv_b[o1])] +
+                        [np.vstack([conv_a, conv_b]).T[(conv_a >= 0) & (conv_b >= 0)]])
+    bsn = np.array(groups, dtype=object)
+    # three bases per byte, base 5, in thirds of the gene (:852-853)
+    for row in bsn:
+        b = row[4]; s = int(np.ceil(len(b) / 3))
+        row[4] = (b[:s] * 25 + b[s:2 * s] * 5 + np.concatenate([b, np.zeros(-b.shape[0] % 3, dtype=int)])[2 * s:]).astype(np.uint8)
+    if overlap.shape[0]:
+        og = ortho_pairs if ortho_pairs is not None else np.zeros([0, 3], dtype=int)
+        og = og[og.T[2] != 0] if len(og) else og
+        sign = {}
+        for a, b, v in og:
+            sign[(a, b)] = 1 if v > 0 else -1
+        for a, b, v in og:                                           # the mirrored pairs are entered after all direct ones (:856-859)
+            sign[(b, a)] = 1 if v > 0 else -1
+        ga, gb = bsn[overlap.T[0], 0], bsn[overlap.T[1], 0]
+        ovl_score = np.array([0 if m == n else sign.get((m, n), 2) for m, n in zip(ga, gb)], dtype=int)
+        overlap = np.hstack([overlap, ovl_score[:, np.newaxis]])
+        overlap = overlap[ovl_score >= 0]
+    else:
+        overlap = np.zeros([0, 3], dtype=np.int64)
+    return bsn, overlap

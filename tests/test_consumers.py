@@ -1,0 +1,106 @@
+"""N4: peppan_b200.consumers.map_bsn_groups against the REFERENCE'S OWN iter_map_bsn (PEPPAN.py:759-867) on the
+same blastab: the reference function runs on the uberBlast shim's output (module swap, search answered by the oracle as in
+tests/test_reference_consumer_cpu.py); the table compare_prediction hands to the grouping / scoring loop is captured and
+given to the columnar implementation, whose groups, scores, encoded sequences and overlap table must equal what the
+reference saved."""
+import os
+
+import numpy as np
+import pytest
+
+from peppan_b200 import consumers, uberBlast as ub, workloads
+from test_reference_consumer_cpu import PEPPAN, REF  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'PEPPAN.py')), reason='reference checkout not present')
+
+
+def _same(a, b):
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        a, b = np.asarray(a), np.asarray(b)
+        if a.shape != b.shape:
+            return False
+        if a.dtype == object or b.dtype == object:
+            return all(_same(x, y) for x, y in zip(a.reshape(-1), b.reshape(-1)))
+        return a.dtype == b.dtype and np.array_equal(a, b)
+    if isinstance(a, (list, tuple)):
+        return len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+@pytest.mark.parametrize('seed,identity', [(41, 0.5), (42, 0.9)])
+def test_columnar_grouping_and_scoring_equals_the_reference_loop(PEPPAN, oracle_as_search, monkeypatch, tmp_path, seed, identity):
+    monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)
+    if not hasattr(np.lib.npyio, 'format'):
+        monkeypatch.setattr(np.lib.npyio, 'format', np.lib.format, raising=False)
+    pool = workloads.GenePool(50, 50, seed=workloads.SEED + seed)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=25, seed=workloads.SEED + seed)
+    # cut the genome inside a gene so that the search returns fragments that linearMerge joins (merge groups of > 1 hit)
+    mid = annot[len(annot) // 2]
+    cut = (int(mid[1]) + int(mid[2])) // 2
+    contigs = [(1001, seq[:cut]), (1002, seq[cut:])]
+    clust = os.path.join(tmp_path, 'exemplar.fa')
+    with open(clust, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    old = os.path.join(tmp_path, 'old.npz')
+    store = PEPPAN.MapBsn(old, 'w')
+    rows = [[a[0], a[1] + 1, a[2], '+' if a[3] > 0 else '-'] for a in annot if a[2] <= cut]
+    store._save(store.conn, '1001', np.array(sorted(rows, key=lambda r: r[1]), dtype=object))
+    store.conn.close()
+    ortho = os.path.join(tmp_path, 'ortho.npy')
+    genes = sorted(set(int(a[0]) for a in annot))
+    pairs = np.array([[genes[i], genes[i + 1], (1 if i % 2 else -1) * 9000] for i in range(0, min(len(genes) - 1, 30))], dtype=int)
+    np.save(ortho, pairs, allow_pickle=True)
+    params = dict(gtable=11, noDiamond=False, match_identity=identity, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+    captured = {}
+    real_ub, real_cp = ub.uberBlast, PEPPAN.compare_prediction
+
+    def spy_ub(argv, *a, **k):
+        tab, ovl = real_ub(argv, *a, **k)
+        captured['ovl'] = ovl.copy()
+        return tab, ovl
+
+    def spy_cp(blastab, old_prediction):
+        out = real_cp(blastab, old_prediction)
+        captured['blastab'] = np.array([[(list(c) if isinstance(c, list) else c) for c in r] for r in out], dtype=object)
+        return out
+
+    monkeypatch.setattr(PEPPAN, 'uberBlast', spy_ub)
+    monkeypatch.setattr(PEPPAN, 'compare_prediction', spy_cp)
+    prefix = os.path.join(tmp_path, 'run')
+    out = PEPPAN.iter_map_bsn((prefix, clust, 0, 'taxon', contigs, ortho, old, params))
+    res = np.load(out + '.bsn.npz', allow_pickle=True)
+    ref_bsn, ref_ovl = res['bsn'], res['ovl']
+
+    bsn, ovl = consumers.map_bsn_groups(captured['blastab'], captured['ovl'], contigs, params, np.load(ortho, allow_pickle=True))
+    assert bsn.shape == ref_bsn.shape and len(bsn) >= 40
+    assert any(len(g[6]) > 1 for g in ref_bsn) or identity > 0.8        # merge groups are exercised at the permissive setting
+    for g, r in zip(bsn, ref_bsn):
+        assert g[0] == r[0] and g[1] == r[1] and g[5] == r[5]
+        assert g[2] == r[2] and g[3] == r[3], (g[:4], r[:4])            # group score: same floating-point operations, same value
+        assert g[4].dtype == np.uint8 and np.array_equal(g[4], r[4])
+        assert _same(g[6], r[6])
+    assert ovl.shape == ref_ovl.shape and np.array_equal(ovl, ref_ovl)
+
+
+def test_score_hits_handles_gaps_frames_and_stops():
+    # one hit with an insertion and a deletion on the minus strand, scored by hand
+    seq = [(7, 'AAACCCGGGTTTACGTACGTTAGCCCAAATTT')]
+    #        1-based 4..21 on the minus strand: rc('CCCGGGTTTACGTACGTT') = 'AACGTACGTAAACCCGGG'
+    row = [1, 7, 1.0, 0, 0, 0, 1, 19, 21, 4, 1.0, 0, 30, 32, '6M2I3M1D8M', 0]
+    sc, enc = consumers.score_hits([row], seq)
+    ms = 'AACGTA' + '--' + 'CGT' + 'AACCCGGG'        # the deletion skips one subject base ('A')
+    assert ''.join(' ACGT'[v] if v else '-' for v in enc[0]) == ms
+    # frames: 6 M in frame 0, +2 -> frame 2: 3 M, -1 -> frame 1: 8 M ; codons of ms: AAC GTA --C GTA ACC CGG (no stop) -> 19
+    assert int(sc[0]) == min(8, len(ms) + 3)
+    row2 = [1, 7, 1.0, 0, 0, 0, 1, 12, 10, 21, 1.0, 0, 30, 32, '12M', 0]      # plus strand: 'TTACGTACGTTA' holds TTA CGT ACG TTA: no stop
+    sc2, enc2 = consumers.score_hits([row2], seq)
+    assert int(sc2[0]) == 12 and len(enc2[0]) == 12
+    row3 = [1, 7, 1.0, 0, 0, 0, 1, 12, 11, 22, 1.0, 0, 30, 32, '12M', 0]      # 'TACGTACGTTAG': TAC GTA CGT TAG -> stop at 9: max(9, 3) + 3
+    sc3, _ = consumers.score_hits([row3], seq)
+    assert int(sc3[0]) == 12
+    row4 = [1, 7, 1.0, 0, 0, 0, 1, 15, 20, 34 - 2, 1.0, 0, 30, 32, '13M', 0]
+    seq4 = [(7, 'AAACCCGGGTTTACGTACGTAGCCCAAATTTGG')]                          # 20..32: 'TAGCCCAAATTTG': stop first -> spans 0 and 13
+    sc4, _ = consumers.score_hits([row4], seq4)
+    assert int(sc4[0]) == 13
