@@ -31,6 +31,7 @@ struct pb_ctx {
     size_t scratch_bytes[4] = {0, 0, 0, 0};
 };
 
+constexpr int PB_SMEM_OPTIN = 232448;        // opt-in dynamic shared memory per block on sm_100 (227 KB)
 void pb_set_error(pb_ctx* ctx, const char* fmt, ...);
 // grow-only scratch slot `k` of the context with at least `bytes` (cudaMalloc; the previous block is freed after the stream drains)
 int pb_scratch(pb_ctx* ctx, int k, size_t bytes, void** out);

@@ -126,7 +126,10 @@ template <int G, int K, int R, bool LONG, int WARPS, bool PACKED, bool REV, bool
 cudaError_t sw_launch_one(const SwArgs& a, int grid, size_t smem, cudaStream_t st)
 {
     auto k = sw_kernel<G, K, R, LONG, PACKED, REV, WARPS, WAVE, MULTI>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // The limit is a property of the FUNCTION, shared by every context and host thread of the process: it is only ever set to
+    // the device maximum, never to the size of one launch (a smaller value set by a concurrent nucleotide search would make
+    // the launch of a protein search fail).
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM_OPTIN);
     if (e != cudaSuccess) return e;
     k<<<grid, WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
@@ -137,7 +140,7 @@ cudaError_t sw_launch_combo(const SwArgs& aw, const SwArgs& ar, int grid, size_t
 {
     auto k = sw_combo_kernel<16, 19, 2, WAVE_G, WAVE_K, WAVE_R, PACKED, REV, 8>;
     static_assert(WAVE_WARPS == 8, "one block shape for both bodies");
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM_OPTIN);
     if (e != cudaSuccess) return e;
     k<<<grid, 8 * 32, smem, st>>>(aw, ar, stride);
     return cudaGetLastError();

@@ -505,7 +505,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
     size_t smem_c[3]; int grid_c[3];
     for (int k = 0; k < 3 && !chunks.empty(); ++k) {
         smem_c[k] = smem_of(tb_shape(k));
-        PB_CUDA(ctx, cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c[k]));
+        PB_CUDA(ctx, cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM_OPTIN));      // function-wide: see pb_sw.cu
         int occ = 1;
         PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], TB_WARPS * 32, smem_c[k]));
         grid_c[k] = ctx->sm_count * std::max(1, std::min(occ, 2));

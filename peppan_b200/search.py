@@ -83,11 +83,10 @@ def _take(out):
     return hits, cigar
 
 
-def search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0,
-                       allgather=False):
-    """pb_search_grouped: many genomes in one call.  Returns (hits, cigar, group_off, stats): the concatenated table in group
-    order, s_id = index into the concatenated target set.  allgather: the table is then merged over the ranks of the context
-    (pb_allgather_hits, one exchange for the whole batch); group_off stays this rank's, stats['rank_offsets'] delimits the ranks."""
+def search_grouped_local(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0):
+    """pb_search_grouped without taking the result: returns (Hits struct still owned by the library, group_off, stats).  The
+    struct goes to `take_hits` -- possibly on another thread and, for the exchange, with another context (the buffers are
+    plain host memory)."""
     bind(ctx.lib)
     q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8); t_bytes = np.ascontiguousarray(t_bytes, dtype=np.uint8)
     q_off = np.ascontiguousarray(q_off, dtype=np.int64); t_off = np.ascontiguousarray(t_off, dtype=np.int64)
@@ -101,14 +100,33 @@ def search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id
     goff = np.zeros(ng + 1, np.int64)
     ctx.check(ctx.lib.pb_search_grouped(ctx.h, C.byref(qs), C.byref(ts), ptr(groups), ng, C.byref(prm), C.byref(out), ptr(goff), C.byref(st)),
               'pb_search_grouped')
-    d = st.as_dict()
+    return out, goff, st.as_dict()
+
+
+def take_hits(ctx, out, allgather=False):
+    """(hits, cigar, rank_offsets or None) of a Hits struct, which is released.  allgather: merged over the ranks of `ctx`
+    first (pb_allgather_hits, one exchange for the whole table)."""
+    bind(ctx.lib)
+    rank_off = None
     try:
         if allgather:
             ctx.check(ctx.lib.pb_allgather_hits(ctx.h, C.byref(out)), 'pb_allgather_hits')
-            d['rank_offsets'] = np.frombuffer((C.c_char * ((out.n_ranks + 1) * 8)).from_address(out.rank_offsets), dtype=np.int64).copy() if out.rank_offsets else None
+            rank_off = np.frombuffer((C.c_char * ((out.n_ranks + 1) * 8)).from_address(out.rank_offsets), dtype=np.int64).copy() if out.rank_offsets else None
         hits, cigar = _take(out)
     finally:
         ctx.lib.pb_free_hits(C.byref(out))
+    return hits, cigar, rank_off
+
+
+def search_grouped_raw(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id=0.3, min_cov=40., min_ratio=0.05, gtable=11, max_hits=0,
+                       allgather=False):
+    """pb_search_grouped: many genomes in one call.  Returns (hits, cigar, group_off, stats): the concatenated table in group
+    order, s_id = index into the concatenated target set.  allgather: the table is then merged over the ranks of the context
+    (pb_allgather_hits, one exchange for the whole batch); group_off stays this rank's, stats['rank_offsets'] delimits the ranks."""
+    out, goff, d = search_grouped_local(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_id, min_cov, min_ratio, gtable, max_hits)
+    hits, cigar, rank_off = take_hits(ctx, out, allgather)
+    if allgather:
+        d['rank_offsets'] = rank_off
     return hits, cigar, goff, d
 
 

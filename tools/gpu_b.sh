@@ -1,6 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/b_pytest.log 2>&1
-tail -3 gpurun_out/b_pytest.log
-for i in 1 2; do PB_DEBUG_TIMING=1 timeout 300 python tools/prof_trace.py 16 1,2 3 2>&1 | grep "device:" | cut -c1-200; done
-timeout 300 python tools/bench_sw.py 1000000 5
+for w in 1 2 3; do (time timeout 900 python bench.py --config 4 --no-cpu-baseline --workers $w --steps 2) > gpurun_out/b_bench_w$w.log 2>&1; grep -o '"config4": {"workload.\{0,700\}' gpurun_out/b_bench_w$w.log | cut -c1-900; done
