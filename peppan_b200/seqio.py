@@ -53,3 +53,24 @@ def to_seqset(seqs):
         off[1:] = np.cumsum([len(s) for _, s in items])
     buf = np.frombuffer(''.join(s for _, s in items).encode(), dtype=np.uint8) if off[-1] else np.zeros(0, np.uint8)
     return names, np.ascontiguousarray(buf), off
+
+
+# The callers of uberBlast hand the same query file to every call (PEPPAN.py:771: one exemplar file, one call per genome);
+# parsing it is most of a call's host time once the search runs on the GPU.  The last few files are kept, keyed by path,
+# size and modification time; the dicts are shared between calls and must not be modified by the caller.
+_CACHE, _CACHE_MAX = {}, 4
+
+
+def read_fastq_cached(path):
+    """-> (dict name -> sequence, (names, bytes, offsets) of to_seqset) for `path`, parsed once per file version"""
+    import os
+    st = os.stat(path)
+    key = (os.path.realpath(path), st.st_size, st.st_mtime_ns)
+    hit = _CACHE.pop(key, None)
+    if hit is None:
+        seqs = read_fastq(path)
+        hit = (seqs, to_seqset(seqs))
+    _CACHE[key] = hit                       # most recently used last
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.pop(next(iter(_CACHE)))
+    return hit

@@ -77,15 +77,17 @@ def rows_from_prot_hits(hits, cigar, qn, rn, min_id):
     """15-column rows of parseDiamond (:16-70) from protein-mode records: identity 1 - round(3 NM / columns, 3) (:38),
     mismatch = 3 NM - gap bases, gapopen = number of gap runs (:55-58), e-value forced to 0.0"""
     c, cg, cl, gapb, ngap = _hit_columns(hits, cigar)
+    # 3 * NM; parseDiamond rounds a numpy scalar (cl is np.int64 there): numpy's multiply-rint-divide rounding, which differs
+    # from Python's round() on half-way quotients such as 3/240 = 0.0125 (:38) -- the array form rounds the same way
+    variation = np.asarray(c['mismatch'], dtype=np.float64) + np.asarray(gapb, dtype=np.float64)
+    iden_all = (1 - np.round(variation / np.asarray(cl, dtype=np.int64), 3)).tolist() if len(hits) else []
+    var_l = variation.tolist()
     rows = []
     for i in range(len(hits)):
-        variation = float(c['mismatch'][i] + gapb[i])          # 3 * NM
-        # parseDiamond rounds a numpy scalar (cl is np.int64 there): numpy's multiply-rint-divide rounding, which differs from
-        # Python's round() on half-way quotients such as 3/240 = 0.0125 (:38)
-        iden = 1 - float(np.round(np.float64(variation) / np.int64(cl[i]), 3))
+        iden = iden_all[i]
         if iden < min_id:
             continue
-        rows.append([qn[c['q_id'][i]], rn[c['s_id'][i]], iden, cl[i], int(variation - gapb[i]), ngap[i], c['q_start'][i], c['q_end'][i],
+        rows.append([qn[c['q_id'][i]], rn[c['s_id'][i]], iden, cl[i], int(var_l[i] - gapb[i]), ngap[i], c['q_start'][i], c['q_end'][i],
                      c['s_start'][i], c['s_end'][i], 0.0, c['raw_score'][i], c['q_len'][i], c['s_len'][i], cg[i]])
     return rows
 
@@ -100,14 +102,16 @@ class RunBlast(object):
     # ---- tools ---------------------------------------------------------------------------------
     def _load(self, ref, qry):
         if not self.qrySeq:
-            self.qrySeq = seqio.read_fastq(qry)
+            self.qrySeq, self._qset = seqio.read_fastq_cached(qry)
         if not self.refSeq:
-            self.refSeq = seqio.read_fastq(ref)
+            self.refSeq, self._rset = seqio.read_fastq_cached(ref)
 
     def _sets(self):
-        """(names, ASCII buffer, offsets) of queries and references, built once per run"""
+        """(names, ASCII buffer, offsets) of queries and references, built once per file version (seqio.read_fastq_cached)"""
         if getattr(self, '_qset', None) is None:
-            self._qset = seqio.to_seqset(self.qrySeq); self._rset = seqio.to_seqset(self.refSeq)
+            self._qset = seqio.to_seqset(self.qrySeq)
+        if getattr(self, '_rset', None) is None:
+            self._rset = seqio.to_seqset(self.refSeq)
         return self._qset, self._rset
 
     def _search(self, mode):
