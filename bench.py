@@ -299,7 +299,7 @@ def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cp
     ng = len(genomes)
     nsteps = int(allmax(pg, float((ng + batch - 1) // batch)))
     modes = (('nt', search.MODE_NT), ('prot6', search.MODE_PROT6))
-    gather = world > 1
+    gather = world > 1 and not os.environ.get('PB_BENCH_NO_GATHER')        # diagnosis aid: shards without the exchange
 
     # One worker context per mode on this rank's GPU, each driven by its own host thread -- the way the reference itself
     # runs this stage (a pool of workers, each calling uberBlast; PEPPAN.py:922): while one context's host code builds
@@ -309,6 +309,10 @@ def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cp
     from peppan_b200._lib import Context
     wctx = [[Context(ctx.device) for _ in range(nworkers)] for _ in modes]
     pools = [[ThreadPoolExecutor(max_workers=1) for _ in range(nworkers)] for _ in modes]
+    if gather:
+        for ws in wctx:
+            for w in ws:
+                w.reserve_sms(4)            # room for the exchange kernels of the communicator context
 
     def batch_views(bi):
         g0, g1 = min(bi * batch, ng), min((bi + 1) * batch, ng)
@@ -330,6 +334,11 @@ def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cp
         return (hits, cig, goff, st), batch_views(bi)[3]
 
     # ---- warm-up on the first batch + verification of the exchange (untimed) ----
+    # every worker context runs one batch before the clock starts (scratch buffers, kernel modules)
+    for f in [pools[mi][w].submit(search.search_grouped_local, wctx[mi][w], qpin, qo, *batch_views(0)[:3], modes[mi][1], **THRESH)
+              for mi in range(len(modes)) for w in range(nworkers)]:
+        o, _g, _s = f.result()
+        search.take_hits(ctx, o, False)
     verified = None
     recovered = None
     isolated = {}
@@ -370,11 +379,15 @@ def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cp
     kept = []
     barrier(pg)
     t0 = time.perf_counter()
+    t_wait = t_xchg = 0.0
     futs = [[submit(bi, mi) for mi in range(len(modes))] for bi in range(nsteps)]       # both workers start at once
     for bi in range(nsteps):
         for mi, (k, m) in enumerate(modes):
+            w0 = time.perf_counter()
             out, goff, st = futs[bi][mi].result(); futs[bi][mi] = None
+            w1 = time.perf_counter()
             hits, cig, roff = search.take_hits(ctx, out, gather)
+            t_wait += w1 - w0; t_xchg += time.perf_counter() - w1
             launches += st['kernel_launches']
             a = acc[k]
             for f in ('ms_encode', 'ms_index', 'ms_seed', 'ms_sw', 'ms_trace', 'ms_total', 'sw_cells', 'n_windows', 'n_seed_hits', 'algo_bytes_seed'):
@@ -404,7 +417,7 @@ def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cp
            'genomes_per_s': n_total / wall, 'genes_per_s': n_total * nq / wall, 'ms_per_genome': 1e3 * wall / max(n_total, 1),
            'ms_per_genome_per_gpu': 1e3 * wall / max(ng, 1), 'h2d_bytes_per_genome': int(2 * (genome_bp + len(qpin) / max(batch, 1))),
            'gpu_launches': launches, 'allgather': 'nccl, one per batch and mode' if gather else None, 'allgather_verified': verified,
-           'planted_genes_recovered_ge80pct_span_first_batch': recovered, 'timing': 'host wall clock around the C-ABI calls, barrier on both sides, max over ranks'}
+           'planted_genes_recovered_ge80pct_span_first_batch': recovered, 'rank0_seconds_waiting_for_workers': t_wait, 'rank0_seconds_in_exchange_and_copy': t_xchg, 'timing': 'host wall clock around the C-ABI calls, barrier on both sides, max over ranks'}
     hbm, _ = hbm_peak()
     for k, _ in modes:
         a = acc[k]

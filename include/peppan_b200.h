@@ -68,6 +68,9 @@ int  pb_device_info(pb_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int64_t*
  * pool and the pool never shrinks, so calls that follow do not pay for growing it (growing costs tens of ms per GB, more
  * than a search of a genome).  Long-running callers (one context per worker, PEPPAN.py:922) reserve once at start-up. */
 int  pb_reserve(pb_ctx* ctx, int64_t bytes);
+/* Leave `n` SMs free of this context's persistent kernels (default 0).  For worker contexts that share a device with a
+ * context carrying the NCCL communicator: the exchange kernels then never wait for a bulk kernel to end. */
+int  pb_reserve_sms(pb_ctx* ctx, int32_t n);
 
 /* ---- batched Smith-Waterman (gapped extension) --------------------------------------- */
 /* Replaces the gapped-extension + traceback arithmetic inside blastn (modules/uberBlast.py:294-296)

@@ -47,6 +47,7 @@ def load():
     lib.pb_nccl_unique_id.argtypes = [vp]
     lib.pb_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     lib.pb_reserve.argtypes = [vp, i64]
+    lib.pb_reserve_sms.argtypes = [vp, i32]
     lib.pb_sw_batch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ScoreParams), vp, vp, vp, vp, vp,
                                 C.POINTER(SwStats)]
     lib.pb_sw_align_batch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ScoreParams), vp, vp, vp, vp, vp, vp, vp,
@@ -97,6 +98,10 @@ class Context(object):
     def reserve(self, nbytes):
         """pb_reserve: let the context's device memory pool hold `nbytes` now, so that later calls do not grow it"""
         self.check(self.lib.pb_reserve(self.h, int(nbytes)), 'pb_reserve')
+
+    def reserve_sms(self, n):
+        """pb_reserve_sms: keep `n` SMs free of this context's persistent kernels (for a communicator context on the same device)"""
+        self.check(self.lib.pb_reserve_sms(self.h, int(n)), 'pb_reserve_sms')
 
     def dpx_peak(self, which=0):
         v = C.c_double()

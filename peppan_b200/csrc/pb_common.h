@@ -12,6 +12,7 @@
 struct pb_ctx {
     int device = 0, rank = 0, world = 1;
     int sm_count = 0, clock_khz = 0;
+    int sm_avail = 0;               // SMs the persistent kernels of this context fill: sm_count minus pb_reserve_sms
     size_t smem_optin = 0;
     int64_t hbm_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -27,8 +28,8 @@ struct pb_ctx {
     void* memo = nullptr;           // PairMemo* of the clustering path (pb_memo.h), created on first use
     // grow-only device scratch of the traceback (direction planes, block borders per shape class): sizes change from call to
     // call, and growing the stream-ordered pool each time costs far more than the kernels (pb_trace.cu)
-    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[4] = {0, 0, 0, 0};
+    void* scratch[8] = {};          // 0-3 traceback, 4-6 hit-table exchange
+    size_t scratch_bytes[8] = {};
 };
 
 constexpr int PB_SMEM_OPTIN = 232448;        // opt-in dynamic shared memory per block on sm_100 (227 KB)

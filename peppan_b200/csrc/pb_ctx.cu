@@ -1,5 +1,6 @@
 // Context management, error reporting and NCCL plumbing of libpeppan_b200.
 #include "pb_common.h"
+#include <chrono>
 #include "pb_memo.h"
 #include <cstdarg>
 #include <dlfcn.h>
@@ -83,10 +84,17 @@ extern "C" int pb_init(int device, int rank, int world, const void* nccl_uid, pb
         pb_set_error(nullptr, "pb_init: device '%s' is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
         delete ctx; return PB_ERR_NODEVICE;
     }
-    ctx->sm_count = prop.multiProcessorCount;
+    ctx->sm_count = prop.multiProcessorCount; ctx->sm_avail = ctx->sm_count;
     ctx->clock_khz = prop.clockRate;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->hbm_bytes = (int64_t)prop.totalGlobalMem;
+    if (world > 1) {
+        // the context of a communicator: its (short) exchange kernels should not queue behind the bulk kernels of worker
+        // contexts on the same device
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
+    } else
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
@@ -177,6 +185,13 @@ extern "C" int pb_reserve(pb_ctx* ctx, int64_t bytes)
     return PB_OK;
 }
 
+extern "C" int pb_reserve_sms(pb_ctx* ctx, int32_t n)
+{
+    if (!ctx || n < 0 || n >= ctx->sm_count) { pb_set_error(ctx, "pb_reserve_sms: invalid argument"); return PB_ERR_ARG; }
+    ctx->sm_avail = ctx->sm_count - n;
+    return PB_OK;
+}
+
 extern "C" int pb_cluster_forget(pb_ctx* ctx)
 {
     if (!ctx) return PB_ERR_ARG;
@@ -213,9 +228,16 @@ extern "C" int pb_allgather_hits(pb_ctx* ctx, pb_hits* io)
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int W = ctx->world;
     cudaStream_t sm = ctx->stream;
+    const bool dbg = getenv("PB_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    // Device buffers of the exchange are the context's own (grow-only), not taken from the stream-ordered pool: the pool is
+    // shared with the worker contexts of the device, and a block handed from this stream to a worker's stream would make the
+    // worker wait for this stream -- which may sit in a collective until the slowest rank arrives.
     // 1. counts
-    DevBuf d_cnt, d_cnts;
-    PB_CUDA(ctx, d_cnt.alloc(16, sm)); PB_CUDA(ctx, d_cnts.alloc(16 * W, sm));
+    void* p_cnt = nullptr;
+    { const int rc0 = pb_scratch(ctx, 4, 16 + 16 * (size_t)W, &p_cnt); if (rc0) return rc0; }
+    struct { void* p; } d_cnt{p_cnt}, d_cnts{(char*)p_cnt + 16};
     int64_t mine[2] = {io->n_hits, io->n_cigar};
     PB_CUDA(ctx, cudaMemcpyAsync(d_cnt.p, mine, 16, cudaMemcpyHostToDevice, sm));
     int rc = allgather(d_cnt.p, d_cnts.p, 2, 4 /* ncclInt64 */, ctx->nccl_comm, sm);
@@ -223,20 +245,28 @@ extern "C" int pb_allgather_hits(pb_ctx* ctx, pb_hits* io)
     std::vector<int64_t> all(2 * W);
     PB_CUDA(ctx, cudaMemcpyAsync(all.data(), d_cnts.p, 16 * W, cudaMemcpyDeviceToHost, sm));
     PB_CUDA(ctx, cudaStreamSynchronize(sm));
+    const double t1 = now();
     int64_t maxh = 0, maxc = 0, toth = 0, totc = 0;
     for (int r = 0; r < W; ++r) { maxh = std::max(maxh, all[2 * r]); maxc = std::max(maxc, all[2 * r + 1]); toth += all[2 * r]; totc += all[2 * r + 1]; }
     // 2. fixed-width records and 3. CIGAR side buffer, padded to the largest rank
     const size_t hb = (size_t)std::max<int64_t>(maxh, 1) * sizeof(pb_hit), cb = (size_t)std::max<int64_t>(maxc, 1) * 4;
-    DevBuf d_h, d_hall, d_c, d_call;
-    PB_CUDA(ctx, d_h.alloc(hb, sm)); PB_CUDA(ctx, d_hall.alloc(hb * W, sm));
-    PB_CUDA(ctx, d_c.alloc(cb, sm)); PB_CUDA(ctx, d_call.alloc(cb * W, sm));
+    void *p_h = nullptr, *p_c = nullptr;
+    { const int rc0 = pb_scratch(ctx, 5, hb * (size_t)(W + 1), &p_h); if (rc0) return rc0; }
+    { const int rc0 = pb_scratch(ctx, 6, cb * (size_t)(W + 1), &p_c); if (rc0) return rc0; }
+    struct { void* p; } d_h{p_h}, d_hall{(char*)p_h + hb}, d_c{p_c}, d_call{(char*)p_c + cb};
     PB_CUDA(ctx, cudaMemsetAsync(d_h.p, 0, hb, sm)); PB_CUDA(ctx, cudaMemsetAsync(d_c.p, 0, cb, sm));
     if (io->n_hits) PB_CUDA(ctx, cudaMemcpyAsync(d_h.p, io->hits, (size_t)io->n_hits * sizeof(pb_hit), cudaMemcpyHostToDevice, sm));
     if (io->n_cigar) PB_CUDA(ctx, cudaMemcpyAsync(d_c.p, io->cigar, (size_t)io->n_cigar * 4, cudaMemcpyHostToDevice, sm));
+    // records and CIGARs in one grouped call: one kernel launch for both (the context may share the device with bulk
+    // kernels of other contexts, and every launch waits for SMs)
+    typedef int (*nccl_group_fn)();
+    auto gstart = (nccl_group_fn)dlsym(ctx->nccl_dl, "ncclGroupStart");
+    auto gend = (nccl_group_fn)dlsym(ctx->nccl_dl, "ncclGroupEnd");
+    if (gstart && gend) gstart();
     rc = allgather(d_h.p, d_hall.p, hb, 0 /* ncclInt8 */, ctx->nccl_comm, sm);
-    if (rc) { pb_set_error(ctx, "ncclAllGather(hits) failed (%d)", rc); return PB_ERR_NCCL; }
-    rc = allgather(d_c.p, d_call.p, cb, 0, ctx->nccl_comm, sm);
-    if (rc) { pb_set_error(ctx, "ncclAllGather(cigar) failed (%d)", rc); return PB_ERR_NCCL; }
+    int rc2 = allgather(d_c.p, d_call.p, cb, 0, ctx->nccl_comm, sm);
+    if (gstart && gend) { const int rc3 = gend(); if (!rc && !rc2) rc = rc3; }
+    if (rc || rc2) { pb_set_error(ctx, "ncclAllGather(hits / cigar) failed (%d, %d)", rc, rc2); return PB_ERR_NCCL; }
     pb_hit* hits = (pb_hit*)malloc((size_t)std::max<int64_t>(toth, 1) * sizeof(pb_hit));
     uint32_t* cig = (uint32_t*)malloc((size_t)std::max<int64_t>(totc, 1) * 4);
     int64_t* roff = (int64_t*)malloc((size_t)(W + 1) * 8);
@@ -250,8 +280,11 @@ extern "C" int pb_allgather_hits(pb_ctx* ctx, pb_hits* io)
         ho += nh; co += ncg;
     }
     roff[W] = ho;
+    const double t2 = now();
     cudaError_t e = cudaStreamSynchronize(sm);
     if (e != cudaSuccess) { free(hits); free(cig); free(roff); pb_set_error(ctx, "pb_allgather_hits: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    if (dbg) fprintf(stderr, "[pb_allgather_hits] rank %d: counts exchange %.1f ms, staging + launches %.1f ms, payload wait %.1f ms (%lld hits mine, %lld total)\n",
+                     ctx->rank, t1 - t0, t2 - t1, now() - t2, (long long)io->n_hits, (long long)toth);
     // rebase the CIGAR offsets of every rank's records
     co = 0;
     for (int r = 0; r < W; ++r) {

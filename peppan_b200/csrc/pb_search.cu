@@ -934,7 +934,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         PB_CUDA(ctx, cudaMemsetAsync(d_cnt.as<unsigned long long>() + 1, 0, 24, sm));
         int occ = 1;
         PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seed_scan_kernel, SCAN_THREADS, 0));
-        const int grid = (int)std::min<int64_t>((LT + SCAN_TILE - 1) / SCAN_TILE, (int64_t)ctx->sm_count * std::max(occ, 1));
+        const int grid = (int)std::min<int64_t>((LT + SCAN_TILE - 1) / SCAN_TILE, (int64_t)ctx->sm_avail * std::max(occ, 1));
         seed_scan_kernel<<<grid, SCAN_THREADS, 0, sm>>>(d_tc.as<uint8_t>(), LT, qc, LQ, d_table.as<uint32_t>(), d_keys.as<uint32_t>(),
                                                          d_vals2.as<uint32_t>(), ds, d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap,
                                                          d_cnt.as<unsigned long long>() + 2, d_longq.as<SeedQ>(), d_cnt.as<unsigned long long>() + 3);
@@ -943,7 +943,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         PB_CUDA(ctx, cudaStreamSynchronize(sm));
         if (cnts[3] <= cap && cnts[3] > 0) {
             const unsigned long long nlong = cnts[3];
-            const int xgrid = (int)std::min<unsigned long long>((nlong + 7) / 8, (unsigned long long)ctx->sm_count * 8);
+            const int xgrid = (int)std::min<unsigned long long>((nlong + 7) / 8, (unsigned long long)ctx->sm_avail * 8);
             xdrop_warp_kernel<<<xgrid, 256, 0, sm>>>(d_tc.as<uint8_t>(), LT, qc, LQ, ds, d_longq.as<SeedQ>(), nlong,
                                                      d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap);
             PB_CUDA(ctx, cudaGetLastError()); ++launches;

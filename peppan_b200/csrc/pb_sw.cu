@@ -172,7 +172,7 @@ static int sw_launch(pb_ctx* ctx, pb_sw_job* J, bool rev, const PairDesc* desc, 
     const int n32 = meta[0], n32L = meta[3], n16L = meta[4];
     J->n32 = n32;
     int bstride = meta[2] > 1 ? ((meta[1] + 63) / 64) * 64 : 0;
-    const int grid = ctx->sm_count;
+    const int grid = ctx->sm_avail;
     if (bstride > 0) {
         size_t need = (size_t)grid * c.WARPS * (32 / c.G) * bstride * sizeof(uint2);
         if (J->boundary.bytes < need) PB_CUDA(ctx, J->boundary.alloc(need, ctx->stream));

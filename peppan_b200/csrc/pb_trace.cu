@@ -508,7 +508,7 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         PB_CUDA(ctx, cudaFuncSetAttribute(kern[k], cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM_OPTIN));      // function-wide: see pb_sw.cu
         int occ = 1;
         PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern[k], TB_WARPS * 32, smem_c[k]));
-        grid_c[k] = ctx->sm_count * std::max(1, std::min(occ, 2));
+        grid_c[k] = ctx->sm_avail * std::max(1, std::min(occ, 2));
     }
     chunk_ops.resize(chunks.size()); chunk_ooff.resize(chunks.size());
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
@@ -539,15 +539,15 @@ int pb_sw_trace(pb_ctx* ctx, pb_sw_job* J, const int64_t* qbeg, const int64_t* t
         int side_sms[3] = {0, 0, 0};
         size_t first = 0;
         TraceArgs narrow_args; bool have_narrow = false; int narrow_main = 0;
-        const int occ0 = std::max(1, grid_c[0] / ctx->sm_count);
+        const int occ0 = std::max(1, grid_c[0] / ctx->sm_avail);
         for (int k = 2; k >= 0; --k) {
             const size_t cnt = c.ncls[k];
             if (cnt == 0) continue;
             const int NG = 32 / tb_shape(k).G;
-            const int occk = std::max(1, grid_c[k] / ctx->sm_count);
+            const int occk = std::max(1, grid_c[k] / ctx->sm_avail);
             const bool fork = k > 0 && cnt < c.count;      // the few long / wide pairs run beside the rest on their own streams
             int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid_c[k], (cnt + (size_t)TB_WARPS * NG - 1) / ((size_t)TB_WARPS * NG)));
-            if (fork) { grid = std::min(grid, std::max(1, ctx->sm_count / 8) * occk); side_sms[k] = (grid + occk - 1) / occk; }
+            if (fork) { grid = std::min(grid, std::max(1, ctx->sm_avail / 8) * occk); side_sms[k] = (grid + occk - 1) / occk; }
             // border rows for every block that may run with this counter (main + helper launches of the narrow kernel)
             { const int rc = pb_scratch(ctx, 1 + k, (size_t)(k == 0 ? grid_c[0] : grid) * TB_WARPS * NG * bstride * sizeof(uint2), &dbound[k]); if (rc) return rc; }
             TraceArgs r = a;

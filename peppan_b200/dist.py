@@ -37,6 +37,11 @@ def init_context_from_env(backend_pg=None):
         return Context(local)
     if backend_pg is None:
         raise ValueError('world > 1 needs a process group to distribute the NCCL unique id')
+    # The exchanges of this path are small (a few MB per batch of genomes) and run BESIDE the search kernels of worker
+    # contexts; a rank that arrives early spins in the collective until its peers arrive.  Two channels (= two thread blocks)
+    # keep that wait off the SMs the searches need; the caller's own setting wins.
+    os.environ.setdefault('NCCL_MAX_NCHANNELS', '2')
+    os.environ.setdefault('NCCL_MIN_NCHANNELS', '1')
     obj = [nccl_unique_id() if rank == 0 else None]
     backend_pg.broadcast_object_list(obj, src=0)
     return Context(local, rank, world, obj[0])
