@@ -386,7 +386,7 @@ def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cp
             w0 = time.perf_counter()
             out, goff, st = futs[bi][mi].result(); futs[bi][mi] = None
             w1 = time.perf_counter()
-            hits, cig, roff = search.take_hits(ctx, out, gather)
+            hits, cig, roff = search.take_hits(ctx, out, gather, copy=not gather)
             t_wait += w1 - w0; t_xchg += time.perf_counter() - w1
             launches += st['kernel_launches']
             a = acc[k]
@@ -395,7 +395,7 @@ def config4_leg(ctx, rank, world, pg, genomes, n_total, qpin, qo, batch, with_cp
             a['hits'] = a.get('hits', 0) + int(len(hits))
             if gather:
                 # cheap order-sensitive fingerprint per exchange (the first batch was compared byte for byte above)
-                hb = np.frombuffer(np.ascontiguousarray(hits).tobytes(), dtype=np.uint32)
+                hb = np.frombuffer(hits, dtype=np.uint32)           # 68-byte records: a whole number of words, no copy
                 kept.update(np.array([len(hits), len(cig), int(hb.sum(dtype=np.uint64)), int(hb[::17].sum(dtype=np.uint64)),
                                       int(np.asarray(cig).sum(dtype=np.uint64))], dtype=np.uint64).tobytes())
     barrier(pg)

@@ -103,18 +103,44 @@ def search_grouped_local(ctx, q_bytes, q_off, t_bytes, t_off, groups, mode, min_
     return out, goff, st.as_dict()
 
 
-def take_hits(ctx, out, allgather=False):
-    """(hits, cigar, rank_offsets or None) of a Hits struct, which is released.  allgather: merged over the ranks of `ctx`
-    first (pb_allgather_hits, one exchange for the whole table)."""
+class _Owned(object):
+    """keeps a library-owned Hits struct alive for the arrays that view it; released with the last of them"""
+
+    def __init__(self, lib, out):
+        self.lib, self.out = lib, out
+
+    def __del__(self):
+        try:
+            self.lib.pb_free_hits(C.byref(self.out))
+        except Exception:
+            pass
+
+
+def take_hits(ctx, out, allgather=False, copy=True):
+    """(hits, cigar, rank_offsets or None) of a Hits struct.  allgather: merged over the ranks of `ctx` first
+    (pb_allgather_hits, one exchange for the whole table).  copy=False: the arrays are read-only views of the library's
+    buffers, which live as long as the arrays do (large gathered tables: no second copy)."""
     bind(ctx.lib)
     rank_off = None
     try:
         if allgather:
             ctx.check(ctx.lib.pb_allgather_hits(ctx.h, C.byref(out)), 'pb_allgather_hits')
             rank_off = np.frombuffer((C.c_char * ((out.n_ranks + 1) * 8)).from_address(out.rank_offsets), dtype=np.int64).copy() if out.rank_offsets else None
+        if not copy and out.n_hits:
+            owner = _Owned(ctx.lib, out)
+            hb = (C.c_char * (out.n_hits * HIT_DTYPE.itemsize)).from_address(out.hits); hb._owner = owner
+            hits = np.frombuffer(hb, dtype=HIT_DTYPE)
+            if out.n_cigar:
+                cb = (C.c_char * (out.n_cigar * 4)).from_address(out.cigar); cb._owner = owner
+                cigar = np.frombuffer(cb, dtype=np.uint32)
+            else:
+                cigar = np.zeros(0, np.uint32)
+            out = None
+            return hits, cigar, rank_off
         hits, cigar = _take(out)
     finally:
-        ctx.lib.pb_free_hits(C.byref(out))
+        if out is not None:
+            ctx.lib.pb_free_hits(C.byref(out))
     return hits, cigar, rank_off
 
 
