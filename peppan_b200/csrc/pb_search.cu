@@ -330,12 +330,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) seed_scan_kernel(const uint8_
                     qpos = __ldg(vals + en.y);
                     // leftmost seed of a match run only: if the preceding residues agree in the seed alphabet the preceding
                     // k-mer is a seed on the same diagonal and extends to the same HSP (position 0 of both arrays is a sentinel)
-                    const uint8_t pa = __ldg(qcodes + qpos - 1), pb = tl[pos - 1];
+                    uint8_t pa;
+                    uint32_t u0 = 0, u1 = 0;            // query residues qpos .. qpos + 6 in bytes 1-3 of u0 and 0-3 of u1 (K <= 7)
+                    if (exact_seed || K > 7) pa = __ldg(qcodes + qpos - 1);
+                    else {
+                        // the residue before the seed and the seed itself: 8 bytes at any alignment from two 64-bit loads
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(qcodes + qpos - 1);
+                        const uint2* wp = reinterpret_cast<const uint2*>(a & ~(uintptr_t)7);
+                        const uint2 r0 = __ldg(wp), r1 = __ldg(wp + 1);
+                        const bool odd = (a & 4) != 0;
+                        const uint32_t x0 = odd ? r0.y : r0.x, x1 = odd ? r1.x : r0.y, x2 = odd ? r1.y : r1.x;
+                        const uint32_t sh = ((uint32_t)a & 3u) * 8u;
+                        u0 = __funnelshift_r(x0, x1, sh); u1 = __funnelshift_r(x1, x2, sh);
+                        pa = (uint8_t)(u0 & 0xffu);
+                    }
+                    const uint8_t pb = tl[pos - 1];
                     const uint8_t sa = pa < 32 ? sp.seedmap[pa] : 255, sb = pb < 32 ? sp.seedmap[pb] : 255;
                     keep = !(sa != 255 && sa == sb);
                     if (keep) {
                         if (exact_seed) score = seed_const;
-                        else for (int i = 0; i < K; ++i) score += sscore[__ldg(qcodes + qpos + i) * 32 + tl[pos + i]];
+                        else if (K > 7) { for (int i = 0; i < K; ++i) score += sscore[__ldg(qcodes + qpos + i) * 32 + tl[pos + i]]; }
+                        else {
+                            for (int i = 0; i < K; ++i) {
+                                const uint32_t qa = i < 3 ? (u0 >> (8 * (i + 1))) & 0xffu : (u1 >> (8 * (i - 3))) & 0xffu;
+                                score += sscore[qa * 32 + tl[pos + i]];
+                            }
+                        }
                     }
                 }
                 const unsigned km = __ballot_sync(FULL, keep);
@@ -349,10 +369,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) seed_scan_kernel(const uint8_
             const uint32_t n2 = s_n2;
             constexpr int NW = SCAN_CH / 4;
             // the SCAN_CH residues starting at byte address p (any alignment) as NW aligned-looking words
+            // (query words come as 64-bit loads: every lane reads its own sectors, so the load/store pipe pays per load
+            // INSTRUCTION and lane -- three 8-byte loads instead of five 4-byte ones)
             auto load_q = [&](const uint8_t* p, uint32_t (&w)[NW + 1]) {
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-#pragma unroll
-                for (int j = 0; j <= NW; ++j) w[j] = __ldg(wp + j);
+                static_assert(NW == 4, "three 64-bit loads cover 16 residues at any alignment");
+                const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+                const uint2* wp = reinterpret_cast<const uint2*>(a & ~(uintptr_t)7);
+                const uint2 r0 = __ldg(wp), r1 = __ldg(wp + 1), r2 = __ldg(wp + 2);
+                const bool odd = (a & 4) != 0;          // the aligned 4-byte word holding *p is the second of its pair
+                w[0] = odd ? r0.y : r0.x; w[1] = odd ? r1.x : r0.y; w[2] = odd ? r1.y : r1.x; w[3] = odd ? r2.x : r1.y; w[4] = odd ? r2.y : r2.x;
             };
             auto load_t = [&](const uint8_t* p, uint32_t (&w)[NW + 1]) {
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
