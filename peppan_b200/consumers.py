@@ -178,3 +178,129 @@ def map_bsn_groups(blastab, overlap, seq, params, ortho_pairs=None):
     else:
         overlap = np.zeros([0, 3], dtype=np.int64)
     return bsn, overlap
+
+
+# ---- get_similar_pairs (PEPPAN.py:194-294) ---------------------------------------------------------------------------------
+def _pair_identity(parts, params):
+    """get_similar (PEPPAN.py:195-224) for the hits of one (query, subject) pair: the positions of the query covered by
+    in-frame matched runs, the identity of the hit that covered a position last, and the verdict taken after the first run
+    at which the covered length suffices.  Returns None (no verdict), or the value stored in ortho_pairs.  The positions of
+    a run are handled as one array slice each (the reference updates a dict per position after a regex pass per hit)."""
+    first = parts[0]
+    qlen, slen = int(first[12]), int(first[13])
+    if min(slen, qlen) * 20 <= max(slen, qlen):
+        return None
+    size = max(int(p[7]) for p in parts) + max(sum(int(n) for n, _ in _CIG.findall(p[14])) for p in parts) + 8
+    covered = np.zeros(size, dtype=bool); val = np.zeros(size, dtype=np.float64)
+    order = []                                  # covered positions in the order they were first covered (dict order)
+    n_cov = 0
+    need_len = min(params['match_len2'], params['match_len'], params['match_len1'])
+    need_prop = min(params['match_prop'], params['match_prop1'], params['match_prop2']) * qlen
+    shifted_ok = 'f' in params['incompleteCDS']
+    for part in parts:
+        s_i, s_j = int(part[6]), int(part[8])
+        for n, t in _CIG.findall(part[14]):
+            n = int(n)
+            if t == 'M':
+                fi, fj = s_i % 3, s_j % 3
+                if fi == fj or shifted_ok:
+                    a = s_i + (3 - (fi - 1)) % 3
+                    b = s_i + n
+                    if b > a:
+                        fresh = np.flatnonzero(~covered[a:b]) + a
+                        if len(fresh):
+                            order.append(fresh); covered[a:b] = True; n_cov += len(fresh)
+                        val[a:b] = part[2]
+                s_i += n; s_j += n
+                if n_cov * 3 >= need_len and n_cov * 3 >= need_prop:
+                    ave = int(np.mean(val[np.concatenate(order)]) * 10000)
+                    if ave >= params['match_identity'] * 10000:
+                        m = min(slen, qlen)
+                        full = min(max(params['match_len'], params['match_prop'] * m), max(params['match_len1'], params['match_prop1'] * m),
+                                   max(params['match_len2'], params['match_prop2'] * m))
+                        return ave if n_cov * 3 >= full else 0
+            elif t == 'I':
+                s_i += n
+            else:
+                s_j += n
+    return None
+
+
+def similar_pairs(self_bsn, priorities, params):
+    """The consumer loop of get_similar_pairs (PEPPAN.py:231-276) on the exemplar-vs-exemplar blastab (names already
+    integers): returns (ortho_pairs dict, presence dict, cluGroups list) as the reference builds them."""
+    presence, ortho_pairs, clu_groups = {}, {}, []
+    save = []
+    root = np.sqrt(params['clust_match_prop'])
+
+    def flush():
+        if len(save) >= 50:
+            presence[save[0][1]] = 0
+        elif save[0][0] != save[0][1]:
+            key = tuple(sorted([save[0][0], save[0][1]]))
+            if key not in ortho_pairs:
+                v = _pair_identity(save, params)
+                if v is not None:
+                    ortho_pairs[key] = v
+
+    for part in self_bsn:
+        q, s = part[0], part[1]
+        if q not in presence:
+            presence[q] = 1
+        elif presence[q] == 0:
+            continue
+        iden, qs, qe, ss, se, ql, sl = float(part[2]), float(part[6]), float(part[7]), float(part[8]), float(part[9]), float(part[12]), float(part[13])
+        if presence.get(s, 1) == 0:
+            continue
+        qa, sa = qe - qs + 1, abs(se - ss) + 1
+        if q != s and iden >= params['clust_identity']:
+            if ss > se or (qs % 3 != ss % 3 and (ql - qe) % 3 == (sl - se) % 3):
+                if qa >= params['clust_match_prop'] * ql or sa >= params['clust_match_prop'] * sl:
+                    ortho_pairs[tuple(sorted([q, s]))] = -2
+                    continue
+            elif ss < se and qs % 3 == ss % 3 and (ql - qe) % 3 == (sl - se) % 3:
+                if ql <= sl:
+                    if qa >= root * sl and priorities[q][0] >= priorities[s][0]:
+                        clu_groups.append([int(s), int(q), int(iden * 10000.)])
+                        presence[q] = 0
+                        continue
+                elif sa >= root * ql and priorities[q][0] <= priorities[s][0]:
+                    clu_groups.append([int(q), int(s), int(iden * 10000.)])
+                    presence[s] = 0
+                    continue
+        if ss >= se:
+            continue
+        if save and (save[0][0] != q or save[0][1] != s):
+            flush()
+            save = []
+        save.append(part)
+    if save:
+        flush()
+    return ortho_pairs, presence, clu_groups
+
+
+def get_similar_pairs(clust, priorities, params, uberblast=None, pool=None):
+    """PEPPAN.get_similar_pairs: the exemplar-vs-exemplar search through uberBlast, the loop above, and the same side effects
+    (merged exemplars dropped from the exemplar file, merges appended to `<clust>.npy`); returns int array (n, 3)."""
+    if uberblast is None:
+        from .uberBlast import uberBlast as uberblast
+    flags = '-r {0} -q {0} --blastn{6} --min_id {1} --min_cov {2} -t {3} --min_ratio {4} -e 3,3 -p --gtable {5}'.format(
+        clust, params['match_identity'] - 0.05, params['match_frag_len'], params['n_thread'], params['match_frag_prop'], params['gtable'],
+        '' if params['noDiamond'] else ' --diamond -s 1')
+    self_bsn = uberblast(flags.split(), pool)
+    self_bsn.T[:2] = self_bsn.T[:2].astype(int)
+    ortho_pairs, presence, clu_groups = similar_pairs(self_bsn, priorities, params)
+    keep, write = [], False
+    with open(params['clust']) as fin:
+        for line in fin:
+            if line.startswith('>'):
+                write = presence.get(int(line[1:].strip().split()[0]), 0) > 0
+            if write:
+                keep.append(line)
+    with open(params['clust'], 'w') as fout:
+        fout.writelines(keep)
+    if clu_groups:
+        npy = params['clust'].rsplit('.', 1)[0] + '.npy'
+        clu = np.vstack([np.load(npy, allow_pickle=True), clu_groups])
+        np.save(npy, clu[np.argsort(-clu.T[2])])
+    return np.array([[k[0], k[1], v] for k, v in ortho_pairs.items() if v != 0], dtype=int)

@@ -104,3 +104,34 @@ def test_score_hits_handles_gaps_frames_and_stops():
     seq4 = [(7, 'AAACCCGGGTTTACGTACGTAGCCCAAATTTGG')]                          # 20..32: 'TAGCCCAAATTTG': stop first -> spans 0 and 13
     sc4, _ = consumers.score_hits([row4], seq4)
     assert int(sc4[0]) == 13
+
+
+def test_get_similar_pairs_equals_the_reference(PEPPAN, oracle_as_search, monkeypatch, tmp_path):
+    """consumers.get_similar_pairs against PEPPAN.get_similar_pairs (PEPPAN.py:194-294) on the same exemplar file: the same
+    ortholog pairs with the same average identities, the same exemplar file afterwards, the same merge records."""
+    import shutil
+    monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)
+    monkeypatch.setattr(PEPPAN, 'pool', None, raising=False)
+    rng = np.random.default_rng(78)
+    gp = workloads.GenePool(36, 0, seed=workloads.SEED + 43)
+    allg = {i: g for i, g in enumerate(gp.genes)}
+    allg.update({100 + i: workloads._diverge(rng, gp.genes[i], 0.95) for i in range(0, 10)})          # merged into their exemplar
+    allg.update({200 + i: workloads._diverge(rng, gp.genes[i], 0.75) for i in range(10, 22)})         # ortholog pairs
+    allg.update({300 + i: workloads._diverge(rng, gp.genes[i], 0.62) for i in range(22, 30)})         # weak pairs: mostly protein hits
+    allg.update({400 + i: gp.genes[i][:len(gp.genes[i]) // 6 * 3] for i in range(30, 34)})            # half-length fragments
+    out = []
+    for tag in ('ref', 'ours'):
+        d = os.path.join(tmp_path, tag); os.makedirs(d)
+        clust = os.path.join(d, 'x.clust.exemplar')
+        with open(clust, 'w') as f:
+            for n, g in allg.items():
+                f.write('>%d\n%s\n' % (n, workloads._NT[g].tobytes().decode()))
+        np.save(os.path.join(d, 'x.clust.npy'), np.zeros([0, 3], dtype=int))
+        priorities = {n: [n % 3, n] for n in allg}
+        params = dict(clust=clust, incompleteCDS='', noDiamond=False, n_thread=2, gtable=11, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25,
+                      match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400., clust_identity=0.9, clust_match_prop=0.8)
+        pairs = PEPPAN.get_similar_pairs(clust, priorities, params) if tag == 'ref' else consumers.get_similar_pairs(clust, priorities, params)
+        out.append((pairs, open(clust).read(), np.load(os.path.join(d, 'x.clust.npy'), allow_pickle=True)))
+    (p0, f0, c0), (p1, f1, c1) = out
+    assert p0.shape == p1.shape and len(p0) >= 12 and np.array_equal(p0, p1)
+    assert f0 == f1 and c0.shape == c1.shape and len(c0) >= 8 and np.array_equal(c0.astype(int), c1.astype(int))
