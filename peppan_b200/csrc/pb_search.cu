@@ -369,15 +369,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) seed_scan_kernel(const uint8_
             const uint32_t n2 = s_n2;
             constexpr int NW = SCAN_CH / 4;
             // the SCAN_CH residues starting at byte address p (any alignment) as NW aligned-looking words
-            // (query words come as 64-bit loads: every lane reads its own sectors, so the load/store pipe pays per load
-            // INSTRUCTION and lane -- three 8-byte loads instead of five 4-byte ones)
+            // (query words come as two 128-bit loads: every lane reads its own sectors, so the load/store pipe pays per load
+            // INSTRUCTION and lane -- two 16-byte loads instead of five 4-byte ones; the word holding *p is then picked out
+            // of the 32 bytes by two levels of selects)
             auto load_q = [&](const uint8_t* p, uint32_t (&w)[NW + 1]) {
-                static_assert(NW == 4, "three 64-bit loads cover 16 residues at any alignment");
+                static_assert(NW == 4, "two 128-bit loads cover 16 residues at any alignment");
                 const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-                const uint2* wp = reinterpret_cast<const uint2*>(a & ~(uintptr_t)7);
-                const uint2 r0 = __ldg(wp), r1 = __ldg(wp + 1), r2 = __ldg(wp + 2);
-                const bool odd = (a & 4) != 0;          // the aligned 4-byte word holding *p is the second of its pair
-                w[0] = odd ? r0.y : r0.x; w[1] = odd ? r1.x : r0.y; w[2] = odd ? r1.y : r1.x; w[3] = odd ? r2.x : r1.y; w[4] = odd ? r2.y : r2.x;
+                const uint4* wp = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                const uint4 r0 = __ldg(wp), r1 = __ldg(wp + 1);
+                const bool o1 = (a & 4) != 0, o2 = (a & 8) != 0;
+                const uint32_t t0 = o1 ? r0.y : r0.x, t1 = o1 ? r0.z : r0.y, t2 = o1 ? r0.w : r0.z, t3 = o1 ? r1.x : r0.w,
+                               t4 = o1 ? r1.y : r1.x, t5 = o1 ? r1.z : r1.y, t6 = o1 ? r1.w : r1.z;
+                w[0] = o2 ? t2 : t0; w[1] = o2 ? t3 : t1; w[2] = o2 ? t4 : t2; w[3] = o2 ? t5 : t3; w[4] = o2 ? t6 : t4;
             };
             auto load_t = [&](const uint8_t* p, uint32_t (&w)[NW + 1]) {
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);

@@ -103,3 +103,23 @@ def test_transeq_device_matches_reference_golden(ctx):
     assert seqcodec.transeq({'a': 'ATGNNNAC-GTA'}, frame='1', ctx=ctx)['a'] == ['MX-V']
     assert seqcodec.transeq({'a': 'TAATAGTGAATGGTGTTGCTG'}, frame='1', transl_table=4, ctx=ctx)['a'] == ['XXWMVLL']
     assert seqcodec.transeq({}, frame='7', ctx=ctx) == {}
+
+
+@pytest.mark.gpu
+def test_grouped_search_in_two_halves_and_views_of_the_library_buffers(ctx):
+    """search_grouped_local + take_hits (the calls worker threads and the exchanging thread make) give the table of
+    search_grouped_raw, also when the arrays are views of the library's buffers (copy=False)."""
+    import gc
+    pool = workloads.GenePool(40, 40, seed=workloads.SEED + 5)
+    seqs = [workloads.synth_genome(pool, g, n_acc_per_genome=20, seed=workloads.SEED + 5)[0] for g in range(3)]
+    qn, qb, qo = seqio.to_seqset(pool.fasta_items()); tn, tb, to = seqio.to_seqset([('g%d' % i, s) for i, s in enumerate(seqs)])
+    groups = np.arange(3, dtype=np.int32)
+    for mode in (search.MODE_NT, search.MODE_PROT6):
+        h0, c0, g0, _ = search.search_grouped_raw(ctx, qb, qo, tb, to, groups, mode, min_id=0.4, min_cov=50, min_ratio=0.25)
+        for copy in (True, False):
+            out, goff, st = search.search_grouped_local(ctx, qb, qo, tb, to, groups, mode, min_id=0.4, min_cov=50, min_ratio=0.25)
+            h, c, roff = search.take_hits(ctx, out, False, copy=copy)
+            assert roff is None and np.array_equal(goff, g0) and len(h) == len(h0) > 100
+            assert h.tobytes() == h0.tobytes() and np.array_equal(c, c0)
+            del h, c
+            gc.collect()
