@@ -237,7 +237,10 @@ constexpr int SCAN_CH = 16;                   // residues per extension chunk; l
 
 struct SeedQ { uint32_t qpos, tpos; };
 
-__global__ void __launch_bounds__(SCAN_THREADS, 4) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
+#ifndef PB_SCAN_BLOCKS
+#define PB_SCAN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SCAN_THREADS, PB_SCAN_BLOCKS) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
                                                                  const uint8_t* __restrict__ qcodes, int64_t qn,
                                                                  const uint32_t* __restrict__ table, const uint32_t* __restrict__ ends,
                                                                  const uint32_t* __restrict__ vals, DevSpec sp,
@@ -260,6 +263,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) seed_scan_kernel(const uint8_
     const bool exact_seed = sp.base == 4;                  // nucleotide seeds are exact matches: their score is k * match
     const int seed_const = K * (int)sp.score[0];
     unsigned long long myseeds = 0;
+    // lane state of phase 2b (a lane keeps its seed across the batches of a tile)
+    bool act = false;
+    uint32_t l_qpos = 1;
+    int l_pos = 0, l_dir = 0, l_c0 = 0, l_cur = 0, l_best = 0, l_blen = 0, l_lbest = 0, l_llen = 0;
     for (int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE; t0 < tn; t0 += (int64_t)gridDim.x * SCAN_TILE) {
         __syncthreads();
         // stage [t0 - HALO, t0 + TILE + HALO) (t0 and HALO are multiples of 16: 128-bit loads); sentinel outside the array
@@ -392,69 +399,84 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) seed_scan_kernel(const uint8_
 #pragma unroll
                 for (int j = 0; j < NW; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh);
             };
-            for (uint32_t e0 = 0; e0 < n2; e0 += SCAN_THREADS) {
-                const uint32_t e = e0 + threadIdx.x;
-                const bool have = e < n2;
-                uint32_t qpos = 1; int pos = 0, best = 0;
-                if (have) { const uint2 en = q2[e]; qpos = en.x; pos = (int)(en.y & 0xffffu); best = (int)(short)(en.y >> 16); }
-                int cur = best, blen = K;
-                bool dropped = !have;
-                // the first chunk of both sides is fetched up front (one exposed load latency per seed, not two)
-                uint32_t qr[NW + 1], ql[NW + 1];
-                load_q(qcodes + qpos + K, qr);
-                load_q(qcodes + (int64_t)qpos - SCAN_CH, ql);
-                // right: residues qpos + K + i against tile position pos + K + i
-                for (int c0 = 0; c0 < T1; c0 += SCAN_CH) {
-                    if (!__any_sync(FULL, !dropped)) break;
-                    if (c0 > 0) load_q(qcodes + qpos + K + c0, qr);
-                    uint32_t tw[NW + 1];
-                    load_t(tl + pos + K + c0, tw);
-                    align_words(qr, qcodes + qpos + K + c0);
-                    align_words(tw, tl + pos + K + c0);
-#pragma unroll
-                    for (int i = 0; i < SCAN_CH; ++i) {
-                        const uint32_t a = (qr[i >> 2] >> ((i & 3) * 8)) & 0xffu, bb = (tw[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-                        cur += sscore[a * 32 + bb];
-                        const bool up = !dropped && cur > best;
-                        dropped = dropped || (!up && best - cur > XD);
-                        best = up ? cur : best;
-                        blen = up ? K + c0 + i + 1 : blen;
+            // A lane holds one seed and works it off one CHUNK per iteration -- right chunks until the X-drop fires, then left
+            // chunks -- and takes the next seed from the queue when it is done.  All lanes run the same chunk code with their
+            // own direction and offset, so nothing diverges, and no lane waits for the slowest seed of its warp (3.7 % of the
+            // seeds survive a first chunk; in seed-per-lane rounds they made 70 % of the warps run a second one).  Lanes keep
+            // their seeds across the batches of a tile and finish them after the last one.
+            bool more = n2 > 0;
+            for (;;) {
+                const unsigned idle = __ballot_sync(FULL, !act);
+                if (idle && more) {
+                    uint32_t hb = 0;
+                    if (lane == 0) hb = atomicAdd(&s_head, (uint32_t)__popc(idle));
+                    hb = __shfl_sync(FULL, hb, 0);
+                    if (hb + (uint32_t)__popc(idle) >= n2) more = false;
+                    if (!act) {
+                        const uint32_t h = hb + __popc(idle & ((1u << lane) - 1u));
+                        if (h < n2) {
+                            const uint2 en = q2[h];
+                            l_qpos = en.x; l_pos = (int)(en.y & 0xffffu);
+                            l_cur = l_best = (int)(short)(en.y >> 16); l_blen = K;
+                            l_dir = 0; l_c0 = 0; act = true;
+                        }
                     }
                 }
-                bool open = have && !dropped;                           // still alive after the lane's budget: warp-per-seed kernel
-                // left: residues qpos - 1 - i against tile position pos - 1 - i, from the right-extended best
-                int lbest = best, llen = 0;
-                cur = best;
-                bool ldropped = !have || open;
-                for (int c0 = 0; c0 < T1; c0 += SCAN_CH) {
-                    if (!__any_sync(FULL, !ldropped)) break;
-                    const uint8_t* qp = qcodes + ((int64_t)qpos - c0 - SCAN_CH);   // lowest query residue of the chunk; below the array only inside the leading pad
-                    if (c0 > 0) load_q(qp, ql);
-                    uint32_t tw[NW + 1];
-                    load_t(tl + pos - c0 - SCAN_CH, tw);
-                    align_words(ql, qp);
-                    align_words(tw, tl + pos - c0 - SCAN_CH);
+                const unsigned busy = __ballot_sync(FULL, act);
+                if (!busy) break;
+                if (!more && !last_batch) break;          // queue drained: the seeds in flight continue in the next batch
+                // one chunk: residues q[qp + i] / t[tp + i] (right) or q[qp + 15 - i] / t[tp + 15 - i] (left), i = 0 .. 15
+                const uint32_t qpos = act ? l_qpos : 1u; const int pos = act ? l_pos : 0;
+                const uint8_t* qp = l_dir == 0 ? qcodes + qpos + K + l_c0 : qcodes + ((int64_t)qpos - l_c0 - SCAN_CH);
+                const uint8_t* tp = l_dir == 0 ? tl + pos + K + l_c0 : tl + pos - l_c0 - SCAN_CH;
+                uint32_t qw[NW + 1], tw[NW + 1];
+                load_q(qp, qw); load_t(tp, tw);
+                align_words(qw, qp); align_words(tw, tp);
+                if (l_dir) {                      // walk the chunk downwards: reverse its 16 bytes
 #pragma unroll
-                    for (int i = 0; i < SCAN_CH; ++i) {
-                        const int r = SCAN_CH - 1 - i;                  // the i-th residue to the left is byte r of the chunk
-                        const uint32_t a = (ql[r >> 2] >> ((r & 3) * 8)) & 0xffu, bb = (tw[r >> 2] >> ((r & 3) * 8)) & 0xffu;
-                        cur += sscore[a * 32 + bb];
-                        const bool up = !ldropped && cur > lbest;
-                        ldropped = ldropped || (!up && lbest - cur > XD);
-                        lbest = up ? cur : lbest;
-                        llen = up ? c0 + i + 1 : llen;
+                    for (int j = 0; j < NW / 2; ++j) {
+                        const uint32_t a0 = __byte_perm(qw[j], 0, 0x0123), a1 = __byte_perm(qw[NW - 1 - j], 0, 0x0123);
+                        qw[j] = a1; qw[NW - 1 - j] = a0;
+                        const uint32_t b0 = __byte_perm(tw[j], 0, 0x0123), b1 = __byte_perm(tw[NW - 1 - j], 0, 0x0123);
+                        tw[j] = b1; tw[NW - 1 - j] = b0;
                     }
                 }
-                if (have && !open && !ldropped) open = true;
-                if (open) {
-                    const unsigned long long slot2 = atomicAdd(nlong, 1ull);
-                    if (slot2 < cap) { SeedQ en; en.qpos = qpos; en.tpos = (uint32_t)(t0 + pos); longq[slot2] = en; }
-                } else if (have && lbest >= sp.min_ungapped) {
-                    const unsigned long long slot2 = atomicAdd(ncand, 1ull);
-                    if (slot2 < cap) {
-                        Cand cd; cd.qpos = qpos - (uint32_t)llen; cd.tpos = (uint32_t)(t0 + pos - llen);
-                        cd.len = (uint32_t)(blen + llen); cd.score = lbest;
-                        cand[slot2] = cd;
+                int cur = l_cur, bb = l_dir == 0 ? l_best : l_lbest, ln = l_dir == 0 ? l_blen : l_llen;
+                const int base_len = l_dir == 0 ? K + l_c0 : l_c0;
+                bool dropped = false;
+#pragma unroll
+                for (int i = 0; i < SCAN_CH; ++i) {
+                    const uint32_t a = (qw[i >> 2] >> ((i & 3) * 8)) & 0xffu, b = (tw[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                    cur += sscore[a * 32 + b];
+                    const bool up = !dropped && cur > bb;
+                    dropped = dropped || (!up && bb - cur > XD);
+                    bb = up ? cur : bb;
+                    ln = up ? base_len + i + 1 : ln;
+                }
+                if (act) {
+                    bool open = false;
+                    if (l_dir == 0) {
+                        l_best = bb; l_blen = ln;
+                        if (dropped) { l_dir = 1; l_c0 = 0; l_cur = bb; l_lbest = bb; l_llen = 0; }
+                        else { l_cur = cur; l_c0 += SCAN_CH; open = l_c0 >= T1; }
+                    } else {
+                        l_lbest = bb; l_llen = ln;
+                        if (dropped) {
+                            if (bb >= sp.min_ungapped) {
+                                const unsigned long long slot2 = atomicAdd(ncand, 1ull);
+                                if (slot2 < cap) {
+                                    Cand cd; cd.qpos = l_qpos - (uint32_t)ln; cd.tpos = (uint32_t)(t0 + l_pos - ln);
+                                    cd.len = (uint32_t)(l_blen + ln); cd.score = bb;
+                                    cand[slot2] = cd;
+                                }
+                            }
+                            act = false;
+                        } else { l_cur = cur; l_c0 += SCAN_CH; open = l_c0 >= T1; }
+                    }
+                    if (open) {                   // still alive after the lane's budget on this side: warp-per-seed kernel
+                        const unsigned long long slot2 = atomicAdd(nlong, 1ull);
+                        if (slot2 < cap) { SeedQ en; en.qpos = l_qpos; en.tpos = (uint32_t)(t0 + l_pos); longq[slot2] = en; }
+                        act = false;
                     }
                 }
             }
