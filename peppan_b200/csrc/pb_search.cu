@@ -486,10 +486,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, PB_SCAN_BLOCKS) seed_scan_kernel
     if (myseeds) atomicAdd(nseed, myseeds);
 }
 
-// One warp per queued seed: the same X-drop extension (right, then left from the right-extended best), 32 residues per
-// step.  With c_i the running score after residue i of the step and b_i the running best (inclusive prefix maximum,
-// seeded with the best so far), the scalar loop stops at the first i that is out of range / a sentinel, or has
-// b_i - c_i > xdrop; the best and its (first) position are those of the residues before the stop.
+// One warp per queued seed: the same X-drop extension (right, then left from the right-extended best), 32 * XR residues per
+// step, XR consecutive ones per lane.  With c_i the running score after residue i of the step and b_i the running best
+// (inclusive prefix maximum, seeded with the best so far), the scalar loop stops at the first i that is out of range / a
+// sentinel, or has b_i - c_i > xdrop; the best and its (first) position are those of the residues before the stop.  Sums and
+// maxima run inside a lane first and over the lanes by shuffles (two scans per step).
+template <int XR>                                 // residues per lane and step
 __global__ void __launch_bounds__(256) xdrop_warp_kernel(const uint8_t* __restrict__ tcodes, int64_t tn, const uint8_t* __restrict__ qcodes, int64_t qn,
                                                          DevSpec sp, const SeedQ* __restrict__ longq, unsigned long long nlong,
                                                          Cand* cand, unsigned long long* ncand, unsigned long long cap)
@@ -510,36 +512,54 @@ __global__ void __launch_bounds__(256) xdrop_warp_kernel(const uint8_t* __restri
         for (int dir = 0; dir < 2; ++dir) {
             int cur = best, len = 0;             // len: residues of this side covered by the best
             int sidebest = best;
-            for (int64_t x0 = 0;; x0 += 32) {
-                const int64_t x = x0 + lane;
-                const int64_t qi = dir == 0 ? qpos + sp.k + x : qpos - 1 - x, ti = dir == 0 ? tpos + sp.k + x : tpos - 1 - x;
-                bool valid = qi >= 0 && ti >= 0 && qi < qn && ti < tn;
-                int sc = 0;
-                if (valid) {
-                    const uint8_t a = qcodes[qi], b = tcodes[ti];
-                    if (a == SENT || b == SENT) valid = false; else sc = sscore[a * 32 + b];
+            for (int64_t x0 = 0;; x0 += 32 * XR) {
+                // lane L holds residues x0 + XR * L + r, r = 0 .. XR-1 of the step
+                int sc[XR]; bool vd[XR];
+#pragma unroll
+                for (int r = 0; r < XR; ++r) {
+                    const int64_t x = x0 + (int64_t)lane * XR + r;
+                    const int64_t qi = dir == 0 ? qpos + sp.k + x : qpos - 1 - x, ti = dir == 0 ? tpos + sp.k + x : tpos - 1 - x;
+                    vd[r] = qi >= 0 && ti >= 0 && qi < qn && ti < tn;
+                    sc[r] = 0;
+                    if (vd[r]) {
+                        const uint8_t a = qcodes[qi], b = tcodes[ti];
+                        if (a == SENT || b == SENT) vd[r] = false; else sc[r] = sscore[a * 32 + b];
+                    }
                 }
-                int c = sc;                      // inclusive prefix sum of the step's scores
+                int p[XR];                       // inclusive prefix sums inside the lane
+                p[0] = sc[0];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, c, o); if (lane >= o) c += v; }
-                c += cur;
-                int bmax = c;                    // inclusive prefix maximum, seeded with the best so far
+                for (int r = 1; r < XR; ++r) p[r] = p[r - 1] + sc[r];
+                int incl = p[XR - 1];            // ... and over the lanes
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, bmax, o); if (lane >= o) bmax = max(bmax, v); }
-                bmax = max(bmax, sidebest);
-                const unsigned stopm = __ballot_sync(FULL, !valid || bmax - c > sp.xdrop);
-                const int nstep = stopm ? __ffs(stopm) - 1 : 32;          // residues consumed before the stop
-                // best among the consumed residues: first lane that reaches a value above the previous best
-                const int cand_v = lane < nstep ? c : INT_MIN;
-                int mx = cand_v;
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                const int base = cur + incl - p[XR - 1];
+                int c[XR], m[XR];                // running score after every residue; running maximum inside the lane
 #pragma unroll
-                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+                for (int r = 0; r < XR; ++r) { c[r] = base + p[r]; m[r] = r ? max(m[r - 1], c[r]) : c[r]; }
+                int im = m[XR - 1];              // inclusive maximum over the lanes -> maximum of everything before this lane
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, im, o); if (lane >= o) im = max(im, v); }
+                int before = __shfl_up_sync(FULL, im, 1);
+                before = lane == 0 ? sidebest : max(before, sidebest);
+                int rs = XR;                     // first residue of the lane at which the scalar loop stops
+#pragma unroll
+                for (int r = XR - 1; r >= 0; --r) if (!vd[r] || max(before, m[r]) - c[r] > sp.xdrop) rs = r;
+                const unsigned stopm = __ballot_sync(FULL, rs < XR);
+                const int ls = stopm ? __ffs(stopm) - 1 : 32;            // first lane with a stop
+                const int kcons = lane < ls ? XR : (lane == ls ? rs : 0);    // residues of this lane that were consumed
+                // best among the consumed residues, first position reaching it
+                int vl = INT_MIN, rf = 0;
+#pragma unroll
+                for (int r = 0; r < XR; ++r) if (r < kcons && c[r] > vl) { vl = c[r]; rf = r; }
+                const int mx = __reduce_max_sync(FULL, vl);
                 if (mx > sidebest) {
-                    const unsigned who = __ballot_sync(FULL, cand_v == mx);
-                    sidebest = mx; len = (int)x0 + __ffs(who);
+                    const unsigned who = __ballot_sync(FULL, vl == mx);
+                    const int lf = __ffs(who) - 1;
+                    sidebest = mx; len = (int)x0 + XR * lf + __shfl_sync(FULL, rf, lf) + 1;
                 }
-                if (nstep < 32) break;
-                cur = __shfl_sync(FULL, c, 31);
+                if (ls < 32) break;
+                cur = __shfl_sync(FULL, c[XR - 1], 31);
             }
             if (dir == 0) { best = sidebest; blen = sp.k + len; }
             else if (lane == 0 && sidebest >= sp.min_ungapped) {
@@ -994,8 +1014,11 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
         if (cnts[3] <= cap && cnts[3] > 0) {
             const unsigned long long nlong = cnts[3];
             const int xgrid = (int)std::min<unsigned long long>((nlong + 7) / 8, (unsigned long long)ctx->sm_avail * 8);
-            xdrop_warp_kernel<<<xgrid, 256, 0, sm>>>(d_tc.as<uint8_t>(), LT, qc, LQ, ds, d_longq.as<SeedQ>(), nlong,
-                                                     d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap);
+            // nucleotide HSPs of homologous genes run for hundreds of bases (128 per step); protein HSPs are short (32 per step)
+            if (nt) xdrop_warp_kernel<4><<<xgrid, 256, 0, sm>>>(d_tc.as<uint8_t>(), LT, qc, LQ, ds, d_longq.as<SeedQ>(), nlong,
+                                                                d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap);
+            else xdrop_warp_kernel<1><<<xgrid, 256, 0, sm>>>(d_tc.as<uint8_t>(), LT, qc, LQ, ds, d_longq.as<SeedQ>(), nlong,
+                                                             d_cand.as<Cand>(), d_cnt.as<unsigned long long>() + 1, cap);
             PB_CUDA(ctx, cudaGetLastError()); ++launches;
             PB_CUDA(ctx, cudaMemcpyAsync(cnts, d_cnt.p, 64, cudaMemcpyDeviceToHost, sm));
             PB_CUDA(ctx, cudaStreamSynchronize(sm));
