@@ -264,8 +264,10 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                 while (j < nh && hs[j].qid == c.qid && hs[j].tid == c.tid && hs[j].diag - d0 <= SPAN) {
                     int dup = j > i && hs[j].diag == hs[j - 1].diag && hs[j].ts == hs[j - 1].ts && hs[j].te == hs[j - 1].te;
                     if (!dup) { if (hs[j].score > smax) smax = hs[j].score; ssum += hs[j].score; }
-                    if (hs[j].ts < c.tmin) c.tmin = hs[j].ts; if (hs[j].te > c.tmax) c.tmax = hs[j].te;
-                    if (hs[j].qs < c.qmin) c.qmin = hs[j].qs; if (hs[j].qe > c.qmax) c.qmax = hs[j].qe;
+                    if (hs[j].ts < c.tmin) c.tmin = hs[j].ts;
+                    if (hs[j].te > c.tmax) c.tmax = hs[j].te;
+                    if (hs[j].qs < c.qmin) c.qmin = hs[j].qs;
+                    if (hs[j].qe > c.qmax) c.qmax = hs[j].qe;
                     ++j;
                 }
                 if (smax >= CMAX || ssum >= CSUM) cl[ncl++] = c;
@@ -279,7 +281,8 @@ int64_t orc_search(const uint8_t* qa, const int64_t* qoff, int64_t nq, const uin
                 int64_t lo = c.tmin - c.qmin - PAD, hi = c.tmax + (QLn - c.qmax) + PAD;
                 if (i > 0 && cl[i - 1].qid == c.qid && cl[i - 1].tid == c.tid && cl[i - 1].tmax <= c.tmin && cl[i - 1].tmax > lo) lo = cl[i - 1].tmax;
                 if (i + 1 < ncl && cl[i + 1].qid == c.qid && cl[i + 1].tid == c.tid && cl[i + 1].tmin >= c.tmax && cl[i + 1].tmin < hi) hi = cl[i + 1].tmin;
-                if (lo < 0) lo = 0; if (hi > TLn) hi = TLn;
+                if (lo < 0) lo = 0;
+                if (hi > TLn) hi = TLn;
                 if (hi <= lo) continue;
                 int64_t w = nwin++;
                 int capc = (int)(QLn + (hi - lo) + 2);
