@@ -304,3 +304,90 @@ def get_similar_pairs(clust, priorities, params, uberblast=None, pool=None):
         clu = np.vstack([np.load(npy, allow_pickle=True), clu_groups])
         np.save(npy, clu[np.argsort(-clu.T[2])])
     return np.array([[k[0], k[1], v] for k, v in ortho_pairs.items() if v != 0], dtype=int)
+
+
+# ---- compare_prediction + the whole of iter_map_bsn (PEPPAN.py:759-902) ---------------------------------------------------
+def compare_prediction(blastab, old_prediction, store=None):
+    """PEPPAN.compare_prediction (:869-902): column 10 of every hit becomes 0.1, or the largest fraction of an old gene
+    prediction on the same contig (in a compatible frame) that the hit covers when the two overlap by >= 60 % of either.
+    `old_prediction`: path of the old-annotation store; `store`: the class to open it with (hitio.FlatStore by default --
+    pass the reference's MapBsn for its zip files).  The hit columns are handled as integer arrays, the sweep over a
+    contig's old predictions keeps the reference's forward-only pointer."""
+    if store is None:
+        from .hitio import FlatStore as store
+    n = len(blastab)
+    smin = np.array([min(r[8], r[9]) for r in blastab], dtype=np.int64)
+    contig_key = np.array([r[1] for r in blastab], dtype=object)
+    # stable order by (contig, leftmost subject coordinate), as DataFrame.sort_values(by=[1, 's']) gives
+    order = sorted(range(n), key=lambda i: (contig_key[i], smin[i]))
+    tab = blastab[order]
+    tab.T[10] = 0.1
+    q6 = np.array([r[6] for r in tab], dtype=np.int64); q7 = np.array([r[7] for r in tab], dtype=np.int64)
+    s8 = np.array([r[8] for r in tab], dtype=np.int64); s9 = np.array([r[9] for r in tab], dtype=np.int64)
+    ql = np.array([r[12] for r in tab], dtype=np.int64)
+    fwd = s8 < s9
+    lo = np.where(fwd, s8, s9); hi = np.where(fwd, s9, s8)
+    f1 = np.where(fwd, (s8 - q6 + 1) % 3 + 1, (-(s8 - q6 + 1)) % 3 - 1)
+    f2 = np.where(fwd, (s9 + (ql - q7) + 1) % 3 + 1, (-(s9 + (ql - q7) - 1)) % 3 - 1)
+    with store(old_prediction) as op:
+        cur_name, old, ptr = None, [], 0
+        p_lo = p_hi = p_fa = p_fb = None
+        for i in range(n):
+            name = tab[i][1]
+            if cur_name is None or cur_name != name:
+                cur_name, ptr = name, 0
+                old = op.get(name)
+                m = len(old)
+                p_lo = np.array([p[1] for p in old], dtype=np.int64) if m else np.zeros(0, np.int64)
+                p_hi = np.array([p[2] for p in old], dtype=np.int64) if m else np.zeros(0, np.int64)
+                plus = np.array([p[3] == '+' for p in old], dtype=bool) if m else np.zeros(0, bool)
+                p_fa = np.where(plus, p_lo % 3 + 1, (-(p_lo - 1)) % 3 - 1)
+                p_fb = np.where(plus, (p_hi + 1) % 3 + 1, (-p_hi) % 3 - 1)
+            m = len(p_lo)
+            s, e = lo[i], hi[i]
+            while ptr < m and s > p_hi[ptr]:
+                ptr += 1
+            if ptr >= m:
+                continue
+            # predictions from the pointer up to the first one that starts behind the hit (they are sorted by start)
+            stop = ptr
+            while stop < m and not e < p_lo[stop]:
+                stop += 1
+            if stop == ptr:
+                continue
+            a, b = p_lo[ptr:stop], p_hi[ptr:stop]
+            ok = (p_fa[ptr:stop] == f1[i]) | (p_fa[ptr:stop] == f2[i]) | (p_fb[ptr:stop] == f1[i]) | (p_fb[ptr:stop] == f2[i])
+            ovl = np.minimum(e, b) - np.maximum(s, a) + 1.
+            ok &= (ovl >= 0.6 * (b - a + 1)) | (ovl >= 0.6 * (e - s + 1))
+            if ok.any():
+                best = float(np.max((ovl / (b - a + 1))[ok]))
+                if best > tab[i][10]:
+                    tab[i][10] = best
+    keys = [(r[0], r[1], r[11]) for r in tab]
+    final = sorted(range(n), key=lambda i: keys[i])
+    return tab[final]
+
+
+def iter_map_bsn(data, uberblast=None, store=None):
+    """PEPPAN.iter_map_bsn (:759-867) on this repository's pieces: the genome is written out, searched with uberBlast
+    (iter_map_bsn's flag set), the hits are compared with the old predictions, grouped and scored, and `<prefix>.<id>.bsn.npz`
+    is written with the arrays the reference writes.  Returns the output prefix."""
+    import os
+    if uberblast is None:
+        from .uberBlast import uberBlast as uberblast
+    prefix, clust, gid, taxon, seq, ortho_group, old_prediction, params = data
+    gfile, out_prefix = '{0}.{1}.genome'.format(prefix, gid), '{0}.{1}'.format(prefix, gid)
+    with open(gfile, 'w') as fout:
+        for n, s in seq:
+            fout.write('>{0}\n{1}\n'.format(n, s))
+    flags = '-r {0} -q {1} -f -m -O --blastn{8} --min_id {2} --min_cov {3} --min_ratio {4} --merge_gap {5} --merge_diff {6} -t 1{9} -e 0,3 --gtable {7}'.format(
+        gfile, clust, params['match_identity'] - 0.1, params['match_frag_len'], params['match_frag_prop'], params['link_gap'], params['link_diff'], params['gtable'],
+        '' if params['noDiamond'] else ' --diamond', '' if params['noDiamond'] else ' -s 1')
+    blastab, overlap = uberblast(flags.split())
+    os.unlink(gfile)
+    blastab.T[:2] = blastab.T[:2].astype(int)
+    blastab = compare_prediction(blastab, old_prediction, store)
+    ortho = np.load(ortho_group, allow_pickle=True)
+    bsn, ovl = map_bsn_groups(blastab, overlap, seq, params, ortho)
+    np.savez_compressed(out_prefix + '.bsn.npz', bsn=bsn, ovl=ovl)
+    return out_prefix

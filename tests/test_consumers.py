@@ -135,3 +135,42 @@ def test_get_similar_pairs_equals_the_reference(PEPPAN, oracle_as_search, monkey
     (p0, f0, c0), (p1, f1, c1) = out
     assert p0.shape == p1.shape and len(p0) >= 12 and np.array_equal(p0, p1)
     assert f0 == f1 and c0.shape == c1.shape and len(c0) >= 8 and np.array_equal(c0.astype(int), c1.astype(int))
+
+
+def test_iter_map_bsn_writes_what_the_reference_writes(PEPPAN, oracle_as_search, monkeypatch, tmp_path):
+    """consumers.iter_map_bsn (search -> compare_prediction -> grouping / scoring -> .bsn.npz) against PEPPAN.iter_map_bsn on
+    the same genome, exemplars, old predictions and ortholog pairs: the saved arrays are equal cell for cell."""
+    monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)
+    if not hasattr(np.lib.npyio, 'format'):
+        monkeypatch.setattr(np.lib.npyio, 'format', np.lib.format, raising=False)
+    pool = workloads.GenePool(50, 50, seed=workloads.SEED + 47)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=25, seed=workloads.SEED + 47)
+    mid = annot[len(annot) // 3]
+    cut = (int(mid[1]) + int(mid[2])) // 2
+    contigs = [(1001, seq[:cut]), (1002, seq[cut:])]
+    clust = os.path.join(tmp_path, 'exemplar.fa')
+    with open(clust, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    # old predictions on both contigs, both strands, some shifted so that the frame test and the 60 % rule both matter
+    old = os.path.join(tmp_path, 'old.npz')
+    store = PEPPAN.MapBsn(old, 'w')
+    r1 = [[a[0], a[1] + 1 + (3 if k % 4 == 0 else 0) + (1 if k % 7 == 0 else 0), a[2] + (90 if k % 5 == 0 else 0), '+' if a[3] > 0 else '-']
+          for k, a in enumerate(annot) if a[2] <= cut]
+    r2 = [[a[0], a[1] + 1 - cut, a[2] - cut, '+' if a[3] > 0 else '-'] for k, a in enumerate(annot) if a[1] >= cut and k % 2 == 0]
+    store._save(store.conn, '1001', np.array(sorted(r1, key=lambda r: r[1]), dtype=object))
+    store._save(store.conn, '1002', np.array(sorted(r2, key=lambda r: r[1]), dtype=object))
+    store.conn.close()
+    ortho = os.path.join(tmp_path, 'ortho.npy')
+    genes = sorted(set(int(a[0]) for a in annot))
+    np.save(ortho, np.array([[genes[i], genes[i + 1], (1 if i % 2 else -1) * 9000] for i in range(0, 30)], dtype=int), allow_pickle=True)
+    params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+    a = PEPPAN.iter_map_bsn((os.path.join(tmp_path, 'ref'), clust, 0, 'taxon', contigs, ortho, old, params))
+    b = consumers.iter_map_bsn((os.path.join(tmp_path, 'ours'), clust, 0, 'taxon', contigs, ortho, old, params), store=PEPPAN.MapBsn)
+    ra, rb = np.load(a + '.bsn.npz', allow_pickle=True), np.load(b + '.bsn.npz', allow_pickle=True)
+    assert ra['bsn'].shape == rb['bsn'].shape and len(ra['bsn']) >= 40
+    assert _same(rb['bsn'], ra['bsn'])
+    assert ra['ovl'].shape == rb['ovl'].shape and np.array_equal(ra['ovl'], rb['ovl'])
+    col10 = [float(t[10]) for g in rb['bsn'] for t in g[6]]
+    assert sum(1 for v in col10 if v > 0.1) >= 20 and sum(1 for v in col10 if 0.1 < v < 0.99) >= 3      # overlap fractions were exercised
