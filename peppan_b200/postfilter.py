@@ -155,6 +155,23 @@ def rescore_m1_table(rows, qry_set, ref_set, min_id):
     return out
 
 
+def post_chain_types():
+    """ctypes mirrors of pb_post_params / pb_post_result (include/peppan_b200.h)"""
+    import ctypes as C
+
+    class Params(C.Structure):
+        _fields_ = [('do_filter', C.c_int32), ('filter_cov', C.c_double), ('filter_delta', C.c_double),
+                    ('do_merge', C.c_int32), ('merge_gap', C.c_double), ('merge_diff', C.c_double),
+                    ('fix_start', C.c_double), ('fix_end', C.c_double),
+                    ('do_overlap', C.c_int32), ('ovl_len', C.c_double), ('ovl_prop', C.c_double)]
+
+    class Result(C.Structure):
+        _fields_ = [('n_rows', C.c_int64), ('row', C.POINTER(C.c_int32)), ('grp_off', C.POINTER(C.c_int64)), ('grp_ids', C.POINTER(C.c_int32)),
+                    ('grp_score', C.POINTER(C.c_double)), ('grp_iden', C.POINTER(C.c_double)), ('grp_len', C.POINTER(C.c_int64)),
+                    ('n_overlaps', C.c_int64), ('overlaps', C.POINTER(C.c_int64))]
+    return Params, Result
+
+
 def post_chain_table(rows, filter_opt, merge_opt, fix_end_opt, overlap_opt):
     """ovl_filter -> linear_merge -> fix_end -> overlaps -> final_sort for the whole table in one library call
     (pb_post_chain, host C++).  `rows` as for the functions below (column 15 = hit id; identity / score already final);

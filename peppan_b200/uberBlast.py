@@ -92,10 +92,63 @@ def rows_from_prot_hits(hits, cigar, qn, rn, min_id):
     return rows
 
 
+
+# ---- columnar path of RunBlast.run -------------------------------------------------------------------------------------------
+# The record tables of the searches stay numpy columns through the thresholds of parseBlast / parseDiamond, reScore (mode 1)
+# and the post-search chain; the object rows the reference's callers expect are built once, at the end.  Same values and
+# Python types as the row-by-row path (which stays for tools supplied through the `tools` seam and for rescoring modes 2 / 3).
+def _gather_ops(cigar, off, cnt):
+    """CIGAR ops of the rows (off[i], cnt[i]) back to back + their n+1 offsets"""
+    coff = np.zeros(len(off) + 1, dtype=np.int64); coff[1:] = np.cumsum(cnt)
+    total = int(coff[-1])
+    if total == 0:
+        return np.zeros(0, dtype=np.uint32), coff
+    idx = np.arange(total, dtype=np.int64) - np.repeat(coff[:-1] - off, cnt)
+    return np.ascontiguousarray(cigar[idx], dtype=np.uint32), coff
+
+
+def _columns_from_hits(hits, cigar, protein, min_id, min_cov, min_ratio):
+    """the rows parseBlast (:275-290) / parseDiamond (:16-70) would keep, as columns"""
+    cigar = np.asarray(cigar, dtype=np.uint32)
+    lens = (cigar >> 2).astype(np.int64); gap = (cigar & 3) != 0
+    off = hits['cigar_off'].astype(np.int64); end = off + hits['cigar_n'].astype(np.int64)
+    c_all = np.concatenate([[0], np.cumsum(lens)]); c_gap = np.concatenate([[0], np.cumsum(np.where(gap, lens, 0))])
+    c_ngap = np.concatenate([[0], np.cumsum(gap)])
+    cl, gapb, ngap = c_all[end] - c_all[off], c_gap[end] - c_gap[off], c_ngap[end] - c_ngap[off]
+    alen = hits['aln_len'].astype(np.int64); mism = hits['mismatch'].astype(np.int64)
+    qs, qe, qlen = hits['q_start'].astype(np.int64), hits['q_end'].astype(np.int64), hits['q_len'].astype(np.int64)
+    if protein:
+        variation = mism.astype(np.float64) + gapb.astype(np.float64)              # 3 * NM
+        iden = 1 - np.round(variation / cl, 3) if len(hits) else np.zeros(0)
+        keep = ~(iden < min_id)
+        col = dict(iden=iden, alen=cl, mism=(variation - gapb).astype(np.int64), gopen=ngap, evalue=np.zeros(len(hits)))
+    else:
+        x = (100.0 * (alen - mism - gapb) / alen).tolist() if len(hits) else []
+        iden = np.array([float('%.3f' % v) / 100. for v in x], dtype=np.float64)     # blastn's 3-decimal pident / 100 (:282)
+        span = qe - qs + 1
+        keep = (iden >= min_id) & (span >= min_cov) & (span >= min_ratio * qlen)
+        col = dict(iden=iden, alen=alen, mism=mism, gopen=hits['gapopen'].astype(np.int64), evalue=hits['evalue'].astype(np.float64))
+    col.update(qi=hits['q_id'].astype(np.int64), si=hits['s_id'].astype(np.int64), qs=qs, qe=qe, ss=hits['s_start'].astype(np.int64),
+               se=hits['s_end'].astype(np.int64), score=hits['raw_score'].astype(np.int64), qlen=qlen, slen=hits['s_len'].astype(np.int64))
+    k = np.flatnonzero(keep)
+    col = {name: v[k] for name, v in col.items()}
+    col['ops'], col['coff'] = _gather_ops(cigar, off[k], (end - off)[k])
+    return col
+
+
+def _concat_columns(tabs):
+    out = {name: np.concatenate([t[name] for t in tabs]) for name in tabs[0] if name not in ('ops', 'coff')}
+    out['ops'] = np.concatenate([t['ops'] for t in tabs])
+    cnt = np.concatenate([np.diff(t['coff']) for t in tabs])
+    out['coff'] = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    return out
+
+
 class RunBlast(object):
-    def __init__(self, ctx=None):
+    def __init__(self, ctx=None, columnar=True):
         self.qrySeq = self.refSeq = None
         self.ctx = ctx
+        self.columnar = columnar      # False: every stage on object rows (the path tools supplied through the seam take)
         self.stats = []
         self.raw = []          # (mode, hits, cigar) of every search of this run: the record tables behind the rows
 
@@ -150,6 +203,9 @@ class RunBlast(object):
         self.min_id, self.min_cov, self.min_ratio, self.table_id, self.n_thread = min_id, min_cov, min_ratio, table_id, n_thread
         # n_thread / useProcess (the reference's Pool / ThreadPool / caller's pool, :333-338) are accepted and ignored:
         # the work runs on the GPU of this process
+        own = all(getattr(type(self), f) is getattr(RunBlast, f) for f in ('runBlast', 'runDiamond', 'runDiamondSELF', '_search'))
+        if own and self.columnar and re_score in (0, 1):
+            return self._run_columnar(ref, qry, methods, min_id, re_score, filter, linear_merge, return_overlap, fix_end)
         tabs = []
         for method in methods:
             if method.lower() in tools:
@@ -180,6 +236,107 @@ class RunBlast(object):
         if return_overlap[0]:
             return blastab, overlap
         return blastab
+
+
+    def _run_columnar(self, ref, qry, methods, min_id, re_score, filter, linear_merge, return_overlap, fix_end):
+        """run() on columns: the searches, the thresholds of parseBlast / parseDiamond, reScore mode 1 (pb_rescore_m1), the
+        post-search chain (pb_post_chain); rows are built once from the final order"""
+        import ctypes as C
+        from ._lib import load, ptr
+        tabs = []
+        modes = dict(blastn=(_srch.MODE_NT, 'BLASTn'), diamond=(_srch.MODE_PROT6, 'diamond'), diamondself=(_srch.MODE_PROT3_SELF, 'diamond'))
+        self._load(ref, qry)
+        qn = rn = None
+        for method in methods:
+            if method.lower() not in modes:
+                continue
+            mode, label = modes[method.lower()]
+            logger('Run {0} starts'.format(label))
+            qn, rn, hits, cigar = self._search(mode)
+            t = _columns_from_hits(hits, cigar, mode != _srch.MODE_NT, self.min_id, self.min_cov, self.min_ratio)
+            logger('Run {0} finishes. Got {1} alignments'.format(label, len(t['qi'])))
+            if len(t['qi']):
+                tabs.append(t)
+        if not tabs:
+            if return_overlap[0]:
+                return np.empty([0, 16], dtype=object), np.empty([0, 3], dtype=int)
+            return np.empty([0, 16], dtype=object)
+        t = _concat_columns(tabs)
+        n = len(t['qi'])
+        hit_id = np.arange(n, dtype=np.int64)
+        score = t['score'].astype(np.float64)
+        lib = load()
+        if re_score == 1:
+            (_, qb, qo), (_, rb, ro) = self._sets()
+            c = [np.ascontiguousarray(t[k], dtype=np.int32) for k in ('qi', 'si', 'qs', 'qe', 'ss', 'se')]
+            iden = np.zeros(n, dtype=np.float64); sc = np.zeros(n, dtype=np.float64)
+            lib.pb_rescore_m1.argtypes = [C.POINTER(_srch.SeqSet), C.POINTER(_srch.SeqSet), C.c_int64] + [C.c_void_p] * 10
+            qs_ = _srch.SeqSet(qb.ctypes.data, qo.ctypes.data, len(qo) - 1); rs_ = _srch.SeqSet(rb.ctypes.data, ro.ctypes.data, len(ro) - 1)
+            ops_in = t['ops'] if len(t['ops']) else np.zeros(1, np.uint32)
+            rc = lib.pb_rescore_m1(C.byref(qs_), C.byref(rs_), n, ptr(c[0]), ptr(c[1]), ptr(c[2]), ptr(c[3]), ptr(c[4]), ptr(c[5]),
+                                   ptr(t['coff']), ptr(ops_in), ptr(iden), ptr(sc))
+            if rc != 0:
+                raise RuntimeError('pb_rescore_m1 failed (%d): %s' % (rc, lib.pb_last_error(None).decode()))
+            iden = np.round(iden, 3); score = np.round(sc, 3)
+            k = np.flatnonzero(iden >= min_id)
+            cnt = np.diff(t['coff'])
+            ops, coff = _gather_ops(t['ops'], t['coff'][:-1][k], cnt[k])
+            t = {name: v[k] for name, v in t.items() if name not in ('ops', 'coff')}
+            t['ops'], t['coff'] = ops, coff
+            t['iden'] = iden[k]; score = score[k]; hit_id = hit_id[k]
+            n = len(k)
+        # ranks of the names in string order: what the final sort and the chain's grouping compare
+        qrank = np.empty(len(qn), dtype=np.int64); qrank[np.argsort(np.array([str(x) for x in qn]), kind='stable')] = np.arange(len(qn))
+        rrank = np.empty(len(rn), dtype=np.int64); rrank[np.argsort(np.array([str(x) for x in rn]), kind='stable')] = np.arange(len(rn))
+        col = [np.ascontiguousarray(v, dtype=np.int32) for v in (qrank[t['qi']], rrank[t['si']], t['qs'], t['qe'], t['ss'], t['se'], t['qlen'], t['slen'], hit_id)]
+        iden = np.ascontiguousarray(t['iden'], dtype=np.float64); score = np.ascontiguousarray(score, dtype=np.float64)
+        ops = np.ascontiguousarray(t['ops'], dtype=np.uint32) if len(t['ops']) else np.zeros(1, dtype=np.uint32)
+        coff = np.ascontiguousarray(t['coff'], dtype=np.int64)
+        Params, Result = pf.post_chain_types()
+        prm = Params(int(bool(filter[0])), float(filter[1]), float(filter[2]), int(bool(linear_merge[0])), float(linear_merge[1]), float(linear_merge[2]),
+                     float(fix_end[0]), float(fix_end[1]), int(bool(return_overlap[0])), float(return_overlap[1]), float(return_overlap[2]))
+        res = Result()
+        lib.pb_post_chain.argtypes = [C.c_int64] + [C.c_void_p] * 13 + [C.POINTER(Params), C.POINTER(Result)]
+        lib.pb_free_post.argtypes = [C.POINTER(Result)]
+        lib.pb_free_post.restype = None
+        rc = lib.pb_post_chain(n, ptr(col[0]), ptr(col[1]), ptr(iden), ptr(score), ptr(col[2]), ptr(col[3]), ptr(col[4]), ptr(col[5]),
+                               ptr(col[6]), ptr(col[7]), ptr(col[8]), ptr(coff), ptr(ops), C.byref(prm), C.byref(res))
+        if rc != 0:
+            raise RuntimeError('pb_post_chain failed (%d): %s' % (rc, lib.pb_last_error(None).decode()))
+        try:
+            m = res.n_rows
+            order = np.ctypeslib.as_array(res.row, shape=(max(m, 1),))[:m].tolist()
+            goff = np.ctypeslib.as_array(res.grp_off, shape=(m + 1,)).tolist()
+            gids = np.ctypeslib.as_array(res.grp_ids, shape=(max(goff[-1], 1),)).tolist()
+            gscore = np.ctypeslib.as_array(res.grp_score, shape=(max(m, 1),)).tolist()
+            giden = np.ctypeslib.as_array(res.grp_iden, shape=(max(m, 1),)).tolist()
+            glen = np.ctypeslib.as_array(res.grp_len, shape=(max(m, 1),)).tolist()
+            overlap = None
+            if return_overlap[0]:
+                overlap = np.ctypeslib.as_array(res.overlaps, shape=(max(res.n_overlaps, 1) * 3,))[:res.n_overlaps * 3].copy().reshape(-1, 3)
+        finally:
+            lib.pb_free_post(C.byref(res))
+        # ---- rows, once ----
+        merge = bool(linear_merge[0])
+        ncol = 17 if merge else 16
+        L = {k: t[k].tolist() for k in ('qi', 'si', 'alen', 'mism', 'gopen', 'evalue', 'qlen', 'slen')}
+        qs, qe, ss, se = col[2].tolist(), col[3].tolist(), col[4].tolist(), col[5].tolist()       # as the chain left them (fixEnd)
+        iden_l = iden.tolist()
+        score_l = score.tolist() if re_score == 1 else t['score'].tolist()                          # raw scores stay integers (:294)
+        hid = hit_id.tolist()
+        pieces = ['%d%s' % (a, 'MID'[b]) for a, b in zip((ops >> 2).tolist(), (ops & 3).tolist())]
+        coff_l = coff.tolist()
+        arr = np.empty([len(order), ncol], dtype=object)
+        for k, r in enumerate(order):
+            row = arr[k]
+            row[0] = qn[L['qi'][r]]; row[1] = rn[L['si'][r]]; row[2] = iden_l[r]; row[3] = L['alen'][r]; row[4] = L['mism'][r]; row[5] = L['gopen'][r]
+            row[6] = qs[r]; row[7] = qe[r]; row[8] = ss[r]; row[9] = se[r]; row[10] = L['evalue'][r]; row[11] = score_l[r]
+            row[12] = L['qlen'][r]; row[13] = L['slen'][r]; row[14] = ''.join(pieces[coff_l[r]:coff_l[r + 1]]); row[15] = hid[r]
+            if merge:
+                row[16] = [gscore[k], giden[k], glen[k]] + gids[goff[k]:goff[k + 1]] if goff[k + 1] > goff[k] else []
+        if return_overlap[0]:
+            return arr, overlap
+        return arr
 
 
 def _as_object_array(rows, ncol):

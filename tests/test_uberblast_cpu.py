@@ -166,3 +166,35 @@ def test_nucl_flag_sets_cpu(files, oracle_as_search):
     args = '-r {qry} -q {qry} --blastn --min_id 0.45 --min_cov 50 -t 4 --min_ratio 0.25 -e 3,3 -p --gtable 11'.format(**files).split()
     self_bsn = ub.uberBlast(args)
     assert self_bsn.shape[1] == 16 and len(set(r[0] for r in self_bsn if r[0] == r[1] and r[6] == 1 and r[7] == r[12])) == 120
+
+
+def test_columnar_run_equals_the_row_by_row_run(oracle_as_search, tmp_path):
+    """RunBlast.run on columns (rows built once at the end) against the same run on object rows, stage by stage through the
+    same library calls: same tables, same Python types, same overlap lists, for the flag sets PEPPAN uses and a few more."""
+    import os
+    from peppan_b200 import uberBlast as ub, workloads
+    pool = workloads.GenePool(40, 40, seed=workloads.SEED + 13)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=20, seed=workloads.SEED + 13)
+    cut = (int(annot[7][1]) + int(annot[7][2])) // 2
+    ref, qry = os.path.join(tmp_path, 'g.fa'), os.path.join(tmp_path, 'q.fa')
+    with open(ref, 'w') as f:
+        f.write('>c1\n%s\n>c2\n%s\n' % (seq[:cut], seq[cut:]))
+    with open(qry, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    cases = [dict(methods=['blastn', 'diamond'], re_score=1, filter=[True, 0.9, 0.], linear_merge=[True, 600., 1.5], return_overlap=[True, 300, 0.6], fix_end=[0., 3.]),
+             dict(methods=['blastn', 'diamond'], re_score=1, filter=[False, 0.9, 0.], linear_merge=[False, 300., 1.2], return_overlap=[False, 300, 0.6], fix_end=[3., 3.]),
+             dict(methods=['blastn'], re_score=0, filter=[True, 0.9, 0.], linear_merge=[True, 600., 1.5], return_overlap=[True, 300, 0.6], fix_end=[0., 0.]),
+             dict(methods=['diamondSELF'], re_score=0, filter=[False, 0.9, 0.], linear_merge=[True, 300., 1.2], return_overlap=[True, 100, 0.3], fix_end=[6., 6.])]
+    for kw in cases:
+        outs = []
+        for columnar in (True, False):
+            r = ub.RunBlast(columnar=columnar).run(ref, qry, kw['methods'], 0.4, 50., 0.25, 11, 1, False, kw['re_score'], kw['filter'], kw['linear_merge'],
+                                                   kw['return_overlap'], kw['fix_end'])
+            outs.append(r if kw['return_overlap'][0] else (r, None))
+        (a, oa), (b, ob) = outs
+        assert a.shape == b.shape and a.shape[0] >= 20 and a.shape[1] == (17 if kw['linear_merge'][0] else 16)
+        for x, y in zip(a.reshape(-1).tolist(), b.reshape(-1).tolist()):
+            assert type(x) is type(y) and x == y, (x, y)
+        if oa is not None:
+            assert oa.dtype == ob.dtype and np.array_equal(oa, ob)
