@@ -162,7 +162,101 @@ def load_bsn(path):
 # iter_map_bsn / get_map_bsn build them -- are written with a small recursive TYPED codec (no pickle, no deflate), the index
 # (key -> offset, length) is written behind the values when the store is closed.
 STORE_MAGIC, STORE_END = b'PBSTORE1', b'PBSTOREX'
-(_V_NONE, _V_INT, _V_FLOAT, _V_STR, _V_BOOL, _V_LIST, _V_TUPLE, _V_ARR, _V_OBJ, _V_BYTES, _V_NPINT, _V_NPFLOAT, _V_NPBOOL, _V_NPSTR) = range(14)
+(_V_NONE, _V_INT, _V_FLOAT, _V_STR, _V_BOOL, _V_LIST, _V_TUPLE, _V_ARR, _V_OBJ, _V_BYTES, _V_NPINT, _V_NPFLOAT, _V_NPBOOL, _V_NPSTR, _V_TABLE) = range(15)
+# column kinds of a _V_TABLE (a 2-D object array stored column by column: typed columns decode through numpy, not cell by cell)
+(_C_GENERIC, _C_INT, _C_FLOAT, _C_STR, _C_NPINT64, _C_NPFLOAT64, _C_NPSTR, _C_TABLES, _C_ARRAYS) = range(9)
+_TABLE_MIN_ROWS = 8
+
+
+def _column_kind(col):
+    t = type(col[0])
+    if any(type(x) is not t for x in col):
+        return _C_GENERIC
+    if t is int:
+        return _C_INT if all(-(1 << 63) <= x < (1 << 63) for x in col) else _C_GENERIC
+    if t is float:
+        return _C_FLOAT
+    if t is str:
+        return _C_STR
+    if t is np.int64:
+        return _C_NPINT64
+    if t is np.float64:
+        return _C_NPFLOAT64
+    if t is np.str_:
+        return _C_NPSTR
+    if t is np.ndarray:
+        if all(x.dtype == object and x.ndim == 2 and x.shape[1] == col[0].shape[1] and x.shape[1] > 0 for x in col):
+            return _C_TABLES
+        if all(x.dtype == col[0].dtype and x.ndim == 1 and x.dtype.kind in 'iufb' for x in col):
+            return _C_ARRAYS
+    return _C_GENERIC
+
+
+def _enc_table(a, out):
+    import struct
+    n, c = a.shape
+    out.append(bytes([_V_TABLE]) + struct.pack('<qq', n, c))
+    for j in range(c):
+        col = [a[i, j] for i in range(n)]
+        k = _column_kind(col)
+        out.append(bytes([k]))
+        if k in (_C_INT, _C_NPINT64):
+            out.append(np.array(col, dtype='<i8').tobytes())
+        elif k in (_C_FLOAT, _C_NPFLOAT64):
+            out.append(np.array(col, dtype='<f8').tobytes())
+        elif k in (_C_STR, _C_NPSTR):
+            enc = [str(x).encode() for x in col]
+            off = np.zeros(n + 1, dtype='<i8'); off[1:] = np.cumsum([len(x) for x in enc])
+            out.append(off.tobytes() + b''.join(enc))
+        elif k == _C_TABLES:
+            cnt = np.array([x.shape[0] for x in col], dtype='<i8')
+            out.append(cnt.tobytes())
+            _enc(np.concatenate(col, axis=0) if int(cnt.sum()) else np.empty([0, col[0].shape[1]], dtype=object), out)
+        elif k == _C_ARRAYS:
+            d = col[0].dtype.str.encode()
+            cnt = np.array([len(x) for x in col], dtype='<i8')
+            out.append(bytes([len(d)]) + d + cnt.tobytes() + (np.concatenate(col).tobytes() if int(cnt.sum()) else b''))
+        else:
+            for x in col:
+                _enc(x, out)
+
+
+def _dec_table(buf, p):
+    import struct
+    n, c = struct.unpack_from('<qq', buf, p); p += 16
+    a = np.empty([n, c], dtype=object)
+    for j in range(c):
+        k = buf[p]; p += 1
+        if k in (_C_INT, _C_NPINT64, _C_FLOAT, _C_NPFLOAT64):
+            v = np.frombuffer(buf, dtype='<i8' if k in (_C_INT, _C_NPINT64) else '<f8', count=n, offset=p); p += 8 * n
+            col = v.tolist() if k in (_C_INT, _C_FLOAT) else list(v.astype(np.int64 if k == _C_NPINT64 else np.float64))
+        elif k in (_C_STR, _C_NPSTR):
+            off = np.frombuffer(buf, dtype='<i8', count=n + 1, offset=p).tolist(); p += 8 * (n + 1)
+            body = bytes(buf[p:p + off[-1]]); p += off[-1]
+            col = [body[off[i]:off[i + 1]].decode() for i in range(n)]
+            if k == _C_NPSTR:
+                col = [np.str_(x) for x in col]
+        elif k == _C_TABLES:
+            cnt = np.frombuffer(buf, dtype='<i8', count=n, offset=p).tolist(); p += 8 * n
+            big, p = _dec(buf, p)
+            col, at = [], 0
+            for m in cnt:
+                col.append(big[at:at + m].copy()); at += m
+        elif k == _C_ARRAYS:
+            dl = buf[p]; d = np.dtype(bytes(buf[p + 1:p + 1 + dl]).decode()); p += 1 + dl
+            cnt = np.frombuffer(buf, dtype='<i8', count=n, offset=p).tolist(); p += 8 * n
+            tot = sum(cnt)
+            flat = np.frombuffer(buf, dtype=d, count=tot, offset=p); p += tot * d.itemsize
+            col, at = [], 0
+            for m in cnt:
+                col.append(flat[at:at + m].copy()); at += m
+        else:
+            col = []
+            for _ in range(n):
+                x, p = _dec(buf, p); col.append(x)
+        for i in range(n):
+            a[i, j] = col[i]
+    return a, p
 
 
 def _enc(v, out):
@@ -196,7 +290,9 @@ def _enc(v, out):
             _enc(x, out)
     elif isinstance(v, np.ndarray):
         shape = struct.pack('<B', v.ndim) + b''.join(struct.pack('<q', int(n)) for n in v.shape)
-        if v.dtype == object:
+        if v.dtype == object and v.ndim == 2 and v.shape[0] >= _TABLE_MIN_ROWS and v.shape[1] > 0:
+            _enc_table(v, out)
+        elif v.dtype == object:
             out.append(bytes([_V_OBJ]) + shape)
             for x in v.reshape(-1):
                 _enc(x, out)
@@ -242,6 +338,8 @@ def _dec(buf, p):
         cnt = int(np.prod(shape)) if nd else 1
         a = np.frombuffer(buf, dtype=d, count=cnt, offset=p).reshape(shape).copy()
         return a, p + cnt * d.itemsize
+    if t == _V_TABLE:
+        return _dec_table(buf, p)
     if t == _V_OBJ:
         nd = buf[p]; shape = struct.unpack_from('<%dq' % nd, buf, p + 1); p += 1 + 8 * nd
         cnt = int(np.prod(shape)) if nd else 1

@@ -159,3 +159,37 @@ def test_flat_store_behaves_like_the_references_mapbsn(tmp_path):
     assert outs[0].shape == outs[1].shape and all(_deep_equal(x, y) for x, y in zip(outs[0].reshape(-1).tolist(), outs[1].reshape(-1).tolist()))
     col10 = sorted(float(r[10]) for r in outs[1])
     assert col10[0] == 0.1 and col10[1] > 0.99 and col10[2] == 1.0
+
+
+def test_typed_codec_stores_tables_column_by_column():
+    """2-D object arrays of >= 8 rows are written column by column (typed columns, nested tables concatenated, typed arrays
+    concatenated): the value that comes back has the same shape, cell types and values -- the layout of the per-genome
+    `bsn` array of PEPPAN.iter_map_bsn (rows of [gene, contig, score, identity, encoded sequence, id, hit rows])."""
+    rng = np.random.default_rng(11)
+    rows = []
+    for i in range(40):
+        k = 1 + int(rng.integers(0, 3))
+        hits = np.array([[int(rng.integers(1, 99)), 1001, float(rng.random()), 300, 2, 0, 1, 300, 5, 304, 0.1 if i % 3 else float(rng.random()),
+                          float(rng.integers(100, 900)), 300, 5000, '%dM' % int(rng.integers(50, 300)), int(rng.integers(0, 9999))] for _ in range(k)], dtype=object)
+        rows.append([int(rng.integers(1, 99)), 1001, np.float64(rng.random() * 100), float(rng.random()), rng.integers(0, 125, int(rng.integers(0, 40))).astype(np.uint8), i, hits])
+    bsn = np.empty([len(rows), 7], dtype=object)
+    for i, r in enumerate(rows):
+        for j, v in enumerate(r):
+            bsn[i, j] = v
+    blob = hitio.encode_value(bsn)
+    assert blob[0] == hitio._V_TABLE
+    back = hitio.decode_value(blob)
+    assert _deep_equal(back, bsn)
+    assert type(back[0, 2]) is np.float64 and type(back[0, 3]) is float and type(back[0, 0]) is int and back[0, 4].dtype == np.uint8
+    assert type(back[0, 6][0, 14]) is str and type(back[0, 6][0, 10]) is float
+    # a column of mixed types falls back to cell-by-cell values; small arrays keep the generic form
+    mixed = np.empty([9, 2], dtype=object)
+    for i in range(9):
+        mixed[i, 0] = i if i % 2 else float(i); mixed[i, 1] = None if i == 4 else 'x%d' % i
+    assert _deep_equal(hitio.decode_value(hitio.encode_value(mixed)), mixed)
+    small = bsn[:3].copy()
+    assert hitio.encode_value(small)[0] == hitio._V_OBJ and _deep_equal(hitio.decode_value(hitio.encode_value(small)), small)
+    empty_nested = np.empty([8, 1], dtype=object)
+    for i in range(8):
+        empty_nested[i, 0] = np.empty([0, 16], dtype=object)
+    assert _deep_equal(hitio.decode_value(hitio.encode_value(empty_nested)), empty_nested)

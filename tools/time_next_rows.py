@@ -1,0 +1,92 @@
+"""CPU timings of the "next" rows beside the reference's own functions, on the same inputs (run where
+/root/reference exists; the search behind N4's tables is answered by the oracle once and cached).
+python tools/time_next_rows.py > profiles/r02_next_rows_cpu.json"""
+import json, os, pickle, stat, sys, tempfile, time, types
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import numpy as np
+REF = os.environ.get('PEPPAN_REFERENCE', '/root/reference')
+stubs = tempfile.mkdtemp(prefix='pb_stubs_')
+for name in ('mmseqs', 'makeblastdb', 'diamond', 'blastn'):
+    p = os.path.join(stubs, name)
+    open(p, 'w').write('#!/bin/sh\nexit 0\n'); os.chmod(p, os.stat(p).st_mode | stat.S_IEXEC)
+os.environ['PATH'] = stubs + os.pathsep + os.environ['PATH']
+m = types.ModuleType('ete3'); m.Tree = object; sys.modules['ete3'] = m
+sys.path.insert(0, REF)
+import warnings
+warnings.simplefilter('ignore')
+import PEPPAN as P
+P.params = dict(min_cds=120., incompleteCDS='')
+if not hasattr(np.lib.npyio, 'format'):
+    np.lib.npyio.format = np.lib.format
+import pb_oracle
+from peppan_b200 import consumers, hitio, ingest, seqcodec, seqio, uberBlast as ub, workloads
+
+
+def best(f, n=3):
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter(); r = f(); ts.append(time.perf_counter() - t0)
+    return min(ts), r
+
+
+out = {'host': '%d cores of the authoring container' % (os.cpu_count() or 1)}
+# ---- N3: ingest of one bundled genome ----
+fn = os.path.join(REF, 'examples', 'GCF_000010485.combined.gff.gz')
+t_ref, (s0, c0) = best(lambda: P.iter_readGFF((fn, 'CDS', 11)), 2)
+t_our, (s1, c1) = best(lambda: ingest.iter_readGFF((fn, 'CDS', 11), min_cds=120., incomplete=''), 2)
+out['N3_iter_readGFF'] = {'input': 'GCF_000010485.combined.gff.gz (%d CDS)' % len(c0), 'reference_s': t_ref, 'ours_s': t_our, 'equal': list(c0) == list(c1) and all(c0[k] == c1[k] for k in c0)}
+
+# ---- the blastab of one full-size synthetic genome (oracle search, cached) ----
+cache = '/tmp/ub_hits.pkl'
+pool = workloads.GenePool(3000, 12000)
+tmp = '/tmp/pb_prof_cpu'; os.makedirs(tmp, exist_ok=True)
+qry, ref = os.path.join(tmp, 'exemplars.fa'), os.path.join(tmp, 'g0.fa')
+if not os.path.exists(ref):
+    seq, _ = workloads.synth_genome(pool, 0)
+    with open(qry, 'w') as f:
+        for name, s in pool.fasta_items(): f.write('>%s\n%s\n' % (name, s))
+    with open(ref, 'w') as f: f.write('>1001\n%s\n' % seq)
+if not os.path.exists(cache):
+    qn, qb, qo = seqio.to_seqset(seqio.read_fastq(qry)); rn, rb, ro = seqio.to_seqset(seqio.read_fastq(ref))
+    pickle.dump({mode: pb_oracle.search(qb, qo, rb, ro, mode, seqcodec.BLOSUM62.reshape(-1), min_id=0.4, min_cov=50, min_ratio=0.25) for mode in (1, 2)}, open(cache, 'wb'))
+res = pickle.load(open(cache, 'rb'))
+
+
+def fake(ctx, qb, qo, rb, ro, mode, *a, **k):
+    h, c = res[mode]
+    return h.copy(), c.copy(), dict(kernel_launches=0)
+
+
+ub._srch.search = fake; ub.get_context = lambda: None
+P.uberBlast = ub.uberBlast
+genome = list(seqio.read_fastq(ref).items())
+contigs = [(1001, genome[0][1])]
+work = tempfile.mkdtemp(prefix='pb_next_')
+old = os.path.join(work, 'old.npz')
+st = P.MapBsn(old, 'w'); st._save(st.conn, '1001', np.array([[1, 10, 900, '+']], dtype=object)); st.conn.close()
+ortho = os.path.join(work, 'ortho.npy'); np.save(ortho, np.zeros([0, 3], dtype=int), allow_pickle=True)
+params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+              match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+# exemplar names are integers in PEPPAN; the synthetic pool's names are integers already
+t_ref, a = best(lambda: P.iter_map_bsn((os.path.join(work, 'ref'), qry, 0, 'taxon', contigs, ortho, old, params)), 2)
+t_our, b = best(lambda: consumers.iter_map_bsn((os.path.join(work, 'ours'), qry, 0, 'taxon', contigs, ortho, old, params), store=P.MapBsn), 2)
+ra, rb = np.load(a + '.bsn.npz', allow_pickle=True), np.load(b + '.bsn.npz', allow_pickle=True)
+same = ra['bsn'].shape == rb['bsn'].shape and all(x[2] == y[2] and np.array_equal(x[4], y[4]) for x, y in zip(ra['bsn'], rb['bsn'])) and np.array_equal(ra['ovl'], rb['ovl'])
+t_ub, _ = best(lambda: ub.uberBlast(('-r %s -q %s -f -m -O --blastn --diamond --min_id 0.4 --min_cov 50 --min_ratio 0.25 --merge_gap 600 --merge_diff 1.5 -t 1 -s 1 -e 0,3 --gtable 11' % (ref, qry)).split()), 2)
+out['N4_iter_map_bsn'] = {'input': '15,000 exemplars vs one synthetic genome (%d groups); both sides call this repository\'s uberBlast() with the search answered from a cache' % len(ra['bsn']),
+                          'reference_s': t_ref, 'ours_s': t_our, 'of_which_uberBlast_s': t_ub, 'reference_loop_s': t_ref - t_ub, 'ours_loop_s': t_our - t_ub, 'equal': bool(same)}
+# ---- N2: the per-genome result through MapBsn / npz vs FlatStore ----
+bsn = ra['bsn']
+def save_ref():
+    s = P.MapBsn(os.path.join(work, 'a.npz'), 'w'); s._save(s.conn, '0', bsn); s.conn.close()
+def save_our():
+    s = hitio.FlatStore(os.path.join(work, 'b.pbs'), 'w'); s._save(s.conn, '0', bsn); s.close()
+def load_ref():
+    with P.MapBsn(os.path.join(work, 'a.npz')) as s: return s.get('0')
+def load_our():
+    with hitio.FlatStore(os.path.join(work, 'b.pbs')) as s: return s.get('0')
+out['N2_store'] = {'value': 'the bsn array of that genome (%d groups with nested hit rows and encoded sequences)' % len(bsn),
+                   'MapBsn_save_s': best(save_ref)[0], 'FlatStore_save_s': best(save_our)[0], 'MapBsn_load_s': best(load_ref)[0], 'FlatStore_load_s': best(load_our)[0],
+                   'MapBsn_bytes': os.path.getsize(os.path.join(work, 'a.npz')), 'FlatStore_bytes': os.path.getsize(os.path.join(work, 'b.pbs'))}
+print(json.dumps(out, indent=1))
