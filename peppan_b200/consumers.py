@@ -368,10 +368,12 @@ def compare_prediction(blastab, old_prediction, store=None):
     return tab[final]
 
 
-def iter_map_bsn(data, uberblast=None, store=None):
+def iter_map_bsn(data, uberblast=None, store=None, out='npz'):
     """PEPPAN.iter_map_bsn (:759-867) on this repository's pieces: the genome is written out, searched with uberBlast
     (iter_map_bsn's flag set), the hits are compared with the old predictions, grouped and scored, and `<prefix>.<id>.bsn.npz`
-    is written with the arrays the reference writes.  Returns the output prefix."""
+    is written with the arrays the reference writes.  Returns the output prefix.  `out`: 'npz' (the reference's pickled,
+    deflated file), 'flat' (`<prefix>.<id>.bsn.pbs`, the typed flat file of hitio: no pickle, no deflate) or 'memory' (nothing
+    is written, (bsn, ovl) is returned -- for get_map_bsn in one process)."""
     import os
     if uberblast is None:
         from .uberBlast import uberBlast as uberblast
@@ -389,5 +391,162 @@ def iter_map_bsn(data, uberblast=None, store=None):
     blastab = compare_prediction(blastab, old_prediction, store)
     ortho = np.load(ortho_group, allow_pickle=True)
     bsn, ovl = map_bsn_groups(blastab, overlap, seq, params, ortho)
-    np.savez_compressed(out_prefix + '.bsn.npz', bsn=bsn, ovl=ovl)
+    if out == 'memory':
+        return bsn, ovl
+    if out == 'flat':
+        from .hitio import FlatStore
+        with FlatStore(out_prefix + '.bsn.pbs', 'w') as st:
+            st.save('bsn', bsn); st.save('ovl', ovl)
+    else:
+        np.savez_compressed(out_prefix + '.bsn.npz', bsn=bsn, ovl=ovl)
     return out_prefix
+
+
+# ---- get_map_bsn (PEPPAN.py:907-983): the per-genome results merged into the four stores -------------------------------------
+class _ChunkedValues(object):
+    """Values kept under running integer keys in chunks of `size` (the `.seq` / `.mat` stores, PEPPAN.py:950-964).  Like the
+    reference, a chunk is written only once something follows it, so 1..size values are in hand until close()."""
+
+    def __init__(self, store, size=1000):
+        self.store, self.size, self.pending, self.key = store, size, [], 0
+
+    def _write(self, values):
+        chunk = np.empty(len(values), dtype=object)
+        for i, v in enumerate(values):
+            chunk[i] = v
+        self.store.save(self.key, chunk)
+        self.key += 1
+
+    def extend(self, values):
+        self.pending.extend(values)
+        while len(self.pending) > self.size:
+            self._write(self.pending[:self.size])
+            del self.pending[:self.size]
+
+    def close(self):
+        if self.pending:
+            self._write(self.pending)
+            self.pending = []
+
+
+class BsnMerger(object):
+    """Merges per-genome (bsn, ovl) results -- what iter_map_bsn writes -- into the stores PEPPAN.get_map_bsn fills:
+
+    tab   key = gene: int rows [gene, genome, score*1e4, identity*1e4, identity*1e4, group id, hits in the group], groups of
+          a genome in descending score order, genomes in arrival order, written every `flush_every` genomes (`:966-976`);
+    seq   chunks of 1,000 encoded matched sequences in group-id order (only with `save_seq`);
+    mat   chunks of 1,000 hit-row tables in group-id order;
+    clf   per 30,000 group ids one array: 30,001 row pointers (offset by 30,001) followed by the neighbours of every group
+          packed as `other id * 10 + relation` (`:933-947, :980-983`).
+
+    Group ids are shifted so that they run on over the genomes.  The stores need MapBsn's `save` / `update` only
+    (hitio.FlatStore or the reference's MapBsn)."""
+    BUCKET = 30000
+
+    def __init__(self, genomes, tab, seq, mat, clf, save_seq, flush_every=500):
+        self.genomes, self.tab, self.clf, self.flush_every = genomes, tab, clf, flush_every
+        self.seq = _ChunkedValues(seq) if save_seq else None
+        self.mat = _ChunkedValues(mat)
+        self.next_id, self.n_added = 0, 0
+        self.rows = []                    # int tables waiting for the next tab flush
+        self.links = {}                   # bucket -> [(local id, packed neighbour) arrays]
+
+    def add(self, bsn, ovl):
+        n, base = len(bsn), self.next_id
+        self.next_id += n
+        # neighbour lists: every overlap in both directions, ordered by the id that owns the entry
+        if len(ovl):
+            a, b, rel = ovl[:, 0] + base, ovl[:, 1] + base, ovl[:, 2]
+            owner = np.concatenate([a, b]); packed = np.concatenate([b, a]) * 10 + np.concatenate([rel, rel])
+            order = np.argsort(owner)                                  # the reference's (unstable) order among equal owners
+            owner, packed = owner[order], packed[order]
+            bucket = owner // self.BUCKET
+            cuts = np.flatnonzero(np.diff(bucket)) + 1
+            for lo, hi in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(owner)]])):
+                self.links.setdefault(int(bucket[lo]), []).append((owner[lo:hi] % self.BUCKET, packed[lo:hi]))
+            for k in [k for k in self.links if (k + 1) * self.BUCKET <= self.next_id]:
+                self._write_links(k)                                   # no later genome can add to these
+        if self.seq is not None:
+            self.seq.extend(bsn[:, 4])
+        self.mat.extend(bsn[:, 6])
+        # the integer table: scores and identities as 1/10,000ths, truncated
+        tab = np.empty([n, 7], dtype=np.int64)
+        tab[:, 0] = bsn[:, 0].astype(np.int64)
+        tab[:, 1] = int(self.genomes.get(bsn[0, 1], [-1])[0])
+        score = bsn[:, 2].astype(np.float64) * 10000
+        tab[:, 2] = score.astype(np.int64)
+        tab[:, 3] = tab[:, 4] = (bsn[:, 3].astype(np.float64) * 10000).astype(np.int64)
+        tab[:, 5] = bsn[:, 5].astype(np.int64) + base
+        tab[:, 6] = np.array([len(m) for m in bsn[:, 6]], dtype=np.int64) & 0xFF      # a uint8 in the reference
+        key = np.empty(n, dtype=object)
+        key[:] = list(-score)                                          # argsort of an object column, as there, for equal ties
+        self.rows.append(tab[np.argsort(key)])
+        self.n_added += 1
+        if self.n_added % self.flush_every == 0:
+            self._flush_tab()
+
+    def _flush_tab(self):
+        if not self.rows:
+            return
+        rows = np.concatenate(self.rows, axis=0)
+        self.rows = []
+        rows = rows[np.argsort(rows[:, 0], kind='stable')]
+        cuts = np.flatnonzero(np.diff(rows[:, 0])) + 1
+        self.tab.update(np.split(rows, cuts))
+
+    def _write_links(self, k):
+        parts = self.links.pop(k)
+        local = np.concatenate([p[0] for p in parts]); packed = np.concatenate([p[1] for p in parts])
+        ptr = np.zeros(self.BUCKET + 1, dtype=np.int64)
+        np.cumsum(np.bincount(local, minlength=self.BUCKET), out=ptr[1:])
+        self.clf.save(k, np.concatenate([ptr + (self.BUCKET + 1), packed]))
+
+    def close(self):
+        self._flush_tab()
+        if self.seq is not None:
+            self.seq.close()
+        self.mat.close()
+        for k in sorted(self.links):
+            self._write_links(k)
+
+
+def load_genome_result(out_prefix, unlink=True):
+    """(bsn, ovl) of one genome as iter_map_bsn left it: `<prefix>.bsn.pbs` (typed flat file) or `<prefix>.bsn.npz`"""
+    import os
+    flat = out_prefix + '.bsn.pbs'
+    if os.path.exists(flat):
+        from .hitio import FlatStore
+        with FlatStore(flat) as st:
+            res = st.get('bsn'), st.get('ovl')
+        path = flat
+    else:
+        path = out_prefix + '.bsn.npz'
+        with np.load(path, allow_pickle=True) as z:
+            res = z['bsn'], z['ovl']
+    if unlink:
+        os.unlink(path)
+    return res
+
+
+def get_map_bsn(prefix, clust, genomes, ortho_group, old_prediction, conn, seq_conn, mat_conn, clf_conn, save_seq, params,
+                pool=None, mapper=None, store=None):
+    """PEPPAN.get_map_bsn (:907-983).  `genomes`: contig -> [genome, sequence]; one search task per genome, run through `pool`
+    (anything with imap_unordered; results arrive as files) or in this process (results stay in memory); `params` and `pool`
+    are module globals in the reference.  `mapper`: the per-genome function (iter_map_bsn of this module by default)."""
+    if len(genomes) == 0:
+        raise ValueError('no genomes')
+    taxa = {}
+    for contig, (taxon, sequence) in genomes.items():
+        taxa.setdefault(taxon, []).append([contig, sequence])
+    tasks = [(prefix, clust, gid, taxon, contigs, ortho_group, old_prediction, params) for gid, (taxon, contigs) in enumerate(taxa.items())]
+    merger = BsnMerger(genomes, conn, seq_conn, mat_conn, clf_conn, save_seq)
+    if pool is not None:
+        import functools
+        fn = mapper or functools.partial(iter_map_bsn, store=store, out='flat')
+        results = (load_genome_result(p) for p in pool.imap_unordered(fn, tasks))
+    else:
+        fn = mapper or (lambda task: iter_map_bsn(task, store=store, out='memory'))
+        results = ((r if isinstance(r, tuple) else load_genome_result(r)) for r in map(fn, tasks))
+    for bsn, ovl in results:
+        merger.add(bsn, ovl)
+    merger.close()

@@ -162,7 +162,7 @@ def load_bsn(path):
 # iter_map_bsn / get_map_bsn build them -- are written with a small recursive TYPED codec (no pickle, no deflate), the index
 # (key -> offset, length) is written behind the values when the store is closed.
 STORE_MAGIC, STORE_END = b'PBSTORE1', b'PBSTOREX'
-(_V_NONE, _V_INT, _V_FLOAT, _V_STR, _V_BOOL, _V_LIST, _V_TUPLE, _V_ARR, _V_OBJ, _V_BYTES, _V_NPINT, _V_NPFLOAT, _V_NPBOOL, _V_NPSTR, _V_TABLE) = range(15)
+(_V_NONE, _V_INT, _V_FLOAT, _V_STR, _V_BOOL, _V_LIST, _V_TUPLE, _V_ARR, _V_OBJ, _V_BYTES, _V_NPINT, _V_NPFLOAT, _V_NPBOOL, _V_NPSTR, _V_TABLE, _V_COLUMN) = range(16)
 # column kinds of a _V_TABLE (a 2-D object array stored column by column: typed columns decode through numpy, not cell by cell)
 (_C_GENERIC, _C_INT, _C_FLOAT, _C_STR, _C_NPINT64, _C_NPFLOAT64, _C_NPSTR, _C_TABLES, _C_ARRAYS) = range(9)
 _TABLE_MIN_ROWS = 8
@@ -292,6 +292,10 @@ def _enc(v, out):
         shape = struct.pack('<B', v.ndim) + b''.join(struct.pack('<q', int(n)) for n in v.shape)
         if v.dtype == object and v.ndim == 2 and v.shape[0] >= _TABLE_MIN_ROWS and v.shape[1] > 0:
             _enc_table(v, out)
+        elif v.dtype == object and v.ndim == 1 and v.shape[0] >= _TABLE_MIN_ROWS and _column_kind(list(v)) in (_C_TABLES, _C_ARRAYS):
+            # a vector of tables / of typed arrays (the 1,000-value chunks of the `.mat` / `.seq` stores): one table of one column
+            out.append(bytes([_V_COLUMN]))
+            _enc_table(v.reshape(-1, 1), out)
         elif v.dtype == object:
             out.append(bytes([_V_OBJ]) + shape)
             for x in v.reshape(-1):
@@ -340,6 +344,9 @@ def _dec(buf, p):
         return a, p + cnt * d.itemsize
     if t == _V_TABLE:
         return _dec_table(buf, p)
+    if t == _V_COLUMN:
+        a, p = _dec_table(buf, p + 1)
+        return a.reshape(-1), p
     if t == _V_OBJ:
         nd = buf[p]; shape = struct.unpack_from('<%dq' % nd, buf, p + 1); p += 1 + 8 * nd
         cnt = int(np.prod(shape)) if nd else 1

@@ -174,3 +174,145 @@ def test_iter_map_bsn_writes_what_the_reference_writes(PEPPAN, oracle_as_search,
     assert ra['ovl'].shape == rb['ovl'].shape and np.array_equal(ra['ovl'], rb['ovl'])
     col10 = [float(t[10]) for g in rb['bsn'] for t in g[6]]
     assert sum(1 for v in col10 if v > 0.1) >= 20 and sum(1 for v in col10 if 0.1 < v < 0.99) >= 3      # overlap fractions were exercised
+
+
+class _SerialPool(object):
+    """stands in for the multiprocessing pool behind PEPPAN.get_map_bsn (`pool.imap_unordered`, PEPPAN.py:924)"""
+    def imap_unordered(self, fn, tasks):
+        return map(fn, tasks)
+
+    def close(self):
+        pass
+
+    def join(self):
+        pass
+
+
+def _stores(cls, d, mode='w'):
+    return [cls(os.path.join(d, name), mode) for name in ('tab.npz', 'seq.npz', 'mat.npz', 'clf.npz')]
+
+
+def _store_equal(a, b):
+    if sorted(a.keys()) != sorted(b.keys()):
+        return False
+    return all(_same(a.get(k), b.get(k)) for k in a.keys())
+
+
+def _synthetic_result(rng, gid, n_groups):
+    """a (bsn, ovl) pair shaped like iter_map_bsn's output: rows [gene, contig, score, identity, encoded sequence, id, hit rows]"""
+    bsn = np.empty([n_groups, 7], dtype=object)
+    for i in range(n_groups):
+        k = 1 + int(rng.integers(0, 3))
+        hits = np.array([[int(rng.integers(1, 60)), 5000 + gid, float(rng.random()), 300, 2, 0, 1, 300, 5, 304, 0.1, float(rng.integers(100, 900)), 300, 5000,
+                          '%dM' % int(rng.integers(50, 300)), int(rng.integers(0, 9999))] for _ in range(k)], dtype=object)
+        # coarse scores so that equal scores occur (the order among ties is the reference's argsort of an object column)
+        bsn[i] = [int(rng.integers(1, 60)), 5000 + gid, np.float64(int(rng.integers(1, 40)) * 12.3456789), float(int(rng.integers(50, 100)) / 100. + 1e-5),
+                  rng.integers(0, 125, int(rng.integers(1, 30))).astype(np.uint8), i, hits]
+    m = int(rng.integers(0, 3 * n_groups)) if gid % 7 else 0
+    ovl = np.stack([rng.integers(0, n_groups, m), rng.integers(0, n_groups, m), rng.integers(0, 3, m)], axis=1).astype(np.int64).reshape(-1, 3)
+    return bsn, ovl
+
+
+@pytest.mark.parametrize('n_genomes,n_groups,save_seq', [(3, 40, True), (7, 450, False), (503, 61, True)])
+def test_bsn_merger_fills_the_stores_like_the_references_get_map_bsn(PEPPAN, monkeypatch, tmp_path, n_genomes, n_groups, save_seq):
+    """consumers.get_map_bsn / BsnMerger against PEPPAN.get_map_bsn (:907-983) on the same per-genome results: the four stores
+    (integer hit table per gene, sequence chunks, hit-row chunks, conflict lists per 30,000 group ids) hold equal values.
+    503 genomes x 61 groups cross the 500-genome flush of the table, the 1,000-value chunks and the 30,000-id bucket."""
+    if not hasattr(np.lib.npyio, 'format'):
+        monkeypatch.setattr(np.lib.npyio, 'format', np.lib.format, raising=False)
+    from peppan_b200 import hitio
+    rng = np.random.default_rng(5 + n_genomes)
+    results = [_synthetic_result(rng, g, n_groups + (g % 3)) for g in range(n_genomes)]
+    genomes = {5000 + g: [700 + g, 'ACGT'] for g in range(n_genomes)}
+
+    def ref_task(data):
+        prefix, gid = data[0], data[2]
+        bsn, ovl = results[gid]
+        np.savez_compressed('%s.%d.bsn.npz' % (prefix, gid), bsn=bsn.copy(), ovl=ovl.copy())
+        return '%s.%d' % (prefix, gid)
+
+    monkeypatch.setattr(PEPPAN, 'pool', _SerialPool(), raising=False)
+    monkeypatch.setattr(PEPPAN, 'iter_map_bsn', ref_task)
+    monkeypatch.setattr(PEPPAN, 'logger', lambda *a, **k: None)
+    dr, do = os.path.join(tmp_path, 'ref'), os.path.join(tmp_path, 'ours')
+    os.makedirs(dr); os.makedirs(do)
+    ref = _stores(PEPPAN.MapBsn, dr)
+    PEPPAN.get_map_bsn(os.path.join(dr, 'run'), 'x', genomes, 'o', 'p', ref[0], ref[1], ref[2], ref[3], save_seq)
+    for s in ref:
+        s.conn.close()
+    ours = _stores(hitio.FlatStore, do)
+    consumers.get_map_bsn(os.path.join(do, 'run'), 'x', genomes, 'o', 'p', ours[0], ours[1], ours[2], ours[3], save_seq, params={},
+                          mapper=lambda data: tuple(x.copy() for x in results[data[2]]))
+    for s in ours:
+        s.close()
+    ref, ours = _stores(PEPPAN.MapBsn, dr, 'r'), _stores(hitio.FlatStore, do, 'r')
+    total = sum(len(r[0]) for r in results)
+    assert ref[0].size() >= 50 and sum(len(v) for v in ours[0].values()) == total
+    for a, b in zip(ref, ours):
+        assert _store_equal(a, b)
+    assert ref[1].size() == ((total + 999) // 1000 if save_seq else 0) and ref[2].size() == (total + 999) // 1000
+    assert ref[3].size() == (total + 29999) // 30000
+    # the same through files and a pool (typed flat files instead of pickled npz), into the reference's own store class
+    if n_genomes <= 7:
+        d2 = os.path.join(tmp_path, 'pool'); os.makedirs(d2)
+
+        def flat_task(data):
+            with hitio.FlatStore('%s.%d.bsn.pbs' % (data[0], data[2]), 'w') as st:
+                st.save('bsn', results[data[2]][0]); st.save('ovl', results[data[2]][1])
+            return '%s.%d' % (data[0], data[2])
+
+        third = _stores(PEPPAN.MapBsn, d2)
+        consumers.get_map_bsn(os.path.join(d2, 'run'), 'x', genomes, 'o', 'p', third[0], third[1], third[2], third[3], save_seq, params={},
+                              pool=_SerialPool(), mapper=flat_task)
+        for s in third:
+            s.conn.close()
+        assert not [f for f in os.listdir(d2) if f.endswith('.pbs')]
+        for a, b in zip(ref, _stores(PEPPAN.MapBsn, d2, 'r')):
+            assert _store_equal(a, b)
+
+
+def test_get_map_bsn_end_to_end_equals_the_reference(PEPPAN, oracle_as_search, monkeypatch, tmp_path):
+    """Three genomes through search -> comparison -> grouping -> merge: the reference's get_map_bsn (its own iter_map_bsn per
+    genome, pickled .bsn.npz files, MapBsn stores) beside consumers.get_map_bsn (results kept in memory, flat stores)."""
+    monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)
+    if not hasattr(np.lib.npyio, 'format'):
+        monkeypatch.setattr(np.lib.npyio, 'format', np.lib.format, raising=False)
+    from peppan_b200 import hitio
+    pool = workloads.GenePool(30, 30, seed=workloads.SEED + 53)
+    clust = os.path.join(tmp_path, 'exemplar.fa')
+    with open(clust, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    genomes = {}
+    for g in range(3):
+        seq, annot = workloads.synth_genome(pool, g, n_acc_per_genome=15, seed=workloads.SEED + 53)
+        mid = annot[len(annot) // 2]
+        cut = (int(mid[1]) + int(mid[2])) // 2          # inside a gene: its two halves form a merge group (overlap entries, without
+        genomes[1000 + 2 * g] = [900 + g, seq[:cut]]    # which the reference's function ends in an unbound `del ovl`, :990)
+        genomes[1001 + 2 * g] = [900 + g, seq[cut:]]
+    ortho = os.path.join(tmp_path, 'ortho.npy')
+    np.save(ortho, np.zeros([0, 3], dtype=int), allow_pickle=True)
+    params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+    monkeypatch.setattr(PEPPAN, 'pool', _SerialPool(), raising=False)
+    monkeypatch.setattr(PEPPAN, 'params', params)
+    monkeypatch.setattr(PEPPAN, 'logger', lambda *a, **k: None)
+    dr, do = os.path.join(tmp_path, 'ref'), os.path.join(tmp_path, 'ours')
+    os.makedirs(dr); os.makedirs(do)
+    for cls, d in ((PEPPAN.MapBsn, dr), (hitio.FlatStore, do)):                # empty old-annotation stores, each in its own format
+        st = cls(os.path.join(d, 'old.npz'), 'w')
+        st._save(st.conn, '0', np.zeros([0, 4], dtype=object))
+        st.close() if hasattr(st, 'close') else st.conn.close()
+    ref = _stores(PEPPAN.MapBsn, dr)
+    PEPPAN.get_map_bsn(os.path.join(dr, 'run'), clust, genomes, ortho, os.path.join(dr, 'old.npz'), ref[0], ref[1], ref[2], ref[3], True)
+    for s in ref:
+        s.conn.close()
+    ours = _stores(hitio.FlatStore, do)
+    consumers.get_map_bsn(os.path.join(do, 'run'), clust, genomes, ortho, os.path.join(do, 'old.npz'), ours[0], ours[1], ours[2], ours[3], True, params)
+    for s in ours:
+        s.close()
+    ref, ours = _stores(PEPPAN.MapBsn, dr, 'r'), _stores(hitio.FlatStore, do, 'r')
+    assert ref[0].size() >= 40 and ref[2].size() == 1
+    for a, b in zip(ref, ours):
+        assert _store_equal(a, b)
+    assert sorted(os.listdir(do)) == ['clf.npz', 'mat.npz', 'old.npz', 'seq.npz', 'tab.npz']          # no per-genome files left behind

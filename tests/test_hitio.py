@@ -193,3 +193,27 @@ def test_typed_codec_stores_tables_column_by_column():
     for i in range(8):
         empty_nested[i, 0] = np.empty([0, 16], dtype=object)
     assert _deep_equal(hitio.decode_value(hitio.encode_value(empty_nested)), empty_nested)
+
+
+def test_typed_codec_stores_vectors_of_tables_and_arrays_concatenated():
+    """1-D object arrays of same-width object tables (a `.mat` chunk of get_map_bsn) or of typed arrays (a `.seq` chunk) are
+    written as one concatenated table / array with the row counts; shapes, cell types and values come back."""
+    rng = np.random.default_rng(12)
+    mats = np.empty(30, dtype=object)
+    for i in range(30):
+        k = 1 + int(rng.integers(0, 3))
+        mats[i] = np.array([[int(rng.integers(1, 99)), 1001, float(rng.random()), '%dM' % int(rng.integers(50, 300)), np.float64(rng.random())] for _ in range(k)], dtype=object)
+    blob = hitio.encode_value(mats)
+    assert blob[0] == hitio._V_COLUMN
+    back = hitio.decode_value(blob)
+    assert back.shape == (30,) and _deep_equal(back, mats)
+    assert type(back[3][0, 0]) is int and type(back[3][0, 2]) is float and type(back[3][0, 3]) is str and type(back[3][0, 4]) is np.float64
+    seqs = np.empty(12, dtype=object)
+    for i in range(12):
+        seqs[i] = rng.integers(0, 125, int(rng.integers(0, 50))).astype(np.uint8)
+    back = hitio.decode_value(hitio.encode_value(seqs))
+    assert hitio.encode_value(seqs)[0] == hitio._V_COLUMN and back.shape == (12,) and _deep_equal(back, seqs) and back[0].dtype == np.uint8
+    ragged = np.empty(9, dtype=object)                       # tables of different widths keep the generic form
+    for i in range(9):
+        ragged[i] = np.empty([1, 2 + i % 2], dtype=object); ragged[i][:] = 1
+    assert hitio.encode_value(ragged)[0] == hitio._V_OBJ and _deep_equal(hitio.decode_value(hitio.encode_value(ragged)), ragged)

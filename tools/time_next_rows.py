@@ -89,4 +89,47 @@ def load_our():
 out['N2_store'] = {'value': 'the bsn array of that genome (%d groups with nested hit rows and encoded sequences)' % len(bsn),
                    'MapBsn_save_s': best(save_ref)[0], 'FlatStore_save_s': best(save_our)[0], 'MapBsn_load_s': best(load_ref)[0], 'FlatStore_load_s': best(load_our)[0],
                    'MapBsn_bytes': os.path.getsize(os.path.join(work, 'a.npz')), 'FlatStore_bytes': os.path.getsize(os.path.join(work, 'b.pbs'))}
+# ---- N2: the merge of per-genome results (get_map_bsn, PEPPAN.py:907-983): pickled + deflated .bsn.npz files into MapBsn zips, vs
+# typed flat files (or memory) into flat stores; the per-genome result is the one computed above, 20 genomes ----
+class SerialPool(object):
+    def imap_unordered(self, fn, tasks): return map(fn, tasks)
+    def close(self): pass
+    def join(self): pass
+NG = 20
+ovl0 = ra['ovl']
+if not len(ovl0):                  # the synthetic genome has no overlapping groups; the bundled genomes have a few hundred
+    ii = np.arange(0, len(bsn) - 1, 15); ovl0 = np.stack([ii, ii + 1, ii % 3], axis=1).astype(np.int64)
+gen20 = {1001 + g: [7000 + g, 'ACGT'] for g in range(NG)}
+P.pool = SerialPool(); P.logger = lambda *a, **k: None
+def ref_task(data):
+    b = bsn.copy(); b.T[1] = 1001 + data[2]
+    np.savez_compressed('%s.%d.bsn.npz' % (data[0], data[2]), bsn=b, ovl=ovl0); return '%s.%d' % (data[0], data[2])
+def flat_task(data):
+    b = bsn.copy(); b.T[1] = 1001 + data[2]
+    with hitio.FlatStore('%s.%d.bsn.pbs' % (data[0], data[2]), 'w') as st:
+        st.save('bsn', b); st.save('ovl', ovl0)
+    return '%s.%d' % (data[0], data[2])
+def mem_task(data):
+    b = bsn.copy(); b.T[1] = 1001 + data[2]
+    return b, ovl0.copy()
+def merge_ref():
+    d = tempfile.mkdtemp(prefix='m_ref_', dir=work); P.iter_map_bsn = ref_task
+    st = [P.MapBsn(os.path.join(d, n), 'w') for n in ('tab.npz', 'seq.npz', 'mat.npz', 'clf.npz')]
+    P.get_map_bsn(os.path.join(d, 'r'), qry, gen20, ortho, old, st[0], st[1], st[2], st[3], True)
+    for x in st: x.conn.close()
+    return d
+def merge_our(task, pool):
+    d = tempfile.mkdtemp(prefix='m_our_', dir=work)
+    st = [hitio.FlatStore(os.path.join(d, n), 'w') for n in ('tab.npz', 'seq.npz', 'mat.npz', 'clf.npz')]
+    consumers.get_map_bsn(os.path.join(d, 'r'), qry, gen20, ortho, old, st[0], st[1], st[2], st[3], True, params, pool=pool, mapper=task)
+    for x in st: x.close()
+    return d
+t_ref, d_ref = best(merge_ref, 2)
+t_flat, d_flat = best(lambda: merge_our(flat_task, SerialPool()), 2)
+t_mem, d_mem = best(lambda: merge_our(mem_task, None), 2)
+with P.MapBsn(os.path.join(d_ref, 'tab.npz')) as a, hitio.FlatStore(os.path.join(d_mem, 'tab.npz')) as b:
+    same_tab = sorted(a.keys()) == sorted(b.keys()) and all(np.array_equal(a.get(k), b.get(k)) for k in a.keys())
+out['N2_get_map_bsn'] = {'input': '%d genomes x %d groups (the result above per genome), sequences kept' % (NG, len(bsn)),
+                         'reference_s': t_ref, 'ours_flat_files_s': t_flat, 'ours_in_memory_s': t_mem, 'tab_store_equal': bool(same_tab),
+                         'note': 'both timings include writing the per-genome results (savez_compressed / flat file / nothing)'}
 print(json.dumps(out, indent=1))
