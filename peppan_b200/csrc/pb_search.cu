@@ -47,6 +47,7 @@ struct SeedSpec {
 
 struct DevSpec {
     int k, base, xdrop, min_ungapped, lane_budget;
+    int bulk_tile;                              // interior tiles of the seed scan arrive by one bulk copy (cp.async.bulk)
     uint8_t seedmap[32];
     int8_t score[1024];
 };
@@ -216,7 +217,8 @@ __global__ void build_ends_kernel(const uint32_t* keys, int64_t nvalid, const ui
 }
 
 // ---- K1b: seed scan + ungapped X-drop ---------------------------------------------------------------
-// Each block stages a tile of the target codes in shared memory with 128-bit loads (with a halo on both sides, so
+// Each block stages a tile of the target codes in shared memory (one cp.async.bulk per interior tile, guarded 128-bit loads for the
+// edge tiles; with a halo on both sides, so
 // that every residue an extension can touch comes from the tile); every thread owns SCAN_PER_THREAD consecutive
 // positions, rolls the k-mer key across them and looks the table up (phase 1).  The seeds of the tile -- (position, slot)
 // for every entry of every position's slot range -- are then worked off in batches of SCAN_QCAP through two queues in
@@ -239,6 +241,9 @@ struct SeedQ { uint32_t qpos, tpos; };
 
 #ifndef PB_SCAN_BLOCKS
 #define PB_SCAN_BLOCKS 4
+#endif
+#ifndef PB_SEED_BULK_DEFAULT
+#define PB_SEED_BULK_DEFAULT 1               // PB_SEED_BULK=0 in the environment: guarded 128-bit loads for every tile (the r02 form before)
 #endif
 __global__ void __launch_bounds__(SCAN_THREADS, PB_SCAN_BLOCKS) seed_scan_kernel(const uint8_t* __restrict__ tcodes, int64_t tn,
                                                                  const uint8_t* __restrict__ qcodes, int64_t qn,
@@ -267,8 +272,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, PB_SCAN_BLOCKS) seed_scan_kernel
     bool act = false;
     uint32_t l_qpos = 1;
     int l_pos = 0, l_dir = 0, l_c0 = 0, l_cur = 0, l_best = 0, l_blen = 0, l_lbest = 0, l_llen = 0;
+    // interior tiles are fetched by ONE bulk copy of the copy engine (cp.async.bulk, global -> shared, completion counted in
+    // bytes on an mbarrier) issued by thread 0; the first and last tiles of the array keep the guarded 128-bit loads
+    __shared__ __align__(8) unsigned long long tile_bar;
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&tile_bar), tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    uint32_t bar_phase = 0;
+    if (sp.bulk_tile && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE; t0 < tn; t0 += (int64_t)gridDim.x * SCAN_TILE) {
         __syncthreads();
+        if (sp.bulk_tile && t0 >= SCAN_HALO && t0 + SCAN_TILE + SCAN_HALO <= tn) {
+            constexpr uint32_t BYTES = SCAN_TILE + 2 * SCAN_HALO;                    // a multiple of 16; source and tile 16-byte aligned
+            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // the tile was read through the generic proxy
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_s), "r"(BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(tile_s), "l"(tcodes + (t0 - SCAN_HALO)), "r"(BYTES), "r"(bar_s) : "memory");
+            }
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar_s), "r"(bar_phase) : "memory");
+            bar_phase ^= 1;
+        } else
         // stage [t0 - HALO, t0 + TILE + HALO) (t0 and HALO are multiples of 16: 128-bit loads); sentinel outside the array
         for (int i = threadIdx.x * 16; i < SCAN_TILE + 2 * SCAN_HALO; i += blockDim.x * 16) {
             const int64_t g = t0 - SCAN_HALO + i;
@@ -887,6 +915,7 @@ static int search_impl(pb_ctx* ctx, const pb_seqset* query, const pb_seqset* tar
     ds.k = spec.k; ds.base = spec.base; ds.xdrop = spec.xdrop; ds.min_ungapped = spec.min_ungapped;
     // residues per side a lane extends before handing the seed to the warp-per-seed kernel: long enough for random seeds to
     // die (expected drift -1.75 / base against X-drop 20 for nucleotides, about -1 / residue against 12 for proteins)
+    { const char* e = getenv("PB_SEED_BULK"); ds.bulk_tile = e ? atoi(e) != 0 : PB_SEED_BULK_DEFAULT; }
     ds.lane_budget = nt ? 48 : 32;                // multiples of SCAN_CH; k + budget <= SCAN_HALO
     memcpy(ds.seedmap, spec.seedmap, 32);
     if (nt) {
