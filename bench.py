@@ -555,6 +555,52 @@ def uberblast_leg(ctx, genomes, pool, n=2):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def stage_leg(ctx, genomes, pool, n=2):
+    """The stage as PEPPAN drives it (PEPPAN.py:1903-1904): get_map_bsn over genomes -- per genome the genome file, uberBlast
+    (both searches on the GPU + the post-search chain), comparison with old predictions, grouping / scoring of the hits -- and
+    the merge into the tab / seq / mat / conflicts stores; this repository's consumers (peppan_b200/consumers.py), one process,
+    per-genome results kept in memory, flat stores.  Reported beside the device-level numbers: it is the host code around the
+    search that sets this pace.  Never fails the bench: an exception is reported in the line."""
+    try:
+        from peppan_b200 import consumers, hitio, uberBlast as ub
+        ub.set_context(ctx)
+        tmp = tempfile.mkdtemp(prefix='pb_stage_')
+        try:
+            qry = os.path.join(tmp, 'exemplars.fa')
+            with open(qry, 'w') as f:
+                for name, s in pool.fasta_items():
+                    f.write('>%s\n%s\n' % (name, s))
+            ortho = os.path.join(tmp, 'ortho.npy'); np.save(ortho, np.zeros([0, 3], dtype=int), allow_pickle=True)
+            old = os.path.join(tmp, 'old.pbs')
+            with hitio.FlatStore(old, 'w') as st:
+                st.save('0', np.zeros([0, 4], dtype=object))
+            params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                          match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+
+            def run(tag, subset):
+                d = os.path.join(tmp, tag); os.makedirs(d)
+                gen = {1001 + idx: [7001 + idx, seq.tobytes().decode()] for idx, seq, _ in subset}
+                stores = [hitio.FlatStore(os.path.join(d, nm), 'w') for nm in ('tab.pbs', 'seq.pbs', 'mat.pbs', 'clf.pbs')]
+                t0 = time.perf_counter()
+                consumers.get_map_bsn(os.path.join(d, 'run'), qry, gen, ortho, old, stores[0], stores[1], stores[2], stores[3], True, params)
+                for x in stores:
+                    x.close()
+                dt = time.perf_counter() - t0
+                with hitio.FlatStore(os.path.join(d, 'tab.pbs')) as tab:
+                    groups = sum(len(v) for v in tab.values())
+                return dt, groups
+            run('warm', genomes[:1])
+            dt, groups = run('timed', genomes[1:1 + n])
+            k = max(len(genomes[1:1 + n]), 1)
+            return {'call': 'consumers.get_map_bsn(...) = PEPPAN.get_map_bsn (PEPPAN.py:907-983): per genome uberBlast (iter_map_bsn flag set) + compare_prediction + '
+                            'grouping / scoring, merged into flat tab / seq / mat / conflicts stores; one process, host code single-threaded',
+                    'seconds_per_genome': dt / k, 'genes_per_s': (N_CORE + N_ACC) / (dt / k), 'groups_per_genome': groups / k, 'genomes_timed': k}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as e:                                  # noqa: BLE001 -- an extra of the line, never its failure
+        return {'error': '%s: %s' % (type(e).__name__, e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -647,7 +693,7 @@ def main():
     e2e_value = total_cells / (e2e_ms * 1e-3) / 1e9
     assert int(out['score'].astype(np.int64).sum()) == checksum
 
-    c4 = c3 = ubl = None
+    c4 = c3 = ubl = stg = None
     if not args.no_search:
         pool, qb, qo = exemplar_set()
         qpin = ctx.pinned_empty(qb.shape, np.uint8); qpin[:] = qb
@@ -659,6 +705,7 @@ def main():
             c3 = config3_leg(ctx, rank, world, pg, c3_genomes, qpin, qo, args.batch)
         if rank == 0 and (genomes or c3_genomes):
             ubl = uberblast_leg(ctx, genomes or c3_genomes, pool)
+            stg = stage_leg(ctx, genomes or c3_genomes, pool)
 
     barrier(pg)
     if rank != 0:
@@ -699,6 +746,7 @@ def main():
         'config4': c4,
         'config3': c3,
         'uberblast': ubl,
+        'stage': stg,
     }
     print(json.dumps(line), flush=True)
     ctx.close()

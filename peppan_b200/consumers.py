@@ -33,6 +33,12 @@ def _excl_cumsum_within(values, first, counts):
 def score_hits(rows, seq, gtable=11):
     """Per hit of `rows` (object rows with the uberBlast columns): (sc, x) where sc is the reference's frame / stop-limited
     match length (PEPPAN.py:818-834) and x the base-encoded matched sequence with query gaps as 0 (:835)."""
+    sc, enc, off = _score_hits_flat(rows, seq, gtable)
+    return sc, [enc[off[i]:off[i + 1]] for i in range(len(rows))]
+
+
+def _score_hits_flat(rows, seq, gtable=11):
+    """score_hits with the encoded sequences of all hits in one array: (sc, flat, offsets)"""
     nh = len(rows)
     names = [n for n, _ in seq]
     cidx = {n: i for i, n in enumerate(names)}
@@ -55,45 +61,49 @@ def score_hits(rows, seq, gtable=11):
     np.add.at(sc3, (hid[is_m], frame[is_m]), L[is_m])
     sc = sc3.max(axis=1) if nh else np.zeros(0, np.int64)
 
-    # matched sequence with '-' for query insertions, all hits in one flat byte array
+    # matched sequence with '-' for query insertions, all hits in one flat byte array: every match run is one slice copy out
+    # of the genome (plus strand) or out of its reverse complement (minus strand: the reverse complement of [send, sstart], :813)
     sub_before = _excl_cumsum_within(np.where(is_m | is_d, L, 0), first, nops)      # subject bases consumed before the run
     emit = is_m | is_i
-    eL, eh, em, esub = L[emit], hid[emit], is_m[emit], sub_before[emit]
-    ms_len = np.bincount(eh, weights=eL, minlength=nh).astype(np.int64)
+    emit_before = _excl_cumsum_within(np.where(emit, L, 0), first, nops)            # characters written before the run
+    ms_len = np.bincount(hid[emit], weights=L[emit], minlength=nh).astype(np.int64)
     ms_off = np.concatenate([[0], np.cumsum(ms_len)]).astype(np.int64)
     total = int(ms_off[-1])
-    run_start = np.cumsum(eL) - eL
-    k = np.arange(total, dtype=np.int64) - np.repeat(run_start, eL)
-    ch_hit = np.repeat(eh, eL)
-    ch_m = np.repeat(em, eL)
     s_start = np.array([r[8] for r in rows], dtype=np.int64); s_end = np.array([r[9] for r in rows], dtype=np.int64)
     contig = np.array([cidx[r[1]] for r in rows], dtype=np.int64)
-    plus = s_start < s_end                                           # otherwise the reverse complement of [send, sstart] (:813)
-    idx = np.repeat(esub, eL) + k                                    # position in the matched (oriented) subject segment
-    gpos = soff[contig[ch_hit]] + np.where(plus[ch_hit], s_start[ch_hit] - 1 + idx, s_start[ch_hit] - 1 - idx)
-    gpos = np.where(ch_m, gpos, 0)
-    base = sbuf[gpos] if total else np.zeros(0, np.uint8)
-    ms = np.where(ch_m, np.where(plus[ch_hit], base, _COMP[base]), ord('-')).astype(np.uint8)
+    plus = s_start < s_end
+    src = sbuf
+    seg0 = soff[contig] + s_start - 1                                # first base of the oriented segment in `src`
+    if nh and not plus.all():
+        rcbuf = np.empty_like(sbuf)
+        for c in range(len(names)):
+            rcbuf[soff[c]:soff[c + 1]] = _COMP[sbuf[soff[c]:soff[c + 1]]][::-1]
+        src = np.concatenate([sbuf, rcbuf])
+        clen = soff[contig + 1] - soff[contig]
+        seg0 = np.where(plus, seg0, len(sbuf) + soff[contig] + clen - s_start)
+    ms = np.full(total, ord('-'), dtype=np.uint8)
+    m_dst = (ms_off[hid] + emit_before)[is_m]; m_src = (seg0[hid] + sub_before)[is_m]
+    for d, a, n in zip(m_dst.tolist(), m_src.tolist(), L[is_m].tolist()):
+        ms[d:d + n] = src[a:a + n]
 
-    # longest stretch between in-frame stop codons, codons counted from the start of the matched string (:833)
-    ncod = ms_len // 3
-    cod_hit = np.repeat(np.arange(nh), ncod)
-    cod_k = np.arange(int(ncod.sum()), dtype=np.int64) - np.repeat(np.cumsum(ncod) - ncod, ncod)
-    c0 = ms_off[cod_hit] + 3 * cod_k
-    if len(c0):
-        a, b, c = ms[c0], ms[c0 + 1], ms[c0 + 2]
-        stop = (a == ord('T')) & (((b == ord('A')) & ((c == ord('A')) | (c == ord('G')))) | ((gtable != 4) & (b == ord('G')) & (c == ord('A'))))
-    else:
-        stop = np.zeros(0, dtype=bool)
-    sh, sp = cod_hit[stop], 3 * cod_k[stop]
-    prev = np.concatenate([[0], sp[:-1]]) if len(sp) else sp
-    prev = np.where(np.concatenate([[True], sh[1:] != sh[:-1]]) if len(sp) else np.zeros(0, bool), 0, prev)
+    # longest stretch between in-frame stop codons, codons counted from the start of the matched string (:833): every 'T' that
+    # starts a stop triplet anywhere, then only those in frame and whole inside their hit's string
     sc2 = np.zeros(nh, dtype=np.int64); last = np.zeros(nh, dtype=np.int64)
-    np.maximum.at(sc2, sh, sp - prev); np.maximum.at(last, sh, sp)
+    if total >= 3:
+        a, b, c = ms[:-2], ms[1:-1], ms[2:]
+        stop = (a == ord('T')) & (((b == ord('A')) & ((c == ord('A')) | (c == ord('G')))) | ((gtable != 4) & (b == ord('G')) & (c == ord('A'))))
+        pos = np.flatnonzero(stop)
+        sh = np.searchsorted(ms_off, pos, side='right') - 1
+        rel = pos - ms_off[sh]
+        keep = (rel % 3 == 0) & (rel + 3 <= ms_len[sh])
+        sh, sp = sh[keep], rel[keep]
+        if len(sp):
+            prev = np.concatenate([[0], sp[:-1]])
+            prev = np.where(np.concatenate([[True], sh[1:] != sh[:-1]]), 0, prev)
+            np.maximum.at(sc2, sh, sp - prev); np.maximum.at(last, sh, sp)
     sc2 = np.maximum(sc2, ms_len - last)
     sc = np.minimum(sc, sc2 + 3)
-    enc = _BASE[ms]
-    return sc, [enc[ms_off[i]:ms_off[i + 1]] for i in range(nh)]
+    return sc, _BASE[ms], ms_off
 
 
 def _passes(value, qlen, p):
@@ -124,7 +134,7 @@ def map_bsn_groups(blastab, overlap, seq, params, ortho_pairs=None):
     conv_a, conv_b = np.tile(-1, nid), np.tile(-1, nid)
 
     members = [t for g in groups for t in g[6]]
-    sc, enc = score_hits(members, seq, params.get('gtable', 11))
+    sc, enc, eoff = _score_hits_flat(members, seq, params.get('gtable', 11))
     qs = np.array([t[6] for t in members], dtype=np.int64); qe = np.array([t[7] for t in members], dtype=np.int64)
     qlen = np.array([t[12] for t in members], dtype=np.int64)
     iden = np.array([t[2] for t in members], dtype=np.float64); ovl = np.array([t[10] for t in members], dtype=np.float64)
@@ -132,18 +142,29 @@ def map_bsn_groups(blastab, overlap, seq, params, ortho_pairs=None):
     r = np.sqrt(scf / qlen * ovl)                                    # :838-840
     msc = (sc * iden) * np.sqrt(sc * r)
     amsc = msc / (qe - qs + 1)
-    at = 0
+    # the matched sequences of every group on the query's coordinates, all groups in one buffer (later members of a merge group
+    # overwrite earlier ones where they overlap, :836)
+    ng = len(groups)
+    gcount = np.array([len(g[6]) for g in groups], dtype=np.int64)
+    gfirst = np.cumsum(gcount) - gcount
+    glen = qlen[gfirst] if ng else np.zeros(0, np.int64)             # length of the first member's query (:804)
+    goff = np.concatenate([[0], np.cumsum(glen)]).astype(np.int64)
+    flat = np.zeros(int(goff[-1]), dtype=np.uint8)
+    dst = np.repeat(goff[:-1], gcount) + qs - 1
+    for d, a, b in zip(dst.tolist(), eoff[:-1].tolist(), eoff[1:].tolist()):
+        flat[d:d + b - a] = enc[a:b]
+    hit_id = np.array([t[15] for t in members], dtype=np.int64)
+    mgroup = np.repeat(np.arange(ng), gcount)
+    single = np.repeat(gcount == 1, gcount)
+    conv_a[hit_id[single]] = mgroup[single]; conv_b[hit_id[~single]] = mgroup[~single]
     for gid, group in enumerate(groups):
-        n = len(group[6])
-        group[4] = np.zeros(group[6][0][12], dtype=np.uint8)
+        n, at = int(gcount[gid]), int(gfirst[gid])
         group[5] = gid
         group[6] = np.array(group[6])
-        hit_ids = group[6].T[15].astype(int)
-        (conv_a if n == 1 else conv_b)[hit_ids] = gid
-        spans = []
-        for j in range(at, at + n):
-            group[4][qs[j] - 1:qs[j] + len(enc[j]) - 1] = enc[j]
-            spans.append([members[j][6], members[j][7], amsc[j], msc[j]])
+        if n == 1:
+            group[2] = msc[at]
+            continue
+        spans = [[members[j][6], members[j][7], amsc[j], msc[j]] for j in range(at, at + n)]
         # members of a merge group that overlap on the query: the better average score keeps the shared part (:842-850;
         # np.max(x, 0) of a scalar is x itself -- the products are not clamped)
         for i in range(1, n):
@@ -154,15 +175,22 @@ def map_bsn_groups(blastab, overlap, seq, params, ortho_pairs=None):
                 else:
                     c[0] = p[1] + 1; c[3] = np.max(c[2] * (c[1] - c[0] + 1), 0)
         group[2] = np.sum([c[3] for c in spans])
-        at += n
     o0, o1 = overlap.T[0], overlap.T[1]
     overlap = np.vstack([np.vstack([m, n]).T[(m >= 0) & (n >= 0)] for m in (conv_a[o0], conv_b[o0]) for n in (conv_a[o1], conv_b[o1])] +
                         [np.vstack([conv_a, conv_b]).T[(conv_a >= 0) & (conv_b >= 0)]])
+    # three bases per byte, base 5, in thirds of the gene (:852-853): byte k of a gene of length n (s = ceil(n / 3)) holds the bases
+    # k, s + k and 2 s + k (0 behind the end), for all groups at once
+    third = (glen + 2) // 3
+    poff = np.concatenate([[0], np.cumsum(third)]).astype(np.int64)
+    k = np.arange(int(poff[-1]), dtype=np.int64) - np.repeat(poff[:-1], third)
+    base, s_rep, n_rep = np.repeat(goff[:-1], third), np.repeat(third, third), np.repeat(glen, third)
+    packed = flat[base + k] * np.uint8(25) + flat[base + s_rep + k] * np.uint8(5)
+    tail = 2 * s_rep + k
+    inside = tail < n_rep
+    packed[inside] += flat[(base + tail)[inside]]
+    for gid, group in enumerate(groups):
+        group[4] = packed[poff[gid]:poff[gid + 1]]
     bsn = np.array(groups, dtype=object)
-    # three bases per byte, base 5, in thirds of the gene (:852-853)
-    for row in bsn:
-        b = row[4]; s = int(np.ceil(len(b) / 3))
-        row[4] = (b[:s] * 25 + b[s:2 * s] * 5 + np.concatenate([b, np.zeros(-b.shape[0] % 3, dtype=int)])[2 * s:]).astype(np.uint8)
     if overlap.shape[0]:
         og = ortho_pairs if ortho_pairs is not None else np.zeros([0, 3], dtype=int)
         og = og[og.T[2] != 0] if len(og) else og

@@ -327,13 +327,17 @@ class RunBlast(object):
         pieces = ['%d%s' % (a, 'MID'[b]) for a, b in zip((ops >> 2).tolist(), (ops & 3).tolist())]
         coff_l = coff.tolist()
         arr = np.empty([len(order), ncol], dtype=object)
-        for k, r in enumerate(order):
-            row = arr[k]
-            row[0] = qn[L['qi'][r]]; row[1] = rn[L['si'][r]]; row[2] = iden_l[r]; row[3] = L['alen'][r]; row[4] = L['mism'][r]; row[5] = L['gopen'][r]
-            row[6] = qs[r]; row[7] = qe[r]; row[8] = ss[r]; row[9] = se[r]; row[10] = L['evalue'][r]; row[11] = score_l[r]
-            row[12] = L['qlen'][r]; row[13] = L['slen'][r]; row[14] = ''.join(pieces[coff_l[r]:coff_l[r + 1]]); row[15] = hid[r]
+        if len(order):
+            # column by column (lists of Python values: the cells keep their types); the group lists cell by cell
+            cols = [[qn[L['qi'][r]] for r in order], [rn[L['si'][r]] for r in order], [iden_l[r] for r in order]] + \
+                   [[L[k][r] for r in order] for k in ('alen', 'mism', 'gopen')] + [[v[r] for r in order] for v in (qs, qe, ss, se)] + \
+                   [[L['evalue'][r] for r in order], [score_l[r] for r in order], [L['qlen'][r] for r in order], [L['slen'][r] for r in order],
+                    [''.join(pieces[coff_l[r]:coff_l[r + 1]]) for r in order], [hid[r] for r in order]]
+            for j, c in enumerate(cols):
+                arr[:, j] = c
             if merge:
-                row[16] = [gscore[k], giden[k], glen[k]] + gids[goff[k]:goff[k + 1]] if goff[k + 1] > goff[k] else []
+                for k in range(len(order)):
+                    arr[k, 16] = [gscore[k], giden[k], glen[k]] + gids[goff[k]:goff[k + 1]] if goff[k + 1] > goff[k] else []
         if return_overlap[0]:
             return arr, overlap
         return arr
