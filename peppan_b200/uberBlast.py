@@ -136,6 +136,25 @@ def _columns_from_hits(hits, cigar, protein, min_id, min_cov, min_ratio):
     return col
 
 
+_RANKS = {}
+
+
+def _name_ranks(names):
+    """(rank of every name in string order, the names as an object array); kept per list object -- the parsed sequence files
+    are kept per file version (seqio.read_fastq_cached), so repeated calls on one exemplar file sort its names once"""
+    hit = _RANKS.get(id(names))
+    if hit is not None and hit[0] is names:
+        return hit[1]
+    rank = np.empty(len(names), dtype=np.int64)
+    rank[np.argsort(np.array([str(x) for x in names]), kind='stable')] = np.arange(len(names))
+    obj = np.empty(len(names), dtype=object)
+    obj[:] = names
+    if len(_RANKS) >= 8:
+        _RANKS.clear()
+    _RANKS[id(names)] = (names, (rank, obj))
+    return rank, obj
+
+
 def _concat_columns(tabs):
     out = {name: np.concatenate([t[name] for t in tabs]) for name in tabs[0] if name not in ('ops', 'coff')}
     out['ops'] = np.concatenate([t['ops'] for t in tabs])
@@ -286,8 +305,7 @@ class RunBlast(object):
             t['iden'] = iden[k]; score = score[k]; hit_id = hit_id[k]
             n = len(k)
         # ranks of the names in string order: what the final sort and the chain's grouping compare
-        qrank = np.empty(len(qn), dtype=np.int64); qrank[np.argsort(np.array([str(x) for x in qn]), kind='stable')] = np.arange(len(qn))
-        rrank = np.empty(len(rn), dtype=np.int64); rrank[np.argsort(np.array([str(x) for x in rn]), kind='stable')] = np.arange(len(rn))
+        (qrank, qobj), (rrank, robj) = _name_ranks(qn), _name_ranks(rn)
         col = [np.ascontiguousarray(v, dtype=np.int32) for v in (qrank[t['qi']], rrank[t['si']], t['qs'], t['qe'], t['ss'], t['se'], t['qlen'], t['slen'], hit_id)]
         iden = np.ascontiguousarray(t['iden'], dtype=np.float64); score = np.ascontiguousarray(score, dtype=np.float64)
         ops = np.ascontiguousarray(t['ops'], dtype=np.uint32) if len(t['ops']) else np.zeros(1, dtype=np.uint32)
@@ -319,20 +337,17 @@ class RunBlast(object):
         # ---- rows, once ----
         merge = bool(linear_merge[0])
         ncol = 17 if merge else 16
-        L = {k: t[k].tolist() for k in ('qi', 'si', 'alen', 'mism', 'gopen', 'evalue', 'qlen', 'slen')}
-        qs, qe, ss, se = col[2].tolist(), col[3].tolist(), col[4].tolist(), col[5].tolist()       # as the chain left them (fixEnd)
-        iden_l = iden.tolist()
-        score_l = score.tolist() if re_score == 1 else t['score'].tolist()                          # raw scores stay integers (:294)
-        hid = hit_id.tolist()
         pieces = ['%d%s' % (a, 'MID'[b]) for a, b in zip((ops >> 2).tolist(), (ops & 3).tolist())]
         coff_l = coff.tolist()
         arr = np.empty([len(order), ncol], dtype=object)
         if len(order):
             # column by column (lists of Python values: the cells keep their types); the group lists cell by cell
-            cols = [[qn[L['qi'][r]] for r in order], [rn[L['si'][r]] for r in order], [iden_l[r] for r in order]] + \
-                   [[L[k][r] for r in order] for k in ('alen', 'mism', 'gopen')] + [[v[r] for r in order] for v in (qs, qe, ss, se)] + \
-                   [[L['evalue'][r] for r in order], [score_l[r] for r in order], [L['qlen'][r] for r in order], [L['slen'][r] for r in order],
-                    [''.join(pieces[coff_l[r]:coff_l[r + 1]]) for r in order], [hid[r] for r in order]]
+            o = np.array(order, dtype=np.int64)
+            raw = score if re_score == 1 else t['score']                                            # raw scores stay integers (:294)
+            cols = [qobj[t['qi'][o]].tolist(), robj[t['si'][o]].tolist(), iden[o].tolist(), t['alen'][o].tolist(), t['mism'][o].tolist(), t['gopen'][o].tolist(),
+                    col[2][o].tolist(), col[3][o].tolist(), col[4][o].tolist(), col[5][o].tolist(),        # as the chain left them (fixEnd)
+                    t['evalue'][o].tolist(), raw[o].tolist(), t['qlen'][o].tolist(), t['slen'][o].tolist(),
+                    [''.join(pieces[coff_l[r]:coff_l[r + 1]]) for r in order], hit_id[o].tolist()]
             for j, c in enumerate(cols):
                 arr[:, j] = c
             if merge:
