@@ -555,7 +555,7 @@ def uberblast_leg(ctx, genomes, pool, n=2):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def stage_leg(ctx, genomes, pool, n=2):
+def stage_leg(ctx, genomes, pool, n=2, nb=32, batch=16, grouped_search=None):
     """The stage as PEPPAN drives it (PEPPAN.py:1903-1904): get_map_bsn over genomes -- per genome the genome file, uberBlast
     (both searches on the GPU + the post-search chain), comparison with old predictions, grouping / scoring of the hits -- and
     the merge into the tab / seq / mat / conflicts stores; this repository's consumers (peppan_b200/consumers.py), one process,
@@ -592,9 +592,34 @@ def stage_leg(ctx, genomes, pool, n=2):
             run('warm', genomes[:1])
             dt, groups = run('timed', genomes[1:1 + n])
             k = max(len(genomes[1:1 + n]), 1)
-            return {'call': 'consumers.get_map_bsn(...) = PEPPAN.get_map_bsn (PEPPAN.py:907-983): per genome uberBlast (iter_map_bsn flag set) + compare_prediction + '
-                            'grouping / scoring, merged into flat tab / seq / mat / conflicts stores; one process, host code single-threaded',
-                    'seconds_per_genome': dt / k, 'genes_per_s': (N_CORE + N_ACC) / (dt / k), 'groups_per_genome': groups / k, 'genomes_timed': k}
+            res = {'call': 'consumers.get_map_bsn(...) = PEPPAN.get_map_bsn (PEPPAN.py:907-983): per genome uberBlast (iter_map_bsn flag set) + compare_prediction + '
+                           'grouping / scoring, merged into flat tab / seq / mat / conflicts stores; one process, host code single-threaded',
+                   'seconds_per_genome': dt / k, 'genes_per_s': (N_CORE + N_ACC) / (dt / k), 'groups_per_genome': groups / k, 'genomes_timed': k}
+            # the same stage with the device fed in batches (pb_search_grouped) and the host loops in worker processes
+            try:
+                workers = max(2, min(16, (os.cpu_count() or 4) - 2))
+                subset = genomes[:nb]
+
+                def run_batched(tag):
+                    d = os.path.join(tmp, tag); os.makedirs(d)
+                    gen = {1001 + idx: [7001 + idx, seq.tobytes().decode()] for idx, seq, _ in subset}
+                    stores = [hitio.FlatStore(os.path.join(d, nm), 'w') for nm in ('tab.pbs', 'seq.pbs', 'mat.pbs', 'clf.pbs')]
+                    t0 = time.perf_counter()
+                    consumers.get_map_bsn_batched(os.path.join(d, 'run'), qry, gen, ortho, old, stores[0], stores[1], stores[2], stores[3], True, params,
+                                                  ctx=ctx, workers=workers, batch=batch, grouped_search=grouped_search, timeout=120.)
+                    for x in stores:
+                        x.close()
+                    dt = time.perf_counter() - t0
+                    with hitio.FlatStore(os.path.join(d, 'tab.pbs')) as tab:
+                        return dt, sum(len(v) for v in tab.values())
+                bdt, bgroups = run_batched('batched')
+                res['batched'] = {'call': 'consumers.get_map_bsn_batched(...): %d genomes per pb_search_grouped call on this process, post-search chain + consumer '
+                                          'loops in %d spawned worker processes (no device), merge in genome order; includes starting the workers' % (batch, workers),
+                                  'genomes': len(subset), 'seconds': bdt, 'seconds_per_genome': bdt / max(len(subset), 1),
+                                  'genes_per_s': (N_CORE + N_ACC) * len(subset) / bdt, 'groups_per_genome': bgroups / max(len(subset), 1), 'workers': workers}
+            except Exception as e:                          # noqa: BLE001
+                res['batched'] = {'error': '%s: %s' % (type(e).__name__, e)}
+            return res
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
     except Exception as e:                                  # noqa: BLE001 -- an extra of the line, never its failure

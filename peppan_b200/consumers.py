@@ -396,12 +396,13 @@ def compare_prediction(blastab, old_prediction, store=None):
     return tab[final]
 
 
-def iter_map_bsn(data, uberblast=None, store=None, out='npz'):
+def iter_map_bsn(data, uberblast=None, store=None, out='npz', tables=None):
     """PEPPAN.iter_map_bsn (:759-867) on this repository's pieces: the genome is written out, searched with uberBlast
     (iter_map_bsn's flag set), the hits are compared with the old predictions, grouped and scored, and `<prefix>.<id>.bsn.npz`
     is written with the arrays the reference writes.  Returns the output prefix.  `out`: 'npz' (the reference's pickled,
     deflated file), 'flat' (`<prefix>.<id>.bsn.pbs`, the typed flat file of hitio: no pickle, no deflate) or 'memory' (nothing
-    is written, (bsn, ovl) is returned -- for get_map_bsn in one process)."""
+    is written, (bsn, ovl) is returned -- for get_map_bsn in one process).  `tables`: the record tables of this genome's searches
+    when they were run elsewhere (uberBlast(..., tables=...))."""
     import os
     if uberblast is None:
         from .uberBlast import uberBlast as uberblast
@@ -413,7 +414,7 @@ def iter_map_bsn(data, uberblast=None, store=None, out='npz'):
     flags = '-r {0} -q {1} -f -m -O --blastn{8} --min_id {2} --min_cov {3} --min_ratio {4} --merge_gap {5} --merge_diff {6} -t 1{9} -e 0,3 --gtable {7}'.format(
         gfile, clust, params['match_identity'] - 0.1, params['match_frag_len'], params['match_frag_prop'], params['link_gap'], params['link_diff'], params['gtable'],
         '' if params['noDiamond'] else ' --diamond', '' if params['noDiamond'] else ' -s 1')
-    blastab, overlap = uberblast(flags.split())
+    blastab, overlap = uberblast(flags.split()) if tables is None else uberblast(flags.split(), tables=tables)
     os.unlink(gfile)
     blastab.T[:2] = blastab.T[:2].astype(int)
     blastab = compare_prediction(blastab, old_prediction, store)
@@ -577,4 +578,91 @@ def get_map_bsn(prefix, clust, genomes, ortho_group, old_prediction, conn, seq_c
         results = ((r if isinstance(r, tuple) else load_genome_result(r)) for r in map(fn, tasks))
     for bsn, ovl in results:
         merger.add(bsn, ovl)
+    merger.close()
+
+
+# ---- the same stage with the GPU fed in batches and the host loops in worker processes -------------------------------------
+def _stage_worker(task):
+    """worker process (no device): one genome's record tables -> (bsn, ovl) as typed bytes"""
+    from .hitio import encode_value
+    data, tables, store = task
+    bsn, ovl = iter_map_bsn(data, store=store, out='memory', tables=tables)
+    return encode_value(bsn), encode_value(ovl)
+
+
+def search_modes(params):
+    from . import search
+    return (search.MODE_NT,) if params['noDiamond'] else (search.MODE_NT, search.MODE_PROT6)
+
+
+def grouped_tables(ctx, qset, batch, params, grouped_search=None):
+    """One grouped search per mode for the genomes of `batch` ([(taxon, [[contig, sequence], ...]), ...]) against the exemplar
+    set `qset` = (names, bytes, offsets): per genome {mode: (hits, cigar)} with s_id = index of the contig in the genome, i.e.
+    the tables uberBlast's own searches of that genome would return (search.search_grouped; thresholds of iter_map_bsn's
+    command line, PEPPAN.py:768-771)."""
+    from . import search, seqio
+    if grouped_search is None:
+        grouped_search = search.search_grouped
+    items, groups = [], []
+    for g, (_, contigs) in enumerate(batch):
+        for name, sequence in contigs:
+            items.append((name, sequence.upper())); groups.append(g)
+    _, tb, to = seqio.to_seqset(items)
+    per_genome = [dict() for _ in batch]
+    for mode in search_modes(params):
+        res, _ = grouped_search(ctx, qset[1], qset[2], tb, to, np.array(groups, dtype=np.int32), mode, min_id=params['match_identity'] - 0.1,
+                                min_cov=params['match_frag_len'], min_ratio=params['match_frag_prop'], gtable=params['gtable'])
+        for g, tab in enumerate(res):
+            per_genome[g][mode] = tab
+    return per_genome
+
+
+def get_map_bsn_batched(prefix, clust, genomes, ortho_group, old_prediction, conn, seq_conn, mat_conn, clf_conn, save_seq, params,
+                        ctx=None, workers=0, batch=16, store=None, grouped_search=None, timeout=600.):
+    """get_map_bsn laid out for one GPU and many host cores: this process owns the device and searches `batch` genomes per
+    pb_search_grouped call (all modes); the post-search chain and the consumer loops of every genome (uberBlast without a
+    search, compare_prediction, grouping / scoring) run in `workers` spawned processes that never touch the device; results
+    come back as typed bytes, in genome order, and are merged here while the next batch is searched.  workers = 0: everything in
+    this process.  The stores end up with the values of get_map_bsn (genomes in input order).  `store`: class of the
+    old-annotation file (must be importable in the workers)."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    from . import seqio
+    from .hitio import decode_value
+    if len(genomes) == 0:
+        raise ValueError('no genomes')
+    if ctx is None and grouped_search is None:
+        from .uberBlast import get_context
+        ctx = get_context()
+    taxa = {}
+    for contig, (taxon, sequence) in genomes.items():
+        taxa.setdefault(taxon, []).append([contig, sequence])
+    taxa = list(taxa.items())
+    _, qset = seqio.read_fastq_cached(clust)
+    merger = BsnMerger(genomes, conn, seq_conn, mat_conn, clf_conn, save_seq)
+    pool = cf.ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context('spawn')) if workers > 0 else None
+    pending = []                                     # futures (or results) in genome order
+
+    def drain(keep):
+        while len(pending) > keep:
+            r = pending.pop(0)
+            if pool is not None:
+                b, o = r.result(timeout=timeout)
+                r = decode_value(b), decode_value(o)
+            merger.add(*r)
+    try:
+        for b0 in range(0, len(taxa), batch):
+            part = taxa[b0:b0 + batch]
+            tables = grouped_tables(ctx, qset, part, params, grouped_search)
+            for k, (taxon, contigs) in enumerate(part):
+                data = (prefix, clust, b0 + k, taxon, contigs, ortho_group, old_prediction, params)
+                if pool is not None:
+                    pending.append(pool.submit(_stage_worker, (data, tables[k], store)))
+                else:
+                    pending.append(iter_map_bsn(data, store=store, out='memory', tables=tables[k]))
+            drain(batch if pool is not None else 0)  # the previous batch is merged while this one is worked on
+        drain(0)
+    finally:
+        if pool is not None:
+            pool.shutdown(wait=False, cancel_futures=True)
     merger.close()

@@ -170,10 +170,10 @@ _TABLE_MIN_ROWS = 8
 
 def _column_kind(col):
     t = type(col[0])
-    if any(type(x) is not t for x in col):
+    if len(set(map(type, col))) != 1:
         return _C_GENERIC
     if t is int:
-        return _C_INT if all(-(1 << 63) <= x < (1 << 63) for x in col) else _C_GENERIC
+        return _C_INT if -(1 << 63) <= min(col) and max(col) < (1 << 63) else _C_GENERIC
     if t is float:
         return _C_FLOAT
     if t is str:
@@ -197,7 +197,7 @@ def _enc_table(a, out):
     n, c = a.shape
     out.append(bytes([_V_TABLE]) + struct.pack('<qq', n, c))
     for j in range(c):
-        col = [a[i, j] for i in range(n)]
+        col = a[:, j].tolist()                 # the cells themselves (object dtype: no conversion)
         k = _column_kind(col)
         out.append(bytes([k]))
         if k in (_C_INT, _C_NPINT64):
@@ -241,21 +241,24 @@ def _dec_table(buf, p):
             big, p = _dec(buf, p)
             col, at = [], 0
             for m in cnt:
-                col.append(big[at:at + m].copy()); at += m
+                col.append(big[at:at + m]); at += m         # disjoint row ranges of one freshly decoded table
         elif k == _C_ARRAYS:
             dl = buf[p]; d = np.dtype(bytes(buf[p + 1:p + 1 + dl]).decode()); p += 1 + dl
             cnt = np.frombuffer(buf, dtype='<i8', count=n, offset=p).tolist(); p += 8 * n
             tot = sum(cnt)
-            flat = np.frombuffer(buf, dtype=d, count=tot, offset=p); p += tot * d.itemsize
+            flat = np.frombuffer(buf, dtype=d, count=tot, offset=p).copy(); p += tot * d.itemsize
             col, at = [], 0
             for m in cnt:
-                col.append(flat[at:at + m].copy()); at += m
+                col.append(flat[at:at + m]); at += m        # disjoint ranges of one writable copy
         else:
             col = []
             for _ in range(n):
                 x, p = _dec(buf, p); col.append(x)
-        for i in range(n):
-            a[i, j] = col[i]
+        if k in (_C_INT, _C_FLOAT, _C_STR, _C_NPINT64, _C_NPFLOAT64, _C_NPSTR):
+            a[:, j] = col                          # scalars: one assignment keeps the cell objects
+        else:
+            for i in range(n):
+                a[i, j] = col[i]
     return a, p
 
 

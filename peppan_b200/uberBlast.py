@@ -164,10 +164,12 @@ def _concat_columns(tabs):
 
 
 class RunBlast(object):
-    def __init__(self, ctx=None, columnar=True):
+    def __init__(self, ctx=None, columnar=True, tables=None):
         self.qrySeq = self.refSeq = None
         self.ctx = ctx
         self.columnar = columnar      # False: every stage on object rows (the path tools supplied through the seam take)
+        self.tables = tables          # {mode: (hits, cigar)}: record tables of searches that were already run for these two files
+                                      # (one grouped search of many genomes, search.search_grouped); no search is launched then
         self.stats = []
         self.raw = []          # (mode, hits, cigar) of every search of this run: the record tables behind the rows
 
@@ -187,8 +189,14 @@ class RunBlast(object):
         return self._qset, self._rset
 
     def _search(self, mode):
-        ctx = self.ctx or get_context()
         (qn, qb, qo), (rn, rb, ro) = self._sets()
+        if self.tables is not None:
+            hits, cigar = self.tables[mode]
+            if len(hits) and (int(hits['q_id'].max()) >= len(qn) or int(hits['s_id'].max()) >= len(rn)):
+                raise ValueError('uberBlast: the record table handed in does not belong to these sequence files')
+            self.raw.append((mode, hits, cigar))
+            return qn, rn, hits, cigar
+        ctx = self.ctx or get_context()
         hits, cigar, st = _srch.search(ctx, qb, qo, rb, ro, mode, self.min_id, self.min_cov, self.min_ratio, self.table_id)
         self.stats.append(st)
         self.raw.append((mode, hits, cigar))
@@ -366,8 +374,10 @@ def _as_object_array(rows, ncol):
     return arr
 
 
-def uberBlast(args, extPool=None):
-    """Argument set identical to the reference's (modules/uberBlast.py:566-593)."""
+def uberBlast(args, extPool=None, tables=None):
+    """Argument set identical to the reference's (modules/uberBlast.py:566-593).  `tables` (not in the reference): {search mode:
+    (hits, cigar)} of searches already run for these two files -- one grouped search of many genomes on the process that owns the
+    GPU (search.search_grouped) -- so that this call is only the post-search chain and runs without a device."""
     import argparse
     parser = argparse.ArgumentParser(description='Five different alignment methods. ')
     parser.add_argument('-r', '--reference', help='[INPUT; REQUIRED] filename for the reference. This is normally a genomic assembly. ', required=True)
@@ -398,7 +408,7 @@ def uberBlast(args, extPool=None):
         args.process = extPool
     methods = [m for m in ('blastn', 'diamond', 'diamondSELF') if getattr(args, m)]
     fix_end = list(map(float, args.fix_end.split(',')[-2:]))
-    runner = RunBlast()
+    runner = RunBlast(tables=tables)
     data = runner.run(args.reference, args.query, methods, args.min_id, args.min_cov, args.min_ratio, args.gtable, args.n_thread,
                           args.process, args.re_score,
                           [args.filter, args.filter_cov, args.filter_score],

@@ -316,3 +316,60 @@ def test_get_map_bsn_end_to_end_equals_the_reference(PEPPAN, oracle_as_search, m
     for a, b in zip(ref, ours):
         assert _store_equal(a, b)
     assert sorted(os.listdir(do)) == ['clf.npz', 'mat.npz', 'old.npz', 'seq.npz', 'tab.npz']          # no per-genome files left behind
+
+
+def test_batched_stage_equals_the_sequential_one(oracle, oracle_as_search, tmp_path):
+    """consumers.get_map_bsn_batched (grouped search of several genomes by the process that owns the device, post-search chain
+    and consumer loops in spawned worker processes that get the record tables handed in, merge in genome order) fills the
+    four stores with the values of consumers.get_map_bsn (one uberBlast call with its own searches per genome).  The grouped
+    search is stood in by the oracle genome by genome -- on the GPU, search.search_grouped returns per-genome tables equal to
+    per-genome searches (tests/test_real_genomes.py)."""
+    from peppan_b200 import hitio, seqcodec
+    pool = workloads.GenePool(30, 30, seed=workloads.SEED + 59)
+    clust = os.path.join(tmp_path, 'exemplar.fa')
+    with open(clust, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    genomes = {}
+    for g in range(5):
+        seq, annot = workloads.synth_genome(pool, g, n_acc_per_genome=15, seed=workloads.SEED + 59)
+        mid = annot[len(annot) // 2]
+        cut = (int(mid[1]) + int(mid[2])) // 2
+        genomes[1000 + 2 * g] = [900 + g, seq[:cut].lower() if g == 1 else seq[:cut]]      # one genome in lower case
+        genomes[1001 + 2 * g] = [900 + g, seq[cut:]]
+    ortho = os.path.join(tmp_path, 'ortho.npy')
+    np.save(ortho, np.zeros([0, 3], dtype=int), allow_pickle=True)
+    params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+    old = os.path.join(tmp_path, 'old.pbs')
+    with hitio.FlatStore(old, 'w') as st:
+        st.save('1000', np.array([[5, 100, 900, '+'], [6, 1200, 2000, '-']], dtype=object))
+    calls = []
+
+    def grouped(ctx, qb, qo, tb, to, groups, mode, min_id, min_cov, min_ratio, gtable):
+        res = []
+        for g in range(int(groups.max()) + 1):
+            idx = np.flatnonzero(groups == g)
+            a = int(to[idx[0]])
+            res.append(oracle.search(qb, qo, tb[a:int(to[idx[-1] + 1])], to[idx[0]:idx[-1] + 2] - a, mode, seqcodec.BLOSUM62.reshape(-1),
+                                     min_id=min_id, min_cov=min_cov, min_ratio=min_ratio, gtable=gtable))
+        calls.append((mode, len(res)))
+        return res, {}
+
+    outs = {}
+    for tag, workers in (('sequential', None), ('inline', 0), ('pool', 2)):
+        d = os.path.join(tmp_path, tag); os.makedirs(d)
+        stores = _stores(hitio.FlatStore, d)
+        if workers is None:
+            consumers.get_map_bsn(os.path.join(d, 'run'), clust, genomes, ortho, old, stores[0], stores[1], stores[2], stores[3], True, params)
+        else:
+            consumers.get_map_bsn_batched(os.path.join(d, 'run'), clust, genomes, ortho, old, stores[0], stores[1], stores[2], stores[3], True, params,
+                                          workers=workers, batch=2, grouped_search=grouped, timeout=120.)
+        for s in stores:
+            s.close()
+        outs[tag] = _stores(hitio.FlatStore, d, 'r')
+    assert calls.count((1, 2)) == 4 and calls.count((2, 1)) == 2                 # batches of 2, 2, 1 genomes, both modes, twice
+    assert outs['sequential'][0].size() >= 40
+    for tag in ('inline', 'pool'):
+        for a, b in zip(outs['sequential'], outs[tag]):
+            assert _store_equal(a, b), tag
