@@ -377,7 +377,8 @@ def _as_object_array(rows, ncol):
 def uberBlast(args, extPool=None, tables=None):
     """Argument set identical to the reference's (modules/uberBlast.py:566-593).  `tables` (not in the reference): {search mode:
     (hits, cigar)} of searches already run for these two files -- one grouped search of many genomes on the process that owns the
-    GPU (search.search_grouped) -- so that this call is only the post-search chain and runs without a device."""
+    GPU (search.search_grouped) -- so that this call is only the post-search chain and runs without a device.  Not a fallback:
+    nothing is searched on the host; a mode that is asked for and has no table raises KeyError."""
     import argparse
     parser = argparse.ArgumentParser(description='Five different alignment methods. ')
     parser.add_argument('-r', '--reference', help='[INPUT; REQUIRED] filename for the reference. This is normally a genomic assembly. ', required=True)
