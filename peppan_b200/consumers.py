@@ -112,6 +112,8 @@ def _passes(value, qlen, p):
 
 
 def map_bsn_groups(blastab, overlap, seq, params, ortho_pairs=None):
+    if len(blastab) == 0:              # a genome without a single hit (the reference stops with an exception here, :775)
+        return np.empty([0, 7], dtype=object), np.zeros([0, 3], dtype=np.int64)
     nid = int(np.max(blastab.T[15])) + 1
     ids = np.zeros(nid, dtype=bool)
     singles, merged = [], {}
@@ -482,6 +484,11 @@ class BsnMerger(object):
 
     def add(self, bsn, ovl):
         n, base = len(bsn), self.next_id
+        if n == 0:                         # a genome without groups adds nothing (and still counts towards the flush interval)
+            self.n_added += 1
+            if self.n_added % self.flush_every == 0:
+                self._flush_tab()
+            return
         self.next_id += n
         # neighbour lists: every overlap in both directions, ordered by the id that owns the entry
         if len(ovl):

@@ -373,3 +373,40 @@ def test_batched_stage_equals_the_sequential_one(oracle, oracle_as_search, tmp_p
     for tag in ('inline', 'pool'):
         for a, b in zip(outs['sequential'], outs[tag]):
             assert _store_equal(a, b), tag
+
+
+def test_a_genome_without_hits_adds_nothing(oracle_as_search, tmp_path):
+    """Where the reference stops with an exception (np.max of an empty column, PEPPAN.py:775), the stage here carries on: the
+    genome yields an empty result and the merged stores hold the other genomes only."""
+    from peppan_b200 import hitio
+    pool = workloads.GenePool(20, 10, seed=workloads.SEED + 61)
+    clust = os.path.join(tmp_path, 'exemplar.fa')
+    with open(clust, 'w') as f:
+        for n, s in pool.fasta_items():
+            f.write('>%s\n%s\n' % (n, s))
+    rng = np.random.default_rng(3)
+    seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=5, seed=workloads.SEED + 61)
+    mid = annot[len(annot) // 2]
+    cut = (int(mid[1]) + int(mid[2])) // 2
+    genomes = {2000: [800, ''.join('ACGT'[i] for i in rng.integers(0, 4, 30000))],      # random: no exemplar matches it
+               2001: [801, seq[:cut]], 2002: [801, seq[cut:]]}
+    ortho = os.path.join(tmp_path, 'ortho.npy')
+    np.save(ortho, np.zeros([0, 3], dtype=int), allow_pickle=True)
+    params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+    old = os.path.join(tmp_path, 'old.pbs')
+    with hitio.FlatStore(old, 'w') as st:
+        st.save('0', np.zeros([0, 4], dtype=object))
+    bsn, ovl = consumers.iter_map_bsn((os.path.join(tmp_path, 'x'), clust, 0, 800, [[2000, genomes[2000][1]]], ortho, old, params), out='memory')
+    assert len(bsn) == 0 and ovl.shape == (0, 3)
+    outs = []
+    for tag, gen in (('with', genomes), ('without', {k: v for k, v in genomes.items() if k != 2000})):
+        d = os.path.join(tmp_path, tag); os.makedirs(d)
+        stores = _stores(hitio.FlatStore, d)
+        consumers.get_map_bsn(os.path.join(d, 'run'), clust, gen, ortho, old, stores[0], stores[1], stores[2], stores[3], True, params)
+        for s in stores:
+            s.close()
+        outs.append(_stores(hitio.FlatStore, d, 'r'))
+    assert outs[0][0].size() >= 15
+    for a, b in zip(*outs):
+        assert _store_equal(a, b)
