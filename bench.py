@@ -233,6 +233,18 @@ def cpu_sw_leg(npairs_sample, threads, seed_rank=0):
     return cells / dt / 1e9, dt, kind
 
 
+def cpu_scalar_leg(npairs_sample=10000):
+    """SURVEY 8(d) fallback (i): the scalar oracle on ONE core over the first pairs of the config-2 workload (score + end + start)"""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pb_oracle
+    from peppan_b200 import seqcodec, workloads
+    q, qoff, t, toff = workloads.sw_microbench_pairs(npairs_sample, seed=workloads.SEED)
+    t0 = time.perf_counter()
+    pb_oracle.sw_batch(q, qoff, t, toff, seqcodec.protein_matrix().reshape(-1), 11, 1, with_cigar=False, nthreads=1)
+    dt = time.perf_counter() - t0
+    return {'value': float(npairs_sample) * 300 * 300 / dt / 1e9, 'unit': UNIT, 'cores': 1, 'sample': '%d pairs, scalar C (-O3), %.1f s' % (npairs_sample, dt)}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -745,6 +757,7 @@ def main():
         v, dt, kind = cpu_sw_leg(args.cpu_pairs, threads)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': 'first %d pairs of the workload (score + end + start), %s, %d threads, %.1f s' % (args.cpu_pairs, kind, threads, dt),
+               'scalar_oracle_one_core': cpu_scalar_leg(),
                'reference_tools': reference_tools_leg(threads)}
     traffic, traffic_src = profiled_traffic()
     line = {
