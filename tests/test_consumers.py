@@ -410,3 +410,46 @@ def test_a_genome_without_hits_adds_nothing(oracle_as_search, tmp_path):
     assert outs[0][0].size() >= 15
     for a, b in zip(*outs):
         assert _store_equal(a, b)
+
+
+def test_real_sequences_through_both_iter_map_bsn(PEPPAN, oracle_as_search, monkeypatch, tmp_path):
+    """Real sequences (the committed slice of the bundled E. coli genomes: 164 CDS of GCF_000010485 against the syntenic 138 kb
+    of GCF_001566635) with the REAL annotation of that region as old predictions: the reference's iter_map_bsn and
+    consumers.iter_map_bsn write the same arrays -- real gene lengths, both strands, partial genes at the slice ends and the overlap
+    fractions with annotated genes (the two strains are close: the alignments of this slice carry mismatches but no gaps; gapped
+    hits are covered by the synthetic cases above)."""
+    import gzip
+    import json
+    import re
+    from peppan_b200 import ingest
+    monkeypatch.setattr(PEPPAN, 'uberBlast', ub.uberBlast)
+    if not hasattr(np.lib.npyio, 'format'):
+        monkeypatch.setattr(np.lib.npyio, 'format', np.lib.format, raising=False)
+    here = os.path.dirname(os.path.abspath(__file__))
+    fx = json.load(gzip.open(os.path.join(here, 'golden', 'real_slice.json.gz'), 'rt'))
+    contig, lo, hi = re.search(r'vs GCF_001566635 (\S+)\[(\d+):(\d+)\]', fx['source']).groups()
+    lo, hi = int(lo), int(hi)
+    clust = os.path.join(tmp_path, 'exemplar.fa')
+    with open(clust, 'w') as f:
+        for n, s in fx['queries']:
+            f.write('>%d\n%s\n' % (int(n) + 1, s))
+    _, cds = ingest.iter_readGFF((os.path.join(REF, 'examples', 'GCF_001566635.combined.gff.gz'), 'CDS', 11))
+    rows = sorted([[5000 + k, c[2] - lo, c[3] - lo, c[4]] for k, c in enumerate(cds.values()) if c[1] == contig and c[2] > lo and c[3] <= hi], key=lambda r: r[1])
+    assert len(rows) >= 100
+    old = os.path.join(tmp_path, 'old.npz')
+    store = PEPPAN.MapBsn(old, 'w')
+    store._save(store.conn, '1001', np.array(rows, dtype=object))
+    store.conn.close()
+    ortho = os.path.join(tmp_path, 'ortho.npy')
+    np.save(ortho, np.array([[i, i + 1, 9000 if i % 2 else -9000] for i in range(1, 120)], dtype=int), allow_pickle=True)
+    params = dict(gtable=11, noDiamond=False, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25, link_gap=600., link_diff=1.5,
+                  match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400.)
+    contigs = [(1001, fx['target'][0][1])]
+    a = PEPPAN.iter_map_bsn((os.path.join(tmp_path, 'ref'), clust, 0, 'taxon', contigs, ortho, old, params))
+    b = consumers.iter_map_bsn((os.path.join(tmp_path, 'ours'), clust, 0, 'taxon', contigs, ortho, old, params), store=PEPPAN.MapBsn)
+    ra, rb = np.load(a + '.bsn.npz', allow_pickle=True), np.load(b + '.bsn.npz', allow_pickle=True)
+    assert ra['bsn'].shape == rb['bsn'].shape and len(ra['bsn']) >= 120
+    assert _same(rb['bsn'], ra['bsn'])
+    assert ra['ovl'].shape == rb['ovl'].shape and np.array_equal(ra['ovl'], rb['ovl'])
+    col10 = [float(t[10]) for g in rb['bsn'] for t in g[6]]
+    assert sum(1 for v in col10 if v > 0.9) >= 80                                          # most hits sit on an annotated gene
