@@ -76,6 +76,43 @@ same = ra['bsn'].shape == rb['bsn'].shape and all(x[2] == y[2] and np.array_equa
 t_ub, _ = best(lambda: ub.uberBlast(('-r %s -q %s -f -m -O --blastn --diamond --min_id 0.4 --min_cov 50 --min_ratio 0.25 --merge_gap 600 --merge_diff 1.5 -t 1 -s 1 -e 0,3 --gtable 11' % (ref, qry)).split()), 2)
 out['N4_iter_map_bsn'] = {'input': '15,000 exemplars vs one synthetic genome (%d groups); both sides call this repository\'s uberBlast() with the search answered from a cache' % len(ra['bsn']),
                           'reference_s': t_ref, 'ours_s': t_our, 'of_which_uberBlast_s': t_ub, 'reference_loop_s': t_ref - t_ub, 'ours_loop_s': t_our - t_ub, 'equal': bool(same)}
+# ---- N4: get_similar_pairs (PEPPAN.py:194-294) on an exemplar-vs-exemplar search (2,000 exemplars with diverged copies; the search
+# is answered by the oracle once and cached) ----
+cache2 = '/tmp/ub_self_hits.pkl'
+rng = np.random.default_rng(78)
+gp = workloads.GenePool(1400, 0, seed=workloads.SEED + 43)
+allg = {i: g for i, g in enumerate(gp.genes)}
+allg.update({5000 + i: workloads._diverge(rng, gp.genes[i], 0.95) for i in range(0, 200)})
+allg.update({6000 + i: workloads._diverge(rng, gp.genes[i], 0.75) for i in range(200, 500)})
+allg.update({7000 + i: workloads._diverge(rng, gp.genes[i], 0.62) for i in range(500, 600)})
+self_fa = os.path.join(tmp, 'self_exemplars.fa')
+with open(self_fa, 'w') as f:
+    for n, g in allg.items(): f.write('>%d\n%s\n' % (n, workloads._NT[g].tobytes().decode()))
+if not os.path.exists(cache2):
+    qn, qb, qo = seqio.to_seqset(seqio.read_fastq(self_fa))
+    pickle.dump({mode: pb_oracle.search(qb, qo, qb, qo, mode, seqcodec.BLOSUM62.reshape(-1), min_id=0.45, min_cov=50, min_ratio=0.25) for mode in (1, 2)}, open(cache2, 'wb'))
+res_self = pickle.load(open(cache2, 'rb'))
+res_genome = res
+def fake_self(ctx, qb, qo, rb, ro, mode, *a, **k):
+    h, c = res_self[mode]
+    return h.copy(), c.copy(), dict(kernel_launches=0)
+ub._srch.search = fake_self
+P.pool = None
+pri = {n: [n % 3, n] for n in allg}
+def sim(fn, tag):
+    d = os.path.join(work, 'sim_' + tag); os.makedirs(d, exist_ok=True)
+    cl = os.path.join(d, 'x.clust.exemplar'); shutil.copy(self_fa, cl)
+    np.save(os.path.join(d, 'x.clust.npy'), np.zeros([0, 3], dtype=int))
+    prm = dict(clust=cl, incompleteCDS='', noDiamond=False, n_thread=2, gtable=11, match_identity=0.5, match_frag_len=50., match_frag_prop=0.25,
+               match_prop=0.5, match_len=250., match_prop1=0.8, match_len1=100., match_prop2=0.4, match_len2=400., clust_identity=0.9, clust_match_prop=0.8)
+    t0 = time.perf_counter(); r = fn(cl, pri, prm); return time.perf_counter() - t0, r
+import shutil
+t_ref, p_ref = sim(P.get_similar_pairs, 'ref')
+t_our, p_our = sim(consumers.get_similar_pairs, 'ours')
+t_ub2, _ = best(lambda: ub.uberBlast(('-r %s -q %s --blastn --diamond -s 1 --min_id 0.45 --min_cov 50.0 -t 2 --min_ratio 0.25 -e 3,3 -p --gtable 11' % (self_fa, self_fa)).split()), 2)
+out['N4_get_similar_pairs'] = {'input': '%d exemplars against themselves, %d hit rows; both sides call this repository\'s uberBlast() with the search answered from a cache' % (len(allg), len(res_self[1][0]) + len(res_self[2][0])),
+                               'reference_s': t_ref, 'ours_s': t_our, 'of_which_uberBlast_s': t_ub2, 'pairs': int(len(p_ref)), 'equal': bool(p_ref.shape == p_our.shape and np.array_equal(p_ref, p_our))}
+ub._srch.search = fake
 # ---- N2: the per-genome result through MapBsn / npz vs FlatStore ----
 bsn = ra['bsn']
 def save_ref():
