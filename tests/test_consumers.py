@@ -331,7 +331,7 @@ def test_batched_stage_equals_the_sequential_one(oracle, oracle_as_search, tmp_p
         for n, s in pool.fasta_items():
             f.write('>%s\n%s\n' % (n, s))
     genomes = {}
-    for g in range(5):
+    for g in range(3):
         seq, annot = workloads.synth_genome(pool, g, n_acc_per_genome=15, seed=workloads.SEED + 59)
         mid = annot[len(annot) // 2]
         cut = (int(mid[1]) + int(mid[2])) // 2
@@ -368,8 +368,8 @@ def test_batched_stage_equals_the_sequential_one(oracle, oracle_as_search, tmp_p
         for s in stores:
             s.close()
         outs[tag] = _stores(hitio.FlatStore, d, 'r')
-    assert calls.count((1, 2)) == 4 and calls.count((2, 1)) == 2                 # batches of 2, 2, 1 genomes, both modes, twice
-    assert outs['sequential'][0].size() >= 40
+    assert calls.count((1, 2)) == 2 and calls.count((2, 2)) == 2 and calls.count((1, 1)) == 2 and calls.count((2, 1)) == 2      # batches of 2 and 1 genomes, both modes, twice
+    assert outs['sequential'][0].size() >= 30
     for tag in ('inline', 'pool'):
         for a, b in zip(outs['sequential'], outs[tag]):
             assert _store_equal(a, b), tag
