@@ -352,6 +352,46 @@ int pb_allgather_i32(pb_ctx* ctx, const std::vector<int32_t>& mine, std::vector<
 }
 
 // ---- host-side hit-table bookkeeping ---------------------------------------------------------------------------
+#if defined(__SSE2__)
+#include <emmintrin.h>
+namespace {
+// nucEncoder classes (modules/uberBlast.py:270-271) of 16 residues at once: A C G T -> 1 2 3 4 (4 3 2 1 for the complement), 0 otherwise
+inline __m128i nuc_class16(__m128i v, int a, int c, int g, int t)
+{
+    const __m128i ka = _mm_and_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('A')), _mm_set1_epi8((char)a));
+    const __m128i kc = _mm_and_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('C')), _mm_set1_epi8((char)c));
+    const __m128i kg = _mm_and_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('G')), _mm_set1_epi8((char)g));
+    const __m128i kt = _mm_and_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('T')), _mm_set1_epi8((char)t));
+    return _mm_or_si128(_mm_or_si128(ka, kc), _mm_or_si128(kg, kt));
+}
+inline __m128i reverse16(__m128i v)
+{
+    v = _mm_shuffle_epi32(v, _MM_SHUFFLE(0, 1, 2, 3));
+    v = _mm_shufflelo_epi16(v, _MM_SHUFFLE(2, 3, 0, 1));
+    v = _mm_shufflehi_epi16(v, _MM_SHUFFLE(2, 3, 0, 1));
+    return _mm_or_si128(_mm_srli_epi16(v, 8), _mm_slli_epi16(v, 8));
+}
+}
+#endif
+
+// columns of a match run whose residues fall into the same class: q[0 .. len) against t[0 .. len) (plus strand), or against the
+// complement of t[0], t[-1], ... t[-(len-1)] (minus strand: t points at the LAST base of the run's slice)
+static int64_t matching_columns(const uint8_t* q, const uint8_t* t, int64_t len, bool minus, const uint8_t* enc)
+{
+    int64_t n = 0, x = 0;
+#if defined(__SSE2__)
+    for (; x + 16 <= len; x += 16) {
+        const __m128i a = nuc_class16(_mm_loadu_si128(reinterpret_cast<const __m128i*>(q + x)), 1, 2, 3, 4);
+        const __m128i b = minus ? nuc_class16(reverse16(_mm_loadu_si128(reinterpret_cast<const __m128i*>(t - x - 15))), 4, 3, 2, 1)
+                                : nuc_class16(_mm_loadu_si128(reinterpret_cast<const __m128i*>(t + x)), 1, 2, 3, 4);
+        n += __builtin_popcount((unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(a, b)));
+    }
+#endif
+    if (!minus) { for (; x < len; ++x) n += enc[q[x]] == enc[t[x]]; }
+    else { for (; x < len; ++x) n += enc[q[x]] == 4 - enc[t[-x]]; }
+    return n;
+}
+
 extern "C" int pb_rescore_m1(const pb_seqset* query, const pb_seqset* target, int64_t n_hits, const int32_t* q_id, const int32_t* s_id,
                              const int32_t* q_start, const int32_t* q_end, const int32_t* s_start, const int32_t* s_end,
                              const int64_t* cigar_off, const uint32_t* cigar, double* iden, double* score)
@@ -377,8 +417,7 @@ extern "C" int pb_rescore_m1(const pb_seqset* query, const pb_seqset* target, in
             const int64_t len = cigar[k] >> 2; const int op = cigar[k] & 3;
             if (op == 0) {
                 if (qi + len > qn || ri + len > tn) { pb_set_error(nullptr, "pb_rescore_m1: CIGAR of hit %lld runs past its alignment slice", (long long)h); return PB_ERR_ARG; }
-                if (!minus) { for (int64_t x = 0; x < len; ++x) nmatch += enc[q[qa + qi + x]] == enc[t[ta + ri + x]]; }
-                else { for (int64_t x = 0; x < len; ++x) nmatch += enc[q[qa + qi + x]] == 4 - enc[t[ta + tn - 1 - (ri + x)]]; }
+                nmatch += matching_columns(q + qa + qi, minus ? t + ta + tn - 1 - ri : t + ta + ri, len, minus, enc);
                 ncol += len; qi += len; ri += len;
             } else {
                 ++ngap; bgap += len; if (len > 3) mgap += len;
