@@ -22,6 +22,7 @@ _BASE = np.zeros(256, dtype=np.uint8)
 _BASE[[ord(c) for c in 'ACGT']] = (1, 2, 3, 4)                       # baseConv, PEPPAN.py:904-905
 _COMP = np.full(256, ord('N'), dtype=np.uint8)                      # rc(), modules/configure.py:152-154
 _COMP[[ord(c) for c in 'ACGT']] = [ord(c) for c in 'TGCA']
+_COMP[[ord(c) for c in 'acgt']] = [ord(c) for c in 'TGCA']           # rc() upper-cases before it complements
 
 
 def _excl_cumsum_within(values, first, counts):

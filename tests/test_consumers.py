@@ -147,7 +147,9 @@ def test_iter_map_bsn_writes_what_the_reference_writes(PEPPAN, oracle_as_search,
     seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=25, seed=workloads.SEED + 47)
     mid = annot[len(annot) // 3]
     cut = (int(mid[1]) + int(mid[2])) // 2
-    contigs = [(1001, seq[:cut]), (1002, seq[cut:])]
+    # the second contig in lower case: the search upper-cases what it reads, the scoring loop sees the raw string (plus-strand hits
+    # encode to zeros, minus-strand hits go through rc(), which upper-cases: modules/configure.py:153-154)
+    contigs = [(1001, seq[:cut]), (1002, seq[cut:].lower())]
     clust = os.path.join(tmp_path, 'exemplar.fa')
     with open(clust, 'w') as f:
         for n, s in pool.fasta_items():
