@@ -70,6 +70,15 @@ for case in range(int(sys.argv[1]), int(sys.argv[2])):
             g = annot[int(rng.integers(0, len(annot)))]; p = int(rng.integers(int(g[1]) + 60, int(g[2]) - 60))
             ins = ''.join('ACGT'[i] for i in rng.integers(0, 4, int(rng.integers(80, 500)))) if rng.random() < 0.6 else seq[int(g[1]):int(g[1]) + int(rng.integers(150, 400))]
             seq = seq[:p] + ins + seq[p:]
+        if os.environ.get('FU_REPEATS'):       # many hits of ONE query on one contig (an insertion-sequence-like repeat family): the branch of
+            g0 = pool.fasta_items()[0][1]      # _linearMerge that walks a Python set of row indices (modules/uberBlast.py:100-218)
+            for k in range(int(os.environ['FU_REPEATS'])):
+                a = int(rng.integers(0, len(g0) // 2)); b = int(rng.integers(a + 150, len(g0) + 1))
+                p = int(rng.integers(0, len(seq)))
+                piece = g0[a:b]
+                if rng.random() < 0.4:
+                    piece = piece.translate(str.maketrans('ACGT', 'TGCA'))[::-1]
+                seq = seq[:p] + piece + ''.join('ACGT'[i] for i in rng.integers(0, 4, int(rng.integers(20, 900)))) + seq[p:]
         cut = len(seq) // 2
         qitems = pool.fasta_items(); titems = [('7', seq[:cut]), ('8', seq[cut:])]
         qry = os.path.join(tmp, 'exemplar.fa'); ref = os.path.join(tmp, 'genome.fa')
