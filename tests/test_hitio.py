@@ -217,3 +217,67 @@ def test_typed_codec_stores_vectors_of_tables_and_arrays_concatenated():
     for i in range(9):
         ragged[i] = np.empty([1, 2 + i % 2], dtype=object); ragged[i][:] = 1
     assert hitio.encode_value(ragged)[0] == hitio._V_OBJ and _deep_equal(hitio.decode_value(hitio.encode_value(ragged)), ragged)
+
+
+def test_typed_codec_round_trips_random_nested_values():
+    """property test (hypothesis): whatever nesting of the carried types -- scalars of Python and numpy, strings, big integers,
+    lists / tuples, typed arrays, object vectors and object tables (below and above the column-wise threshold, with uniform and
+    mixed columns, nested tables of one width, typed arrays) -- comes back with the same shapes, cell types and values."""
+    hyp = pytest.importorskip('hypothesis')
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    scalars = st.one_of(st.none(), st.booleans(), st.integers(-(1 << 70), 1 << 70), st.floats(allow_nan=False), st.text(max_size=8),
+                        st.integers(-1000, 1000).map(np.int64), st.floats(allow_nan=False, width=32).map(np.float64),
+                        st.text(alphabet='ACGT', max_size=6).map(np.str_), st.booleans().map(np.bool_))
+    typed = st.one_of(st.lists(st.integers(0, 255), max_size=12).map(lambda v: np.array(v, dtype=np.uint8)),
+                      st.lists(st.integers(-5, 5), min_size=0, max_size=6).map(lambda v: np.array(v, dtype=np.int64).reshape(-1, 1)),
+                      st.lists(st.floats(allow_nan=False), max_size=5).map(lambda v: np.array(v, dtype=np.float64)),
+                      st.lists(st.text(alphabet='MID0123456789', max_size=5), min_size=1, max_size=4).map(lambda v: np.array(v)))
+
+    def obj_vector(items):
+        a = np.empty(len(items), dtype=object)
+        for i, v in enumerate(items):
+            a[i] = v
+        return a
+
+    def obj_table(rows_cols):
+        rows, cols, cells = rows_cols
+        a = np.empty([rows, cols], dtype=object)
+        for i in range(rows):
+            for j in range(cols):
+                a[i, j] = cells[(i * cols + j) % len(cells)] if cells else None
+        return a
+
+    leaf = st.one_of(scalars, typed)
+    value = st.recursive(leaf, lambda inner: st.one_of(
+        st.lists(inner, max_size=4), st.lists(inner, max_size=3).map(tuple), st.lists(inner, max_size=12).map(obj_vector),
+        st.tuples(st.integers(0, 12), st.integers(1, 4), st.lists(inner, max_size=7)).map(obj_table),
+        # a uniform column layout, as the pipeline's tables have: every row the same kinds
+        st.tuples(st.integers(8, 14), st.lists(st.sampled_from(['i', 'f', 's', 'a', 't']), min_size=1, max_size=5), st.integers(0, 1 << 30)).map(
+            lambda x: _uniform_table(*x))), max_leaves=12)
+
+    @settings(max_examples=int(os.environ.get("PB_CODEC_EXAMPLES", 150)), deadline=None, derandomize="PB_CODEC_EXAMPLES" not in os.environ, suppress_health_check=list(HealthCheck))
+    @given(value)
+    def check(v):
+        assert _deep_equal(hitio.decode_value(hitio.encode_value(v)), v)
+    check()
+
+
+def _uniform_table(rows, kinds, seed):
+    rng = np.random.default_rng(seed)
+    a = np.empty([rows, len(kinds)], dtype=object)
+    for i in range(rows):
+        for j, k in enumerate(kinds):
+            if k == 'i':
+                a[i, j] = int(rng.integers(-9, 9))
+            elif k == 'f':
+                a[i, j] = float(rng.random())
+            elif k == 's':
+                a[i, j] = '%dM' % int(rng.integers(1, 300))
+            elif k == 'a':
+                a[i, j] = rng.integers(0, 125, int(rng.integers(0, 9))).astype(np.uint8)
+            else:
+                t = np.empty([int(rng.integers(0, 3)), 3], dtype=object)
+                for r in range(t.shape[0]):
+                    t[r] = [int(rng.integers(0, 9)), float(rng.random()), 'x']
+                a[i, j] = t
+    return a
