@@ -245,3 +245,40 @@ def test_runblast_run_wiring_on_golden_scenarios(scen):
         _same([list(r) for r in tab], run['tab_out'], 'tab')
         if ovl is not None:
             _same(ovl.tolist(), run['overlap_out'], 'overlap')
+
+
+def test_rescore_m1_counts_matching_columns_like_nucencoder_on_any_bytes():
+    """pb_rescore_m1 compares 16 columns at a time where it can: single-run alignments of every length 1..70 at every offset
+    parity, both strands, over an alphabet with ambiguity codes, gaps and lower case, against the class rule of the reference
+    (nucEncoder, modules/uberBlast.py:270-271: A 0, C 1, G 3, T 4, anything else 2; minus strand: 4 - class of the reversed
+    subject)."""
+    from peppan_b200 import seqio
+    rng = np.random.default_rng(23)
+    alpha = np.frombuffer(b'ACGTACGTACGTNRYacgt-*', dtype=np.uint8)
+    enc = np.full(256, 2, dtype=np.int64); enc[[ord(c) for c in 'ACGT']] = (0, 1, 3, 4)
+    genes = {'g': alpha[rng.integers(0, len(alpha), 400)].tobytes().decode()}
+    contigs = {'c': alpha[rng.integers(0, len(alpha), 400)].tobytes().decode()}
+    # plant similarity: copy stretches of the gene (and of its reverse complement class-wise) into the contig
+    g = np.frombuffer(genes['g'].encode(), dtype=np.uint8); c = np.frombuffer(contigs['c'].encode(), dtype=np.uint8).copy()
+    c[50:150] = g[50:150]
+    comp = np.arange(256, dtype=np.uint8); comp[[ord(x) for x in 'ACGT']] = [ord(x) for x in 'TGCA']
+    c[200:300] = comp[g[100:200]][::-1]
+    contigs['c'] = c.tobytes().decode()
+    rows, want = [], []
+    for n in range(1, 71):
+        for minus in (False, True):
+            qa = int(rng.integers(0, 300)); ta = int(rng.integers(40, 300)) if not minus else int(rng.integers(190, 320))
+            if n % 2 == 0:                 # on the planted stretches: mostly matching columns
+                k = int(rng.integers(0, 100 - n + 1))
+                qa, ta = (50 + k, 50 + k) if not minus else (100 + k, 200 + 100 - k - n)
+            q = g[qa:qa + n]; t = c[ta:ta + n]
+            tt = t if not minus else t[::-1]
+            same = enc[q] == (enc[tt] if not minus else 4 - enc[tt])
+            nm = int(same.sum())
+            rows.append(['g', 'c', 0.0, n, 0, 0, qa + 1, qa + n, (ta + 1) if not minus else (ta + n), (ta + n) if not minus else (ta + 1), 0.0, 0, 400, 400, [[n, 'M']], len(rows)])
+            want.append((round(nm / float(n), 3), float(nm * 3 - (n - nm))))
+    got = pf.rescore_m1_table([list(r) for r in rows], seqio.to_seqset(genes), seqio.to_seqset(contigs), -1.0)
+    assert len(got) == len(rows)
+    for r, (iden, score) in zip(got, want):
+        assert abs(r[2] - iden) < 1e-12 and r[11] == score, (r[3], r[8] > r[9], r[2], iden, r[11], score)
+    assert sum(1 for w in want if w[0] > 0.9) >= 10 and sum(1 for w in want if w[0] < 0.5) >= 10
