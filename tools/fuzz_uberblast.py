@@ -66,7 +66,12 @@ for case in range(int(sys.argv[1]), int(sys.argv[2])):
         tmp = tempfile.mkdtemp(prefix='fu_')
         pool = workloads.GenePool(40, 40, seed=workloads.SEED + 400 + case % 2)
         seq, annot = workloads.synth_genome(pool, 0, n_acc_per_genome=20, seed=workloads.SEED + 400 + case % 2)
-        for k in range(6):                  # long insertions / duplications inside genes: split hits, overlaps
+        real = None
+        if os.environ.get('FU_REAL'):          # the committed slice of the bundled E. coli genomes instead: 164 real CDS vs 138 kb
+            import gzip
+            real = json.load(gzip.open(os.path.join(ROOT, 'tests', 'golden', 'real_slice.json.gz'), 'rt'))
+            seq = real['target'][0][1]; annot = []
+        for k in range(6 if real is None else 0):   # long insertions / duplications inside genes: split hits, overlaps
             g = annot[int(rng.integers(0, len(annot)))]; p = int(rng.integers(int(g[1]) + 60, int(g[2]) - 60))
             ins = ''.join('ACGT'[i] for i in rng.integers(0, 4, int(rng.integers(80, 500)))) if rng.random() < 0.6 else seq[int(g[1]):int(g[1]) + int(rng.integers(150, 400))]
             seq = seq[:p] + ins + seq[p:]
@@ -80,7 +85,8 @@ for case in range(int(sys.argv[1]), int(sys.argv[2])):
                     piece = piece.translate(str.maketrans('ACGT', 'TGCA'))[::-1]
                 seq = seq[:p] + piece + ''.join('ACGT'[i] for i in rng.integers(0, 4, int(rng.integers(20, 900)))) + seq[p:]
         cut = len(seq) // 2
-        qitems = pool.fasta_items(); titems = [('7', seq[:cut]), ('8', seq[cut:])]
+        qitems = pool.fasta_items() if real is None else [(str(int(n) + 1), x) for n, x in real['queries']]
+        titems = [('7', seq[:cut]), ('8', seq[cut:])]
         qry = os.path.join(tmp, 'exemplar.fa'); ref = os.path.join(tmp, 'genome.fa')
         open(qry, 'w').write(''.join('>%s\n%s\n' % x for x in qitems)); open(ref, 'w').write(''.join('>%s\n%s\n' % x for x in titems))
         qn, qb, qo = seqio.to_seqset(qitems); tn, tb, to = seqio.to_seqset(titems)
