@@ -61,7 +61,26 @@ for case in range(int(sys.argv[1]), int(sys.argv[2])):
     rng = np.random.default_rng(7000 + case)
     gtable = int(rng.choice([11, 11, 4]))
     min_id, min_cov, min_ratio = float(rng.choice([0.3, 0.4, 0.6])), int(rng.choice([40, 50, 100])), float(rng.choice([0.05, 0.25]))
-    gkey = (case % 2, gtable, min_id, min_cov, min_ratio)
+    whole = os.environ.get('FU_WHOLE')         # 'g765' / 'g635': 1,000 real CDS against a WHOLE bundled genome, hit tables from the committed
+    if whole:                                  # oracle fixture (tests/golden/real_genomes.npz, searched at 0.4 / 50 / 0.25, table 11)
+        gtable, min_id, min_cov, min_ratio = 11, 0.4, 50, 0.25
+    gkey = (case % 2, gtable, min_id, min_cov, min_ratio) if not whole else whole
+    if gkey not in prepared and whole:
+        tmp = tempfile.mkdtemp(prefix='fu_')
+        with np.load(os.path.join(ROOT, 'tests', 'golden', 'real_genomes.npz')) as z:
+            fx = {k: z[k] for k in z.files}
+        cut = lambda b, o: [b[o[i]:o[i + 1]].tobytes().decode() for i in range(len(o) - 1)]
+        qitems = [(str(i + 1), x) for i, x in enumerate(cut(fx['q_bytes'], fx['q_off']))]
+        titems = [(str(7001 + i), x) for i, x in enumerate(cut(fx[whole + '_bytes'], fx[whole + '_off']))]
+        qry = os.path.join(tmp, 'exemplar.fa'); ref = os.path.join(tmp, 'genome.fa')
+        open(qry, 'w').write(''.join('>%s\n%s\n' % x for x in qitems)); open(ref, 'w').write(''.join('>%s\n%s\n' % x for x in titems))
+        qn, tn = [n for n, _ in qitems], [n for n, _ in titems]
+        hits, cigar = fx[whole + '_m1_hits'], fx[whole + '_m1_cigar']; phits, pcigar = fx[whole + '_m2_hits'], fx[whole + '_m2_cigar']
+        tsv = os.path.join(tmp, 'prepared.tsv'); open(tsv, 'w').write('\n'.join(H._blastn_tsv_lines(hits, cigar, qn, tn, dict(qitems), dict(titems))) + '\n')
+        js = os.path.join(tmp, 'prepared.json'); json.dump(H._diamond_sam_records(phits, pcigar, qn, tn), open(js, 'w'))
+        for name, body in (('blastn', H._FAKE_BLASTN.format(py=sys.executable, tsv=tsv)), ('diamond', _FAKE_DIAMOND.format(py=sys.executable, js=js)), ('makeblastdb', '#!/bin/sh\nexit 0\n')):
+            p = os.path.join(tmp, name); open(p, 'w').write(body); os.chmod(p, os.stat(p).st_mode | stat.S_IEXEC)
+        prepared[gkey] = (tmp, ref, qry, (hits, cigar), (phits, pcigar), js)
     if gkey not in prepared:
         tmp = tempfile.mkdtemp(prefix='fu_')
         pool = workloads.GenePool(40, 40, seed=workloads.SEED + 400 + case % 2)
