@@ -34,6 +34,10 @@ for case in range(int(sys.argv[1]), int(sys.argv[2])):
             if rng.random() < 0.25:
                 g = g[:int(g.size * rng.uniform(0.4, 0.95))]
             items.append(workloads._NT[g].tobytes().decode())
+    if os.environ.get('FG_REAL'):              # real genes instead: the first FG_REAL valid CDS of GCF_000010485 (committed fixture)
+        with np.load(os.path.join(ROOT, 'tests', 'golden', 'real_genomes.npz')) as z:
+            qb, qo = z['q_bytes'], z['q_off']
+        items = [qb[qo[i]:qo[i + 1]].tobytes().decode() for i in range(int(os.environ['FG_REAL']))]
     items.sort(key=lambda s: -len(s))
     fa = os.path.join(tmp, 'genes.fa')
     with open(fa, 'w') as f:
