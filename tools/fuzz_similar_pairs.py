@@ -25,6 +25,13 @@ for case in range(int(sys.argv[1]), int(sys.argv[2])):
             if r2 < 0.2: g = (3 - g[::-1]).astype(g.dtype)                                   # reverse complement
             elif r2 < 0.35: g = np.concatenate([rng.integers(0, 4, int(rng.integers(1, 3))).astype(g.dtype), g])     # out of frame
             allg[100 * (c + 1) + i] = g
+    if os.environ.get('FS_REAL'):              # real genes instead: the first FS_REAL valid CDS of GCF_000010485 (committed fixture), a tenth of
+        with np.load(os.path.join(ROOT, 'tests', 'golden', 'real_genomes.npz')) as z:      # them also as a diverged copy
+            qb, qo = z['q_bytes'], z['q_off']
+        code = np.full(256, 0, dtype=np.int8); code[[ord(c) for c in 'ACGT']] = (0, 1, 2, 3)
+        allg = {i + 1: code[qb[qo[i]:qo[i + 1]]] for i in range(int(os.environ['FS_REAL']))}
+        for i in list(allg)[::10]:
+            allg[5000 + i] = workloads._diverge(rng, allg[i], float(rng.choice([0.97, 0.9, 0.8, 0.7])))
     outs = []
     for tag in ('ref', 'ours'):
         d = tempfile.mkdtemp(prefix='fs%d_%s_' % (case, tag))
