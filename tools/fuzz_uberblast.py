@@ -2,8 +2,8 @@
 runBlast / runDiamond -> poolBlast / parseDiamond -> reScore -> ovlFilter -> linearMerge -> fixEnd -> returnOverlap) run with
 its external tools replaced by stand-ins that answer with OUR hits in the tools' own formats (the harness of
 tests/test_reference_consumer_cpu.py): random flag sets -- rescoring modes 0-3, filter / merge / overlap switches with random
-parameters, end fixing, thresholds, one or both searches, genetic table 11 / 4.  Final tables and overlap lists must be equal
-(hit ids aside: they number the rows in tool-output order).  Protein hits that span two of the reference's >= 1000-aa target
+parameters, end fixing, thresholds, one or both searches, genetic table 11 / 4.  Final tables and overlap lists must be equal in value and in the
+Python type of every cell (hit ids aside: they number the rows in tool-output order).  Protein hits that span two of the reference's >= 1000-aa target
 chunks cannot be written in its SAM; they are counted and left out on both sides (uberBlast(tables=...)).  Needs /root/reference.
     python tools/fuzz_uberblast.py 0 24 >> profiles/r02_consumer_fuzz.txt"""
 import json, os, stat, sys, tempfile, warnings
@@ -53,6 +53,15 @@ def canon(tab, ovl, merged):
             row += ((round(float(g[0]), 6), round(float(g[1]), 6), int(g[2]), tuple(key[int(i)] for i in g[3:])) if len(g) else (),)
         rows.append(row)
     return sorted(rows, key=repr), (sorted((key[int(a)], key[int(b)], int(c)) for a, b, c in ovl) if ovl is not None else None)
+
+
+def cell_types(tab):
+    from collections import Counter
+    c = Counter()
+    for r in tab:
+        for j, x in enumerate(r):
+            c[(j, 'list of ' + ','.join(sorted(set(type(y).__name__ for y in x))) if isinstance(x, list) else type(x).__name__)] += 1
+    return c
 
 
 bad = 0
@@ -142,7 +151,7 @@ for case in range(int(sys.argv[1]), int(sys.argv[2])):
     rtab, rovl = r if ovl_on else (r, None)
     otab, oovl = o if ovl_on else (o, None)
     a, b = canon(rtab, rovl, merged), canon(otab, oovl, merged)
-    ok = a == b
+    ok = a == b and cell_types(rtab) == cell_types(otab) and (rovl is None or rovl.dtype == oovl.dtype)       # values AND Python types of the cells
     print('case', case, 'rows', len(rtab), 'overlaps', (len(rovl) if rovl is not None else '-'), 'protein hits across chunk borders', dropped, 'ok' if ok else 'DIFF', ' '.join(args[4:]), flush=True)
     bad += not ok
 print('bad', bad)
