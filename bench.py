@@ -638,6 +638,33 @@ def stage_leg(ctx, genomes, pool, n=2, nb=32, batch=16, grouped_search=None):
         return {'error': '%s: %s' % (type(e).__name__, e)}
 
 
+def stage_main(device):
+    """child process of the bench: its own genomes, its own context on `device`, the stage leg, one JSON line"""
+    from peppan_b200 import workloads
+    from peppan_b200._lib import Context
+    made = workloads.synth_genomes_parallel(list(range(33)), N_CORE, N_ACC, procs=max(1, min(16, (os.cpu_count() or 1) // 2)))
+    pool = workloads.GenePool(N_CORE, N_ACC)
+    ctx = Context(device)
+    res = stage_leg(ctx, made, pool)
+    ctx.close()
+    print('STAGE ' + json.dumps(res), flush=True)
+    return 0
+
+
+def stage_leg_isolated(device):
+    """the stage leg in a child process (python bench.py --stage-only DEVICE): an error, a crash or a time-out there is reported in
+    the line and never takes the measurements of this process with it"""
+    try:
+        env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'TORCHELASTIC_RUN_ID')}
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--stage-only', str(device)], capture_output=True, text=True, timeout=600, env=env)
+        for line in reversed(out.stdout.splitlines()):
+            if line.startswith('STAGE '):
+                return json.loads(line[6:])
+        return {'error': 'child exited with %d: %s' % (out.returncode, (out.stderr or out.stdout)[-400:])}
+    except Exception as e:                                  # noqa: BLE001
+        return {'error': '%s: %s' % (type(e).__name__, e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -654,9 +681,13 @@ def main():
     ap.add_argument('--batch', type=int, default=16, help='genomes per pb_search_grouped call')
     ap.add_argument('--workers', type=int, default=0, help='worker contexts (+ host threads) per search mode and GPU in the config-4 leg (0: 1-3 by host cores per rank)')
     ap.add_argument('--no-search', action='store_true', help='skip the genome-scale legs')
+    ap.add_argument('--stage-only', type=int, default=-1, metavar='DEVICE', help='internal: run only the stage leg on this device and print its JSON (the bench runs it in a '
+                    'child process, so that nothing it does can take the main line down)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.stage_only >= 0:
+        return stage_main(args.stage_only)
     if args.config == 3:
         args.c3_genomes = max(args.c3_genomes, 100)
 
@@ -742,7 +773,7 @@ def main():
             c3 = config3_leg(ctx, rank, world, pg, c3_genomes, qpin, qo, args.batch)
         if rank == 0 and (genomes or c3_genomes):
             ubl = uberblast_leg(ctx, genomes or c3_genomes, pool)
-            stg = stage_leg(ctx, genomes or c3_genomes, pool)
+            stg = stage_leg_isolated(ctx.device)
 
     barrier(pg)
     if rank != 0:
