@@ -772,7 +772,10 @@ def main():
         if args.config != 4:
             c3 = config3_leg(ctx, rank, world, pg, c3_genomes, qpin, qo, args.batch)
         if rank == 0 and (genomes or c3_genomes):
-            ubl = uberblast_leg(ctx, genomes or c3_genomes, pool)
+            try:
+                ubl = uberblast_leg(ctx, genomes or c3_genomes, pool)
+            except Exception as e:                          # noqa: BLE001 -- an extra of the line, never its failure
+                ubl = {'error': '%s: %s' % (type(e).__name__, e)}
             stg = stage_leg_isolated(ctx.device)
 
     barrier(pg)
